@@ -1,0 +1,203 @@
+"""numpy executor for a lowered model blob (oracle; test infrastructure only).
+
+Runs the SAME blob the CUDA kernel consumes, with plain numpy arrays as the register file and
+LAPACK (partial pivoting) for the Newton step, so that (a) the host-side lowering can be tested
+on a CPU-only box against the hand-written restatement in ``oracle/kinetics.py`` and (b) any
+model the DSL can express has a CPU oracle for the GPU parity tests.
+
+Algorithm restated: per finite element solve  sum_k adot[k][j] x_k = h f(x_j)  (j = 1..3) by full
+Newton from x_j = x_0; quadrature states advance by  h * sum_j bw_j fq(x_j);  afterwards evaluate
+the CQAs g_k, the relaxed big-M indicator y = max(0, max_k g_k/M_k) (reference pyds/utils.py:23-29,
+SURVEY.md A.4) and snap it as pyds/solver.py:71-80 does.
+"""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+_OPS = ["MOV", "NEG", "ADD", "SUB", "MUL", "DIV", "FMA", "FMS", "FNMA", "SQR", "RCP", "EXP", "LOG",
+        "SQRT", "SIN", "COS", "TANH", "POW", "ABS", "MIN", "MAX"]
+_REF_CONST, _REF_WIDE, _REF_MASK, _REF_NONE = 1 << 13, 1 << 12, 0xFFF, 0x3FFF
+_DT = {0: np.uint32, 1: np.float64, 2: np.uint64, 3: np.uint16}
+
+
+def parse_blob(blob: bytes):
+    magic, ver, nsec, _ = struct.unpack_from("<IIII", blob, 0)
+    assert magic == 0x42534450 and ver == 1
+    off, out = 16, {}
+    for _ in range(nsec):
+        tag, dt, cnt, _ = struct.unpack_from("<4sIII", blob, off)
+        off += 16
+        nbytes = cnt * np.dtype(_DT[dt]).itemsize
+        out[tag.decode()] = np.frombuffer(blob, dtype=_DT[dt], count=cnt, offset=off).copy()
+        off += nbytes + ((-nbytes) % 8)
+    return out
+
+
+class TapeVM:
+    def __init__(self, blob: bytes):
+        s = parse_blob(blob)
+        self.sec = s
+        (self.ns, self.nq, self.ng, self.d_dim, self.p_dim, self.nz, self.nfe, self.ncp, self.nce, self.n_units,
+         self.param_slot, self.ctrl_slot, self.xe_slot, self.qe_slot, self.x_slot, self.max_it) = [int(v) for v in s["HEAD"]]
+        self.rtol = float(s["DBLS"][0])
+        self.consts = s["CNST"]
+        self.adot = s["ADOT"].reshape(self.ncp + 1, self.ncp + 1)
+        self.bw = s["BWTS"]
+        self.big_m = s["BIGM"]
+        self.cmap = s["CMAP"].reshape(self.nfe, -1)
+
+    # register file: R[slot] is an array (S,) ; wide slots are three consecutive entries ---------
+    def _ld(self, R, ref, w):
+        ref = int(ref)
+        if ref == _REF_NONE:
+            return 0.0
+        if ref & _REF_CONST:
+            return self.consts[ref & _REF_MASK]
+        idx = ref & _REF_MASK
+        return R[idx + (w if ref & _REF_WIDE else 0)]
+
+    def _run(self, R, code, width):
+        for word in code:
+            word = int(word)
+            op = _OPS[word & 0xFF]
+            dst, a, b, c = (word >> 8) & 0x3FFF, (word >> 22) & 0x3FFF, (word >> 36) & 0x3FFF, (word >> 50) & 0x3FFF
+            for w in range(width):
+                A = self._ld(R, a, w)
+                if op == "MOV": v = A
+                elif op == "NEG": v = -A
+                elif op == "ADD": v = A + self._ld(R, b, w)
+                elif op == "SUB": v = A - self._ld(R, b, w)
+                elif op == "MUL": v = A * self._ld(R, b, w)
+                elif op == "DIV": v = A / self._ld(R, b, w)
+                elif op == "FMA": v = A * self._ld(R, b, w) + self._ld(R, c, w)
+                elif op == "FMS": v = A * self._ld(R, b, w) - self._ld(R, c, w)
+                elif op == "FNMA": v = self._ld(R, c, w) - A * self._ld(R, b, w)
+                elif op == "SQR": v = A * A
+                elif op == "RCP": v = 1.0 / A
+                elif op == "EXP": v = np.exp(A)
+                elif op == "LOG": v = np.log(A)
+                elif op == "SQRT": v = np.sqrt(A)
+                elif op == "SIN": v = np.sin(A)
+                elif op == "COS": v = np.cos(A)
+                elif op == "TANH": v = np.tanh(A)
+                elif op == "POW": v = np.power(A, self._ld(R, b, w))
+                elif op == "ABS": v = np.abs(A)
+                elif op == "MIN": v = np.minimum(A, self._ld(R, b, w))
+                elif op == "MAX": v = np.maximum(A, self._ld(R, b, w))
+                else: raise ValueError(op)
+                idx = dst & _REF_MASK
+                R[idx + (w if dst & _REF_WIDE else 0)] = np.broadcast_to(v, R[0].shape).copy()
+
+    def evaluate(self, d, p, z=None, tol=None, max_it=None, return_traj=False):
+        """g over the (n_d, n_p) grid.  ``z``: None (model defaults), (nz,), (n_d, nz) or (n_d, n_p, nz).
+        Returns dict(g=(n_d,n_p,ng), y, feasible, iters=(n_d,n_p) total Newton iterations, status)."""
+        d = np.atleast_2d(np.asarray(d, dtype=np.float64))
+        p = np.atleast_2d(np.asarray(p, dtype=np.float64))
+        n_d, n_p = d.shape[0], p.shape[0]
+        S = n_d * n_p
+        tol = self.rtol if tol is None else tol
+        max_it = self.max_it if max_it is None else max_it
+        R = [np.zeros(S) for _ in range(self.n_units)]
+        for i in range(self.d_dim):
+            R[self.param_slot + i] = np.repeat(d[:, i], n_p)
+        for i in range(self.p_dim):
+            R[self.param_slot + self.d_dim + i] = np.tile(p[:, i], n_d)
+        s = self.sec
+        self._run(R, s["TPRO"], 1)
+        one = np.ones(S)
+        if z is None:
+            Z = [self._ld(R, r, 0) * one for r in s["RZ__"][:self.nz]]
+        else:
+            z = np.asarray(z, dtype=np.float64)
+            if z.ndim == 1: z = np.broadcast_to(z, (n_d, n_p, self.nz))
+            elif z.ndim == 2: z = np.broadcast_to(z[:, None, :], (n_d, n_p, self.nz))
+            z = z.reshape(S, self.nz)
+            # fixed (parameter-defined) controls always come from the tape
+            Z = [(self._ld(R, s["RZ__"][k], 0) * one) if s["ZFIX"][k] else z[:, k].copy() for k in range(self.nz)]
+        ns, nq, ncp = self.ns, self.nq, self.ncp
+        x0 = np.stack([self._ld(R, r, 0) * one for r in s["RX0_"][:ns]], axis=1)
+        q = np.stack([self._ld(R, r, 0) * one for r in s["RQ0_"][:nq]], axis=1) if nq else np.zeros((S, 0))
+        h = 1.0 / self.nfe
+        A = self.adot
+        iters = np.zeros(S, dtype=np.int64)
+        failed = np.zeros(S, dtype=bool)
+        traj = np.zeros((S, self.nfe * ncp + 1, ns))
+        traj[:, 0] = x0
+        n = ns * ncp
+        for e in range(self.nfe):
+            for k in range(self.nce):
+                R[self.ctrl_slot + k] = Z[int(self.cmap[e, k])]
+            self._run(R, s["TELM"], 1)
+            X = np.repeat(x0[:, None, :], ncp, axis=1)            # (S, pt, state)
+            active = ~failed
+            for it in range(max_it):
+                if not active.any():
+                    break
+                for i in range(ns):
+                    for w in range(ncp):
+                        R[self.x_slot + 3 * i + w] = X[:, w, i]
+                self._run(R, s["TPNT"], ncp)
+                f = np.stack([np.stack([self._ld(R, r, w) * one for r in s["RF__"][:ns]], axis=1) for w in range(ncp)], axis=1)
+                J = np.zeros((S, ncp, ns, ns))
+                for w in range(ncp):
+                    for r_ in range(ns):
+                        for c_ in range(ns):
+                            J[:, w, r_, c_] = self._ld(R, s["RJ__"][r_ * ns + c_], w)
+                lin = np.einsum("kj,skn->sjn", A[1:, 1:], X) + A[0, 1:][None, :, None] * x0[:, None, :]
+                Rres = lin - h * f
+                M = np.zeros((S, ncp, ns, ncp, ns))
+                eye = np.eye(ns)
+                for j in range(ncp):
+                    for k in range(ncp):
+                        M[:, j, :, k, :] += A[k + 1, j + 1] * eye
+                    M[:, j, :, j, :] -= h * J[:, j]
+                idx = np.nonzero(active)[0]
+                with np.errstate(all="ignore"):
+                    try:
+                        dX = np.linalg.solve(M.reshape(S, n, n)[idx], -Rres.reshape(S, n, 1)[idx]).reshape(-1, ncp, ns)
+                    except np.linalg.LinAlgError:
+                        dX = np.full((idx.size, ncp, ns), np.nan)
+                X[idx] += dX
+                iters[idx] += 1
+                scale = np.maximum(np.abs(X[idx]).max(axis=(1, 2)), 1.0)
+                dmax = np.abs(dX).max(axis=(1, 2))
+                bad = ~np.isfinite(dmax)
+                failed[idx[bad]] = True
+                done = (dmax <= tol * scale) | bad
+                active[idx[done]] = False
+            failed |= active                                         # iteration cap reached
+            # quadratures use the converged point values
+            for i in range(ns):
+                for w in range(ncp):
+                    R[self.x_slot + 3 * i + w] = X[:, w, i]
+            self._run(R, s["TPNT"], ncp)
+            for k in range(nq):
+                acc = 0.0
+                for w in range(ncp):
+                    acc = acc + self.bw[w] * self._ld(R, s["RFQ_"][k], w)
+                q[:, k] = q[:, k] + h * acc
+            traj[:, e * ncp + 1:(e + 1) * ncp + 1] = X
+            x0 = X[:, ncp - 1, :].copy()
+        for i in range(ns):
+            R[self.xe_slot + i] = x0[:, i]
+        for k in range(nq):
+            R[self.qe_slot + k] = q[:, k]
+        self._run(R, s["TGEE"], 1)
+        g = np.stack([self._ld(R, r, 0) * one for r in s["RG__"][:self.ng]], axis=1)
+        g[failed] = np.nan
+        with np.errstate(invalid="ignore"):
+            y = np.maximum(0.0, np.max(g / self.big_m[None, :], axis=1))
+        y[failed] = 1.0
+        feas = (y == 0.0)
+        out = dict(g=g.reshape(n_d, n_p, self.ng), y=y.reshape(n_d, n_p), feasible=feas.reshape(n_d, n_p),
+                   iters=iters.reshape(n_d, n_p), status=failed.reshape(n_d, n_p).astype(np.int32),
+                   x_end=x0.reshape(n_d, n_p, ns), q_end=q.reshape(n_d, n_p, nq))
+        if return_traj:
+            out["traj"] = traj.reshape(n_d, n_p, -1, ns)
+        return out
+
+    def prob_feasible(self, d, p, w, z=None, **kw):
+        r = self.evaluate(d, p, z, **kw)
+        return (r["feasible"] * np.asarray(w, dtype=np.float64)[None, :]).sum(axis=1)

@@ -1,0 +1,298 @@
+"""Process-model description and its lowering to the binary tape blob the C-ABI consumes.
+
+This is the Pyomo-free core behind ``pyds_b200.simulator.Simulator``: it describes exactly
+the model class the reference's stage rules build (reference ``run_twostage.py:12-79``):
+
+* mutable parameters bound through the ``input map`` (design variables ``d`` and uncertain
+  parameters ``theta``)                                          -- ``run_twostage.py:14-15, 38-41, 85``
+* differential states with fixed initial values                  -- ``:17-21, 44-45, 72-74``
+* piecewise-constant controls, one value per finite element      -- ``:19, 79``
+* ODE right-hand sides                                           -- ``:22-23, 49-58``
+* critical quality attributes ``g_k <= 0`` in big-M form         -- ``:60-71``, ``pyds/utils.py:7-44``
+* Radau collocation ``nfe`` x 3                                  -- ``:76-79``
+
+``DaeModel.lower()`` partitions the expression graph by dependency level, differentiates the
+right-hand sides symbolically and serialises everything (tapes, reference tables, collocation
+constants) into one blob; see ``include/pydsb.h`` (``pydsb_model_create``) for the layout.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import tape as T
+from .collocation import radau_tables
+
+BLOB_MAGIC = 0x42534450  # 'PDSB'
+BLOB_VERSION = 1
+
+_DT = {"u32": 0, "f64": 1, "u64": 2, "u16": 3}
+_NP = {"u32": np.uint32, "f64": np.float64, "u64": np.uint64, "u16": np.uint16}
+
+
+@dataclass
+class _State:
+    name: str
+    x0: object
+    rhs: object = None
+
+
+@dataclass
+class _Control:
+    name: str
+    lo: float
+    hi: float
+    init: object          # float, list of floats (per piece) or Expr of parameters
+    pieces: int           # number of z entries (nfe, or 1 for a constant-in-time control)
+    z0: int = 0           # first index in the z vector
+    fixed: bool = False   # fixed controls are parameter expressions, never optimised
+
+
+class DaeModel:
+    def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-10, newton_max_it=25):
+        self.graph = T.Graph()
+        self.d_names = list(d_names)
+        self.p_names = list(p_names)
+        self.nfe, self.ncp = int(nfe), int(ncp)
+        self.newton_rtol = float(newton_rtol)
+        self.newton_max_it = int(newton_max_it)
+        self.states: list[_State] = []
+        self.controls: list[_Control] = []
+        self.constraints = []          # (name, Expr (<= 0 feasible), bigM)
+        g = self.graph
+        self.d = {n: g.param(i) for i, n in enumerate(self.d_names)}
+        self.p = {n: g.param(len(self.d_names) + i) for i, n in enumerate(self.p_names)}
+        self._end_leaf = {}
+
+    # -- declaration ------------------------------------------------------------------------------
+    @property
+    def n_param(self):
+        return len(self.d_names) + len(self.p_names)
+
+    def param(self, name):
+        return self.d[name] if name in self.d else self.p[name]
+
+    def state(self, name, x0=0.0):
+        i = len(self.states)
+        self.states.append(_State(name, x0))
+        return self.graph._mk("x", (), i)            # provisional index = declaration order
+
+    def control(self, name, lo, hi, init=0.0, per_element=True):
+        k = len(self.controls)
+        self.controls.append(_Control(name, float(lo), float(hi), init, self.nfe if per_element else 1))
+        return self.graph.ctrl(k)
+
+    def fixed_control(self, name, value):
+        """A control profile that is a function of the parameters only (no recourse)."""
+        k = len(self.controls)
+        self.controls.append(_Control(name, -np.inf, np.inf, value, 1, fixed=True))
+        return self.graph.ctrl(k)
+
+    def ode(self, state, rhs):
+        assert state.op == "x"
+        self.states[state.value].rhs = self.graph.wrap(rhs)
+
+    def end(self, state):
+        """Value of a state at the final time (tau = 1)."""
+        assert state.op == "x"
+        return self.graph._mk("xe", (), 1000 + state.value)     # provisional, remapped in lower()
+
+    def initial(self, state):
+        assert state.op == "x"
+        return self.graph.wrap(self.states[state.value].x0)
+
+    def constraint(self, name, expr_le0, big_m):
+        self.constraints.append((name, self.graph.wrap(expr_le0), float(big_m)))
+
+    # -- lowering -----------------------------------------------------------------------------------
+    def _rebuild(self, e, leaf_map, memo):
+        """Re-create ``e`` with leaves substituted (runs the simplifier again)."""
+        g = self.graph
+        for n in T.topo_order([e]):
+            if n.id in memo:
+                continue
+            if not n.args:
+                memo[n.id] = leaf_map.get((n.op, n.value), n)
+                continue
+            a = [memo[c.id] for c in n.args]
+            op = n.op
+            if op == "add": r = g.add(*a)
+            elif op == "sub": r = g.sub(*a)
+            elif op == "mul": r = g.mul(*a)
+            elif op == "div": r = g.div(*a)
+            elif op == "neg": r = g.neg(*a)
+            elif op == "sqr": r = g.mul(a[0], a[0])
+            elif op == "rcp": r = g.div(1.0, a[0])
+            elif op == "pow": r = g.pow(*a)
+            elif op == "min": r = g.minimum(*a)
+            elif op == "max": r = g.maximum(*a)
+            else: r = getattr(g, op)(*a)
+            memo[n.id] = r
+        return memo[e.id]
+
+    def lower(self):
+        g = self.graph
+        n_states = len(self.states)
+        for s in self.states:
+            if s.rhs is None:
+                raise ValueError(f"state '{s.name}' has no ODE")
+        # quadrature states: appear in no right-hand side (their end value is a weighted sum)
+        used = set()
+        for s in self.states:
+            for n in T.topo_order([s.rhs]):
+                if n.op == "x":
+                    used.add(n.value)
+        dyn = [i for i in range(n_states) if i in used]
+        quad = [i for i in range(n_states) if i not in used]
+        ns, nq = len(dyn), len(quad)
+        if ns == 0:
+            raise ValueError("model has no dynamic state")
+        leaf_map = {}
+        for new, old in enumerate(dyn):
+            leaf_map[("x", old)] = g.x(new) if new != old else g._mk("x", (), new)
+            leaf_map[("xe", 1000 + old)] = g.xe(new)
+        for new, old in enumerate(quad):
+            leaf_map[("xe", 1000 + old)] = g.qe(new)
+        memo = {}
+        rb = lambda e: self._rebuild(g.wrap(e), leaf_map, memo)
+
+        f = [rb(self.states[i].rhs) for i in dyn]
+        fq = [rb(self.states[i].rhs) for i in quad]
+        x0 = [rb(self.states[i].x0) for i in dyn]
+        q0 = [rb(self.states[i].x0) for i in quad]
+        for e in x0 + q0:
+            if e.level > T.LEVEL_PARAM:
+                raise ValueError("initial values may depend on parameters only")
+        J = [g.diff(f[r], g.x(c)) for r in range(ns) for c in range(ns)]
+        gk = [rb(e) for _, e, _ in self.constraints]
+        ng = len(gk)
+        if ng == 0:
+            raise ValueError("model has no constraint")
+
+        # controls -> z vector
+        nce = len(self.controls)
+        z_exprs, z_lo, z_hi, z_fixed = [], [], [], []
+        cmap = np.zeros((self.nfe, max(nce, 1)), dtype=np.uint16)
+        for k, c in enumerate(self.controls):
+            c.z0 = len(z_exprs)
+            for piece in range(c.pieces):
+                if isinstance(c.init, (list, tuple, np.ndarray)):
+                    v = c.init[piece if c.pieces > 1 else 0]
+                else:
+                    v = c.init
+                v = rb(v)
+                if v.level > T.LEVEL_PARAM:
+                    raise ValueError("control values may depend on parameters only")
+                z_exprs.append(v)
+                z_lo.append(c.lo); z_hi.append(c.hi); z_fixed.append(1 if c.fixed else 0)
+            for e in range(self.nfe):
+                cmap[e, k] = c.z0 + (e if c.pieces > 1 else 0)
+        nz = len(z_exprs)
+
+        roots = {"x0": x0, "q0": q0, "z": z_exprs, "f": f, "J": J, "fq": fq, "g": gk}
+        low = T.lower(g, n_param=self.n_param, n_ctrl_elem=nce, ns=ns, nq=nq, roots=roots, ncp=self.ncp)
+        lay = low.layout
+        tau, adot, bw = radau_tables(self.ncp)
+
+        secs = []
+
+        def sec(tag, dtype, arr):
+            arr = np.ascontiguousarray(np.asarray(arr, dtype=_NP[dtype]).reshape(-1))
+            secs.append((tag, dtype, arr))
+
+        sec("HEAD", "u32", [ns, nq, ng, len(self.d_names), len(self.p_names), nz, self.nfe, self.ncp, nce,
+                            lay.n_units, lay.param_slot, lay.ctrl_slot, lay.xe_slot, lay.qe_slot, lay.x_slot,
+                            self.newton_max_it])
+        sec("DBLS", "f64", [self.newton_rtol])
+        sec("CNST", "f64", low.consts if len(low.consts) else [0.0])
+        sec("ADOT", "f64", adot)
+        sec("BWTS", "f64", bw)
+        sec("BIGM", "f64", [m for _, _, m in self.constraints])
+        sec("ZLOW", "f64", z_lo if nz else [0.0])
+        sec("ZHIG", "f64", z_hi if nz else [0.0])
+        sec("ZFIX", "u16", z_fixed if nz else [0])
+        sec("TPRO", "u64", low.code["pro"])
+        sec("TELM", "u64", low.code["elem"])
+        sec("TPNT", "u64", low.code["pt"])
+        sec("TGEE", "u64", low.code["g"])
+        sec("RX0_", "u16", low.refs["x0"])
+        sec("RQ0_", "u16", low.refs["q0"] if nq else [T.REF_NONE])
+        sec("RZ__", "u16", low.refs["z"] if nz else [T.REF_NONE])
+        sec("RF__", "u16", low.refs["f"])
+        sec("RJ__", "u16", low.refs["J"])
+        sec("RFQ_", "u16", low.refs["fq"] if nq else [T.REF_NONE])
+        sec("RG__", "u16", low.refs["g"])
+        sec("CMAP", "u16", cmap)
+
+        blob = bytearray(struct.pack("<IIII", BLOB_MAGIC, BLOB_VERSION, len(secs), 0))
+        for tag, dtype, arr in secs:
+            raw = arr.tobytes()
+            pad = (-len(raw)) % 8
+            blob += struct.pack("<4sIII", tag.encode(), _DT[dtype], arr.size, 0)
+            blob += raw + b"\0" * pad
+        info = LoweredModel(
+            blob=bytes(blob), ns=ns, nq=nq, ng=ng, nz=nz, d_dim=len(self.d_names), p_dim=len(self.p_names),
+            nfe=self.nfe, ncp=self.ncp, n_units=lay.n_units, tapes=low, dyn_states=[self.states[i].name for i in dyn],
+            quad_states=[self.states[i].name for i in quad], z_lo=np.asarray(z_lo), z_hi=np.asarray(z_hi),
+            z_fixed=np.asarray(z_fixed, dtype=bool), big_m=np.asarray([m for _, _, m in self.constraints]),
+            constraint_names=[n for n, _, _ in self.constraints], cmap=cmap, newton_rtol=self.newton_rtol,
+            newton_max_it=self.newton_max_it)
+        return info
+
+
+@dataclass
+class LoweredModel:
+    blob: bytes
+    ns: int
+    nq: int
+    ng: int
+    nz: int
+    d_dim: int
+    p_dim: int
+    nfe: int
+    ncp: int
+    n_units: int
+    tapes: T.LoweredTapes
+    dyn_states: list
+    quad_states: list
+    z_lo: np.ndarray
+    z_hi: np.ndarray
+    z_fixed: np.ndarray
+    big_m: np.ndarray
+    constraint_names: list
+    cmap: np.ndarray
+    newton_rtol: float
+    newton_max_it: int
+
+    def flops_per_newton_iteration(self):
+        """Algorithmic flops of one Newton iteration on one finite element:
+        point tape (x ncp) + linear collocation residual + dense LU + two triangular solves."""
+        n = self.ns * self.ncp
+        tape = self.tapes.stats["flops"]["pt"] * self.ncp
+        resid = 2 * n * (self.ncp + 1)
+        return tape + resid + (2 * n ** 3) // 3 + 2 * n * n
+
+    def flops_per_evaluation(self, mean_newton_iters_per_element):
+        fl = self.tapes.stats["flops"]
+        return (fl["pro"] + fl["g"] + self.nfe * (fl["elem"] + mean_newton_iters_per_element *
+                                                   self.flops_per_newton_iteration()))
+
+
+def parse_blob(blob: bytes):
+    """Decode a blob back into {tag: ndarray} (used by tests and the oracle's tape VM)."""
+    magic, ver, nsec, _ = struct.unpack_from("<IIII", blob, 0)
+    if magic != BLOB_MAGIC or ver != BLOB_VERSION:
+        raise ValueError("not a pyds_b200 model blob")
+    off = 16
+    out = {}
+    inv = {v: k for k, v in _DT.items()}
+    for _ in range(nsec):
+        tag, dt, cnt, _ = struct.unpack_from("<4sIII", blob, off)
+        off += 16
+        dtype = _NP[inv[dt]]
+        nbytes = cnt * np.dtype(dtype).itemsize
+        out[tag.decode()] = np.frombuffer(blob, dtype=dtype, count=cnt, offset=off).copy()
+        off += nbytes + ((-nbytes) % 8)
+    return out
