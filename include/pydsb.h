@@ -1,0 +1,110 @@
+/* pydsb.h -- C ABI of libpyds_b200.so, the B200 (sm_100a) feasibility engine behind
+ * pyds_b200.run.TwoStageManager / ThreeStageManager.
+ *
+ * The reference (cornelmarck/pyds) has NO FFI of its own: its hot path is a Python callable
+ * g(d, p) handed to DEUS (reference run_twostage.py:145-165) that loops over design points and
+ * launches one GAMS/CONOPT process per point (reference pyds/run.py:47-69, pyds/solver.py:50-55).
+ * Each entry point below names the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative pydsb_status on error; the message is
+ *     available from pydsb_last_error() (thread local);
+ *   - no exceptions cross the boundary; no torch / C++ types in any signature;
+ *   - unless the name ends in _host, array arguments are DEVICE pointers to contiguous row-major
+ *     fp64 on the handle's device, and `stream` is a cudaStream_t passed as void* (NULL = legacy
+ *     default stream); calls are asynchronous with respect to the host;
+ *   - one handle per (process, device); a handle is not thread-safe.
+ */
+#ifndef PYDSB_H
+#define PYDSB_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pydsb_status {
+    PYDSB_OK = 0,
+    PYDSB_ERR_INVALID = -1,     /* bad argument / malformed blob */
+    PYDSB_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+    PYDSB_ERR_UNSUPPORTED = -3, /* model shape outside what the kernels are instantiated for */
+    PYDSB_ERR_NO_DEVICE = -4    /* no CUDA device: there is deliberately no CPU fallback */
+} pydsb_status;
+
+/* control-vector sources for pydsb_eval (`z_mode`) */
+enum {
+    PYDSB_Z_MODEL = 0,        /* model defaults: warm-start profile / parameter-defined controls
+                                 (reference run_twostage.py:25-26 F_in_default)                    */
+    PYDSB_Z_SHARED = 1,       /* z is (nz): one profile for every scenario                          */
+    PYDSB_Z_PER_DESIGN = 2,   /* z is (n_d, nz): shared across theta -- the reference's two-stage
+                                 formulation (stage-0 F_in, reference pyds/utils.py:92-112)         */
+    PYDSB_Z_PER_SCENARIO = 3  /* z is (n_d, n_t, nz): per-scenario recourse                         */
+};
+
+/* indices into the array returned by pydsb_model_info */
+enum {
+    PYDSB_INFO_NS = 0, PYDSB_INFO_NQ, PYDSB_INFO_NG, PYDSB_INFO_D_DIM, PYDSB_INFO_P_DIM, PYDSB_INFO_NZ,
+    PYDSB_INFO_NFE, PYDSB_INFO_NCP, PYDSB_INFO_N_UNITS, PYDSB_INFO_SMEM_BYTES, PYDSB_INFO_BLOCKS_PER_SM,
+    PYDSB_INFO_NUM_SMS, PYDSB_INFO_REGS_PER_THREAD, PYDSB_INFO_COUNT
+};
+
+/* indices into the array returned by pydsb_get_counters */
+enum {
+    PYDSB_CNT_SCENARIOS = 0,     /* (d,theta) evaluations completed                                  */
+    PYDSB_CNT_NEWTON_ITERS,      /* Newton iterations until each scenario's own convergence          */
+    PYDSB_CNT_NEWTON_WARP_ITERS, /* iterations actually executed (warp-uniform loop), x32 lanes      */
+    PYDSB_CNT_FAILED,            /* scenarios whose state solve failed (counted infeasible; cf.
+                                    reference pyds/solver.py:39-44, 63-69)                           */
+    PYDSB_CNT_LAUNCHES,          /* kernel launches issued by this handle                            */
+    PYDSB_CNT_COUNT
+};
+
+const char* pydsb_last_error(void);
+int pydsb_version(void);
+
+/* Replaces Manager._build_model / utils.create_EF (reference pyds/run.py:32-34, pyds/utils.py:92-112):
+ * instead of rebuilding a Pyomo block tree whenever n_p changes, the model is lowered once to a
+ * tape blob (pyds_b200/model.py) and uploaded to the device here. */
+int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handle);
+int pydsb_model_destroy(void* handle);
+int pydsb_model_info(void* handle, long long* out, int n);
+
+/* The whole hot path in one launch sequence: state solve (collocation Newton), CQAs g, big-M
+ * indicator and the weighted P(feasible) reduction over theta.
+ * Replaces the body of TwoStageManager.g / ThreeStageManager.g for given controls
+ * (reference pyds/run.py:55-67, 85-96: load_input -> simulate -> solver.solve -> -indicator) and
+ * DEUS's efp reduction  P_i = sum_j w_j 1[all_k g_ijk >= 0].
+ *   d      (n_d, d_dim)      theta (n_t, p_dim)      w (n_t) or NULL (= 1/n_t)
+ *   z      per z_mode (may be NULL for PYDSB_Z_MODEL)
+ *   g_out  NULL or (n_d, n_t, n_g)   constraint values g_k (feasible <=> all g_k <= 0)
+ *   ind_out NULL or (n_d, n_t)       -indicator in {-0.0, -1.0}: exactly what Manager.g returns
+ *   P_out  NULL or (n_d)             weighted probability of feasibility
+ */
+int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta, const double* w,
+               long long n_t, const double* z, int z_mode, double* g_out, double* ind_out, double* P_out,
+               void* stream);
+
+/* Convenience forms with the names SURVEY.md section 8b proposes. */
+int pydsb_eval_g(void* handle, const double* d, long long n_d, const double* theta, long long n_t,
+                 double* g_out, void* stream);
+int pydsb_efp(void* handle, const double* d, long long n_d, const double* theta, const double* w,
+              long long n_t, double* P_out, void* stream);
+
+/* Same as pydsb_eval but with HOST pointers: stages through pinned buffers, copies in, runs,
+ * copies the requested outputs back and synchronises.  This is the call the drop-in Manager.g
+ * makes for numpy inputs (the reference's g(d, p) takes and returns numpy arrays). */
+int pydsb_eval_host(void* handle, const double* d, long long n_d, const double* theta, const double* w,
+                    long long n_t, const double* z, int z_mode, double* g_out, double* ind_out, double* P_out);
+
+/* Counters since the last reset (device-side totals; synchronises the handle's work). */
+int pydsb_get_counters(void* handle, unsigned long long* out, int n, int reset);
+
+/* Measured FP64 FMA throughput of the device (dependent-chain-free DFMA microkernel, CUDA-event
+ * timed): the roofline denominator for this path.  Returns TFLOP/s in *tflops (2 flop per FMA). */
+int pydsb_dfma_peak(int device, int repeats, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYDSB_H */

@@ -17,7 +17,7 @@ import struct
 import numpy as np
 
 _OPS = ["MOV", "NEG", "ADD", "SUB", "MUL", "DIV", "FMA", "FMS", "FNMA", "SQR", "RCP", "EXP", "LOG",
-        "SQRT", "SIN", "COS", "TANH", "POW", "ABS", "MIN", "MAX"]
+        "SQRT", "SIN", "COS", "TANH", "POW", "ABS", "MIN", "MAX", "BC3"]
 _REF_CONST, _REF_WIDE, _REF_MASK, _REF_NONE = 1 << 13, 1 << 12, 0xFFF, 0x3FFF
 _DT = {0: np.uint32, 1: np.float64, 2: np.uint64, 3: np.uint16}
 
@@ -40,7 +40,8 @@ class TapeVM:
         s = parse_blob(blob)
         self.sec = s
         (self.ns, self.nq, self.ng, self.d_dim, self.p_dim, self.nz, self.nfe, self.ncp, self.nce, self.n_units,
-         self.param_slot, self.ctrl_slot, self.xe_slot, self.qe_slot, self.x_slot, self.max_it) = [int(v) for v in s["HEAD"]]
+         self.param_slot, self.ctrl_slot, self.xe_slot, self.qe_slot, self.x_slot, self.max_it,
+         self.f_slot, self.j_slot, self.fq_slot, self.j_mask, self.fq_state_dep) = [int(v) for v in s["HEAD"]]
         self.rtol = float(s["DBLS"][0])
         self.consts = s["CNST"]
         self.adot = s["ADOT"].reshape(self.ncp + 1, self.ncp + 1)
@@ -63,6 +64,10 @@ class TapeVM:
             word = int(word)
             op = _OPS[word & 0xFF]
             dst, a, b, c = (word >> 8) & 0x3FFF, (word >> 22) & 0x3FFF, (word >> 36) & 0x3FFF, (word >> 50) & 0x3FFF
+            if op == "BC3":
+                for w in range(3):
+                    R[(dst & _REF_MASK) + w] = np.broadcast_to(self._ld(R, a, 0), R[0].shape).copy()
+                continue
             for w in range(width):
                 A = self._ld(R, a, w)
                 if op == "MOV": v = A
@@ -139,12 +144,13 @@ class TapeVM:
                     for w in range(ncp):
                         R[self.x_slot + 3 * i + w] = X[:, w, i]
                 self._run(R, s["TPNT"], ncp)
-                f = np.stack([np.stack([self._ld(R, r, w) * one for r in s["RF__"][:ns]], axis=1) for w in range(ncp)], axis=1)
+                f = np.stack([np.stack([R[self.f_slot + 3 * i + w] for i in range(ns)], axis=1) for w in range(ncp)], axis=1)
                 J = np.zeros((S, ncp, ns, ns))
                 for w in range(ncp):
                     for r_ in range(ns):
                         for c_ in range(ns):
-                            J[:, w, r_, c_] = self._ld(R, s["RJ__"][r_ * ns + c_], w)
+                            if (self.j_mask >> (r_ * ns + c_)) & 1:
+                                J[:, w, r_, c_] = R[self.j_slot + 3 * (r_ * ns + c_) + w]
                 lin = np.einsum("kj,skn->sjn", A[1:, 1:], X) + A[0, 1:][None, :, None] * x0[:, None, :]
                 Rres = lin - h * f
                 M = np.zeros((S, ncp, ns, ncp, ns))
@@ -176,7 +182,7 @@ class TapeVM:
             for k in range(nq):
                 acc = 0.0
                 for w in range(ncp):
-                    acc = acc + self.bw[w] * self._ld(R, s["RFQ_"][k], w)
+                    acc = acc + self.bw[w] * R[self.fq_slot + 3 * k + w]
                 q[:, k] = q[:, k] + h * acc
             traj[:, e * ncp + 1:(e + 1) * ncp + 1] = X
             x0 = X[:, ncp - 1, :].copy()

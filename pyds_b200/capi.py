@@ -1,0 +1,169 @@
+"""ctypes binding of libpyds_b200.so (the C ABI declared in ``include/pydsb.h``).
+
+PyTorch tensors are used only as device buffers: the library receives raw ``data_ptr()`` values
+and a CUDA stream handle.  There is no CPU fallback -- if the library is missing it must be built
+(``python -m pyds_b200.build``), and on a machine without a CUDA device ``Engine`` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+Z_MODEL, Z_SHARED, Z_PER_DESIGN, Z_PER_SCENARIO = 0, 1, 2, 3
+INFO_NAMES = ["ns", "nq", "ng", "d_dim", "p_dim", "nz", "nfe", "ncp", "n_units", "smem_bytes", "blocks_per_sm",
+              "num_sms", "regs_per_thread"]
+COUNTER_NAMES = ["scenarios", "newton_iters", "newton_warp_iters", "failed", "launches"]
+
+EXPORTS = ["pydsb_last_error", "pydsb_version", "pydsb_model_create", "pydsb_model_destroy", "pydsb_model_info",
+           "pydsb_eval", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_get_counters", "pydsb_dfma_peak"]
+
+
+class PydsbError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building if the sources are newer) the shared library and declare its prototypes."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if _build.is_stale():
+        _build.build()
+    L = ctypes.CDLL(path)
+    vp, ll, dp, ci = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int
+    L.pydsb_last_error.restype = ctypes.c_char_p
+    L.pydsb_last_error.argtypes = []
+    L.pydsb_version.restype = ci
+    L.pydsb_model_create.restype = ci
+    L.pydsb_model_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ci, ctypes.POINTER(vp)]
+    L.pydsb_model_destroy.restype = ci
+    L.pydsb_model_destroy.argtypes = [vp]
+    L.pydsb_model_info.restype = ci
+    L.pydsb_model_info.argtypes = [vp, ctypes.POINTER(ll), ci]
+    L.pydsb_eval.restype = ci
+    L.pydsb_eval.argtypes = [vp, dp, ll, dp, dp, ll, dp, ci, dp, dp, dp, vp]
+    L.pydsb_eval_g.restype = ci
+    L.pydsb_eval_g.argtypes = [vp, dp, ll, dp, ll, dp, vp]
+    L.pydsb_efp.restype = ci
+    L.pydsb_efp.argtypes = [vp, dp, ll, dp, dp, ll, dp, vp]
+    L.pydsb_eval_host.restype = ci
+    L.pydsb_eval_host.argtypes = [vp, dp, ll, dp, dp, ll, dp, ci, dp, dp, dp]
+    L.pydsb_get_counters.restype = ci
+    L.pydsb_get_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong), ci, ci]
+    L.pydsb_dfma_peak.restype = ci
+    L.pydsb_dfma_peak.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise PydsbError(f"libpyds_b200 error {rc}: {load().pydsb_last_error().decode()}")
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _np64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Engine:
+    """One uploaded model on one device (wraps a ``pydsb_model`` handle)."""
+
+    def __init__(self, blob: bytes, device: int = 0):
+        self._h = ctypes.c_void_p()
+        self._lib = load()
+        self.device = int(device)
+        _check(self._lib.pydsb_model_create(blob, len(blob), self.device, ctypes.byref(self._h)))
+        buf = (ctypes.c_longlong * len(INFO_NAMES))()
+        _check(self._lib.pydsb_model_info(self._h, buf, len(INFO_NAMES)))
+        self.info = {k: int(v) for k, v in zip(INFO_NAMES, buf)}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pydsb_model_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- host (numpy) path: what the drop-in Manager.g uses --------------------------------------
+    def eval_host(self, d, theta, w=None, z=None, z_mode=None, want_g=False, want_ind=False, want_P=True):
+        d = _np64(d)
+        d = d.reshape(-1, self.info["d_dim"]) if self.info["d_dim"] else d.reshape(len(d), 0)
+        theta = _np64(theta).reshape(-1, self.info["p_dim"])
+        n_d, n_t = d.shape[0], theta.shape[0]
+        w = _np64(w)
+        if w is not None and w.shape != (n_t,):
+            raise ValueError("w must have one weight per theta sample")
+        z, z_mode = self._norm_z(z, z_mode, n_d, n_t)
+        g = np.empty((n_d, n_t, self.info["ng"])) if want_g else None
+        ind = np.empty((n_d, n_t)) if want_ind else None
+        P = np.empty(n_d) if want_P else None
+        _check(self._lib.pydsb_eval_host(self._h, _np_ptr(d), n_d, _np_ptr(theta), _np_ptr(w), n_t, _np_ptr(z), z_mode,
+                                         _np_ptr(g), _np_ptr(ind), _np_ptr(P)))
+        return g, ind, P
+
+    def _norm_z(self, z, z_mode, n_d, n_t):
+        nz = self.info["nz"]
+        if z is None or nz == 0:
+            return None, Z_MODEL
+        z = _np64(z)
+        if z_mode is None:
+            z_mode = {1: Z_SHARED, 2: Z_PER_DESIGN, 3: Z_PER_SCENARIO}[z.ndim]
+        want = {Z_SHARED: (nz,), Z_PER_DESIGN: (n_d, nz), Z_PER_SCENARIO: (n_d, n_t, nz)}[z_mode]
+        if z.shape != want:
+            raise ValueError(f"z has shape {z.shape}, expected {want}")
+        return z, z_mode
+
+    # -- device (torch tensor) path ----------------------------------------------------------------
+    def eval_device(self, d, theta, w=None, z=None, z_mode=Z_MODEL, g_out=None, ind_out=None, P_out=None, stream=None):
+        """All arguments are contiguous fp64 CUDA tensors (or None); asynchronous on ``stream``."""
+        import torch
+        for name, t in (("d", d), ("theta", theta), ("w", w), ("z", z), ("g_out", g_out), ("ind_out", ind_out), ("P_out", P_out)):
+            if t is None:
+                continue
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.device.index == self.device):
+                raise ValueError(f"{name} must be a contiguous float64 CUDA tensor on device {self.device}")
+        n_d = d.shape[0]
+        n_t = theta.shape[0]
+        if theta.shape[1] != self.info["p_dim"] or (d.dim() != 2 or d.shape[1] != self.info["d_dim"]):
+            raise ValueError("d/theta column count does not match the model")
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        _check(self._lib.pydsb_eval(self._h, ptr(d), n_d, ptr(theta), ptr(w), n_t, ptr(z), z_mode if z is not None else Z_MODEL,
+                                    ptr(g_out), ptr(ind_out), ptr(P_out), ctypes.c_void_p(stream.cuda_stream)))
+
+    def counters(self, reset=False):
+        buf = (ctypes.c_ulonglong * len(COUNTER_NAMES))()
+        _check(self._lib.pydsb_get_counters(self._h, buf, len(COUNTER_NAMES), 1 if reset else 0))
+        return {k: int(v) for k, v in zip(COUNTER_NAMES, buf)}
+
+
+def dfma_peak(device: int = 0, repeats: int = 5):
+    """Measured FP64 FMA throughput (TFLOP/s, best of ``repeats``) and the kernel time in ms."""
+    t, ms = ctypes.c_double(), ctypes.c_double()
+    _check(load().pydsb_dfma_peak(device, repeats, ctypes.byref(t), ctypes.byref(ms)))
+    return t.value, ms.value

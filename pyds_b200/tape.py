@@ -36,7 +36,7 @@ import numpy as np
 # opcodes -- must match csrc/tape_vm.cuh
 # ---------------------------------------------------------------------------------------------
 OPS = ["MOV", "NEG", "ADD", "SUB", "MUL", "DIV", "FMA", "FMS", "FNMA", "SQR", "RCP", "EXP", "LOG",
-       "SQRT", "SIN", "COS", "TANH", "POW", "ABS", "MIN", "MAX"]
+       "SQRT", "SIN", "COS", "TANH", "POW", "ABS", "MIN", "MAX", "BC3"]
 OPCODE = {n: i for i, n in enumerate(OPS)}
 
 REF_CONST = 1 << 13
@@ -342,6 +342,11 @@ class TapeLayout:
     xe_slot: int = 0
     qe_slot: int = 0
     x_slot: int = 0            # wide: slot x_slot + 3*i + point
+    f_slot: int = 0            # wide, dense: f_slot + 3*i + point           (pinned outputs of the point tape)
+    j_slot: int = 0            # wide, dense: j_slot + 3*(r*ns + c) + point
+    fq_slot: int = 0           # wide, dense: fq_slot + 3*k + point
+    j_mask: int = 0            # bit r*ns+c set when dJ[r][c] is not structurally zero
+    fq_state_dep: int = 0      # 1 when some quadrature integrand depends on the dynamic states
     n_units: int = 0           # total narrow-equivalent slots
 
 
@@ -428,6 +433,9 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
     lay.xe_slot = cur; cur += ns
     lay.qe_slot = cur; cur += nq
     lay.x_slot = cur; cur += 3 * ns
+    lay.f_slot = cur; cur += 3 * ns
+    lay.j_slot = cur; cur += 3 * ns * ns
+    lay.fq_slot = cur; cur += 3 * nq
 
     level_tape = {LEVEL_PARAM: "pro", LEVEL_CTRL: "elem", LEVEL_STATE: "pt", LEVEL_END: "g"}
     sched = {"pro": [], "elem": [], "pt": [], "g": []}
@@ -479,6 +487,31 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
 
     slot_of = {}
 
+    # dense, pinned outputs of the point tape: f, J, fq land at fixed wide slots so that the
+    # compiled Newton code reads them with immediate offsets.  Lower-level roots (constants,
+    # parameter- or control-level values) are broadcast into their slot by the pro / elem tape.
+    pinned = {}                 # node id -> REF_WIDE|slot of its first pinned destination
+    extra = {"pro": [], "elem": [], "pt": []}      # (opname, dst, src node) appended after the tape body
+    dense = [("f", lay.f_slot), ("J", lay.j_slot), ("fq", lay.fq_slot)]
+    for tname, base in dense:
+        for i, e in enumerate(roots.get(tname, [])):
+            dst = REF_WIDE | (base + 3 * i)
+            if tname == "J" and e is not None and not e.is_const(0.0):
+                lay.j_mask |= 1 << i
+            if e is None:
+                e = graph.const(0.0)
+            if tname == "fq" and e.level == LEVEL_STATE:
+                lay.fq_state_dep = 1
+            if e.level == LEVEL_STATE and e.args and e.id not in pinned:
+                pinned[e.id] = dst
+            elif e.level == LEVEL_STATE:
+                extra["pt"].append(("MOV", dst, e))
+            elif e.level == LEVEL_CTRL:
+                extra["elem"].append(("BC3", dst, e))
+            else:
+                extra["pro"].append(("BC3", dst, e))
+    dense_names = {t for t, _ in dense}
+
     def leaf_ref(n):
         if n.op == "const": return cref(n.value)
         if n.op == "param": return lay.param_slot + n.value
@@ -507,9 +540,12 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
             for s in release_at.pop(pos, []):
                 pool.give(s)
             args = eff_args(n)
-            s = pool.take()
-            slot_of[n.id] = (REF_WIDE | s) if wide else s
-            if n.id not in persistent:
+            if n.id in pinned:
+                slot_of[n.id] = pinned[n.id]
+            else:
+                s = pool.take()
+                slot_of[n.id] = (REF_WIDE | s) if wide else s
+            if n.id not in persistent and n.id not in pinned:
                 lu = last_use.get(n.id, pos)
                 release_at.setdefault(lu + 1, []).append(s)
             if n.id in fma_form:
@@ -521,6 +557,8 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
                 words.append(encode(_UNOPS[n.op], slot_of[n.id], ref(args[0])))
             else:
                 raise NotImplementedError(n.op)
+        for opn, dst, src in extra.get(name, []):
+            words.append(encode(opn, dst, ref(src)))
         code[name] = np.asarray(words, dtype=np.uint64)
         narrow_next = pool.next
     if narrow_next - 1 > REF_MASK:
@@ -529,6 +567,8 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
 
     ref_tables = {}
     for name, lst in roots.items():
+        if name in dense_names:
+            continue
         out = []
         for e in lst:
             if e is None or e.is_const(0.0):
