@@ -288,6 +288,8 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
     const long long max_ctas = (long long)m->num_sms * m->blocks_per_sm;
     const int grid = (int)(total < max_ctas ? total : max_ctas);
     KernelFn fn = kernel_for(m->img.ns);
+    // several models may share one template instantiation: (re)assert this model's smem size
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, m->img.smem_bytes));
     fn<<<grid, BLOCK, m->img.smem_bytes, st>>>(m->img, la);
     CUDA_TRY(cudaGetLastError());
     m->launches += 1;

@@ -1,0 +1,94 @@
+"""Multi-GPU sharding of the feasibility path: one process per GPU, design points sharded.
+
+The path has no data-path exchange: each design point's P(feasible) depends only on its own
+``d`` row and the replicated theta set, so every rank runs the same kernel on a
+contiguous block of rows and the only communication is one small all-gather of the per-point
+probabilities (NCCL over NVLink on the GPU box, gloo in the CPU tests).  The reference itself is
+strictly serial (DEUS ``"method": "serial"``, reference ``run_twostage.py:146,160``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_rows(n: int, world: int, rank: int):
+    """Contiguous, balanced row block of rank ``rank``: returns (start, stop)."""
+    base, rem = divmod(int(n), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n: int, world: int):
+    return [shard_rows(n, world, r)[1] - shard_rows(n, world, r)[0] for r in range(world)]
+
+
+class ShardedEfp:
+    """P(feasible) for a design-point batch spread over the ranks of a process group."""
+
+    def __init__(self, engine, world: int = 1, rank: int = 0, group=None):
+        self.engine, self.world, self.rank, self.group = engine, int(world), int(rank), group
+        self._P_local = None
+
+    # -- device-resident inputs (equal shard sizes: every rank passes its own rows) ----------------
+    def launch_local(self, d, theta, w=None, z=None, z_mode=0):
+        import torch
+        n = d.shape[0]
+        if self._P_local is None or self._P_local.shape[0] != n or self._P_local.device != d.device:
+            self._P_local = torch.empty(n, dtype=torch.float64, device=d.device)
+        self.engine.eval_device(d, theta, w=w, z=z, z_mode=z_mode, P_out=self._P_local)
+        return self._P_local
+
+    def gather(self, P_all):
+        import torch.distributed as dist
+        if self.world == 1:
+            P_all.copy_(self._P_local)
+        else:
+            dist.all_gather_into_tensor(P_all, self._P_local, group=self.group)
+        return P_all
+
+    def efp_device(self, d, theta, w, P_all):
+        self.launch_local(d, theta, w)
+        return self.gather(P_all)
+
+    # -- host inputs: the user-facing call (numpy in, numpy out) -------------------------------------
+    def efp_host(self, d_local, theta, w=None, z=None):
+        """``d_local`` are THIS rank's rows; returns the probabilities of all ranks' rows, rank order."""
+        _, _, P = self.engine.eval_host(d_local, theta, w, z=z, want_P=True)
+        if self.world == 1:
+            return P
+        return self.all_gather_host(P)
+
+    def all_gather_host(self, P_local):
+        import torch
+        import torch.distributed as dist
+        backend = dist.get_backend(self.group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(np.ascontiguousarray(P_local, dtype=np.float64)).to(dev)
+        sizes = [None] * self.world
+        dist.all_gather_object(sizes, int(t.numel()), group=self.group)
+        if len(set(sizes)) == 1:
+            out = torch.empty(self.world * t.numel(), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(out, t, group=self.group)
+            return out.cpu().numpy()
+        m = max(sizes)                                   # ragged shards: pad to the longest, trim after
+        pad = torch.zeros(m, dtype=torch.float64, device=dev)
+        pad[:t.numel()] = t
+        out = torch.empty(self.world * m, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        out = out.view(self.world, m).cpu().numpy()
+        return np.concatenate([out[r, :sizes[r]] for r in range(self.world)])
+
+    def efp_global(self, d_global, theta, w=None, z=None):
+        """Every rank passes the SAME global batch; rows are sharded here and the full result returned."""
+        a, b = shard_rows(len(d_global), self.world, self.rank)
+        zl = None
+        if z is not None:
+            z = np.asarray(z)
+            zl = z[a:b] if z.ndim >= 2 else z
+        if b > a:
+            P = self.engine.eval_host(np.asarray(d_global)[a:b], theta, w, z=zl, want_P=True)[2]
+        else:
+            P = np.empty(0)
+        if self.world == 1:
+            return P
+        return self.all_gather_host(P)

@@ -1,0 +1,71 @@
+"""world_size-2 gloo tests of the N>1 host logic (sharding + gather).  The compute stand-in is the
+oracle -- this is test infrastructure; on the GPU box the engine is the CUDA one."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_rows_partition():
+    from pyds_b200.parallel import shard_rows, shard_sizes
+    for n in (0, 1, 7, 8, 100, 12501):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_rows(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = shard_sizes(n, world)
+            assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+
+
+class _OracleEngine:
+    """Stand-in with the Engine.eval_host signature, backed by the C oracle (tests only)."""
+
+    def eval_host(self, d, theta, w=None, z=None, z_mode=None, want_g=False, want_ind=False, want_P=True):
+        from oracle import cbind
+        n_t = len(theta)
+        w = np.full(n_t, 1.0 / n_t) if w is None else w
+        g, P, _ = cbind.kinetics_grid(d, theta, w, F=z, want_g=want_g)
+        return g, None, P
+
+
+def _worker(rank, world, port, n_d, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import kinetics as K
+    from pyds_b200.parallel import ShardedEfp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(4)
+    d = np.stack([rng.uniform(250, 350, n_d), rng.uniform(250, 300, n_d)], axis=1)
+    p = K.theta_samples()
+    w = np.full(50, 0.02)
+    sh = ShardedEfp(_OracleEngine(), world, rank)
+    P = sh.efp_global(d, p, w)
+    q.put((rank, P))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_d", [10, 11, 1])
+def test_sharded_efp_gloo_world2(n_d):
+    from oracle import cbind, kinetics as K
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n_d) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_d, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = dict(q.get(timeout=180) for _ in range(2))
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    rng = np.random.default_rng(4)
+    d = np.stack([rng.uniform(250, 350, n_d), rng.uniform(250, 300, n_d)], axis=1)
+    _, P_ref, _ = cbind.kinetics_grid(d, K.theta_samples(), np.full(50, 0.02), want_g=False)
+    for r in range(2):
+        np.testing.assert_allclose(res[r], P_ref, atol=1e-15)
