@@ -40,8 +40,9 @@ class TapeVM:
         s = parse_blob(blob)
         self.sec = s
         (self.ns, self.nq, self.ng, self.d_dim, self.p_dim, self.nz, self.nfe, self.ncp, self.nce, self.n_units,
-         self.param_slot, self.ctrl_slot, self.xe_slot, self.qe_slot, self.x_slot, self.max_it,
-         self.f_slot, self.j_slot, self.fq_slot, self.j_mask, self.fq_state_dep) = [int(v) for v in s["HEAD"]]
+         self.ctrl_slot, self.xe_slot, self.qe_slot, self.x_slot, self.max_it,
+         self.f_slot, self.j_slot, self.fq_slot, self.j_mask, self.fq_state_dep, self.predictor) = [int(v) for v in s["HEAD"]]
+        self.param_slots = [int(v) for v in s["RPAR"]]
         self.rtol = float(s["DBLS"][0])
         self.consts = s["CNST"]
         self.adot = s["ADOT"].reshape(self.ncp + 1, self.ncp + 1)
@@ -106,9 +107,9 @@ class TapeVM:
         max_it = self.max_it if max_it is None else max_it
         R = [np.zeros(S) for _ in range(self.n_units)]
         for i in range(self.d_dim):
-            R[self.param_slot + i] = np.repeat(d[:, i], n_p)
+            R[self.param_slots[i]] = np.repeat(d[:, i], n_p)
         for i in range(self.p_dim):
-            R[self.param_slot + self.d_dim + i] = np.tile(p[:, i], n_d)
+            R[self.param_slots[self.d_dim + i]] = np.tile(p[:, i], n_d)
         s = self.sec
         self._run(R, s["TPRO"], 1)
         one = np.ones(S)

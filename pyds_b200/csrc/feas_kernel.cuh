@@ -29,18 +29,20 @@ namespace pydsb {
 
 struct ExecImage {
     // global-memory copies made by pydsb_model_create
-    const uint64_t* code;      // pro | elem | pt | g
+    const uint64_t* code;      // pro | elem | g   (narrow tapes; staged in shared memory)
     const double* consts;      // constant pool
-    const uint16_t* tabs;      // x0[ns] q0[nq] ztab[nz] zfix[nz] gtab[ng] cmap[nfe*nce]
+    const uint16_t* tabs;      // par[n_param] x0[ns] q0[nq] ztab[nz] zfix[nz] gtab[ng] cmap[nfe*nce]
     int n_pro, n_elem, n_pt, n_g, n_const, n_tabs;
     int ns, nq, ng, d_dim, p_dim, nz, nfe, nce, n_units;
-    int param_slot, ctrl_slot, xe_slot, qe_slot, x_slot, f_slot, j_slot, fq_slot;
+    int ctrl_slot, xe_slot, qe_slot, x_slot, f_slot, j_slot, fq_slot;
     unsigned j_mask;
     int fq_state_dep;
+    int predictor;
     int max_it;
-    double rtol;
+    double rtol2;              // (relative Newton tolerance)^2
     double adot[16];
     double bw[3];
+    double ext[12];            // ext[4*j + k] = l_k(1 + tau_{j+1}): previous element's cubic extrapolated
     // shared-memory carve-up (bytes from the start of dynamic smem)
     int off_code, off_const, off_tabs, off_land, off_slots, smem_bytes;
 };
@@ -59,6 +61,13 @@ struct LaunchArgs {
     double* ind_out;
     unsigned long long* counters;
 };
+
+// The point tape, pre-decoded by pydsb_model_create into byte offsets and kept in the constant
+// bank: the fetch is a uniform LDCU and every operand address is [thread base + uniform offset],
+// so the hot interpreter spends no vector-ALU instructions on decoding.
+//   word 0: op | words 1-3: dst offsets (points 0,1,2) | 4-6: a | 7-9: b | 10-12: c | 13-15: pad
+constexpr int MAX_PT = 448;
+__constant__ uint4 c_pt[4 * MAX_PT];
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier / bulk-TMA helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP)
@@ -141,6 +150,89 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v)
     return v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Hot interpreter: the point tape, three collocation points per instruction, operands addressed
+// as [thread base + uniform byte offset] (LDS/STS with a uniform-register offset).
+// ---------------------------------------------------------------------------------------------
+#define PT_LD(off) (*reinterpret_cast<const double*>(base + (off)))
+#define PT_ST(off, v) (*reinterpret_cast<double*>(base + (off)) = (v))
+#define PT_UN(expr)                                                   \
+    {                                                                 \
+        double a;                                                     \
+        a = PT_LD(q1.x); const double r0 = (expr);                    \
+        a = PT_LD(q1.y); const double r1 = (expr);                    \
+        a = PT_LD(q1.z); const double r2 = (expr);                    \
+        PT_ST(q0.y, r0); PT_ST(q0.z, r1); PT_ST(q0.w, r2);            \
+    }                                                                 \
+    break;
+#define PT_BIN(expr)                                                  \
+    {                                                                 \
+        const uint4 q2 = c_pt[4 * pc + 2];                            \
+        double a, b;                                                  \
+        a = PT_LD(q1.x); b = PT_LD(q1.w); const double r0 = (expr);   \
+        a = PT_LD(q1.y); b = PT_LD(q2.x); const double r1 = (expr);   \
+        a = PT_LD(q1.z); b = PT_LD(q2.y); const double r2 = (expr);   \
+        PT_ST(q0.y, r0); PT_ST(q0.z, r1); PT_ST(q0.w, r2);            \
+    }                                                                 \
+    break;
+#define PT_TER(expr)                                                  \
+    {                                                                 \
+        const uint4 q2 = c_pt[4 * pc + 2];                            \
+        const uint4 q3 = c_pt[4 * pc + 3];                            \
+        double a, b, c;                                               \
+        a = PT_LD(q1.x); b = PT_LD(q1.w); c = PT_LD(q2.z); const double r0 = (expr);   \
+        a = PT_LD(q1.y); b = PT_LD(q2.x); c = PT_LD(q2.w); const double r1 = (expr);   \
+        a = PT_LD(q1.z); b = PT_LD(q2.y); c = PT_LD(q3.x); const double r2 = (expr);   \
+        PT_ST(q0.y, r0); PT_ST(q0.z, r1); PT_ST(q0.w, r2);            \
+    }                                                                 \
+    break;
+
+__device__ __forceinline__ void run_point_tape(char* __restrict__ base, int n)
+{
+    for (int pc = 0; pc < n; ++pc) {
+        const uint4 q0 = c_pt[4 * pc];
+        const uint4 q1 = c_pt[4 * pc + 1];
+        switch (q0.x) {
+        case OP_FMA: PT_TER(fma(a, b, c))
+        case OP_FMS: PT_TER(fma(a, b, -c))
+        case OP_FNMA: PT_TER(fma(-a, b, c))
+        case OP_MUL: PT_BIN(a * b)
+        case OP_ADD: PT_BIN(a + b)
+        case OP_SUB: PT_BIN(a - b)
+        case OP_SQR: PT_UN(a * a)
+        case OP_MOV: PT_UN(a)
+        case OP_NEG: PT_UN(-a)
+        case OP_DIV: PT_BIN(a / b)
+        case OP_RCP: PT_UN(1.0 / a)
+        case OP_EXP: PT_UN(exp(a))
+        case OP_LOG: PT_UN(log(a))
+        case OP_SQRT: PT_UN(sqrt(a))
+        case OP_SIN: PT_UN(sin(a))
+        case OP_COS: PT_UN(cos(a))
+        case OP_TANH: PT_UN(tanh(a))
+        case OP_POW: PT_BIN(pow(a, b))
+        case OP_ABS: PT_UN(fabs(a))
+        case OP_MIN: PT_BIN(fmin(a, b))
+        case OP_MAX: PT_BIN(fmax(a, b))
+        default: break;
+        }
+    }
+}
+#undef PT_LD
+#undef PT_ST
+#undef PT_UN
+#undef PT_BIN
+#undef PT_TER
+
+// The narrow tapes (pro / elem / g) run once per scenario or element: keep one out-of-line copy.
+__device__ __noinline__ void run_narrow_tape(double* S, const double* cpool, const uint64_t* code, int n)
+{
+    VM vm;
+    vm.S = S;
+    vm.cpool = cpool;
+    run_tape<1>(vm, code, n);
+}
+
 template <int NS>
 __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
     feas_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ LaunchArgs la)
@@ -150,32 +242,31 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);                 // [2]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);                 // [1]
     double* red = reinterpret_cast<double*>(smem + 16);                 // [BLOCK/32]
     uint64_t* code = reinterpret_cast<uint64_t*>(smem + img.off_code);
     double* cpool = reinterpret_cast<double*>(smem + img.off_const) + 1;   // cpool[-1] = 0.0
     uint16_t* tabs = reinterpret_cast<uint16_t*>(smem + img.off_tabs);
-    double* land = reinterpret_cast<double*>(smem + img.off_land);      // [2][BLOCK*p_dim]
+    double* land = reinterpret_cast<double*>(smem + img.off_land);      // [BLOCK*p_dim]
     double* S = reinterpret_cast<double*>(smem + img.off_slots) + tid;
 
-    // ---- stage the tapes, constants and tables in shared memory (once per CTA) ----
-    const int n_code = img.n_pro + img.n_elem + img.n_pt + img.n_g;
+    // ---- stage the narrow tapes, constants and tables in shared memory (once per CTA) ----
+    const int n_code = img.n_pro + img.n_elem + img.n_g;
     for (int i = tid; i < n_code; i += BLOCK) code[i] = img.code[i];
     for (int i = tid; i < img.n_const; i += BLOCK) cpool[i] = img.consts[i];
     for (int i = tid; i < img.n_tabs; i += BLOCK) tabs[i] = img.tabs[i];
     if (tid == 0) {
         cpool[-1] = 0.0;
         mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
         mbar_fence_init();
     }
     __syncthreads();
 
     const uint64_t* code_pro = code;
     const uint64_t* code_elem = code_pro + img.n_pro;
-    const uint64_t* code_pt = code_elem + img.n_elem;
-    const uint64_t* code_g = code_pt + img.n_pt;
-    const uint16_t* tab_x0 = tabs;
+    const uint64_t* code_g = code_elem + img.n_elem;
+    const uint16_t* tab_par = tabs;
+    const uint16_t* tab_x0 = tab_par + img.d_dim + img.p_dim;
     const uint16_t* tab_q0 = tab_x0 + img.ns;
     const uint16_t* tab_z = tab_q0 + img.nq;
     const uint16_t* tab_zfix = tab_z + img.nz;
@@ -190,14 +281,13 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
     const double* const Fs = S + img.f_slot * BLOCK;
     const double* const Js = S + img.j_slot * BLOCK;
     const double* const FQs = S + img.fq_slot * BLOCK;
-    double* const Ps = S + img.param_slot * BLOCK;
 
     const double h = 1.0 / (double)img.nfe;
     const int p_dim = img.p_dim, d_dim = img.d_dim;
-    const unsigned tile_bytes_full = (unsigned)(BLOCK * p_dim * sizeof(double));
+    const bool final_eval = img.nq > 0 && img.fq_state_dep;
 
     const long long total = la.n_d * (long long)la.n_tiles;
-    unsigned phase_bits = 0;
+    unsigned phase = 0;
 
     auto tile_rows = [&](long long t) -> int {
         const long long j0 = (t % la.n_tiles) * (long long)BLOCK;
@@ -207,53 +297,52 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
     auto tile_tma = [&](int rows) -> bool {
         return la.theta_tma_ok && ((rows * p_dim * (int)sizeof(double)) % 16 == 0);
     };
-    auto issue = [&](long long t, int b) {
+    auto issue = [&](long long t) {
         const int rows = tile_rows(t);
         if (tile_tma(rows)) {
             const long long j0 = (t % la.n_tiles) * (long long)BLOCK;
             const unsigned bytes = (unsigned)(rows * p_dim * sizeof(double));
-            mbar_expect_tx(&mbar[b], bytes);
-            tma_load_1d(land + (size_t)b * BLOCK * p_dim, la.theta + j0 * p_dim, bytes, &mbar[b]);
+            mbar_expect_tx(&mbar[0], bytes);
+            tma_load_1d(land, la.theta + j0 * p_dim, bytes, &mbar[0]);
         }
     };
 
     long long t = blockIdx.x;
-    if (t < total && tid == 0) issue(t, 0);
+    if (t < total && tid == 0) issue(t);
 
-    unsigned long long cnt_iters = 0, cnt_warp_iters = 0;
-    unsigned cnt_failed = 0, cnt_done = 0;
+    unsigned long long cnt_iters = 0;
+    unsigned cnt_warp_iters = 0, cnt_failed = 0, cnt_done = 0;
 
-    for (int k = 0; t < total; t += gridDim.x, ++k) {
-        const int b = k & 1;
+    for (; t < total; t += gridDim.x) {
         const long long i_d = t / la.n_tiles;
         const long long j0 = (t % la.n_tiles) * (long long)BLOCK;
         const int rows = tile_rows(t);
         const bool valid = tid < rows;
-        const int row = valid ? tid : rows - 1;           // clamp: idle lanes replay the last row
+        const int row = valid ? tid : rows - 1;           // idle lanes replay the last row
         const long long j = j0 + row;
 
-        // ---- parameters into the slot file ----
+        // ---- parameters into the register file (theta from the TMA landing buffer) ----
         if (tile_tma(rows)) {
-            mbar_wait(&mbar[b], (phase_bits >> b) & 1u);
-            phase_bits ^= 1u << b;
-            const double* src = land + (size_t)b * BLOCK * p_dim + (size_t)row * p_dim;
-            for (int c = 0; c < p_dim; ++c) Ps[(d_dim + c) * BLOCK] = src[c];
+            mbar_wait(&mbar[0], phase);
+            phase ^= 1u;
+            const double* src = land + (size_t)row * p_dim;
+            for (int c = 0; c < p_dim; ++c) S[tab_par[d_dim + c] * BLOCK] = src[c];
         } else {
             const double* src = la.theta + j * p_dim;
-            for (int c = 0; c < p_dim; ++c) Ps[(d_dim + c) * BLOCK] = __ldg(src + c);
+            for (int c = 0; c < p_dim; ++c) S[tab_par[d_dim + c] * BLOCK] = __ldg(src + c);
         }
-        for (int c = 0; c < d_dim; ++c) Ps[c * BLOCK] = __ldg(la.d + i_d * d_dim + c);
-        __syncthreads();                                   // landing buffer b^1 and `red` are free again
+        for (int c = 0; c < d_dim; ++c) S[tab_par[c] * BLOCK] = __ldg(la.d + i_d * d_dim + c);
+        __syncthreads();                                   // landing buffer and `red` are free again
         {
-            const long long nt = t + gridDim.x;
-            if (nt < total && tid == 0) issue(nt, b ^ 1);
+            const long long nt = t + gridDim.x;            // prefetch the next tile's theta rows
+            if (nt < total && tid == 0) issue(nt);
         }
 
         // ---- prologue ----
-        run_tape<1>(vm, code_pro, img.n_pro);
-        double xprev[NS];
+        run_narrow_tape(S, cpool, code_pro, img.n_pro);
+        double xs[NS], xs_old[NS];
 #pragma unroll
-        for (int n = 0; n < NS; ++n) xprev[n] = vm_ld(vm, tab_x0[n]);
+        for (int n = 0; n < NS; ++n) xs[n] = xs_old[n] = vm_ld(vm, tab_x0[n]);
         for (int q = 0; q < img.nq; ++q) S[(img.qe_slot + q) * BLOCK] = vm_ld(vm, tab_q0[q]);
 
         bool failed = false;
@@ -270,97 +359,108 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
                 else zv = __ldg(la.z + (i_d * la.n_t + j) * img.nz + zi);
                 S[(img.ctrl_slot + c) * BLOCK] = zv;
             }
-            run_tape<1>(vm, code_elem, img.n_elem);
+            run_narrow_tape(S, cpool, code_elem, img.n_elem);
 
-            // Newton start: every collocation point at the element's initial state
+            // Newton start: the previous element's collocation cubic extrapolated into this one
+            // (first element / predictor off: the element's initial state)
+            double xv[3][NS];
+            if (e > 0 && img.predictor) {
+#pragma unroll
+                for (int n = 0; n < NS; ++n) {
+                    const double p1 = Xs[(3 * n + 0) * BLOCK], p2 = Xs[(3 * n + 1) * BLOCK];
+#pragma unroll
+                    for (int jj = 0; jj < 3; ++jj) {
+                        double v = img.ext[4 * jj] * xs_old[n];
+                        v = fma(img.ext[4 * jj + 1], p1, v);
+                        v = fma(img.ext[4 * jj + 2], p2, v);
+                        v = fma(img.ext[4 * jj + 3], xs[n], v);
+                        xv[jj][n] = v;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int n = 0; n < NS; ++n) xv[0][n] = xv[1][n] = xv[2][n] = xs[n];
+            }
 #pragma unroll
             for (int n = 0; n < NS; ++n) {
-                Xs[(3 * n + 0) * BLOCK] = xprev[n];
-                Xs[(3 * n + 1) * BLOCK] = xprev[n];
-                Xs[(3 * n + 2) * BLOCK] = xprev[n];
+                Xs[(3 * n + 0) * BLOCK] = xv[0][n];
+                Xs[(3 * n + 1) * BLOCK] = xv[1][n];
+                Xs[(3 * n + 2) * BLOCK] = xv[2][n];
             }
-            bool conv = false;
-            for (int it = 0; it < img.max_it; ++it) {
-                run_tape<3>(vm, code_pt, img.n_pt);
 
-                double M[N][N], r[N], xv[3][NS];
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                    for (int n = 0; n < NS; ++n) xv[kk][n] = Xs[(3 * n + kk) * BLOCK];
+            bool conv = false, stop = false;
+            double s_prev = 0.0;                          // no rate estimate before the second step
+            for (int it = 0;; ++it) {
+                if (stop && !final_eval) break;
+                run_point_tape(reinterpret_cast<char*>(S), img.n_pt);     // f, df/dx, fq at the 3 points
+                if (stop) break;
+
+                double M[N][N], r[N];
 #pragma unroll
                 for (int jj = 0; jj < 3; ++jj) {
 #pragma unroll
                     for (int n = 0; n < NS; ++n) {
-                        double lin = img.adot[jj + 1] * xprev[n];                    // adot[0][jj+1]
+                        double lin = img.adot[jj + 1] * xs[n];                       // adot[0][jj+1]
 #pragma unroll
                         for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
                         r[jj * NS + n] = fma(h, Fs[(3 * n + jj) * BLOCK], -lin);
 #pragma unroll
                         for (int kk = 0; kk < 3; ++kk)
 #pragma unroll
-                            for (int m = 0; m < NS; ++m)
-                                M[jj * NS + n][kk * NS + m] = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
+                            for (int m = 0; m < NS; ++m) {
+                                const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
+                                M[jj * NS + n][kk * NS + m] =
+                                    (kk == jj) ? fma(-h, Js[(3 * (n * NS + m) + jj) * BLOCK], a) : a;
+                            }
                     }
                 }
-#pragma unroll
-                for (int n = 0; n < NS; ++n)
-#pragma unroll
-                    for (int m = 0; m < NS; ++m)
-                        if ((img.j_mask >> (n * NS + m)) & 1u) {
-#pragma unroll
-                            for (int jj = 0; jj < 3; ++jj)
-                                M[jj * NS + n][jj * NS + m] =
-                                    fma(-h, Js[(3 * (n * NS + m) + jj) * BLOCK], M[jj * NS + n][jj * NS + m]);
-                        }
 
                 lu_solve_inplace<N>(M, r);
 
-                double dmax = 0.0, xmax = 1.0;
+                double s = 0.0, sc = 0.0;
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk)
 #pragma unroll
                     for (int n = 0; n < NS; ++n) {
                         const double dx = r[kk * NS + n];
                         const double xn = xv[kk][n] + dx;
+                        xv[kk][n] = xn;
                         Xs[(3 * n + kk) * BLOCK] = xn;
-                        dmax = fmax(dmax, fabs(dx));
-                        xmax = fmax(xmax, fabs(xn));
-                        if (kk == 2) xv[2][n] = xn;
+                        s = fma(dx, dx, s);
+                        sc = fma(xn, xn, sc);
                     }
                 if (!conv) ++my_iters;
-                const bool bad = !(dmax <= DBL_MAX);          // inf or nan
+                ++cnt_warp_iters;
+                // stop when the step is below tolerance, or when the contraction rate seen so far
+                // bounds the remaining error below it:  |dx_k|^2 / |dx_{k-1}| <= rtol * |X|
+                const double lim = img.rtol2 * fmax(sc, 1.0);
+                const bool bad = !(s <= DBL_MAX);                        // inf or nan
+                const bool ok = (s <= lim) || (s * s <= lim * s_prev && s <= 0.01 * s_prev);
+                s_prev = s;
                 if (bad) failed = true;
-                if (bad || dmax <= img.rtol * xmax) conv = true;
-                cnt_warp_iters += 32;
-                if (__all_sync(0xffffffffu, conv)) {
-#pragma unroll
-                    for (int n = 0; n < NS; ++n) xprev[n] = xv[2][n];
-                    break;
-                }
-                if (it == img.max_it - 1) {
-#pragma unroll
-                    for (int n = 0; n < NS; ++n) xprev[n] = xv[2][n];
-                }
+                if (ok || bad) conv = true;
+                stop = __all_sync(0xffffffffu, conv) || (it + 1 >= img.max_it);
             }
             if (!conv) failed = true;
 
             // quadrature states: x_q += h * sum_j bw_j fq(x_j) at the converged points
-            if (img.nq > 0) {
-                if (img.fq_state_dep) run_tape<3>(vm, code_pt, img.n_pt);
-                for (int q = 0; q < img.nq; ++q) {
-                    double acc = img.bw[0] * FQs[(3 * q + 0) * BLOCK];
-                    acc = fma(img.bw[1], FQs[(3 * q + 1) * BLOCK], acc);
-                    acc = fma(img.bw[2], FQs[(3 * q + 2) * BLOCK], acc);
-                    S[(img.qe_slot + q) * BLOCK] = fma(h, acc, S[(img.qe_slot + q) * BLOCK]);
-                }
+            for (int q = 0; q < img.nq; ++q) {
+                double acc = img.bw[0] * FQs[(3 * q + 0) * BLOCK];
+                acc = fma(img.bw[1], FQs[(3 * q + 1) * BLOCK], acc);
+                acc = fma(img.bw[2], FQs[(3 * q + 2) * BLOCK], acc);
+                S[(img.qe_slot + q) * BLOCK] = fma(h, acc, S[(img.qe_slot + q) * BLOCK]);
+            }
+#pragma unroll
+            for (int n = 0; n < NS; ++n) {
+                xs_old[n] = xs[n];
+                xs[n] = xv[2][n];
             }
         }
 
         // ---- CQAs, indicator, outputs ----
 #pragma unroll
-        for (int n = 0; n < NS; ++n) S[(img.xe_slot + n) * BLOCK] = xprev[n];
-        run_tape<1>(vm, code_g, img.n_g);
+        for (int n = 0; n < NS; ++n) S[(img.xe_slot + n) * BLOCK] = xs[n];
+        run_narrow_tape(S, cpool, code_g, img.n_g);
         bool feasible = !failed;
         for (int c = 0; c < img.ng; ++c) {
             double gv = vm_ld(vm, tab_g[c]);
@@ -381,17 +481,17 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
         }
         __syncthreads();
         if (tid == 0) {
-            double s = 0.0;
+            double sum = 0.0;
 #pragma unroll
-            for (int i = 0; i < BLOCK / 32; ++i) s += red[i];
-            la.partial[t] = s;
+            for (int i = 0; i < BLOCK / 32; ++i) sum += red[i];
+            la.partial[t] = sum;
         }
     }
 
     // ---- counters: one atomic per warp ----
     if (la.counters) {
-        const unsigned it_lo = warp_sum_u32((unsigned)cnt_iters);   // < 2^32 per CTA lifetime at these sizes
-        const unsigned wi = warp_sum_u32((unsigned)(cnt_warp_iters / 32));
+        const unsigned it_lo = warp_sum_u32((unsigned)cnt_iters);
+        const unsigned wi = warp_sum_u32(cnt_warp_iters);
         const unsigned fl = warp_sum_u32(cnt_failed);
         const unsigned dn = warp_sum_u32(cnt_done);
         if (lane == 0) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <math.h>
 #include <string.h>
 
 #include <string>
@@ -43,6 +44,7 @@ struct Model {
     void* d_code = nullptr;
     void* d_consts = nullptr;
     void* d_tabs = nullptr;
+    std::vector<uint32_t> xpt;          // pre-decoded point tape (16 words per instruction)
     unsigned long long* d_counters = nullptr;
     double* d_partial = nullptr;
     size_t partial_cap = 0;
@@ -127,7 +129,7 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
         secs.push_back(s);
     }
     const char* need[] = {"HEAD", "DBLS", "CNST", "ADOT", "BWTS", "BIGM", "ZFIX", "TPRO", "TELM", "TPNT",
-                          "TGEE", "RX0_", "RQ0_", "RZ__", "RG__", "CMAP"};
+                          "TGEE", "RPAR", "RX0_", "RQ0_", "RZ__", "RG__", "CMAP"};
     for (const char* t : need)
         if (!find(secs, t)) return fail(PYDSB_ERR_INVALID, std::string("blob lacks section ") + t);
     const Section* head = find(secs, "HEAD");
@@ -139,31 +141,73 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
     ExecImage& g = m->img;
     g.ns = H[0]; g.nq = H[1]; g.ng = H[2]; g.d_dim = H[3]; g.p_dim = H[4]; g.nz = H[5]; g.nfe = H[6];
     const int ncp = H[7];
-    g.nce = H[8]; g.n_units = H[9]; g.param_slot = H[10]; g.ctrl_slot = H[11]; g.xe_slot = H[12];
-    g.qe_slot = H[13]; g.x_slot = H[14]; g.max_it = H[15]; g.f_slot = H[16]; g.j_slot = H[17];
-    g.fq_slot = H[18]; g.j_mask = H[19]; g.fq_state_dep = H[20];
+    g.nce = H[8]; g.n_units = H[9]; g.ctrl_slot = H[10]; g.xe_slot = H[11]; g.qe_slot = H[12];
+    g.x_slot = H[13]; g.max_it = H[14]; g.f_slot = H[15]; g.j_slot = H[16]; g.fq_slot = H[17];
+    g.j_mask = H[18]; g.fq_state_dep = H[19]; g.predictor = H[20];
     if (ncp != 3) { delete m; return fail(PYDSB_ERR_UNSUPPORTED, "kernels are built for ncp = 3 (Radau)"); }
     if (!kernel_for(g.ns)) {
         delete m;
         return fail(PYDSB_ERR_UNSUPPORTED, "register-resident Newton kernels cover 1..3 dynamic states");
     }
     if (g.ng < 1 || g.nfe < 1 || g.p_dim < 1 || g.d_dim < 0) { delete m; return fail(PYDSB_ERR_INVALID, "bad dimensions"); }
-    g.rtol = reinterpret_cast<const double*>(find(secs, "DBLS")->data)[0];
+    {
+        const double rtol = reinterpret_cast<const double*>(find(secs, "DBLS")->data)[0];
+        g.rtol2 = rtol * rtol;
+    }
     const Section* adot = find(secs, "ADOT");
     const Section* bw = find(secs, "BWTS");
     if (adot->count != 16 || bw->count != 3) { delete m; return fail(PYDSB_ERR_INVALID, "bad collocation tables"); }
     memcpy(g.adot, adot->data, 16 * sizeof(double));
     memcpy(g.bw, bw->data, 3 * sizeof(double));
+    {
+        // extrapolation weights of the previous element's cubic: l_k(1 + tau_j), nodes tau from ADOT's
+        // generator (Radau-3: 0, (4 -+ sqrt 6)/10, 1)
+        const long double s6 = sqrtl(6.0L);
+        const long double tau[4] = {0.0L, (4.0L - s6) / 10.0L, (4.0L + s6) / 10.0L, 1.0L};
+        for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 4; ++k) {
+                long double v = 1.0L;
+                for (int l = 0; l < 4; ++l)
+                    if (l != k) v *= (1.0L + tau[j + 1] - tau[l]) / (tau[k] - tau[l]);
+                g.ext[4 * j + k] = (double)v;
+            }
+    }
 
     const Section *tp = find(secs, "TPRO"), *te = find(secs, "TELM"), *tn = find(secs, "TPNT"), *tg = find(secs, "TGEE");
     g.n_pro = tp->count; g.n_elem = te->count; g.n_pt = tn->count; g.n_g = tg->count;
     std::vector<uint64_t> code;
-    for (const Section* s : {tp, te, tn, tg}) {
+    for (const Section* s : {tp, te, tg}) {
         const uint64_t* c = reinterpret_cast<const uint64_t*>(s->data);
         code.insert(code.end(), c, c + s->count);
     }
     for (uint64_t w : code)
         if ((w & 0xFF) >= OP_COUNT) { delete m; return fail(PYDSB_ERR_INVALID, "unknown opcode in tape"); }
+    // pre-decode the point tape: per operand the byte offsets of the three collocation points
+    if (g.n_pt > MAX_PT) { delete m; return fail(PYDSB_ERR_UNSUPPORTED, "point tape longer than the constant-bank window"); }
+    {
+        const uint64_t* c = reinterpret_cast<const uint64_t*>(tn->data);
+        m->xpt.assign((size_t)16 * (g.n_pt > 0 ? g.n_pt : 1), 0u);
+        for (int i = 0; i < g.n_pt; ++i) {
+            const uint64_t w = c[i];
+            const unsigned op = (unsigned)(w & 0xFF);
+            const unsigned refs[4] = {(unsigned)(w >> 8) & 0x3FFFu, (unsigned)(w >> 22) & 0x3FFFu,
+                                      (unsigned)(w >> 36) & 0x3FFFu, (unsigned)(w >> 50) & 0x3FFFu};
+            if (op >= OP_BC3) { delete m; return fail(PYDSB_ERR_INVALID, "opcode not allowed in the point tape"); }
+            const int nops = (op == OP_FMA || op == OP_FMS || op == OP_FNMA) ? 3
+                             : (op == OP_ADD || op == OP_SUB || op == OP_MUL || op == OP_DIV || op == OP_POW ||
+                                op == OP_MIN || op == OP_MAX) ? 2 : 1;
+            uint32_t* x = &m->xpt[(size_t)16 * i];
+            x[0] = op;
+            for (int k = 0; k <= nops; ++k) {
+                const unsigned r = refs[k];
+                if (r & REF_CONST) { delete m; return fail(PYDSB_ERR_INVALID, "constant operand in the point tape"); }
+                if ((int)(r & REF_MASK) + 2 >= g.n_units + 2 && (r & REF_WIDE)) { delete m; return fail(PYDSB_ERR_INVALID, "slot out of range"); }
+                for (int p3 = 0; p3 < 3; ++p3)
+                    x[1 + 3 * k + p3] = ((r & REF_MASK) + ((r & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
+            }
+            if (!(refs[0] & REF_WIDE)) { delete m; return fail(PYDSB_ERR_INVALID, "point tape writes a narrow slot"); }
+        }
+    }
     const Section* cn = find(secs, "CNST");
     g.n_const = cn->count;
 
@@ -175,8 +219,8 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
         tabs.insert(tabs.end(), v, v + n);
         return true;
     };
-    bool ok = push("RX0_", g.ns) && push("RQ0_", g.nq) && push("RZ__", g.nz) && push("ZFIX", g.nz) &&
-              push("RG__", g.ng) && push("CMAP", (size_t)g.nfe * g.nce);
+    bool ok = push("RPAR", (size_t)g.d_dim + g.p_dim) && push("RX0_", g.ns) && push("RQ0_", g.nq) && push("RZ__", g.nz) &&
+              push("ZFIX", g.nz) && push("RG__", g.ng) && push("CMAP", (size_t)g.nfe * g.nce);
     if (!ok) { delete m; return fail(PYDSB_ERR_INVALID, "reference table shorter than its dimension"); }
     g.n_tabs = (int)tabs.size();
 
@@ -185,7 +229,7 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
     g.off_code = o; o += (int)code.size() * 8;
     g.off_const = o; o += (g.n_const + 1) * 8;
     g.off_tabs = o; o = align_up(o + g.n_tabs * 2, 128);
-    g.off_land = o; o = align_up(o + 2 * BLOCK * g.p_dim * 8, 128);
+    g.off_land = o; o = align_up(o + BLOCK * g.p_dim * 8, 128);
     g.off_slots = o; o += g.n_units * BLOCK * 8;
     g.smem_bytes = o;
 
@@ -288,8 +332,10 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
     const long long max_ctas = (long long)m->num_sms * m->blocks_per_sm;
     const int grid = (int)(total < max_ctas ? total : max_ctas);
     KernelFn fn = kernel_for(m->img.ns);
-    // several models may share one template instantiation: (re)assert this model's smem size
+    // several models may share one template instantiation: (re)assert this model's smem size and
+    // (re)load its point tape into the constant bank (stream ordered)
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, m->img.smem_bytes));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_pt, m->xpt.data(), m->xpt.size() * sizeof(uint32_t), 0, cudaMemcpyHostToDevice, st));
     fn<<<grid, BLOCK, m->img.smem_bytes, st>>>(m->img, la);
     CUDA_TRY(cudaGetLastError());
     m->launches += 1;

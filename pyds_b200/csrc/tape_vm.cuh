@@ -59,16 +59,15 @@ __device__ __forceinline__ double vm_ld(const VM& vm, unsigned ref)
     return *o.p;
 }
 
-// Fast reciprocal: MUFU.RCP64H seed + two Newton steps (<= 1 ulp for normal inputs).
+// Pivot reciprocal for the Newton LU: MUFU.RCP64H seed (20 bits) + two Newton steps with the
+// second one folded (y*(1+e+e^2) form): relative error ~2^-60 before rounding.
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
+    const double e = fma(-x, y, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(y, e2, y);
 }
 
 #define PYDSB_UNARY(expr)                                                        \

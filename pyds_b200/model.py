@@ -51,13 +51,14 @@ class _Control:
 
 
 class DaeModel:
-    def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-10, newton_max_it=25):
+    def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-12, newton_max_it=25, predictor=False):
         self.graph = T.Graph()
         self.d_names = list(d_names)
         self.p_names = list(p_names)
         self.nfe, self.ncp = int(nfe), int(ncp)
         self.newton_rtol = float(newton_rtol)
         self.newton_max_it = int(newton_max_it)
+        self.predictor = bool(predictor)        # start Newton from the extrapolated previous element
         self.states: list[_State] = []
         self.controls: list[_Control] = []
         self.constraints = []          # (name, Expr (<= 0 feasible), bigM)
@@ -203,8 +204,10 @@ class DaeModel:
             secs.append((tag, dtype, arr))
 
         sec("HEAD", "u32", [ns, nq, ng, len(self.d_names), len(self.p_names), nz, self.nfe, self.ncp, nce,
-                            lay.n_units, lay.param_slot, lay.ctrl_slot, lay.xe_slot, lay.qe_slot, lay.x_slot,
-                            self.newton_max_it, lay.f_slot, lay.j_slot, lay.fq_slot, lay.j_mask, lay.fq_state_dep])
+                            lay.n_units, lay.ctrl_slot, lay.xe_slot, lay.qe_slot, lay.x_slot, self.newton_max_it,
+                            lay.f_slot, lay.j_slot, lay.fq_slot, lay.j_mask, lay.fq_state_dep,
+                            1 if self.predictor else 0])
+        sec("RPAR", "u16", lay.param_slots)
         sec("DBLS", "f64", [self.newton_rtol])
         sec("CNST", "f64", low.consts if len(low.consts) else [0.0])
         sec("ADOT", "f64", adot)

@@ -332,12 +332,12 @@ def topo_order(roots):
 # ---------------------------------------------------------------------------------------------
 @dataclass
 class TapeLayout:
-    """Slot assignment shared between the lowering and the kernel."""
+    """Slot assignment shared between the lowering and the kernel (units of one double per thread)."""
     n_param: int
     n_ctrl_elem: int
     ns: int
     nq: int
-    param_slot: int = 0
+    param_slots: list = field(default_factory=list)   # slot of every parameter (d first, then theta)
     ctrl_slot: int = 0
     xe_slot: int = 0
     qe_slot: int = 0
@@ -362,6 +362,7 @@ class LoweredTapes:
 _BINOPS = {"add": "ADD", "sub": "SUB", "mul": "MUL", "div": "DIV", "pow": "POW", "min": "MIN", "max": "MAX"}
 _UNOPS = {"neg": "NEG", "sqr": "SQR", "rcp": "RCP", "exp": "EXP", "log": "LOG", "sqrt": "SQRT", "sin": "SIN",
           "cos": "COS", "tanh": "TANH", "abs": "ABS"}
+_FMA_OPS = ("FMA", "FMS", "FNMA")
 
 
 def encode(op, dst, a=0, b=0, c=0):
@@ -374,75 +375,75 @@ def decode(word):
 
 
 class _SlotPool:
-    def __init__(self, first, width):
-        self.next = first
-        self.free = []
+    """Linear-scan slot allocator over a list of free units (optionally growing at the end)."""
+
+    def __init__(self, width, free=None, grow_from=None):
         self.width = width
+        self.free = list(free or [])
+        self.next = grow_from
+        self.high = grow_from if grow_from is not None else 0
 
     def take(self):
         if self.free:
-            return self.free.pop()
+            return self.free.pop(0)
+        if self.next is None:
+            raise RuntimeError("slot pool exhausted")
         s = self.next
         self.next += self.width
+        self.high = self.next
         return s
 
     def give(self, s):
-        self.free.append(s)
+        self.free.insert(0, s)
 
 
 def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int = 3) -> LoweredTapes:
     """Lower root expressions to the four tapes.
 
     ``roots`` maps a table name to a list of :class:`Expr` (or ``None`` for "absent"), e.g.
-    ``{"x0": [...ns], "z": [...nz], "f": [...ns], "J": [...ns*ns], "fq": [...nq], "g": [...ng]}``.
-    A table may only contain nodes up to the level its consumer can see: x0/z <= PARAM,
-    f/J/fq/fz <= STATE, g and its derivatives <= END.
+    ``{"x0": [...ns], "q0": [...nq], "z": [...nz], "f": [...ns], "J": [...ns*ns], "fq": [...nq], "g": [...ng]}``.
+    A table may only contain nodes up to the level its consumer can see: x0/q0/z <= PARAM,
+    f/J/fq <= STATE, g <= END.
+
+    Register-file layout (one unit = one double per thread)::
+
+        [ persistent narrow: live parameters | ctrl | xe | qe | constants used by the point tape |
+          pro / elem values consumed by later tapes ]
+        [ wide: X | F | J | FQ | point-tape temporaries ]              (3 units per value)
+
+    Short-lived values -- parameters read only by the prologue, prologue temporaries, g-tape
+    temporaries -- are overlaid on wide units that are dead while they live (X and the point
+    temporaries before the first element; everything wide after the last element), which keeps
+    the file small enough for 4 CTAs per SM.
     """
     if ncp != 3:
         raise NotImplementedError("the kernel evaluates the point tape 3-wide (ncp = 3)")
+    dense_names = ("f", "J", "fq")
     all_roots = [e for lst in roots.values() for e in lst if e is not None]
     order = topo_order(all_roots)
 
-    # users per node, for FMA fusion and liveness
     users = {}
     for n in order:
         for a in n.args:
             users.setdefault(a.id, []).append(n)
     root_ids = {e.id for e in all_roots}
 
-    # constant pool -----------------------------------------------------------------------------
-    const_index = {}
-    consts = []
+    # ---- constant pool ---------------------------------------------------------------------------
+    const_index, consts = {}, []
 
     def cref(v):
         key = struct.pack("<d", float(v))
         i = const_index.get(key)
         if i is None:
             i = len(consts)
-            if i > REF_MASK:
-                raise ValueError("constant pool overflow (4096 entries)")
+            if i >= REF_MASK:
+                raise ValueError("constant pool overflow")
             const_index[key] = i
             consts.append(float(v))
         return REF_CONST | i
 
-    # fixed input slots ---------------------------------------------------------------------------
-    lay = TapeLayout(n_param=n_param, n_ctrl_elem=n_ctrl_elem, ns=ns, nq=nq)
-    cur = 0
-    lay.param_slot = cur; cur += n_param
-    lay.ctrl_slot = cur; cur += n_ctrl_elem
-    lay.xe_slot = cur; cur += ns
-    lay.qe_slot = cur; cur += nq
-    lay.x_slot = cur; cur += 3 * ns
-    lay.f_slot = cur; cur += 3 * ns
-    lay.j_slot = cur; cur += 3 * ns * ns
-    lay.fq_slot = cur; cur += 3 * nq
-
-    level_tape = {LEVEL_PARAM: "pro", LEVEL_CTRL: "elem", LEVEL_STATE: "pt", LEVEL_END: "g"}
-    sched = {"pro": [], "elem": [], "pt": [], "g": []}
-
-    # FMA fusion: add/sub with a single-use mul of the same level -------------------------------
-    fused_into = {}     # mul node id -> consumer id
-    fma_form = {}       # consumer id -> (opname, a, b, c)
+    # ---- FMA fusion: add/sub with a single-use mul of the same level --------------------------------
+    fused_into, fma_form = {}, {}
     for n in order:
         if n.op not in ("add", "sub") or n.level == LEVEL_CONST:
             continue
@@ -450,52 +451,33 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
         cand = None
         if l.op == "mul" and len(users.get(l.id, [])) == 1 and l.id not in root_ids and l.level == n.level \
                 and l.id not in fused_into:
-            cand = ("FMA" if n.op == "add" else "FMS", l, r)           # l*.. + r   |  l*.. - r
+            cand = ("FMA" if n.op == "add" else "FMS", l, r)
         elif r.op == "mul" and len(users.get(r.id, [])) == 1 and r.id not in root_ids and r.level == n.level \
                 and r.id not in fused_into:
-            cand = ("FMA" if n.op == "add" else "FNMA", r, l)          # r*.. + l   |  l - r*..
+            cand = ("FMA" if n.op == "add" else "FNMA", r, l)
         if cand is not None:
             opn, m, other = cand
             fused_into[m.id] = n.id
             fma_form[n.id] = (opn, m.args[0], m.args[1], other)
 
+    level_tape = {LEVEL_PARAM: "pro", LEVEL_CTRL: "elem", LEVEL_STATE: "pt", LEVEL_END: "g"}
+    sched = {"pro": [], "elem": [], "pt": [], "g": []}
     for n in order:
         if n.level == LEVEL_CONST or not n.args or n.id in fused_into:
             continue
         sched[level_tape[n.level]].append(n)
 
     def eff_args(n):
-        if n.id in fma_form:
-            return fma_form[n.id][1:]
-        return n.args
+        return fma_form[n.id][1:] if n.id in fma_form else n.args
 
-    # liveness: a value is "persistent" if it is a root or consumed by a later tape ---------------
-    tape_of = {}
-    for name, lst in sched.items():
-        for n in lst:
-            tape_of[n.id] = name
-    persistent = set(root_ids)
-    last_use = {}
-    for name, lst in sched.items():
-        for pos, n in enumerate(lst):
-            for a in eff_args(n):
-                if a.id in tape_of:
-                    if tape_of[a.id] != name:
-                        persistent.add(a.id)
-                    else:
-                        last_use[a.id] = pos
-
-    slot_of = {}
-
-    # dense, pinned outputs of the point tape: f, J, fq land at fixed wide slots so that the
-    # compiled Newton code reads them with immediate offsets.  Lower-level roots (constants,
-    # parameter- or control-level values) are broadcast into their slot by the pro / elem tape.
-    pinned = {}                 # node id -> REF_WIDE|slot of its first pinned destination
-    extra = {"pro": [], "elem": [], "pt": []}      # (opname, dst, src node) appended after the tape body
-    dense = [("f", lay.f_slot), ("J", lay.j_slot), ("fq", lay.fq_slot)]
-    for tname, base in dense:
+    # ---- dense pinned outputs of the point tape ----------------------------------------------------
+    lay = TapeLayout(n_param=n_param, n_ctrl_elem=n_ctrl_elem, ns=ns, nq=nq)
+    pinned = {}                                  # node id -> wide unit of its first pinned destination
+    extra = {"pro": [], "elem": [], "pt": []}    # (opname, dst unit | REF_WIDE, src node)
+    dense_rel = {"f": 0, "J": 3 * ns, "fq": 3 * ns + 3 * ns * ns}      # relative to f_slot
+    for tname in dense_names:
         for i, e in enumerate(roots.get(tname, [])):
-            dst = REF_WIDE | (base + 3 * i)
+            rel = dense_rel[tname] + 3 * i
             if tname == "J" and e is not None and not e.is_const(0.0):
                 lay.j_mask |= 1 << i
             if e is None:
@@ -503,67 +485,156 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
             if tname == "fq" and e.level == LEVEL_STATE:
                 lay.fq_state_dep = 1
             if e.level == LEVEL_STATE and e.args and e.id not in pinned:
-                pinned[e.id] = dst
+                pinned[e.id] = rel
             elif e.level == LEVEL_STATE:
-                extra["pt"].append(("MOV", dst, e))
+                extra["pt"].append(("MOV", rel, e))
             elif e.level == LEVEL_CTRL:
-                extra["elem"].append(("BC3", dst, e))
+                extra["elem"].append(("BC3", rel, e))
             else:
-                extra["pro"].append(("BC3", dst, e))
-    dense_names = {t for t, _ in dense}
+                extra["pro"].append(("BC3", rel, e))
 
-    def leaf_ref(n):
-        if n.op == "const": return cref(n.value)
-        if n.op == "param": return lay.param_slot + n.value
+    # ---- who reads what, and where ------------------------------------------------------------------
+    tape_of = {n.id: name for name, lst in sched.items() for n in lst}
+    read_in = {}                                  # node id -> set of tape names that read it
+    for name, lst in sched.items():
+        for n in lst:
+            for a in eff_args(n):
+                read_in.setdefault(a.id, set()).add(name)
+    for name, lst in extra.items():
+        for _, _, src in lst:
+            read_in.setdefault(src.id, set()).add(name)
+    table_read = set()                            # read by the kernel itself through a reference table
+    for tname, lst in roots.items():
+        if tname in dense_names:
+            continue
+        for e in lst:
+            if e is not None:
+                table_read.add(e.id)
+
+    def persistent(n):
+        """Must keep its value beyond the tape that produces it (parameters: beyond the prologue)."""
+        if n.id in table_read:
+            return True
+        home = tape_of.get(n.id, "pro")           # leaves of parameter level behave like pro values
+        return bool(read_in.get(n.id, set()) - {home})
+
+    # ---- persistent narrow region -------------------------------------------------------------------
+    cur = 0
+    slot_of = {}
+    params = [graph.param(i) for i in range(n_param)]
+    lay.param_slots = [None] * n_param
+    for i, pn in enumerate(params):
+        if persistent(pn):
+            lay.param_slots[i] = cur; cur += 1
+    lay.ctrl_slot = cur; cur += n_ctrl_elem
+    lay.xe_slot = cur; cur += ns
+    lay.qe_slot = cur; cur += nq
+    # constants used as operands by the point tape get a per-thread slot (filled by the prologue) so
+    # that every operand of the hot tape is addressed the same way
+    const_slot = {}
+    for n in sched["pt"]:
+        for a in eff_args(n):
+            if a.op == "const":
+                key = struct.pack("<d", a.value)
+                if key not in const_slot:
+                    const_slot[key] = cur; cur += 1
+                    extra["pro"].append(("MOV", None, a))          # dst patched below
+    for name in ("pro", "elem"):
+        for n in sched[name]:
+            if persistent(n) or name == "elem":
+                slot_of[n.id] = cur; cur += 1
+
+    # ---- wide region ---------------------------------------------------------------------------------
+    lay.x_slot = cur; cur += 3 * ns
+    lay.f_slot = cur
+    lay.j_slot = lay.f_slot + 3 * ns
+    lay.fq_slot = lay.j_slot + 3 * ns * ns
+    cur = lay.fq_slot + 3 * nq
+    wide_fixed_end = cur
+
+    def leaf_ref(n, in_pt=False):
+        if n.op == "const":
+            if in_pt:
+                return const_slot[struct.pack("<d", n.value)]
+            return cref(n.value)
+        if n.op == "param": return lay.param_slots[n.value]
         if n.op == "ctrl": return lay.ctrl_slot + n.value
         if n.op == "xe": return lay.xe_slot + n.value
         if n.op == "qe": return lay.qe_slot + n.value
         if n.op == "x": return REF_WIDE | (lay.x_slot + 3 * n.value)
         raise KeyError(n.op)
 
-    def ref(n):
+    def assign(name, lst, pool, wide):
+        """Linear-scan assignment for the not-yet-placed nodes of one tape."""
+        last_use = {}
+        for pos, n in enumerate(lst):
+            for a in eff_args(n):
+                last_use[a.id] = pos
+        for _, _, src in extra.get(name, []):             # trailing MOV/BC3 read their source at the end
+            last_use[src.id] = len(lst)
+        release_at = {}
+        for pos, n in enumerate(lst):
+            for s in release_at.pop(pos, []):
+                pool.give(s)
+            if n.id in slot_of:
+                continue
+            if wide and n.id in pinned:
+                slot_of[n.id] = REF_WIDE | (lay.f_slot + pinned[n.id])
+                continue
+            s = pool.take()
+            slot_of[n.id] = (REF_WIDE | s) if wide else s
+            if n.id not in table_read:                     # values the kernel reads afterwards stay put
+                release_at.setdefault(last_use.get(n.id, pos) + 1, []).append(s)
+
+    pt_pool = _SlotPool(3, grow_from=cur)
+    assign("pt", sched["pt"], pt_pool, True)
+    cur = max(cur, pt_pool.high)
+    pt_temp_units = list(range(wide_fixed_end, cur))
+
+    # scratch for the prologue: X units and point temporaries (dead until the first element starts)
+    x_units = list(range(lay.x_slot, lay.x_slot + 3 * ns))
+    pro_pool = _SlotPool(1, free=x_units + pt_temp_units, grow_from=cur)
+    # parameters that only the prologue reads are loaded straight into scratch units
+    for i, pn in enumerate(params):
+        if lay.param_slots[i] is None:
+            lay.param_slots[i] = pro_pool.take()
+    assign("pro", sched["pro"], pro_pool, False)
+    cur = max(cur, pro_pool.high)
+    # scratch for the g tape: the whole wide region is dead after the last element
+    g_pool = _SlotPool(1, free=list(range(lay.x_slot, cur)), grow_from=cur)
+    assign("g", sched["g"], g_pool, False)
+    cur = max(cur, g_pool.high)
+    if cur - 1 > REF_MASK:
+        raise ValueError("register file overflow (4096 slots)")
+    lay.n_units = cur
+
+    # ---- emit ------------------------------------------------------------------------------------------
+    def ref(n, in_pt=False):
         if not n.args:
-            return leaf_ref(n)
+            return leaf_ref(n, in_pt)
         return slot_of[n.id]
 
     code = {}
-    narrow_next = cur
-    # narrow tapes first (pro, elem, g), then wide (pt) so that wide slots are contiguous at the end
-    for name in ("pro", "elem", "g", "pt"):
-        wide = name == "pt"
-        pool = _SlotPool(narrow_next, 3 if wide else 1)
+    for name in ("pro", "elem", "pt", "g"):
+        in_pt = name == "pt"
         words = []
-        lst = sched[name]
-        release_at = {}
-        for pos, n in enumerate(lst):
-            # free the slots whose last use was an earlier instruction
-            for s in release_at.pop(pos, []):
-                pool.give(s)
-            args = eff_args(n)
-            if n.id in pinned:
-                slot_of[n.id] = pinned[n.id]
-            else:
-                s = pool.take()
-                slot_of[n.id] = (REF_WIDE | s) if wide else s
-            if n.id not in persistent and n.id not in pinned:
-                lu = last_use.get(n.id, pos)
-                release_at.setdefault(lu + 1, []).append(s)
+        for n in sched[name]:
+            dst = slot_of[n.id]
             if n.id in fma_form:
                 opn, a, b, c = fma_form[n.id]
-                words.append(encode(opn, slot_of[n.id], ref(a), ref(b), ref(c)))
+                words.append(encode(opn, dst, ref(a, in_pt), ref(b, in_pt), ref(c, in_pt)))
             elif n.op in _BINOPS:
-                words.append(encode(_BINOPS[n.op], slot_of[n.id], ref(args[0]), ref(args[1])))
+                words.append(encode(_BINOPS[n.op], dst, ref(n.args[0], in_pt), ref(n.args[1], in_pt)))
             elif n.op in _UNOPS:
-                words.append(encode(_UNOPS[n.op], slot_of[n.id], ref(args[0])))
+                words.append(encode(_UNOPS[n.op], dst, ref(n.args[0], in_pt)))
             else:
                 raise NotImplementedError(n.op)
-        for opn, dst, src in extra.get(name, []):
-            words.append(encode(opn, dst, ref(src)))
+        for opn, rel, src in extra.get(name, []):
+            if rel is None:                                         # constant -> per-thread slot
+                words.append(encode("MOV", const_slot[struct.pack("<d", src.value)], cref(src.value)))
+            else:
+                words.append(encode(opn, REF_WIDE | (lay.f_slot + rel), ref(src, in_pt and opn == "MOV")))
         code[name] = np.asarray(words, dtype=np.uint64)
-        narrow_next = pool.next
-    if narrow_next - 1 > REF_MASK:
-        raise ValueError("register file overflow (4096 slots)")
-    lay.n_units = narrow_next
 
     ref_tables = {}
     for name, lst in roots.items():
@@ -571,13 +642,10 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
             continue
         out = []
         for e in lst:
-            if e is None or e.is_const(0.0):
-                out.append(REF_NONE)
-            else:
-                out.append(ref(e))
+            out.append(REF_NONE if (e is None or e.is_const(0.0)) else ref(e))
         ref_tables[name] = np.asarray(out, dtype=np.uint16)
 
     stats = {k: int(len(v)) for k, v in code.items()}
-    stats["flops"] = {k: int(sum(2 if decode(w)[0] in ("FMA", "FMS", "FNMA") else (0 if decode(w)[0] == "MOV" else 1)
+    stats["flops"] = {k: int(sum(2 if decode(w)[0] in _FMA_OPS else (0 if decode(w)[0] in ("MOV", "BC3") else 1)
                                  for w in v)) for k, v in code.items()}
     return LoweredTapes(layout=lay, consts=np.asarray(consts, dtype=np.float64), code=code, refs=ref_tables, stats=stats)
