@@ -41,7 +41,7 @@ class TapeVM:
         self.sec = s
         (self.ns, self.nq, self.ng, self.d_dim, self.p_dim, self.nz, self.nfe, self.ncp, self.nce, self.n_units,
          self.ctrl_slot, self.xe_slot, self.qe_slot, self.x_slot, self.max_it,
-         self.f_slot, self.j_slot, self.fq_slot, self.j_mask, self.fq_state_dep, self.predictor) = [int(v) for v in s["HEAD"]]
+         self.j_mask, self.fq_state_dep, self.predictor) = [int(v) for v in s["HEAD"]]
         self.param_slots = [int(v) for v in s["RPAR"]]
         self.rtol = float(s["DBLS"][0])
         self.consts = s["CNST"]
@@ -145,13 +145,12 @@ class TapeVM:
                     for w in range(ncp):
                         R[self.x_slot + 3 * i + w] = X[:, w, i]
                 self._run(R, s["TPNT"], ncp)
-                f = np.stack([np.stack([R[self.f_slot + 3 * i + w] for i in range(ns)], axis=1) for w in range(ncp)], axis=1)
+                f = np.stack([np.stack([self._ld(R, r, w) * one for r in s["RF__"][:ns]], axis=1) for w in range(ncp)], axis=1)
                 J = np.zeros((S, ncp, ns, ns))
                 for w in range(ncp):
                     for r_ in range(ns):
                         for c_ in range(ns):
-                            if (self.j_mask >> (r_ * ns + c_)) & 1:
-                                J[:, w, r_, c_] = R[self.j_slot + 3 * (r_ * ns + c_) + w]
+                            J[:, w, r_, c_] = self._ld(R, s["RJ__"][r_ * ns + c_], w)
                 lin = np.einsum("kj,skn->sjn", A[1:, 1:], X) + A[0, 1:][None, :, None] * x0[:, None, :]
                 Rres = lin - h * f
                 M = np.zeros((S, ncp, ns, ncp, ns))
@@ -183,7 +182,7 @@ class TapeVM:
             for k in range(nq):
                 acc = 0.0
                 for w in range(ncp):
-                    acc = acc + self.bw[w] * R[self.fq_slot + 3 * k + w]
+                    acc = acc + self.bw[w] * self._ld(R, s["RFQ_"][k], w)
                 q[:, k] = q[:, k] + h * acc
             traj[:, e * ncp + 1:(e + 1) * ncp + 1] = X
             x0 = X[:, ncp - 1, :].copy()

@@ -34,8 +34,12 @@ struct ExecImage {
     const uint16_t* tabs;      // par[n_param] x0[ns] q0[nq] ztab[nz] zfix[nz] gtab[ng] cmap[nfe*nce]
     int n_pro, n_elem, n_pt, n_g, n_const, n_tabs;
     int ns, nq, ng, d_dim, p_dim, nz, nfe, nce, n_units;
-    int ctrl_slot, xe_slot, qe_slot, x_slot, f_slot, j_slot, fq_slot;
-    unsigned j_mask;
+    int ctrl_slot, xe_slot, qe_slot, x_slot;
+    unsigned j_mask;           // bit r*ns+c: df_r/dx_c is not structurally zero
+    unsigned f_off[3], f_str[3];       // byte offset of point 0 / byte stride between points (0 = narrow)
+    unsigned j_off[9], j_str[9];
+    unsigned fq_off[8], fq_str[8];
+    unsigned fq_mask;
     int fq_state_dep;
     int predictor;
     int max_it;
@@ -152,8 +156,29 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v)
 
 // ---------------------------------------------------------------------------------------------
 // Hot interpreter: the point tape, three collocation points per instruction, operands addressed
-// as [thread base + uniform byte offset] (LDS/STS with a uniform-register offset).
+// as [thread base + uniform byte offset] (LDS/STS with a uniform-register offset).  Sixteen dense
+// execution opcodes (XOP_*) so that the dispatch is one jump table; everything transcendental
+// goes through one out-of-line cold function.
 // ---------------------------------------------------------------------------------------------
+enum XOp : unsigned {
+    XOP_FMA = 0, XOP_FMS, XOP_FNMA, XOP_MUL, XOP_ADD, XOP_SUB, XOP_SQR, XOP_MOV, XOP_NEG, XOP_DIV, XOP_RCP,
+    XOP_ABS, XOP_MIN, XOP_MAX, XOP_NOP, XOP_COLD
+};
+
+__device__ __noinline__ double cold_op(unsigned op, double a, double b)
+{
+    switch (op) {
+    case OP_EXP: return exp(a);
+    case OP_LOG: return log(a);
+    case OP_SQRT: return sqrt(a);
+    case OP_SIN: return sin(a);
+    case OP_COS: return cos(a);
+    case OP_TANH: return tanh(a);
+    case OP_POW: return pow(a, b);
+    default: return a;
+    }
+}
+
 #define PT_LD(off) (*reinterpret_cast<const double*>(base + (off)))
 #define PT_ST(off, v) (*reinterpret_cast<double*>(base + (off)) = (v))
 #define PT_UN(expr)                                                   \
@@ -192,33 +217,29 @@ __device__ __forceinline__ void run_point_tape(char* __restrict__ base, int n)
     for (int pc = 0; pc < n; ++pc) {
         const uint4 q0 = c_pt[4 * pc];
         const uint4 q1 = c_pt[4 * pc + 1];
-        switch (q0.x) {
-        case OP_FMA: PT_TER(fma(a, b, c))
-        case OP_FMS: PT_TER(fma(a, b, -c))
-        case OP_FNMA: PT_TER(fma(-a, b, c))
-        case OP_MUL: PT_BIN(a * b)
-        case OP_ADD: PT_BIN(a + b)
-        case OP_SUB: PT_BIN(a - b)
-        case OP_SQR: PT_UN(a * a)
-        case OP_MOV: PT_UN(a)
-        case OP_NEG: PT_UN(-a)
-        case OP_DIV: PT_BIN(a / b)
-        case OP_RCP: PT_UN(1.0 / a)
-        case OP_EXP: PT_UN(exp(a))
-        case OP_LOG: PT_UN(log(a))
-        case OP_SQRT: PT_UN(sqrt(a))
-        case OP_SIN: PT_UN(sin(a))
-        case OP_COS: PT_UN(cos(a))
-        case OP_TANH: PT_UN(tanh(a))
-        case OP_POW: PT_BIN(pow(a, b))
-        case OP_ABS: PT_UN(fabs(a))
-        case OP_MIN: PT_BIN(fmin(a, b))
-        case OP_MAX: PT_BIN(fmax(a, b))
-        default: break;
+        switch (q0.x & 15u) {
+        case XOP_FMA: PT_TER(fma(a, b, c))
+        case XOP_FMS: PT_TER(fma(a, b, -c))
+        case XOP_FNMA: PT_TER(fma(-a, b, c))
+        case XOP_MUL: PT_BIN(a * b)
+        case XOP_ADD: PT_BIN(a + b)
+        case XOP_SUB: PT_BIN(a - b)
+        case XOP_SQR: PT_UN(a * a)
+        case XOP_MOV: PT_UN(a)
+        case XOP_NEG: PT_UN(-a)
+        case XOP_DIV: PT_BIN(a / b)
+        case XOP_RCP: PT_UN(1.0 / a)
+        case XOP_ABS: PT_UN(fabs(a))
+        case XOP_MIN: PT_BIN(fmin(a, b))
+        case XOP_MAX: PT_BIN(fmax(a, b))
+        case XOP_NOP: break;
+        case XOP_COLD: {
+            const unsigned op = q0.x >> 8;
+            PT_BIN(cold_op(op, a, b))
+        }
         }
     }
 }
-#undef PT_LD
 #undef PT_ST
 #undef PT_UN
 #undef PT_BIN
@@ -278,9 +299,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
     vm.cpool = cpool;
 
     double* const Xs = S + img.x_slot * BLOCK;
-    const double* const Fs = S + img.f_slot * BLOCK;
-    const double* const Js = S + img.j_slot * BLOCK;
-    const double* const FQs = S + img.fq_slot * BLOCK;
+    char* const base = reinterpret_cast<char*>(S);
 
     const double h = 1.0 / (double)img.nfe;
     const int p_dim = img.p_dim, d_dim = img.d_dim;
@@ -392,7 +411,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
             double s_prev = 0.0;                          // no rate estimate before the second step
             for (int it = 0;; ++it) {
                 if (stop && !final_eval) break;
-                run_point_tape(reinterpret_cast<char*>(S), img.n_pt);     // f, df/dx, fq at the 3 points
+                run_point_tape(base, img.n_pt);                           // f, df/dx, fq at the 3 points
                 if (stop) break;
 
                 double M[N][N], r[N];
@@ -403,14 +422,16 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
                         double lin = img.adot[jj + 1] * xs[n];                       // adot[0][jj+1]
 #pragma unroll
                         for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
-                        r[jj * NS + n] = fma(h, Fs[(3 * n + jj) * BLOCK], -lin);
+                        r[jj * NS + n] = fma(h, PT_LD(img.f_off[n] + jj * img.f_str[n]), -lin);
 #pragma unroll
                         for (int kk = 0; kk < 3; ++kk)
 #pragma unroll
                             for (int m = 0; m < NS; ++m) {
                                 const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
-                                M[jj * NS + n][kk * NS + m] =
-                                    (kk == jj) ? fma(-h, Js[(3 * (n * NS + m) + jj) * BLOCK], a) : a;
+                                M[jj * NS + n][kk * NS + m] = a;
+                                if (kk == jj && ((img.j_mask >> (n * NS + m)) & 1u))
+                                    M[jj * NS + n][kk * NS + m] =
+                                        fma(-h, PT_LD(img.j_off[n * NS + m] + jj * img.j_str[n * NS + m]), a);
                             }
                     }
                 }
@@ -445,9 +466,10 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
 
             // quadrature states: x_q += h * sum_j bw_j fq(x_j) at the converged points
             for (int q = 0; q < img.nq; ++q) {
-                double acc = img.bw[0] * FQs[(3 * q + 0) * BLOCK];
-                acc = fma(img.bw[1], FQs[(3 * q + 1) * BLOCK], acc);
-                acc = fma(img.bw[2], FQs[(3 * q + 2) * BLOCK], acc);
+                if (!((img.fq_mask >> q) & 1u)) continue;
+                double acc = img.bw[0] * PT_LD(img.fq_off[q]);
+                acc = fma(img.bw[1], PT_LD(img.fq_off[q] + img.fq_str[q]), acc);
+                acc = fma(img.bw[2], PT_LD(img.fq_off[q] + 2 * img.fq_str[q]), acc);
                 S[(img.qe_slot + q) * BLOCK] = fma(h, acc, S[(img.qe_slot + q) * BLOCK]);
             }
 #pragma unroll
@@ -502,6 +524,8 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
         }
     }
 }
+
+#undef PT_LD
 
 // Deterministic finish of the P(feasible) reduction: one thread per design point sums its tile
 // partials in tile order.

@@ -129,11 +129,11 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
         secs.push_back(s);
     }
     const char* need[] = {"HEAD", "DBLS", "CNST", "ADOT", "BWTS", "BIGM", "ZFIX", "TPRO", "TELM", "TPNT",
-                          "TGEE", "RPAR", "RX0_", "RQ0_", "RZ__", "RG__", "CMAP"};
+                          "TGEE", "RPAR", "RX0_", "RQ0_", "RZ__", "RF__", "RJ__", "RFQ_", "RG__", "CMAP"};
     for (const char* t : need)
         if (!find(secs, t)) return fail(PYDSB_ERR_INVALID, std::string("blob lacks section ") + t);
     const Section* head = find(secs, "HEAD");
-    if (head->count < 21) return fail(PYDSB_ERR_INVALID, "HEAD too short");
+    if (head->count < 18) return fail(PYDSB_ERR_INVALID, "HEAD too short");
     const uint32_t* H = reinterpret_cast<const uint32_t*>(head->data);
 
     Model* m = new Model();
@@ -142,14 +142,42 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
     g.ns = H[0]; g.nq = H[1]; g.ng = H[2]; g.d_dim = H[3]; g.p_dim = H[4]; g.nz = H[5]; g.nfe = H[6];
     const int ncp = H[7];
     g.nce = H[8]; g.n_units = H[9]; g.ctrl_slot = H[10]; g.xe_slot = H[11]; g.qe_slot = H[12];
-    g.x_slot = H[13]; g.max_it = H[14]; g.f_slot = H[15]; g.j_slot = H[16]; g.fq_slot = H[17];
-    g.j_mask = H[18]; g.fq_state_dep = H[19]; g.predictor = H[20];
+    g.x_slot = H[13]; g.max_it = H[14]; g.j_mask = H[15]; g.fq_state_dep = H[16]; g.predictor = H[17];
     if (ncp != 3) { delete m; return fail(PYDSB_ERR_UNSUPPORTED, "kernels are built for ncp = 3 (Radau)"); }
     if (!kernel_for(g.ns)) {
         delete m;
         return fail(PYDSB_ERR_UNSUPPORTED, "register-resident Newton kernels cover 1..3 dynamic states");
     }
     if (g.ng < 1 || g.nfe < 1 || g.p_dim < 1 || g.d_dim < 0) { delete m; return fail(PYDSB_ERR_INVALID, "bad dimensions"); }
+    if (g.nq > 8) { delete m; return fail(PYDSB_ERR_UNSUPPORTED, "at most 8 quadrature states"); }
+    {
+        // f / J / fq outputs of the point tape -> (offset, stride) tables read by the compiled Newton code
+        auto resolve = [&](const char* tag, int n, unsigned* off, unsigned* str, unsigned* mask) -> bool {
+            const Section* s = find(secs, tag);
+            if ((int)s->count < n) return false;
+            const uint16_t* v = reinterpret_cast<const uint16_t*>(s->data);
+            *mask = 0;
+            for (int i = 0; i < n; ++i) {
+                off[i] = 0; str[i] = 0;
+                if (v[i] == REF_NONE) continue;
+                if (v[i] & REF_CONST) return false;
+                *mask |= 1u << i;
+                off[i] = (v[i] & REF_MASK) * BLOCK * 8u;
+                str[i] = (v[i] & REF_WIDE) ? BLOCK * 8u : 0u;
+            }
+            return true;
+        };
+        unsigned fmask = 0, jmask = 0;
+        if (!resolve("RF__", g.ns, g.f_off, g.f_str, &fmask) || !resolve("RJ__", g.ns * g.ns, g.j_off, g.j_str, &jmask) ||
+            !resolve("RFQ_", g.nq, g.fq_off, g.fq_str, &g.fq_mask)) {
+            delete m;
+            return fail(PYDSB_ERR_INVALID, "bad f/J/fq reference table");
+        }
+        g.j_mask = jmask;
+        // a structurally zero right-hand side reads the always-zero constant slot: point it at offset of X (harmless)
+        // and rely on h*0: keep it simple by requiring f to be non-zero
+        if (fmask != (1u << g.ns) - 1u) { delete m; return fail(PYDSB_ERR_UNSUPPORTED, "a dynamic state has an identically zero right-hand side"); }
+    }
     {
         const double rtol = reinterpret_cast<const double*>(find(secs, "DBLS")->data)[0];
         g.rtol2 = rtol * rtol;
@@ -197,7 +225,13 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
                              : (op == OP_ADD || op == OP_SUB || op == OP_MUL || op == OP_DIV || op == OP_POW ||
                                 op == OP_MIN || op == OP_MAX) ? 2 : 1;
             uint32_t* x = &m->xpt[(size_t)16 * i];
-            x[0] = op;
+            static const int xmap[OP_COUNT] = {/*MOV*/ XOP_MOV, /*NEG*/ XOP_NEG, /*ADD*/ XOP_ADD, /*SUB*/ XOP_SUB, /*MUL*/ XOP_MUL,
+                                               /*DIV*/ XOP_DIV, /*FMA*/ XOP_FMA, /*FMS*/ XOP_FMS, /*FNMA*/ XOP_FNMA, /*SQR*/ XOP_SQR,
+                                               /*RCP*/ XOP_RCP, /*EXP*/ XOP_COLD, /*LOG*/ XOP_COLD, /*SQRT*/ XOP_COLD, /*SIN*/ XOP_COLD,
+                                               /*COS*/ XOP_COLD, /*TANH*/ XOP_COLD, /*POW*/ XOP_COLD, /*ABS*/ XOP_ABS, /*MIN*/ XOP_MIN,
+                                               /*MAX*/ XOP_MAX, /*BC3*/ XOP_NOP};
+            x[0] = (uint32_t)xmap[op] | (op << 8);
+            const bool cold_unary = (xmap[op] == XOP_COLD && nops == 1);
             for (int k = 0; k <= nops; ++k) {
                 const unsigned r = refs[k];
                 if (r & REF_CONST) { delete m; return fail(PYDSB_ERR_INVALID, "constant operand in the point tape"); }
@@ -205,6 +239,8 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
                 for (int p3 = 0; p3 < 3; ++p3)
                     x[1 + 3 * k + p3] = ((r & REF_MASK) + ((r & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
             }
+            if (cold_unary)
+                for (int p3 = 0; p3 < 3; ++p3) x[7 + p3] = x[4 + p3];
             if (!(refs[0] & REF_WIDE)) { delete m; return fail(PYDSB_ERR_INVALID, "point tape writes a narrow slot"); }
         }
     }

@@ -205,8 +205,7 @@ class DaeModel:
 
         sec("HEAD", "u32", [ns, nq, ng, len(self.d_names), len(self.p_names), nz, self.nfe, self.ncp, nce,
                             lay.n_units, lay.ctrl_slot, lay.xe_slot, lay.qe_slot, lay.x_slot, self.newton_max_it,
-                            lay.f_slot, lay.j_slot, lay.fq_slot, lay.j_mask, lay.fq_state_dep,
-                            1 if self.predictor else 0])
+                            lay.j_mask, lay.fq_state_dep, 1 if self.predictor else 0])
         sec("RPAR", "u16", lay.param_slots)
         sec("DBLS", "f64", [self.newton_rtol])
         sec("CNST", "f64", low.consts if len(low.consts) else [0.0])
@@ -223,6 +222,9 @@ class DaeModel:
         sec("RX0_", "u16", low.refs["x0"])
         sec("RQ0_", "u16", low.refs["q0"] if nq else [T.REF_NONE])
         sec("RZ__", "u16", low.refs["z"] if nz else [T.REF_NONE])
+        sec("RF__", "u16", low.refs["f"])
+        sec("RJ__", "u16", low.refs["J"])
+        sec("RFQ_", "u16", low.refs["fq"] if nq else [T.REF_NONE])
         sec("RG__", "u16", low.refs["g"])
         sec("CMAP", "u16", cmap)
 

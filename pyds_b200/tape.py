@@ -342,9 +342,6 @@ class TapeLayout:
     xe_slot: int = 0
     qe_slot: int = 0
     x_slot: int = 0            # wide: slot x_slot + 3*i + point
-    f_slot: int = 0            # wide, dense: f_slot + 3*i + point           (pinned outputs of the point tape)
-    j_slot: int = 0            # wide, dense: j_slot + 3*(r*ns + c) + point
-    fq_slot: int = 0           # wide, dense: fq_slot + 3*k + point
     j_mask: int = 0            # bit r*ns+c set when dJ[r][c] is not structurally zero
     fq_state_dep: int = 0      # 1 when some quadrature integrand depends on the dynamic states
     n_units: int = 0           # total narrow-equivalent slots
@@ -470,28 +467,22 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
     def eff_args(n):
         return fma_form[n.id][1:] if n.id in fma_form else n.args
 
-    # ---- dense pinned outputs of the point tape ----------------------------------------------------
+    # ---- outputs of the point tape (f, J = df/dx, fq) are read by the compiled Newton code through
+    # (offset, stride) tables, so a root may live in any per-thread slot: wide (state dependent) or
+    # narrow (parameter / control level).  Non-zero constant roots get a per-thread slot too.
     lay = TapeLayout(n_param=n_param, n_ctrl_elem=n_ctrl_elem, ns=ns, nq=nq)
-    pinned = {}                                  # node id -> wide unit of its first pinned destination
-    extra = {"pro": [], "elem": [], "pt": []}    # (opname, dst unit | REF_WIDE, src node)
-    dense_rel = {"f": 0, "J": 3 * ns, "fq": 3 * ns + 3 * ns * ns}      # relative to f_slot
+    extra = {"pro": [], "elem": [], "pt": []}    # (opname, dst, src node) appended after the tape body
+    const_roots = []
     for tname in dense_names:
         for i, e in enumerate(roots.get(tname, [])):
-            rel = dense_rel[tname] + 3 * i
-            if tname == "J" and e is not None and not e.is_const(0.0):
+            if e is None or e.is_const(0.0):
+                continue
+            if tname == "J":
                 lay.j_mask |= 1 << i
-            if e is None:
-                e = graph.const(0.0)
             if tname == "fq" and e.level == LEVEL_STATE:
                 lay.fq_state_dep = 1
-            if e.level == LEVEL_STATE and e.args and e.id not in pinned:
-                pinned[e.id] = rel
-            elif e.level == LEVEL_STATE:
-                extra["pt"].append(("MOV", rel, e))
-            elif e.level == LEVEL_CTRL:
-                extra["elem"].append(("BC3", rel, e))
-            else:
-                extra["pro"].append(("BC3", rel, e))
+            if e.op == "const":
+                const_roots.append(e)
 
     # ---- who reads what, and where ------------------------------------------------------------------
     tape_of = {n.id: name for name, lst in sched.items() for n in lst}
@@ -505,8 +496,6 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
             read_in.setdefault(src.id, set()).add(name)
     table_read = set()                            # read by the kernel itself through a reference table
     for tname, lst in roots.items():
-        if tname in dense_names:
-            continue
         for e in lst:
             if e is not None:
                 table_read.add(e.id)
@@ -532,13 +521,12 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
     # constants used as operands by the point tape get a per-thread slot (filled by the prologue) so
     # that every operand of the hot tape is addressed the same way
     const_slot = {}
-    for n in sched["pt"]:
-        for a in eff_args(n):
-            if a.op == "const":
-                key = struct.pack("<d", a.value)
-                if key not in const_slot:
-                    const_slot[key] = cur; cur += 1
-                    extra["pro"].append(("MOV", None, a))          # dst patched below
+    for a in [a for n in sched["pt"] for a in eff_args(n)] + const_roots:
+        if a.op == "const":
+            key = struct.pack("<d", a.value)
+            if key not in const_slot:
+                const_slot[key] = cur; cur += 1
+                extra["pro"].append(("MOV", None, a))              # dst patched below
     for name in ("pro", "elem"):
         for n in sched[name]:
             if persistent(n) or name == "elem":
@@ -546,10 +534,6 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
 
     # ---- wide region ---------------------------------------------------------------------------------
     lay.x_slot = cur; cur += 3 * ns
-    lay.f_slot = cur
-    lay.j_slot = lay.f_slot + 3 * ns
-    lay.fq_slot = lay.j_slot + 3 * ns * ns
-    cur = lay.fq_slot + 3 * nq
     wide_fixed_end = cur
 
     def leaf_ref(n, in_pt=False):
@@ -577,9 +561,6 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
             for s in release_at.pop(pos, []):
                 pool.give(s)
             if n.id in slot_of:
-                continue
-            if wide and n.id in pinned:
-                slot_of[n.id] = REF_WIDE | (lay.f_slot + pinned[n.id])
                 continue
             s = pool.take()
             slot_of[n.id] = (REF_WIDE | s) if wide else s
@@ -629,20 +610,20 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
                 words.append(encode(_UNOPS[n.op], dst, ref(n.args[0], in_pt)))
             else:
                 raise NotImplementedError(n.op)
-        for opn, rel, src in extra.get(name, []):
-            if rel is None:                                         # constant -> per-thread slot
-                words.append(encode("MOV", const_slot[struct.pack("<d", src.value)], cref(src.value)))
-            else:
-                words.append(encode(opn, REF_WIDE | (lay.f_slot + rel), ref(src, in_pt and opn == "MOV")))
+        for opn, rel, src in extra.get(name, []):                   # constants -> per-thread slots
+            words.append(encode("MOV", const_slot[struct.pack("<d", src.value)], cref(src.value)))
         code[name] = np.asarray(words, dtype=np.uint64)
 
     ref_tables = {}
     for name, lst in roots.items():
-        if name in dense_names:
-            continue
         out = []
         for e in lst:
-            out.append(REF_NONE if (e is None or e.is_const(0.0)) else ref(e))
+            if e is None or e.is_const(0.0):
+                out.append(REF_NONE)
+            elif e.op == "const" and name in dense_names:
+                out.append(const_slot[struct.pack("<d", e.value)])
+            else:
+                out.append(ref(e))
         ref_tables[name] = np.asarray(out, dtype=np.uint16)
 
     stats = {k: int(len(v)) for k, v in code.items()}
