@@ -97,6 +97,23 @@ int pydsb_efp(void* handle, const double* d, long long n_d, const double* theta,
 int pydsb_eval_host(void* handle, const double* d, long long n_d, const double* theta, const double* w,
                     long long n_t, const double* z, int z_mode, double* g_out, double* ind_out, double* P_out);
 
+/* Control (recourse) optimisation: replaces Solver.solve / _solve_relaxation (reference
+ * pyds/solver.py:26-55), i.e. the GAMS/CONOPT solve of the big-M relaxation
+ *     max (1/N) sum_s (1 - y_s)  s.t.  g_k <= M_k y_s                  (pyds/utils.py:7-51)
+ * in its reduced form  min_z sum_s w_s max(0, max_k g_ks(z)/M_k)  over the control box.
+ *   per_scenario = 0: one control vector per design point, shared by all theta (the reference's
+ *                     two-stage formulation); G = n_d groups
+ *   per_scenario = 1: one control vector per (d, theta) scenario; G = n_d*n_t groups, w ignored
+ *   z0      NULL (zeros) or (z0_rows, nz) start profile, z0_rows in {1, G}
+ *   opts    NULL or 6 doubles {mu0, mu_min, lam0, step_tol, max_iter, check_every} (<= 0: default)
+ *   z_out   (G, nz) optimised controls          phi_out  NULL or (G) objective value at z_out
+ *   status_out NULL or (G): 1 all scenarios feasible, 2 converged, 3 iteration cap
+ *   iters_out  NULL or (G) evaluations used
+ * All pointers are DEVICE pointers; the call synchronises `stream` while it iterates. */
+int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long long n_d, const double* theta,
+                         const double* w, long long n_t, const double* z0, long long z0_rows, const double* opts,
+                         double* z_out, double* phi_out, int* status_out, int* iters_out, void* stream);
+
 /* Counters since the last reset (device-side totals; synchronises the handle's work). */
 int pydsb_get_counters(void* handle, unsigned long long* out, int n, int reset);
 

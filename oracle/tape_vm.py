@@ -26,18 +26,25 @@ def parse_blob(blob: bytes):
     magic, ver, nsec, _ = struct.unpack_from("<IIII", blob, 0)
     assert magic == 0x42534450 and ver == 1
     off, out = 16, {}
+    cur = out
     for _ in range(nsec):
         tag, dt, cnt, _ = struct.unpack_from("<4sIII", blob, off)
         off += 16
         nbytes = cnt * np.dtype(_DT[dt]).itemsize
-        out[tag.decode()] = np.frombuffer(blob, dtype=_DT[dt], count=cnt, offset=off).copy()
+        arr = np.frombuffer(blob, dtype=_DT[dt], count=cnt, offset=off).copy()
         off += nbytes + ((-nbytes) % 8)
+        if tag == b"PSEP":
+            cur = out.setdefault("sens", {})
+            continue
+        cur[tag.decode()] = arr
     return out
 
 
 class TapeVM:
-    def __init__(self, blob: bytes):
+    def __init__(self, blob: bytes, program: int = 0):
         s = parse_blob(blob)
+        if program:
+            s = s["sens"]
         self.sec = s
         (self.ns, self.nq, self.ng, self.d_dim, self.p_dim, self.nz, self.nfe, self.ncp, self.nce, self.n_units,
          self.ctrl_slot, self.xe_slot, self.qe_slot, self.x_slot, self.max_it,
@@ -96,7 +103,7 @@ class TapeVM:
                 idx = dst & _REF_MASK
                 R[idx + (w if dst & _REF_WIDE else 0)] = np.broadcast_to(v, R[0].shape).copy()
 
-    def evaluate(self, d, p, z=None, tol=None, max_it=None, return_traj=False):
+    def evaluate(self, d, p, z=None, tol=None, max_it=None, return_traj=False, want_sens=False):
         """g over the (n_d, n_p) grid.  ``z``: None (model defaults), (nz,), (n_d, nz) or (n_d, n_p, nz).
         Returns dict(g=(n_d,n_p,ng), y, feasible, iters=(n_d,n_p) total Newton iterations, status)."""
         d = np.atleast_2d(np.asarray(d, dtype=np.float64))
@@ -132,6 +139,11 @@ class TapeVM:
         traj = np.zeros((S, self.nfe * ncp + 1, ns))
         traj[:, 0] = x0
         n = ns * ncp
+        if want_sens:
+            if "RFZ_" not in s:
+                raise ValueError("sensitivities need the blob's program 1: TapeVM(blob, program=1)")
+            Sx = np.zeros((S, ns, self.nz))
+            Sq = np.zeros((S, nq, self.nz))
         for e in range(self.nfe):
             for k in range(self.nce):
                 R[self.ctrl_slot + k] = Z[int(self.cmap[e, k])]
@@ -184,6 +196,43 @@ class TapeVM:
                 for w in range(ncp):
                     acc = acc + self.bw[w] * self._ld(R, s["RFQ_"][k], w)
                 q[:, k] = q[:, k] + h * acc
+            if want_sens:
+                # forward sensitivities: M dX_c = -dR/dx_prev S[:,c] - dR/dz_c at the converged points
+                J = np.zeros((S, ncp, ns, ns))
+                for w in range(ncp):
+                    for r_ in range(ns):
+                        for c_ in range(ns):
+                            J[:, w, r_, c_] = self._ld(R, s["RJ__"][r_ * ns + c_], w)
+                M = np.zeros((S, ncp, ns, ncp, ns))
+                eye = np.eye(ns)
+                for j in range(ncp):
+                    for k in range(ncp):
+                        M[:, j, :, k, :] += A[k + 1, j + 1] * eye
+                    M[:, j, :, j, :] -= h * J[:, j]
+                M = M.reshape(S, n, n)
+                rhs = np.zeros((S, ncp, ns, self.nz))
+                for c in range(self.nz):
+                    for j in range(ncp):
+                        rhs[:, j, :, c] = -A[0, j + 1] * Sx[:, :, c]
+                        for k in range(self.nce):
+                            if int(self.cmap[e, k]) == c:
+                                for r_ in range(ns):
+                                    rhs[:, j, r_, c] += h * self._ld(R, s["RFZ_"][r_ * self.nce + k], j)
+                with np.errstate(all="ignore"):
+                    dXc = np.linalg.solve(M, rhs.reshape(S, n, self.nz)).reshape(S, ncp, ns, self.nz)
+                Sx = dXc[:, ncp - 1].copy()
+                for qq in range(nq):
+                    for c in range(self.nz):
+                        acc = 0.0
+                        for j in range(ncp):
+                            t = 0.0
+                            for r_ in range(ns):
+                                t = t + self._ld(R, s["RFQX"][qq * ns + r_], j) * dXc[:, j, r_, c]
+                            for k in range(self.nce):
+                                if int(self.cmap[e, k]) == c:
+                                    t = t + self._ld(R, s["RFQZ"][qq * self.nce + k], j)
+                            acc = acc + self.bw[j] * t
+                        Sq[:, qq, c] += h * acc
             traj[:, e * ncp + 1:(e + 1) * ncp + 1] = X
             x0 = X[:, ncp - 1, :].copy()
         for i in range(ns):
@@ -200,6 +249,15 @@ class TapeVM:
         out = dict(g=g.reshape(n_d, n_p, self.ng), y=y.reshape(n_d, n_p), feasible=feas.reshape(n_d, n_p),
                    iters=iters.reshape(n_d, n_p), status=failed.reshape(n_d, n_p).astype(np.int32),
                    x_end=x0.reshape(n_d, n_p, ns), q_end=q.reshape(n_d, n_p, nq))
+        if want_sens:
+            dg = np.zeros((S, self.ng, self.nz))
+            for k in range(self.ng):
+                for r_ in range(ns):
+                    dg[:, k, :] += (self._ld(R, s["RGX_"][k * ns + r_], 0) * one)[:, None] * Sx[:, r_, :]
+                for qq in range(nq):
+                    dg[:, k, :] += (self._ld(R, s["RGQ_"][k * nq + qq], 0) * one)[:, None] * Sq[:, qq, :]
+            dg[:, :, s["ZFIX"][:self.nz].astype(bool)] = 0.0
+            out["dg"] = dg.reshape(n_d, n_p, self.ng, self.nz)
         if return_traj:
             out["traj"] = traj.reshape(n_d, n_p, -1, ns)
         return out

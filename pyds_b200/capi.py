@@ -21,7 +21,8 @@ INFO_NAMES = ["ns", "nq", "ng", "d_dim", "p_dim", "nz", "nfe", "ncp", "n_units",
 COUNTER_NAMES = ["scenarios", "newton_iters", "newton_warp_iters", "failed", "launches"]
 
 EXPORTS = ["pydsb_last_error", "pydsb_version", "pydsb_model_create", "pydsb_model_destroy", "pydsb_model_info",
-           "pydsb_eval", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_get_counters", "pydsb_dfma_peak"]
+           "pydsb_eval", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_recourse_solve", "pydsb_get_counters",
+           "pydsb_dfma_peak"]
 
 
 class PydsbError(RuntimeError):
@@ -59,6 +60,8 @@ def load():
     L.pydsb_efp.argtypes = [vp, dp, ll, dp, dp, ll, dp, vp]
     L.pydsb_eval_host.restype = ci
     L.pydsb_eval_host.argtypes = [vp, dp, ll, dp, dp, ll, dp, ci, dp, dp, dp]
+    L.pydsb_recourse_solve.restype = ci
+    L.pydsb_recourse_solve.argtypes = [vp, ci, dp, ll, dp, dp, ll, dp, ll, dp, dp, dp, vp, vp, vp]
     L.pydsb_get_counters.restype = ci
     L.pydsb_get_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong), ci, ci]
     L.pydsb_dfma_peak.restype = ci
@@ -155,6 +158,44 @@ class Engine:
         ptr = lambda t: None if t is None else t.data_ptr()
         _check(self._lib.pydsb_eval(self._h, ptr(d), n_d, ptr(theta), ptr(w), n_t, ptr(z), z_mode if z is not None else Z_MODEL,
                                     ptr(g_out), ptr(ind_out), ptr(P_out), ctypes.c_void_p(stream.cuda_stream)))
+
+    def recourse_solve(self, d, theta, w=None, z0=None, per_scenario=False, mu0=0.0, mu_min=0.0, lam0=0.0, step_tol=0.0,
+                       max_iter=0, check_every=0):
+        """Optimise the controls (numpy in / numpy out).  Returns dict(z, phi, status, iters); ``z`` is
+        (n_d, nz) in shared mode and (n_d, n_t, nz) in per-scenario mode."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        d = _np64(d).reshape(-1, self.info["d_dim"])
+        theta = _np64(theta).reshape(-1, self.info["p_dim"])
+        n_d, n_t, nz = d.shape[0], theta.shape[0], self.info["nz"]
+        G = n_d * n_t if per_scenario else n_d
+        td = torch.from_numpy(d).to(dev)
+        tt = torch.from_numpy(theta).to(dev)
+        tw = None if w is None else torch.from_numpy(_np64(w)).to(dev)
+        tz0, rows = None, 0
+        if z0 is not None:
+            z0 = _np64(z0).reshape(-1, nz)
+            if z0.shape[0] not in (1, G):
+                raise ValueError(f"z0 must have 1 or {G} rows")
+            tz0, rows = torch.from_numpy(z0).to(dev), z0.shape[0]
+        z = torch.empty((max(G, 1), nz), dtype=torch.float64, device=dev)
+        phi = torch.empty(max(G, 1), dtype=torch.float64, device=dev)
+        st = torch.zeros(max(G, 1), dtype=torch.int32, device=dev)
+        it = torch.zeros(max(G, 1), dtype=torch.int32, device=dev)
+        opts = np.array([mu0, mu_min, lam0, step_tol, max_iter, check_every], dtype=np.float64)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        stream = torch.cuda.current_stream(self.device)
+        torch.cuda.synchronize(self.device)
+        _check(self._lib.pydsb_recourse_solve(self._h, 1 if per_scenario else 0, ptr(td), n_d, ptr(tt), ptr(tw), n_t, ptr(tz0),
+                                              rows, opts.ctypes.data, ptr(z), ptr(phi), ptr(st), ptr(it),
+                                              ctypes.c_void_p(stream.cuda_stream)))
+        shape = (n_d, n_t, nz) if per_scenario else (n_d, nz)
+        out = dict(z=z[:G].cpu().numpy().reshape(shape), phi=phi[:G].cpu().numpy(), status=st[:G].cpu().numpy(),
+                   iters=it[:G].cpu().numpy())
+        if per_scenario:
+            for k in ("phi", "status", "iters"):
+                out[k] = out[k].reshape(n_d, n_t)
+        return out
 
     def counters(self, reset=False):
         buf = (ctypes.c_ulonglong * len(COUNTER_NAMES))()

@@ -40,6 +40,12 @@ struct ExecImage {
     unsigned j_off[9], j_str[9];
     unsigned fq_off[8], fq_str[8];
     unsigned fq_mask;
+    // program 1 only: df/dz (ns x nce), dfq/dx (nq x ns), dfq/dz (nq x nce) -- same (offset, stride) form;
+    // dg/dxe (ng x ns) and dg/dqe (ng x nq) are narrow references in `tabs` after cmap
+    unsigned fz_off[12], fz_str[12], fz_mask;
+    unsigned fqx_off[24], fqx_str[24], fqx_mask;
+    unsigned fqz_off[32], fqz_str[32], fqz_mask;
+    double bigm_inv[8];        // 1 / M_k
     int fq_state_dep;
     int predictor;
     int max_it;
@@ -70,8 +76,9 @@ struct LaunchArgs {
 // bank: the fetch is a uniform LDCU and every operand address is [thread base + uniform offset],
 // so the hot interpreter spends no vector-ALU instructions on decoding.
 //   word 0: op | words 1-3: dst offsets (points 0,1,2) | 4-6: a | 7-9: b | 10-12: c | 13-15: pad
-constexpr int MAX_PT = 448;
-__constant__ uint4 c_pt[4 * MAX_PT];
+constexpr int MAX_PT = 320;
+__constant__ uint4 c_pt[4 * MAX_PT];        // program 0: feasibility
+__constant__ uint4 c_pt_s[4 * MAX_PT];      // program 1: feasibility + control sensitivities
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier / bulk-TMA helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP)
@@ -118,20 +125,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 // produces inf/nan which the caller reports as a failed scenario.
 // ---------------------------------------------------------------------------------------------
 template <int N>
-__device__ __forceinline__ void lu_solve_inplace(double (&M)[N][N], double (&r)[N])
+__device__ __forceinline__ void lu_factor(double (&M)[N][N], double (&inv)[N])
 {
-    double inv[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         inv[k] = fast_rcp(M[k][k]);
 #pragma unroll
         for (int i = k + 1; i < N; ++i) {
             const double l = M[i][k] * inv[k];
+            M[i][k] = l;                                   // keep the multiplier: more right-hand sides may follow
 #pragma unroll
             for (int c = k + 1; c < N; ++c) M[i][c] = fma(-l, M[k][c], M[i][c]);
-            r[i] = fma(-l, r[k], r[i]);
         }
     }
+}
+
+template <int N>
+__device__ __forceinline__ void lu_apply(const double (&M)[N][N], const double (&inv)[N], double (&r)[N])
+{
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) r[i] = fma(-M[i][k], r[k], r[i]);
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
         double s = r[k];
@@ -139,6 +154,14 @@ __device__ __forceinline__ void lu_solve_inplace(double (&M)[N][N], double (&r)[
         for (int c = k + 1; c < N; ++c) s = fma(-M[k][c], r[c], s);
         r[k] = s * inv[k];
     }
+}
+
+template <int N>
+__device__ __forceinline__ void lu_solve_inplace(double (&M)[N][N], double (&r)[N])
+{
+    double inv[N];
+    lu_factor<N>(M, inv);
+    lu_apply<N>(M, inv, r);
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -212,8 +235,10 @@ __device__ __noinline__ double cold_op(unsigned op, double a, double b)
     }                                                                 \
     break;
 
+template <bool SENS>
 __device__ __forceinline__ void run_point_tape(char* __restrict__ base, int n)
 {
+    const uint4* const c_pt = SENS ? c_pt_s : pydsb::c_pt;
     for (int pc = 0; pc < n; ++pc) {
         const uint4 q0 = c_pt[4 * pc];
         const uint4 q1 = c_pt[4 * pc + 1];
@@ -411,7 +436,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
             double s_prev = 0.0;                          // no rate estimate before the second step
             for (int it = 0;; ++it) {
                 if (stop && !final_eval) break;
-                run_point_tape(base, img.n_pt);                           // f, df/dx, fq at the 3 points
+                run_point_tape<false>(base, img.n_pt);                           // f, df/dx, fq at the 3 points
                 if (stop) break;
 
                 double M[N][N], r[N];

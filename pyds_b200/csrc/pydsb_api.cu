@@ -1,17 +1,18 @@
-// C-ABI of libpyds_b200.so (see include/pydsb.h).  Host side only: blob parsing, device image,
-// launch configuration, pinned staging for the *_host entry points.  No CPU compute fallback:
-// without a CUDA device every entry point fails with PYDSB_ERR_NO_DEVICE.
+// C-ABI of libpyds_b200.so (see include/pydsb.h).  Host side only: blob parsing, device images,
+// launch configuration, the host loop of the recourse optimiser, pinned staging for the *_host
+// entry points.  No CPU compute fallback: without a CUDA device every entry point fails with
+// PYDSB_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <math.h>
 #include <string.h>
 
 #include <string>
 #include <vector>
 
 #include "../../include/pydsb.h"
-#include "feas_kernel.cuh"
+#include "recourse_kernel.cuh"
 
 using namespace pydsb;
 
@@ -37,37 +38,48 @@ struct Section {
     uint32_t dtype, count;
     const unsigned char* data;
 };
+typedef std::vector<Section> Sections;
 
-struct Model {
-    int device = 0;
-    ExecImage img{};
-    void* d_code = nullptr;
-    void* d_consts = nullptr;
-    void* d_tabs = nullptr;
-    std::vector<uint32_t> xpt;          // pre-decoded point tape (16 words per instruction)
-    unsigned long long* d_counters = nullptr;
-    double* d_partial = nullptr;
-    size_t partial_cap = 0;
-    int num_sms = 0, blocks_per_sm = 0, regs = 0;
-    unsigned long long launches = 0;
-    // pinned + device staging for the *_host entry points
-    double* h_pin = nullptr;
-    size_t h_pin_cap = 0;
-    double* d_stage = nullptr;
-    size_t d_stage_cap = 0;
-    cudaStream_t own_stream = nullptr;
-};
-
-const Section* find(const std::vector<Section>& secs, const char* tag)
+const Section* find(const Sections& secs, const char* tag)
 {
     for (const auto& s : secs)
         if (strncmp(s.tag, tag, 4) == 0) return &s;
     return nullptr;
 }
 
-typedef void (*KernelFn)(const ExecImage, const LaunchArgs);
+// One lowered program (0: feasibility, 1: feasibility + control sensitivities) on the device.
+struct Program {
+    ExecImage img{};
+    void* d_code = nullptr;
+    void* d_consts = nullptr;
+    void* d_tabs = nullptr;
+    std::vector<uint32_t> xpt;          // pre-decoded point tape (16 words per instruction)
+    bool present = false;
+};
 
-KernelFn kernel_for(int ns)
+struct Model {
+    int device = 0;
+    Program prog[2];
+    std::vector<double> z_lo, z_hi;
+    std::vector<unsigned char> z_fix;
+    double* d_zlo = nullptr;
+    double* d_zhi = nullptr;
+    unsigned char* d_zfix = nullptr;
+    unsigned long long* d_counters = nullptr;
+    double* d_partial = nullptr;
+    size_t partial_cap = 0;
+    int num_sms = 0, blocks_per_sm = 0, regs = 0;
+    unsigned long long launches = 0;
+    double* h_pin = nullptr;            // pinned + device staging for the *_host entry points
+    size_t h_pin_cap = 0;
+    double* d_stage = nullptr;
+    cudaStream_t own_stream = nullptr;
+};
+
+typedef void (*FeasFn)(const ExecImage, const LaunchArgs);
+typedef void (*SensFn)(const ExecImage, const RecourseArgs);
+
+FeasFn feas_for(int ns)
 {
     switch (ns) {
     case 1: return feas_kernel<1>;
@@ -76,8 +88,204 @@ KernelFn kernel_for(int ns)
     default: return nullptr;
     }
 }
+SensFn sens_for(int ns)
+{
+    switch (ns) {
+    case 1: return sens_kernel<1>;
+    case 2: return sens_kernel<2>;
+    case 3: return sens_kernel<3>;
+    default: return nullptr;
+    }
+}
 
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+void free_program(Program& p)
+{
+    if (p.d_code) cudaFree(p.d_code);
+    if (p.d_consts) cudaFree(p.d_consts);
+    if (p.d_tabs) cudaFree(p.d_tabs);
+    p.d_code = p.d_consts = p.d_tabs = nullptr;
+}
+
+bool resolve_table(const Sections& secs, const char* tag, int n, int cap, unsigned* off, unsigned* str, unsigned* mask)
+{
+    const Section* s = find(secs, tag);
+    if (!s || (int)s->count < n || n > cap) return false;
+    const uint16_t* v = reinterpret_cast<const uint16_t*>(s->data);
+    *mask = 0;
+    for (int i = 0; i < n; ++i) {
+        off[i] = 0; str[i] = 0;
+        if (v[i] == REF_NONE) continue;
+        if (v[i] & REF_CONST) return false;
+        *mask |= 1u << i;
+        off[i] = (v[i] & REF_MASK) * BLOCK * 8u;
+        str[i] = (v[i] & REF_WIDE) ? BLOCK * 8u : 0u;
+    }
+    return true;
+}
+
+// Parse one program's sections into an ExecImage + device buffers.
+int build_program(const Sections& secs, bool sens, Program& P)
+{
+    static const char* need[] = {"HEAD", "DBLS", "CNST", "ADOT", "BWTS", "BIGM", "ZFIX", "TPRO", "TELM", "TPNT", "TGEE",
+                                 "RPAR", "RX0_", "RQ0_", "RZ__", "RF__", "RJ__", "RFQ_", "RG__", "CMAP"};
+    for (const char* t : need)
+        if (!find(secs, t)) return fail(PYDSB_ERR_INVALID, std::string("blob lacks section ") + t);
+    const Section* head = find(secs, "HEAD");
+    if (head->count < 18) return fail(PYDSB_ERR_INVALID, "HEAD too short");
+    const uint32_t* H = reinterpret_cast<const uint32_t*>(head->data);
+    ExecImage& g = P.img;
+    g.ns = H[0]; g.nq = H[1]; g.ng = H[2]; g.d_dim = H[3]; g.p_dim = H[4]; g.nz = H[5]; g.nfe = H[6];
+    const int ncp = H[7];
+    g.nce = H[8]; g.n_units = H[9]; g.ctrl_slot = H[10]; g.xe_slot = H[11]; g.qe_slot = H[12];
+    g.x_slot = H[13]; g.max_it = H[14]; g.j_mask = H[15]; g.fq_state_dep = H[16]; g.predictor = H[17];
+    if (ncp != 3) return fail(PYDSB_ERR_UNSUPPORTED, "kernels are built for ncp = 3 (Radau)");
+    if (!feas_for(g.ns)) return fail(PYDSB_ERR_UNSUPPORTED, "register-resident Newton kernels cover 1..3 dynamic states");
+    if (g.ng < 1 || g.ng > 8 || g.nfe < 1 || g.p_dim < 1 || g.d_dim < 0) return fail(PYDSB_ERR_INVALID, "bad dimensions");
+    if (g.nq > 8) return fail(PYDSB_ERR_UNSUPPORTED, "at most 8 quadrature states");
+    if (g.nce > 4) return fail(PYDSB_ERR_UNSUPPORTED, "at most 4 control functions");
+    unsigned fmask = 0, jmask = 0;
+    if (!resolve_table(secs, "RF__", g.ns, 3, g.f_off, g.f_str, &fmask) ||
+        !resolve_table(secs, "RJ__", g.ns * g.ns, 9, g.j_off, g.j_str, &jmask) ||
+        !resolve_table(secs, "RFQ_", g.nq, 8, g.fq_off, g.fq_str, &g.fq_mask))
+        return fail(PYDSB_ERR_INVALID, "bad f/J/fq reference table");
+    g.j_mask = jmask;
+    if (fmask != (1u << g.ns) - 1u)
+        return fail(PYDSB_ERR_UNSUPPORTED, "a dynamic state has an identically zero right-hand side");
+    {
+        const double rtol = reinterpret_cast<const double*>(find(secs, "DBLS")->data)[0];
+        g.rtol2 = rtol * rtol;
+    }
+    const Section* adot = find(secs, "ADOT");
+    const Section* bw = find(secs, "BWTS");
+    const Section* bigm = find(secs, "BIGM");
+    if (adot->count != 16 || bw->count != 3 || (int)bigm->count < g.ng) return fail(PYDSB_ERR_INVALID, "bad collocation tables");
+    memcpy(g.adot, adot->data, 16 * sizeof(double));
+    memcpy(g.bw, bw->data, 3 * sizeof(double));
+    for (int k = 0; k < g.ng; ++k) {
+        const double M = reinterpret_cast<const double*>(bigm->data)[k];
+        if (!(M > 0.0)) return fail(PYDSB_ERR_INVALID, "big-M constants must be positive");
+        g.bigm_inv[k] = 1.0 / M;
+    }
+    {
+        // extrapolation weights of the previous element's cubic: l_k(1 + tau_j), Radau-3 nodes
+        const long double s6 = sqrtl(6.0L);
+        const long double tau[4] = {0.0L, (4.0L - s6) / 10.0L, (4.0L + s6) / 10.0L, 1.0L};
+        for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 4; ++k) {
+                long double v = 1.0L;
+                for (int l = 0; l < 4; ++l)
+                    if (l != k) v *= (1.0L + tau[j + 1] - tau[l]) / (tau[k] - tau[l]);
+                g.ext[4 * j + k] = (double)v;
+            }
+    }
+
+    const Section *tp = find(secs, "TPRO"), *te = find(secs, "TELM"), *tn = find(secs, "TPNT"), *tg = find(secs, "TGEE");
+    g.n_pro = tp->count; g.n_elem = te->count; g.n_pt = tn->count; g.n_g = tg->count;
+    std::vector<uint64_t> code;
+    for (const Section* s : {tp, te, tg}) {
+        const uint64_t* c = reinterpret_cast<const uint64_t*>(s->data);
+        code.insert(code.end(), c, c + s->count);
+    }
+    for (uint64_t w : code)
+        if ((w & 0xFF) >= OP_COUNT) return fail(PYDSB_ERR_INVALID, "unknown opcode in tape");
+    // pre-decode the point tape: per operand the byte offsets of the three collocation points
+    if (g.n_pt > MAX_PT) return fail(PYDSB_ERR_UNSUPPORTED, "point tape longer than the constant-bank window");
+    {
+        static const int xmap[OP_COUNT] = {/*MOV*/ XOP_MOV, /*NEG*/ XOP_NEG, /*ADD*/ XOP_ADD, /*SUB*/ XOP_SUB, /*MUL*/ XOP_MUL,
+                                           /*DIV*/ XOP_DIV, /*FMA*/ XOP_FMA, /*FMS*/ XOP_FMS, /*FNMA*/ XOP_FNMA, /*SQR*/ XOP_SQR,
+                                           /*RCP*/ XOP_RCP, /*EXP*/ XOP_COLD, /*LOG*/ XOP_COLD, /*SQRT*/ XOP_COLD, /*SIN*/ XOP_COLD,
+                                           /*COS*/ XOP_COLD, /*TANH*/ XOP_COLD, /*POW*/ XOP_COLD, /*ABS*/ XOP_ABS, /*MIN*/ XOP_MIN,
+                                           /*MAX*/ XOP_MAX, /*BC3*/ XOP_NOP};
+        const uint64_t* c = reinterpret_cast<const uint64_t*>(tn->data);
+        P.xpt.assign((size_t)16 * (g.n_pt > 0 ? g.n_pt : 1), 0u);
+        for (int i = 0; i < g.n_pt; ++i) {
+            const uint64_t w = c[i];
+            const unsigned op = (unsigned)(w & 0xFF);
+            const unsigned refs[4] = {(unsigned)(w >> 8) & 0x3FFFu, (unsigned)(w >> 22) & 0x3FFFu,
+                                      (unsigned)(w >> 36) & 0x3FFFu, (unsigned)(w >> 50) & 0x3FFFu};
+            if (op >= OP_BC3) return fail(PYDSB_ERR_INVALID, "opcode not allowed in the point tape");
+            const int nops = (op == OP_FMA || op == OP_FMS || op == OP_FNMA) ? 3
+                             : (op == OP_ADD || op == OP_SUB || op == OP_MUL || op == OP_DIV || op == OP_POW ||
+                                op == OP_MIN || op == OP_MAX) ? 2 : 1;
+            uint32_t* x = &P.xpt[(size_t)16 * i];
+            x[0] = (uint32_t)xmap[op] | (op << 8);
+            const bool cold_unary = (xmap[op] == XOP_COLD && nops == 1);
+            for (int k = 0; k <= nops; ++k) {
+                const unsigned r = refs[k];
+                if (r & REF_CONST) return fail(PYDSB_ERR_INVALID, "constant operand in the point tape");
+                if ((int)(r & REF_MASK) + ((r & REF_WIDE) ? 2 : 0) >= g.n_units) return fail(PYDSB_ERR_INVALID, "slot out of range");
+                for (int p3 = 0; p3 < 3; ++p3)
+                    x[1 + 3 * k + p3] = ((r & REF_MASK) + ((r & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
+            }
+            if (cold_unary)
+                for (int p3 = 0; p3 < 3; ++p3) x[7 + p3] = x[4 + p3];
+            if (!(refs[0] & REF_WIDE)) return fail(PYDSB_ERR_INVALID, "point tape writes a narrow slot");
+        }
+    }
+    const Section* cn = find(secs, "CNST");
+    g.n_const = cn->count;
+
+    std::vector<uint16_t> tabs;
+    auto push = [&](const char* tag, size_t n) -> bool {
+        const Section* s = find(secs, tag);
+        if (!s || s->count < n) return false;
+        const uint16_t* v = reinterpret_cast<const uint16_t*>(s->data);
+        tabs.insert(tabs.end(), v, v + n);
+        return true;
+    };
+    bool ok = push("RPAR", (size_t)g.d_dim + g.p_dim) && push("RX0_", g.ns) && push("RQ0_", g.nq) && push("RZ__", g.nz) &&
+              push("ZFIX", g.nz) && push("RG__", g.ng) && push("CMAP", (size_t)g.nfe * g.nce);
+    if (!ok) return fail(PYDSB_ERR_INVALID, "reference table shorter than its dimension");
+    if (sens) {
+        if (g.nz > MAX_NZ) return fail(PYDSB_ERR_UNSUPPORTED, "at most 16 control values for the recourse optimiser");
+        if (!resolve_table(secs, "RFZ_", g.ns * g.nce, 12, g.fz_off, g.fz_str, &g.fz_mask) ||
+            !resolve_table(secs, "RFQX", g.nq * g.ns, 24, g.fqx_off, g.fqx_str, &g.fqx_mask) ||
+            !resolve_table(secs, "RFQZ", g.nq * g.nce, 32, g.fqz_off, g.fqz_str, &g.fqz_mask))
+            return fail(PYDSB_ERR_INVALID, "bad sensitivity reference table");
+        if (!push("RGX_", (size_t)g.ng * g.ns) || !push("RGQ_", (size_t)g.ng * g.nq))
+            return fail(PYDSB_ERR_INVALID, "bad dg reference table");
+        // live[e]: controls that have acted in an element <= e
+        const uint16_t* cmap = reinterpret_cast<const uint16_t*>(find(secs, "CMAP")->data);
+        unsigned live = 0;
+        for (int e = 0; e < g.nfe; ++e) {
+            for (int k = 0; k < g.nce; ++k) live |= 1u << cmap[e * g.nce + k];
+            tabs.push_back((uint16_t)live);
+        }
+    }
+    g.n_tabs = (int)tabs.size();
+
+    // shared-memory carve-up
+    int o = 128;                                            // mbarrier + reduction scratch
+    g.off_code = o; o += (int)code.size() * 8;
+    g.off_const = o; o += (g.n_const + 1) * 8;
+    g.off_tabs = o; o = align_up(o + g.n_tabs * 2, 128);
+    int land = BLOCK * g.p_dim * 8;
+    if (sens) {
+        const int need_ws = (BLOCK / 32) * recourse_nv(g.nz) * 8;
+        if (need_ws > land) land = need_ws;
+    }
+    g.off_land = o; o = align_up(o + land, 128);
+    g.off_slots = o;
+    int units = g.n_units;
+    if (sens) units += (g.ns + g.nq + g.ng) * g.nz;        // Sx, Sq, Dc blocks of sens_kernel
+    o += units * BLOCK * 8;
+    g.smem_bytes = o;
+
+    cudaError_t e = cudaMalloc(&P.d_code, code.size() * 8 + 8);
+    if (e == cudaSuccess) e = cudaMemcpy(P.d_code, code.data(), code.size() * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&P.d_consts, (size_t)g.n_const * 8 + 8);
+    if (e == cudaSuccess) e = cudaMemcpy(P.d_consts, cn->data, (size_t)g.n_const * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&P.d_tabs, tabs.size() * 2 + 8);
+    if (e == cudaSuccess) e = cudaMemcpy(P.d_tabs, tabs.data(), tabs.size() * 2, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(PYDSB_ERR_CUDA, std::string("model upload: ") + cudaGetErrorString(e));
+    g.code = static_cast<const uint64_t*>(P.d_code);
+    g.consts = static_cast<const double*>(P.d_consts);
+    g.tabs = static_cast<const uint16_t*>(P.d_tabs);
+    P.present = true;
+    return PYDSB_OK;
+}
 
 int ensure_partial(Model* m, size_t n)
 {
@@ -100,17 +308,18 @@ int pydsb_version(void) { return 1; }
 int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handle)
 {
     if (!blob || !handle || nbytes < 16) return fail(PYDSB_ERR_INVALID, "null or truncated blob");
+    const unsigned char* p = static_cast<const unsigned char*>(blob);
+    uint32_t magic, ver, nsec;
+    memcpy(&magic, p, 4); memcpy(&ver, p + 4, 4); memcpy(&nsec, p + 8, 4);
+    if (magic != 0x42534450u || ver != 1u) return fail(PYDSB_ERR_INVALID, "bad blob magic/version");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
         return fail(PYDSB_ERR_NO_DEVICE, "no CUDA device visible: pyds_b200 has no CPU fallback");
     }
     if (device < 0 || device >= ndev) return fail(PYDSB_ERR_INVALID, "device index out of range");
-    const unsigned char* p = static_cast<const unsigned char*>(blob);
-    uint32_t magic, ver, nsec;
-    memcpy(&magic, p, 4); memcpy(&ver, p + 4, 4); memcpy(&nsec, p + 8, 4);
-    if (magic != 0x42534450u || ver != 1u) return fail(PYDSB_ERR_INVALID, "bad blob magic/version");
-    std::vector<Section> secs;
+    Sections progs[2];
+    int cur = 0;
     size_t off = 16;
     static const size_t dsz[4] = {4, 8, 8, 2};
     for (uint32_t i = 0; i < nsec; ++i) {
@@ -126,167 +335,57 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
         if (off + nb > nbytes) return fail(PYDSB_ERR_INVALID, "truncated section payload");
         s.data = p + off;
         off += nb;
-        secs.push_back(s);
+        if (strncmp(s.tag, "PSEP", 4) == 0) {
+            if (++cur > 1) return fail(PYDSB_ERR_INVALID, "more than two programs in blob");
+            continue;
+        }
+        progs[cur].push_back(s);
     }
-    const char* need[] = {"HEAD", "DBLS", "CNST", "ADOT", "BWTS", "BIGM", "ZFIX", "TPRO", "TELM", "TPNT",
-                          "TGEE", "RPAR", "RX0_", "RQ0_", "RZ__", "RF__", "RJ__", "RFQ_", "RG__", "CMAP"};
-    for (const char* t : need)
-        if (!find(secs, t)) return fail(PYDSB_ERR_INVALID, std::string("blob lacks section ") + t);
-    const Section* head = find(secs, "HEAD");
-    if (head->count < 18) return fail(PYDSB_ERR_INVALID, "HEAD too short");
-    const uint32_t* H = reinterpret_cast<const uint32_t*>(head->data);
-
+    CUDA_TRY(cudaSetDevice(device));
     Model* m = new Model();
     m->device = device;
-    ExecImage& g = m->img;
-    g.ns = H[0]; g.nq = H[1]; g.ng = H[2]; g.d_dim = H[3]; g.p_dim = H[4]; g.nz = H[5]; g.nfe = H[6];
-    const int ncp = H[7];
-    g.nce = H[8]; g.n_units = H[9]; g.ctrl_slot = H[10]; g.xe_slot = H[11]; g.qe_slot = H[12];
-    g.x_slot = H[13]; g.max_it = H[14]; g.j_mask = H[15]; g.fq_state_dep = H[16]; g.predictor = H[17];
-    if (ncp != 3) { delete m; return fail(PYDSB_ERR_UNSUPPORTED, "kernels are built for ncp = 3 (Radau)"); }
-    if (!kernel_for(g.ns)) {
-        delete m;
-        return fail(PYDSB_ERR_UNSUPPORTED, "register-resident Newton kernels cover 1..3 dynamic states");
+    int rc = build_program(progs[0], false, m->prog[0]);
+    if (rc == PYDSB_OK && cur == 1) rc = build_program(progs[1], true, m->prog[1]);
+    if (rc != PYDSB_OK) {
+        std::string msg = g_err;
+        pydsb_model_destroy(m);
+        return fail(rc, msg);
     }
-    if (g.ng < 1 || g.nfe < 1 || g.p_dim < 1 || g.d_dim < 0) { delete m; return fail(PYDSB_ERR_INVALID, "bad dimensions"); }
-    if (g.nq > 8) { delete m; return fail(PYDSB_ERR_UNSUPPORTED, "at most 8 quadrature states"); }
+    const ExecImage& g = m->prog[0].img;
+    // control bounds
     {
-        // f / J / fq outputs of the point tape -> (offset, stride) tables read by the compiled Newton code
-        auto resolve = [&](const char* tag, int n, unsigned* off, unsigned* str, unsigned* mask) -> bool {
-            const Section* s = find(secs, tag);
-            if ((int)s->count < n) return false;
-            const uint16_t* v = reinterpret_cast<const uint16_t*>(s->data);
-            *mask = 0;
-            for (int i = 0; i < n; ++i) {
-                off[i] = 0; str[i] = 0;
-                if (v[i] == REF_NONE) continue;
-                if (v[i] & REF_CONST) return false;
-                *mask |= 1u << i;
-                off[i] = (v[i] & REF_MASK) * BLOCK * 8u;
-                str[i] = (v[i] & REF_WIDE) ? BLOCK * 8u : 0u;
+        const Section *zl = find(progs[0], "ZLOW"), *zh = find(progs[0], "ZHIG"), *zf = find(progs[0], "ZFIX");
+        const int nz = g.nz;
+        m->z_lo.assign(nz, 0.0); m->z_hi.assign(nz, 0.0); m->z_fix.assign(nz > 0 ? nz : 1, 0);
+        if (nz > 0) {
+            if (!zl || !zh || (int)zl->count < nz || (int)zh->count < nz || (int)zf->count < nz) {
+                pydsb_model_destroy(m);
+                return fail(PYDSB_ERR_INVALID, "control bound tables shorter than nz");
             }
-            return true;
-        };
-        unsigned fmask = 0, jmask = 0;
-        if (!resolve("RF__", g.ns, g.f_off, g.f_str, &fmask) || !resolve("RJ__", g.ns * g.ns, g.j_off, g.j_str, &jmask) ||
-            !resolve("RFQ_", g.nq, g.fq_off, g.fq_str, &g.fq_mask)) {
-            delete m;
-            return fail(PYDSB_ERR_INVALID, "bad f/J/fq reference table");
-        }
-        g.j_mask = jmask;
-        // a structurally zero right-hand side reads the always-zero constant slot: point it at offset of X (harmless)
-        // and rely on h*0: keep it simple by requiring f to be non-zero
-        if (fmask != (1u << g.ns) - 1u) { delete m; return fail(PYDSB_ERR_UNSUPPORTED, "a dynamic state has an identically zero right-hand side"); }
-    }
-    {
-        const double rtol = reinterpret_cast<const double*>(find(secs, "DBLS")->data)[0];
-        g.rtol2 = rtol * rtol;
-    }
-    const Section* adot = find(secs, "ADOT");
-    const Section* bw = find(secs, "BWTS");
-    if (adot->count != 16 || bw->count != 3) { delete m; return fail(PYDSB_ERR_INVALID, "bad collocation tables"); }
-    memcpy(g.adot, adot->data, 16 * sizeof(double));
-    memcpy(g.bw, bw->data, 3 * sizeof(double));
-    {
-        // extrapolation weights of the previous element's cubic: l_k(1 + tau_j), nodes tau from ADOT's
-        // generator (Radau-3: 0, (4 -+ sqrt 6)/10, 1)
-        const long double s6 = sqrtl(6.0L);
-        const long double tau[4] = {0.0L, (4.0L - s6) / 10.0L, (4.0L + s6) / 10.0L, 1.0L};
-        for (int j = 0; j < 3; ++j)
-            for (int k = 0; k < 4; ++k) {
-                long double v = 1.0L;
-                for (int l = 0; l < 4; ++l)
-                    if (l != k) v *= (1.0L + tau[j + 1] - tau[l]) / (tau[k] - tau[l]);
-                g.ext[4 * j + k] = (double)v;
-            }
-    }
-
-    const Section *tp = find(secs, "TPRO"), *te = find(secs, "TELM"), *tn = find(secs, "TPNT"), *tg = find(secs, "TGEE");
-    g.n_pro = tp->count; g.n_elem = te->count; g.n_pt = tn->count; g.n_g = tg->count;
-    std::vector<uint64_t> code;
-    for (const Section* s : {tp, te, tg}) {
-        const uint64_t* c = reinterpret_cast<const uint64_t*>(s->data);
-        code.insert(code.end(), c, c + s->count);
-    }
-    for (uint64_t w : code)
-        if ((w & 0xFF) >= OP_COUNT) { delete m; return fail(PYDSB_ERR_INVALID, "unknown opcode in tape"); }
-    // pre-decode the point tape: per operand the byte offsets of the three collocation points
-    if (g.n_pt > MAX_PT) { delete m; return fail(PYDSB_ERR_UNSUPPORTED, "point tape longer than the constant-bank window"); }
-    {
-        const uint64_t* c = reinterpret_cast<const uint64_t*>(tn->data);
-        m->xpt.assign((size_t)16 * (g.n_pt > 0 ? g.n_pt : 1), 0u);
-        for (int i = 0; i < g.n_pt; ++i) {
-            const uint64_t w = c[i];
-            const unsigned op = (unsigned)(w & 0xFF);
-            const unsigned refs[4] = {(unsigned)(w >> 8) & 0x3FFFu, (unsigned)(w >> 22) & 0x3FFFu,
-                                      (unsigned)(w >> 36) & 0x3FFFu, (unsigned)(w >> 50) & 0x3FFFu};
-            if (op >= OP_BC3) { delete m; return fail(PYDSB_ERR_INVALID, "opcode not allowed in the point tape"); }
-            const int nops = (op == OP_FMA || op == OP_FMS || op == OP_FNMA) ? 3
-                             : (op == OP_ADD || op == OP_SUB || op == OP_MUL || op == OP_DIV || op == OP_POW ||
-                                op == OP_MIN || op == OP_MAX) ? 2 : 1;
-            uint32_t* x = &m->xpt[(size_t)16 * i];
-            static const int xmap[OP_COUNT] = {/*MOV*/ XOP_MOV, /*NEG*/ XOP_NEG, /*ADD*/ XOP_ADD, /*SUB*/ XOP_SUB, /*MUL*/ XOP_MUL,
-                                               /*DIV*/ XOP_DIV, /*FMA*/ XOP_FMA, /*FMS*/ XOP_FMS, /*FNMA*/ XOP_FNMA, /*SQR*/ XOP_SQR,
-                                               /*RCP*/ XOP_RCP, /*EXP*/ XOP_COLD, /*LOG*/ XOP_COLD, /*SQRT*/ XOP_COLD, /*SIN*/ XOP_COLD,
-                                               /*COS*/ XOP_COLD, /*TANH*/ XOP_COLD, /*POW*/ XOP_COLD, /*ABS*/ XOP_ABS, /*MIN*/ XOP_MIN,
-                                               /*MAX*/ XOP_MAX, /*BC3*/ XOP_NOP};
-            x[0] = (uint32_t)xmap[op] | (op << 8);
-            const bool cold_unary = (xmap[op] == XOP_COLD && nops == 1);
-            for (int k = 0; k <= nops; ++k) {
-                const unsigned r = refs[k];
-                if (r & REF_CONST) { delete m; return fail(PYDSB_ERR_INVALID, "constant operand in the point tape"); }
-                if ((int)(r & REF_MASK) + 2 >= g.n_units + 2 && (r & REF_WIDE)) { delete m; return fail(PYDSB_ERR_INVALID, "slot out of range"); }
-                for (int p3 = 0; p3 < 3; ++p3)
-                    x[1 + 3 * k + p3] = ((r & REF_MASK) + ((r & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
-            }
-            if (cold_unary)
-                for (int p3 = 0; p3 < 3; ++p3) x[7 + p3] = x[4 + p3];
-            if (!(refs[0] & REF_WIDE)) { delete m; return fail(PYDSB_ERR_INVALID, "point tape writes a narrow slot"); }
+            memcpy(m->z_lo.data(), zl->data, nz * sizeof(double));
+            memcpy(m->z_hi.data(), zh->data, nz * sizeof(double));
+            for (int i = 0; i < nz; ++i) m->z_fix[i] = (unsigned char)reinterpret_cast<const uint16_t*>(zf->data)[i];
         }
     }
-    const Section* cn = find(secs, "CNST");
-    g.n_const = cn->count;
-
-    std::vector<uint16_t> tabs;
-    auto push = [&](const char* tag, size_t n) -> bool {
-        const Section* s = find(secs, tag);
-        if (s->count < n) return false;
-        const uint16_t* v = reinterpret_cast<const uint16_t*>(s->data);
-        tabs.insert(tabs.end(), v, v + n);
-        return true;
-    };
-    bool ok = push("RPAR", (size_t)g.d_dim + g.p_dim) && push("RX0_", g.ns) && push("RQ0_", g.nq) && push("RZ__", g.nz) &&
-              push("ZFIX", g.nz) && push("RG__", g.ng) && push("CMAP", (size_t)g.nfe * g.nce);
-    if (!ok) { delete m; return fail(PYDSB_ERR_INVALID, "reference table shorter than its dimension"); }
-    g.n_tabs = (int)tabs.size();
-
-    // shared-memory carve-up
-    int o = 128;                                            // mbarriers + reduction scratch
-    g.off_code = o; o += (int)code.size() * 8;
-    g.off_const = o; o += (g.n_const + 1) * 8;
-    g.off_tabs = o; o = align_up(o + g.n_tabs * 2, 128);
-    g.off_land = o; o = align_up(o + BLOCK * g.p_dim * 8, 128);
-    g.off_slots = o; o += g.n_units * BLOCK * 8;
-    g.smem_bytes = o;
-
-    cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_code, code.size() * 8 + 8);
-    if (e == cudaSuccess) e = cudaMemcpy(m->d_code, code.data(), code.size() * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_consts, (size_t)g.n_const * 8 + 8);
-    if (e == cudaSuccess) e = cudaMemcpy(m->d_consts, cn->data, (size_t)g.n_const * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_tabs, tabs.size() * 2 + 8);
-    if (e == cudaSuccess) e = cudaMemcpy(m->d_tabs, tabs.data(), tabs.size() * 2, cudaMemcpyHostToDevice);
+    cudaDeviceProp prop{};
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    const int nzb = g.nz > 0 ? g.nz : 1;
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_zlo, nzb * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_zhi, nzb * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_zfix, nzb);
+    if (e == cudaSuccess && g.nz > 0) e = cudaMemcpy(m->d_zlo, m->z_lo.data(), g.nz * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && g.nz > 0) e = cudaMemcpy(m->d_zhi, m->z_hi.data(), g.nz * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_zfix, m->z_fix.data(), nzb, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&m->d_counters, PYDSB_CNT_COUNT * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(m->d_counters, 0, PYDSB_CNT_COUNT * sizeof(unsigned long long));
-    cudaDeviceProp prop{};
-    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
-    if (e == cudaSuccess && (size_t)g.smem_bytes > prop.sharedMemPerBlockOptin) {
-        pydsb_model_destroy(m);
-        return fail(PYDSB_ERR_UNSUPPORTED, "model needs " + std::to_string(g.smem_bytes) +
-                                               " B of shared memory per CTA, device offers " +
-                                               std::to_string(prop.sharedMemPerBlockOptin));
+    if (e == cudaSuccess) {
+        for (int q = 0; q < 2; ++q)
+            if (m->prog[q].present && (size_t)m->prog[q].img.smem_bytes > prop.sharedMemPerBlockOptin) {
+                pydsb_model_destroy(m);
+                return fail(PYDSB_ERR_UNSUPPORTED, "model needs more shared memory per CTA than the device offers");
+            }
     }
-    KernelFn fn = kernel_for(g.ns);
+    FeasFn fn = feas_for(g.ns);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
     int bps = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, BLOCK, g.smem_bytes);
@@ -298,9 +397,6 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
         pydsb_model_destroy(m);
         return fail(PYDSB_ERR_CUDA, msg);
     }
-    g.code = static_cast<const uint64_t*>(m->d_code);
-    g.consts = static_cast<const double*>(m->d_consts);
-    g.tabs = static_cast<const uint16_t*>(m->d_tabs);
     m->num_sms = prop.multiProcessorCount;
     m->blocks_per_sm = bps > 0 ? bps : 1;
     m->regs = fa.numRegs;
@@ -313,9 +409,11 @@ int pydsb_model_destroy(void* handle)
     Model* m = static_cast<Model*>(handle);
     if (!m) return PYDSB_OK;
     cudaSetDevice(m->device);
-    if (m->d_code) cudaFree(m->d_code);
-    if (m->d_consts) cudaFree(m->d_consts);
-    if (m->d_tabs) cudaFree(m->d_tabs);
+    free_program(m->prog[0]);
+    free_program(m->prog[1]);
+    if (m->d_zlo) cudaFree(m->d_zlo);
+    if (m->d_zhi) cudaFree(m->d_zhi);
+    if (m->d_zfix) cudaFree(m->d_zfix);
     if (m->d_counters) cudaFree(m->d_counters);
     if (m->d_partial) cudaFree(m->d_partial);
     if (m->d_stage) cudaFree(m->d_stage);
@@ -329,9 +427,9 @@ int pydsb_model_info(void* handle, long long* out, int n)
 {
     Model* m = static_cast<Model*>(handle);
     if (!m || !out) return fail(PYDSB_ERR_INVALID, "null handle/out");
-    long long v[PYDSB_INFO_COUNT] = {m->img.ns, m->img.nq, m->img.ng, m->img.d_dim, m->img.p_dim, m->img.nz,
-                                     m->img.nfe, 3, m->img.n_units, m->img.smem_bytes, m->blocks_per_sm,
-                                     m->num_sms, m->regs};
+    const ExecImage& g = m->prog[0].img;
+    long long v[PYDSB_INFO_COUNT] = {g.ns, g.nq, g.ng, g.d_dim, g.p_dim, g.nz, g.nfe, 3, g.n_units, g.smem_bytes,
+                                     m->blocks_per_sm, m->num_sms, m->regs};
     for (int i = 0; i < n && i < PYDSB_INFO_COUNT; ++i) out[i] = v[i];
     return PYDSB_OK;
 }
@@ -343,9 +441,10 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
     if (!m) return fail(PYDSB_ERR_INVALID, "null handle");
     if (n_d < 0 || n_t < 0) return fail(PYDSB_ERR_INVALID, "negative size");
     if (n_d == 0) return PYDSB_OK;
-    if (!theta || (!d && m->img.d_dim > 0)) return fail(PYDSB_ERR_INVALID, "null d/theta");
+    const ExecImage& img = m->prog[0].img;
+    if (!theta || (!d && img.d_dim > 0)) return fail(PYDSB_ERR_INVALID, "null d/theta");
     if (z_mode < 0 || z_mode > 3) return fail(PYDSB_ERR_INVALID, "bad z_mode");
-    if (z_mode != 0 && !z && m->img.nz > 0) return fail(PYDSB_ERR_INVALID, "z_mode needs a z array");
+    if (z_mode != 0 && !z && img.nz > 0) return fail(PYDSB_ERR_INVALID, "z_mode needs a z array");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(m->device));
     if (n_t == 0) {                     // empty theta set: P = 0 for every design point
@@ -367,12 +466,13 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
 
     const long long max_ctas = (long long)m->num_sms * m->blocks_per_sm;
     const int grid = (int)(total < max_ctas ? total : max_ctas);
-    KernelFn fn = kernel_for(m->img.ns);
+    FeasFn fn = feas_for(img.ns);
     // several models may share one template instantiation: (re)assert this model's smem size and
     // (re)load its point tape into the constant bank (stream ordered)
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, m->img.smem_bytes));
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_pt, m->xpt.data(), m->xpt.size() * sizeof(uint32_t), 0, cudaMemcpyHostToDevice, st));
-    fn<<<grid, BLOCK, m->img.smem_bytes, st>>>(m->img, la);
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_pt, m->prog[0].xpt.data(), m->prog[0].xpt.size() * sizeof(uint32_t), 0,
+                                     cudaMemcpyHostToDevice, st));
+    fn<<<grid, BLOCK, img.smem_bytes, st>>>(img, la);
     CUDA_TRY(cudaGetLastError());
     m->launches += 1;
     if (P_out) {
@@ -405,26 +505,24 @@ int pydsb_eval_host(void* handle, const double* d, long long n_d, const double* 
     if (n_d == 0) return PYDSB_OK;
     if (z_mode < 0 || z_mode > 3) return fail(PYDSB_ERR_INVALID, "bad z_mode");
     CUDA_TRY(cudaSetDevice(m->device));
-    const ExecImage& g = m->img;
+    const ExecImage& g = m->prog[0].img;
     const size_t nd = (size_t)n_d * g.d_dim, nth = (size_t)n_t * g.p_dim, nw = w ? (size_t)n_t : 0;
     size_t nz = 0;
     if (z && z_mode == 1) nz = g.nz;
     if (z && z_mode == 2) nz = (size_t)n_d * g.nz;
     if (z && z_mode == 3) nz = (size_t)n_d * n_t * g.nz;
-    const size_t n_in = nd + nth + nw + nz;
     const size_t ng = g_out ? (size_t)n_d * n_t * g.ng : 0, ni = ind_out ? (size_t)n_d * n_t : 0, np = P_out ? (size_t)n_d : 0;
     const size_t n_out = ng + ni + np;
     // layout (doubles): inputs padded so that theta starts 16-byte aligned
     const size_t o_d = 0, o_th = (nd + 1) / 2 * 2, o_w = o_th + nth, o_z = o_w + nw, o_out = (o_z + nz + 1) / 2 * 2;
     const size_t need = o_out + n_out;
-    (void)n_in;
     if (need > m->h_pin_cap) {
         if (m->h_pin) cudaFreeHost(m->h_pin);
         if (m->d_stage) cudaFree(m->d_stage);
-        m->h_pin = nullptr; m->d_stage = nullptr; m->h_pin_cap = m->d_stage_cap = 0;
+        m->h_pin = nullptr; m->d_stage = nullptr; m->h_pin_cap = 0;
         CUDA_TRY(cudaMallocHost(&m->h_pin, need * sizeof(double)));
         CUDA_TRY(cudaMalloc(&m->d_stage, need * sizeof(double)));
-        m->h_pin_cap = m->d_stage_cap = need;
+        m->h_pin_cap = need;
     }
     double* hp = m->h_pin;
     double* dp = m->d_stage;
@@ -445,6 +543,114 @@ int pydsb_eval_host(void* handle, const double* d, long long n_d, const double* 
     if (ng) memcpy(g_out, hp + o_out, ng * sizeof(double));
     if (ni) memcpy(ind_out, hp + o_out + ng, ni * sizeof(double));
     if (np) memcpy(P_out, hp + o_out + ng + ni, np * sizeof(double));
+    return PYDSB_OK;
+}
+
+int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long long n_d, const double* theta,
+                         const double* w, long long n_t, const double* z0, long long z0_rows, const double* opts,
+                         double* z_out, double* phi_out, int* status_out, int* iters_out, void* stream)
+{
+    Model* m = static_cast<Model*>(handle);
+    if (!m) return fail(PYDSB_ERR_INVALID, "null handle");
+    if (!m->prog[1].present) return fail(PYDSB_ERR_UNSUPPORTED, "blob carries no sensitivity program");
+    const ExecImage& img = m->prog[1].img;
+    const int nz = img.nz;
+    if (nz < 1) return fail(PYDSB_ERR_INVALID, "model has no control to optimise");
+    if (n_d < 0 || n_t < 1) return fail(PYDSB_ERR_INVALID, "bad sizes");
+    if (n_d == 0) return PYDSB_OK;
+    if (!d && img.d_dim > 0) return fail(PYDSB_ERR_INVALID, "null d");
+    if (!theta || !z_out) return fail(PYDSB_ERR_INVALID, "null theta/z_out");
+    const long long G = per_scenario ? n_d * n_t : n_d;
+    if (z0 && !(z0_rows == 1 || z0_rows == G)) return fail(PYDSB_ERR_INVALID, "z0 must have 1 or G rows");
+    // options: mu0, mu_min, lam0, step_tol, max_iter, check_every
+    double o[6] = {1e-4, 1e-9, 1e-3, 1e-8, 200, 4};
+    if (opts)
+        for (int i = 0; i < 6; ++i)
+            if (opts[i] > 0) o[i] = opts[i];
+    const int max_iter = (int)o[4], check_every = (int)o[5] < 1 ? 1 : (int)o[5];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(m->device));
+
+    const int n_tiles = (int)((n_t + BLOCK - 1) / BLOCK);
+    const int NV = recourse_nv(nz);
+    const int acc_per_group = per_scenario ? 1 : n_tiles;
+    // workspace: doubles then ints
+    const size_t nd_dbl = (size_t)G * (2 * nz + 2 + nz + (size_t)nz * nz + 2) + (size_t)G * acc_per_group * NV;
+    const size_t nd_int = (size_t)G * 3 + 1;
+    double* ws = nullptr;
+    int* wsi = nullptr;
+    CUDA_TRY(cudaMalloc(&ws, nd_dbl * sizeof(double)));
+    if (cudaMalloc(&wsi, nd_int * sizeof(int)) != cudaSuccess) {
+        cudaFree(ws);
+        return fail(PYDSB_ERR_CUDA, "cudaMalloc(workspace)");
+    }
+    double* z_cur = ws;
+    double* z_try = z_cur + (size_t)G * nz;
+    double* F_cur = z_try + (size_t)G * nz;
+    double* raw_cur = F_cur + G;
+    double* gr = raw_cur + G;
+    double* Hh = gr + (size_t)G * nz;
+    double* lam = Hh + (size_t)G * nz * nz;
+    double* mu = lam + G;
+    double* acc = mu + G;
+    int* status = wsi;
+    int* first = status + G;
+    int* iters = first + G;
+    int* n_running = iters + G;
+
+    auto cleanup = [&]() { cudaFree(ws); cudaFree(wsi); };
+#define CUDA_TRY_WS(expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            cleanup();                                                                            \
+            return fail(PYDSB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+        }                                                                                         \
+    } while (0)
+
+    const int tb = 128;
+    const unsigned gb = (unsigned)((G + tb - 1) / tb);
+    lm_init_kernel<<<gb, tb, 0, st>>>(G, nz, z0, (int)(z0 ? z0_rows : 0), z_cur, z_try, F_cur, raw_cur, lam, mu, status,
+                                      first, iters, o[2], o[0]);
+    CUDA_TRY_WS(cudaGetLastError());
+    SensFn fn = sens_for(img.ns);
+    CUDA_TRY_WS(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
+    CUDA_TRY_WS(cudaMemcpyToSymbolAsync(c_pt_s, m->prog[1].xpt.data(), m->prog[1].xpt.size() * sizeof(uint32_t), 0,
+                                        cudaMemcpyHostToDevice, st));
+    RecourseArgs ra{};
+    ra.d = d; ra.theta = theta; ra.w = w; ra.n_d = n_d; ra.n_t = n_t; ra.n_tiles = n_tiles;
+    ra.per_scenario = per_scenario ? 1 : 0;
+    ra.z_try = z_try; ra.status = status; ra.mu = mu; ra.acc = acc; ra.counters = m->d_counters;
+    ra.sens_slot = img.n_units;
+    LmArgs la{};
+    la.n_groups = G; la.nz = nz; la.n_tiles = acc_per_group; la.acc = acc; la.lo = m->d_zlo; la.hi = m->d_zhi;
+    la.zfix = m->d_zfix; la.z_cur = z_cur; la.z_try = z_try; la.F_cur = F_cur; la.raw_cur = raw_cur; la.gr = gr; la.H = Hh;
+    la.lam = lam; la.mu = mu; la.status = status; la.first = first; la.iters = iters; la.n_running = n_running;
+    la.mu_min = o[1]; la.lam0 = o[2]; la.step_tol = o[3]; la.max_iter = max_iter;
+    const long long total_tiles = n_d * (long long)n_tiles;
+    if (total_tiles > 0x7fffffffLL) { cleanup(); return fail(PYDSB_ERR_INVALID, "grid too large"); }
+    // every group stops after max_iter evaluations (status 3) at the latest
+    for (int it = 0; it < max_iter + 1; ++it) {
+        CUDA_TRY_WS(cudaMemsetAsync(n_running, 0, sizeof(int), st));
+        fn<<<(unsigned)total_tiles, BLOCK, img.smem_bytes, st>>>(img, ra);
+        CUDA_TRY_WS(cudaGetLastError());
+        lm_update_kernel<<<gb, tb, 0, st>>>(la);
+        CUDA_TRY_WS(cudaGetLastError());
+        m->launches += 2;
+        if ((it + 1) % check_every == 0 || it == max_iter) {
+            int running = 0;
+            CUDA_TRY_WS(cudaMemcpyAsync(&running, n_running, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY_WS(cudaStreamSynchronize(st));
+            if (running == 0) break;
+        }
+    }
+    CUDA_TRY_WS(cudaMemcpyAsync(z_out, z_cur, (size_t)G * nz * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (phi_out) CUDA_TRY_WS(cudaMemcpyAsync(phi_out, raw_cur, (size_t)G * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (status_out) CUDA_TRY_WS(cudaMemcpyAsync(status_out, status, (size_t)G * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (iters_out) CUDA_TRY_WS(cudaMemcpyAsync(iters_out, iters, (size_t)G * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY_WS(cudaStreamSynchronize(st));
+    cleanup();
+#undef CUDA_TRY_WS
     return PYDSB_OK;
 }
 

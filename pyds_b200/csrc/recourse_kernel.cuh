@@ -1,0 +1,506 @@
+// Batched control (recourse) optimisation: the GPU replacement for the NLP solve the reference
+// hands to GAMS/CONOPT once per design point (reference pyds/solver.py:26-55; the model is the
+// big-M relaxation of pyds/utils.py:7-51).  Eliminating the relaxed indicators
+// leaves, per group of scenarios that share a control vector z,
+//
+//     min_{z in box}  Phi(z) = sum_s w_s max(0, max_k g_ks(z) / M_k)
+//
+// minimised by projected Levenberg-Marquardt steps on the log-sum-exp smoothing
+// phi_mu(c) = mu log(1 + sum_k exp(c_k/mu)), mu -> mu_min (the primal form of the barrier an
+// interior-point method would use), with a Gauss-Newton Hessian built from forward control
+// sensitivities.  One iteration = two launches:
+//
+//   sens_kernel<NS>   thread per scenario: state solve as in feas_kernel, plus per finite element the
+//                     sensitivity systems  M dX_c = -dR/dx_prev S_c - dR/dz_c  solved with the LU
+//                     factors of the converged Newton matrix (register resident); then c_k, grad c_k,
+//                     softmax weights, and the per-group sums {Phi_mu, Phi, grad, H} reduced with warp
+//                     shuffles (shared mode) or written per scenario (per-scenario mode)
+//   lm_update_kernel  thread per group: accept / reject, damping and mu schedule, active-set
+//                     projected step by Cholesky (nz <= 16), convergence mask.
+//
+// Groups: shared mode -> one group per design point (the reference's two-stage formulation: stage-0
+// F_in shared by every theta); per-scenario mode -> one group per (d, theta).
+#pragma once
+#include "feas_kernel.cuh"
+
+namespace pydsb {
+
+#define PT_LD(off) (*reinterpret_cast<const double*>(base + (off)))
+
+constexpr int MAX_NZ = 16;
+
+struct RecourseArgs {
+    const double* d;
+    const double* theta;
+    const double* w;           // may be null -> 1/n_t (shared) ; per-scenario mode uses weight 1
+    long long n_d, n_t;
+    int n_tiles;
+    int per_scenario;          // 0: group = design point, 1: group = scenario
+    // per-group optimiser state
+    double* z_try;             // (G, nz)   evaluated by sens_kernel
+    const int* status;         // (G)       0 = running
+    const double* mu;          // (G)
+    double* acc;               // shared: (n_d, n_tiles, NV) tile partials ; per-scenario: (G, NV)
+    unsigned long long* counters;
+    int sens_slot;             // first unit of the per-thread sensitivity block (after the program's units)
+};
+
+__host__ __device__ inline int recourse_nv(int nz) { return 2 + nz + nz * (nz + 1) / 2; }
+
+template <int NS>
+__global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
+    sens_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ RecourseArgs ra)
+{
+    constexpr int N = 3 * NS;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    uint64_t* code = reinterpret_cast<uint64_t*>(smem + img.off_code);
+    double* cpool = reinterpret_cast<double*>(smem + img.off_const) + 1;
+    uint16_t* tabs = reinterpret_cast<uint16_t*>(smem + img.off_tabs);
+    double* wsum = reinterpret_cast<double*>(smem + img.off_land);      // [BLOCK/32][NV] (reuses the landing area)
+    double* S = reinterpret_cast<double*>(smem + img.off_slots) + tid;
+
+    const int n_code = img.n_pro + img.n_elem + img.n_g;
+    for (int i = tid; i < n_code; i += BLOCK) code[i] = img.code[i];
+    for (int i = tid; i < img.n_const; i += BLOCK) cpool[i] = img.consts[i];
+    for (int i = tid; i < img.n_tabs; i += BLOCK) tabs[i] = img.tabs[i];
+    if (tid == 0) cpool[-1] = 0.0;
+    __syncthreads();
+
+    const uint64_t* code_pro = code;
+    const uint64_t* code_elem = code_pro + img.n_pro;
+    const uint64_t* code_g = code_elem + img.n_elem;
+    const uint16_t* tab_par = tabs;
+    const uint16_t* tab_x0 = tab_par + img.d_dim + img.p_dim;
+    const uint16_t* tab_q0 = tab_x0 + img.ns;
+    const uint16_t* tab_z = tab_q0 + img.nq;
+    const uint16_t* tab_zfix = tab_z + img.nz;
+    const uint16_t* tab_g = tab_zfix + img.nz;
+    const uint16_t* tab_cmap = tab_g + img.ng;
+    const uint16_t* tab_gx = tab_cmap + img.nfe * img.nce;
+    const uint16_t* tab_gq = tab_gx + img.ng * img.ns;
+    const uint16_t* tab_live = tab_gq + img.ng * img.nq;       // [nfe] bit c: control c acted in an element <= e
+
+    VM vm;
+    vm.S = S;
+    vm.cpool = cpool;
+    char* const base = reinterpret_cast<char*>(S);
+    double* const Xs = S + img.x_slot * BLOCK;
+    const int nz = img.nz, nq = img.nq, ng = img.ng;
+    double* const Sx = S + (size_t)ra.sens_slot * BLOCK;       // Sx[n*nz + c]
+    double* const Sq = Sx + (size_t)NS * nz * BLOCK;           // Sq[q*nz + c]
+    double* const Dc = Sq + (size_t)nq * nz * BLOCK;           // Dc[k*nz + c] = d c_k / d z_c
+    const double h = 1.0 / (double)img.nfe;
+    const int NV = recourse_nv(nz);
+
+    const long long t = blockIdx.x;
+    const long long i_d = t / ra.n_tiles;
+    const long long j0 = (t % ra.n_tiles) * (long long)BLOCK;
+    const long long rem = ra.n_t - j0;
+    const int rows = rem < BLOCK ? (int)rem : BLOCK;
+    const bool valid = tid < rows;
+    const int row = valid ? tid : rows - 1;
+    const long long j = j0 + row;
+    const long long grp = ra.per_scenario ? (i_d * ra.n_t + j) : i_d;
+    if (!ra.per_scenario && ra.status[i_d] != 0) return;        // block-uniform: group already finished
+    const bool active = valid && ra.status[grp] == 0;
+    if (!__syncthreads_or(active)) return;
+
+    for (int c = 0; c < img.p_dim; ++c) S[tab_par[img.d_dim + c] * BLOCK] = __ldg(ra.theta + j * img.p_dim + c);
+    for (int c = 0; c < img.d_dim; ++c) S[tab_par[c] * BLOCK] = __ldg(ra.d + i_d * img.d_dim + c);
+    const double* zg = ra.z_try + grp * nz;
+
+    run_narrow_tape(S, cpool, code_pro, img.n_pro);
+    double xs[NS];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) xs[n] = vm_ld(vm, tab_x0[n]);
+    for (int q = 0; q < nq; ++q) S[(img.qe_slot + q) * BLOCK] = vm_ld(vm, tab_q0[q]);
+    for (int i = 0; i < (NS + nq) * nz; ++i) Sx[(size_t)i * BLOCK] = 0.0;
+
+    bool failed = false;
+    unsigned my_iters = 0;
+    for (int e = 0; e < img.nfe; ++e) {
+        for (int c = 0; c < img.nce; ++c) {
+            const int zi = tab_cmap[e * img.nce + c];
+            S[(img.ctrl_slot + c) * BLOCK] = tab_zfix[zi] ? vm_ld(vm, tab_z[zi]) : __ldg(zg + zi);
+        }
+        run_narrow_tape(S, cpool, code_elem, img.n_elem);
+        double xv[3][NS];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            xv[0][n] = xv[1][n] = xv[2][n] = xs[n];
+            Xs[(3 * n + 0) * BLOCK] = xs[n];
+            Xs[(3 * n + 1) * BLOCK] = xs[n];
+            Xs[(3 * n + 2) * BLOCK] = xs[n];
+        }
+        bool conv = !active, stop = false;
+        double s_prev = 0.0;
+        double M[N][N], inv[N], r[N];
+        for (int it = 0;; ++it) {
+            run_point_tape<true>(base, img.n_pt);
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj)
+#pragma unroll
+                for (int n = 0; n < NS; ++n) {
+                    double lin = img.adot[jj + 1] * xs[n];
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
+                    r[jj * NS + n] = fma(h, PT_LD(img.f_off[n] + jj * img.f_str[n]), -lin);
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+                        for (int m = 0; m < NS; ++m) {
+                            const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
+                            M[jj * NS + n][kk * NS + m] = a;
+                            if (kk == jj && ((img.j_mask >> (n * NS + m)) & 1u))
+                                M[jj * NS + n][kk * NS + m] =
+                                    fma(-h, PT_LD(img.j_off[n * NS + m] + jj * img.j_str[n * NS + m]), a);
+                        }
+                }
+            lu_factor<N>(M, inv);                       // at the last pass: factors at the converged point
+            if (stop) break;
+            lu_apply<N>(M, inv, r);
+            double s = 0.0, sc = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+                for (int n = 0; n < NS; ++n) {
+                    const double dx = r[kk * NS + n];
+                    const double xn = xv[kk][n] + dx;
+                    xv[kk][n] = xn;
+                    Xs[(3 * n + kk) * BLOCK] = xn;
+                    s = fma(dx, dx, s);
+                    sc = fma(xn, xn, sc);
+                }
+            if (!conv) ++my_iters;
+            const double lim = img.rtol2 * fmax(sc, 1.0);
+            const bool bad = !(s <= DBL_MAX);
+            const bool ok = (s <= lim) || (s * s <= lim * s_prev && s <= 0.01 * s_prev);
+            s_prev = s;
+            if (bad && active) failed = true;
+            if (ok || bad) conv = true;
+            stop = __all_sync(0xffffffffu, conv) || (it + 1 >= img.max_it);
+        }
+        if (!conv) failed = true;
+
+        // quadratures at the converged points
+        for (int q = 0; q < nq; ++q) {
+            if (!((img.fq_mask >> q) & 1u)) continue;
+            double acc = img.bw[0] * PT_LD(img.fq_off[q]);
+            acc = fma(img.bw[1], PT_LD(img.fq_off[q] + img.fq_str[q]), acc);
+            acc = fma(img.bw[2], PT_LD(img.fq_off[q] + 2 * img.fq_str[q]), acc);
+            S[(img.qe_slot + q) * BLOCK] = fma(h, acc, S[(img.qe_slot + q) * BLOCK]);
+        }
+        // forward sensitivities of this element with respect to every control that has acted so far
+        const unsigned live = tab_live[e];
+        for (int c = 0; c < nz; ++c) {
+            if (!((live >> c) & 1u)) continue;
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj)
+#pragma unroll
+                for (int n = 0; n < NS; ++n) r[jj * NS + n] = -img.adot[jj + 1] * Sx[(size_t)(n * nz + c) * BLOCK];
+            for (int k = 0; k < img.nce; ++k) {
+                if (tab_cmap[e * img.nce + k] != c) continue;
+#pragma unroll
+                for (int n = 0; n < NS; ++n) {
+                    const int idx = n * img.nce + k;
+                    if (!((img.fz_mask >> idx) & 1u)) continue;
+#pragma unroll
+                    for (int jj = 0; jj < 3; ++jj)
+                        r[jj * NS + n] = fma(h, PT_LD(img.fz_off[idx] + jj * img.fz_str[idx]), r[jj * NS + n]);
+                }
+            }
+            lu_apply<N>(M, inv, r);
+#pragma unroll
+            for (int n = 0; n < NS; ++n) Sx[(size_t)(n * nz + c) * BLOCK] = r[2 * NS + n];
+            for (int q = 0; q < nq; ++q) {
+                double acc = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj) {
+                    double tq = 0.0;
+#pragma unroll
+                    for (int n = 0; n < NS; ++n) {
+                        const int idx = q * NS + n;
+                        if ((img.fqx_mask >> idx) & 1u)
+                            tq = fma(PT_LD(img.fqx_off[idx] + jj * img.fqx_str[idx]), r[jj * NS + n], tq);
+                    }
+                    for (int k = 0; k < img.nce; ++k) {
+                        const int idx = q * img.nce + k;
+                        if (tab_cmap[e * img.nce + k] == c && ((img.fqz_mask >> idx) & 1u))
+                            tq += PT_LD(img.fqz_off[idx] + jj * img.fqz_str[idx]);
+                    }
+                    acc = fma(img.bw[jj], tq, acc);
+                }
+                Sq[(size_t)(q * nz + c) * BLOCK] = fma(h, acc, Sq[(size_t)(q * nz + c) * BLOCK]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NS; ++n) xs[n] = xv[2][n];
+    }
+
+    // ---- scaled constraints c_k = g_k / M_k and their control gradients ----
+#pragma unroll
+    for (int n = 0; n < NS; ++n) S[(img.xe_slot + n) * BLOCK] = xs[n];
+    run_narrow_tape(S, cpool, code_g, img.n_g);
+    double cmax = 0.0;                       // max(0, max_k c_k)
+    double ck[8];
+    for (int k = 0; k < ng; ++k) {
+        ck[k] = vm_ld(vm, tab_g[k]) * img.bigm_inv[k];
+        cmax = fmax(cmax, ck[k]);
+        for (int c = 0; c < nz; ++c) {
+            double v = 0.0;
+            if (!tab_zfix[c]) {
+#pragma unroll
+                for (int n = 0; n < NS; ++n) v = fma(vm_ld(vm, tab_gx[k * NS + n]), Sx[(size_t)(n * nz + c) * BLOCK], v);
+                for (int q = 0; q < nq; ++q) v = fma(vm_ld(vm, tab_gq[k * nq + q]), Sq[(size_t)(q * nz + c) * BLOCK], v);
+                v *= img.bigm_inv[k];
+            }
+            Dc[(size_t)(k * nz + c) * BLOCK] = v;
+        }
+    }
+    // smoothed hinge: phi = m + mu log(e^{-m/mu} + sum_k e^{(c_k-m)/mu}),  p_k = softmax weights
+    const double mu = ra.mu[grp];
+    double wv = 0.0;
+    if (active) wv = ra.per_scenario ? 1.0 : (ra.w ? __ldg(ra.w + j) : 1.0 / (double)ra.n_t);
+    double pk[8];
+    double phi, raw;
+    if (failed) {                            // a failed state solve counts as indicator 1 with no slope
+        phi = raw = 1.0;
+        for (int k = 0; k < ng; ++k) pk[k] = 0.0;
+    } else {
+        double Z = exp(-cmax / mu);
+        for (int k = 0; k < ng; ++k) { pk[k] = exp((ck[k] - cmax) / mu); Z += pk[k]; }
+        const double zi = 1.0 / Z;
+        for (int k = 0; k < ng; ++k) pk[k] *= zi;
+        phi = cmax + mu * log(Z);
+        raw = cmax;
+    }
+    // v_c = sum_k p_k dc_kc kept in the (now free) Sx block
+    double* const Vv = Sx;
+    for (int c = 0; c < nz; ++c) {
+        double v = 0.0;
+        for (int k = 0; k < ng; ++k) v = fma(pk[k], Dc[(size_t)(k * nz + c) * BLOCK], v);
+        Vv[(size_t)c * BLOCK] = v;
+    }
+    const double wmu = wv / mu;
+    double* out = ra.per_scenario ? (ra.acc + grp * NV) : nullptr;
+    auto emit = [&](int idx, double val) {
+        if (ra.per_scenario) {
+            if (active) out[idx] = val;
+        } else {
+            const double sm = warp_sum(val);
+            if (lane == 0) wsum[warp * NV + idx] = sm;
+        }
+    };
+    emit(0, wv * phi);
+    emit(1, wv * raw);
+    for (int c = 0; c < nz; ++c) emit(2 + c, wv * Vv[(size_t)c * BLOCK]);
+    int idx = 2 + nz;
+    for (int a = 0; a < nz; ++a)
+        for (int b = a; b < nz; ++b, ++idx) {
+            double hv = 0.0;
+            for (int k = 0; k < ng; ++k) hv = fma(pk[k] * Dc[(size_t)(k * nz + a) * BLOCK], Dc[(size_t)(k * nz + b) * BLOCK], hv);
+            hv = fma(-Vv[(size_t)a * BLOCK], Vv[(size_t)b * BLOCK], hv);
+            emit(idx, wmu * hv);
+        }
+    if (!ra.per_scenario) {
+        __syncthreads();
+        for (int v = tid; v < NV; v += BLOCK) {
+            double sm = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < BLOCK / 32; ++wq) sm += wsum[wq * NV + v];     // fixed order: deterministic
+            ra.acc[(i_d * ra.n_tiles + (t % ra.n_tiles)) * NV + v] = sm;
+        }
+    }
+    if (ra.counters) {
+        const unsigned it_sum = warp_sum_u32(active ? my_iters : 0u);
+        const unsigned dn = warp_sum_u32(active ? 1u : 0u);
+        const unsigned fl = warp_sum_u32((active && failed) ? 1u : 0u);
+        if (lane == 0) {
+            atomicAdd(&ra.counters[0], (unsigned long long)dn);
+            atomicAdd(&ra.counters[1], (unsigned long long)it_sum);
+            atomicAdd(&ra.counters[3], (unsigned long long)fl);
+        }
+    }
+}
+
+struct LmArgs {
+    long long n_groups;
+    int nz, n_tiles;           // n_tiles = partial sums per group (1 in per-scenario mode)
+    const double* acc;         // (G, n_tiles, NV)
+    const double* lo;
+    const double* hi;
+    const unsigned char* zfix;
+    double* z_cur;
+    double* z_try;
+    double* F_cur;
+    double* raw_cur;
+    double* gr;                // (G, nz)
+    double* H;                 // (G, nz, nz)
+    double* lam;
+    double* mu;
+    int* status;
+    int* first;
+    int* iters;
+    int* n_running;            // device counter of groups still running after this update
+    double mu_min, lam0, step_tol;
+    int max_iter;
+};
+
+// One thread per group: the accept/reject + step logic of oracle/recourse.py::minimize_hinge.
+__global__ void lm_update_kernel(const LmArgs a)
+{
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= a.n_groups) return;
+    if (a.status[g] != 0) return;
+    const int nz = a.nz;
+    const int NV = recourse_nv(nz);
+    double F_t = 0.0, raw_t = 0.0, g_t[MAX_NZ], H_t[MAX_NZ * MAX_NZ];
+    for (int c = 0; c < nz; ++c) g_t[c] = 0.0;
+    for (int i = 0; i < nz * nz; ++i) H_t[i] = 0.0;
+    for (int t = 0; t < a.n_tiles; ++t) {
+        const double* p = a.acc + (g * a.n_tiles + t) * NV;
+        F_t += p[0];
+        raw_t += p[1];
+        for (int c = 0; c < nz; ++c) g_t[c] += p[2 + c];
+        int idx = 2 + nz;
+        for (int r = 0; r < nz; ++r)
+            for (int c = r; c < nz; ++c, ++idx) H_t[r * nz + c] += p[idx];
+    }
+    for (int r = 0; r < nz; ++r)
+        for (int c = 0; c < r; ++c) H_t[r * nz + c] = H_t[c * nz + r];
+
+    double* zc = a.z_cur + g * nz;
+    double* zt = a.z_try + g * nz;
+    double* gr = a.gr + g * nz;
+    double* H = a.H + g * nz * nz;
+    a.iters[g] += 1;
+    bool converged_here = false;
+    bool done = false;
+    if (raw_t == 0.0) {                       // every scenario of the group is feasible: Phi = 0 exactly
+        for (int c = 0; c < nz; ++c) zc[c] = zt[c];
+        a.raw_cur[g] = 0.0;
+        a.status[g] = 1;
+        done = true;
+    }
+    if (!done) {
+        const bool first = a.first[g] != 0;
+        if (first || F_t < a.F_cur[g]) {
+            double moved = 0.0;
+            for (int c = 0; c < nz; ++c) {
+                const double span = (a.hi[c] - a.lo[c] <= DBL_MAX) ? (a.hi[c] - a.lo[c]) : 1.0;
+                moved = fmax(moved, fabs(zt[c] - zc[c]) / span);
+            }
+            const bool small = !first && (moved <= a.step_tol || a.F_cur[g] - F_t <= 1e-13 * fmax(F_t, 1e-300));
+            for (int c = 0; c < nz; ++c) { zc[c] = zt[c]; gr[c] = g_t[c]; }
+            for (int i = 0; i < nz * nz; ++i) H[i] = H_t[i];
+            a.F_cur[g] = F_t;
+            a.raw_cur[g] = raw_t;
+            if (!first) a.lam[g] = fmax(a.lam[g] / 3.0, 1e-12);
+            a.first[g] = 0;
+            converged_here = small;
+        } else {
+            a.lam[g] = a.lam[g] * 4.0;
+            if (a.lam[g] >= 1e12) converged_here = true;
+        }
+        if (!converged_here) {
+            // projected LM step on the free set
+            int idx[MAX_NZ], nf = 0;
+            for (int c = 0; c < nz; ++c) {
+                const bool at_lo = zc[c] <= a.lo[c] && gr[c] > 0.0;
+                const bool at_hi = zc[c] >= a.hi[c] && gr[c] < 0.0;
+                if (!a.zfix[c] && !at_lo && !at_hi) idx[nf++] = c;
+            }
+            double step[MAX_NZ];
+            for (int c = 0; c < nz; ++c) step[c] = 0.0;
+            if (nf > 0) {
+                double dmax = 0.0;
+                for (int i = 0; i < nf; ++i) dmax = fmax(dmax, H[idx[i] * nz + idx[i]]);
+                const double floor_ = 1e-8 * fmax(dmax, 0.0) + 1e-300;
+                double l = a.lam[g];
+                for (int attempt = 0; attempt < 12; ++attempt) {
+                    double A[MAX_NZ * MAX_NZ];
+                    for (int i = 0; i < nf; ++i)
+                        for (int jx = 0; jx < nf; ++jx) A[i * nf + jx] = H[idx[i] * nz + idx[jx]];
+                    for (int i = 0; i < nf; ++i) A[i * nf + i] += l * (H[idx[i] * nz + idx[i]] + floor_) + 1e-30;
+                    bool okc = true;                       // in-place Cholesky A = L L^T
+                    for (int i = 0; i < nf && okc; ++i)
+                        for (int jx = 0; jx <= i; ++jx) {
+                            double sum = A[i * nf + jx];
+                            for (int k = 0; k < jx; ++k) sum -= A[i * nf + k] * A[jx * nf + k];
+                            if (i == jx) {
+                                if (!(sum > 0.0)) { okc = false; break; }
+                                A[i * nf + i] = sqrt(sum);
+                            } else {
+                                A[i * nf + jx] = sum / A[jx * nf + jx];
+                            }
+                        }
+                    if (!okc) { l *= 10.0; continue; }
+                    double y[MAX_NZ];
+                    for (int i = 0; i < nf; ++i) {
+                        double sum = -gr[idx[i]];
+                        for (int k = 0; k < i; ++k) sum -= A[i * nf + k] * y[k];
+                        y[i] = sum / A[i * nf + i];
+                    }
+                    for (int i = nf - 1; i >= 0; --i) {
+                        double sum = y[i];
+                        for (int k = i + 1; k < nf; ++k) sum -= A[k * nf + i] * y[k];
+                        y[i] = sum / A[i * nf + i];
+                    }
+                    for (int i = 0; i < nf; ++i) step[idx[i]] = y[i];
+                    break;
+                }
+            }
+            bool same = true;
+            for (int c = 0; c < nz; ++c) {
+                const double zn = fmin(fmax(zc[c] + step[c], a.lo[c]), a.hi[c]);
+                if (zn != zc[c]) same = false;
+                step[c] = zn;
+            }
+            if (same) converged_here = true;
+            else for (int c = 0; c < nz; ++c) zt[c] = step[c];
+        }
+        if (converged_here) {
+            if (a.mu[g] <= a.mu_min * 1.0001) {
+                a.status[g] = 2;
+                done = true;
+            } else {
+                a.mu[g] = fmax(a.mu[g] / 10.0, a.mu_min);
+                a.first[g] = 1;
+                a.lam[g] = a.lam0;
+                for (int c = 0; c < nz; ++c) zt[c] = zc[c];
+            }
+        }
+        if (!done && a.iters[g] >= a.max_iter) {
+            a.status[g] = 3;
+            done = true;
+        }
+    }
+    if (!done) atomicAdd(a.n_running, 1);
+}
+
+__global__ void lm_init_kernel(long long n_groups, int nz, const double* z0, int z0_rows, double* z_cur, double* z_try,
+                               double* F_cur, double* raw_cur, double* lam, double* mu, int* status, int* first, int* iters,
+                               double lam0, double mu0)
+{
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    for (int c = 0; c < nz; ++c) {
+        const double v = z0 ? z0[(z0_rows > 1 ? g : 0) * nz + c] : 0.0;
+        z_cur[g * nz + c] = v;
+        z_try[g * nz + c] = v;
+    }
+    F_cur[g] = DBL_MAX;
+    raw_cur[g] = DBL_MAX;
+    lam[g] = lam0;
+    mu[g] = mu0;
+    status[g] = 0;
+    first[g] = 1;
+    iters[g] = 0;
+}
+
+#undef PT_LD
+
+}  // namespace pydsb

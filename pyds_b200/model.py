@@ -192,41 +192,67 @@ class DaeModel:
                 cmap[e, k] = c.z0 + (e if c.pieces > 1 else 0)
         nz = len(z_exprs)
 
+        for e in gk:
+            for n in T.topo_order([e]):
+                if n.op in ("ctrl", "x"):
+                    raise ValueError("constraints may use end-point values m.end(state) and parameters only")
         roots = {"x0": x0, "q0": q0, "z": z_exprs, "f": f, "J": J, "fq": fq, "g": gk}
-        low = T.lower(g, n_param=self.n_param, n_ctrl_elem=nce, ns=ns, nq=nq, roots=roots, ncp=self.ncp)
-        lay = low.layout
+        # program 1 ("sens") adds what forward control sensitivities need: df/dz, dfq/dx, dfq/dz, dg/dxe, dg/dqe
+        roots_s = dict(roots)
+        roots_s["fz"] = [g.diff(f[r], g.ctrl(k)) for r in range(ns) for k in range(nce)]
+        roots_s["fqx"] = [g.diff(fq[q], g.x(c)) for q in range(nq) for c in range(ns)]
+        roots_s["fqz"] = [g.diff(fq[q], g.ctrl(k)) for q in range(nq) for k in range(nce)]
+        roots_s["gx"] = [g.diff(gk[k], g.xe(c)) for k in range(ng) for c in range(ns)]
+        roots_s["gq"] = [g.diff(gk[k], g.qe(q)) for k in range(ng) for q in range(nq)]
         tau, adot, bw = radau_tables(self.ncp)
-
         secs = []
 
         def sec(tag, dtype, arr):
             arr = np.ascontiguousarray(np.asarray(arr, dtype=_NP[dtype]).reshape(-1))
             secs.append((tag, dtype, arr))
 
-        sec("HEAD", "u32", [ns, nq, ng, len(self.d_names), len(self.p_names), nz, self.nfe, self.ncp, nce,
-                            lay.n_units, lay.ctrl_slot, lay.xe_slot, lay.qe_slot, lay.x_slot, self.newton_max_it,
-                            lay.j_mask, lay.fq_state_dep, 1 if self.predictor else 0])
-        sec("RPAR", "u16", lay.param_slots)
-        sec("DBLS", "f64", [self.newton_rtol])
-        sec("CNST", "f64", low.consts if len(low.consts) else [0.0])
-        sec("ADOT", "f64", adot)
-        sec("BWTS", "f64", bw)
-        sec("BIGM", "f64", [m for _, _, m in self.constraints])
-        sec("ZLOW", "f64", z_lo if nz else [0.0])
-        sec("ZHIG", "f64", z_hi if nz else [0.0])
-        sec("ZFIX", "u16", z_fixed if nz else [0])
-        sec("TPRO", "u64", low.code["pro"])
-        sec("TELM", "u64", low.code["elem"])
-        sec("TPNT", "u64", low.code["pt"])
-        sec("TGEE", "u64", low.code["g"])
-        sec("RX0_", "u16", low.refs["x0"])
-        sec("RQ0_", "u16", low.refs["q0"] if nq else [T.REF_NONE])
-        sec("RZ__", "u16", low.refs["z"] if nz else [T.REF_NONE])
-        sec("RF__", "u16", low.refs["f"])
-        sec("RJ__", "u16", low.refs["J"])
-        sec("RFQ_", "u16", low.refs["fq"] if nq else [T.REF_NONE])
-        sec("RG__", "u16", low.refs["g"])
-        sec("CMAP", "u16", cmap)
+        def tab(low, name, n):
+            return low.refs[name] if n else [T.REF_NONE]
+
+        lows = []
+        for prog, rts in enumerate((roots, roots_s)):
+            low = T.lower(g, n_param=self.n_param, n_ctrl_elem=nce, ns=ns, nq=nq, roots=rts, ncp=self.ncp)
+            lows.append(low)
+            lay = low.layout
+            if prog:
+                sec("PSEP", "u32", [prog])
+            sec("HEAD", "u32", [ns, nq, ng, len(self.d_names), len(self.p_names), nz, self.nfe, self.ncp, nce,
+                                lay.n_units, lay.ctrl_slot, lay.xe_slot, lay.qe_slot, lay.x_slot, self.newton_max_it,
+                                lay.j_mask, lay.fq_state_dep, 1 if self.predictor else 0])
+            sec("RPAR", "u16", lay.param_slots)
+            sec("DBLS", "f64", [self.newton_rtol])
+            sec("CNST", "f64", low.consts if len(low.consts) else [0.0])
+            sec("ADOT", "f64", adot)
+            sec("BWTS", "f64", bw)
+            sec("BIGM", "f64", [m for _, _, m in self.constraints])
+            sec("ZLOW", "f64", z_lo if nz else [0.0])
+            sec("ZHIG", "f64", z_hi if nz else [0.0])
+            sec("ZFIX", "u16", z_fixed if nz else [0])
+            sec("TPRO", "u64", low.code["pro"])
+            sec("TELM", "u64", low.code["elem"])
+            sec("TPNT", "u64", low.code["pt"])
+            sec("TGEE", "u64", low.code["g"])
+            sec("RX0_", "u16", low.refs["x0"])
+            sec("RQ0_", "u16", tab(low, "q0", nq))
+            sec("RZ__", "u16", tab(low, "z", nz))
+            sec("RF__", "u16", low.refs["f"])
+            sec("RJ__", "u16", low.refs["J"])
+            sec("RFQ_", "u16", tab(low, "fq", nq))
+            sec("RG__", "u16", low.refs["g"])
+            sec("CMAP", "u16", cmap)
+            if prog:
+                sec("RFZ_", "u16", tab(low, "fz", ns * nce))
+                sec("RFQX", "u16", tab(low, "fqx", nq * ns))
+                sec("RFQZ", "u16", tab(low, "fqz", nq * nce))
+                sec("RGX_", "u16", tab(low, "gx", ng * ns))
+                sec("RGQ_", "u16", tab(low, "gq", ng * nq))
+        low = lows[0]
+        lay = low.layout
 
         blob = bytearray(struct.pack("<IIII", BLOB_MAGIC, BLOB_VERSION, len(secs), 0))
         for tag, dtype, arr in secs:
@@ -238,6 +264,7 @@ class DaeModel:
             blob=bytes(blob), ns=ns, nq=nq, ng=ng, nz=nz, d_dim=len(self.d_names), p_dim=len(self.p_names),
             nfe=self.nfe, ncp=self.ncp, n_units=lay.n_units, tapes=low, dyn_states=[self.states[i].name for i in dyn],
             quad_states=[self.states[i].name for i in quad], z_lo=np.asarray(z_lo), z_hi=np.asarray(z_hi),
+            tapes_sens=lows[1], z_init=z_exprs,
             z_fixed=np.asarray(z_fixed, dtype=bool), big_m=np.asarray([m for _, _, m in self.constraints]),
             constraint_names=[n for n, _, _ in self.constraints], cmap=cmap, newton_rtol=self.newton_rtol,
             newton_max_it=self.newton_max_it)
@@ -257,6 +284,8 @@ class LoweredModel:
     ncp: int
     n_units: int
     tapes: T.LoweredTapes
+    tapes_sens: T.LoweredTapes
+    z_init: list
     dyn_states: list
     quad_states: list
     z_lo: np.ndarray
@@ -283,18 +312,23 @@ class LoweredModel:
 
 
 def parse_blob(blob: bytes):
-    """Decode a blob back into {tag: ndarray} (used by tests and the oracle's tape VM)."""
+    """Decode a blob back into {tag: ndarray}; the sensitivity program's sections sit under key "sens"."""
     magic, ver, nsec, _ = struct.unpack_from("<IIII", blob, 0)
     if magic != BLOB_MAGIC or ver != BLOB_VERSION:
         raise ValueError("not a pyds_b200 model blob")
     off = 16
     out = {}
+    cur = out
     inv = {v: k for k, v in _DT.items()}
     for _ in range(nsec):
         tag, dt, cnt, _ = struct.unpack_from("<4sIII", blob, off)
         off += 16
         dtype = _NP[inv[dt]]
         nbytes = cnt * np.dtype(dtype).itemsize
-        out[tag.decode()] = np.frombuffer(blob, dtype=dtype, count=cnt, offset=off).copy()
+        arr = np.frombuffer(blob, dtype=dtype, count=cnt, offset=off).copy()
         off += nbytes + ((-nbytes) % 8)
+        if tag == b"PSEP":
+            cur = out.setdefault("sens", {})
+            continue
+        cur[tag.decode()] = arr
     return out

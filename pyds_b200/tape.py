@@ -415,7 +415,7 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
     """
     if ncp != 3:
         raise NotImplementedError("the kernel evaluates the point tape 3-wide (ncp = 3)")
-    dense_names = ("f", "J", "fq")
+    dense_names = ("f", "J", "fq", "fz", "fqx", "fqz", "gx", "gq")      # read through per-thread slots
     all_roots = [e for lst in roots.values() for e in lst if e is not None]
     order = topo_order(all_roots)
 
