@@ -104,6 +104,8 @@ int pydsb_eval_host(void* handle, const double* d, long long n_d, const double* 
  *   per_scenario = 0: one control vector per design point, shared by all theta (the reference's
  *                     two-stage formulation); G = n_d groups
  *   per_scenario = 1: one control vector per (d, theta) scenario; G = n_d*n_t groups, w ignored
+ *   per_scenario = 2: ONE control vector for the whole (d, theta) grid, G = 1 -- the reference's
+ *                     three-stage formulation (stage-0 F_in above the design stage, pyds/run.py:76-91)
  *   z0      NULL (zeros) or (z0_rows, nz) start profile, z0_rows in {1, G}
  *   opts    NULL or 6 doubles {mu0, mu_min, lam0, step_tol, max_iter, check_every} (<= 0: default)
  *   z_out   (G, nz) optimised controls          phi_out  NULL or (G) objective value at z_out

@@ -154,6 +154,26 @@ def shared_control_problem(vm, d, p, w, z0=None, **kw):
     return out
 
 
+def global_control_problem(vm, d, p, w, z0=None, **kw):
+    """The reference's three-stage formulation (pyds/run.py:76-91): ONE control vector for the whole
+    (d, theta) tree; objective = average over design points of the weighted hinge sum."""
+    d = np.atleast_2d(d); p = np.atleast_2d(p)
+    n_d, n_p = len(d), len(p)
+    bigm = vm.big_m
+    lo, hi = vm.sec["ZLOW"][:vm.nz], vm.sec["ZHIG"][:vm.nz]
+    z0 = np.zeros((1, vm.nz)) if z0 is None else np.asarray(z0, float).reshape(1, vm.nz).copy()
+    ww = np.tile(np.asarray(w, float), n_d) / n_d
+
+    def eval_c(z, active):
+        r = vm.evaluate(d, p, z=z[0], tol=1e-13, want_sens=True)
+        return (r["g"] / bigm).reshape(1, n_d * n_p, vm.ng), (r["dg"] / bigm[:, None]).reshape(1, n_d * n_p, vm.ng, vm.nz)
+
+    out = minimize_hinge(eval_c, z0, lo, hi, ww, **kw)
+    out["z"] = out["z"][0]
+    out["g"] = vm.evaluate(d, p, z=out["z"], tol=1e-13)["g"]
+    return out
+
+
 def per_scenario_problem(vm, d, p, z0=None, **kw):
     """Per-scenario recourse: every (d, theta) pair optimises its own control vector."""
     d = np.atleast_2d(d); p = np.atleast_2d(p)

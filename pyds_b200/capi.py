@@ -159,7 +159,7 @@ class Engine:
         _check(self._lib.pydsb_eval(self._h, ptr(d), n_d, ptr(theta), ptr(w), n_t, ptr(z), z_mode if z is not None else Z_MODEL,
                                     ptr(g_out), ptr(ind_out), ptr(P_out), ctypes.c_void_p(stream.cuda_stream)))
 
-    def recourse_solve(self, d, theta, w=None, z0=None, per_scenario=False, mu0=0.0, mu_min=0.0, lam0=0.0, step_tol=0.0,
+    def recourse_solve(self, d, theta, w=None, z0=None, per_scenario=False, global_group=False, mu0=0.0, mu_min=0.0, lam0=0.0, step_tol=0.0,
                        max_iter=0, check_every=0):
         """Optimise the controls (numpy in / numpy out).  Returns dict(z, phi, status, iters); ``z`` is
         (n_d, nz) in shared mode and (n_d, n_t, nz) in per-scenario mode."""
@@ -168,7 +168,8 @@ class Engine:
         d = _np64(d).reshape(-1, self.info["d_dim"])
         theta = _np64(theta).reshape(-1, self.info["p_dim"])
         n_d, n_t, nz = d.shape[0], theta.shape[0], self.info["nz"]
-        G = n_d * n_t if per_scenario else n_d
+        mode = 1 if per_scenario else (2 if global_group else 0)
+        G = n_d * n_t if per_scenario else (1 if global_group else n_d)
         td = torch.from_numpy(d).to(dev)
         tt = torch.from_numpy(theta).to(dev)
         tw = None if w is None else torch.from_numpy(_np64(w)).to(dev)
@@ -186,10 +187,10 @@ class Engine:
         ptr = lambda t: None if t is None else t.data_ptr()
         stream = torch.cuda.current_stream(self.device)
         torch.cuda.synchronize(self.device)
-        _check(self._lib.pydsb_recourse_solve(self._h, 1 if per_scenario else 0, ptr(td), n_d, ptr(tt), ptr(tw), n_t, ptr(tz0),
+        _check(self._lib.pydsb_recourse_solve(self._h, mode, ptr(td), n_d, ptr(tt), ptr(tw), n_t, ptr(tz0),
                                               rows, opts.ctypes.data, ptr(z), ptr(phi), ptr(st), ptr(it),
                                               ctypes.c_void_p(stream.cuda_stream)))
-        shape = (n_d, n_t, nz) if per_scenario else (n_d, nz)
+        shape = (n_d, n_t, nz) if per_scenario else ((nz,) if global_group else (n_d, nz))
         out = dict(z=z[:G].cpu().numpy().reshape(shape), phi=phi[:G].cpu().numpy(), status=st[:G].cpu().numpy(),
                    iters=it[:G].cpu().numpy())
         if per_scenario:

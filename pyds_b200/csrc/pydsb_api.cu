@@ -560,7 +560,8 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     if (n_d == 0) return PYDSB_OK;
     if (!d && img.d_dim > 0) return fail(PYDSB_ERR_INVALID, "null d");
     if (!theta || !z_out) return fail(PYDSB_ERR_INVALID, "null theta/z_out");
-    const long long G = per_scenario ? n_d * n_t : n_d;
+    if (per_scenario < 0 || per_scenario > 2) return fail(PYDSB_ERR_INVALID, "mode must be 0, 1 or 2");
+    const long long G = per_scenario == 1 ? n_d * n_t : (per_scenario == 2 ? 1 : n_d);
     if (z0 && !(z0_rows == 1 || z0_rows == G)) return fail(PYDSB_ERR_INVALID, "z0 must have 1 or G rows");
     // options: mu0, mu_min, lam0, step_tol, max_iter, check_every
     double o[6] = {1e-4, 1e-9, 1e-3, 1e-8, 200, 4};
@@ -573,7 +574,9 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
 
     const int n_tiles = (int)((n_t + BLOCK - 1) / BLOCK);
     const int NV = recourse_nv(nz);
-    const int acc_per_group = per_scenario ? 1 : n_tiles;
+    const long long acc_per_group_ll = per_scenario == 1 ? 1 : (per_scenario == 2 ? n_d * (long long)n_tiles : n_tiles);
+    if (acc_per_group_ll > 0x7fffffffLL) return fail(PYDSB_ERR_INVALID, "grid too large");
+    const int acc_per_group = (int)acc_per_group_ll;
     // workspace: doubles then ints
     const size_t nd_dbl = (size_t)G * (2 * nz + 2 + nz + (size_t)nz * nz + 2) + (size_t)G * acc_per_group * NV;
     const size_t nd_int = (size_t)G * 3 + 1;
@@ -619,7 +622,7 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
                                         cudaMemcpyHostToDevice, st));
     RecourseArgs ra{};
     ra.d = d; ra.theta = theta; ra.w = w; ra.n_d = n_d; ra.n_t = n_t; ra.n_tiles = n_tiles;
-    ra.per_scenario = per_scenario ? 1 : 0;
+    ra.per_scenario = per_scenario;
     ra.z_try = z_try; ra.status = status; ra.mu = mu; ra.acc = acc; ra.counters = m->d_counters;
     ra.sens_slot = img.n_units;
     LmArgs la{};

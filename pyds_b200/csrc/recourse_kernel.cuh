@@ -35,7 +35,7 @@ struct RecourseArgs {
     const double* w;           // may be null -> 1/n_t (shared) ; per-scenario mode uses weight 1
     long long n_d, n_t;
     int n_tiles;
-    int per_scenario;          // 0: group = design point, 1: group = scenario
+    int per_scenario;          // 0: group = design point, 1: group = scenario, 2: one group for the whole grid
     // per-group optimiser state
     double* z_try;             // (G, nz)   evaluated by sens_kernel
     const int* status;         // (G)       0 = running
@@ -103,8 +103,9 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
     const bool valid = tid < rows;
     const int row = valid ? tid : rows - 1;
     const long long j = j0 + row;
-    const long long grp = ra.per_scenario ? (i_d * ra.n_t + j) : i_d;
-    if (!ra.per_scenario && ra.status[i_d] != 0) return;        // block-uniform: group already finished
+    const bool per_scen = ra.per_scenario == 1;
+    const long long grp = per_scen ? (i_d * ra.n_t + j) : (ra.per_scenario == 2 ? 0 : i_d);
+    if (!per_scen && ra.status[grp] != 0) return;               // block-uniform: group already finished
     const bool active = valid && ra.status[grp] == 0;
     if (!__syncthreads_or(active)) return;
 
@@ -263,7 +264,10 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
     // smoothed hinge: phi = m + mu log(e^{-m/mu} + sum_k e^{(c_k-m)/mu}),  p_k = softmax weights
     const double mu = ra.mu[grp];
     double wv = 0.0;
-    if (active) wv = ra.per_scenario ? 1.0 : (ra.w ? __ldg(ra.w + j) : 1.0 / (double)ra.n_t);
+    if (active) {
+        wv = per_scen ? 1.0 : (ra.w ? __ldg(ra.w + j) : 1.0 / (double)ra.n_t);
+        if (ra.per_scenario == 2) wv /= (double)ra.n_d;          // the whole grid is one sample average
+    }
     double pk[8];
     double phi, raw;
     if (failed) {                            // a failed state solve counts as indicator 1 with no slope
@@ -285,9 +289,9 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
         Vv[(size_t)c * BLOCK] = v;
     }
     const double wmu = wv / mu;
-    double* out = ra.per_scenario ? (ra.acc + grp * NV) : nullptr;
-    auto emit = [&](int idx, double val) {
-        if (ra.per_scenario) {
+    double* out = per_scen ? (ra.acc + grp * NV) : nullptr;
+        auto emit = [&](int idx, double val) {
+        if (per_scen) {
             if (active) out[idx] = val;
         } else {
             const double sm = warp_sum(val);
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
             hv = fma(-Vv[(size_t)a * BLOCK], Vv[(size_t)b * BLOCK], hv);
             emit(idx, wmu * hv);
         }
-    if (!ra.per_scenario) {
+    if (!per_scen) {
         __syncthreads();
         for (int v = tid; v < NV; v += BLOCK) {
             double sm = 0.0;

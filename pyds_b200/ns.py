@@ -1,0 +1,126 @@
+"""A compact nested-sampling design-space driver with DEUS's activity-form interface.
+
+The reference hands ``Manager.g`` to DEUS (``DEUS(the_activity_form).solve()``, reference
+``run_twostage.py:212-214``); DEUS is a third-party package that is not installed here, so the
+example scripts fall back to this driver when ``import deus`` fails.  It reads the same nested dict
+(reference run_twostage.py:122-210): design box, theta samples + weights, target reliability,
+``points_schedule`` = (reliability level, n_live, n_replacements) rows, ``inside_fraction`` stop,
+``prng_seed``; proposals come from the enlarged bounding ellipsoid of the live points
+("suob-ellipsoid").  PARITY with DEUS's own sampler is UNPINNED -- DEUS's algorithmic details are
+restated from memory; what is exact is the contract: the constraint function is called as
+``g(d, p) -> list of (n_p, n_g)`` and the probability of feasibility is
+``sum_j w_j 1[all_k g_jk >= 0]``.  If the function's owner offers ``efp(d, p, w)`` (pyds_b200's
+managers do), that fused GPU path is used instead and g is never materialised.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+
+def efp_from_g(g_list, w):
+    """DEUS's reduction on the g-function output (note: -0.0 >= 0 counts as feasible)."""
+    return np.array([float(np.sum(w * np.all(np.asarray(gm) >= 0.0, axis=1))) for gm in g_list])
+
+
+class DEUS:
+    def __init__(self, form):
+        if form.get("activity_type") != "ds":
+            raise NotImplementedError("only the design-space ('ds') activity is implemented")
+        self.form = form
+        prob = form["problem"]
+        self.names = [list(v.keys())[0] for v in prob["design_variables"]]
+        self.lo = np.array([list(v.values())[0][0] for v in prob["design_variables"]], dtype=np.float64)
+        self.hi = np.array([list(v.values())[0][1] for v in prob["design_variables"]], dtype=np.float64)
+        self.p = np.array([s["c"] for s in prob["parameters_samples"]], dtype=np.float64)
+        self.w = np.array([s["w"] for s in prob["parameters_samples"]], dtype=np.float64)
+        self.p_best = np.array([prob["parameters_best_estimate"]], dtype=np.float64)
+        self.target = float(prob["target_reliability"])
+        sol = form["solver"]
+        if sol.get("name") != "ds-ns":
+            raise NotImplementedError("only the 'ds-ns' solver is implemented")
+        st = sol["settings"]
+        self.g_func = st["efp_evaluation"]["constraints_func_ptr"]
+        self.schedule = sorted(st["points_schedule"])
+        self.inside_fraction = 1.0
+        for c in st.get("stop_criteria", []):
+            self.inside_fraction = float(c.get("inside_fraction", self.inside_fraction))
+        alg = sol["algorithms"]["sampling"]["settings"]
+        self.seed = int(alg.get("prng_seed", 0))
+        self.f0 = float(alg.get("f0", 0.1))
+        self.alpha = float(alg.get("alpha", 0.3))
+        self.max_iterations = 100000
+        for c in alg.get("stop_criteria", []):
+            self.max_iterations = int(c.get("max_iterations", self.max_iterations))
+        self.use_fast_path = bool(st["efp_evaluation"].get("use_fused_efp", True))
+        self.result = None
+
+    # ----------------------------------------------------------------------------------------------
+    def efp(self, d):
+        owner = getattr(self.g_func, "__self__", None)
+        if self.use_fast_path and owner is not None and hasattr(owner, "efp"):
+            return np.asarray(owner.efp(d, self.p, self.w), dtype=np.float64)
+        return efp_from_g(self.g_func(d, self.p), self.w)
+
+    def _propose(self, rng, live, n, enlarge):
+        """Uniform samples from the enlarged bounding ellipsoid of ``live``, clipped to the box."""
+        dim = live.shape[1]
+        span = self.hi - self.lo
+        u = (live - self.lo) / span
+        mu = u.mean(axis=0)
+        cov = np.cov(u.T) + 1e-12 * np.eye(dim) if len(u) > dim else np.eye(dim) * 0.25
+        L = np.linalg.cholesky(np.atleast_2d(cov))
+        y = np.linalg.solve(L, (u - mu).T).T
+        r = np.sqrt((y * y).sum(axis=1)).max() * (1.0 + enlarge)          # smallest scaled ellipsoid holding all points
+        out = []
+        while len(out) < n:
+            z = rng.normal(size=(4 * n, dim))
+            z /= np.linalg.norm(z, axis=1)[:, None]
+            z *= rng.uniform(size=(4 * n, 1)) ** (1.0 / dim) * r
+            cand = mu + z @ L.T
+            ok = np.all((cand >= 0.0) & (cand <= 1.0), axis=1)
+            out.extend(cand[ok])
+        return self.lo + np.array(out[:n]) * span
+
+    def solve(self):
+        rng = np.random.default_rng(self.seed)
+        dim = len(self.lo)
+        level, n_live, n_rep = self.schedule[0]
+        live = self.lo + rng.uniform(size=(n_live, dim)) * (self.hi - self.lo)
+        t_start = time.time()
+        live_p = self.efp(live)
+        n_evals = len(live)
+        history, iter_times = [(live.copy(), live_p.copy())], []
+        it = 0
+        while it < self.max_iterations:
+            inside = float(np.mean(live_p >= self.target))
+            if inside >= self.inside_fraction:
+                break
+            t0 = time.time()
+            worst = live_p.min()
+            for lv, nl, nr in self.schedule:                 # the last schedule row whose level has been reached
+                if worst >= lv:
+                    level, n_live, n_rep = lv, nl, nr
+            enlarge = self.f0 * max(1.0 - inside, 0.05) ** self.alpha
+            cand = self._propose(rng, live, n_rep, enlarge)
+            cand_p = self.efp(cand)
+            n_evals += len(cand)
+            history.append((cand.copy(), cand_p.copy()))
+            for c, cp in zip(cand, cand_p):
+                if len(live) < n_live:
+                    if cp >= live_p.min():
+                        live = np.vstack([live, c]); live_p = np.append(live_p, cp)
+                    continue
+                k = int(np.argmin(live_p))
+                if cp > live_p[k] or (cp == live_p[k] and cp >= self.target):
+                    live[k], live_p[k] = c, cp
+            iter_times.append(time.time() - t0)
+            it += 1
+        self.result = {
+            "live_points": live, "live_efp": live_p, "iterations": it, "evaluations": n_evals,
+            "inside_fraction": float(np.mean(live_p >= self.target)), "seconds": time.time() - t_start,
+            "seconds_per_iteration": float(np.mean(iter_times)) if iter_times else 0.0,
+            "samples": np.vstack([h[0] for h in history]), "samples_efp": np.concatenate([h[1] for h in history]),
+        }
+        return self.result

@@ -1,0 +1,96 @@
+"""``Solver``: the control (recourse) optimisation + indicator logic, batched on the GPU.
+
+Same constructor and entry points as the reference's ``pyds/solver.py`` (``Solver(parent, config)``,
+``solve()``, ``_get_indicator_var_values()``, the ``no_infeasible`` counter and the
+``warn infeasible`` message), with the GAMS/CONOPT process launch per design point
+(reference pyds/solver.py:50-55) replaced by ``pydsb_recourse_solve`` over ALL design points at
+once, followed by one pass of the feasibility kernel at the optimised controls.
+
+Classification rule (reference pyds/solver.py:71-80): the relaxed indicator is snapped ``value == 0
+-> 0 else 1``.  CONOPT returns an indicator sitting on its bound as exactly 0 while satisfying the
+big-M rows to its feasibility tolerance; the equivalent here is ``max_k g_k/M_k <= feasibility
+tolerance`` at the optimised controls (default 1e-7 in big-M-scaled units; 0 when the controls are
+not optimised).  A scenario whose state solve fails is reported infeasible (indicator 1), as the
+reference does for an infeasible NLP (pyds/solver.py:39-44, 63-69).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Solver:
+    def __init__(self, parent, config):
+        self.parent = parent
+        self.tee = config["tee"]
+        config.setdefault("use relaxation", True)
+        self.use_relaxation = config["use relaxation"]
+        self.io_options = config["io options"]
+        self.io_options.setdefault("warmstart", True)
+        self.solve_trajectories = config["solve trajectories"]
+        self.warn_infeasible = config["warn infeasible"]
+        self.save_output = config["save output"]
+        self.save_solution_states = config["save solution state"]
+        self.no_infeasible = 0
+        self.name = config["name"]                       # 'gams' in the reference scripts: informational
+        opt = self.io_options
+        self.optimise_controls = bool(opt.get("optimise controls", True))
+        self.feas_tol = float(opt.get("feasibility tolerance", 1e-7))
+        self.lm_options = {k: opt[k] for k in ("mu0", "mu_min", "lam0", "step_tol", "max_iter", "check_every") if k in opt}
+        self.result = None
+        self.output = {"relaxation": None, "trajectories": None}
+        self._indicator = None
+        self.controls = None
+
+    # ------------------------------------------------------------------------------------------------
+    def solve(self, d=None, p=None, w=None, mode="shared"):
+        """Optimise the controls for the current batch and classify every scenario.
+
+        ``mode``: ``"shared"`` one control vector per design point (two-stage, reference run.py:55-67),
+        ``"global"`` one for the whole grid (three-stage, reference run.py:76-91), ``"per_scenario"``.
+        Returns the indicator matrix (n_d, n_p) in {0, 1}."""
+        sim = self.parent.simulator
+        eng = sim.engine
+        if d is None:
+            d, p = self.parent._current_inputs
+        d = np.atleast_2d(np.asarray(d, dtype=np.float64))
+        p = np.atleast_2d(np.asarray(p, dtype=np.float64))
+        self.output = {"relaxation": None, "trajectories": None}
+        n_free = int((~sim.lowered.z_fixed).sum()) if sim.lowered.nz else 0
+        z, z_mode, tol = None, None, 0.0
+        self.result = {"status": None, "iters": None, "phi": None}
+        if self.use_relaxation and self.optimise_controls and n_free > 0:
+            z0 = sim.default_controls()[None, :]
+            res = eng.recourse_solve(d, p, w, z0=z0, per_scenario=(mode == "per_scenario"), global_group=(mode == "global"),
+                                     **self.lm_options)
+            z = res["z"]
+            self.result = {"status": res["status"], "iters": res["iters"], "phi": res["phi"]}
+            tol = self.feas_tol
+        elif n_free > 0:
+            z = sim.default_controls()
+        self.controls = z
+        g, ind, _ = eng.eval_host(d, p, None, z=z, want_g=True, want_ind=False, want_P=False)
+        c = g / sim.lowered.big_m[None, None, :]
+        with np.errstate(invalid="ignore"):
+            y = np.maximum(0.0, c.max(axis=-1))
+            indicator = np.where(y <= tol, 0.0, 1.0)
+        failed = ~np.isfinite(c).all(axis=-1)
+        indicator[failed] = 1.0
+        if failed.any():
+            self.no_infeasible += int(failed.sum())
+            if self.warn_infeasible:
+                print("Warning: Infeasible relaxation. Total number of infeasible solves: {}".format(self.no_infeasible))
+        self._indicator = indicator
+        self._g = g
+        if self.save_output:
+            self.output["relaxation"] = self._collect_output()
+        return indicator
+
+    def _get_indicator_var_values(self):
+        """Indicators of the final-stage scenarios in leaf (product) order (reference solver.py:91-98)."""
+        return self._indicator.reshape(-1).copy()
+
+    def _collect_output(self):
+        return {"data": [{"g": self._g[i].copy(), "controls": None if self.controls is None else np.asarray(self.controls).copy()}
+                         for i in range(self._g.shape[0])],
+                "objective": None if self.result["phi"] is None else np.asarray(self.result["phi"]).copy(),
+                "user time": None, "infeasible": bool((self._indicator == 1).all())}

@@ -68,6 +68,12 @@ class Expr:
     def __pow__(self, o): return self.g.pow(self, o)
     def __rpow__(self, o): return self.g.pow(o, self)
 
+    # relations (used by the modelling layer: ``lhs == rhs``, ``body <= ub``) ---------------------------
+    def __eq__(self, o): return Relational(self, o, "==")
+    def __le__(self, o): return Relational(self, o, "<=")
+    def __ge__(self, o): return Relational(self, o, ">=")
+    def __hash__(self): return id(self)
+
     def is_const(self, v=None):
         return self.op == "const" and (v is None or self.value == v)
 
@@ -79,10 +85,24 @@ class Expr:
         return f"{self.op}({', '.join(map(repr, self.args))})"
 
 
+class Relational:
+    """``lhs (==|<=|>=) rhs`` recorded symbolically (never evaluated to a bool)."""
+    __slots__ = ("lhs", "rhs", "op")
+
+    def __init__(self, lhs, rhs, op):
+        self.lhs, self.rhs, self.op = lhs, rhs, op
+
+    def __bool__(self):
+        raise TypeError("a symbolic relation has no truth value")
+
+
 class Graph:
     """Hash-consing expression factory with algebraic simplification."""
 
-    LEAF_LEVEL = {"param": LEVEL_PARAM, "ctrl": LEVEL_CTRL, "x": LEVEL_STATE, "xe": LEVEL_END, "qe": LEVEL_END}
+    # "v" (variable reference), "dv" (time derivative) and "alg" (algebraic variable) are placeholders
+    # of the modelling layer; they are substituted before lowering.
+    LEAF_LEVEL = {"param": LEVEL_PARAM, "ctrl": LEVEL_CTRL, "x": LEVEL_STATE, "xe": LEVEL_END, "qe": LEVEL_END,
+                  "v": LEVEL_STATE, "dv": LEVEL_STATE, "alg": LEVEL_END, "pn": LEVEL_PARAM}
 
     def __init__(self):
         self._tab = {}
@@ -107,6 +127,8 @@ class Graph:
     def qe(self, i): return self._mk("qe", (), int(i))
 
     def wrap(self, v):
+        if hasattr(v, "_as_expr"):
+            v = v._as_expr()
         if isinstance(v, Expr):
             if v.g is not self:
                 raise ValueError("expression belongs to another graph")

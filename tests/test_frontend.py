@@ -1,0 +1,169 @@
+"""Host-side front end on the CPU: the Pyomo-shaped modelling layer, its lowering, the reference's
+helper semantics (utils / output manager) and the nested-sampling driver.  No GPU calls."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+import pyds_b200.environ as pyo
+from oracle import kinetics as K, tape_vm
+from pyds_b200 import dae, models, ns, utils
+from pyds_b200.output_manager import OutputManager
+from pyds_b200.simulator import LoweringError, lower_stage_model
+from pyds_b200.user_utils import read_last_file, read_output_file
+
+
+def _lower_example(mod, tmp_path):
+    cfg = mod.build_config(str(tmp_path))
+    m = utils.create_flattened_model(cfg["problem"]["stage rules"])
+    cfg["problem"]["model transformation"](m)
+    return lower_stage_model(m, cfg["problem"]["input map"], m.component("F_in_default")).lower(), cfg
+
+
+def test_twostage_script_lowers_to_the_reference_equations(tmp_path):
+    from examples import twostage_reactor as ex
+    lm, cfg = _lower_example(ex, tmp_path)
+    assert (lm.ns, lm.nq, lm.ng, lm.nz, lm.d_dim, lm.p_dim, lm.nfe) == (2, 2, 2, 8, 2, 4, 8)
+    np.testing.assert_array_equal(lm.big_m, [1e2, 1e7])
+    np.testing.assert_array_equal(lm.z_lo, 0.0)
+    np.testing.assert_array_equal(lm.z_hi, 2.5)
+    assert [e.value for e in lm.z_init] == [0.0] * 8                       # F_in_default = {0: 0}
+    vm = tape_vm.TapeVM(lm.blob)
+    rng = np.random.default_rng(8)
+    d = np.stack([rng.uniform(250, 350, 9), rng.uniform(250, 300, 9)], axis=1)
+    p = K.theta_samples()
+    F = rng.uniform(0, 2.5, 8)
+    r = vm.evaluate(d, p, z=F, tol=1e-13)
+    g1, g2, _ = K.g_grid(d, p, F=F)
+    np.testing.assert_allclose(r["g"][..., 0], g1, atol=1e-13)
+    np.testing.assert_allclose(r["g"][..., 1], g2, atol=1e-8)
+
+
+def test_threestage_repaired_script_lowers_and_keeps_warm_start(tmp_path):
+    from examples import threestage_reactor as ex
+    lm, cfg = _lower_example(ex, tmp_path)
+    assert cfg["problem"]["input map"] == {1: ["t_f", "T"], 2: ["E1", "E2", "k1", "k2"]}
+    # warm start {0: 2.5, 0.2: 0} sampled at the element mid-points of 8 elements
+    assert [e.value for e in lm.z_init] == [2.5, 2.5, 0, 0, 0, 0, 0, 0]
+    vm = tape_vm.TapeVM(lm.blob)
+    d = np.array([[320.0, 280.0]])
+    p = K.theta_samples(5)
+    F = np.array([e.value for e in lm.z_init])
+    r = vm.evaluate(d, p, z=F, tol=1e-13)
+    g1, g2, _ = K.g_grid(d, p, F=F)
+    np.testing.assert_allclose(r["g"][..., 0], g1, atol=1e-13)
+
+
+def test_modelling_layer_rejects_what_the_kernel_cannot_express():
+    m = pyo.ConcreteModel()
+    m.t = dae.ContinuousSet(bounds=(0, 1))
+    m.k = pyo.Param(initialize=0, mutable=True)
+    m.x = pyo.Var(m.t)
+    m.dx = dae.DerivativeVar(m.x, wrt=m.t)
+    m.q = pyo.Var(m.t, bounds=(0, 1))
+    m.ode = pyo.Constraint(m.t, rule=lambda _m, t: _m.dx[t] == -_m.k * _m.x[t] + _m.q[t])
+    m.y = pyo.Var()
+    m.cy = pyo.Constraint(rule=lambda _m: _m.y == _m.x[1] - 0.5)
+    utils.add_BigMConstraint(m, "c1", 10.0, expr=m.y <= 0)
+    imap = {0: [], 1: ["k"]}
+    with pytest.raises(LoweringError, match="dae.collocation"):
+        lower_stage_model(m, imap)
+    tf = pyo.TransformationFactory("dae.collocation")
+    tf.apply_to(m, nfe=4, ncp=3)
+    with pytest.raises(LoweringError, match="initial value"):
+        lower_stage_model(m, imap)
+    m.x[0].fix(1.0)
+    with pytest.raises(LoweringError, match="piecewise constant"):
+        lower_stage_model(m, imap)
+    tf.reduce_collocation_points(m, var=m.q, ncp=1, contset=m.t)
+    lm = lower_stage_model(m, imap).lower()
+    assert (lm.ns, lm.nz, lm.ng, lm.nfe) == (1, 4, 1, 4)
+    # x' = -k x + q with q = 0: x(1) = exp(-k); collocation error of Radau-3 on 4 elements is tiny
+    r = tape_vm.TapeVM(lm.blob).evaluate(np.zeros((1, 0)), np.array([[0.7]]), tol=1e-13)
+    assert abs(r["g"][0, 0, 0] - (np.exp(-0.7) - 0.5)) < 1e-7
+
+
+def test_bigm_forms():
+    m = pyo.ConcreteModel()
+    m.a = pyo.Var()
+    utils.add_BigMConstraint(m, "up", 5.0, expr=m.a <= 2)
+    utils.add_BigMConstraint(m, "lo", 7.0, expr=m.a >= -1)
+    utils.add_BigMConstraint(m, "eq", 9.0, expr=m.a == 3)
+    names = [n for n, _, _ in m._bigm]
+    assert names == ["up", "lo", "eq[1]", "eq[2]"]
+    assert [M for _, _, M in m._bigm] == [5.0, 7.0, 9.0, 9.0]
+    assert hasattr(m, "_indicator_var") and m._indicator_var.bounds == (0, 1)      # one shared indicator
+
+
+def test_utils_tree_helpers_and_load_input():
+    m = utils.create_EF([lambda mm, st: None, lambda mm, st: None], [1, 3])
+    assert m.BFs == [1, 3] and m.n_stages == 2
+    assert list(utils.get_all_idx([1, 2, 2])) == [(0, 0, 0), (0, 0, 1), (0, 1, 0), (0, 1, 1)]
+    assert utils.get_final_scenarios(m) == [(0, 0), (0, 1), (0, 2)]
+    out = utils.load_input(m, {0: ["a"], 1: ["b", "c"]}, {0: np.array([[1.0]]), 1: np.arange(6.0).reshape(3, 2)})
+    assert out[1].shape == (3, 2)
+    with pytest.raises(ValueError, match="Undefined input binding"):
+        utils.load_input(m, {0: ["a"]}, {1: np.zeros((3, 1))})
+    with pytest.raises(ValueError):
+        utils.create_EF([lambda mm, st: None], [1])
+
+
+def test_output_manager_stream(tmp_path):
+    path = tmp_path / "pyds_output.pkl"
+    path.write_bytes(b"stale")
+    om = OutputManager(str(tmp_path))
+    assert not path.exists()                                   # previous log is removed (reference output_manager.py:9-11)
+    for i in range(3):
+        om.clear_buffer()
+        om.add_input({0: np.array([[float(i)]])})
+        om.add_solver_solution({"relaxation": {"objective": i}})
+        om.add_simulator_solution([{"user time": 0.0}])
+        om.write_data_to_disk()
+    recs = read_output_file(str(path))
+    assert len(recs) == 3 and recs[2]["solver"]["relaxation"]["objective"] == 2
+    assert read_last_file(str(path))["input"][0][0, 0] == 2.0
+    assert set(recs[0].keys()) == {"input", "solver", "simulator"}
+
+
+def test_manager_config_contract(tmp_path):
+    """Missing config keys raise KeyError as in the reference (no defaults except 'use relaxation' and
+    'io options'.warmstart); construction must not need a GPU (the engine is created on first use)."""
+    from examples import twostage_reactor as ex
+    from pyds_b200.run import TwoStageManager
+    cfg = ex.build_config(str(tmp_path))
+    m = TwoStageManager(cfg)
+    assert m.n_stages == 2 and m.model is None and m.solver.use_relaxation is True
+    assert cfg["solver"]["io options"]["warmstart"] is True
+    assert m.simulator.lowered.nz == 8 and m.simulator.input_names == ["t_f", "T", "E1", "E2", "k1", "k2"]
+    bad = ex.build_config(str(tmp_path))
+    del bad["problem"]["output map"]
+    with pytest.raises(KeyError):
+        TwoStageManager(bad)
+    with pytest.raises(ValueError):
+        m._check(np.zeros((3, 3)), np.zeros((5, 4)))
+
+
+def test_ns_driver_with_a_cpu_constraint_function():
+    """The driver against a cheap analytic g (disc of radius 0.3 feasible with probability 1)."""
+    calls = []
+
+    def g(d, p):
+        calls.append(len(d))
+        out = []
+        for row in d:
+            r = np.hypot(row[0] - 0.5, row[1] - 0.5)
+            out.append(np.where(p[:, 0] * 0 + r <= 0.3, 0.0, -1.0)[:, None] * np.ones((len(p), 1)))
+        return out
+
+    form = {"activity_type": "ds", "problem": {"parameters_best_estimate": [0.0], "parameters_samples": [{"c": [0.0], "w": 0.5}, {"c": [1.0], "w": 0.5}],
+                                              "target_reliability": 0.9, "design_variables": [{"a": [0, 1]}, {"b": [0, 1]}]},
+            "solver": {"name": "ds-ns", "settings": {"efp_evaluation": {"constraints_func_ptr": g}, "points_schedule": [(0.0, 40, 8), (0.5, 60, 12)],
+                                                     "stop_criteria": [{"inside_fraction": 1.0}]},
+                       "algorithms": {"sampling": {"settings": {"prng_seed": 1989, "f0": 0.1, "alpha": 0.3, "stop_criteria": [{"max_iterations": 500}]}}}}}
+    res = ns.DEUS(form).solve()
+    assert res["inside_fraction"] == 1.0 and len(res["live_points"]) >= 40
+    assert np.all(np.hypot(res["live_points"][:, 0] - 0.5, res["live_points"][:, 1] - 0.5) <= 0.3)
+    assert res["evaluations"] == sum(calls)
+    # efp reduction: -0.0 >= 0 counts as feasible
+    assert ns.efp_from_g([np.array([[-0.0], [-1.0]])], np.array([0.25, 0.75]))[0] == 0.25

@@ -1,0 +1,115 @@
+"""The drop-in boundary on the GPU: ``TwoStageManager.g`` / ``ThreeStageManager.g`` built from the
+example user scripts, checked against the CPU restatement (state solve + control optimisation +
+classification rule).  Parity against the reference's CONOPT optimum itself is UNPINNED."""
+import numpy as np
+import pytest
+
+from oracle import kinetics as K, recourse as RC, tape_vm
+from pyds_b200 import ns
+from pyds_b200.run import ThreeStageManager, TwoStageManager
+from pyds_b200.user_utils import read_output_file
+
+pytestmark = pytest.mark.gpu
+
+FEAS_TOL = 1e-7
+
+
+def _oracle_indicator(vm, d, p, w, mode):
+    if isinstance(mode, str):
+        ref = RC.shared_control_problem(vm, d, p, w)
+    else:                                            # global group; ``mode`` carries the warm-start profile
+        ref = RC.global_control_problem(vm, d, p, w, z0=mode)
+    c = (ref["g"] / vm.big_m).max(-1)
+    return np.where(np.maximum(c, 0.0) <= FEAS_TOL, 0.0, 1.0), c, ref
+
+
+def test_twostage_manager_g_contract_and_classification(tmp_path):
+    from examples import twostage_reactor as ex
+    m = TwoStageManager(ex.build_config(str(tmp_path)))
+    rng = np.random.default_rng(1989)
+    d = np.stack([rng.uniform(250, 350, 12), rng.uniform(250, 300, 12)], axis=1)
+    p = K.theta_samples()
+    g_list = m.g(d, p)
+    # the reference's contract (pyds/run.py:56-69): list of n_d arrays (n_p, 1) of -indicator
+    assert isinstance(g_list, list) and len(g_list) == 12
+    assert all(g.shape == (50, 1) and g.dtype == np.float64 for g in g_list)
+    assert all(set(np.unique(g)) <= {0.0, -1.0} for g in g_list)
+    vm = tape_vm.TapeVM(m.simulator.lowered.blob, program=1)
+    w = np.full(50, 1 / 50)
+    ind_ref, c_ref, ref = _oracle_indicator(vm, d, p, w, "shared")
+    ind = -np.stack([g[:, 0] for g in g_list])
+    near = np.abs(c_ref - FEAS_TOL) < 1e-6                          # scenarios sitting on the kink are exempt
+    assert np.all((ind == ind_ref) | near)
+    assert near.mean() < 0.2
+    # DEUS's reduction on the returned list equals the fused fast path
+    P_from_g = ns.efp_from_g(g_list, w)
+    np.testing.assert_allclose(m.efp(d, p, w), P_from_g, atol=1e-15)
+    # optimising the controls never lowers the probability of feasibility relative to the warm start
+    g0 = m.simulator.simulate_all_scenarios(m.model, {0: d, 1: p})
+    P0 = ((g0 <= 0).all(-1) * w).sum(1)
+    assert np.all(P_from_g >= P0 - 1e-15) and P_from_g.sum() > P0.sum()
+    # best-estimate call with n_p = 1 (DEUS score evaluation) rebuilds nothing and still works
+    g1 = m.g(d, np.array([K.P_BEST]))
+    assert len(g1) == 12 and g1[0].shape == (1, 1)
+    # one pickle record per design point (reference run.py:67)
+    recs = read_output_file(str(tmp_path / "pyds_output.pkl"))
+    assert len(recs) == 24 and set(recs[0].keys()) == {"input", "solver", "simulator"}
+
+
+def test_twostage_manager_without_control_optimisation_matches_plain_oracle(tmp_path):
+    from examples import twostage_reactor as ex
+    m = TwoStageManager(ex.build_config(str(tmp_path), **{"optimise controls": False}))
+    rng = np.random.default_rng(3)
+    d = np.stack([rng.uniform(250, 350, 40), rng.uniform(250, 300, 40)], axis=1)
+    p = K.theta_samples()
+    g_list = m.g(d, p)
+    ref = K.manager_g(d, p, F=np.zeros(8))
+    for a, b in zip(g_list, ref):
+        np.testing.assert_array_equal(a, b)
+    # empty batch
+    assert m.g(np.zeros((0, 2)), p) == []
+
+
+def test_threestage_manager_global_control(tmp_path):
+    from examples import threestage_reactor as ex
+    m = ThreeStageManager(ex.build_config(str(tmp_path)))
+    rng = np.random.default_rng(7)
+    d = np.stack([rng.uniform(250, 400, 6), rng.uniform(250, 300, 6)], axis=1)
+    p = K.theta_samples(20)
+    g_list = m.g(d, p)
+    assert len(g_list) == 6 and all(g.shape == (20, 1) for g in g_list)
+    vm = tape_vm.TapeVM(m.simulator.lowered.blob, program=1)
+    w = np.full(20, 1 / 20)
+    z0 = m.simulator.default_controls()
+    assert list(z0) == [2.5, 2.5, 0, 0, 0, 0, 0, 0]
+    ind_ref, c_ref, ref = _oracle_indicator(vm, d, p, w, z0)
+    # one control vector for the whole tree
+    assert m.solver.controls.shape == (8,)
+    np.testing.assert_allclose(m.solver.result["phi"][0], ref["phi_raw"][0], rtol=1e-6, atol=1e-9)
+    ind = -np.stack([g[:, 0] for g in g_list])
+    near = np.abs(c_ref - FEAS_TOL) < 1e-6
+    assert np.all((ind == ind_ref) | near)
+    # per-design-point slicing of the leaf vector (reference run.py:93-96)
+    flat = m.solver._get_indicator_var_values()
+    for i in range(6):
+        np.testing.assert_array_equal(-g_list[i][:, 0], flat[20 * i:20 * (i + 1)])
+    recs = read_output_file(str(tmp_path / "pyds_output.pkl"))
+    assert len(recs) == 1                                            # one record per call (reference run.py:97)
+
+
+def test_nested_sampling_on_the_twostage_problem(tmp_path):
+    """A short design-space run through the DEUS-shaped activity form with the GPU manager."""
+    from examples import twostage_reactor as ex
+    from examples.reactor_model import theta_samples
+    m = TwoStageManager(ex.build_config(str(tmp_path)))
+    p_best, p_samples = theta_samples()
+    form = ex.activity_form(m, p_best, p_samples)
+    form["solver"]["settings"]["points_schedule"] = [(.0, 40, 10), (.3, 50, 12)]
+    form["solver"]["algorithms"]["sampling"]["settings"]["stop_criteria"] = [{"max_iterations": 60}]
+    res = ns.DEUS(form).solve()
+    assert res["iterations"] >= 1 and res["evaluations"] >= 40
+    assert res["live_efp"].min() >= 0.0 and res["live_efp"].max() <= 1.0 + 1e-12
+    # the live set moved into the high-probability region found by the survey probe (T in ~[265, 295])
+    assert res["live_efp"].mean() > res["samples_efp"][:40].mean()
+    best = res["live_points"][np.argmax(res["live_efp"])]
+    assert 255.0 <= best[1] <= 300.0
