@@ -30,6 +30,8 @@ def lib():
         L.oracle_kinetics_grid.restype = ctypes.c_longlong
         L.oracle_kinetics_grid.argtypes = [ctypes.c_longlong, ctypes.c_int, dp, ctypes.c_longlong, dp, dp, dp,
                                            ctypes.c_longlong, ctypes.c_double, ctypes.c_int, dp, dp]
+        L.oracle_set_threads.restype = ctypes.c_int
+        L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_set_tables.restype = None
         L.oracle_set_tables.argtypes = [dp, dp]
         a = np.ascontiguousarray(np.asarray(ADOT, dtype=np.float64).reshape(-1))
@@ -58,6 +60,6 @@ def kinetics_grid(d, p, w=None, F=None, tol=1e-13, max_it=60, want_g=True, want_
     g = np.empty((n_d, n_p, 2)) if want_g else None
     P = np.empty(n_d) if want_P else None
     if threads is not None:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+        L.oracle_set_threads(int(threads))
     it = L.oracle_kinetics_grid(n_d, d_dim, _ptr(d), n_p, _ptr(p), _ptr(w), _ptr(F), f_rows, tol, max_it, _ptr(g), _ptr(P))
     return g, P, int(it)

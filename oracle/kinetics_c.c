@@ -17,6 +17,9 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define NFE 8
 #define NCP 3
@@ -60,6 +63,18 @@ void oracle_set_tables(const double* adot16, const double* bw3)
     for (int k = 0; k < 4; ++k) for (int j = 0; j < 4; ++j) A[k][j] = adot16[4 * k + j];
     for (int j = 0; j < 3; ++j) BW[j] = bw3[j];
     tables_ready = 1;
+}
+
+/* Number of OpenMP threads for the grid evaluation (torchrun exports OMP_NUM_THREADS=1). */
+int oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }
 
 static int lu_solve9(double M[NN][NN], double r[NN])
