@@ -36,15 +36,17 @@ struct ExecImage {
     int ns, nq, ng, d_dim, p_dim, nz, nfe, nce, n_units;
     int ctrl_slot, xe_slot, qe_slot, x_slot;
     unsigned j_mask;           // bit r*ns+c: df_r/dx_c is not structurally zero
-    unsigned f_off[3], f_str[3];       // byte offset of point 0 / byte stride between points (0 = narrow)
-    unsigned j_off[9], j_str[9];
-    unsigned fq_off[8], fq_str[8];
+    // outputs of the point tape read by the compiled Newton code: byte offset of every collocation
+    // point (equal offsets = narrow value), so that each access is LDS [thread base + uniform offset]
+    unsigned f_o[3][3];
+    unsigned j_o[9][3];
+    unsigned fq_o[8][3];
     unsigned fq_mask;
-    // program 1 only: df/dz (ns x nce), dfq/dx (nq x ns), dfq/dz (nq x nce) -- same (offset, stride) form;
+    unsigned fqx_o[24][3], fqx_mask;                  // dfq/dx (nq x ns)
+    // program 1 only: df/dz (ns x nce), dfq/dz (nq x nce) -- same (offset, stride) form;
     // dg/dxe (ng x ns) and dg/dqe (ng x nq) are narrow references in `tabs` after cmap
-    unsigned fz_off[12], fz_str[12], fz_mask;
-    unsigned fqx_off[24], fqx_str[24], fqx_mask;
-    unsigned fqz_off[32], fqz_str[32], fqz_mask;
+    unsigned fz_o[12][3], fz_mask;
+    unsigned fqz_o[32][3], fqz_mask;
     double bigm_inv[8];        // 1 / M_k
     int fq_state_dep;
     int predictor;
@@ -204,22 +206,30 @@ __device__ __noinline__ double cold_op(unsigned op, double a, double b)
 
 #define PT_LD(off) (*reinterpret_cast<const double*>(base + (off)))
 #define PT_ST(off, v) (*reinterpret_cast<double*>(base + (off)) = (v))
+// a narrow operand (same slot for the three points) is loaded once
+#define PT_LOAD3(v, o0, o1, o2, narrow)                               \
+    const double v##0 = PT_LD(o0);                                    \
+    double v##1 = v##0, v##2 = v##0;                                  \
+    if (!(narrow)) { v##1 = PT_LD(o1); v##2 = PT_LD(o2); }
 #define PT_UN(expr)                                                   \
     {                                                                 \
+        PT_LOAD3(a, q1.x, q1.y, q1.z, q0.x & 16u)                     \
         double a;                                                     \
-        a = PT_LD(q1.x); const double r0 = (expr);                    \
-        a = PT_LD(q1.y); const double r1 = (expr);                    \
-        a = PT_LD(q1.z); const double r2 = (expr);                    \
+        a = a0; const double r0 = (expr);                             \
+        a = a1; const double r1 = (expr);                             \
+        a = a2; const double r2 = (expr);                             \
         PT_ST(q0.y, r0); PT_ST(q0.z, r1); PT_ST(q0.w, r2);            \
     }                                                                 \
     break;
 #define PT_BIN(expr)                                                  \
     {                                                                 \
         const uint4 q2 = c_pt[4 * pc + 2];                            \
+        PT_LOAD3(a, q1.x, q1.y, q1.z, q0.x & 16u)                     \
+        PT_LOAD3(b, q1.w, q2.x, q2.y, q0.x & 32u)                     \
         double a, b;                                                  \
-        a = PT_LD(q1.x); b = PT_LD(q1.w); const double r0 = (expr);   \
-        a = PT_LD(q1.y); b = PT_LD(q2.x); const double r1 = (expr);   \
-        a = PT_LD(q1.z); b = PT_LD(q2.y); const double r2 = (expr);   \
+        a = a0; b = b0; const double r0 = (expr);                     \
+        a = a1; b = b1; const double r1 = (expr);                     \
+        a = a2; b = b2; const double r2 = (expr);                     \
         PT_ST(q0.y, r0); PT_ST(q0.z, r1); PT_ST(q0.w, r2);            \
     }                                                                 \
     break;
@@ -227,10 +237,13 @@ __device__ __noinline__ double cold_op(unsigned op, double a, double b)
     {                                                                 \
         const uint4 q2 = c_pt[4 * pc + 2];                            \
         const uint4 q3 = c_pt[4 * pc + 3];                            \
+        PT_LOAD3(a, q1.x, q1.y, q1.z, q0.x & 16u)                     \
+        PT_LOAD3(b, q1.w, q2.x, q2.y, q0.x & 32u)                     \
+        PT_LOAD3(c, q2.z, q2.w, q3.x, q0.x & 64u)                     \
         double a, b, c;                                               \
-        a = PT_LD(q1.x); b = PT_LD(q1.w); c = PT_LD(q2.z); const double r0 = (expr);   \
-        a = PT_LD(q1.y); b = PT_LD(q2.x); c = PT_LD(q2.w); const double r1 = (expr);   \
-        a = PT_LD(q1.z); b = PT_LD(q2.y); c = PT_LD(q3.x); const double r2 = (expr);   \
+        a = a0; b = b0; c = c0; const double r0 = (expr);             \
+        a = a1; b = b1; c = c1; const double r1 = (expr);             \
+        a = a2; b = b2; c = c2; const double r2 = (expr);             \
         PT_ST(q0.y, r0); PT_ST(q0.z, r1); PT_ST(q0.w, r2);            \
     }                                                                 \
     break;
@@ -266,6 +279,7 @@ __device__ __forceinline__ void run_point_tape(char* __restrict__ base, int n)
     }
 }
 #undef PT_ST
+#undef PT_LOAD3
 #undef PT_UN
 #undef PT_BIN
 #undef PT_TER
@@ -328,7 +342,6 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
 
     const double h = 1.0 / (double)img.nfe;
     const int p_dim = img.p_dim, d_dim = img.d_dim;
-    const bool final_eval = img.nq > 0 && img.fq_state_dep;
 
     const long long total = la.n_d * (long long)la.n_tiles;
     unsigned phase = 0;
@@ -432,14 +445,13 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
                 Xs[(3 * n + 2) * BLOCK] = xv[2][n];
             }
 
-            bool conv = false, stop = false;
+            bool conv = false;
             double s_prev = 0.0;                          // no rate estimate before the second step
+            double r[N];                                  // after the loop: the last Newton update
             for (int it = 0;; ++it) {
-                if (stop && !final_eval) break;
                 run_point_tape<false>(base, img.n_pt);                           // f, df/dx, fq at the 3 points
-                if (stop) break;
 
-                double M[N][N], r[N];
+                double M[N][N];
 #pragma unroll
                 for (int jj = 0; jj < 3; ++jj) {
 #pragma unroll
@@ -447,7 +459,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
                         double lin = img.adot[jj + 1] * xs[n];                       // adot[0][jj+1]
 #pragma unroll
                         for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
-                        r[jj * NS + n] = fma(h, PT_LD(img.f_off[n] + jj * img.f_str[n]), -lin);
+                        r[jj * NS + n] = fma(h, PT_LD(img.f_o[n][jj]), -lin);
 #pragma unroll
                         for (int kk = 0; kk < 3; ++kk)
 #pragma unroll
@@ -456,7 +468,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
                                 M[jj * NS + n][kk * NS + m] = a;
                                 if (kk == jj && ((img.j_mask >> (n * NS + m)) & 1u))
                                     M[jj * NS + n][kk * NS + m] =
-                                        fma(-h, PT_LD(img.j_off[n * NS + m] + jj * img.j_str[n * NS + m]), a);
+                                        fma(-h, PT_LD(img.j_o[n * NS + m][jj]), a);
                             }
                     }
                 }
@@ -485,16 +497,25 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
                 s_prev = s;
                 if (bad) failed = true;
                 if (ok || bad) conv = true;
-                stop = __all_sync(0xffffffffu, conv) || (it + 1 >= img.max_it);
+                if (__all_sync(0xffffffffu, conv) || (it + 1 >= img.max_it)) break;
             }
             if (!conv) failed = true;
 
-            // quadrature states: x_q += h * sum_j bw_j fq(x_j) at the converged points
+            // quadrature states: x_q += h * sum_j bw_j fq(x_j).  The tape evaluated fq one Newton update
+            // before the converged point; dfq/dx * (last update) closes the gap (exact for integrands that
+            // are linear in the states, second order in a <= 1e-6 relative update otherwise).
             for (int q = 0; q < img.nq; ++q) {
                 if (!((img.fq_mask >> q) & 1u)) continue;
-                double acc = img.bw[0] * PT_LD(img.fq_off[q]);
-                acc = fma(img.bw[1], PT_LD(img.fq_off[q] + img.fq_str[q]), acc);
-                acc = fma(img.bw[2], PT_LD(img.fq_off[q] + 2 * img.fq_str[q]), acc);
+                double acc = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj) {
+                    double v = PT_LD(img.fq_o[q][jj]);
+#pragma unroll
+                    for (int n = 0; n < NS; ++n)
+                        if ((img.fqx_mask >> (q * NS + n)) & 1u)
+                            v = fma(PT_LD(img.fqx_o[q * NS + n][jj]), r[jj * NS + n], v);
+                    acc = fma(img.bw[jj], v, acc);
+                }
                 S[(img.qe_slot + q) * BLOCK] = fma(h, acc, S[(img.qe_slot + q) * BLOCK]);
             }
 #pragma unroll

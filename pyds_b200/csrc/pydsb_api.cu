@@ -108,19 +108,19 @@ void free_program(Program& p)
     p.d_code = p.d_consts = p.d_tabs = nullptr;
 }
 
-bool resolve_table(const Sections& secs, const char* tag, int n, int cap, unsigned* off, unsigned* str, unsigned* mask)
+bool resolve_table(const Sections& secs, const char* tag, int n, int cap, unsigned (*off)[3], unsigned* mask)
 {
     const Section* s = find(secs, tag);
     if (!s || (int)s->count < n || n > cap) return false;
     const uint16_t* v = reinterpret_cast<const uint16_t*>(s->data);
     *mask = 0;
     for (int i = 0; i < n; ++i) {
-        off[i] = 0; str[i] = 0;
+        off[i][0] = off[i][1] = off[i][2] = 0;
         if (v[i] == REF_NONE) continue;
         if (v[i] & REF_CONST) return false;
         *mask |= 1u << i;
-        off[i] = (v[i] & REF_MASK) * BLOCK * 8u;
-        str[i] = (v[i] & REF_WIDE) ? BLOCK * 8u : 0u;
+        for (int p3 = 0; p3 < 3; ++p3)
+            off[i][p3] = ((v[i] & REF_MASK) + ((v[i] & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
     }
     return true;
 }
@@ -146,9 +146,10 @@ int build_program(const Sections& secs, bool sens, Program& P)
     if (g.nq > 8) return fail(PYDSB_ERR_UNSUPPORTED, "at most 8 quadrature states");
     if (g.nce > 4) return fail(PYDSB_ERR_UNSUPPORTED, "at most 4 control functions");
     unsigned fmask = 0, jmask = 0;
-    if (!resolve_table(secs, "RF__", g.ns, 3, g.f_off, g.f_str, &fmask) ||
-        !resolve_table(secs, "RJ__", g.ns * g.ns, 9, g.j_off, g.j_str, &jmask) ||
-        !resolve_table(secs, "RFQ_", g.nq, 8, g.fq_off, g.fq_str, &g.fq_mask))
+    if (!resolve_table(secs, "RF__", g.ns, 3, g.f_o, &fmask) ||
+        !resolve_table(secs, "RJ__", g.ns * g.ns, 9, g.j_o, &jmask) ||
+        !resolve_table(secs, "RFQ_", g.nq, 8, g.fq_o, &g.fq_mask) ||
+        !resolve_table(secs, "RFQX", g.nq * g.ns, 24, g.fqx_o, &g.fqx_mask))
         return fail(PYDSB_ERR_INVALID, "bad f/J/fq reference table");
     g.j_mask = jmask;
     if (fmask != (1u << g.ns) - 1u)
@@ -191,7 +192,7 @@ int build_program(const Sections& secs, bool sens, Program& P)
     for (uint64_t w : code)
         if ((w & 0xFF) >= OP_COUNT) return fail(PYDSB_ERR_INVALID, "unknown opcode in tape");
     // pre-decode the point tape: per operand the byte offsets of the three collocation points
-    if (g.n_pt > MAX_PT) return fail(PYDSB_ERR_UNSUPPORTED, "point tape longer than the constant-bank window");
+    if (g.n_pt + 1 > MAX_PT) return fail(PYDSB_ERR_UNSUPPORTED, "point tape longer than the constant-bank window");
     {
         static const int xmap[OP_COUNT] = {/*MOV*/ XOP_MOV, /*NEG*/ XOP_NEG, /*ADD*/ XOP_ADD, /*SUB*/ XOP_SUB, /*MUL*/ XOP_MUL,
                                            /*DIV*/ XOP_DIV, /*FMA*/ XOP_FMA, /*FMS*/ XOP_FMS, /*FNMA*/ XOP_FNMA, /*SQR*/ XOP_SQR,
@@ -199,7 +200,8 @@ int build_program(const Sections& secs, bool sens, Program& P)
                                            /*COS*/ XOP_COLD, /*TANH*/ XOP_COLD, /*POW*/ XOP_COLD, /*ABS*/ XOP_ABS, /*MIN*/ XOP_MIN,
                                            /*MAX*/ XOP_MAX, /*BC3*/ XOP_NOP};
         const uint64_t* c = reinterpret_cast<const uint64_t*>(tn->data);
-        P.xpt.assign((size_t)16 * (g.n_pt > 0 ? g.n_pt : 1), 0u);
+        P.xpt.assign((size_t)16 * (g.n_pt + 1), 0u);                 // + one padding entry (prefetched, never run)
+        P.xpt[(size_t)16 * g.n_pt] = XOP_NOP;
         for (int i = 0; i < g.n_pt; ++i) {
             const uint64_t w = c[i];
             const unsigned op = (unsigned)(w & 0xFF);
@@ -211,6 +213,8 @@ int build_program(const Sections& secs, bool sens, Program& P)
                                 op == OP_MIN || op == OP_MAX) ? 2 : 1;
             uint32_t* x = &P.xpt[(size_t)16 * i];
             x[0] = (uint32_t)xmap[op] | (op << 8);
+            for (int k = 1; k <= nops; ++k)
+                if (!(refs[k] & REF_WIDE)) x[0] |= 1u << (3 + k);          // bits 4,5,6: operand a,b,c is narrow
             const bool cold_unary = (xmap[op] == XOP_COLD && nops == 1);
             for (int k = 0; k <= nops; ++k) {
                 const unsigned r = refs[k];
@@ -240,9 +244,8 @@ int build_program(const Sections& secs, bool sens, Program& P)
     if (!ok) return fail(PYDSB_ERR_INVALID, "reference table shorter than its dimension");
     if (sens) {
         if (g.nz > MAX_NZ) return fail(PYDSB_ERR_UNSUPPORTED, "at most 16 control values for the recourse optimiser");
-        if (!resolve_table(secs, "RFZ_", g.ns * g.nce, 12, g.fz_off, g.fz_str, &g.fz_mask) ||
-            !resolve_table(secs, "RFQX", g.nq * g.ns, 24, g.fqx_off, g.fqx_str, &g.fqx_mask) ||
-            !resolve_table(secs, "RFQZ", g.nq * g.nce, 32, g.fqz_off, g.fqz_str, &g.fqz_mask))
+        if (!resolve_table(secs, "RFZ_", g.ns * g.nce, 12, g.fz_o, &g.fz_mask) ||
+            !resolve_table(secs, "RFQZ", g.nq * g.nce, 32, g.fqz_o, &g.fqz_mask))
             return fail(PYDSB_ERR_INVALID, "bad sensitivity reference table");
         if (!push("RGX_", (size_t)g.ng * g.ns) || !push("RGQ_", (size_t)g.ng * g.nq))
             return fail(PYDSB_ERR_INVALID, "bad dg reference table");

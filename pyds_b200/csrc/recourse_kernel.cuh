@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
                     double lin = img.adot[jj + 1] * xs[n];
 #pragma unroll
                     for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
-                    r[jj * NS + n] = fma(h, PT_LD(img.f_off[n] + jj * img.f_str[n]), -lin);
+                    r[jj * NS + n] = fma(h, PT_LD(img.f_o[n][jj]), -lin);
 #pragma unroll
                     for (int kk = 0; kk < 3; ++kk)
 #pragma unroll
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
                             M[jj * NS + n][kk * NS + m] = a;
                             if (kk == jj && ((img.j_mask >> (n * NS + m)) & 1u))
                                 M[jj * NS + n][kk * NS + m] =
-                                    fma(-h, PT_LD(img.j_off[n * NS + m] + jj * img.j_str[n * NS + m]), a);
+                                    fma(-h, PT_LD(img.j_o[n * NS + m][jj]), a);
                         }
                 }
             lu_factor<N>(M, inv);                       // at the last pass: factors at the converged point
@@ -189,9 +189,9 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
         // quadratures at the converged points
         for (int q = 0; q < nq; ++q) {
             if (!((img.fq_mask >> q) & 1u)) continue;
-            double acc = img.bw[0] * PT_LD(img.fq_off[q]);
-            acc = fma(img.bw[1], PT_LD(img.fq_off[q] + img.fq_str[q]), acc);
-            acc = fma(img.bw[2], PT_LD(img.fq_off[q] + 2 * img.fq_str[q]), acc);
+            double acc = img.bw[0] * PT_LD(img.fq_o[q][0]);
+            acc = fma(img.bw[1], PT_LD(img.fq_o[q][1]), acc);
+            acc = fma(img.bw[2], PT_LD(img.fq_o[q][2]), acc);
             S[(img.qe_slot + q) * BLOCK] = fma(h, acc, S[(img.qe_slot + q) * BLOCK]);
         }
         // forward sensitivities of this element with respect to every control that has acted so far
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
                     if (!((img.fz_mask >> idx) & 1u)) continue;
 #pragma unroll
                     for (int jj = 0; jj < 3; ++jj)
-                        r[jj * NS + n] = fma(h, PT_LD(img.fz_off[idx] + jj * img.fz_str[idx]), r[jj * NS + n]);
+                        r[jj * NS + n] = fma(h, PT_LD(img.fz_o[idx][jj]), r[jj * NS + n]);
                 }
             }
             lu_apply<N>(M, inv, r);
@@ -225,12 +225,12 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
                     for (int n = 0; n < NS; ++n) {
                         const int idx = q * NS + n;
                         if ((img.fqx_mask >> idx) & 1u)
-                            tq = fma(PT_LD(img.fqx_off[idx] + jj * img.fqx_str[idx]), r[jj * NS + n], tq);
+                            tq = fma(PT_LD(img.fqx_o[idx][jj]), r[jj * NS + n], tq);
                     }
                     for (int k = 0; k < img.nce; ++k) {
                         const int idx = q * img.nce + k;
                         if (tab_cmap[e * img.nce + k] == c && ((img.fqz_mask >> idx) & 1u))
-                            tq += PT_LD(img.fqz_off[idx] + jj * img.fqz_str[idx]);
+                            tq += PT_LD(img.fqz_o[idx][jj]);
                     }
                     acc = fma(img.bw[jj], tq, acc);
                 }

@@ -196,11 +196,13 @@ class DaeModel:
             for n in T.topo_order([e]):
                 if n.op in ("ctrl", "x"):
                     raise ValueError("constraints may use end-point values m.end(state) and parameters only")
-        roots = {"x0": x0, "q0": q0, "z": z_exprs, "f": f, "J": J, "fq": fq, "g": gk}
-        # program 1 ("sens") adds what forward control sensitivities need: df/dz, dfq/dx, dfq/dz, dg/dxe, dg/dqe
+        # dfq/dx lets the kernel correct the quadrature integrands for the last Newton update instead of
+        # re-running the point tape at the converged state (exact for integrands linear in the states)
+        roots = {"x0": x0, "q0": q0, "z": z_exprs, "f": f, "J": J, "fq": fq, "g": gk,
+                 "fqx": [g.diff(fq[q], g.x(c)) for q in range(nq) for c in range(ns)]}
+        # program 1 ("sens") adds what forward control sensitivities need: df/dz, dfq/dz, dg/dxe, dg/dqe
         roots_s = dict(roots)
         roots_s["fz"] = [g.diff(f[r], g.ctrl(k)) for r in range(ns) for k in range(nce)]
-        roots_s["fqx"] = [g.diff(fq[q], g.x(c)) for q in range(nq) for c in range(ns)]
         roots_s["fqz"] = [g.diff(fq[q], g.ctrl(k)) for q in range(nq) for k in range(nce)]
         roots_s["gx"] = [g.diff(gk[k], g.xe(c)) for k in range(ng) for c in range(ns)]
         roots_s["gq"] = [g.diff(gk[k], g.qe(q)) for k in range(ng) for q in range(nq)]
@@ -245,9 +247,9 @@ class DaeModel:
             sec("RFQ_", "u16", tab(low, "fq", nq))
             sec("RG__", "u16", low.refs["g"])
             sec("CMAP", "u16", cmap)
+            sec("RFQX", "u16", tab(low, "fqx", nq * ns))
             if prog:
                 sec("RFZ_", "u16", tab(low, "fz", ns * nce))
-                sec("RFQX", "u16", tab(low, "fqx", nq * ns))
                 sec("RFQZ", "u16", tab(low, "fqz", nq * nce))
                 sec("RGX_", "u16", tab(low, "gx", ng * ns))
                 sec("RGQ_", "u16", tab(low, "gq", ng * nq))
