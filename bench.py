@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=200, help="design points per step of the CPU reference arm")
     ap.add_argument("--cpu-rows", type=int, default=1000, help="design points of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense9", action="store_true", help="keep cC in the Newton system (9 unknowns, SURVEY A.5 flop count)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -175,7 +176,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    lm = models.kinetics("design4").lower()
+    lm = models.kinetics("design4", dense9=args.dense9).lower()
     eng = capi.Engine(lm.blob, local_rank)
     sharded = ShardedEfp(eng, world, rank)
     n_d, n_t = args.n_d, args.n_theta

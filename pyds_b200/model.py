@@ -51,7 +51,8 @@ class _Control:
 
 
 class DaeModel:
-    def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-12, newton_max_it=25, predictor=False):
+    def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-12, newton_max_it=25, predictor=False,
+                 quadratures="auto"):
         self.graph = T.Graph()
         self.d_names = list(d_names)
         self.p_names = list(p_names)
@@ -59,6 +60,9 @@ class DaeModel:
         self.newton_rtol = float(newton_rtol)
         self.newton_max_it = int(newton_max_it)
         self.predictor = bool(predictor)        # start Newton from the extrapolated previous element
+        # "auto": every state that appears in no right-hand side becomes a quadrature (exact); or an explicit
+        # list of state names, e.g. ["u"] keeps cC in the Newton system (the 9-unknown form of SURVEY.md A.3)
+        self.quadratures = quadratures
         self.states: list[_State] = []
         self.controls: list[_Control] = []
         self.constraints = []          # (name, Expr (<= 0 feasible), bigM)
@@ -145,8 +149,14 @@ class DaeModel:
             for n in T.topo_order([s.rhs]):
                 if n.op == "x":
                     used.add(n.value)
-        dyn = [i for i in range(n_states) if i in used]
-        quad = [i for i in range(n_states) if i not in used]
+        if self.quadratures == "auto":
+            quad = [i for i in range(n_states) if i not in used]
+        else:
+            quad = [i for i in range(n_states) if self.states[i].name in self.quadratures]
+            bad = [self.states[i].name for i in quad if i in used]
+            if bad:
+                raise ValueError(f"states {bad} appear in a right-hand side and cannot be quadratures")
+        dyn = [i for i in range(n_states) if i not in quad]
         ns, nq = len(dyn), len(quad)
         if ns == 0:
             raise ValueError("model has no dynamic state")

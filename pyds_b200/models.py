@@ -19,7 +19,11 @@ from .model import DaeModel
 THETA_NAMES = ["E1", "E2", "k1", "k2"]
 
 
-def kinetics(variant: str = "twostage", nfe: int = 8, f_init=0.0, **kw) -> DaeModel:
+def kinetics(variant: str = "twostage", nfe: int = 8, f_init=0.0, dense9: bool = False, **kw) -> DaeModel:
+    """``dense9=True`` keeps cC inside the Newton system (3 dynamic states, 9 unknowns per element -- the
+    formulation SURVEY.md A.3/A.5 counts flops for) instead of treating it as a quadrature."""
+    if dense9:
+        kw["quadratures"] = ["u"]
     d_names = {"twostage": ["t_f", "T"], "design4": ["t_f", "T", "cA0", "Fbar"],
                "design6": ["t_f", "T", "cA0", "Fbar", "pB", "pA"]}[variant]
     m = DaeModel(d_names, THETA_NAMES, nfe=nfe, ncp=3, **kw)

@@ -320,9 +320,17 @@ class Graph:
                 return self.mul(self.mul(b, self.pow(a, self.const(b.value - 1.0))), da)
             return self.mul(n, self.add(self.mul(db, self.log(a)), self.div(self.mul(b, da), a)))
         if op in ("abs", "min", "max"):
+            # almost-everywhere derivatives with the subgradient 0 at the kink:
+            #   sign(v) = v / max(|v|, tiny);  min/max(a,b) = (a + b -/+ |a - b|)/2
             if da.is_const(0.0) and (len(n.args) == 1 or db.is_const(0.0)):
                 return self.const(0.0)
-            raise NotImplementedError(f"derivative of non-smooth op '{op}'")
+            sign = lambda v: self.div(v, self.maximum(self.abs(v), 1e-300))
+            if op == "abs":
+                return self.mul(sign(a), da)
+            s = sign(self.sub(a, b))
+            half_sum = self.mul(0.5, self.add(da, db))
+            half_dif = self.mul(0.5, self.mul(s, self.sub(da, db)))
+            return self.sub(half_sum, half_dif) if op == "min" else self.add(half_sum, half_dif)
         raise NotImplementedError(op)
 
 

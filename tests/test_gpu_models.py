@@ -1,0 +1,84 @@
+"""Other kernel instantiations and the generic interpreter paths on the GPU: NS = 3 (the 9-unknown
+form of the shipped model), NS = 1 with transcendental tape ops (out-of-line cold path), parameter-free
+design (d_dim = 0), state-dependent nonlinear quadrature integrand."""
+import numpy as np
+import pytest
+
+from oracle import cbind, kinetics as K, tape_vm
+from pyds_b200 import capi, models
+from pyds_b200.model import DaeModel
+
+pytestmark = pytest.mark.gpu
+G_SCALE = np.array([1.0, 1e5])
+
+
+def test_dense9_variant_ns3():
+    lm = models.kinetics("design4", dense9=True).lower()
+    assert (lm.ns, lm.nq) == (3, 1)
+    eng = capi.Engine(lm.blob, 0)
+    assert eng.info["ns"] == 3
+    rng = np.random.default_rng(12)
+    n_d, n_t = 41, 333
+    d = np.stack([rng.uniform(250, 350, n_d), rng.uniform(250, 300, n_d), rng.uniform(1500, 2500, n_d), rng.uniform(0, 2.5, n_d)], axis=1)
+    p = K.theta_samples(n_t)
+    g, ind, P = eng.eval_host(d, p, None, want_g=True, want_ind=True)
+    go, Po, _ = cbind.kinetics_grid(d, p, np.full(n_t, 1.0 / n_t), tol=1e-13)
+    assert np.all(np.abs(g - go) <= 1e-10 * np.maximum(np.abs(go), G_SCALE))
+    np.testing.assert_allclose(P, Po, atol=1e-12)
+    assert eng.counters()["failed"] == 0
+
+
+def _transcendental_model():
+    m = DaeModel(["a"], ["b", "c"], nfe=6)
+    g = m.graph
+    a, b, c = m.d["a"], m.p["b"], m.p["c"]
+    x = m.state("x", 1.0 + 0.1 * b)
+    q = m.state("q", 0.0)
+    m.ode(x, -a * g.tanh(x) * g.sqrt(1.0 + x * x) + b * g.log(2.0 + x ** 2) - g.sin(c * x) / (3.0 + g.cos(x)) + g.abs(x) ** 1.5 * 0.01)
+    m.ode(q, g.exp(-x) * x * x + g.minimum(x, 0.5) + g.maximum(c, x))          # nonlinear, state-dependent integrand
+    m.constraint("c1", m.end(x) - 1.2, 10.0)
+    m.constraint("c2", m.end(q) - 1.5 * c, 5.0)
+    return m
+
+
+def test_ns1_transcendental_ops_and_nonlinear_quadrature():
+    lm = _transcendental_model().lower()
+    assert (lm.ns, lm.nq, lm.ng) == (1, 1, 2)
+    eng = capi.Engine(lm.blob, 0)
+    vm = tape_vm.TapeVM(lm.blob)
+    rng = np.random.default_rng(5)
+    d = rng.uniform(0.3, 2.0, (23, 1))
+    p = np.stack([rng.uniform(0.2, 1.5, 150), rng.uniform(0.5, 1.2, 150)], axis=1)
+    g, ind, P = eng.eval_host(d, p, None, want_g=True, want_ind=True)
+    r = vm.evaluate(d, p, tol=1e-13)
+    # the kernel corrects the quadrature integrand to first order in the last Newton update instead of
+    # re-evaluating it: second-order term is far below the 1e-10 tolerance
+    assert np.all(np.abs(g - r["g"]) <= 1e-10 * np.maximum(np.abs(r["g"]), 1.0))
+    near = np.any(np.abs(r["g"]) < 1e-8, axis=-1)
+    assert np.all(((ind == 0.0) == r["feasible"]) | near)
+    assert 0.0 < P.mean() < 1.0
+
+
+def test_model_without_design_variables():
+    m = DaeModel([], ["k"], nfe=4)
+    x = m.state("x", 1.0)
+    m.ode(x, -m.p["k"] * x)
+    m.constraint("c", m.end(x) - 0.5, 1.0)
+    eng = capi.Engine(m.lower().blob, 0)
+    p = np.linspace(0.2, 1.5, 77)[:, None]
+    g, ind, P = eng.eval_host(np.zeros((2, 0)), p, None, want_g=True, want_ind=True)
+    r = tape_vm.TapeVM(m.lower().blob).evaluate(np.zeros((2, 0)), p, tol=1e-13)
+    np.testing.assert_allclose(g, r["g"], atol=1e-12)
+    np.testing.assert_allclose(g[0, :, 0], np.exp(-p[:, 0]) - 0.5, atol=1e-6)      # Radau 4x3 discretisation error
+    np.testing.assert_array_equal(g[0], g[1])
+    assert P[0] == np.mean(g[0, :, 0] <= 0.0)
+
+
+def test_unsupported_shapes_fail_loudly():
+    m = DaeModel(["a"], ["b"])
+    xs = [m.state(f"x{i}", 1.0) for i in range(4)]
+    for i in range(4):
+        m.ode(xs[i], -xs[(i + 1) % 4] * m.p["b"])          # 4 coupled dynamic states
+    m.constraint("c", m.end(xs[0]) - m.d["a"], 1.0)
+    with pytest.raises(capi.PydsbError, match="1..3 dynamic states"):
+        capi.Engine(m.lower().blob, 0)
