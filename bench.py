@@ -236,6 +236,13 @@ def main():
     k_ms = float(np.mean(kern_ms))
     achieved = n_d * n_t * f_alg / (k_ms * 1e-3) / 1e12
     alg_bytes = 8 * (n_d * lm.d_dim + n_t * (lm.p_dim + 1) + n_d)
+    traffic = None                      # dram bytes per launch from the committed ncu --set full capture of this config
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_feas_kernel.json")))
+        if tj["kernel"] == f"feas_kernel<{lm.ns}>" and tj["n_d"] == n_d and tj["n_theta"] == n_t:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        pass
 
     # end to end through the host-buffer C-ABI call (pinned staging, H2D, kernels, D2H inside the timed region)
     P_host = None
@@ -273,7 +280,7 @@ def main():
                        "l2": "256 MiB buffer written between timed steps (flush); inputs are < 1 MB, the path is fp64-pipe bound",
                        "newton_iters_per_element": I, "flops_per_eval": f_alg, "newton_unknowns": lm.ns * lm.ncp},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": None, "kernel": f"feas_kernel<{lm.ns}>",
+                         "frac": achieved / peak_tflops, "traffic": traffic, "kernel": f"feas_kernel<{lm.ns}>",
                          "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "peak_source": "measured in this run: pydsb_dfma_peak (independent-chain DFMA microkernel, best of 5); "
                                         "MEASURED_PEAKS.json carries no fp64 figure"},
