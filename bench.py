@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=1000, help="design points of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense9", action="store_true", help="keep cC in the Newton system (9 unknowns, SURVEY A.5 flop count)")
+    ap.add_argument("--coupled", action="store_true", help="one coupled 6-unknown Newton system instead of the block-triangular solve")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -176,7 +177,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    lm = models.kinetics("design4", dense9=args.dense9).lower()
+    lm = models.kinetics("design4", dense9=args.dense9, **({"block_triangular": False} if args.coupled else {})).lower()
     eng = capi.Engine(lm.blob, local_rank)
     sharded = ShardedEfp(eng, world, rank)
     n_d, n_t = args.n_d, args.n_theta
@@ -232,14 +233,14 @@ def main():
 
     # roofline of the dominant kernel (feas_kernel): algorithmic flops per launch / its event time
     I = cnt["newton_iters"] / max(cnt["scenarios"], 1) / lm.nfe
-    f_alg = lm.flops_per_evaluation(I)
+    f_alg = lm.flops_per_evaluation(I, newton_flops_per_eval=cnt["newton_flops"] / max(cnt["scenarios"], 1))
     k_ms = float(np.mean(kern_ms))
     achieved = n_d * n_t * f_alg / (k_ms * 1e-3) / 1e12
     alg_bytes = 8 * (n_d * lm.d_dim + n_t * (lm.p_dim + 1) + n_d)
     traffic = None                      # dram bytes per launch from the committed ncu --set full capture of this config
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_feas_kernel.json")))
-        if tj["kernel"] == f"feas_kernel<{lm.ns}>" and tj["n_d"] == n_d and tj["n_theta"] == n_t:
+        if tj["kernel"] == f"feas_kernel<{max(len(s) for s in lm.blocks)}>" and tj["n_d"] == n_d and tj["n_theta"] == n_t:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     except (OSError, KeyError, ValueError):
         pass
@@ -278,9 +279,10 @@ def main():
                                    f"{n_d} design points per GPU x {n_t} theta, no recourse; P(feasible) per point",
                        "n_d_per_gpu": n_d, "n_theta": n_t, "sharding": f"design points over {world} GPU(s), theta replicated",
                        "l2": "256 MiB buffer written between timed steps (flush); inputs are < 1 MB, the path is fp64-pipe bound",
-                       "newton_iters_per_element": I, "flops_per_eval": f_alg, "newton_unknowns": lm.ns * lm.ncp},
+                       "newton_iters_per_element": I, "flops_per_eval": f_alg,
+                       "state_blocks": [{"states": s, "unknowns": len(s) * lm.ncp, "linear": bool(l)} for s, l in zip(lm.blocks, lm.block_linear)]},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": traffic, "kernel": f"feas_kernel<{lm.ns}>",
+                         "frac": achieved / peak_tflops, "traffic": traffic, "kernel": f"feas_kernel<{max(len(s) for s in lm.blocks)}>",
                          "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "peak_source": "measured in this run: pydsb_dfma_peak (independent-chain DFMA microkernel, best of 5); "
                                         "MEASURED_PEAKS.json carries no fp64 figure"},

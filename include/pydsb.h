@@ -57,6 +57,8 @@ enum {
     PYDSB_CNT_FAILED,            /* scenarios whose state solve failed (counted infeasible; cf.
                                     reference pyds/solver.py:39-44, 63-69)                           */
     PYDSB_CNT_LAUNCHES,          /* kernel launches issued by this handle                            */
+    PYDSB_CNT_NEWTON_FLOPS,      /* sum over scenarios and blocks of (own iterations x algorithmic flops
+                                    of one Newton iteration of that block): the variable part of F_alg  */
     PYDSB_CNT_COUNT
 };
 

@@ -48,7 +48,17 @@ class TapeVM:
         self.sec = s
         (self.ns, self.nq, self.ng, self.d_dim, self.p_dim, self.nz, self.nfe, self.ncp, self.nce, self.n_units,
          self.ctrl_slot, self.xe_slot, self.qe_slot, self.x_slot, self.max_it,
-         self.j_mask, self.fq_state_dep, self.predictor) = [int(v) for v in s["HEAD"]]
+         _, self.fq_state_dep, self.predictor, self.n_blocks) = [int(v) for v in s["HEAD"]]
+        # blocks of the block-triangular state solve: (states, linear flag, tape) + the quadrature tape
+        B, Tn = s["BLKS"], s["BLKT"]
+        self.blocks, pc, fpos, jpos = [], 0, 0, 0
+        for b in range(self.n_blocks):
+            nsb = int(B[5 * b])
+            st = [int(x) for x in B[5 * b + 2:5 * b + 2 + nsb]]
+            self.blocks.append(dict(states=st, linear=int(B[5 * b + 1]), code=s["TPNT"][pc:pc + int(Tn[b])],
+                                    f=s["RF__"][fpos:fpos + nsb], J=s["RJ__"][jpos:jpos + nsb * nsb]))
+            pc += int(Tn[b]); fpos += nsb; jpos += nsb * nsb
+        self.q_code = s["TPNT"][pc:pc + int(Tn[self.n_blocks])]
         self.param_slots = [int(v) for v in s["RPAR"]]
         self.rtol = float(s["DBLS"][0])
         self.consts = s["CNST"]
@@ -149,48 +159,61 @@ class TapeVM:
                 R[self.ctrl_slot + k] = Z[int(self.cmap[e, k])]
             self._run(R, s["TELM"], 1)
             X = np.repeat(x0[:, None, :], ncp, axis=1)            # (S, pt, state)
-            active = ~failed
-            for it in range(max_it):
-                if not active.any():
-                    break
+
+            def put_states(Xc):
                 for i in range(ns):
                     for w in range(ncp):
-                        R[self.x_slot + 3 * i + w] = X[:, w, i]
-                self._run(R, s["TPNT"], ncp)
-                f = np.stack([np.stack([self._ld(R, r, w) * one for r in s["RF__"][:ns]], axis=1) for w in range(ncp)], axis=1)
-                J = np.zeros((S, ncp, ns, ns))
-                for w in range(ncp):
-                    for r_ in range(ns):
-                        for c_ in range(ns):
-                            J[:, w, r_, c_] = self._ld(R, s["RJ__"][r_ * ns + c_], w)
-                lin = np.einsum("kj,skn->sjn", A[1:, 1:], X) + A[0, 1:][None, :, None] * x0[:, None, :]
-                Rres = lin - h * f
-                M = np.zeros((S, ncp, ns, ncp, ns))
-                eye = np.eye(ns)
-                for j in range(ncp):
-                    for k in range(ncp):
-                        M[:, j, :, k, :] += A[k + 1, j + 1] * eye
-                    M[:, j, :, j, :] -= h * J[:, j]
-                idx = np.nonzero(active)[0]
-                with np.errstate(all="ignore"):
-                    try:
-                        dX = np.linalg.solve(M.reshape(S, n, n)[idx], -Rres.reshape(S, n, 1)[idx]).reshape(-1, ncp, ns)
-                    except np.linalg.LinAlgError:
-                        dX = np.full((idx.size, ncp, ns), np.nan)
-                X[idx] += dX
-                iters[idx] += 1
-                scale = np.maximum(np.abs(X[idx]).max(axis=(1, 2)), 1.0)
-                dmax = np.abs(dX).max(axis=(1, 2))
-                bad = ~np.isfinite(dmax)
-                failed[idx[bad]] = True
-                done = (dmax <= tol * scale) | bad
-                active[idx[done]] = False
-            failed |= active                                         # iteration cap reached
-            # quadratures use the converged point values
-            for i in range(ns):
-                for w in range(ncp):
-                    R[self.x_slot + 3 * i + w] = X[:, w, i]
-            self._run(R, s["TPNT"], ncp)
+                        R[self.x_slot + 3 * i + w] = Xc[:, w, i]
+
+            put_states(X)
+            for blk in self.blocks:
+                st = blk["states"]
+                nb = len(st)
+                nbn = nb * ncp
+                active = ~failed
+                for it in range(max_it):
+                    if not active.any():
+                        break
+                    put_states(X)
+                    self._run(R, blk["code"], ncp)
+                    f = np.stack([np.stack([self._ld(R, r, w) * one for r in blk["f"]], axis=1) for w in range(ncp)], axis=1)
+                    J = np.zeros((S, ncp, nb, nb))
+                    for w in range(ncp):
+                        for r_ in range(nb):
+                            for c_ in range(nb):
+                                J[:, w, r_, c_] = self._ld(R, blk["J"][r_ * nb + c_], w)
+                    Xb = X[:, :, st]
+                    lin = np.einsum("kj,skn->sjn", A[1:, 1:], Xb) + A[0, 1:][None, :, None] * x0[:, None, st]
+                    Rres = lin - h * f
+                    M = np.zeros((S, ncp, nb, ncp, nb))
+                    eye = np.eye(nb)
+                    for j in range(ncp):
+                        for k in range(ncp):
+                            M[:, j, :, k, :] += A[k + 1, j + 1] * eye
+                        M[:, j, :, j, :] -= h * J[:, j]
+                    idx = np.nonzero(active)[0]
+                    with np.errstate(all="ignore"):
+                        try:
+                            dX = np.linalg.solve(M.reshape(S, nbn, nbn)[idx], -Rres.reshape(S, nbn, 1)[idx]).reshape(-1, ncp, nb)
+                        except np.linalg.LinAlgError:
+                            dX = np.full((idx.size, ncp, nb), np.nan)
+                    Xn = X[idx]
+                    Xn[:, :, st] += dX
+                    X[idx] = Xn
+                    iters[idx] += 1
+                    scale = np.maximum(np.abs(X[idx][:, :, st]).max(axis=(1, 2)), 1.0)
+                    dmax = np.abs(dX).max(axis=(1, 2))
+                    bad = ~np.isfinite(dmax)
+                    failed[idx[bad]] = True
+                    done = (dmax <= tol * scale) | bad
+                    active[idx[done]] = False
+                failed |= active                                     # iteration cap reached
+            # quadrature integrands (and, in the sensitivity program, everything else) at the converged points
+            put_states(X)
+            for blk in self.blocks:
+                if want_sens or not len(self.q_code):
+                    self._run(R, blk["code"], ncp)
+            self._run(R, self.q_code, ncp)
             for k in range(nq):
                 acc = 0.0
                 for w in range(ncp):

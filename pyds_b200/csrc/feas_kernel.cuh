@@ -8,10 +8,11 @@
 // Per scenario (what the reference does inside one GAMS/CONOPT solve per design point,
 // pyds/run.py:55-67 + pyds/solver.py:50-55, for fixed controls):
 //   1. `pro` tape: parameter-only sub-expressions (Arrhenius factors etc.), initial states
-//   2. for each finite element: `elem` tape, then full Newton on the 3*NS collocation unknowns:
-//        `pt` tape (f, df/dx at the 3 Radau points, evaluated 3-wide) -> residual and Jacobian
-//        assembled in registers -> register-resident dense LU -> update
-//      quadrature states advance with the Radau weights
+//   2. for each finite element: `elem` tape, then, block after block of the (block-triangular) state
+//      dependency graph, full Newton on the block's 3*NSB collocation unknowns:
+//        point tape of the block (f, df/dx at the 3 Radau points, evaluated 3-wide) -> residual and
+//        Jacobian assembled in registers -> register-resident dense LU -> update
+//      then the quadrature tape; quadrature states advance with the Radau weights
 //   3. `g` tape -> constraint values; indicator = any(g_k > 0)   (utils.py:23-29, solver.py:71-80)
 //   4. w_j * 1[feasible] reduced with warp shuffles; one partial per tile (deterministic finish
 //      in reduce_partials_kernel) -- DEUS's efp reduction.
@@ -27,34 +28,42 @@
 
 namespace pydsb {
 
+constexpr int MAX_BLOCKS = 4;          // blocks of the block-triangular state solve
+constexpr int MAX_STATES = 8;          // dynamic states in total (each block holds at most 3)
+
 struct ExecImage {
     // global-memory copies made by pydsb_model_create
     const uint64_t* code;      // pro | elem | g   (narrow tapes; staged in shared memory)
     const double* consts;      // constant pool
-    const uint16_t* tabs;      // par[n_param] x0[ns] q0[nq] ztab[nz] zfix[nz] gtab[ng] cmap[nfe*nce]
+    const uint16_t* tabs;      // par[n_param] x0[ns] q0[nq] ztab[nz] zfix[nz] gtab[ng] cmap[nfe*nce] (+ sens tables)
     int n_pro, n_elem, n_pt, n_g, n_const, n_tabs;
     int ns, nq, ng, d_dim, p_dim, nz, nfe, nce, n_units;
     int ctrl_slot, xe_slot, qe_slot, x_slot;
-    unsigned j_mask;           // bit r*ns+c: df_r/dx_c is not structurally zero
-    // outputs of the point tape read by the compiled Newton code: byte offset of every collocation
-    // point (equal offsets = narrow value), so that each access is LDS [thread base + uniform offset]
-    unsigned f_o[3][3];
-    unsigned j_o[9][3];
-    unsigned fq_o[8][3];
-    unsigned fq_mask;
-    unsigned fqx_o[24][3], fqx_mask;                  // dfq/dx (nq x ns)
-    // program 1 only: df/dz (ns x nce), dfq/dz (nq x nce) -- same (offset, stride) form;
-    // dg/dxe (ng x ns) and dg/dqe (ng x nq) are narrow references in `tabs` after cmap
-    unsigned fz_o[12][3], fz_mask;
-    unsigned fqz_o[32][3], fqz_mask;
-    double bigm_inv[8];        // 1 / M_k
     int fq_state_dep;
-    int predictor;
     int max_it;
     double rtol2;              // (relative Newton tolerance)^2
     double adot[16];
     double bw[3];
-    double ext[12];            // ext[4*j + k] = l_k(1 + tau_{j+1}): previous element's cubic extrapolated
+    // block-triangular state solve: block b owns blk_ns[b] states and instructions
+    // [blk_pc0[b], blk_pc0[b] + blk_npt[b]) of the pre-decoded point tape; then the quadrature tape
+    int n_blocks;
+    int blk_ns[MAX_BLOCKS], blk_lin[MAX_BLOCKS], blk_pc0[MAX_BLOCKS], blk_npt[MAX_BLOCKS];
+    unsigned blk_flops[MAX_BLOCKS];            // algorithmic flops of one Newton iteration of the block
+    int q_pc0, q_npt;
+    // byte offsets (per collocation point; equal offsets = narrow value) so that every access of the
+    // compiled Newton code is LDS/STS [thread base + uniform offset]
+    unsigned blk_x_o[MAX_BLOCKS][3][3];        // the block's states in the X region
+    unsigned blk_f_o[MAX_BLOCKS][3][3];        // f of the block's states
+    unsigned blk_j_o[MAX_BLOCKS][9][3];        // d f_r / d x_c within the block
+    unsigned blk_jmask[MAX_BLOCKS];            // bit r*nsb+c: entry not structurally zero
+    unsigned fq_o[8][3];
+    unsigned fq_mask;
+    // program 1 only (one block): dfq/dx (nq x ns), df/dz (ns x nce), dfq/dz (nq x nce);
+    // dg/dxe (ng x ns) and dg/dqe (ng x nq) are narrow references in `tabs` after cmap
+    unsigned fqx_o[24][3], fqx_mask;
+    unsigned fz_o[12][3], fz_mask;
+    unsigned fqz_o[32][3], fqz_mask;
+    double bigm_inv[8];        // 1 / M_k
     // shared-memory carve-up (bytes from the start of dynamic smem)
     int off_code, off_const, off_tabs, off_land, off_slots, smem_bytes;
 };
@@ -172,6 +181,12 @@ __device__ __forceinline__ double warp_sum(double v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __device__ __forceinline__ unsigned warp_sum_u32(unsigned v)
 {
 #pragma unroll
@@ -249,10 +264,10 @@ __device__ __noinline__ double cold_op(unsigned op, double a, double b)
     break;
 
 template <bool SENS>
-__device__ __forceinline__ void run_point_tape(char* __restrict__ base, int n)
+__device__ __forceinline__ void run_point_tape(char* __restrict__ base, int pc0, int n)
 {
     const uint4* const c_pt = SENS ? c_pt_s : pydsb::c_pt;
-    for (int pc = 0; pc < n; ++pc) {
+    for (int pc = pc0; pc < pc0 + n; ++pc) {
         const uint4 q0 = c_pt[4 * pc];
         const uint4 q1 = c_pt[4 * pc + 1];
         switch (q0.x & 15u) {
@@ -278,7 +293,6 @@ __device__ __forceinline__ void run_point_tape(char* __restrict__ base, int n)
         }
     }
 }
-#undef PT_ST
 #undef PT_LOAD3
 #undef PT_UN
 #undef PT_BIN
@@ -293,11 +307,90 @@ __device__ __noinline__ void run_narrow_tape(double* S, const double* cpool, con
     run_tape<1>(vm, code, n);
 }
 
-template <int NS>
-__global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
+// ---------------------------------------------------------------------------------------------
+// Newton solve of one block (NSB states, N = 3*NSB collocation unknowns) on one finite element.
+// Residual and Jacobian are assembled in registers from the block's point tape outputs; dense LU
+// without pivoting, register resident.  Returns the iterations this thread needed (own convergence).
+// ---------------------------------------------------------------------------------------------
+template <int NSB>
+__device__ __forceinline__ unsigned newton_block(const ExecImage& img, int b, char* __restrict__ base, double h,
+                                                 bool& failed, unsigned& warp_iters)
+{
+    constexpr int N = 3 * NSB;
+    double xs[NSB], xv[3][NSB];
+    // element start = end point of the previous element (the prologue seeds point 2 with x(0))
+#pragma unroll
+    for (int n = 0; n < NSB; ++n) {
+        xs[n] = PT_LD(img.blk_x_o[b][n][2]);
+        xv[0][n] = xv[1][n] = xv[2][n] = xs[n];
+        PT_ST(img.blk_x_o[b][n][0], xs[n]);
+        PT_ST(img.blk_x_o[b][n][1], xs[n]);
+    }
+    const int pc0 = img.blk_pc0[b], npt = img.blk_npt[b];
+    const unsigned jmask = img.blk_jmask[b];
+    const bool linear = img.blk_lin[b] != 0;
+    bool conv = false;
+    unsigned my_iters = 0;
+    double s_prev = 0.0;                          // no rate estimate before the second step
+    for (int it = 0;; ++it) {
+        run_point_tape<false>(base, pc0, npt);    // f and df/dx of this block at the 3 points
+
+        double M[N][N], r[N];
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+#pragma unroll
+            for (int n = 0; n < NSB; ++n) {
+                double lin = img.adot[jj + 1] * xs[n];                       // adot[0][jj+1]
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
+                r[jj * NSB + n] = fma(h, PT_LD(img.blk_f_o[b][n][jj]), -lin);
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+                    for (int m = 0; m < NSB; ++m) {
+                        const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
+                        M[jj * NSB + n][kk * NSB + m] = a;
+                        if (kk == jj && ((jmask >> (n * NSB + m)) & 1u))
+                            M[jj * NSB + n][kk * NSB + m] = fma(-h, PT_LD(img.blk_j_o[b][n * NSB + m][jj]), a);
+                    }
+            }
+        }
+
+        lu_solve_inplace<N>(M, r);
+
+        double s = 0.0, sc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+            for (int n = 0; n < NSB; ++n) {
+                const double dx = r[kk * NSB + n];
+                const double xn = xv[kk][n] + dx;
+                xv[kk][n] = xn;
+                PT_ST(img.blk_x_o[b][n][kk], xn);
+                s = fma(dx, dx, s);
+                sc = fma(xn, xn, sc);
+            }
+        if (!conv) ++my_iters;
+        ++warp_iters;
+        // stop when the step is below tolerance, or when the contraction rate seen so far bounds the
+        // remaining error below it:  |dx_k|^2 / |dx_{k-1}| <= rtol * |X|.  A linear block is exact after
+        // one step.
+        const double lim = img.rtol2 * fmax(sc, 1.0);
+        const bool bad = !(s <= DBL_MAX);                        // inf or nan
+        const bool ok = linear || (s <= lim) || (s * s <= lim * s_prev && s <= 0.01 * s_prev);
+        s_prev = s;
+        if (bad) failed = true;
+        if (ok || bad) conv = true;
+        if (__all_sync(0xffffffffu, conv) || (it + 1 >= img.max_it)) break;
+    }
+    if (!conv) failed = true;
+    return my_iters;
+}
+
+template <int MAXNS>
+__global__ void __launch_bounds__(BLOCK, (MAXNS <= 2 ? 4 : 2))
     feas_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ LaunchArgs la)
 {
-    constexpr int N = 3 * NS;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -367,7 +460,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
     long long t = blockIdx.x;
     if (t < total && tid == 0) issue(t);
 
-    unsigned long long cnt_iters = 0;
+    unsigned long long cnt_iters = 0, cnt_flops = 0;
     unsigned cnt_warp_iters = 0, cnt_failed = 0, cnt_done = 0;
 
     for (; t < total; t += gridDim.x) {
@@ -395,15 +488,18 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
             if (nt < total && tid == 0) issue(nt);
         }
 
-        // ---- prologue ----
+        // ---- prologue: parameter-only values, initial states (seeded at collocation point 2) ----
         run_narrow_tape(S, cpool, code_pro, img.n_pro);
-        double xs[NS], xs_old[NS];
-#pragma unroll
-        for (int n = 0; n < NS; ++n) xs[n] = xs_old[n] = vm_ld(vm, tab_x0[n]);
+        {
+            double x0v[MAX_STATES];
+            for (int n = 0; n < img.ns; ++n) x0v[n] = vm_ld(vm, tab_x0[n]);      // read all before X overlays are written
+            for (int n = 0; n < img.ns; ++n) Xs[(3 * n + 2) * BLOCK] = x0v[n];
+        }
         for (int q = 0; q < img.nq; ++q) S[(img.qe_slot + q) * BLOCK] = vm_ld(vm, tab_q0[q]);
 
         bool failed = false;
         unsigned my_iters = 0;
+        unsigned long long my_flops = 0;
 
         for (int e = 0; e < img.nfe; ++e) {
             // controls of this finite element
@@ -418,116 +514,36 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
             }
             run_narrow_tape(S, cpool, code_elem, img.n_elem);
 
-            // Newton start: the previous element's collocation cubic extrapolated into this one
-            // (first element / predictor off: the element's initial state)
-            double xv[3][NS];
-            if (e > 0 && img.predictor) {
-#pragma unroll
-                for (int n = 0; n < NS; ++n) {
-                    const double p1 = Xs[(3 * n + 0) * BLOCK], p2 = Xs[(3 * n + 1) * BLOCK];
-#pragma unroll
-                    for (int jj = 0; jj < 3; ++jj) {
-                        double v = img.ext[4 * jj] * xs_old[n];
-                        v = fma(img.ext[4 * jj + 1], p1, v);
-                        v = fma(img.ext[4 * jj + 2], p2, v);
-                        v = fma(img.ext[4 * jj + 3], xs[n], v);
-                        xv[jj][n] = v;
-                    }
+            // blocks of the state dependency graph, dependencies first
+            for (int b = 0; b < img.n_blocks; ++b) {
+                unsigned it_b = 0;
+                const int nsb = img.blk_ns[b];
+                if (nsb == 1) it_b = newton_block<1>(img, b, base, h, failed, cnt_warp_iters);
+                if constexpr (MAXNS >= 2) { if (nsb == 2) it_b = newton_block<2>(img, b, base, h, failed, cnt_warp_iters); }
+                if constexpr (MAXNS >= 3) { if (nsb == 3) it_b = newton_block<3>(img, b, base, h, failed, cnt_warp_iters); }
+                my_iters += it_b;
+                my_flops += (unsigned long long)it_b * img.blk_flops[b];
+            }
+
+            // quadrature states: x_q += h * sum_j bw_j fq(x_j) at the converged points
+            if (img.nq > 0) {
+                run_point_tape<false>(base, img.q_pc0, img.q_npt);
+                for (int q = 0; q < img.nq; ++q) {
+                    if (!((img.fq_mask >> q) & 1u)) continue;
+                    double acc = img.bw[0] * PT_LD(img.fq_o[q][0]);
+                    acc = fma(img.bw[1], PT_LD(img.fq_o[q][1]), acc);
+                    acc = fma(img.bw[2], PT_LD(img.fq_o[q][2]), acc);
+                    S[(img.qe_slot + q) * BLOCK] = fma(h, acc, S[(img.qe_slot + q) * BLOCK]);
                 }
-            } else {
-#pragma unroll
-                for (int n = 0; n < NS; ++n) xv[0][n] = xv[1][n] = xv[2][n] = xs[n];
-            }
-#pragma unroll
-            for (int n = 0; n < NS; ++n) {
-                Xs[(3 * n + 0) * BLOCK] = xv[0][n];
-                Xs[(3 * n + 1) * BLOCK] = xv[1][n];
-                Xs[(3 * n + 2) * BLOCK] = xv[2][n];
-            }
-
-            bool conv = false;
-            double s_prev = 0.0;                          // no rate estimate before the second step
-            double r[N];                                  // after the loop: the last Newton update
-            for (int it = 0;; ++it) {
-                run_point_tape<false>(base, img.n_pt);                           // f, df/dx, fq at the 3 points
-
-                double M[N][N];
-#pragma unroll
-                for (int jj = 0; jj < 3; ++jj) {
-#pragma unroll
-                    for (int n = 0; n < NS; ++n) {
-                        double lin = img.adot[jj + 1] * xs[n];                       // adot[0][jj+1]
-#pragma unroll
-                        for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
-                        r[jj * NS + n] = fma(h, PT_LD(img.f_o[n][jj]), -lin);
-#pragma unroll
-                        for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                            for (int m = 0; m < NS; ++m) {
-                                const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
-                                M[jj * NS + n][kk * NS + m] = a;
-                                if (kk == jj && ((img.j_mask >> (n * NS + m)) & 1u))
-                                    M[jj * NS + n][kk * NS + m] =
-                                        fma(-h, PT_LD(img.j_o[n * NS + m][jj]), a);
-                            }
-                    }
-                }
-
-                lu_solve_inplace<N>(M, r);
-
-                double s = 0.0, sc = 0.0;
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                    for (int n = 0; n < NS; ++n) {
-                        const double dx = r[kk * NS + n];
-                        const double xn = xv[kk][n] + dx;
-                        xv[kk][n] = xn;
-                        Xs[(3 * n + kk) * BLOCK] = xn;
-                        s = fma(dx, dx, s);
-                        sc = fma(xn, xn, sc);
-                    }
-                if (!conv) ++my_iters;
-                ++cnt_warp_iters;
-                // stop when the step is below tolerance, or when the contraction rate seen so far
-                // bounds the remaining error below it:  |dx_k|^2 / |dx_{k-1}| <= rtol * |X|
-                const double lim = img.rtol2 * fmax(sc, 1.0);
-                const bool bad = !(s <= DBL_MAX);                        // inf or nan
-                const bool ok = (s <= lim) || (s * s <= lim * s_prev && s <= 0.01 * s_prev);
-                s_prev = s;
-                if (bad) failed = true;
-                if (ok || bad) conv = true;
-                if (__all_sync(0xffffffffu, conv) || (it + 1 >= img.max_it)) break;
-            }
-            if (!conv) failed = true;
-
-            // quadrature states: x_q += h * sum_j bw_j fq(x_j).  The tape evaluated fq one Newton update
-            // before the converged point; dfq/dx * (last update) closes the gap (exact for integrands that
-            // are linear in the states, second order in a <= 1e-6 relative update otherwise).
-            for (int q = 0; q < img.nq; ++q) {
-                if (!((img.fq_mask >> q) & 1u)) continue;
-                double acc = 0.0;
-#pragma unroll
-                for (int jj = 0; jj < 3; ++jj) {
-                    double v = PT_LD(img.fq_o[q][jj]);
-#pragma unroll
-                    for (int n = 0; n < NS; ++n)
-                        if ((img.fqx_mask >> (q * NS + n)) & 1u)
-                            v = fma(PT_LD(img.fqx_o[q * NS + n][jj]), r[jj * NS + n], v);
-                    acc = fma(img.bw[jj], v, acc);
-                }
-                S[(img.qe_slot + q) * BLOCK] = fma(h, acc, S[(img.qe_slot + q) * BLOCK]);
-            }
-#pragma unroll
-            for (int n = 0; n < NS; ++n) {
-                xs_old[n] = xs[n];
-                xs[n] = xv[2][n];
             }
         }
 
         // ---- CQAs, indicator, outputs ----
-#pragma unroll
-        for (int n = 0; n < NS; ++n) S[(img.xe_slot + n) * BLOCK] = xs[n];
+        {
+            double xe[MAX_STATES];
+            for (int n = 0; n < img.ns; ++n) xe[n] = Xs[(3 * n + 2) * BLOCK];
+            for (int n = 0; n < img.ns; ++n) S[(img.xe_slot + n) * BLOCK] = xe[n];
+        }
         run_narrow_tape(S, cpool, code_g, img.n_g);
         bool feasible = !failed;
         for (int c = 0; c < img.ng; ++c) {
@@ -544,6 +560,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
         if (lane == 0) red[warp] = wv;
         if (valid) {
             cnt_iters += my_iters;
+            cnt_flops += my_flops;
             cnt_failed += failed ? 1u : 0u;
             cnt_done += 1u;
         }
@@ -558,20 +575,23 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 4 : 2))
 
     // ---- counters: one atomic per warp ----
     if (la.counters) {
-        const unsigned it_lo = warp_sum_u32((unsigned)cnt_iters);
+        const unsigned long long it_sum = warp_sum_u64(cnt_iters);
+        const unsigned long long fl_sum = warp_sum_u64(cnt_flops);
         const unsigned wi = warp_sum_u32(cnt_warp_iters);
         const unsigned fl = warp_sum_u32(cnt_failed);
         const unsigned dn = warp_sum_u32(cnt_done);
         if (lane == 0) {
             atomicAdd(&la.counters[0], (unsigned long long)dn);
-            atomicAdd(&la.counters[1], (unsigned long long)it_lo);
+            atomicAdd(&la.counters[1], it_sum);
             atomicAdd(&la.counters[2], (unsigned long long)wi);
             atomicAdd(&la.counters[3], (unsigned long long)fl);
+            atomicAdd(&la.counters[5], fl_sum);
         }
     }
 }
 
 #undef PT_LD
+#undef PT_ST
 
 // Deterministic finish of the P(feasible) reduction: one thread per design point sums its tile
 // partials in tile order.

@@ -133,27 +133,65 @@ int build_program(const Sections& secs, bool sens, Program& P)
     for (const char* t : need)
         if (!find(secs, t)) return fail(PYDSB_ERR_INVALID, std::string("blob lacks section ") + t);
     const Section* head = find(secs, "HEAD");
-    if (head->count < 18) return fail(PYDSB_ERR_INVALID, "HEAD too short");
+    if (head->count < 19) return fail(PYDSB_ERR_INVALID, "HEAD too short");
     const uint32_t* H = reinterpret_cast<const uint32_t*>(head->data);
     ExecImage& g = P.img;
     g.ns = H[0]; g.nq = H[1]; g.ng = H[2]; g.d_dim = H[3]; g.p_dim = H[4]; g.nz = H[5]; g.nfe = H[6];
     const int ncp = H[7];
     g.nce = H[8]; g.n_units = H[9]; g.ctrl_slot = H[10]; g.xe_slot = H[11]; g.qe_slot = H[12];
-    g.x_slot = H[13]; g.max_it = H[14]; g.j_mask = H[15]; g.fq_state_dep = H[16]; g.predictor = H[17];
+    g.x_slot = H[13]; g.max_it = H[14]; g.fq_state_dep = H[16]; g.n_blocks = H[18];
     if (ncp != 3) return fail(PYDSB_ERR_UNSUPPORTED, "kernels are built for ncp = 3 (Radau)");
-    if (!feas_for(g.ns)) return fail(PYDSB_ERR_UNSUPPORTED, "register-resident Newton kernels cover 1..3 dynamic states");
+    if (g.ns < 1 || g.ns > MAX_STATES) return fail(PYDSB_ERR_UNSUPPORTED, "1..8 dynamic states are supported");
+    if (g.n_blocks < 1 || g.n_blocks > MAX_BLOCKS) return fail(PYDSB_ERR_UNSUPPORTED, "1..4 blocks of coupled states are supported");
+    {
+        // blocks: [nsb, linear, s0, s1, s2] each; tape lengths per block + quadrature tape
+        const Section *bs = find(secs, "BLKS"), *bt = find(secs, "BLKT"), *bf = find(secs, "BLKF");
+        if (!bs || !bt || !bf || (int)bs->count < 5 * g.n_blocks || (int)bt->count < g.n_blocks + 1 || (int)bf->count < g.n_blocks)
+            return fail(PYDSB_ERR_INVALID, "bad block tables");
+        const uint16_t* B = reinterpret_cast<const uint16_t*>(bs->data);
+        const uint32_t* T = reinterpret_cast<const uint32_t*>(bt->data);
+        const uint32_t* F = reinterpret_cast<const uint32_t*>(bf->data);
+        const Section *rf = find(secs, "RF__"), *rj = find(secs, "RJ__");
+        const uint16_t* RF = reinterpret_cast<const uint16_t*>(rf->data);
+        const uint16_t* RJ = reinterpret_cast<const uint16_t*>(rj->data);
+        int pc = 0, fpos = 0, jpos = 0, seen = 0;
+        for (int b = 0; b < g.n_blocks; ++b) {
+            const int nsb = B[5 * b];
+            if (nsb < 1 || nsb > 3)
+                return fail(PYDSB_ERR_UNSUPPORTED, "register-resident Newton kernels cover 1..3 dynamic states per coupled block");
+            g.blk_ns[b] = nsb; g.blk_lin[b] = B[5 * b + 1]; g.blk_pc0[b] = pc; g.blk_npt[b] = (int)T[b]; g.blk_flops[b] = F[b];
+            pc += (int)T[b];
+            if ((int)rf->count < fpos + nsb || (int)rj->count < jpos + nsb * nsb) return fail(PYDSB_ERR_INVALID, "bad f/J tables");
+            g.blk_jmask[b] = 0;
+            for (int n = 0; n < nsb; ++n) {
+                const int st = B[5 * b + 2 + n];
+                if (st >= g.ns) return fail(PYDSB_ERR_INVALID, "bad state index in block table");
+                seen |= 1 << st;
+                const unsigned rfv = RF[fpos + n];
+                if (rfv == REF_NONE || (rfv & REF_CONST)) return fail(PYDSB_ERR_UNSUPPORTED, "a dynamic state has an identically zero right-hand side");
+                for (int p3 = 0; p3 < 3; ++p3) {
+                    g.blk_x_o[b][n][p3] = (unsigned)(g.x_slot + 3 * st + p3) * BLOCK * 8u;
+                    g.blk_f_o[b][n][p3] = ((rfv & REF_MASK) + ((rfv & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
+                }
+            }
+            for (int i = 0; i < nsb * nsb; ++i) {
+                const unsigned v = RJ[jpos + i];
+                for (int p3 = 0; p3 < 3; ++p3) g.blk_j_o[b][i][p3] = 0;
+                if (v == REF_NONE) continue;
+                if (v & REF_CONST) return fail(PYDSB_ERR_INVALID, "constant reference in J table");
+                g.blk_jmask[b] |= 1u << i;
+                for (int p3 = 0; p3 < 3; ++p3) g.blk_j_o[b][i][p3] = ((v & REF_MASK) + ((v & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
+            }
+            fpos += nsb; jpos += nsb * nsb;
+        }
+        if (seen != (1 << g.ns) - 1) return fail(PYDSB_ERR_INVALID, "blocks do not cover every dynamic state");
+        g.q_pc0 = pc; g.q_npt = (int)T[g.n_blocks];
+    }
     if (g.ng < 1 || g.ng > 8 || g.nfe < 1 || g.p_dim < 1 || g.d_dim < 0) return fail(PYDSB_ERR_INVALID, "bad dimensions");
     if (g.nq > 8) return fail(PYDSB_ERR_UNSUPPORTED, "at most 8 quadrature states");
     if (g.nce > 4) return fail(PYDSB_ERR_UNSUPPORTED, "at most 4 control functions");
-    unsigned fmask = 0, jmask = 0;
-    if (!resolve_table(secs, "RF__", g.ns, 3, g.f_o, &fmask) ||
-        !resolve_table(secs, "RJ__", g.ns * g.ns, 9, g.j_o, &jmask) ||
-        !resolve_table(secs, "RFQ_", g.nq, 8, g.fq_o, &g.fq_mask) ||
-        !resolve_table(secs, "RFQX", g.nq * g.ns, 24, g.fqx_o, &g.fqx_mask))
-        return fail(PYDSB_ERR_INVALID, "bad f/J/fq reference table");
-    g.j_mask = jmask;
-    if (fmask != (1u << g.ns) - 1u)
-        return fail(PYDSB_ERR_UNSUPPORTED, "a dynamic state has an identically zero right-hand side");
+    if (!resolve_table(secs, "RFQ_", g.nq, 8, g.fq_o, &g.fq_mask))
+        return fail(PYDSB_ERR_INVALID, "bad fq reference table");
     {
         const double rtol = reinterpret_cast<const double*>(find(secs, "DBLS")->data)[0];
         g.rtol2 = rtol * rtol;
@@ -169,19 +207,6 @@ int build_program(const Sections& secs, bool sens, Program& P)
         if (!(M > 0.0)) return fail(PYDSB_ERR_INVALID, "big-M constants must be positive");
         g.bigm_inv[k] = 1.0 / M;
     }
-    {
-        // extrapolation weights of the previous element's cubic: l_k(1 + tau_j), Radau-3 nodes
-        const long double s6 = sqrtl(6.0L);
-        const long double tau[4] = {0.0L, (4.0L - s6) / 10.0L, (4.0L + s6) / 10.0L, 1.0L};
-        for (int j = 0; j < 3; ++j)
-            for (int k = 0; k < 4; ++k) {
-                long double v = 1.0L;
-                for (int l = 0; l < 4; ++l)
-                    if (l != k) v *= (1.0L + tau[j + 1] - tau[l]) / (tau[k] - tau[l]);
-                g.ext[4 * j + k] = (double)v;
-            }
-    }
-
     const Section *tp = find(secs, "TPRO"), *te = find(secs, "TELM"), *tn = find(secs, "TPNT"), *tg = find(secs, "TGEE");
     g.n_pro = tp->count; g.n_elem = te->count; g.n_pt = tn->count; g.n_g = tg->count;
     std::vector<uint64_t> code;
@@ -244,7 +269,9 @@ int build_program(const Sections& secs, bool sens, Program& P)
     if (!ok) return fail(PYDSB_ERR_INVALID, "reference table shorter than its dimension");
     if (sens) {
         if (g.nz > MAX_NZ) return fail(PYDSB_ERR_UNSUPPORTED, "at most 16 control values for the recourse optimiser");
-        if (!resolve_table(secs, "RFZ_", g.ns * g.nce, 12, g.fz_o, &g.fz_mask) ||
+        if (g.n_blocks != 1 || g.ns > 3) return fail(PYDSB_ERR_UNSUPPORTED, "the sensitivity program is one coupled block of <= 3 states");
+        if (!resolve_table(secs, "RFQX", g.nq * g.ns, 24, g.fqx_o, &g.fqx_mask) ||
+            !resolve_table(secs, "RFZ_", g.ns * g.nce, 12, g.fz_o, &g.fz_mask) ||
             !resolve_table(secs, "RFQZ", g.nq * g.nce, 32, g.fqz_o, &g.fqz_mask))
             return fail(PYDSB_ERR_INVALID, "bad sensitivity reference table");
         if (!push("RGX_", (size_t)g.ng * g.ns) || !push("RGQ_", (size_t)g.ng * g.nq))
@@ -388,7 +415,9 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
                 return fail(PYDSB_ERR_UNSUPPORTED, "model needs more shared memory per CTA than the device offers");
             }
     }
-    FeasFn fn = feas_for(g.ns);
+    int maxns = 1;
+    for (int b = 0; b < g.n_blocks; ++b) if (g.blk_ns[b] > maxns) maxns = g.blk_ns[b];
+    FeasFn fn = feas_for(maxns);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
     int bps = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, BLOCK, g.smem_bytes);
@@ -469,7 +498,9 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
 
     const long long max_ctas = (long long)m->num_sms * m->blocks_per_sm;
     const int grid = (int)(total < max_ctas ? total : max_ctas);
-    FeasFn fn = feas_for(img.ns);
+    int maxns = 1;
+    for (int b = 0; b < img.n_blocks; ++b) if (img.blk_ns[b] > maxns) maxns = img.blk_ns[b];
+    FeasFn fn = feas_for(maxns);
     // several models may share one template instantiation: (re)assert this model's smem size and
     // (re)load its point tape into the constant bank (stream ordered)
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
         double s_prev = 0.0;
         double M[N][N], inv[N], r[N];
         for (int it = 0;; ++it) {
-            run_point_tape<true>(base, img.n_pt);
+            run_point_tape<true>(base, 0, img.n_pt);
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj)
 #pragma unroll
@@ -148,16 +148,16 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
                     double lin = img.adot[jj + 1] * xs[n];
 #pragma unroll
                     for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
-                    r[jj * NS + n] = fma(h, PT_LD(img.f_o[n][jj]), -lin);
+                    r[jj * NS + n] = fma(h, PT_LD(img.blk_f_o[0][n][jj]), -lin);
 #pragma unroll
                     for (int kk = 0; kk < 3; ++kk)
 #pragma unroll
                         for (int m = 0; m < NS; ++m) {
                             const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
                             M[jj * NS + n][kk * NS + m] = a;
-                            if (kk == jj && ((img.j_mask >> (n * NS + m)) & 1u))
+                            if (kk == jj && ((img.blk_jmask[0] >> (n * NS + m)) & 1u))
                                 M[jj * NS + n][kk * NS + m] =
-                                    fma(-h, PT_LD(img.j_o[n * NS + m][jj]), a);
+                                    fma(-h, PT_LD(img.blk_j_o[0][n * NS + m][jj]), a);
                         }
                 }
             lu_factor<N>(M, inv);                       // at the last pass: factors at the converged point

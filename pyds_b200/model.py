@@ -52,7 +52,7 @@ class _Control:
 
 class DaeModel:
     def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-12, newton_max_it=25, predictor=False,
-                 quadratures="auto"):
+                 quadratures="auto", block_triangular=True):
         self.graph = T.Graph()
         self.d_names = list(d_names)
         self.p_names = list(p_names)
@@ -63,6 +63,9 @@ class DaeModel:
         # "auto": every state that appears in no right-hand side becomes a quadrature (exact); or an explicit
         # list of state names, e.g. ["u"] keeps cC in the Newton system (the 9-unknown form of SURVEY.md A.3)
         self.quadratures = quadratures
+        # solve the strongly connected components of the state dependency graph one after the other
+        # (A -> B -> C kinetics: cA alone, then cB, which is linear given cA) instead of one coupled system
+        self.block_triangular = bool(block_triangular)
         self.states: list[_State] = []
         self.controls: list[_Control] = []
         self.constraints = []          # (name, Expr (<= 0 feasible), bigM)
@@ -206,16 +209,37 @@ class DaeModel:
             for n in T.topo_order([e]):
                 if n.op in ("ctrl", "x"):
                     raise ValueError("constraints may use end-point values m.end(state) and parameters only")
-        # dfq/dx lets the kernel correct the quadrature integrands for the last Newton update instead of
-        # re-running the point tape at the converged state (exact for integrands linear in the states)
-        roots = {"x0": x0, "q0": q0, "z": z_exprs, "f": f, "J": J, "fq": fq, "g": gk,
-                 "fqx": [g.diff(fq[q], g.x(c)) for q in range(nq) for c in range(ns)]}
-        # program 1 ("sens") adds what forward control sensitivities need: df/dz, dfq/dz, dg/dxe, dg/dqe
-        roots_s = dict(roots)
-        roots_s["fz"] = [g.diff(f[r], g.ctrl(k)) for r in range(ns) for k in range(nce)]
-        roots_s["fqz"] = [g.diff(fq[q], g.ctrl(k)) for q in range(nq) for k in range(nce)]
-        roots_s["gx"] = [g.diff(gk[k], g.xe(c)) for k in range(ng) for c in range(ns)]
-        roots_s["gq"] = [g.diff(gk[k], g.qe(q)) for k in range(ng) for q in range(nq)]
+        # ---- blocks of the state solve: strongly connected components, dependencies first ----------------
+        dep = [[c for c in range(ns) if not J[r * ns + c].is_const(0.0)] for r in range(ns)]
+        if self.block_triangular:
+            blocks = _tarjan_scc(dep)
+        else:
+            blocks = [list(range(ns))]
+        for blk in blocks:
+            if len(blk) > 3:
+                raise ValueError(f"a block of {len(blk)} mutually coupled dynamic states exceeds the kernel's limit of 3")
+        roots = {"x0": x0, "q0": q0, "z": z_exprs, "g": gk, "fq": fq}
+        groups = []
+        blk_linear = []
+        for b, blk in enumerate(blocks):
+            roots[f"f{b}"] = [f[i] for i in blk]
+            roots[f"J{b}"] = [J[r * ns + c] for r in blk for c in blk]
+            groups.append((f"pt{b}", [f"f{b}", f"J{b}"]))
+            # linear block: its Jacobian does not depend on its own states -> Newton is exact in one step
+            own = {("x", i) for i in blk}
+            lin = all(not any((n.op, n.value) in own for n in T.topo_order([e])) for e in roots[f"J{b}"])
+            blk_linear.append(1 if lin else 0)
+        groups.append(("ptq", ["fq"]))
+        # program 1 ("sens"): one coupled block with everything forward control sensitivities need:
+        # df/dz, dfq/dx, dfq/dz in the point tape, dg/dxe, dg/dqe after the g tape
+        all_blk = list(range(ns))
+        roots_s = {"x0": x0, "q0": q0, "z": z_exprs, "g": gk, "fq": fq, "f0": f, "J0": J,
+                   "fqx": [g.diff(fq[q], g.x(c)) for q in range(nq) for c in range(ns)],
+                   "fz": [g.diff(f[r], g.ctrl(k)) for r in range(ns) for k in range(nce)],
+                   "fqz": [g.diff(fq[q], g.ctrl(k)) for q in range(nq) for k in range(nce)],
+                   "gx": [g.diff(gk[k], g.xe(c)) for k in range(ng) for c in range(ns)],
+                   "gq": [g.diff(gk[k], g.qe(q)) for k in range(ng) for q in range(nq)]}
+        groups_s = [("pt0", ["f0", "J0", "fq", "fqx", "fz", "fqz"])]
         tau, adot, bw = radau_tables(self.ncp)
         secs = []
 
@@ -227,15 +251,30 @@ class DaeModel:
             return low.refs[name] if n else [T.REF_NONE]
 
         lows = []
-        for prog, rts in enumerate((roots, roots_s)):
-            low = T.lower(g, n_param=self.n_param, n_ctrl_elem=nce, ns=ns, nq=nq, roots=rts, ncp=self.ncp)
+        blk_flops = []
+        programs = [(roots, groups, blocks, blk_linear)]
+        if ns <= 3:          # the sensitivity program is one coupled block: only for <= 3 dynamic states
+            programs.append((roots_s, groups_s, [all_blk], [0]))
+        for prog, (rts, grp, blks, lin) in enumerate(programs):
+            low = T.lower(g, n_param=self.n_param, n_ctrl_elem=nce, ns=ns, nq=nq, roots=rts, pt_groups=grp, ncp=self.ncp)
             lows.append(low)
             lay = low.layout
             if prog:
                 sec("PSEP", "u32", [prog])
+            tape_names = [name for name, _ in grp]
+            pt_code = np.concatenate([low.code[n] for n in tape_names]) if tape_names else np.zeros(0, np.uint64)
+            blkt = [len(low.code[f"pt{b}"]) for b in range(len(blks))] + [len(low.code["ptq"]) if "ptq" in low.code else 0]
+            blks_tab = []
+            flops = []
+            for b, blk in enumerate(blks):
+                blks_tab += [len(blk), lin[b]] + list(blk) + [0] * (3 - len(blk))
+                n_b = len(blk) * self.ncp
+                flops.append(low.stats["flops"][f"pt{b}"] * self.ncp + 2 * n_b * (self.ncp + 1) + (2 * n_b ** 3) // 3 + 2 * n_b * n_b)
+            if not prog:
+                blk_flops = flops
             sec("HEAD", "u32", [ns, nq, ng, len(self.d_names), len(self.p_names), nz, self.nfe, self.ncp, nce,
                                 lay.n_units, lay.ctrl_slot, lay.xe_slot, lay.qe_slot, lay.x_slot, self.newton_max_it,
-                                lay.j_mask, lay.fq_state_dep, 1 if self.predictor else 0])
+                                0, lay.fq_state_dep, 1 if self.predictor else 0, len(blks)])
             sec("RPAR", "u16", lay.param_slots)
             sec("DBLS", "f64", [self.newton_rtol])
             sec("CNST", "f64", low.consts if len(low.consts) else [0.0])
@@ -247,18 +286,21 @@ class DaeModel:
             sec("ZFIX", "u16", z_fixed if nz else [0])
             sec("TPRO", "u64", low.code["pro"])
             sec("TELM", "u64", low.code["elem"])
-            sec("TPNT", "u64", low.code["pt"])
+            sec("TPNT", "u64", pt_code)
             sec("TGEE", "u64", low.code["g"])
+            sec("BLKS", "u16", blks_tab)
+            sec("BLKT", "u32", blkt)
+            sec("BLKF", "u32", flops)
             sec("RX0_", "u16", low.refs["x0"])
             sec("RQ0_", "u16", tab(low, "q0", nq))
             sec("RZ__", "u16", tab(low, "z", nz))
-            sec("RF__", "u16", low.refs["f"])
-            sec("RJ__", "u16", low.refs["J"])
+            sec("RF__", "u16", np.concatenate([low.refs[f"f{b}"] for b in range(len(blks))]))
+            sec("RJ__", "u16", np.concatenate([low.refs[f"J{b}"] for b in range(len(blks))]))
             sec("RFQ_", "u16", tab(low, "fq", nq))
             sec("RG__", "u16", low.refs["g"])
             sec("CMAP", "u16", cmap)
-            sec("RFQX", "u16", tab(low, "fqx", nq * ns))
             if prog:
+                sec("RFQX", "u16", tab(low, "fqx", nq * ns))
                 sec("RFZ_", "u16", tab(low, "fz", ns * nce))
                 sec("RFQZ", "u16", tab(low, "fqz", nq * nce))
                 sec("RGX_", "u16", tab(low, "gx", ng * ns))
@@ -272,11 +314,13 @@ class DaeModel:
             pad = (-len(raw)) % 8
             blob += struct.pack("<4sIII", tag.encode(), _DT[dtype], arr.size, 0)
             blob += raw + b"\0" * pad
+        dyn_names = [self.states[i].name for i in dyn]
         info = LoweredModel(
             blob=bytes(blob), ns=ns, nq=nq, ng=ng, nz=nz, d_dim=len(self.d_names), p_dim=len(self.p_names),
             nfe=self.nfe, ncp=self.ncp, n_units=lay.n_units, tapes=low, dyn_states=[self.states[i].name for i in dyn],
             quad_states=[self.states[i].name for i in quad], z_lo=np.asarray(z_lo), z_hi=np.asarray(z_hi),
-            tapes_sens=lows[1], z_init=z_exprs,
+            tapes_sens=lows[1] if len(lows) > 1 else None, z_init=z_exprs, blocks=[[dyn_names[i] for i in blk] for blk in blocks], block_linear=blk_linear,
+            block_flops=blk_flops,
             z_fixed=np.asarray(z_fixed, dtype=bool), big_m=np.asarray([m for _, _, m in self.constraints]),
             constraint_names=[n for n, _, _ in self.constraints], cmap=cmap, newton_rtol=self.newton_rtol,
             newton_max_it=self.newton_max_it)
@@ -298,6 +342,9 @@ class LoweredModel:
     tapes: T.LoweredTapes
     tapes_sens: T.LoweredTapes
     z_init: list
+    blocks: list
+    block_linear: list
+    block_flops: list
     dyn_states: list
     quad_states: list
     z_lo: np.ndarray
@@ -309,18 +356,52 @@ class LoweredModel:
     newton_rtol: float
     newton_max_it: int
 
-    def flops_per_newton_iteration(self):
-        """Algorithmic flops of one Newton iteration on one finite element:
+    def flops_per_newton_iteration(self, block=0):
+        """Algorithmic flops of one Newton iteration of one block on one finite element:
         point tape (x ncp) + linear collocation residual + dense LU + two triangular solves."""
-        n = self.ns * self.ncp
-        tape = self.tapes.stats["flops"]["pt"] * self.ncp
-        resid = 2 * n * (self.ncp + 1)
-        return tape + resid + (2 * n ** 3) // 3 + 2 * n * n
+        return self.block_flops[block]
 
-    def flops_per_evaluation(self, mean_newton_iters_per_element):
+    def fixed_flops_per_evaluation(self):
+        """Tape work that does not depend on the Newton iteration count."""
         fl = self.tapes.stats["flops"]
-        return (fl["pro"] + fl["g"] + self.nfe * (fl["elem"] + mean_newton_iters_per_element *
-                                                   self.flops_per_newton_iteration()))
+        return fl["pro"] + fl["g"] + self.nfe * (fl["elem"] + self.ncp * fl.get("ptq", 0))
+
+    def flops_per_evaluation(self, mean_newton_iters_per_element, newton_flops_per_eval=None):
+        """F_alg per (d,theta) evaluation.  With block-triangular solves pass the measured
+        ``newton_flops_per_eval`` (device counter: sum over blocks of iterations x block flops)."""
+        if newton_flops_per_eval is None:
+            newton_flops_per_eval = self.nfe * mean_newton_iters_per_element * sum(self.block_flops)
+        return self.fixed_flops_per_evaluation() + newton_flops_per_eval
+
+
+def _tarjan_scc(dep):
+    """Strongly connected components of ``i -> dep[i]``, emitted dependencies first."""
+    n = len(dep)
+    index, low, on, stack, out = [None] * n, [0] * n, [False] * n, [], []
+    counter = [0]
+
+    def visit(v):
+        index[v] = low[v] = counter[0]; counter[0] += 1
+        stack.append(v); on[v] = True
+        for w in dep[v]:
+            if w == v:
+                continue
+            if index[w] is None:
+                visit(w); low[v] = min(low[v], low[w])
+            elif on[w]:
+                low[v] = min(low[v], index[w])
+        if low[v] == index[v]:
+            comp = []
+            while True:
+                w = stack.pop(); on[w] = False; comp.append(w)
+                if w == v:
+                    break
+            out.append(sorted(comp))
+
+    for v in range(n):
+        if index[v] is None:
+            visit(v)
+    return out
 
 
 def parse_blob(blob: bytes):

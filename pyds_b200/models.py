@@ -24,6 +24,7 @@ def kinetics(variant: str = "twostage", nfe: int = 8, f_init=0.0, dense9: bool =
     formulation SURVEY.md A.3/A.5 counts flops for) instead of treating it as a quadrature."""
     if dense9:
         kw["quadratures"] = ["u"]
+        kw["block_triangular"] = False
     d_names = {"twostage": ["t_f", "T"], "design4": ["t_f", "T", "cA0", "Fbar"],
                "design6": ["t_f", "T", "cA0", "Fbar", "pB", "pA"]}[variant]
     m = DaeModel(d_names, THETA_NAMES, nfe=nfe, ncp=3, **kw)

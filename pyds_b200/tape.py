@@ -424,28 +424,34 @@ class _SlotPool:
         self.free.insert(0, s)
 
 
-def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int = 3) -> LoweredTapes:
-    """Lower root expressions to the four tapes.
+def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, pt_groups=None, ncp: int = 3) -> LoweredTapes:
+    """Lower root expressions to tapes.
 
-    ``roots`` maps a table name to a list of :class:`Expr` (or ``None`` for "absent"), e.g.
-    ``{"x0": [...ns], "q0": [...nq], "z": [...nz], "f": [...ns], "J": [...ns*ns], "fq": [...nq], "g": [...ng]}``.
-    A table may only contain nodes up to the level its consumer can see: x0/q0/z <= PARAM,
-    f/J/fq <= STATE, g <= END.
+    ``roots`` maps a table name to a list of :class:`Expr` (``None`` = absent).  Tables read by the kernel
+    through reference tables: ``x0``, ``q0``, ``z`` (<= PARAM level), ``g``, ``gx``, ``gq`` (<= END level) and the
+    point-level tables named in ``pt_groups``.
+
+    ``pt_groups`` is an ordered list ``[(tape name, [table names]), ...]``: every group becomes one point tape
+    holding the STATE-level nodes its tables need.  The kernel runs the groups one after the other inside a
+    finite element (one group per block of the block-triangular state solve, then the quadrature integrands),
+    so a STATE-level node needed by two groups is *recomputed* in each -- the states it depends on have moved
+    in between -- and all groups share the same temporaries.  Default: one tape ``"pt"`` with ``f``, ``J``, ``fq``.
 
     Register-file layout (one unit = one double per thread)::
 
-        [ persistent narrow: live parameters | ctrl | xe | qe | constants used by the point tape |
+        [ persistent narrow: live parameters | ctrl | xe | qe | constants used by point tapes |
           pro / elem values consumed by later tapes ]
-        [ wide: X | F | J | FQ | point-tape temporaries ]              (3 units per value)
+        [ wide: X | point-tape outputs and temporaries (shared by all point tapes) ]     (3 units per value)
 
-    Short-lived values -- parameters read only by the prologue, prologue temporaries, g-tape
-    temporaries -- are overlaid on wide units that are dead while they live (X and the point
-    temporaries before the first element; everything wide after the last element), which keeps
-    the file small enough for 4 CTAs per SM.
+    Short-lived values -- parameters read only by the prologue, prologue temporaries, g-tape temporaries --
+    are overlaid on wide units that are dead while they live.
     """
     if ncp != 3:
-        raise NotImplementedError("the kernel evaluates the point tape 3-wide (ncp = 3)")
-    dense_names = ("f", "J", "fq", "fz", "fqx", "fqz", "gx", "gq")      # read through per-thread slots
+        raise NotImplementedError("the kernel evaluates the point tapes 3-wide (ncp = 3)")
+    if pt_groups is None:
+        pt_groups = [("pt", [t for t in ("f", "J", "fq") if t in roots])]
+    slot_tables = set(t for _, tabs in pt_groups for t in tabs) | {"gx", "gq"}      # read through per-thread slots
+    pt_names = [name for name, _ in pt_groups]
     all_roots = [e for lst in roots.values() for e in lst if e is not None]
     order = topo_order(all_roots)
 
@@ -487,59 +493,69 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
             fused_into[m.id] = n.id
             fma_form[n.id] = (opn, m.args[0], m.args[1], other)
 
-    level_tape = {LEVEL_PARAM: "pro", LEVEL_CTRL: "elem", LEVEL_STATE: "pt", LEVEL_END: "g"}
-    sched = {"pro": [], "elem": [], "pt": [], "g": []}
-    for n in order:
-        if n.level == LEVEL_CONST or not n.args or n.id in fused_into:
-            continue
-        sched[level_tape[n.level]].append(n)
-
     def eff_args(n):
         return fma_form[n.id][1:] if n.id in fma_form else n.args
 
-    # ---- outputs of the point tape (f, J = df/dx, fq) are read by the compiled Newton code through
-    # (offset, stride) tables, so a root may live in any per-thread slot: wide (state dependent) or
-    # narrow (parameter / control level).  Non-zero constant roots get a per-thread slot too.
+    def reachable(root_list, level):
+        """Nodes of ``level`` needed by ``root_list`` (dependencies first), fused muls folded away."""
+        seen, out = set(), []
+        stack = [(e, 0) for e in reversed([e for e in root_list if e is not None])]
+        while stack:
+            n, i = stack.pop()
+            if i == 0:
+                if n.id in seen or not n.args or n.level != level:
+                    continue
+                seen.add(n.id)
+            args = eff_args(n)
+            if i < len(args):
+                stack.append((n, i + 1))
+                stack.append((args[i], 0))
+            else:
+                out.append(n)
+        return out
+
+    sched = {"pro": [], "elem": [], "g": []}
+    level_tape = {LEVEL_PARAM: "pro", LEVEL_CTRL: "elem", LEVEL_END: "g"}
+    for n in order:
+        if n.level in level_tape and n.args and n.id not in fused_into:
+            sched[level_tape[n.level]].append(n)
+    for name, tabs in pt_groups:
+        sched[name] = reachable([e for t in tabs for e in roots.get(t, [])], LEVEL_STATE)
+
     lay = TapeLayout(n_param=n_param, n_ctrl_elem=n_ctrl_elem, ns=ns, nq=nq)
-    extra = {"pro": [], "elem": [], "pt": []}    # (opname, dst, src node) appended after the tape body
+    extra = {"pro": []}                          # constants -> per-thread slots, appended to the prologue
     const_roots = []
-    for tname in dense_names:
-        for i, e in enumerate(roots.get(tname, [])):
-            if e is None or e.is_const(0.0):
-                continue
-            if tname == "J":
-                lay.j_mask |= 1 << i
-            if tname == "fq" and e.level == LEVEL_STATE:
-                lay.fq_state_dep = 1
-            if e.op == "const":
+    for tname in slot_tables:
+        for e in roots.get(tname, []):
+            if e is not None and e.op == "const" and not e.is_const(0.0):
                 const_roots.append(e)
+    for e in roots.get("fq", []):
+        if e is not None and e.level == LEVEL_STATE:
+            lay.fq_state_dep = 1
+    for i, e in enumerate(roots.get("J", [])):
+        if e is not None and not e.is_const(0.0):
+            lay.j_mask |= 1 << i
 
     # ---- who reads what, and where ------------------------------------------------------------------
-    tape_of = {n.id: name for name, lst in sched.items() for n in lst}
-    read_in = {}                                  # node id -> set of tape names that read it
+    home = {}                                     # node id -> set of tapes that compute it
+    read_in = {}                                  # node id -> set of tapes that read it
     for name, lst in sched.items():
         for n in lst:
+            home.setdefault(n.id, set()).add(name)
             for a in eff_args(n):
                 read_in.setdefault(a.id, set()).add(name)
-    for name, lst in extra.items():
-        for _, _, src in lst:
-            read_in.setdefault(src.id, set()).add(name)
-    table_read = set()                            # read by the kernel itself through a reference table
-    for tname, lst in roots.items():
-        for e in lst:
-            if e is not None:
-                table_read.add(e.id)
+    table_read = {e.id for lst in roots.values() for e in lst if e is not None}
 
     def persistent(n):
-        """Must keep its value beyond the tape that produces it (parameters: beyond the prologue)."""
+        """A narrow value that must outlive the tape producing it (parameters: the prologue)."""
         if n.id in table_read:
             return True
-        home = tape_of.get(n.id, "pro")           # leaves of parameter level behave like pro values
-        return bool(read_in.get(n.id, set()) - {home})
+        h = home.get(n.id, {"pro"})               # parameter leaves behave like prologue values
+        return bool(read_in.get(n.id, set()) - h)
 
     # ---- persistent narrow region -------------------------------------------------------------------
     cur = 0
-    slot_of = {}
+    slot_of = {}                                  # narrow tapes: node id -> slot
     params = [graph.param(i) for i in range(n_param)]
     lay.param_slots = [None] * n_param
     for i, pn in enumerate(params):
@@ -548,15 +564,13 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
     lay.ctrl_slot = cur; cur += n_ctrl_elem
     lay.xe_slot = cur; cur += ns
     lay.qe_slot = cur; cur += nq
-    # constants used as operands by the point tape get a per-thread slot (filled by the prologue) so
-    # that every operand of the hot tape is addressed the same way
     const_slot = {}
-    for a in [a for n in sched["pt"] for a in eff_args(n)] + const_roots:
+    for a in [a for name in pt_names for n in sched[name] for a in eff_args(n)] + const_roots:
         if a.op == "const":
             key = struct.pack("<d", a.value)
             if key not in const_slot:
                 const_slot[key] = cur; cur += 1
-                extra["pro"].append(("MOV", None, a))              # dst patched below
+                extra["pro"].append(a)
     for name in ("pro", "elem"):
         for n in sched[name]:
             if persistent(n) or name == "elem":
@@ -568,9 +582,7 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
 
     def leaf_ref(n, in_pt=False):
         if n.op == "const":
-            if in_pt:
-                return const_slot[struct.pack("<d", n.value)]
-            return cref(n.value)
+            return const_slot[struct.pack("<d", n.value)] if in_pt else cref(n.value)
         if n.op == "param": return lay.param_slots[n.value]
         if n.op == "ctrl": return lay.ctrl_slot + n.value
         if n.op == "xe": return lay.xe_slot + n.value
@@ -578,82 +590,85 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, ncp: int =
         if n.op == "x": return REF_WIDE | (lay.x_slot + 3 * n.value)
         raise KeyError(n.op)
 
-    def assign(name, lst, pool, wide):
-        """Linear-scan assignment for the not-yet-placed nodes of one tape."""
+    def assign(lst, pool, wide, slots):
+        """Linear-scan assignment of the not-yet-placed nodes of one tape into ``slots``."""
         last_use = {}
         for pos, n in enumerate(lst):
             for a in eff_args(n):
                 last_use[a.id] = pos
-        for _, _, src in extra.get(name, []):             # trailing MOV/BC3 read their source at the end
-            last_use[src.id] = len(lst)
         release_at = {}
         for pos, n in enumerate(lst):
-            for s in release_at.pop(pos, []):
-                pool.give(s)
-            if n.id in slot_of:
+            for s_ in release_at.pop(pos, []):
+                pool.give(s_)
+            if n.id in slots:
                 continue
-            s = pool.take()
-            slot_of[n.id] = (REF_WIDE | s) if wide else s
+            s_ = pool.take()
+            slots[n.id] = (REF_WIDE | s_) if wide else s_
             if n.id not in table_read:                     # values the kernel reads afterwards stay put
-                release_at.setdefault(last_use.get(n.id, pos) + 1, []).append(s)
+                release_at.setdefault(last_use.get(n.id, pos) + 1, []).append(s_)
 
-    pt_pool = _SlotPool(3, grow_from=cur)
-    assign("pt", sched["pt"], pt_pool, True)
-    cur = max(cur, pt_pool.high)
+    pt_slots = {}
+    wide_end = cur
+    for name in pt_names:                                   # every point tape starts from the same base
+        pool = _SlotPool(3, grow_from=wide_fixed_end)
+        pt_slots[name] = {}
+        assign(sched[name], pool, True, pt_slots[name])
+        wide_end = max(wide_end, pool.high)
+    cur = wide_end
     pt_temp_units = list(range(wide_fixed_end, cur))
 
-    # scratch for the prologue: X units and point temporaries (dead until the first element starts)
     x_units = list(range(lay.x_slot, lay.x_slot + 3 * ns))
     pro_pool = _SlotPool(1, free=x_units + pt_temp_units, grow_from=cur)
-    # parameters that only the prologue reads are loaded straight into scratch units
     for i, pn in enumerate(params):
         if lay.param_slots[i] is None:
             lay.param_slots[i] = pro_pool.take()
-    assign("pro", sched["pro"], pro_pool, False)
+    # trailing constant moves read nothing but the pool; prologue temporaries may use the scratch
+    assign(sched["pro"], pro_pool, False, slot_of)
     cur = max(cur, pro_pool.high)
-    # scratch for the g tape: the whole wide region is dead after the last element
     g_pool = _SlotPool(1, free=list(range(lay.x_slot, cur)), grow_from=cur)
-    assign("g", sched["g"], g_pool, False)
+    assign(sched["g"], g_pool, False, slot_of)
     cur = max(cur, g_pool.high)
     if cur - 1 > REF_MASK:
         raise ValueError("register file overflow (4096 slots)")
     lay.n_units = cur
 
     # ---- emit ------------------------------------------------------------------------------------------
-    def ref(n, in_pt=False):
+    def ref(n, tape=None):
         if not n.args:
-            return leaf_ref(n, in_pt)
+            return leaf_ref(n, tape in pt_slots)
+        if tape in pt_slots and n.level == LEVEL_STATE:
+            return pt_slots[tape][n.id]
         return slot_of[n.id]
 
     code = {}
-    for name in ("pro", "elem", "pt", "g"):
-        in_pt = name == "pt"
+    for name in ["pro", "elem", "g"] + pt_names:
         words = []
         for n in sched[name]:
-            dst = slot_of[n.id]
+            dst = ref(n, name)
             if n.id in fma_form:
                 opn, a, b, c = fma_form[n.id]
-                words.append(encode(opn, dst, ref(a, in_pt), ref(b, in_pt), ref(c, in_pt)))
+                words.append(encode(opn, dst, ref(a, name), ref(b, name), ref(c, name)))
             elif n.op in _BINOPS:
-                words.append(encode(_BINOPS[n.op], dst, ref(n.args[0], in_pt), ref(n.args[1], in_pt)))
+                words.append(encode(_BINOPS[n.op], dst, ref(n.args[0], name), ref(n.args[1], name)))
             elif n.op in _UNOPS:
-                words.append(encode(_UNOPS[n.op], dst, ref(n.args[0], in_pt)))
+                words.append(encode(_UNOPS[n.op], dst, ref(n.args[0], name)))
             else:
                 raise NotImplementedError(n.op)
-        for opn, rel, src in extra.get(name, []):                   # constants -> per-thread slots
+        for src in extra.get(name, []):                              # constants -> per-thread slots
             words.append(encode("MOV", const_slot[struct.pack("<d", src.value)], cref(src.value)))
         code[name] = np.asarray(words, dtype=np.uint64)
 
+    table_tape = {t: name for name, tabs in pt_groups for t in tabs}
     ref_tables = {}
     for name, lst in roots.items():
         out = []
         for e in lst:
             if e is None or e.is_const(0.0):
                 out.append(REF_NONE)
-            elif e.op == "const" and name in dense_names:
+            elif e.op == "const" and name in slot_tables:
                 out.append(const_slot[struct.pack("<d", e.value)])
             else:
-                out.append(ref(e))
+                out.append(ref(e, table_tape.get(name)))
         ref_tables[name] = np.asarray(out, dtype=np.uint16)
 
     stats = {k: int(len(v)) for k, v in code.items()}

@@ -80,5 +80,24 @@ def test_unsupported_shapes_fail_loudly():
     for i in range(4):
         m.ode(xs[i], -xs[(i + 1) % 4] * m.p["b"])          # 4 coupled dynamic states
     m.constraint("c", m.end(xs[0]) - m.d["a"], 1.0)
-    with pytest.raises(capi.PydsbError, match="1..3 dynamic states"):
-        capi.Engine(m.lower().blob, 0)
+    with pytest.raises(ValueError, match="limit of 3"):
+        m.lower()
+    # five states in blocks of (2, 1, 2) are fine: the limit is per coupled block
+    m2 = DaeModel(["a"], ["b"], nfe=4)
+    ys = [m2.state(f"y{i}", 1.0 + 0.1 * i) for i in range(5)]
+    b_ = m2.p["b"]
+    m2.ode(ys[0], -b_ * ys[0] + 0.3 * ys[1])
+    m2.ode(ys[1], 0.2 * ys[0] - ys[1] * ys[1])
+    m2.ode(ys[2], ys[0] - 0.5 * ys[2])
+    m2.ode(ys[3], ys[2] * ys[4] - ys[3])
+    m2.ode(ys[4], -ys[3] * 0.1 - 0.7 * ys[4] + ys[1])
+    m2.constraint("c", m2.end(ys[3]) + m2.end(ys[4]) - m2.d["a"], 2.0)
+    lm2 = m2.lower()
+    assert sorted(len(b) for b in lm2.blocks) == [1, 2, 2]
+    eng = capi.Engine(lm2.blob, 0)
+    d = np.linspace(0.2, 1.5, 9)[:, None]
+    p = np.linspace(0.3, 1.2, 40)[:, None]
+    g, ind, P = eng.eval_host(d, p, None, want_g=True, want_ind=True)
+    r = tape_vm.TapeVM(lm2.blob).evaluate(d, p, tol=1e-13)
+    np.testing.assert_allclose(g, r["g"], rtol=1e-10, atol=1e-12)
+    assert eng.counters()["failed"] == 0

@@ -92,8 +92,16 @@ def test_kinetics_structure():
     np.testing.assert_array_equal(lm.z_hi, 2.5)
     np.testing.assert_array_equal(lm.big_m, [1e2, 1e7])
     sec = parse_blob(lm.blob)
-    assert sec["TPNT"].size == lm.tapes.stats["pt"] <= 8
-    assert lm.tapes.layout.j_mask == 0b1101                      # dfA/dcA, dfB/dcA, dfB/dcB
+    # block-triangular solve: cA alone (nonlinear), then cB (linear given cA), then the quadrature integrands
+    assert lm.blocks == [["cA"], ["cB"]] and lm.block_linear == [0, 1]
+    st = lm.tapes.stats
+    assert sec["TPNT"].size == st["pt0"] + st["pt1"] + st["ptq"] <= 8
+    assert list(sec["BLKT"]) == [st["pt0"], st["pt1"], st["ptq"]]
+    assert list(sec["BLKS"]) == [1, 0, 0, 0, 0, 1, 1, 1, 0, 0]
+    # the coupled single-block form (what the sensitivity program and dense9 use)
+    lmc = models.kinetics("twostage", block_triangular=False).lower()
+    assert lmc.blocks == [["cA", "cB"]]
+    assert [int(r) == T.REF_NONE for r in parse_blob(lmc.blob)["RJ__"]] == [False, True, False, False]   # dfA/dcB == 0
     # every opcode the kernel may meet is known on both sides
     for name in ("TPRO", "TELM", "TPNT", "TGEE"):
         for w in sec[name]:

@@ -58,7 +58,7 @@ for n_d, n_t in ((1000, 10000), (10000, 10000)):
     ms = e0.elapsed_time(e1)
     c = eng.counters()
     I = c["newton_iters"] / c["scenarios"] / lm.nfe
-    fl = lm.flops_per_evaluation(I)
+    fl = lm.flops_per_evaluation(I, newton_flops_per_eval=c['newton_flops'] / c['scenarios'])
     print(f"C3-shape {n_d}x{n_t}: {ms:.2f} ms  {n_d * n_t / ms * 1e3:.3e} evals/s  I={I:.2f}/elem  F_alg={fl:.0f} flop/eval "
           f"-> {n_d * n_t * fl / ms / 1e9:.2f} TFLOP/s ({n_d * n_t * fl / ms / 1e9 / tf * 100:.1f}% of DFMA peak)  counters={c}")
     out[f"c3_{n_d}"] = dict(ms=ms, evals_per_s=n_d * n_t / ms * 1e3, I=I, flops=fl)
