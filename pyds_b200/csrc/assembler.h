@@ -1,0 +1,217 @@
+// Host side of the feasibility interpreter: assemble the lowered tapes of a model blob (pro / elem /
+// point tapes per block / quadrature tape / g -- pyds_b200/tape.py) into the ONE pre-decoded program
+// feas_kernel runs per scenario (layout and opcodes: feas_kernel.cuh).  Every operand becomes a byte
+// offset from the thread's base in the shared-memory register file; every point op is specialised on
+// its operand pattern (narrow / wide), commutative operands are ordered narrow first.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "feas_kernel.cuh"
+
+namespace pydsb {
+
+struct AsmInput {
+    const uint64_t *pro, *elem, *g, *pt;       // 64-bit tape words (tape_vm.cuh encoding)
+    int n_pro, n_elem, n_g;
+    int n_blocks;
+    const int *blk_npt, *blk_ns, *blk_lin;
+    const unsigned* blk_flops;
+    int q_npt;
+    int nce, ctrl_slot, nq, qe_slot, n_units;
+    const uint16_t* fq_refs;                   // [nq] reference of every quadrature integrand
+    const ExecImage* img;                      // resolved per-block offsets: blk_x_o, blk_f_o, blk_j_o, blk_jmask
+};
+
+class Assembler {
+public:
+    std::vector<uint32_t> words;               // 8 per instruction
+    std::string err;
+
+    int pc() const { return (int)(words.size() / 4); }      // uint4 index of the next instruction
+
+    bool assemble(const AsmInput& in)
+    {
+        in_ = &in;
+        for (int i = 0; i < in.n_pro; ++i)
+            if (!scalar_op(in.pro[i])) return false;
+        emit(X_INIT);
+        const int l_elem = pc();
+        for (int c = 0; c < in.nce; ++c) emit(X_LDCTRL, (uint32_t)(in.ctrl_slot + c) * US, (uint32_t)c);
+        for (int i = 0; i < in.n_elem; ++i)
+            if (!scalar_op(in.elem[i])) return false;
+        int pos = 0;
+        for (int b = 0; b < in.n_blocks; ++b) {
+            const int nsb = in.blk_ns[b];
+            if (nsb < 1 || nsb > 3) return fail("block size out of range");
+            static const uint32_t nb_code[3] = {X_NB1, X_NB2, X_NB3}, ns_code[3] = {X_NS1, X_NS2, X_NS3};
+            const ExecImage& g = *in.img;
+            emit(nb_code[nsb - 1], g.blk_x_o[b][0][0], nsb > 1 ? g.blk_x_o[b][1][0] : 0u, nsb > 2 ? g.blk_x_o[b][2][0] : 0u);
+            const int l_blk = pc();
+            for (int i = 0; i < in.blk_npt[b]; ++i)
+                if (!point_op(in.pt[pos++])) return false;
+            // NS: first uint4, then the operand table x_o[k] | f_o[k][3] | j_o[k*k][3], padded to whole uint4s
+            const uint32_t head[4] = {ns_code[nsb - 1], (uint32_t)l_blk, in.blk_flops[b],
+                                      (g.blk_jmask[b] & 0xFFFFu) | ((in.blk_lin[b] ? 1u : 0u) << 16)};
+            words.insert(words.end(), head, head + 4);
+            std::vector<uint32_t> tab;
+            for (int n = 0; n < nsb; ++n) tab.push_back(g.blk_x_o[b][n][0]);
+            for (int n = 0; n < nsb; ++n)
+                for (int p3 = 0; p3 < 3; ++p3) tab.push_back(g.blk_f_o[b][n][p3]);
+            for (int i = 0; i < nsb * nsb; ++i)
+                for (int p3 = 0; p3 < 3; ++p3) tab.push_back(g.blk_j_o[b][i][p3]);
+            tab.resize((size_t)(ns_length(nsb) - 1) * 4, 0u);
+            words.insert(words.end(), tab.begin(), tab.end());
+        }
+        for (int i = 0; i < in.q_npt; ++i)
+            if (!point_op(in.pt[pos++])) return false;
+        for (int q = 0; q < in.nq; ++q) {
+            const unsigned r = in.fq_refs[q];
+            if (r == REF_NONE) continue;
+            if (r & REF_CONST) return fail("constant reference in the quadrature table");
+            const uint32_t o = slot_off(r), st = (r & REF_WIDE) ? US : 0u;
+            if (!check_slot(r)) return false;
+            emit(X_QACC, (uint32_t)(in.qe_slot + q) * US, o, o + st, o + 2 * st);
+        }
+        emit(X_ELEM_END, (uint32_t)l_elem);
+        emit(X_XEND);
+        for (int i = 0; i < in.n_g; ++i)
+            if (!scalar_op(in.g[i])) return false;
+        emit(X_END);
+        if (pc() > 2 * MAX_PROG) return fail("program longer than the constant-bank window");
+        return true;
+    }
+
+private:
+    const AsmInput* in_ = nullptr;
+
+    bool fail(const std::string& m)
+    {
+        err = m;
+        return false;
+    }
+    void emit(uint32_t x, uint32_t y = 0, uint32_t z = 0, uint32_t w = 0, uint32_t x1 = 0, uint32_t y1 = 0, uint32_t z1 = 0)
+    {
+        const uint32_t v[8] = {x, y, z, w, x1, y1, z1, 0};
+        words.insert(words.end(), v, v + 8);
+    }
+    static uint32_t slot_off(unsigned ref) { return (ref & REF_MASK) * US; }
+    bool check_slot(unsigned ref)
+    {
+        if ((int)(ref & REF_MASK) + ((ref & REF_WIDE) ? 2 : 0) >= in_->n_units) return fail("slot out of range");
+        return true;
+    }
+    static int arity(unsigned op)
+    {
+        if (op == OP_FMA || op == OP_FMS || op == OP_FNMA) return 3;
+        if (op == OP_ADD || op == OP_SUB || op == OP_MUL || op == OP_DIV || op == OP_POW || op == OP_MIN || op == OP_MAX)
+            return 2;
+        return 1;
+    }
+    static void split(uint64_t w, unsigned& op, unsigned (&refs)[4])
+    {
+        op = (unsigned)(w & 0xFF);
+        refs[0] = (unsigned)(w >> 8) & 0x3FFFu;
+        refs[1] = (unsigned)(w >> 22) & 0x3FFFu;
+        refs[2] = (unsigned)(w >> 36) & 0x3FFFu;
+        refs[3] = (unsigned)(w >> 50) & 0x3FFFu;
+    }
+    static bool is_cold(unsigned op)
+    {
+        return op == OP_EXP || op == OP_LOG || op == OP_SQRT || op == OP_SIN || op == OP_COS || op == OP_TANH || op == OP_POW;
+    }
+
+    // pro / elem / g tapes: one value per scenario; operands are slots or constant-pool entries
+    bool scalar_op(uint64_t w)
+    {
+        unsigned op, refs[4];
+        split(w, op, refs);
+        if (op >= OP_BC3) return fail("unknown opcode in a scalar tape");
+        static const int map[OP_BC3] = {X_MOV1, X_NEG1, X_ADD1, X_SUB1, X_MUL1, X_DIV1, X_FMA1, X_FMS1, X_FNMA1, X_SQR1,
+                                        X_RCP1, X_COLD1, X_COLD1, X_COLD1, X_COLD1, X_COLD1, X_COLD1, X_COLD1, X_ABS1,
+                                        X_MIN1, X_MAX1};
+        const int n = arity(op);
+        if (refs[0] & REF_CONST) return fail("scalar tape writes a constant");
+        if (!check_slot(refs[0] & ~REF_WIDE)) return false;
+        uint32_t off[3] = {0, 0, 0}, flags = 0;
+        for (int k = 0; k < n; ++k) {
+            const unsigned r = refs[k + 1];
+            if (r & REF_CONST) {
+                flags |= 1u << k;
+                off[k] = (r == REF_NONE) ? 0u : ((r & REF_MASK) + 1u) * 8u;      // relative to cpool - 1 (cpool[-1] = 0.0)
+            } else {
+                if (!check_slot(r & ~REF_WIDE)) return false;
+                off[k] = slot_off(r);
+            }
+        }
+        if (n == 1) {                                     // cold unary ops are dispatched as binary: b = a
+            off[1] = off[0];
+            if (flags & 1u) flags |= 2u;
+        }
+        emit((uint32_t)map[op], slot_off(refs[0]), off[0], off[1], off[2], flags, is_cold(op) ? op : 0u);
+        return true;
+    }
+
+    // point tapes: three collocation points per instruction; operands are narrow or wide slots
+    bool point_op(uint64_t w)
+    {
+        unsigned op, refs[4];
+        split(w, op, refs);
+        if (op >= OP_BC3) return fail("opcode not allowed in the point tape");
+        const int n = arity(op);
+        for (int k = 0; k <= n; ++k) {
+            if (refs[k] & REF_CONST) return fail("constant operand in the point tape");
+            if (!check_slot(refs[k])) return false;
+        }
+        if (!(refs[0] & REF_WIDE)) return fail("point tape writes a narrow slot");
+        unsigned a = refs[1], b = refs[2], c = refs[3];
+        auto wide = [](unsigned r) { return (r & REF_WIDE) != 0; };
+        const uint32_t d = slot_off(refs[0]);
+        if (is_cold(op)) {
+            if (n == 1) b = a;
+            emit(X_COLD_W, d, slot_off(a), slot_off(b), 0u, (wide(a) ? 1u : 0u) | (wide(b) ? 2u : 0u), op);
+            return true;
+        }
+        switch (op) {
+        case OP_FMA: case OP_FMS: case OP_FNMA: {
+            if (wide(a) && !wide(b)) { const unsigned t = a; a = b; b = t; }
+            if (!wide(b)) return fail("point-level product of two narrow values (should have been hoisted)");
+            static const uint32_t tab[3][4] = {{X_FMA_NWN, X_FMA_NWW, X_FMA_WWN, X_FMA_WWW},
+                                               {X_FMS_NWN, X_FMS_NWW, X_FMS_WWN, X_FMS_WWW},
+                                               {X_FNMA_NWN, X_FNMA_NWW, X_FNMA_WWN, X_FNMA_WWW}};
+            const int fam = op == OP_FMA ? 0 : (op == OP_FMS ? 1 : 2);
+            emit(tab[fam][(wide(a) ? 2 : 0) + (wide(c) ? 1 : 0)], d, slot_off(a), slot_off(b), slot_off(c));
+            return true;
+        }
+        case OP_MUL: case OP_ADD: case OP_MIN: case OP_MAX: {
+            if (wide(a) && !wide(b)) { const unsigned t = a; a = b; b = t; }
+            if (!wide(b)) return fail("point-level binary op on two narrow values (should have been hoisted)");
+            static const uint32_t tab[4][2] = {{X_MUL_NW, X_MUL_WW}, {X_ADD_NW, X_ADD_WW}, {X_MIN_NW, X_MIN_WW}, {X_MAX_NW, X_MAX_WW}};
+            const int fam = op == OP_MUL ? 0 : (op == OP_ADD ? 1 : (op == OP_MIN ? 2 : 3));
+            emit(tab[fam][wide(a) ? 1 : 0], d, slot_off(a), slot_off(b));
+            return true;
+        }
+        case OP_SUB: case OP_DIV: {
+            if (!wide(a) && !wide(b)) return fail("point-level binary op on two narrow values (should have been hoisted)");
+            static const uint32_t tab[2][3] = {{X_SUB_NW, X_SUB_WN, X_SUB_WW}, {X_DIV_NW, X_DIV_WN, X_DIV_WW}};
+            emit(tab[op == OP_SUB ? 0 : 1][!wide(a) ? 0 : (!wide(b) ? 1 : 2)], d, slot_off(a), slot_off(b));
+            return true;
+        }
+        case OP_MOV:
+            emit(wide(a) ? X_MOV_W : X_BC_N, d, slot_off(a));
+            return true;
+        case OP_SQR: case OP_NEG: case OP_RCP: case OP_ABS: {
+            if (!wide(a)) return fail("point-level unary op on a narrow value (should have been hoisted)");
+            const uint32_t code = op == OP_SQR ? X_SQR_W : (op == OP_NEG ? X_NEG_W : (op == OP_RCP ? X_RCP_W : X_ABS_W));
+            emit(code, d, slot_off(a));
+            return true;
+        }
+        default:
+            return fail("opcode not allowed in the point tape");
+        }
+    }
+};
+
+}  // namespace pydsb

@@ -1,394 +1,212 @@
 // Feasibility kernel: collocation state solve + CQAs + big-M indicator + P(feasible) partials.
 //
 // Work decomposition (B200: 148 SMs, persistent CTAs):
-//   tile  = one design point d_i  x  BLOCK consecutive theta samples
-//   CTA   = BLOCK threads, loops over tiles  t = blockIdx.x, +gridDim.x, ...
+//   tile   = one design point d_i  x  BLOCK consecutive theta samples
+//   CTA    = BLOCK threads, loops over tiles  t = blockIdx.x, +gridDim.x, ...
 //   thread = one (d_i, theta_j) scenario for the whole pipeline
 //
 // Per scenario (what the reference does inside one GAMS/CONOPT solve per design point,
-// pyds/run.py:55-67 + pyds/solver.py:50-55, for fixed controls):
-//   1. `pro` tape: parameter-only sub-expressions (Arrhenius factors etc.), initial states
-//   2. for each finite element: `elem` tape, then, block after block of the (block-triangular) state
-//      dependency graph, full Newton on the block's 3*NSB collocation unknowns:
-//        point tape of the block (f, df/dx at the 3 Radau points, evaluated 3-wide) -> residual and
-//        Jacobian assembled in registers -> register-resident dense LU -> update
-//      then the quadrature tape; quadrature states advance with the Radau weights
-//   3. `g` tape -> constraint values; indicator = any(g_k > 0)   (utils.py:23-29, solver.py:71-80)
-//   4. w_j * 1[feasible] reduced with warp shuffles; one partial per tile (deterministic finish
-//      in reduce_partials_kernel) -- DEUS's efp reduction.
+// pyds/run.py:55-67 + pyds/solver.py:50-55, for fixed controls) the thread runs ONE program, assembled
+// by pydsb_model_create (assembler.h) from the lowered tapes and kept pre-decoded in the constant bank:
+//
+//     pro ops (parameter-only values: Arrhenius factors, ...)            INIT (initial states)
+//     element loop:  LDCTRL..., elem ops,
+//                    per block of the (block-triangular) state graph:
+//                        NB   start the block's Newton solve from the element's initial value
+//                        point ops: f and df/dx of the block at the 3 Radau points, evaluated 3-wide
+//                        NS   residual + Jacobian assembled in registers -> register-resident dense LU
+//                             -> update -> stop test; loops back to the block's point ops
+//                    quadrature ops, QACC (Radau weights)                 ELEM_END
+//     XEND, g ops (CQAs), END
+//
+// then (hand-written epilogue) indicator = any(g_k > 0)   (utils.py:23-29, solver.py:71-80) and
+// w_j * 1[feasible] reduced with warp shuffles; one partial per tile (deterministic finish in
+// reduce_partials_kernel) -- DEUS's efp reduction.
+//
+// The interpreter: the program counter and every decoded field live in uniform registers (LDCU
+// fetch), the dispatch is one dense switch, and every opcode is specialised on its operand pattern
+// (N = narrow: one value per scenario, W = wide: one value per collocation point, 1 KiB apart), so a
+// body is nothing but LDS [thread base + uniform offset (+ imm)], the DFMAs, and STS.
 //
 // theta tiles are staged by 1-D bulk TMA (cp.async.bulk + mbarrier), double buffered: the copy
 // for tile k+1 is in flight while tile k is computed.
 #pragma once
-#include <cuda_runtime.h>
-#include <float.h>
-#include <stdint.h>
-
-#include "tape_vm.cuh"
+#include "common.cuh"
 
 namespace pydsb {
 
-constexpr int MAX_BLOCKS = 4;          // blocks of the block-triangular state solve
-constexpr int MAX_STATES = 8;          // dynamic states in total (each block holds at most 3)
+// Opcodes, numbered by dispatch tier: the dispatch is a compare tree over uniform registers, so the ops
+// that run once per Newton iteration sit at depth <= 3, the other common point ops at depth <= 5.
+enum XCode : unsigned {
+    // tier 1 (op < 4)
+    X_NS1 = 0, X_FMA_NWN, X_MUL_NW, X_SQR_W,
+    // tier 2 (op < 16)
+    X_FMA_NWW, X_FMA_WWN, X_FMA_WWW, X_FMS_NWN, X_FMS_NWW, X_FNMA_NWN, X_MUL_WW, X_ADD_NW, X_SUB_WW, X_NS2, X_NB1, X_QACC,
+    // tier 3: remaining three-wide point ops, by operand pattern (N narrow, W wide) ...
+    X_FMS_WWN, X_FMS_WWW, X_FNMA_NWW, X_FNMA_WWN, X_FNMA_WWW, X_ADD_WW, X_SUB_NW, X_SUB_WN, X_DIV_NW, X_DIV_WN, X_DIV_WW,
+    X_NEG_W, X_RCP_W, X_ABS_W, X_MOV_W, X_BC_N, X_MIN_NW, X_MIN_WW, X_MAX_NW, X_MAX_WW, X_COLD_W,
+    // ... scalar ops (pro / elem / g tapes; flags: operand a/b/c lives in the constant pool) ...
+    X_FMA1, X_FMS1, X_FNMA1, X_MUL1, X_ADD1, X_SUB1, X_DIV1, X_SQR1, X_NEG1, X_RCP1, X_ABS1, X_MOV1,
+    X_MIN1, X_MAX1, X_COLD1,
+    // ... structure
+    X_INIT, X_LDCTRL, X_NB2, X_NB3, X_NS3, X_ELEM_END, X_XEND, X_END,
+    X_COUNT
+};
+constexpr unsigned X_TIER1 = 4, X_TIER2 = 16;
 
-struct ExecImage {
-    // global-memory copies made by pydsb_model_create
-    const uint64_t* code;      // pro | elem | g   (narrow tapes; staged in shared memory)
-    const double* consts;      // constant pool
-    const uint16_t* tabs;      // par[n_param] x0[ns] q0[nq] ztab[nz] zfix[nz] gtab[ng] cmap[nfe*nce] (+ sens tables)
-    int n_pro, n_elem, n_pt, n_g, n_const, n_tabs;
-    int ns, nq, ng, d_dim, p_dim, nz, nfe, nce, n_units;
-    int ctrl_slot, xe_slot, qe_slot, x_slot;
-    int fq_state_dep;
-    int max_it;
-    double rtol2;              // (relative Newton tolerance)^2
-    double adot[16];
-    double bw[3];
-    // block-triangular state solve: block b owns blk_ns[b] states and instructions
-    // [blk_pc0[b], blk_pc0[b] + blk_npt[b]) of the pre-decoded point tape; then the quadrature tape
-    int n_blocks;
-    int blk_ns[MAX_BLOCKS], blk_lin[MAX_BLOCKS], blk_pc0[MAX_BLOCKS], blk_npt[MAX_BLOCKS];
-    unsigned blk_flops[MAX_BLOCKS];            // algorithmic flops of one Newton iteration of the block
-    int q_pc0, q_npt;
-    // byte offsets (per collocation point; equal offsets = narrow value) so that every access of the
-    // compiled Newton code is LDS/STS [thread base + uniform offset]
-    unsigned blk_x_o[MAX_BLOCKS][3][3];        // the block's states in the X region
-    unsigned blk_f_o[MAX_BLOCKS][3][3];        // f of the block's states
-    unsigned blk_j_o[MAX_BLOCKS][9][3];        // d f_r / d x_c within the block
-    unsigned blk_jmask[MAX_BLOCKS];            // bit r*nsb+c: entry not structurally zero
-    unsigned fq_o[8][3];
-    unsigned fq_mask;
-    // program 1 only (one block): dfq/dx (nq x ns), df/dz (ns x nce), dfq/dz (nq x nce);
-    // dg/dxe (ng x ns) and dg/dqe (ng x nq) are narrow references in `tabs` after cmap
-    unsigned fqx_o[24][3], fqx_mask;
-    unsigned fz_o[12][3], fz_mask;
-    unsigned fqz_o[32][3], fqz_mask;
-    double bigm_inv[8];        // 1 / M_k
-    // shared-memory carve-up (bytes from the start of dynamic smem)
-    int off_code, off_const, off_tabs, off_land, off_slots, smem_bytes;
+// Instruction layout (uint4 units; `pcw` indexes c_prog):
+//   data ops    w0 = { op, dst, a, b }            w1 = { c, flags, cold opcode, - }                 length 2
+//   NBk         w0 = { op, x_o[0..2] }                                                             length 2
+//   NSk         w0 = { op, target pcw, flops, jmask | linear << 16 }
+//               then x_o[k], f_o[k][3], j_o[k*k][3] packed word by word                          length 1 + ceil(k(4+3k)/4)
+//   QACC        w0 = { op, dst, o0, o1 }          w1 = { o2 }        LDCTRL  w0 = { op, dst, control }
+//   ELEM_END    w0 = { op, target pcw }
+__host__ __device__ constexpr int ns_words(int nsb) { return nsb + 3 * nsb + 3 * nsb * nsb; }
+__host__ __device__ constexpr int ns_length(int nsb) { return 1 + (ns_words(nsb) + 3) / 4; }
+
+constexpr unsigned US = BLOCK * 8u;                       // bytes between consecutive slots of one thread
+
+#define LDN(o) (*reinterpret_cast<const double*>(base + (o)))
+#define LDP(o, p) (*reinterpret_cast<const double*>(base + (o) + (p) * US))
+#define STN(o, v) (*reinterpret_cast<double*>(base + (o)) = (v))
+#define STP(o, p, v) (*reinterpret_cast<double*>(base + (o) + (p) * US) = (v))
+
+// ---------------------------------------------------------------------------------------------
+// Newton solve of one block (NSB states, N = 3*NSB collocation unknowns) on one finite element.
+// newton_begin: start from the end point of the previous element (the INIT op seeds point 2 with x(0)).
+// newton_step:  residual and Jacobian assembled in registers from the block's point-op outputs, dense LU
+//               without pivoting (register resident), update, stop test.
+// ---------------------------------------------------------------------------------------------
+template <int NSB, int MAXNS>
+__device__ __forceinline__ void newton_begin(const unsigned (&xo)[3], char* __restrict__ base, double (&xs)[MAXNS],
+                                             double (&xv)[3][MAXNS])
+{
+#pragma unroll
+    for (int n = 0; n < NSB; ++n) {
+        const double v = LDP(xo[n], 2);
+        xs[n] = v;
+        xv[0][n] = xv[1][n] = xv[2][n] = v;
+        STP(xo[n], 0, v);
+        STP(xo[n], 1, v);
+    }
+}
+
+// word k of the operand table that follows an NS instruction's first uint4
+template <int NW>
+struct NsTab {
+    uint4 q[NW];
+    __device__ __forceinline__ unsigned operator[](int k) const
+    {
+        const uint4& v = q[k >> 2];
+        return (k & 3) == 0 ? v.x : ((k & 3) == 1 ? v.y : ((k & 3) == 2 ? v.z : v.w));
+    }
 };
 
-struct LaunchArgs {
-    const double* d;
-    const double* theta;
-    const double* w;           // may be null -> uniform 1/n_t
-    const double* z;
-    int z_mode;
-    long long n_d, n_t;
-    int n_tiles;               // theta tiles per design point
-    int theta_tma_ok;          // base pointer 16-byte aligned
-    double* partial;           // (n_d, n_tiles)
-    double* g_out;
-    double* ind_out;
-    unsigned long long* counters;
-};
-
-// The point tape, pre-decoded by pydsb_model_create into byte offsets and kept in the constant
-// bank: the fetch is a uniform LDCU and every operand address is [thread base + uniform offset],
-// so the hot interpreter spends no vector-ALU instructions on decoding.
-//   word 0: op | words 1-3: dst offsets (points 0,1,2) | 4-6: a | 7-9: b | 10-12: c | 13-15: pad
-constexpr int MAX_PT = 320;
-__constant__ uint4 c_pt[4 * MAX_PT];        // program 0: feasibility
-__constant__ uint4 c_pt_s[4 * MAX_PT];      // program 1: feasibility + control sensitivities
-
-// ---------------------------------------------------------------------------------------------
-// mbarrier / bulk-TMA helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+template <int NSB, int MAXNS>
+__device__ __forceinline__ void newton_step(const ExecImage& img, int pcw, unsigned jmask, bool linear,
+                                            char* __restrict__ base, double h, const double (&xs)[MAXNS],
+                                            double (&xv)[3][MAXNS], double& s_prev, bool& conv, bool& failed)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-    unsigned done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Register-resident dense LU solve without pivoting (N = 3, 6, 9).  The Newton matrix
-//   A^T (x) I - h * blockdiag(df/dx)
-// has the fixed, well-conditioned collocation part on every diagonal block; a vanishing pivot
-// produces inf/nan which the caller reports as a failed scenario.
-// ---------------------------------------------------------------------------------------------
-template <int N>
-__device__ __forceinline__ void lu_factor(double (&M)[N][N], double (&inv)[N])
-{
+    constexpr int N = 3 * NSB;
+    constexpr int NW = ns_length(NSB) - 1;
+    NsTab<NW> tab;
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        inv[k] = fast_rcp(M[k][k]);
+    for (int i = 0; i < NW; ++i) tab.q[i] = c_prog[pcw + 1 + i];
+    // table: x_o[NSB] | f_o[NSB][3] | j_o[NSB*NSB][3]
+    constexpr int F0 = NSB, J0 = NSB + 3 * NSB;
+    double M[N][N], r[N];
 #pragma unroll
-        for (int i = k + 1; i < N; ++i) {
-            const double l = M[i][k] * inv[k];
-            M[i][k] = l;                                   // keep the multiplier: more right-hand sides may follow
+    for (int jj = 0; jj < 3; ++jj) {
 #pragma unroll
-            for (int c = k + 1; c < N; ++c) M[i][c] = fma(-l, M[k][c], M[i][c]);
+        for (int n = 0; n < NSB; ++n) {
+            double lin = img.adot[jj + 1] * xs[n];                       // adot[0][jj+1]
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
+            r[jj * NSB + n] = fma(h, LDN(tab[F0 + 3 * n + jj]), -lin);
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+                for (int m = 0; m < NSB; ++m) {
+                    const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
+                    M[jj * NSB + n][kk * NSB + m] = a;
+                    if (kk == jj && ((jmask >> (n * NSB + m)) & 1u))
+                        M[jj * NSB + n][kk * NSB + m] = fma(-h, LDN(tab[J0 + 3 * (n * NSB + m) + jj]), a);
+                }
         }
     }
+
+    lu_solve_inplace<N>(M, r);
+
+    double sq = 0.0, sc = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+        for (int n = 0; n < NSB; ++n) {
+            const double dx = r[kk * NSB + n];
+            const double xn = xv[kk][n] + dx;
+            xv[kk][n] = xn;
+            STP(tab[n], kk, xn);
+            sq = fma(dx, dx, sq);
+            sc = fma(xn, xn, sc);
+        }
+    // stop when the step is below tolerance, or when the contraction rate seen so far bounds the
+    // remaining error below it:  |dx_k|^2 / |dx_{k-1}| <= rtol * |X|.  A linear block is exact after
+    // one step.
+    const double lim = img.rtol2 * fmax(sc, 1.0);
+    const bool bad = !(sq <= DBL_MAX);                        // inf or nan
+    const bool ok = linear || (sq <= lim) || (sq * sq <= lim * s_prev && sq <= 0.01 * s_prev);
+    s_prev = sq;
+    if (bad) failed = true;
+    if (ok || bad) conv = true;
 }
 
-template <int N>
-__device__ __forceinline__ void lu_apply(const double (&M)[N][N], const double (&inv)[N], double (&r)[N])
-{
-#pragma unroll
-    for (int k = 0; k < N; ++k)
-#pragma unroll
-        for (int i = k + 1; i < N; ++i) r[i] = fma(-M[i][k], r[k], r[i]);
-#pragma unroll
-    for (int k = N - 1; k >= 0; --k) {
-        double s = r[k];
-#pragma unroll
-        for (int c = k + 1; c < N; ++c) s = fma(-M[k][c], r[c], s);
-        r[k] = s * inv[k];
-    }
-}
-
-template <int N>
-__device__ __forceinline__ void lu_solve_inplace(double (&M)[N][N], double (&r)[N])
-{
-    double inv[N];
-    lu_factor<N>(M, inv);
-    lu_apply<N>(M, inv, r);
-}
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ unsigned warp_sum_u32(unsigned v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Hot interpreter: the point tape, three collocation points per instruction, operands addressed
-// as [thread base + uniform byte offset] (LDS/STS with a uniform-register offset).  Sixteen dense
-// execution opcodes (XOP_*) so that the dispatch is one jump table; everything transcendental
-// goes through one out-of-line cold function.
-// ---------------------------------------------------------------------------------------------
-enum XOp : unsigned {
-    XOP_FMA = 0, XOP_FMS, XOP_FNMA, XOP_MUL, XOP_ADD, XOP_SUB, XOP_SQR, XOP_MOV, XOP_NEG, XOP_DIV, XOP_RCP,
-    XOP_ABS, XOP_MIN, XOP_MAX, XOP_NOP, XOP_COLD
-};
-
-__device__ __noinline__ double cold_op(unsigned op, double a, double b)
-{
-    switch (op) {
-    case OP_EXP: return exp(a);
-    case OP_LOG: return log(a);
-    case OP_SQRT: return sqrt(a);
-    case OP_SIN: return sin(a);
-    case OP_COS: return cos(a);
-    case OP_TANH: return tanh(a);
-    case OP_POW: return pow(a, b);
-    default: return a;
-    }
-}
-
-#define PT_LD(off) (*reinterpret_cast<const double*>(base + (off)))
-#define PT_ST(off, v) (*reinterpret_cast<double*>(base + (off)) = (v))
-// a narrow operand (same slot for the three points) is loaded once
-#define PT_LOAD3(v, o0, o1, o2, narrow)                               \
-    const double v##0 = PT_LD(o0);                                    \
-    double v##1 = v##0, v##2 = v##0;                                  \
-    if (!(narrow)) { v##1 = PT_LD(o1); v##2 = PT_LD(o2); }
-#define PT_UN(expr)                                                   \
+// operand loaders of the point ops: N = narrow (one load), W = wide (three loads, 1 KiB apart)
+#define XLD_N(v, o) const double v##0 = LDN(o); const double v##1 = v##0, v##2 = v##0;
+#define XLD_W(v, o) const double v##0 = LDP(o, 0), v##1 = LDP(o, 1), v##2 = LDP(o, 2);
+#define XST3(o) STP(o, 0, r0); STP(o, 1, r1); STP(o, 2, r2);
+#define X_TER(PA, PB, PC, expr)                                       \
     {                                                                 \
-        PT_LOAD3(a, q1.x, q1.y, q1.z, q0.x & 16u)                     \
-        double a;                                                     \
-        a = a0; const double r0 = (expr);                             \
-        a = a1; const double r1 = (expr);                             \
-        a = a2; const double r2 = (expr);                             \
-        PT_ST(q0.y, r0); PT_ST(q0.z, r1); PT_ST(q0.w, r2);            \
-    }                                                                 \
-    break;
-#define PT_BIN(expr)                                                  \
-    {                                                                 \
-        const uint4 q2 = c_pt[4 * pc + 2];                            \
-        PT_LOAD3(a, q1.x, q1.y, q1.z, q0.x & 16u)                     \
-        PT_LOAD3(b, q1.w, q2.x, q2.y, q0.x & 32u)                     \
-        double a, b;                                                  \
-        a = a0; b = b0; const double r0 = (expr);                     \
-        a = a1; b = b1; const double r1 = (expr);                     \
-        a = a2; b = b2; const double r2 = (expr);                     \
-        PT_ST(q0.y, r0); PT_ST(q0.z, r1); PT_ST(q0.w, r2);            \
-    }                                                                 \
-    break;
-#define PT_TER(expr)                                                  \
-    {                                                                 \
-        const uint4 q2 = c_pt[4 * pc + 2];                            \
-        const uint4 q3 = c_pt[4 * pc + 3];                            \
-        PT_LOAD3(a, q1.x, q1.y, q1.z, q0.x & 16u)                     \
-        PT_LOAD3(b, q1.w, q2.x, q2.y, q0.x & 32u)                     \
-        PT_LOAD3(c, q2.z, q2.w, q3.x, q0.x & 64u)                     \
+        const unsigned oc = c_prog[pcw - 1].x;                        \
+        XLD_##PA(a, w0.z) XLD_##PB(b, w0.w) XLD_##PC(c, oc)           \
         double a, b, c;                                               \
         a = a0; b = b0; c = c0; const double r0 = (expr);             \
         a = a1; b = b1; c = c1; const double r1 = (expr);             \
         a = a2; b = b2; c = c2; const double r2 = (expr);             \
-        PT_ST(q0.y, r0); PT_ST(q0.z, r1); PT_ST(q0.w, r2);            \
+        XST3(w0.y)                                                    \
     }                                                                 \
     break;
+#define X_BIN(PA, PB, expr)                                           \
+    {                                                                 \
+        XLD_##PA(a, w0.z) XLD_##PB(b, w0.w)                           \
+        double a, b;                                                  \
+        a = a0; b = b0; const double r0 = (expr);                     \
+        a = a1; b = b1; const double r1 = (expr);                     \
+        a = a2; b = b2; const double r2 = (expr);                     \
+        XST3(w0.y)                                                    \
+    }                                                                 \
+    break;
+#define X_UN(PA, expr)                                                \
+    {                                                                 \
+        XLD_##PA(a, w0.z)                                             \
+        double a;                                                     \
+        a = a0; const double r0 = (expr);                             \
+        a = a1; const double r1 = (expr);                             \
+        a = a2; const double r2 = (expr);                             \
+        XST3(w0.y)                                                    \
+    }                                                                 \
+    break;
+// scalar ops: an operand is a slot of this thread or an entry of the (block-uniform) constant pool
+#define X1_A const double a = *reinterpret_cast<const double*>(((fl & 1u) ? cz : base) + w0.z);
+#define X1_B const double b = *reinterpret_cast<const double*>(((fl & 2u) ? cz : base) + w0.w);
+#define X1_C const double c = *reinterpret_cast<const double*>(((fl & 4u) ? cz : base) + w1.x);
+#define X1_FL const uint4 w1 = c_prog[pcw - 1]; const unsigned fl = w1.y;
+#define X1_TER(expr) { X1_FL X1_A X1_B X1_C STN(w0.y, (expr)); } break;
+#define X1_BIN(expr) { X1_FL X1_A X1_B STN(w0.y, (expr)); } break;
+#define X1_UN(expr) { X1_FL X1_A STN(w0.y, (expr)); } break;
 
-template <bool SENS>
-__device__ __forceinline__ void run_point_tape(char* __restrict__ base, int pc0, int n)
-{
-    const uint4* const c_pt = SENS ? c_pt_s : pydsb::c_pt;
-    for (int pc = pc0; pc < pc0 + n; ++pc) {
-        const uint4 q0 = c_pt[4 * pc];
-        const uint4 q1 = c_pt[4 * pc + 1];
-        switch (q0.x & 15u) {
-        case XOP_FMA: PT_TER(fma(a, b, c))
-        case XOP_FMS: PT_TER(fma(a, b, -c))
-        case XOP_FNMA: PT_TER(fma(-a, b, c))
-        case XOP_MUL: PT_BIN(a * b)
-        case XOP_ADD: PT_BIN(a + b)
-        case XOP_SUB: PT_BIN(a - b)
-        case XOP_SQR: PT_UN(a * a)
-        case XOP_MOV: PT_UN(a)
-        case XOP_NEG: PT_UN(-a)
-        case XOP_DIV: PT_BIN(a / b)
-        case XOP_RCP: PT_UN(1.0 / a)
-        case XOP_ABS: PT_UN(fabs(a))
-        case XOP_MIN: PT_BIN(fmin(a, b))
-        case XOP_MAX: PT_BIN(fmax(a, b))
-        case XOP_NOP: break;
-        case XOP_COLD: {
-            const unsigned op = q0.x >> 8;
-            PT_BIN(cold_op(op, a, b))
-        }
-        }
-    }
-}
-#undef PT_LOAD3
-#undef PT_UN
-#undef PT_BIN
-#undef PT_TER
-
-// The narrow tapes (pro / elem / g) run once per scenario or element: keep one out-of-line copy.
-__device__ __noinline__ void run_narrow_tape(double* S, const double* cpool, const uint64_t* code, int n)
-{
-    VM vm;
-    vm.S = S;
-    vm.cpool = cpool;
-    run_tape<1>(vm, code, n);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Newton solve of one block (NSB states, N = 3*NSB collocation unknowns) on one finite element.
-// Residual and Jacobian are assembled in registers from the block's point tape outputs; dense LU
-// without pivoting, register resident.  Returns the iterations this thread needed (own convergence).
-// ---------------------------------------------------------------------------------------------
-template <int NSB>
-__device__ __forceinline__ unsigned newton_block(const ExecImage& img, int b, char* __restrict__ base, double h,
-                                                 bool& failed, unsigned& warp_iters)
-{
-    constexpr int N = 3 * NSB;
-    double xs[NSB], xv[3][NSB];
-    // element start = end point of the previous element (the prologue seeds point 2 with x(0))
-#pragma unroll
-    for (int n = 0; n < NSB; ++n) {
-        xs[n] = PT_LD(img.blk_x_o[b][n][2]);
-        xv[0][n] = xv[1][n] = xv[2][n] = xs[n];
-        PT_ST(img.blk_x_o[b][n][0], xs[n]);
-        PT_ST(img.blk_x_o[b][n][1], xs[n]);
-    }
-    const int pc0 = img.blk_pc0[b], npt = img.blk_npt[b];
-    const unsigned jmask = img.blk_jmask[b];
-    const bool linear = img.blk_lin[b] != 0;
-    bool conv = false;
-    unsigned my_iters = 0;
-    double s_prev = 0.0;                          // no rate estimate before the second step
-    for (int it = 0;; ++it) {
-        run_point_tape<false>(base, pc0, npt);    // f and df/dx of this block at the 3 points
-
-        double M[N][N], r[N];
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-#pragma unroll
-            for (int n = 0; n < NSB; ++n) {
-                double lin = img.adot[jj + 1] * xs[n];                       // adot[0][jj+1]
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
-                r[jj * NSB + n] = fma(h, PT_LD(img.blk_f_o[b][n][jj]), -lin);
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                    for (int m = 0; m < NSB; ++m) {
-                        const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
-                        M[jj * NSB + n][kk * NSB + m] = a;
-                        if (kk == jj && ((jmask >> (n * NSB + m)) & 1u))
-                            M[jj * NSB + n][kk * NSB + m] = fma(-h, PT_LD(img.blk_j_o[b][n * NSB + m][jj]), a);
-                    }
-            }
-        }
-
-        lu_solve_inplace<N>(M, r);
-
-        double s = 0.0, sc = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-            for (int n = 0; n < NSB; ++n) {
-                const double dx = r[kk * NSB + n];
-                const double xn = xv[kk][n] + dx;
-                xv[kk][n] = xn;
-                PT_ST(img.blk_x_o[b][n][kk], xn);
-                s = fma(dx, dx, s);
-                sc = fma(xn, xn, sc);
-            }
-        if (!conv) ++my_iters;
-        ++warp_iters;
-        // stop when the step is below tolerance, or when the contraction rate seen so far bounds the
-        // remaining error below it:  |dx_k|^2 / |dx_{k-1}| <= rtol * |X|.  A linear block is exact after
-        // one step.
-        const double lim = img.rtol2 * fmax(sc, 1.0);
-        const bool bad = !(s <= DBL_MAX);                        // inf or nan
-        const bool ok = linear || (s <= lim) || (s * s <= lim * s_prev && s <= 0.01 * s_prev);
-        s_prev = s;
-        if (bad) failed = true;
-        if (ok || bad) conv = true;
-        if (__all_sync(0xffffffffu, conv) || (it + 1 >= img.max_it)) break;
-    }
-    if (!conv) failed = true;
-    return my_iters;
-}
-
+// MAXNS = largest block of coupled states (1..3).
 template <int MAXNS>
-__global__ void __launch_bounds__(BLOCK, (MAXNS <= 2 ? 4 : 2))
+__global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2)))
     feas_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ LaunchArgs la)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -397,15 +215,12 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 2 ? 4 : 2))
 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);                 // [1]
     double* red = reinterpret_cast<double*>(smem + 16);                 // [BLOCK/32]
-    uint64_t* code = reinterpret_cast<uint64_t*>(smem + img.off_code);
     double* cpool = reinterpret_cast<double*>(smem + img.off_const) + 1;   // cpool[-1] = 0.0
     uint16_t* tabs = reinterpret_cast<uint16_t*>(smem + img.off_tabs);
     double* land = reinterpret_cast<double*>(smem + img.off_land);      // [BLOCK*p_dim]
     double* S = reinterpret_cast<double*>(smem + img.off_slots) + tid;
 
-    // ---- stage the narrow tapes, constants and tables in shared memory (once per CTA) ----
-    const int n_code = img.n_pro + img.n_elem + img.n_g;
-    for (int i = tid; i < n_code; i += BLOCK) code[i] = img.code[i];
+    // ---- stage constants and reference tables in shared memory (once per CTA) ----
     for (int i = tid; i < img.n_const; i += BLOCK) cpool[i] = img.consts[i];
     for (int i = tid; i < img.n_tabs; i += BLOCK) tabs[i] = img.tabs[i];
     if (tid == 0) {
@@ -415,9 +230,6 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 2 ? 4 : 2))
     }
     __syncthreads();
 
-    const uint64_t* code_pro = code;
-    const uint64_t* code_elem = code_pro + img.n_pro;
-    const uint64_t* code_g = code_elem + img.n_elem;
     const uint16_t* tab_par = tabs;
     const uint16_t* tab_x0 = tab_par + img.d_dim + img.p_dim;
     const uint16_t* tab_q0 = tab_x0 + img.ns;
@@ -430,8 +242,8 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 2 ? 4 : 2))
     vm.S = S;
     vm.cpool = cpool;
 
-    double* const Xs = S + img.x_slot * BLOCK;
     char* const base = reinterpret_cast<char*>(S);
+    const char* const cz = reinterpret_cast<const char*>(cpool - 1);    // constant operands: (index + 1) * 8
 
     const double h = 1.0 / (double)img.nfe;
     const int p_dim = img.p_dim, d_dim = img.d_dim;
@@ -468,7 +280,7 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 2 ? 4 : 2))
         const long long j0 = (t % la.n_tiles) * (long long)BLOCK;
         const int rows = tile_rows(t);
         const bool valid = tid < rows;
-        const int row = valid ? tid : rows - 1;           // idle lanes replay the last row
+        const int row = valid ? tid : rows - 1;               // idle lanes replay the last row
         const long long j = j0 + row;
 
         // ---- parameters into the register file (theta from the TMA landing buffer) ----
@@ -488,63 +300,153 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 2 ? 4 : 2))
             if (nt < total && tid == 0) issue(nt);
         }
 
-        // ---- prologue: parameter-only values, initial states (seeded at collocation point 2) ----
-        run_narrow_tape(S, cpool, code_pro, img.n_pro);
-        {
-            double x0v[MAX_STATES];
-            for (int n = 0; n < img.ns; ++n) x0v[n] = vm_ld(vm, tab_x0[n]);      // read all before X overlays are written
-            for (int n = 0; n < img.ns; ++n) Xs[(3 * n + 2) * BLOCK] = x0v[n];
-        }
-        for (int q = 0; q < img.nq; ++q) S[(img.qe_slot + q) * BLOCK] = vm_ld(vm, tab_q0[q]);
-
-        bool failed = false;
-        unsigned my_iters = 0;
-        unsigned long long my_flops = 0;
-
-        for (int e = 0; e < img.nfe; ++e) {
-            // controls of this finite element
-            for (int c = 0; c < img.nce; ++c) {
-                const int zi = tab_cmap[e * img.nce + c];
-                double zv;
-                if (la.z_mode == 0 || tab_zfix[zi]) zv = vm_ld(vm, tab_z[zi]);
-                else if (la.z_mode == 1) zv = __ldg(la.z + zi);
-                else if (la.z_mode == 2) zv = __ldg(la.z + i_d * img.nz + zi);
-                else zv = __ldg(la.z + (i_d * la.n_t + j) * img.nz + zi);
-                S[(img.ctrl_slot + c) * BLOCK] = zv;
-            }
-            run_narrow_tape(S, cpool, code_elem, img.n_elem);
-
-            // blocks of the state dependency graph, dependencies first
-            for (int b = 0; b < img.n_blocks; ++b) {
-                unsigned it_b = 0;
-                const int nsb = img.blk_ns[b];
-                if (nsb == 1) it_b = newton_block<1>(img, b, base, h, failed, cnt_warp_iters);
-                if constexpr (MAXNS >= 2) { if (nsb == 2) it_b = newton_block<2>(img, b, base, h, failed, cnt_warp_iters); }
-                if constexpr (MAXNS >= 3) { if (nsb == 3) it_b = newton_block<3>(img, b, base, h, failed, cnt_warp_iters); }
-                my_iters += it_b;
-                my_flops += (unsigned long long)it_b * img.blk_flops[b];
-            }
-
-            // quadrature states: x_q += h * sum_j bw_j fq(x_j) at the converged points
-            if (img.nq > 0) {
-                run_point_tape<false>(base, img.q_pc0, img.q_npt);
-                for (int q = 0; q < img.nq; ++q) {
-                    if (!((img.fq_mask >> q) & 1u)) continue;
-                    double acc = img.bw[0] * PT_LD(img.fq_o[q][0]);
-                    acc = fma(img.bw[1], PT_LD(img.fq_o[q][1]), acc);
-                    acc = fma(img.bw[2], PT_LD(img.fq_o[q][2]), acc);
-                    S[(img.qe_slot + q) * BLOCK] = fma(h, acc, S[(img.qe_slot + q) * BLOCK]);
+        // ---- the scenario's program ----
+        bool failed = false, conv = false;
+        unsigned my_iters = 0, my_flops = 0;
+        double xs[MAXNS], xv[3][MAXNS];
+        double s_prev = 0.0;
+        int it = 0, e = 0;
+        int pcw = 0;                                       // uint4 index of the next instruction
+#define X_NS_CASE(K)                                                                                            \
+    {                                                                                                           \
+        const int at = pcw - 2;                                                                                 \
+        pcw = at + ns_length(K);                                                                                \
+        if (!conv) { ++my_iters; my_flops += w0.z; }                                                            \
+        newton_step<K, MAXNS>(img, at, w0.w & 0xFFFFu, (w0.w >> 16) != 0, base, h, xs, xv, s_prev, conv, failed); \
+        ++cnt_warp_iters;                                                                                       \
+        ++it;                                                                                                   \
+        if (!__all_sync(0xffffffffu, conv) && it < img.max_it) pcw = (int)w0.y;     /* back to the point ops */  \
+        else if (!conv) failed = true;                                                                          \
+    }                                                                                                           \
+    break;
+#define X_NB_CASE(K)                                                                                            \
+    {                                                                                                           \
+        const unsigned xo[3] = {w0.y, w0.z, w0.w};                                                              \
+        newton_begin<K, MAXNS>(xo, base, xs, xv);                                                               \
+        conv = false; s_prev = 0.0; it = 0;                                                                     \
+    }                                                                                                           \
+    break;
+        for (;;) {
+            const uint4 w0 = c_prog[pcw];
+            pcw += 2;
+            const unsigned op = w0.x;
+            if (op < X_TIER1) {
+                switch (op) {
+                case X_NS1: X_NS_CASE(1)
+                case X_FMA_NWN: X_TER(N, W, N, fma(a, b, c))
+                case X_MUL_NW: X_BIN(N, W, a * b)
+                case X_SQR_W: X_UN(W, a * a)
                 }
+            } else if (op < X_TIER2) {
+                switch (op) {
+                case X_FMA_NWW: X_TER(N, W, W, fma(a, b, c))
+                case X_FMA_WWN: X_TER(W, W, N, fma(a, b, c))
+                case X_FMA_WWW: X_TER(W, W, W, fma(a, b, c))
+                case X_FMS_NWN: X_TER(N, W, N, fma(a, b, -c))
+                case X_FMS_NWW: X_TER(N, W, W, fma(a, b, -c))
+                case X_FNMA_NWN: X_TER(N, W, N, fma(-a, b, c))
+                case X_MUL_WW: X_BIN(W, W, a * b)
+                case X_ADD_NW: X_BIN(N, W, a + b)
+                case X_SUB_WW: X_BIN(W, W, a - b)
+                case X_NS2:
+                    if constexpr (MAXNS >= 2) X_NS_CASE(2)
+                    break;
+                case X_NB1: X_NB_CASE(1)
+                case X_QACC: {                             // quadrature: x_q += h * sum_j bw_j fq(x_j) at the converged points
+                    const unsigned o2 = c_prog[pcw - 1].x;
+                    double acc = img.bw[0] * LDN(w0.z);
+                    acc = fma(img.bw[1], LDN(w0.w), acc);
+                    acc = fma(img.bw[2], LDN(o2), acc);
+                    STN(w0.y, fma(h, acc, LDN(w0.y)));
+                    break;
+                }
+                }
+            } else {
+                switch (op) {
+                case X_FMS_WWN: X_TER(W, W, N, fma(a, b, -c))
+                case X_FMS_WWW: X_TER(W, W, W, fma(a, b, -c))
+                case X_FNMA_NWW: X_TER(N, W, W, fma(-a, b, c))
+                case X_FNMA_WWN: X_TER(W, W, N, fma(-a, b, c))
+                case X_FNMA_WWW: X_TER(W, W, W, fma(-a, b, c))
+                case X_ADD_WW: X_BIN(W, W, a + b)
+                case X_SUB_NW: X_BIN(N, W, a - b)
+                case X_SUB_WN: X_BIN(W, N, a - b)
+                case X_DIV_NW: X_BIN(N, W, a / b)
+                case X_DIV_WN: X_BIN(W, N, a / b)
+                case X_DIV_WW: X_BIN(W, W, a / b)
+                case X_NEG_W: X_UN(W, -a)
+                case X_RCP_W: X_UN(W, 1.0 / a)
+                case X_ABS_W: X_UN(W, fabs(a))
+                case X_MOV_W: X_UN(W, a)
+                case X_BC_N: X_UN(N, a)
+                case X_MIN_NW: X_BIN(N, W, fmin(a, b))
+                case X_MIN_WW: X_BIN(W, W, fmin(a, b))
+                case X_MAX_NW: X_BIN(N, W, fmax(a, b))
+                case X_MAX_WW: X_BIN(W, W, fmax(a, b))
+                case X_COLD_W: {                           // transcendental, 3-wide; flag bit 0/1: a/b is wide
+                    const uint4 w1 = c_prog[pcw - 1];
+                    const unsigned sa = (w1.y & 1u) ? US : 0u, sb = (w1.y & 2u) ? US : 0u;
+#pragma unroll 1
+                    for (unsigned p = 0; p < 3; ++p)
+                        STN(w0.y + p * US, cold_op(w1.z, LDN(w0.z + p * sa), LDN(w0.w + p * sb)));
+                    break;
+                }
+                case X_FMA1: X1_TER(fma(a, b, c))
+                case X_FMS1: X1_TER(fma(a, b, -c))
+                case X_FNMA1: X1_TER(fma(-a, b, c))
+                case X_MUL1: X1_BIN(a * b)
+                case X_ADD1: X1_BIN(a + b)
+                case X_SUB1: X1_BIN(a - b)
+                case X_DIV1: X1_BIN(a / b)
+                case X_SQR1: X1_UN(a * a)
+                case X_NEG1: X1_UN(-a)
+                case X_RCP1: X1_UN(1.0 / a)
+                case X_ABS1: X1_UN(fabs(a))
+                case X_MOV1: X1_UN(a)
+                case X_MIN1: X1_BIN(fmin(a, b))
+                case X_MAX1: X1_BIN(fmax(a, b))
+                case X_COLD1: X1_BIN(cold_op(w1.z, a, b))
+                case X_INIT: {                             // initial states (seeded at collocation point 2), quadratures
+                    double x0v[MAX_STATES];
+                    for (int n = 0; n < img.ns; ++n) x0v[n] = vm_ld(vm, tab_x0[n]);
+                    for (int n = 0; n < img.ns; ++n) S[(img.x_slot + 3 * n + 2) * BLOCK] = x0v[n];
+                    for (int q = 0; q < img.nq; ++q) S[(img.qe_slot + q) * BLOCK] = vm_ld(vm, tab_q0[q]);
+                    break;
+                }
+                case X_LDCTRL: {                           // control w0.z of finite element e -> slot w0.y
+                    const int zi = tab_cmap[e * img.nce + (int)w0.z];
+                    double zv;
+                    if (la.z_mode == 0 || tab_zfix[zi]) zv = vm_ld(vm, tab_z[zi]);
+                    else if (la.z_mode == 1) zv = __ldg(la.z + zi);
+                    else if (la.z_mode == 2) zv = __ldg(la.z + i_d * img.nz + zi);
+                    else zv = __ldg(la.z + (i_d * la.n_t + j) * img.nz + zi);
+                    STN(w0.y, zv);
+                    break;
+                }
+                case X_NB2:
+                    if constexpr (MAXNS >= 2) X_NB_CASE(2)
+                    break;
+                case X_NB3:
+                    if constexpr (MAXNS >= 3) X_NB_CASE(3)
+                    break;
+                case X_NS3:
+                    if constexpr (MAXNS >= 3) X_NS_CASE(3)
+                    break;
+                case X_ELEM_END:
+                    if (++e < img.nfe) pcw = (int)w0.y;
+                    break;
+                case X_XEND:                               // end-point states for the CQA tape
+                    for (int n = 0; n < img.ns; ++n) S[(img.xe_slot + n) * BLOCK] = S[(img.x_slot + 3 * n + 2) * BLOCK];
+                    break;
+                default: break;
+                }
+                if (op == X_END) break;
             }
         }
+#undef X_NS_CASE
+#undef X_NB_CASE
 
-        // ---- CQAs, indicator, outputs ----
-        {
-            double xe[MAX_STATES];
-            for (int n = 0; n < img.ns; ++n) xe[n] = Xs[(3 * n + 2) * BLOCK];
-            for (int n = 0; n < img.ns; ++n) S[(img.xe_slot + n) * BLOCK] = xe[n];
-        }
-        run_narrow_tape(S, cpool, code_g, img.n_g);
+        // ---- indicator, outputs ----
         bool feasible = !failed;
         for (int c = 0; c < img.ng; ++c) {
             double gv = vm_ld(vm, tab_g[c]);
@@ -553,17 +455,16 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 2 ? 4 : 2))
             if (la.g_out && valid) la.g_out[(i_d * la.n_t + j) * img.ng + c] = gv;
         }
         if (la.ind_out && valid) la.ind_out[i_d * la.n_t + j] = feasible ? -0.0 : -1.0;
-
         double wv = 0.0;
         if (valid && feasible) wv = la.w ? __ldg(la.w + j) : 1.0 / (double)la.n_t;
-        wv = warp_sum(wv);
-        if (lane == 0) red[warp] = wv;
         if (valid) {
             cnt_iters += my_iters;
             cnt_flops += my_flops;
             cnt_failed += failed ? 1u : 0u;
             cnt_done += 1u;
         }
+        wv = warp_sum(wv);
+        if (lane == 0) red[warp] = wv;
         __syncthreads();
         if (tid == 0) {
             double sum = 0.0;
@@ -590,35 +491,22 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 2 ? 4 : 2))
     }
 }
 
-#undef PT_LD
-#undef PT_ST
-
-// Deterministic finish of the P(feasible) reduction: one thread per design point sums its tile
-// partials in tile order.
-__global__ void reduce_partials_kernel(const double* __restrict__ partial, int n_tiles, long long n_d,
-                                       double* __restrict__ P)
-{
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n_d) return;
-    const double* p = partial + i * n_tiles;
-    double s = 0.0;
-    for (int t = 0; t < n_tiles; ++t) s += p[t];
-    P[i] = s;
-}
-
-// FP64 FMA throughput probe: 8 independent chains per thread, no memory traffic.
-__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b)
-{
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-        }
-    }
-    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
-    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
+#undef XLD_N
+#undef XLD_W
+#undef XST3
+#undef X_TER
+#undef X_BIN
+#undef X_UN
+#undef X1_A
+#undef X1_B
+#undef X1_C
+#undef X1_FL
+#undef X1_TER
+#undef X1_BIN
+#undef X1_UN
+#undef LDN
+#undef LDP
+#undef STN
+#undef STP
 
 }  // namespace pydsb

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/pydsb.h"
+#include "assembler.h"
 #include "recourse_kernel.cuh"
 
 using namespace pydsb;
@@ -53,7 +54,8 @@ struct Program {
     void* d_code = nullptr;
     void* d_consts = nullptr;
     void* d_tabs = nullptr;
-    std::vector<uint32_t> xpt;          // pre-decoded point tape (16 words per instruction)
+    std::vector<uint32_t> xpt;          // program 1: pre-decoded point tape (16 words per instruction)
+    std::vector<uint32_t> xprog;        // program 0: the assembled per-scenario program (8 words per instruction)
     bool present = false;
 };
 
@@ -217,8 +219,8 @@ int build_program(const Sections& secs, bool sens, Program& P)
     for (uint64_t w : code)
         if ((w & 0xFF) >= OP_COUNT) return fail(PYDSB_ERR_INVALID, "unknown opcode in tape");
     // pre-decode the point tape: per operand the byte offsets of the three collocation points
-    if (g.n_pt + 1 > MAX_PT) return fail(PYDSB_ERR_UNSUPPORTED, "point tape longer than the constant-bank window");
-    {
+    if (sens) {
+        if (g.n_pt + 1 > MAX_PT) return fail(PYDSB_ERR_UNSUPPORTED, "point tape longer than the constant-bank window");
         static const int xmap[OP_COUNT] = {/*MOV*/ XOP_MOV, /*NEG*/ XOP_NEG, /*ADD*/ XOP_ADD, /*SUB*/ XOP_SUB, /*MUL*/ XOP_MUL,
                                            /*DIV*/ XOP_DIV, /*FMA*/ XOP_FMA, /*FMS*/ XOP_FMS, /*FNMA*/ XOP_FNMA, /*SQR*/ XOP_SQR,
                                            /*RCP*/ XOP_RCP, /*EXP*/ XOP_COLD, /*LOG*/ XOP_COLD, /*SQRT*/ XOP_COLD, /*SIN*/ XOP_COLD,
@@ -252,6 +254,28 @@ int build_program(const Sections& secs, bool sens, Program& P)
                 for (int p3 = 0; p3 < 3; ++p3) x[7 + p3] = x[4 + p3];
             if (!(refs[0] & REF_WIDE)) return fail(PYDSB_ERR_INVALID, "point tape writes a narrow slot");
         }
+    }
+    if (!sens) {
+        // program 0: assemble the unified per-scenario program of feas_kernel
+        AsmInput in{};
+        in.pro = reinterpret_cast<const uint64_t*>(tp->data); in.n_pro = g.n_pro;
+        in.elem = reinterpret_cast<const uint64_t*>(te->data); in.n_elem = g.n_elem;
+        in.g = reinterpret_cast<const uint64_t*>(tg->data); in.n_g = g.n_g;
+        in.pt = reinterpret_cast<const uint64_t*>(tn->data);
+        in.n_blocks = g.n_blocks; in.blk_npt = g.blk_npt; in.blk_ns = g.blk_ns; in.blk_lin = g.blk_lin;
+        in.blk_flops = g.blk_flops; in.q_npt = g.q_npt;
+        int sum_pt = g.q_npt;
+        for (int b = 0; b < g.n_blocks; ++b) sum_pt += g.blk_npt[b];
+        if (sum_pt != g.n_pt) return fail(PYDSB_ERR_INVALID, "block tape lengths do not add up to the point tape");
+        in.nce = g.nce; in.ctrl_slot = g.ctrl_slot; in.nq = g.nq; in.qe_slot = g.qe_slot; in.n_units = g.n_units;
+        const Section* rfq = find(secs, "RFQ_");
+        if ((int)rfq->count < g.nq) return fail(PYDSB_ERR_INVALID, "bad fq reference table");
+        in.fq_refs = reinterpret_cast<const uint16_t*>(rfq->data);
+        in.img = &g;
+        Assembler as;
+        if (!as.assemble(in)) return fail(PYDSB_ERR_UNSUPPORTED, "assembler: " + as.err);
+        P.xprog.swap(as.words);
+        g.n_prog = (int)(P.xprog.size() / 4);             // uint4 units
     }
     const Section* cn = find(secs, "CNST");
     g.n_const = cn->count;
@@ -288,7 +312,7 @@ int build_program(const Sections& secs, bool sens, Program& P)
 
     // shared-memory carve-up
     int o = 128;                                            // mbarrier + reduction scratch
-    g.off_code = o; o += (int)code.size() * 8;
+    g.off_code = o; o += sens ? (int)code.size() * 8 : 0;     // program 0 keeps no tape in shared memory
     g.off_const = o; o += (g.n_const + 1) * 8;
     g.off_tabs = o; o = align_up(o + g.n_tabs * 2, 128);
     int land = BLOCK * g.p_dim * 8;
@@ -504,7 +528,7 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
     // several models may share one template instantiation: (re)assert this model's smem size and
     // (re)load its point tape into the constant bank (stream ordered)
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_pt, m->prog[0].xpt.data(), m->prog[0].xpt.size() * sizeof(uint32_t), 0,
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, m->prog[0].xprog.data(), m->prog[0].xprog.size() * sizeof(uint32_t), 0,
                                      cudaMemcpyHostToDevice, st));
     fn<<<grid, BLOCK, img.smem_bytes, st>>>(img, la);
     CUDA_TRY(cudaGetLastError());

@@ -21,7 +21,7 @@
 // Groups: shared mode -> one group per design point (the reference's two-stage formulation: stage-0
 // F_in shared by every theta); per-scenario mode -> one group per (d, theta).
 #pragma once
-#include "feas_kernel.cuh"
+#include "point_tape.cuh"
 
 namespace pydsb {
 
