@@ -46,22 +46,29 @@ public:
         for (int b = 0; b < in.n_blocks; ++b) {
             const int nsb = in.blk_ns[b];
             if (nsb < 1 || nsb > 3) return fail("block size out of range");
-            static const uint32_t nb_code[3] = {X_NB1, X_NB2, X_NB3}, ns_code[3] = {X_NS1, X_NS2, X_NS3};
+            static const uint32_t nb_code[3] = {X_NB1, X_NB2, X_NB3}, ns_code[3] = {X_NS1, X_NS2, X_NS3},
+                                  nsl_code[3] = {X_NS1L, X_NS2L, X_NS3L};
             const ExecImage& g = *in.img;
             emit(nb_code[nsb - 1], g.blk_x_o[b][0][0], nsb > 1 ? g.blk_x_o[b][1][0] : 0u, nsb > 2 ? g.blk_x_o[b][2][0] : 0u);
             const int l_blk = pc();
             for (int i = 0; i < in.blk_npt[b]; ++i)
                 if (!point_op(in.pt[pos++])) return false;
             // NS: first uint4, then the operand table x_o[k] | f_o[k][3] | j_o[k*k][3], padded to whole uint4s
-            const uint32_t head[4] = {ns_code[nsb - 1], (uint32_t)l_blk, in.blk_flops[b],
-                                      (g.blk_jmask[b] & 0xFFFFu) | ((in.blk_lin[b] ? 1u : 0u) << 16)};
+            if (g.max_it < 1 || g.max_it > 0xFFFF) return fail("Newton iteration cap out of range");
+            const uint32_t head[4] = {in.blk_lin[b] ? nsl_code[nsb - 1] : ns_code[nsb - 1], (uint32_t)l_blk, in.blk_flops[b],
+                                      (g.blk_jmask[b] & 0xFFFFu) | ((uint32_t)g.max_it << 16)};
             words.insert(words.end(), head, head + 4);
             std::vector<uint32_t> tab;
             for (int n = 0; n < nsb; ++n) tab.push_back(g.blk_x_o[b][n][0]);
             for (int n = 0; n < nsb; ++n)
                 for (int p3 = 0; p3 < 3; ++p3) tab.push_back(g.blk_f_o[b][n][p3]);
             for (int i = 0; i < nsb * nsb; ++i)
-                for (int p3 = 0; p3 < 3; ++p3) tab.push_back(g.blk_j_o[b][i][p3]);
+                for (int p3 = 0; p3 < 3; ++p3) {
+                    // a 1-state block always loads its Jacobian entry: structurally zero -> the zero slot
+                    const bool zero = nsb == 1 && !(g.blk_jmask[b] & 1u);
+                    if (zero && !g.zero_off) return fail("model needs the zero slot");
+                    tab.push_back(zero ? g.zero_off : g.blk_j_o[b][i][p3]);
+                }
             tab.resize((size_t)(ns_length(nsb) - 1) * 4, 0u);
             words.insert(words.end(), tab.begin(), tab.end());
         }

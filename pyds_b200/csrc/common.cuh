@@ -22,6 +22,7 @@ struct ExecImage {
     int ctrl_slot, xe_slot, qe_slot, x_slot;
     int fq_state_dep;
     int max_it;
+    unsigned zero_off;         // byte offset of a slot INIT keeps at 0.0 (0: the model needs none)
     double rtol2;              // (relative Newton tolerance)^2
     double adot[16];
     double bw[3];

@@ -41,15 +41,15 @@ enum XCode : unsigned {
     // tier 1 (op < 4)
     X_NS1 = 0, X_FMA_NWN, X_MUL_NW, X_SQR_W,
     // tier 2 (op < 16)
-    X_FMA_NWW, X_FMA_WWN, X_FMA_WWW, X_FMS_NWN, X_FMS_NWW, X_FNMA_NWN, X_MUL_WW, X_ADD_NW, X_SUB_WW, X_NS2, X_NB1, X_QACC,
+    X_FMA_NWW, X_FMA_WWN, X_FMA_WWW, X_FMS_NWN, X_FMS_NWW, X_FNMA_NWN, X_MUL_WW, X_ADD_NW, X_NS1L, X_NS2, X_NB1, X_QACC,
     // tier 3: remaining three-wide point ops, by operand pattern (N narrow, W wide) ...
-    X_FMS_WWN, X_FMS_WWW, X_FNMA_NWW, X_FNMA_WWN, X_FNMA_WWW, X_ADD_WW, X_SUB_NW, X_SUB_WN, X_DIV_NW, X_DIV_WN, X_DIV_WW,
+    X_FMS_WWN, X_FMS_WWW, X_FNMA_NWW, X_FNMA_WWN, X_FNMA_WWW, X_ADD_WW, X_SUB_WW, X_SUB_NW, X_SUB_WN, X_DIV_NW, X_DIV_WN, X_DIV_WW,
     X_NEG_W, X_RCP_W, X_ABS_W, X_MOV_W, X_BC_N, X_MIN_NW, X_MIN_WW, X_MAX_NW, X_MAX_WW, X_COLD_W,
     // ... scalar ops (pro / elem / g tapes; flags: operand a/b/c lives in the constant pool) ...
     X_FMA1, X_FMS1, X_FNMA1, X_MUL1, X_ADD1, X_SUB1, X_DIV1, X_SQR1, X_NEG1, X_RCP1, X_ABS1, X_MOV1,
     X_MIN1, X_MAX1, X_COLD1,
     // ... structure
-    X_INIT, X_LDCTRL, X_NB2, X_NB3, X_NS3, X_ELEM_END, X_XEND, X_END,
+    X_INIT, X_LDCTRL, X_NB2, X_NB3, X_NS3, X_NS2L, X_NS3L, X_ELEM_END, X_XEND, X_END,
     X_COUNT
 };
 constexpr unsigned X_TIER1 = 4, X_TIER2 = 16;
@@ -57,7 +57,7 @@ constexpr unsigned X_TIER1 = 4, X_TIER2 = 16;
 // Instruction layout (uint4 units; `pcw` indexes c_prog):
 //   data ops    w0 = { op, dst, a, b }            w1 = { c, flags, cold opcode, - }                 length 2
 //   NBk         w0 = { op, x_o[0..2] }                                                             length 2
-//   NSk         w0 = { op, target pcw, flops, jmask | linear << 16 }
+//   NSk / NSkL  w0 = { op, target pcw, flops, jmask | max_it << 16 }
 //               then x_o[k], f_o[k][3], j_o[k*k][3] packed word by word                          length 1 + ceil(k(4+3k)/4)
 //   QACC        w0 = { op, dst, o0, o1 }          w1 = { o2 }        LDCTRL  w0 = { op, dst, control }
 //   ELEM_END    w0 = { op, target pcw }
@@ -79,13 +79,13 @@ constexpr unsigned US = BLOCK * 8u;                       // bytes between conse
 // ---------------------------------------------------------------------------------------------
 template <int NSB, int MAXNS>
 __device__ __forceinline__ void newton_begin(const unsigned (&xo)[3], char* __restrict__ base, double (&xs)[MAXNS],
-                                             double (&xv)[3][MAXNS])
+                                             double (&zv)[3][MAXNS])
 {
 #pragma unroll
     for (int n = 0; n < NSB; ++n) {
         const double v = LDP(xo[n], 2);
         xs[n] = v;
-        xv[0][n] = xv[1][n] = xv[2][n] = v;
+        zv[0][n] = zv[1][n] = zv[2][n] = 0.0;             // increments z_j = x_j - x(element start)
         STP(xo[n], 0, v);
         STP(xo[n], 1, v);
     }
@@ -102,16 +102,21 @@ struct NsTab {
     }
 };
 
-template <int NSB, int MAXNS>
-__device__ __forceinline__ void newton_step(const ExecImage& img, int pcw, unsigned jmask, bool linear,
-                                            char* __restrict__ base, double h, const double (&xs)[MAXNS],
-                                            double (&xv)[3][MAXNS], double& s_prev, bool& conv, bool& failed)
+// One Newton step on the collocation equations in increment form (the rows of the differentiation matrix
+// sum to zero, so  sum_k adot[k][j] x_k = sum_{k>=1} adot[k][j] z_k):
+//     r_j = h f(x_j) - sum_k A_kj z_k,    (A^T (x) I - h blockdiag(df/dx)) dz = r,    z += dz,   x_j = x_s + z_j.
+// MASKED: skip the structurally zero Jacobian entries (bit n*NSB+m of jmask); 1-state blocks always load J.
+// Returns |dz|^2 and |x|^2 for the stop test.
+template <int NSB, int MAXNS, bool MASKED>
+__device__ __forceinline__ void newton_step(const ExecImage& img, int at, unsigned jmask, char* __restrict__ base,
+                                            double h, const double (&xs)[MAXNS], double (&zv)[3][MAXNS], double& sq,
+                                            double& sc)
 {
     constexpr int N = 3 * NSB;
     constexpr int NW = ns_length(NSB) - 1;
     NsTab<NW> tab;
 #pragma unroll
-    for (int i = 0; i < NW; ++i) tab.q[i] = c_prog[pcw + 1 + i];
+    for (int i = 0; i < NW; ++i) tab.q[i] = c_prog[at + 1 + i];
     // table: x_o[NSB] | f_o[NSB][3] | j_o[NSB*NSB][3]
     constexpr int F0 = NSB, J0 = NSB + 3 * NSB;
     double M[N][N], r[N];
@@ -119,9 +124,9 @@ __device__ __forceinline__ void newton_step(const ExecImage& img, int pcw, unsig
     for (int jj = 0; jj < 3; ++jj) {
 #pragma unroll
         for (int n = 0; n < NSB; ++n) {
-            double lin = img.adot[jj + 1] * xs[n];                       // adot[0][jj+1]
-#pragma unroll
-            for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
+            double lin = img.adot[4 + jj + 1] * zv[0][n];
+            lin = fma(img.adot[8 + jj + 1], zv[1][n], lin);
+            lin = fma(img.adot[12 + jj + 1], zv[2][n], lin);
             r[jj * NSB + n] = fma(h, LDN(tab[F0 + 3 * n + jj]), -lin);
 #pragma unroll
             for (int kk = 0; kk < 3; ++kk)
@@ -129,7 +134,7 @@ __device__ __forceinline__ void newton_step(const ExecImage& img, int pcw, unsig
                 for (int m = 0; m < NSB; ++m) {
                     const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
                     M[jj * NSB + n][kk * NSB + m] = a;
-                    if (kk == jj && ((jmask >> (n * NSB + m)) & 1u))
+                    if (kk == jj && (!MASKED || ((jmask >> (n * NSB + m)) & 1u)))
                         M[jj * NSB + n][kk * NSB + m] = fma(-h, LDN(tab[J0 + 3 * (n * NSB + m) + jj]), a);
                 }
         }
@@ -137,27 +142,20 @@ __device__ __forceinline__ void newton_step(const ExecImage& img, int pcw, unsig
 
     lu_solve_inplace<N>(M, r);
 
-    double sq = 0.0, sc = 0.0;
+    sq = 0.0;
+    sc = 0.0;
 #pragma unroll
     for (int kk = 0; kk < 3; ++kk)
 #pragma unroll
         for (int n = 0; n < NSB; ++n) {
-            const double dx = r[kk * NSB + n];
-            const double xn = xv[kk][n] + dx;
-            xv[kk][n] = xn;
+            const double dz = r[kk * NSB + n];
+            const double zn = zv[kk][n] + dz;
+            const double xn = xs[n] + zn;
+            zv[kk][n] = zn;
             STP(tab[n], kk, xn);
-            sq = fma(dx, dx, sq);
+            sq = fma(dz, dz, sq);
             sc = fma(xn, xn, sc);
         }
-    // stop when the step is below tolerance, or when the contraction rate seen so far bounds the
-    // remaining error below it:  |dx_k|^2 / |dx_{k-1}| <= rtol * |X|.  A linear block is exact after
-    // one step.
-    const double lim = img.rtol2 * fmax(sc, 1.0);
-    const bool bad = !(sq <= DBL_MAX);                        // inf or nan
-    const bool ok = linear || (sq <= lim) || (sq * sq <= lim * s_prev && sq <= 0.01 * s_prev);
-    s_prev = sq;
-    if (bad) failed = true;
-    if (ok || bad) conv = true;
 }
 
 // operand loaders of the point ops: N = narrow (one load), W = wide (three loads, 1 KiB apart)
@@ -302,27 +300,48 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
 
         // ---- the scenario's program ----
         bool failed = false, conv = false;
-        unsigned my_iters = 0, my_flops = 0;
-        double xs[MAXNS], xv[3][MAXNS];
+        unsigned long long my_acc = 0;                     // Newton iterations << 40 | algorithmic flops
+        double xs[MAXNS], zv[3][MAXNS];
         double s_prev = 0.0;
         int it = 0, e = 0;
         int pcw = 0;                                       // uint4 index of the next instruction
-#define X_NS_CASE(K)                                                                                            \
+// NS: w0 = { op, target pcw, iteration-and-flop increment, jmask | max_it << 16 }.  Stop when the step is below
+// tolerance, or when the contraction rate seen so far bounds the remaining error below it:
+// |dz_k|^2 / |dz_{k-1}| <= rtol |X|  (with |dz_k| <= 0.1 |dz_{k-1}|).  A non-finite step never passes the test:
+// the scenario runs into the iteration cap and is reported failed.
+#define X_NS_CASE(K, MASKED)                                                                                    \
     {                                                                                                           \
         const int at = pcw - 2;                                                                                 \
         pcw = at + ns_length(K);                                                                                \
-        if (!conv) { ++my_iters; my_flops += w0.z; }                                                            \
-        newton_step<K, MAXNS>(img, at, w0.w & 0xFFFFu, (w0.w >> 16) != 0, base, h, xs, xv, s_prev, conv, failed); \
+        if (!conv) my_acc += ((1ull << 40) | w0.z);                                                             \
+        double sq, sc;                                                                                          \
+        newton_step<K, MAXNS, MASKED>(img, at, w0.w & 0xFFFFu, base, h, xs, zv, sq, sc);                        \
+        const double lim = fma(img.rtol2, sc, img.rtol2);                                                       \
+        const bool ok = (sq <= lim) | ((sq * sq <= lim * s_prev) & (sq <= 0.01 * s_prev));                      \
+        s_prev = sq;                                                                                            \
+        conv = conv | ok;                                                                                       \
         ++cnt_warp_iters;                                                                                       \
         ++it;                                                                                                   \
-        if (!__all_sync(0xffffffffu, conv) && it < img.max_it) pcw = (int)w0.y;     /* back to the point ops */  \
-        else if (!conv) failed = true;                                                                          \
+        if (!__all_sync(0xffffffffu, conv) && it < (int)(w0.w >> 16)) pcw = (int)w0.y;                          \
+        else failed = failed | !conv;                                                                           \
+    }                                                                                                           \
+    break;
+// NSL: the block is linear in its own states (its Jacobian does not depend on them): one exact step
+#define X_NSL_CASE(K, MASKED)                                                                                   \
+    {                                                                                                           \
+        const int at = pcw - 2;                                                                                 \
+        pcw = at + ns_length(K);                                                                                \
+        my_acc += ((1ull << 40) | w0.z);                                                                        \
+        double sq, sc;                                                                                          \
+        newton_step<K, MAXNS, MASKED>(img, at, w0.w & 0xFFFFu, base, h, xs, zv, sq, sc);                        \
+        failed = failed | !(sq <= DBL_MAX);                                                                     \
+        ++cnt_warp_iters;                                                                                       \
     }                                                                                                           \
     break;
 #define X_NB_CASE(K)                                                                                            \
     {                                                                                                           \
         const unsigned xo[3] = {w0.y, w0.z, w0.w};                                                              \
-        newton_begin<K, MAXNS>(xo, base, xs, xv);                                                               \
+        newton_begin<K, MAXNS>(xo, base, xs, zv);                                                               \
         conv = false; s_prev = 0.0; it = 0;                                                                     \
     }                                                                                                           \
     break;
@@ -332,7 +351,7 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
             const unsigned op = w0.x;
             if (op < X_TIER1) {
                 switch (op) {
-                case X_NS1: X_NS_CASE(1)
+                case X_NS1: X_NS_CASE(1, false)
                 case X_FMA_NWN: X_TER(N, W, N, fma(a, b, c))
                 case X_MUL_NW: X_BIN(N, W, a * b)
                 case X_SQR_W: X_UN(W, a * a)
@@ -347,11 +366,11 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
                 case X_FNMA_NWN: X_TER(N, W, N, fma(-a, b, c))
                 case X_MUL_WW: X_BIN(W, W, a * b)
                 case X_ADD_NW: X_BIN(N, W, a + b)
-                case X_SUB_WW: X_BIN(W, W, a - b)
                 case X_NS2:
-                    if constexpr (MAXNS >= 2) X_NS_CASE(2)
+                    if constexpr (MAXNS >= 2) X_NS_CASE(2, true)
                     break;
                 case X_NB1: X_NB_CASE(1)
+                case X_NS1L: X_NSL_CASE(1, false)
                 case X_QACC: {                             // quadrature: x_q += h * sum_j bw_j fq(x_j) at the converged points
                     const unsigned o2 = c_prog[pcw - 1].x;
                     double acc = img.bw[0] * LDN(w0.z);
@@ -369,6 +388,7 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
                 case X_FNMA_WWN: X_TER(W, W, N, fma(-a, b, c))
                 case X_FNMA_WWW: X_TER(W, W, W, fma(-a, b, c))
                 case X_ADD_WW: X_BIN(W, W, a + b)
+                case X_SUB_WW: X_BIN(W, W, a - b)
                 case X_SUB_NW: X_BIN(N, W, a - b)
                 case X_SUB_WN: X_BIN(W, N, a - b)
                 case X_DIV_NW: X_BIN(N, W, a / b)
@@ -411,6 +431,7 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
                     for (int n = 0; n < img.ns; ++n) x0v[n] = vm_ld(vm, tab_x0[n]);
                     for (int n = 0; n < img.ns; ++n) S[(img.x_slot + 3 * n + 2) * BLOCK] = x0v[n];
                     for (int q = 0; q < img.nq; ++q) S[(img.qe_slot + q) * BLOCK] = vm_ld(vm, tab_q0[q]);
+                    if (img.zero_off) STN(img.zero_off, 0.0);
                     break;
                 }
                 case X_LDCTRL: {                           // control w0.z of finite element e -> slot w0.y
@@ -429,8 +450,14 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
                 case X_NB3:
                     if constexpr (MAXNS >= 3) X_NB_CASE(3)
                     break;
+                case X_NS2L:
+                    if constexpr (MAXNS >= 2) X_NSL_CASE(2, true)
+                    break;
+                case X_NS3L:
+                    if constexpr (MAXNS >= 3) X_NSL_CASE(3, true)
+                    break;
                 case X_NS3:
-                    if constexpr (MAXNS >= 3) X_NS_CASE(3)
+                    if constexpr (MAXNS >= 3) X_NS_CASE(3, true)
                     break;
                 case X_ELEM_END:
                     if (++e < img.nfe) pcw = (int)w0.y;
@@ -444,6 +471,7 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
             }
         }
 #undef X_NS_CASE
+#undef X_NSL_CASE
 #undef X_NB_CASE
 
         // ---- indicator, outputs ----
@@ -458,8 +486,8 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
         double wv = 0.0;
         if (valid && feasible) wv = la.w ? __ldg(la.w + j) : 1.0 / (double)la.n_t;
         if (valid) {
-            cnt_iters += my_iters;
-            cnt_flops += my_flops;
+            cnt_iters += my_acc >> 40;
+            cnt_flops += my_acc & ((1ull << 40) - 1);
             cnt_failed += failed ? 1u : 0u;
             cnt_done += 1u;
         }

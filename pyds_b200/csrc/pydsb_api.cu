@@ -255,6 +255,13 @@ int build_program(const Sections& secs, bool sens, Program& P)
             if (!(refs[0] & REF_WIDE)) return fail(PYDSB_ERR_INVALID, "point tape writes a narrow slot");
         }
     }
+    g.zero_off = 0;
+    if (!sens) {
+        // a 1-state block with an identically zero Jacobian reads it from a slot INIT keeps at 0.0
+        bool need_zero = false;
+        for (int b = 0; b < g.n_blocks; ++b) need_zero = need_zero || (g.blk_ns[b] == 1 && !(g.blk_jmask[b] & 1u));
+        if (need_zero) g.zero_off = (unsigned)g.n_units * BLOCK * 8u;
+    }
     if (!sens) {
         // program 0: assemble the unified per-scenario program of feas_kernel
         AsmInput in{};
@@ -322,7 +329,7 @@ int build_program(const Sections& secs, bool sens, Program& P)
     }
     g.off_land = o; o = align_up(o + land, 128);
     g.off_slots = o;
-    int units = g.n_units;
+    int units = g.n_units + (g.zero_off ? 1 : 0);
     if (sens) units += (g.ns + g.nq + g.ng) * g.nz;        // Sx, Sq, Dc blocks of sens_kernel
     o += units * BLOCK * 8;
     g.smem_bytes = o;
