@@ -34,11 +34,12 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """``defines``/``out``: development variants (tools/build_variant.py), loaded through PYDSB_LIB."""
+    if not force and not is_stale() and out == LIB:
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a gcc without its spec files; let nvcc pick the system one
     env.pop("CC", None)
@@ -48,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -38,9 +38,11 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if _build.is_stale():
-        _build.build()
+    path = os.environ.get("PYDSB_LIB")          # development: a variant built by tools/build_variant.py
+    if not path:
+        path = _build.LIB
+        if _build.is_stale():
+            _build.build()
     L = ctypes.CDLL(path)
     vp, ll, dp, ci = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int
     L.pydsb_last_error.restype = ctypes.c_char_p

@@ -22,6 +22,7 @@ struct AsmInput {
     int q_npt;
     int nce, ctrl_slot, nq, qe_slot, n_units;
     const uint16_t* fq_refs;                   // [nq] reference of every quadrature integrand
+    int spt;                                   // scenarios per thread: slot stride = spt * US bytes
     const ExecImage* img;                      // resolved per-block offsets: blk_x_o, blk_f_o, blk_j_o, blk_jmask
 };
 
@@ -39,7 +40,7 @@ public:
             if (!scalar_op(in.pro[i])) return false;
         emit(X_INIT);
         const int l_elem = pc();
-        for (int c = 0; c < in.nce; ++c) emit(X_LDCTRL, (uint32_t)(in.ctrl_slot + c) * US, (uint32_t)c);
+        for (int c = 0; c < in.nce; ++c) emit(X_LDCTRL, (uint32_t)(in.ctrl_slot + c) * US * (uint32_t)in.spt, (uint32_t)c);
         for (int i = 0; i < in.n_elem; ++i)
             if (!scalar_op(in.elem[i])) return false;
         int pos = 0;
@@ -78,16 +79,16 @@ public:
             const unsigned r = in.fq_refs[q];
             if (r == REF_NONE) continue;
             if (r & REF_CONST) return fail("constant reference in the quadrature table");
-            const uint32_t o = slot_off(r), st = (r & REF_WIDE) ? US : 0u;
+            const uint32_t o = slot_off(r), st = (r & REF_WIDE) ? US * (uint32_t)in.spt : 0u;
             if (!check_slot(r)) return false;
-            emit(X_QACC, (uint32_t)(in.qe_slot + q) * US, o, o + st, o + 2 * st);
+            emit(X_QACC, (uint32_t)(in.qe_slot + q) * US * (uint32_t)in.spt, o, o + st, o + 2 * st);
         }
         emit(X_ELEM_END, (uint32_t)l_elem);
         emit(X_XEND);
         for (int i = 0; i < in.n_g; ++i)
             if (!scalar_op(in.g[i])) return false;
         emit(X_END);
-        if (pc() > 2 * MAX_PROG) return fail("program longer than the constant-bank window");
+        if (pc() > 2 * MAX_PROG - 2) return fail("program longer than the constant-bank window");
         return true;
     }
 
@@ -104,7 +105,7 @@ private:
         const uint32_t v[8] = {x, y, z, w, x1, y1, z1, 0};
         words.insert(words.end(), v, v + 8);
     }
-    static uint32_t slot_off(unsigned ref) { return (ref & REF_MASK) * US; }
+    uint32_t slot_off(unsigned ref) const { return (ref & REF_MASK) * US * (uint32_t)in_->spt; }
     bool check_slot(unsigned ref)
     {
         if ((int)(ref & REF_MASK) + ((ref & REF_WIDE) ? 2 : 0) >= in_->n_units) return fail("slot out of range");

@@ -23,6 +23,8 @@ struct ExecImage {
     int fq_state_dep;
     int max_it;
     unsigned zero_off;         // byte offset of a slot INIT keeps at 0.0 (0: the model needs none)
+    int zero_slot;
+    int spt;                   // scenarios per thread the offsets of this image are laid out for
     double rtol2;              // (relative Newton tolerance)^2
     double adot[16];
     double bw[3];

@@ -1,9 +1,11 @@
 // Feasibility kernel: collocation state solve + CQAs + big-M indicator + P(feasible) partials.
 //
 // Work decomposition (B200: 148 SMs, persistent CTAs):
-//   tile   = one design point d_i  x  BLOCK consecutive theta samples
+//   tile   = one design point d_i  x  SPT*BLOCK consecutive theta samples
 //   CTA    = BLOCK threads, loops over tiles  t = blockIdx.x, +gridDim.x, ...
-//   thread = one (d_i, theta_j) scenario for the whole pipeline
+//   thread = SPT (1 or 2) (d_i, theta_j) scenarios for the whole pipeline; with SPT = 2 the two scenarios of
+//            a thread sit side by side in the register file (one LDS.128 / STS.128 moves both) and share
+//            every fetch, dispatch and address of the interpreter
 //
 // Per scenario (what the reference does inside one GAMS/CONOPT solve per design point,
 // pyds/run.py:55-67 + pyds/solver.py:50-55, for fixed controls) the thread runs ONE program, assembled
@@ -64,30 +66,41 @@ constexpr unsigned X_TIER1 = 4, X_TIER2 = 16;
 __host__ __device__ constexpr int ns_words(int nsb) { return nsb + 3 * nsb + 3 * nsb * nsb; }
 __host__ __device__ constexpr int ns_length(int nsb) { return 1 + (ns_words(nsb) + 3) / 4; }
 
-constexpr unsigned US = BLOCK * 8u;                       // bytes between consecutive slots of one thread
+constexpr unsigned US = BLOCK * 8u;                       // bytes between consecutive slots, per scenario of a thread
 
-#define LDN(o) (*reinterpret_cast<const double*>(base + (o)))
-#define LDP(o, p) (*reinterpret_cast<const double*>(base + (o) + (p) * US))
-#define STN(o, v) (*reinterpret_cast<double*>(base + (o)) = (v))
-#define STP(o, p, v) (*reinterpret_cast<double*>(base + (o) + (p) * US) = (v))
+// The SPT scenarios of one thread, adjacent in the shared-memory register file: S[slot][thread][scenario].
+template <int SPT>
+struct alignas(8 * SPT) Vec {
+    double v[SPT];
+};
+
+#define LDV(o) (*reinterpret_cast<const VecT*>(base + (o)))
+#define LDVP(o, p) (*reinterpret_cast<const VecT*>(base + (o) + (p) * USP))
+#define STV(o, val) (*reinterpret_cast<VecT*>(base + (o)) = (val))
+#define STVP(o, p, val) (*reinterpret_cast<VecT*>(base + (o) + (p) * USP) = (val))
 
 // ---------------------------------------------------------------------------------------------
 // Newton solve of one block (NSB states, N = 3*NSB collocation unknowns) on one finite element.
 // newton_begin: start from the end point of the previous element (the INIT op seeds point 2 with x(0)).
 // newton_step:  residual and Jacobian assembled in registers from the block's point-op outputs, dense LU
-//               without pivoting (register resident), update, stop test.
+//               without pivoting (register resident), update.
 // ---------------------------------------------------------------------------------------------
-template <int NSB, int MAXNS>
-__device__ __forceinline__ void newton_begin(const unsigned (&xo)[3], char* __restrict__ base, double (&xs)[MAXNS],
-                                             double (&zv)[3][MAXNS])
+template <int NSB, int MAXNS, int SPT>
+__device__ __forceinline__ void newton_begin(const unsigned (&xo)[3], char* __restrict__ base, double (&xs)[SPT][MAXNS],
+                                             double (&zv)[SPT][3][MAXNS])
 {
+    typedef Vec<SPT> VecT;
+    constexpr unsigned USP = US * SPT;
 #pragma unroll
     for (int n = 0; n < NSB; ++n) {
-        const double v = LDP(xo[n], 2);
-        xs[n] = v;
-        zv[0][n] = zv[1][n] = zv[2][n] = 0.0;             // increments z_j = x_j - x(element start)
-        STP(xo[n], 0, v);
-        STP(xo[n], 1, v);
+        const VecT v = LDVP(xo[n], 2);
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            xs[s][n] = v.v[s];
+            zv[s][0][n] = zv[s][1][n] = zv[s][2][n] = 0.0;    // increments z_j = x_j - x(element start)
+        }
+        STVP(xo[n], 0, v);
+        STVP(xo[n], 1, v);
     }
 }
 
@@ -106,12 +119,13 @@ struct NsTab {
 // sum to zero, so  sum_k adot[k][j] x_k = sum_{k>=1} adot[k][j] z_k):
 //     r_j = h f(x_j) - sum_k A_kj z_k,    (A^T (x) I - h blockdiag(df/dx)) dz = r,    z += dz,   x_j = x_s + z_j.
 // MASKED: skip the structurally zero Jacobian entries (bit n*NSB+m of jmask); 1-state blocks always load J.
-// Returns |dz|^2 and |x|^2 for the stop test.
-template <int NSB, int MAXNS, bool MASKED>
+// Returns |dz|^2 and |x|^2 per scenario for the stop test.
+template <int NSB, int MAXNS, bool MASKED, int SPT>
 __device__ __forceinline__ void newton_step(const ExecImage& img, int at, unsigned jmask, char* __restrict__ base,
-                                            double h, const double (&xs)[MAXNS], double (&zv)[3][MAXNS], double& sq,
-                                            double& sc)
+                                            double h, const double (&xs)[SPT][MAXNS], double (&zv)[SPT][3][MAXNS],
+                                            double (&sq)[SPT], double (&sc)[SPT])
 {
+    typedef Vec<SPT> VecT;
     constexpr int N = 3 * NSB;
     constexpr int NW = ns_length(NSB) - 1;
     NsTab<NW> tab;
@@ -119,94 +133,166 @@ __device__ __forceinline__ void newton_step(const ExecImage& img, int at, unsign
     for (int i = 0; i < NW; ++i) tab.q[i] = c_prog[at + 1 + i];
     // table: x_o[NSB] | f_o[NSB][3] | j_o[NSB*NSB][3]
     constexpr int F0 = NSB, J0 = NSB + 3 * NSB;
-    double M[N][N], r[N];
+    // SPT = 2: one 128-bit load serves both scenarios, so the operands are fetched up front; SPT = 1 loads each
+    // operand where the assembly consumes it (the 6x6 / 9x9 systems have no registers to spare)
+    constexpr bool PRE = SPT > 1;
+    VecT fv[PRE ? NSB : 1][3], jv[PRE ? NSB * NSB : 1][3];
+    if constexpr (PRE) {
 #pragma unroll
-    for (int jj = 0; jj < 3; ++jj) {
+        for (int n = 0; n < NSB; ++n)
 #pragma unroll
-        for (int n = 0; n < NSB; ++n) {
-            double lin = img.adot[4 + jj + 1] * zv[0][n];
-            lin = fma(img.adot[8 + jj + 1], zv[1][n], lin);
-            lin = fma(img.adot[12 + jj + 1], zv[2][n], lin);
-            r[jj * NSB + n] = fma(h, LDN(tab[F0 + 3 * n + jj]), -lin);
+            for (int jj = 0; jj < 3; ++jj) fv[n][jj] = LDV(tab[F0 + 3 * n + jj]);
 #pragma unroll
-            for (int kk = 0; kk < 3; ++kk)
+        for (int i = 0; i < NSB * NSB; ++i)
 #pragma unroll
-                for (int m = 0; m < NSB; ++m) {
-                    const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
-                    M[jj * NSB + n][kk * NSB + m] = a;
-                    if (kk == jj && (!MASKED || ((jmask >> (n * NSB + m)) & 1u)))
-                        M[jj * NSB + n][kk * NSB + m] = fma(-h, LDN(tab[J0 + 3 * (n * NSB + m) + jj]), a);
-                }
-        }
+            for (int jj = 0; jj < 3; ++jj)
+                if (!MASKED || ((jmask >> i) & 1u)) jv[i][jj] = LDV(tab[J0 + 3 * i + jj]);
     }
-
-    lu_solve_inplace<N>(M, r);
-
-    sq = 0.0;
-    sc = 0.0;
+    VecT xn[NSB][3];
 #pragma unroll
-    for (int kk = 0; kk < 3; ++kk)
+    for (int s = 0; s < SPT; ++s) {
+        double M[N][N], r[N];
 #pragma unroll
-        for (int n = 0; n < NSB; ++n) {
-            const double dz = r[kk * NSB + n];
-            const double zn = zv[kk][n] + dz;
-            const double xn = xs[n] + zn;
-            zv[kk][n] = zn;
-            STP(tab[n], kk, xn);
-            sq = fma(dz, dz, sq);
-            sc = fma(xn, xn, sc);
+        for (int jj = 0; jj < 3; ++jj) {
+#pragma unroll
+            for (int n = 0; n < NSB; ++n) {
+                double lin = img.adot[4 + jj + 1] * zv[s][0][n];
+                lin = fma(img.adot[8 + jj + 1], zv[s][1][n], lin);
+                lin = fma(img.adot[12 + jj + 1], zv[s][2][n], lin);
+                const double fval = PRE ? fv[PRE ? n : 0][jj].v[s] : LDV(tab[F0 + 3 * n + jj]).v[s];
+                r[jj * NSB + n] = fma(h, fval, -lin);
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+                    for (int m = 0; m < NSB; ++m) {
+                        const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
+                        M[jj * NSB + n][kk * NSB + m] = a;
+                        if (kk == jj && (!MASKED || ((jmask >> (n * NSB + m)) & 1u)))
+                            M[jj * NSB + n][kk * NSB + m] =
+                                fma(-h, PRE ? jv[PRE ? n * NSB + m : 0][jj].v[s] : LDV(tab[J0 + 3 * (n * NSB + m) + jj]).v[s], a);
+                    }
+            }
         }
+
+        lu_solve_inplace<N>(M, r);
+
+        sq[s] = 0.0;
+        sc[s] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+            for (int n = 0; n < NSB; ++n) {
+                const double dz = r[kk * NSB + n];
+                const double zn = zv[s][kk][n] + dz;
+                const double x = xs[s][n] + zn;
+                zv[s][kk][n] = zn;
+                xn[n][kk].v[s] = x;
+                sq[s] = fma(dz, dz, sq[s]);
+                sc[s] = fma(x, x, sc[s]);
+            }
+    }
+    constexpr unsigned USP = US * SPT;
+#pragma unroll
+    for (int n = 0; n < NSB; ++n)
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) STVP(tab[n], kk, xn[n][kk]);
 }
 
-// operand loaders of the point ops: N = narrow (one load), W = wide (three loads, 1 KiB apart)
-#define XLD_N(v, o) const double v##0 = LDN(o); const double v##1 = v##0, v##2 = v##0;
-#define XLD_W(v, o) const double v##0 = LDP(o, 0), v##1 = LDP(o, 1), v##2 = LDP(o, 2);
-#define XST3(o) STP(o, 0, r0); STP(o, 1, r1); STP(o, 2, r2);
+// operand loaders of the point ops: N = narrow (one load), W = wide (three loads, one slot apart)
+#define XLD_N(v, o) const VecT v##0 = LDV(o); const VecT v##1 = v##0, v##2 = v##0;
+#define XLD_W(v, o) const VecT v##0 = LDVP(o, 0), v##1 = LDVP(o, 1), v##2 = LDVP(o, 2);
+#define XST3(o) STVP(o, 0, r0); STVP(o, 1, r1); STVP(o, 2, r2);
 #define X_TER(PA, PB, PC, expr)                                       \
     {                                                                 \
         const unsigned oc = c_prog[pcw - 1].x;                        \
         XLD_##PA(a, w0.z) XLD_##PB(b, w0.w) XLD_##PC(c, oc)           \
-        double a, b, c;                                               \
-        a = a0; b = b0; c = c0; const double r0 = (expr);             \
-        a = a1; b = b1; c = c1; const double r1 = (expr);             \
-        a = a2; b = b2; c = c2; const double r2 = (expr);             \
+        VecT r0, r1, r2;                                              \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {             \
+            double a, b, c;                                           \
+            a = a0.v[s]; b = b0.v[s]; c = c0.v[s]; r0.v[s] = (expr);  \
+            a = a1.v[s]; b = b1.v[s]; c = c1.v[s]; r1.v[s] = (expr);  \
+            a = a2.v[s]; b = b2.v[s]; c = c2.v[s]; r2.v[s] = (expr);  \
+        }                                                             \
         XST3(w0.y)                                                    \
     }                                                                 \
     break;
 #define X_BIN(PA, PB, expr)                                           \
     {                                                                 \
         XLD_##PA(a, w0.z) XLD_##PB(b, w0.w)                           \
-        double a, b;                                                  \
-        a = a0; b = b0; const double r0 = (expr);                     \
-        a = a1; b = b1; const double r1 = (expr);                     \
-        a = a2; b = b2; const double r2 = (expr);                     \
+        VecT r0, r1, r2;                                              \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {             \
+            double a, b;                                              \
+            a = a0.v[s]; b = b0.v[s]; r0.v[s] = (expr);               \
+            a = a1.v[s]; b = b1.v[s]; r1.v[s] = (expr);               \
+            a = a2.v[s]; b = b2.v[s]; r2.v[s] = (expr);               \
+        }                                                             \
         XST3(w0.y)                                                    \
     }                                                                 \
     break;
 #define X_UN(PA, expr)                                                \
     {                                                                 \
         XLD_##PA(a, w0.z)                                             \
-        double a;                                                     \
-        a = a0; const double r0 = (expr);                             \
-        a = a1; const double r1 = (expr);                             \
-        a = a2; const double r2 = (expr);                             \
+        VecT r0, r1, r2;                                              \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {             \
+            double a;                                                 \
+            a = a0.v[s]; r0.v[s] = (expr);                            \
+            a = a1.v[s]; r1.v[s] = (expr);                            \
+            a = a2.v[s]; r2.v[s] = (expr);                            \
+        }                                                             \
         XST3(w0.y)                                                    \
     }                                                                 \
     break;
 // scalar ops: an operand is a slot of this thread or an entry of the (block-uniform) constant pool
-#define X1_A const double a = *reinterpret_cast<const double*>(((fl & 1u) ? cz : base) + w0.z);
-#define X1_B const double b = *reinterpret_cast<const double*>(((fl & 2u) ? cz : base) + w0.w);
-#define X1_C const double c = *reinterpret_cast<const double*>(((fl & 4u) ? cz : base) + w1.x);
+#define X1_OPND(n, bit, off)                                                             \
+    VecT n##v;                                                                           \
+    if (fl & (bit)) {                                                                    \
+        const double kc = *reinterpret_cast<const double*>(cz + (off));                  \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) n##v.v[s] = kc;                  \
+    } else n##v = LDV(off);
 #define X1_FL const uint4 w1 = c_prog[pcw - 1]; const unsigned fl = w1.y;
-#define X1_TER(expr) { X1_FL X1_A X1_B X1_C STN(w0.y, (expr)); } break;
-#define X1_BIN(expr) { X1_FL X1_A X1_B STN(w0.y, (expr)); } break;
-#define X1_UN(expr) { X1_FL X1_A STN(w0.y, (expr)); } break;
+#define X1_TER(expr)                                                                     \
+    {                                                                                    \
+        X1_FL X1_OPND(a, 1u, w0.z) X1_OPND(b, 2u, w0.w) X1_OPND(c, 4u, w1.x)             \
+        VecT rv;                                                                         \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                \
+            const double a = av.v[s], b = bv.v[s], c = cv.v[s];                          \
+            rv.v[s] = (expr);                                                            \
+        }                                                                                \
+        STV(w0.y, rv);                                                                   \
+    }                                                                                    \
+    break;
+#define X1_BIN(expr)                                                                     \
+    {                                                                                    \
+        X1_FL X1_OPND(a, 1u, w0.z) X1_OPND(b, 2u, w0.w)                                  \
+        VecT rv;                                                                         \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                \
+            const double a = av.v[s], b = bv.v[s];                                       \
+            rv.v[s] = (expr);                                                            \
+        }                                                                                \
+        STV(w0.y, rv);                                                                   \
+    }                                                                                    \
+    break;
+#define X1_UN(expr)                                                                      \
+    {                                                                                    \
+        X1_FL X1_OPND(a, 1u, w0.z)                                                       \
+        VecT rv;                                                                         \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                \
+            const double a = av.v[s];                                                    \
+            rv.v[s] = (expr);                                                            \
+        }                                                                                \
+        STV(w0.y, rv);                                                                   \
+    }                                                                                    \
+    break;
 
-// MAXNS = largest block of coupled states (1..3).
-template <int MAXNS>
-__global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2)))
+// MAXNS = largest block of coupled states (1..3); SPT = scenarios per thread (2 only with MAXNS = 1: the
+// Newton matrices of two scenarios have to fit the register file).
+template <int MAXNS, int SPT>
+__global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))))
     feas_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ LaunchArgs la)
 {
+    typedef Vec<SPT> VecT;
+    constexpr unsigned USP = US * SPT;                                  // bytes between consecutive slots
+    constexpr int TILE = SPT * BLOCK;                                   // theta rows per tile
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -215,8 +301,8 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
     double* red = reinterpret_cast<double*>(smem + 16);                 // [BLOCK/32]
     double* cpool = reinterpret_cast<double*>(smem + img.off_const) + 1;   // cpool[-1] = 0.0
     uint16_t* tabs = reinterpret_cast<uint16_t*>(smem + img.off_tabs);
-    double* land = reinterpret_cast<double*>(smem + img.off_land);      // [BLOCK*p_dim]
-    double* S = reinterpret_cast<double*>(smem + img.off_slots) + tid;
+    double* land = reinterpret_cast<double*>(smem + img.off_land);      // [TILE*p_dim]
+    double* S = reinterpret_cast<double*>(smem + img.off_slots) + tid * SPT;   // S[slot * TILE + s]
 
     // ---- stage constants and reference tables in shared memory (once per CTA) ----
     for (int i = tid; i < img.n_const; i += BLOCK) cpool[i] = img.consts[i];
@@ -236,9 +322,12 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
     const uint16_t* tab_g = tab_zfix + img.nz;
     const uint16_t* tab_cmap = tab_g + img.ng;
 
-    VM vm;
-    vm.S = S;
-    vm.cpool = cpool;
+    // cold-path access through 14-bit references (tape_vm.cuh): slot of scenario s, or constant pool
+    auto slot = [&](int idx, int s) -> double& { return S[(size_t)idx * TILE + s]; };
+    auto ref_ld = [&](unsigned ref, int s) -> double {
+        if (ref & REF_CONST) return (ref == REF_NONE) ? 0.0 : cpool[ref & REF_MASK];
+        return S[(size_t)(ref & REF_MASK) * TILE + s];
+    };
 
     char* const base = reinterpret_cast<char*>(S);
     const char* const cz = reinterpret_cast<const char*>(cpool - 1);    // constant operands: (index + 1) * 8
@@ -250,9 +339,9 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
     unsigned phase = 0;
 
     auto tile_rows = [&](long long t) -> int {
-        const long long j0 = (t % la.n_tiles) * (long long)BLOCK;
+        const long long j0 = (t % la.n_tiles) * (long long)TILE;
         const long long rem = la.n_t - j0;
-        return rem < BLOCK ? (int)rem : BLOCK;
+        return rem < TILE ? (int)rem : TILE;
     };
     auto tile_tma = [&](int rows) -> bool {
         return la.theta_tma_ok && ((rows * p_dim * (int)sizeof(double)) % 16 == 0);
@@ -260,7 +349,7 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
     auto issue = [&](long long t) {
         const int rows = tile_rows(t);
         if (tile_tma(rows)) {
-            const long long j0 = (t % la.n_tiles) * (long long)BLOCK;
+            const long long j0 = (t % la.n_tiles) * (long long)TILE;
             const unsigned bytes = (unsigned)(rows * p_dim * sizeof(double));
             mbar_expect_tx(&mbar[0], bytes);
             tma_load_1d(land, la.theta + j0 * p_dim, bytes, &mbar[0]);
@@ -275,55 +364,81 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
 
     for (; t < total; t += gridDim.x) {
         const long long i_d = t / la.n_tiles;
-        const long long j0 = (t % la.n_tiles) * (long long)BLOCK;
+        const long long j0 = (t % la.n_tiles) * (long long)TILE;
         const int rows = tile_rows(t);
-        const bool valid = tid < rows;
-        const int row = valid ? tid : rows - 1;               // idle lanes replay the last row
-        const long long j = j0 + row;
+        bool valid[SPT];
+        long long jj_[SPT];
+        int row[SPT];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            const int r = tid * SPT + s;                   // a thread's scenarios are consecutive theta rows
+            valid[s] = r < rows;
+            row[s] = valid[s] ? r : rows - 1;              // idle lanes replay the last row
+            jj_[s] = j0 + row[s];
+        }
 
         // ---- parameters into the register file (theta from the TMA landing buffer) ----
         if (tile_tma(rows)) {
             mbar_wait(&mbar[0], phase);
             phase ^= 1u;
-            const double* src = land + (size_t)row * p_dim;
-            for (int c = 0; c < p_dim; ++c) S[tab_par[d_dim + c] * BLOCK] = src[c];
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) {
+                const double* src = land + (size_t)row[s] * p_dim;
+                for (int c = 0; c < p_dim; ++c) slot(tab_par[d_dim + c], s) = src[c];
+            }
         } else {
-            const double* src = la.theta + j * p_dim;
-            for (int c = 0; c < p_dim; ++c) S[tab_par[d_dim + c] * BLOCK] = __ldg(src + c);
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) {
+                const double* src = la.theta + jj_[s] * p_dim;
+                for (int c = 0; c < p_dim; ++c) slot(tab_par[d_dim + c], s) = __ldg(src + c);
+            }
         }
-        for (int c = 0; c < d_dim; ++c) S[tab_par[c] * BLOCK] = __ldg(la.d + i_d * d_dim + c);
+        for (int c = 0; c < d_dim; ++c) {
+            const double dv = __ldg(la.d + i_d * d_dim + c);
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) slot(tab_par[c], s) = dv;
+        }
         __syncthreads();                                   // landing buffer and `red` are free again
         {
             const long long nt = t + gridDim.x;            // prefetch the next tile's theta rows
             if (nt < total && tid == 0) issue(nt);
         }
 
-        // ---- the scenario's program ----
-        bool failed = false, conv = false;
-        unsigned long long my_acc = 0;                     // Newton iterations << 40 | algorithmic flops
-        double xs[MAXNS], zv[3][MAXNS];
-        double s_prev = 0.0;
+        // ---- the scenarios' program ----
+        bool failed[SPT], conv[SPT];
+        unsigned long long my_acc[SPT];                    // Newton iterations << 40 | algorithmic flops
+        double xs[SPT][MAXNS], zv[SPT][3][MAXNS];
+        double s_prev[SPT];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) { failed[s] = false; conv[s] = false; my_acc[s] = 0; s_prev[s] = 0.0; }
         int it = 0, e = 0;
         int pcw = 0;                                       // uint4 index of the next instruction
-// NS: w0 = { op, target pcw, iteration-and-flop increment, jmask | max_it << 16 }.  Stop when the step is below
-// tolerance, or when the contraction rate seen so far bounds the remaining error below it:
-// |dz_k|^2 / |dz_{k-1}| <= rtol |X|  (with |dz_k| <= 0.1 |dz_{k-1}|).  A non-finite step never passes the test:
-// the scenario runs into the iteration cap and is reported failed.
+// NS: w0 = { op, target pcw, flops, jmask | max_it << 16 }.  Stop when the step is below tolerance, or when
+// the contraction rate seen so far bounds the remaining error below it:  |dz_k|^2 / |dz_{k-1}| <= rtol |X|
+// (with |dz_k| <= 0.1 |dz_{k-1}|).  A non-finite step never passes the test: the scenario runs into the
+// iteration cap and is reported failed.
 #define X_NS_CASE(K, MASKED)                                                                                    \
     {                                                                                                           \
         const int at = pcw - 2;                                                                                 \
         pcw = at + ns_length(K);                                                                                \
-        if (!conv) my_acc += ((1ull << 40) | w0.z);                                                             \
-        double sq, sc;                                                                                          \
-        newton_step<K, MAXNS, MASKED>(img, at, w0.w & 0xFFFFu, base, h, xs, zv, sq, sc);                        \
-        const double lim = fma(img.rtol2, sc, img.rtol2);                                                       \
-        const bool ok = (sq <= lim) | ((sq * sq <= lim * s_prev) & (sq <= 0.01 * s_prev));                      \
-        s_prev = sq;                                                                                            \
-        conv = conv | ok;                                                                                       \
+        double sq[SPT], sc[SPT];                                                                                \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s)                                                         \
+            if (!conv[s]) my_acc[s] += ((1ull << 40) | w0.z);                                                   \
+        newton_step<K, MAXNS, MASKED, SPT>(img, at, w0.w & 0xFFFFu, base, h, xs, zv, sq, sc);                   \
+        bool all = true;                                                                                        \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                                       \
+            const double lim = fma(img.rtol2, sc[s], img.rtol2);                                                \
+            const bool ok = (sq[s] <= lim) | ((sq[s] * sq[s] <= lim * s_prev[s]) & (sq[s] <= 0.01 * s_prev[s])); \
+            s_prev[s] = sq[s];                                                                                  \
+            conv[s] = conv[s] | ok;                                                                             \
+            all = all & conv[s];                                                                                \
+        }                                                                                                       \
         ++cnt_warp_iters;                                                                                       \
         ++it;                                                                                                   \
-        if (!__all_sync(0xffffffffu, conv) && it < (int)(w0.w >> 16)) pcw = (int)w0.y;                          \
-        else failed = failed | !conv;                                                                           \
+        if (!__all_sync(0xffffffffu, all) && it < (int)(w0.w >> 16)) pcw = (int)w0.y;                           \
+        else {                                                                                                  \
+            _Pragma("unroll") for (int s = 0; s < SPT; ++s) failed[s] = failed[s] | !conv[s];                   \
+        }                                                                                                       \
     }                                                                                                           \
     break;
 // NSL: the block is linear in its own states (its Jacobian does not depend on them): one exact step
@@ -331,18 +446,21 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
     {                                                                                                           \
         const int at = pcw - 2;                                                                                 \
         pcw = at + ns_length(K);                                                                                \
-        my_acc += ((1ull << 40) | w0.z);                                                                        \
-        double sq, sc;                                                                                          \
-        newton_step<K, MAXNS, MASKED>(img, at, w0.w & 0xFFFFu, base, h, xs, zv, sq, sc);                        \
-        failed = failed | !(sq <= DBL_MAX);                                                                     \
+        double sq[SPT], sc[SPT];                                                                                \
+        newton_step<K, MAXNS, MASKED, SPT>(img, at, w0.w & 0xFFFFu, base, h, xs, zv, sq, sc);                   \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                                       \
+            my_acc[s] += ((1ull << 40) | w0.z);                                                                 \
+            failed[s] = failed[s] | !(sq[s] <= DBL_MAX);                                                        \
+        }                                                                                                       \
         ++cnt_warp_iters;                                                                                       \
     }                                                                                                           \
     break;
 #define X_NB_CASE(K)                                                                                            \
     {                                                                                                           \
         const unsigned xo[3] = {w0.y, w0.z, w0.w};                                                              \
-        newton_begin<K, MAXNS>(xo, base, xs, zv);                                                               \
-        conv = false; s_prev = 0.0; it = 0;                                                                     \
+        newton_begin<K, MAXNS, SPT>(xo, base, xs, zv);                                                          \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) { conv[s] = false; s_prev[s] = 0.0; }                   \
+        it = 0;                                                                                                 \
     }                                                                                                           \
     break;
         for (;;) {
@@ -373,10 +491,16 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
                 case X_NS1L: X_NSL_CASE(1, false)
                 case X_QACC: {                             // quadrature: x_q += h * sum_j bw_j fq(x_j) at the converged points
                     const unsigned o2 = c_prog[pcw - 1].x;
-                    double acc = img.bw[0] * LDN(w0.z);
-                    acc = fma(img.bw[1], LDN(w0.w), acc);
-                    acc = fma(img.bw[2], LDN(o2), acc);
-                    STN(w0.y, fma(h, acc, LDN(w0.y)));
+                    const VecT f0 = LDV(w0.z), f1 = LDV(w0.w), f2 = LDV(o2);
+                    VecT q = LDV(w0.y);
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) {
+                        double acc = img.bw[0] * f0.v[s];
+                        acc = fma(img.bw[1], f1.v[s], acc);
+                        acc = fma(img.bw[2], f2.v[s], acc);
+                        q.v[s] = fma(h, acc, q.v[s]);
+                    }
+                    STV(w0.y, q);
                     break;
                 }
                 }
@@ -405,10 +529,15 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
                 case X_MAX_WW: X_BIN(W, W, fmax(a, b))
                 case X_COLD_W: {                           // transcendental, 3-wide; flag bit 0/1: a/b is wide
                     const uint4 w1 = c_prog[pcw - 1];
-                    const unsigned sa = (w1.y & 1u) ? US : 0u, sb = (w1.y & 2u) ? US : 0u;
+                    const unsigned sa = (w1.y & 1u) ? USP : 0u, sb = (w1.y & 2u) ? USP : 0u;
 #pragma unroll 1
-                    for (unsigned p = 0; p < 3; ++p)
-                        STN(w0.y + p * US, cold_op(w1.z, LDN(w0.z + p * sa), LDN(w0.w + p * sb)));
+                    for (unsigned p = 0; p < 3; ++p) {
+                        const VecT a = LDV(w0.z + p * sa), b = LDV(w0.w + p * sb);
+                        VecT r;
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) r.v[s] = cold_op(w1.z, a.v[s], b.v[s]);
+                        STV(w0.y + p * USP, r);
+                    }
                     break;
                 }
                 case X_FMA1: X1_TER(fma(a, b, c))
@@ -426,22 +555,29 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
                 case X_MIN1: X1_BIN(fmin(a, b))
                 case X_MAX1: X1_BIN(fmax(a, b))
                 case X_COLD1: X1_BIN(cold_op(w1.z, a, b))
-                case X_INIT: {                             // initial states (seeded at collocation point 2), quadratures
-                    double x0v[MAX_STATES];
-                    for (int n = 0; n < img.ns; ++n) x0v[n] = vm_ld(vm, tab_x0[n]);
-                    for (int n = 0; n < img.ns; ++n) S[(img.x_slot + 3 * n + 2) * BLOCK] = x0v[n];
-                    for (int q = 0; q < img.nq; ++q) S[(img.qe_slot + q) * BLOCK] = vm_ld(vm, tab_q0[q]);
-                    if (img.zero_off) STN(img.zero_off, 0.0);
+                case X_INIT:                               // initial states (seeded at collocation point 2), quadratures
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) {
+                        double x0v[MAX_STATES];
+                        for (int n = 0; n < img.ns; ++n) x0v[n] = ref_ld(tab_x0[n], s);
+                        for (int n = 0; n < img.ns; ++n) slot(img.x_slot + 3 * n + 2, s) = x0v[n];
+                        for (int q = 0; q < img.nq; ++q) slot(img.qe_slot + q, s) = ref_ld(tab_q0[q], s);
+                        if (img.zero_slot) slot(img.zero_slot, s) = 0.0;
+                    }
                     break;
-                }
                 case X_LDCTRL: {                           // control w0.z of finite element e -> slot w0.y
                     const int zi = tab_cmap[e * img.nce + (int)w0.z];
-                    double zv;
-                    if (la.z_mode == 0 || tab_zfix[zi]) zv = vm_ld(vm, tab_z[zi]);
-                    else if (la.z_mode == 1) zv = __ldg(la.z + zi);
-                    else if (la.z_mode == 2) zv = __ldg(la.z + i_d * img.nz + zi);
-                    else zv = __ldg(la.z + (i_d * la.n_t + j) * img.nz + zi);
-                    STN(w0.y, zv);
+                    VecT zv_;
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) {
+                        double zv1;
+                        if (la.z_mode == 0 || tab_zfix[zi]) zv1 = ref_ld(tab_z[zi], s);
+                        else if (la.z_mode == 1) zv1 = __ldg(la.z + zi);
+                        else if (la.z_mode == 2) zv1 = __ldg(la.z + i_d * img.nz + zi);
+                        else zv1 = __ldg(la.z + (i_d * la.n_t + jj_[s]) * img.nz + zi);
+                        zv_.v[s] = zv1;
+                    }
+                    STV(w0.y, zv_);
                     break;
                 }
                 case X_NB2:
@@ -463,7 +599,9 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
                     if (++e < img.nfe) pcw = (int)w0.y;
                     break;
                 case X_XEND:                               // end-point states for the CQA tape
-                    for (int n = 0; n < img.ns; ++n) S[(img.xe_slot + n) * BLOCK] = S[(img.x_slot + 3 * n + 2) * BLOCK];
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s)
+                        for (int n = 0; n < img.ns; ++n) slot(img.xe_slot + n, s) = slot(img.x_slot + 3 * n + 2, s);
                     break;
                 default: break;
                 }
@@ -475,21 +613,25 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
 #undef X_NB_CASE
 
         // ---- indicator, outputs ----
-        bool feasible = !failed;
-        for (int c = 0; c < img.ng; ++c) {
-            double gv = vm_ld(vm, tab_g[c]);
-            if (failed) gv = __longlong_as_double(0x7ff8000000000000LL);
-            feasible = feasible && (gv <= 0.0);
-            if (la.g_out && valid) la.g_out[(i_d * la.n_t + j) * img.ng + c] = gv;
-        }
-        if (la.ind_out && valid) la.ind_out[i_d * la.n_t + j] = feasible ? -0.0 : -1.0;
         double wv = 0.0;
-        if (valid && feasible) wv = la.w ? __ldg(la.w + j) : 1.0 / (double)la.n_t;
-        if (valid) {
-            cnt_iters += my_acc >> 40;
-            cnt_flops += my_acc & ((1ull << 40) - 1);
-            cnt_failed += failed ? 1u : 0u;
-            cnt_done += 1u;
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            bool feasible = !failed[s];
+            const long long j = jj_[s];
+            for (int c = 0; c < img.ng; ++c) {
+                double gv = ref_ld(tab_g[c], s);
+                if (failed[s]) gv = __longlong_as_double(0x7ff8000000000000LL);
+                feasible = feasible && (gv <= 0.0);
+                if (la.g_out && valid[s]) la.g_out[(i_d * la.n_t + j) * img.ng + c] = gv;
+            }
+            if (la.ind_out && valid[s]) la.ind_out[i_d * la.n_t + j] = feasible ? -0.0 : -1.0;
+            if (valid[s] && feasible) wv += la.w ? __ldg(la.w + j) : 1.0 / (double)la.n_t;
+            if (valid[s]) {
+                cnt_iters += my_acc[s] >> 40;
+                cnt_flops += my_acc[s] & ((1ull << 40) - 1);
+                cnt_failed += failed[s] ? 1u : 0u;
+                cnt_done += 1u;
+            }
         }
         wv = warp_sum(wv);
         if (lane == 0) red[warp] = wv;
@@ -512,7 +654,7 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
         if (lane == 0) {
             atomicAdd(&la.counters[0], (unsigned long long)dn);
             atomicAdd(&la.counters[1], it_sum);
-            atomicAdd(&la.counters[2], (unsigned long long)wi);
+            atomicAdd(&la.counters[2], (unsigned long long)wi * SPT);
             atomicAdd(&la.counters[3], (unsigned long long)fl);
             atomicAdd(&la.counters[5], fl_sum);
         }
@@ -525,16 +667,14 @@ __global__ void __launch_bounds__(BLOCK, (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))
 #undef X_TER
 #undef X_BIN
 #undef X_UN
-#undef X1_A
-#undef X1_B
-#undef X1_C
+#undef X1_OPND
 #undef X1_FL
 #undef X1_TER
 #undef X1_BIN
 #undef X1_UN
-#undef LDN
-#undef LDP
-#undef STN
-#undef STP
+#undef LDV
+#undef LDVP
+#undef STV
+#undef STVP
 
 }  // namespace pydsb

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -81,14 +82,38 @@ struct Model {
 typedef void (*FeasFn)(const ExecImage, const LaunchArgs);
 typedef void (*SensFn)(const ExecImage, const RecourseArgs);
 
-FeasFn feas_for(int ns)
+// MAXNS = largest coupled block, SPT = scenarios per thread.  SPT = 2 (both scenarios of a thread moved by one
+// LDS.128, fetch and dispatch shared) executes ~30 % fewer instructions per scenario but halves the resident
+// warps; the interpreter is bound by its dependent fetch -> dispatch -> load -> math chain, i.e. by warps in
+// flight, and measures 20 % slower on C3 -- kept selectable (PYDSB_SPT=2) for models where that flips.
+FeasFn feas_for(int ns, int spt)
 {
-    switch (ns) {
-    case 1: return feas_kernel<1>;
-    case 2: return feas_kernel<2>;
-    case 3: return feas_kernel<3>;
+    switch (ns * 10 + spt) {
+    case 11: return feas_kernel<1, 1>;
+    case 12: return feas_kernel<1, 2>;
+    case 21: return feas_kernel<2, 1>;
+    case 31: return feas_kernel<3, 1>;
     default: return nullptr;
     }
+}
+
+int image_maxns(const ExecImage& g)
+{
+    int maxns = 1;
+    for (int b = 0; b < g.n_blocks; ++b)
+        if (g.blk_ns[b] > maxns) maxns = g.blk_ns[b];
+    return maxns;
+}
+
+// scenarios per thread of the feasibility program; PYDSB_SPT=1|2 overrides (experiments)
+int choose_spt(int maxns)
+{
+    int spt = 1;
+    if (const char* e = getenv("PYDSB_SPT")) {
+        const int v = atoi(e);
+        if (v == 1 || (v == 2 && maxns == 1)) spt = v;
+    }
+    return spt;
 }
 SensFn sens_for(int ns)
 {
@@ -110,7 +135,7 @@ void free_program(Program& p)
     p.d_code = p.d_consts = p.d_tabs = nullptr;
 }
 
-bool resolve_table(const Sections& secs, const char* tag, int n, int cap, unsigned (*off)[3], unsigned* mask)
+bool resolve_table(const Sections& secs, const char* tag, int n, int cap, unsigned (*off)[3], unsigned* mask, unsigned US)
 {
     const Section* s = find(secs, tag);
     if (!s || (int)s->count < n || n > cap) return false;
@@ -122,7 +147,7 @@ bool resolve_table(const Sections& secs, const char* tag, int n, int cap, unsign
         if (v[i] & REF_CONST) return false;
         *mask |= 1u << i;
         for (int p3 = 0; p3 < 3; ++p3)
-            off[i][p3] = ((v[i] & REF_MASK) + ((v[i] & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
+            off[i][p3] = ((v[i] & REF_MASK) + ((v[i] & REF_WIDE) ? p3 : 0)) * US;
     }
     return true;
 }
@@ -145,6 +170,16 @@ int build_program(const Sections& secs, bool sens, Program& P)
     if (ncp != 3) return fail(PYDSB_ERR_UNSUPPORTED, "kernels are built for ncp = 3 (Radau)");
     if (g.ns < 1 || g.ns > MAX_STATES) return fail(PYDSB_ERR_UNSUPPORTED, "1..8 dynamic states are supported");
     if (g.n_blocks < 1 || g.n_blocks > MAX_BLOCKS) return fail(PYDSB_ERR_UNSUPPORTED, "1..4 blocks of coupled states are supported");
+    {
+        // scenarios per thread: the byte offsets below are laid out for slot stride spt*BLOCK doubles
+        const Section* bs0 = find(secs, "BLKS");
+        int maxns = 1;
+        if (bs0)
+            for (int b = 0; b < g.n_blocks && 5 * b < (int)bs0->count; ++b)
+                if (reinterpret_cast<const uint16_t*>(bs0->data)[5 * b] > maxns) maxns = reinterpret_cast<const uint16_t*>(bs0->data)[5 * b];
+        g.spt = sens ? 1 : choose_spt(maxns);
+    }
+    const unsigned US = (unsigned)g.spt * BLOCK * 8u;      // bytes between consecutive slots
     {
         // blocks: [nsb, linear, s0, s1, s2] each; tape lengths per block + quadrature tape
         const Section *bs = find(secs, "BLKS"), *bt = find(secs, "BLKT"), *bf = find(secs, "BLKF");
@@ -172,8 +207,8 @@ int build_program(const Sections& secs, bool sens, Program& P)
                 const unsigned rfv = RF[fpos + n];
                 if (rfv == REF_NONE || (rfv & REF_CONST)) return fail(PYDSB_ERR_UNSUPPORTED, "a dynamic state has an identically zero right-hand side");
                 for (int p3 = 0; p3 < 3; ++p3) {
-                    g.blk_x_o[b][n][p3] = (unsigned)(g.x_slot + 3 * st + p3) * BLOCK * 8u;
-                    g.blk_f_o[b][n][p3] = ((rfv & REF_MASK) + ((rfv & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
+                    g.blk_x_o[b][n][p3] = (unsigned)(g.x_slot + 3 * st + p3) * US;
+                    g.blk_f_o[b][n][p3] = ((rfv & REF_MASK) + ((rfv & REF_WIDE) ? p3 : 0)) * US;
                 }
             }
             for (int i = 0; i < nsb * nsb; ++i) {
@@ -182,7 +217,7 @@ int build_program(const Sections& secs, bool sens, Program& P)
                 if (v == REF_NONE) continue;
                 if (v & REF_CONST) return fail(PYDSB_ERR_INVALID, "constant reference in J table");
                 g.blk_jmask[b] |= 1u << i;
-                for (int p3 = 0; p3 < 3; ++p3) g.blk_j_o[b][i][p3] = ((v & REF_MASK) + ((v & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
+                for (int p3 = 0; p3 < 3; ++p3) g.blk_j_o[b][i][p3] = ((v & REF_MASK) + ((v & REF_WIDE) ? p3 : 0)) * US;
             }
             fpos += nsb; jpos += nsb * nsb;
         }
@@ -192,7 +227,7 @@ int build_program(const Sections& secs, bool sens, Program& P)
     if (g.ng < 1 || g.ng > 8 || g.nfe < 1 || g.p_dim < 1 || g.d_dim < 0) return fail(PYDSB_ERR_INVALID, "bad dimensions");
     if (g.nq > 8) return fail(PYDSB_ERR_UNSUPPORTED, "at most 8 quadrature states");
     if (g.nce > 4) return fail(PYDSB_ERR_UNSUPPORTED, "at most 4 control functions");
-    if (!resolve_table(secs, "RFQ_", g.nq, 8, g.fq_o, &g.fq_mask))
+    if (!resolve_table(secs, "RFQ_", g.nq, 8, g.fq_o, &g.fq_mask, US))
         return fail(PYDSB_ERR_INVALID, "bad fq reference table");
     {
         const double rtol = reinterpret_cast<const double*>(find(secs, "DBLS")->data)[0];
@@ -255,12 +290,12 @@ int build_program(const Sections& secs, bool sens, Program& P)
             if (!(refs[0] & REF_WIDE)) return fail(PYDSB_ERR_INVALID, "point tape writes a narrow slot");
         }
     }
-    g.zero_off = 0;
+    g.zero_off = 0; g.zero_slot = 0;
     if (!sens) {
         // a 1-state block with an identically zero Jacobian reads it from a slot INIT keeps at 0.0
         bool need_zero = false;
         for (int b = 0; b < g.n_blocks; ++b) need_zero = need_zero || (g.blk_ns[b] == 1 && !(g.blk_jmask[b] & 1u));
-        if (need_zero) g.zero_off = (unsigned)g.n_units * BLOCK * 8u;
+        if (need_zero) { g.zero_slot = g.n_units; g.zero_off = (unsigned)g.n_units * US; }
     }
     if (!sens) {
         // program 0: assemble the unified per-scenario program of feas_kernel
@@ -279,6 +314,7 @@ int build_program(const Sections& secs, bool sens, Program& P)
         if ((int)rfq->count < g.nq) return fail(PYDSB_ERR_INVALID, "bad fq reference table");
         in.fq_refs = reinterpret_cast<const uint16_t*>(rfq->data);
         in.img = &g;
+        in.spt = g.spt;
         Assembler as;
         if (!as.assemble(in)) return fail(PYDSB_ERR_UNSUPPORTED, "assembler: " + as.err);
         P.xprog.swap(as.words);
@@ -301,9 +337,9 @@ int build_program(const Sections& secs, bool sens, Program& P)
     if (sens) {
         if (g.nz > MAX_NZ) return fail(PYDSB_ERR_UNSUPPORTED, "at most 16 control values for the recourse optimiser");
         if (g.n_blocks != 1 || g.ns > 3) return fail(PYDSB_ERR_UNSUPPORTED, "the sensitivity program is one coupled block of <= 3 states");
-        if (!resolve_table(secs, "RFQX", g.nq * g.ns, 24, g.fqx_o, &g.fqx_mask) ||
-            !resolve_table(secs, "RFZ_", g.ns * g.nce, 12, g.fz_o, &g.fz_mask) ||
-            !resolve_table(secs, "RFQZ", g.nq * g.nce, 32, g.fqz_o, &g.fqz_mask))
+        if (!resolve_table(secs, "RFQX", g.nq * g.ns, 24, g.fqx_o, &g.fqx_mask, US) ||
+            !resolve_table(secs, "RFZ_", g.ns * g.nce, 12, g.fz_o, &g.fz_mask, US) ||
+            !resolve_table(secs, "RFQZ", g.nq * g.nce, 32, g.fqz_o, &g.fqz_mask, US))
             return fail(PYDSB_ERR_INVALID, "bad sensitivity reference table");
         if (!push("RGX_", (size_t)g.ng * g.ns) || !push("RGQ_", (size_t)g.ng * g.nq))
             return fail(PYDSB_ERR_INVALID, "bad dg reference table");
@@ -322,7 +358,7 @@ int build_program(const Sections& secs, bool sens, Program& P)
     g.off_code = o; o += sens ? (int)code.size() * 8 : 0;     // program 0 keeps no tape in shared memory
     g.off_const = o; o += (g.n_const + 1) * 8;
     g.off_tabs = o; o = align_up(o + g.n_tabs * 2, 128);
-    int land = BLOCK * g.p_dim * 8;
+    int land = g.spt * BLOCK * g.p_dim * 8;
     if (sens) {
         const int need_ws = (BLOCK / 32) * recourse_nv(g.nz) * 8;
         if (need_ws > land) land = need_ws;
@@ -331,7 +367,7 @@ int build_program(const Sections& secs, bool sens, Program& P)
     g.off_slots = o;
     int units = g.n_units + (g.zero_off ? 1 : 0);
     if (sens) units += (g.ns + g.nq + g.ng) * g.nz;        // Sx, Sq, Dc blocks of sens_kernel
-    o += units * BLOCK * 8;
+    o += units * g.spt * BLOCK * 8;
     g.smem_bytes = o;
 
     cudaError_t e = cudaMalloc(&P.d_code, code.size() * 8 + 8);
@@ -446,9 +482,7 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
                 return fail(PYDSB_ERR_UNSUPPORTED, "model needs more shared memory per CTA than the device offers");
             }
     }
-    int maxns = 1;
-    for (int b = 0; b < g.n_blocks; ++b) if (g.blk_ns[b] > maxns) maxns = g.blk_ns[b];
-    FeasFn fn = feas_for(maxns);
+    FeasFn fn = feas_for(image_maxns(g), g.spt);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
     int bps = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, BLOCK, g.smem_bytes);
@@ -514,7 +548,8 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
         if (P_out) CUDA_TRY(cudaMemsetAsync(P_out, 0, (size_t)n_d * sizeof(double), st));
         return PYDSB_OK;
     }
-    const long long n_tiles_ll = (n_t + BLOCK - 1) / BLOCK;
+    const long long tile = (long long)img.spt * BLOCK;               // theta rows per tile
+    const long long n_tiles_ll = (n_t + tile - 1) / tile;
     if (n_tiles_ll > 0x7fffffffLL) return fail(PYDSB_ERR_INVALID, "n_t too large");
     const int n_tiles = (int)n_tiles_ll;
     const long long total = n_d * n_tiles_ll;
@@ -529,9 +564,7 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
 
     const long long max_ctas = (long long)m->num_sms * m->blocks_per_sm;
     const int grid = (int)(total < max_ctas ? total : max_ctas);
-    int maxns = 1;
-    for (int b = 0; b < img.n_blocks; ++b) if (img.blk_ns[b] > maxns) maxns = img.blk_ns[b];
-    FeasFn fn = feas_for(maxns);
+    FeasFn fn = feas_for(image_maxns(img), img.spt);
     // several models may share one template instantiation: (re)assert this model's smem size and
     // (re)load its point tape into the constant bank (stream ordered)
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
