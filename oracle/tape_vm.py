@@ -55,8 +55,12 @@ class TapeVM:
         for b in range(self.n_blocks):
             nsb = int(B[5 * b])
             st = [int(x) for x in B[5 * b + 2:5 * b + 2 + nsb]]
-            self.blocks.append(dict(states=st, linear=int(B[5 * b + 1]), code=s["TPNT"][pc:pc + int(Tn[b])],
-                                    f=s["RF__"][fpos:fpos + nsb], J=s["RJ__"][jpos:jpos + nsb * nsb]))
+            kind = int(B[5 * b + 1])                      # bit 0: linear, bit 1: polynomial in its own single state
+            blk = dict(states=st, linear=kind & 1, code=s["TPNT"][pc:pc + int(Tn[b])],
+                       f=s["RF__"][fpos:fpos + nsb], J=s["RJ__"][jpos:jpos + nsb * nsb], poly=None)
+            if kind & 2:                                  # f = c0 + c1 x + c2 x^2: references of the coefficients
+                blk["poly"] = [int(s["RF__"][fpos]), int(s["RJ__"][jpos]), int(s["RP2_"][b])]
+            self.blocks.append(blk)
             pc += int(Tn[b]); fpos += nsb; jpos += nsb * nsb
         self.q_code = s["TPNT"][pc:pc + int(Tn[self.n_blocks])]
         self.param_slots = [int(v) for v in s["RPAR"]]
@@ -171,17 +175,30 @@ class TapeVM:
                 nb = len(st)
                 nbn = nb * ncp
                 active = ~failed
+                if blk["poly"] is not None:
+                    # the block tape computes the coefficients once (they depend on earlier blocks' states only)
+                    put_states(X)
+                    self._run(R, blk["code"], ncp)
+                    coef = [[self._ld(R, r, w) * one for w in range(ncp)] for r in blk["poly"]]
                 for it in range(max_it):
                     if not active.any():
                         break
-                    put_states(X)
-                    self._run(R, blk["code"], ncp)
-                    f = np.stack([np.stack([self._ld(R, r, w) * one for r in blk["f"]], axis=1) for w in range(ncp)], axis=1)
-                    J = np.zeros((S, ncp, nb, nb))
-                    for w in range(ncp):
-                        for r_ in range(nb):
-                            for c_ in range(nb):
-                                J[:, w, r_, c_] = self._ld(R, blk["J"][r_ * nb + c_], w)
+                    if blk["poly"] is not None:
+                        f = np.zeros((S, ncp, 1))
+                        J = np.zeros((S, ncp, 1, 1))
+                        for w in range(ncp):
+                            xw = X[:, w, st[0]]
+                            f[:, w, 0] = (coef[2][w] * xw + coef[1][w]) * xw + coef[0][w]
+                            J[:, w, 0, 0] = 2.0 * coef[2][w] * xw + coef[1][w]
+                    else:
+                        put_states(X)
+                        self._run(R, blk["code"], ncp)
+                        f = np.stack([np.stack([self._ld(R, r, w) * one for r in blk["f"]], axis=1) for w in range(ncp)], axis=1)
+                        J = np.zeros((S, ncp, nb, nb))
+                        for w in range(ncp):
+                            for r_ in range(nb):
+                                for c_ in range(nb):
+                                    J[:, w, r_, c_] = self._ld(R, blk["J"][r_ * nb + c_], w)
                     Xb = X[:, :, st]
                     lin = np.einsum("kj,skn->sjn", A[1:, 1:], Xb) + A[0, 1:][None, :, None] * x0[:, None, st]
                     Rres = lin - h * f

@@ -13,6 +13,13 @@
 
 namespace pydsb {
 
+// A one-state block lowered to the coefficients of  f = c0 + c1 x + c2 x^2  (byte offsets; narrow or wide)
+struct PolyBlock {
+    bool is_poly = false;
+    bool present[3] = {false, false, false}, wide[3] = {false, false, false};
+    uint32_t off[3] = {0, 0, 0};
+};
+
 struct AsmInput {
     const uint64_t *pro, *elem, *g, *pt;       // 64-bit tape words (tape_vm.cuh encoding)
     int n_pro, n_elem, n_g;
@@ -23,6 +30,7 @@ struct AsmInput {
     int nce, ctrl_slot, nq, qe_slot, n_units;
     const uint16_t* fq_refs;                   // [nq] reference of every quadrature integrand
     int spt;                                   // scenarios per thread: slot stride = spt * US bytes
+    const PolyBlock* poly;                     // [n_blocks]
     const ExecImage* img;                      // resolved per-block offsets: blk_x_o, blk_f_o, blk_j_o, blk_jmask
 };
 
@@ -50,12 +58,26 @@ public:
             static const uint32_t nb_code[3] = {X_NB1, X_NB2, X_NB3}, ns_code[3] = {X_NS1, X_NS2, X_NS3},
                                   nsl_code[3] = {X_NS1L, X_NS2L, X_NS3L};
             const ExecImage& g = *in.img;
+            if (g.max_it < 1 || g.max_it > 0xFFFF) return fail("Newton iteration cap out of range");
+            if (in.poly[b].is_poly) {
+                // the coefficients that depend on earlier blocks' states (once per element), then the whole solve
+                for (int i = 0; i < in.blk_npt[b]; ++i)
+                    if (!point_op(in.pt[pos++])) return false;
+                const PolyBlock& pb = in.poly[b];
+                uint32_t off[3], flags = in.blk_lin[b] ? 8u : 0u;
+                for (int k = 0; k < 3; ++k) {
+                    if (!pb.present[k] && !g.zero_off) return fail("model needs the zero slot");
+                    off[k] = pb.present[k] ? pb.off[k] : g.zero_off;
+                    if (pb.present[k] && pb.wide[k]) flags |= 1u << k;
+                }
+                emit(X_POLY1, g.blk_x_o[b][0][0], in.blk_flops[b], (uint32_t)g.max_it, off[0], off[1], off[2], flags);
+                continue;
+            }
             emit(nb_code[nsb - 1], g.blk_x_o[b][0][0], nsb > 1 ? g.blk_x_o[b][1][0] : 0u, nsb > 2 ? g.blk_x_o[b][2][0] : 0u);
             const int l_blk = pc();
             for (int i = 0; i < in.blk_npt[b]; ++i)
                 if (!point_op(in.pt[pos++])) return false;
             // NS: first uint4, then the operand table x_o[k] | f_o[k][3] | j_o[k*k][3], padded to whole uint4s
-            if (g.max_it < 1 || g.max_it > 0xFFFF) return fail("Newton iteration cap out of range");
             const uint32_t head[4] = {in.blk_lin[b] ? nsl_code[nsb - 1] : ns_code[nsb - 1], (uint32_t)l_blk, in.blk_flops[b],
                                       (g.blk_jmask[b] & 0xFFFFu) | ((uint32_t)g.max_it << 16)};
             words.insert(words.end(), head, head + 4);
@@ -100,9 +122,10 @@ private:
         err = m;
         return false;
     }
-    void emit(uint32_t x, uint32_t y = 0, uint32_t z = 0, uint32_t w = 0, uint32_t x1 = 0, uint32_t y1 = 0, uint32_t z1 = 0)
+    void emit(uint32_t x, uint32_t y = 0, uint32_t z = 0, uint32_t w = 0, uint32_t x1 = 0, uint32_t y1 = 0, uint32_t z1 = 0,
+              uint32_t w1 = 0)
     {
-        const uint32_t v[8] = {x, y, z, w, x1, y1, z1, 0};
+        const uint32_t v[8] = {x, y, z, w, x1, y1, z1, w1};
         words.insert(words.end(), v, v + 8);
     }
     uint32_t slot_off(unsigned ref) const { return (ref & REF_MASK) * US * (uint32_t)in_->spt; }

@@ -43,9 +43,9 @@ enum XCode : unsigned {
     // tier 1 (op < 4)
     X_NS1 = 0, X_FMA_NWN, X_MUL_NW, X_SQR_W,
     // tier 2 (op < 16)
-    X_FMA_NWW, X_FMA_WWN, X_FMA_WWW, X_FMS_NWN, X_FMS_NWW, X_FNMA_NWN, X_MUL_WW, X_ADD_NW, X_NS1L, X_NS2, X_NB1, X_QACC,
+    X_FMA_NWW, X_FMA_WWN, X_POLY1, X_FMS_NWN, X_FMS_NWW, X_FNMA_NWN, X_MUL_WW, X_ADD_NW, X_NS1L, X_NS2, X_NB1, X_QACC,
     // tier 3: remaining three-wide point ops, by operand pattern (N narrow, W wide) ...
-    X_FMS_WWN, X_FMS_WWW, X_FNMA_NWW, X_FNMA_WWN, X_FNMA_WWW, X_ADD_WW, X_SUB_WW, X_SUB_NW, X_SUB_WN, X_DIV_NW, X_DIV_WN, X_DIV_WW,
+    X_FMA_WWW, X_FMS_WWN, X_FMS_WWW, X_FNMA_NWW, X_FNMA_WWN, X_FNMA_WWW, X_ADD_WW, X_SUB_WW, X_SUB_NW, X_SUB_WN, X_DIV_NW, X_DIV_WN, X_DIV_WW,
     X_NEG_W, X_RCP_W, X_ABS_W, X_MOV_W, X_BC_N, X_MIN_NW, X_MIN_WW, X_MAX_NW, X_MAX_WW, X_COLD_W,
     // ... scalar ops (pro / elem / g tapes; flags: operand a/b/c lives in the constant pool) ...
     X_FMA1, X_FMS1, X_FNMA1, X_MUL1, X_ADD1, X_SUB1, X_DIV1, X_SQR1, X_NEG1, X_RCP1, X_ABS1, X_MOV1,
@@ -61,6 +61,7 @@ constexpr unsigned X_TIER1 = 4, X_TIER2 = 16;
 //   NBk         w0 = { op, x_o[0..2] }                                                             length 2
 //   NSk / NSkL  w0 = { op, target pcw, flops, jmask | max_it << 16 }
 //               then x_o[k], f_o[k][3], j_o[k*k][3] packed word by word                          length 1 + ceil(k(4+3k)/4)
+//   POLY1       w0 = { op, x_o, flops, max_it }   w1 = { c0, c1, c2, wide bits 0-2 | linear << 3 }
 //   QACC        w0 = { op, dst, o0, o1 }          w1 = { o2 }        LDCTRL  w0 = { op, dst, control }
 //   ELEM_END    w0 = { op, target pcw }
 __host__ __device__ constexpr int ns_words(int nsb) { return nsb + 3 * nsb + 3 * nsb * nsb; }
@@ -463,6 +464,72 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
         it = 0;                                                                                                 \
     }                                                                                                           \
     break;
+// POLY1: a one-state block whose right-hand side is  f = c0 + c1 x + c2 x^2  in its own state (coefficients:
+// parameter / control values or functions of earlier blocks' states, fixed during this solve).  The whole
+// Newton loop runs here, in registers: no dispatch, no register-file traffic until the converged points are
+// stored.  Same equations, start and stop rule as NB + point ops + NS.
+#define X_POLY1_CASE                                                                                            \
+    {                                                                                                           \
+        const uint4 w1 = c_prog[pcw - 1];                                                                       \
+        const unsigned st0 = (w1.w & 1u) ? USP : 0u, st1 = (w1.w & 2u) ? USP : 0u, st2 = (w1.w & 4u) ? USP : 0u; \
+        const bool linear = (w1.w & 8u) != 0;                                                                   \
+        VecT c0v[3], c1v[3], c2v[3];                                                                            \
+        _Pragma("unroll") for (unsigned p = 0; p < 3; ++p) {                                                    \
+            c0v[p] = LDV(w1.x + p * st0);                                                                       \
+            c1v[p] = LDV(w1.y + p * st1);                                                                       \
+            c2v[p] = LDV(w1.z + p * st2);                                                                       \
+        }                                                                                                       \
+        const VecT xsv = LDVP(w0.y, 2);                                                                         \
+        double z[SPT][3];                                                                                       \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                                       \
+            z[s][0] = z[s][1] = z[s][2] = 0.0;                                                                  \
+            conv[s] = false;                                                                                    \
+            s_prev[s] = 0.0;                                                                                    \
+        }                                                                                                       \
+        for (it = 0;;) {                                                                                        \
+            bool all = true;                                                                                    \
+            _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                                   \
+                if (!conv[s]) my_acc[s] += ((1ull << 40) | w0.z);                                               \
+                double M[3][3], r[3];                                                                           \
+                _Pragma("unroll") for (int jj = 0; jj < 3; ++jj) {                                              \
+                    const double x = xsv.v[s] + z[s][jj];                                                       \
+                    const double t = fma(c2v[jj].v[s], x, c1v[jj].v[s]);                                        \
+                    const double fx = fma(t, x, c0v[jj].v[s]);                                                  \
+                    const double jx = fma(c2v[jj].v[s], x, t);                                                  \
+                    double lin = img.adot[4 + jj + 1] * z[s][0];                                                \
+                    lin = fma(img.adot[8 + jj + 1], z[s][1], lin);                                              \
+                    lin = fma(img.adot[12 + jj + 1], z[s][2], lin);                                             \
+                    r[jj] = fma(h, fx, -lin);                                                                   \
+                    _Pragma("unroll") for (int kk = 0; kk < 3; ++kk) M[jj][kk] = img.adot[4 * (kk + 1) + jj + 1]; \
+                    M[jj][jj] = fma(-h, jx, M[jj][jj]);                                                         \
+                }                                                                                               \
+                lu_solve_inplace<3>(M, r);                                                                      \
+                double sq = 0.0, sc = 0.0;                                                                      \
+                _Pragma("unroll") for (int kk = 0; kk < 3; ++kk) {                                              \
+                    z[s][kk] += r[kk];                                                                          \
+                    const double x = xsv.v[s] + z[s][kk];                                                       \
+                    sq = fma(r[kk], r[kk], sq);                                                                 \
+                    sc = fma(x, x, sc);                                                                         \
+                }                                                                                               \
+                const double lim = fma(img.rtol2, sc, img.rtol2);                                               \
+                const bool ok = linear ? (sq <= DBL_MAX)                                                        \
+                                       : ((sq <= lim) | ((sq * sq <= lim * s_prev[s]) & (sq <= 0.01 * s_prev[s]))); \
+                s_prev[s] = sq;                                                                                 \
+                conv[s] = conv[s] | ok;                                                                         \
+                all = all & conv[s];                                                                            \
+            }                                                                                                   \
+            ++cnt_warp_iters;                                                                                   \
+            ++it;                                                                                               \
+            if (linear || __all_sync(0xffffffffu, all) || it >= (int)w0.w) break;                               \
+        }                                                                                                       \
+        VecT xo[3];                                                                                             \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                                       \
+            failed[s] = failed[s] | !conv[s];                                                                   \
+            _Pragma("unroll") for (int kk = 0; kk < 3; ++kk) xo[kk].v[s] = xsv.v[s] + z[s][kk];                 \
+        }                                                                                                       \
+        STVP(w0.y, 0, xo[0]); STVP(w0.y, 1, xo[1]); STVP(w0.y, 2, xo[2]);                                       \
+    }                                                                                                           \
+    break;
         for (;;) {
             const uint4 w0 = c_prog[pcw];
             pcw += 2;
@@ -478,7 +545,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 switch (op) {
                 case X_FMA_NWW: X_TER(N, W, W, fma(a, b, c))
                 case X_FMA_WWN: X_TER(W, W, N, fma(a, b, c))
-                case X_FMA_WWW: X_TER(W, W, W, fma(a, b, c))
+                case X_POLY1: X_POLY1_CASE
                 case X_FMS_NWN: X_TER(N, W, N, fma(a, b, -c))
                 case X_FMS_NWW: X_TER(N, W, W, fma(a, b, -c))
                 case X_FNMA_NWN: X_TER(N, W, N, fma(-a, b, c))
@@ -506,6 +573,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 }
             } else {
                 switch (op) {
+                case X_FMA_WWW: X_TER(W, W, W, fma(a, b, c))
                 case X_FMS_WWN: X_TER(W, W, N, fma(a, b, -c))
                 case X_FMS_WWW: X_TER(W, W, W, fma(a, b, -c))
                 case X_FNMA_NWW: X_TER(N, W, W, fma(-a, b, c))
@@ -608,6 +676,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 if (op == X_END) break;
             }
         }
+#undef X_POLY1_CASE
 #undef X_NS_CASE
 #undef X_NSL_CASE
 #undef X_NB_CASE

@@ -57,6 +57,7 @@ struct Program {
     void* d_tabs = nullptr;
     std::vector<uint32_t> xpt;          // program 1: pre-decoded point tape (16 words per instruction)
     std::vector<uint32_t> xprog;        // program 0: the assembled per-scenario program (8 words per instruction)
+    PolyBlock poly[MAX_BLOCKS];         // program 0: blocks lowered to polynomial coefficients
     bool present = false;
 };
 
@@ -196,10 +197,33 @@ int build_program(const Sections& secs, bool sens, Program& P)
             const int nsb = B[5 * b];
             if (nsb < 1 || nsb > 3)
                 return fail(PYDSB_ERR_UNSUPPORTED, "register-resident Newton kernels cover 1..3 dynamic states per coupled block");
-            g.blk_ns[b] = nsb; g.blk_lin[b] = B[5 * b + 1]; g.blk_pc0[b] = pc; g.blk_npt[b] = (int)T[b]; g.blk_flops[b] = F[b];
+            const unsigned kind = B[5 * b + 1];            // bit 0: linear, bit 1: polynomial in its own (single) state
+            g.blk_ns[b] = nsb; g.blk_lin[b] = kind & 1u; g.blk_pc0[b] = pc; g.blk_npt[b] = (int)T[b]; g.blk_flops[b] = F[b];
             pc += (int)T[b];
             if ((int)rf->count < fpos + nsb || (int)rj->count < jpos + nsb * nsb) return fail(PYDSB_ERR_INVALID, "bad f/J tables");
             g.blk_jmask[b] = 0;
+            P.poly[b] = PolyBlock{};
+            if (kind & 2u) {
+                // RF__/RJ__/RP2_ hold the references of c0/c1/c2:  f = c0 + c1 x + c2 x^2
+                const Section* rp = find(secs, "RP2_");
+                if (sens || nsb != 1 || !rp || (int)rp->count <= b) return fail(PYDSB_ERR_INVALID, "bad polynomial block");
+                const int st = B[5 * b + 2];
+                if (st >= g.ns) return fail(PYDSB_ERR_INVALID, "bad state index in block table");
+                seen |= 1 << st;
+                for (int p3 = 0; p3 < 3; ++p3) g.blk_x_o[b][0][p3] = (unsigned)(g.x_slot + 3 * st + p3) * US;
+                const unsigned refs[3] = {RF[fpos], RJ[jpos], reinterpret_cast<const uint16_t*>(rp->data)[b]};
+                P.poly[b].is_poly = true;
+                for (int k = 0; k < 3; ++k) {
+                    if (refs[k] == REF_NONE) continue;
+                    if (refs[k] & REF_CONST) return fail(PYDSB_ERR_INVALID, "constant reference in a polynomial block");
+                    if ((int)(refs[k] & REF_MASK) + ((refs[k] & REF_WIDE) ? 2 : 0) >= g.n_units) return fail(PYDSB_ERR_INVALID, "slot out of range");
+                    P.poly[b].present[k] = true;
+                    P.poly[b].wide[k] = (refs[k] & REF_WIDE) != 0;
+                    P.poly[b].off[k] = (refs[k] & REF_MASK) * US;
+                }
+                fpos += 1; jpos += 1;
+                continue;
+            }
             for (int n = 0; n < nsb; ++n) {
                 const int st = B[5 * b + 2 + n];
                 if (st >= g.ns) return fail(PYDSB_ERR_INVALID, "bad state index in block table");
@@ -294,7 +318,10 @@ int build_program(const Sections& secs, bool sens, Program& P)
     if (!sens) {
         // a 1-state block with an identically zero Jacobian reads it from a slot INIT keeps at 0.0
         bool need_zero = false;
-        for (int b = 0; b < g.n_blocks; ++b) need_zero = need_zero || (g.blk_ns[b] == 1 && !(g.blk_jmask[b] & 1u));
+        for (int b = 0; b < g.n_blocks; ++b) {
+            if (P.poly[b].is_poly) need_zero = need_zero || !(P.poly[b].present[0] && P.poly[b].present[1] && P.poly[b].present[2]);
+            else need_zero = need_zero || (g.blk_ns[b] == 1 && !(g.blk_jmask[b] & 1u));
+        }
         if (need_zero) { g.zero_slot = g.n_units; g.zero_off = (unsigned)g.n_units * US; }
     }
     if (!sens) {
@@ -314,6 +341,7 @@ int build_program(const Sections& secs, bool sens, Program& P)
         if ((int)rfq->count < g.nq) return fail(PYDSB_ERR_INVALID, "bad fq reference table");
         in.fq_refs = reinterpret_cast<const uint16_t*>(rfq->data);
         in.img = &g;
+        in.poly = P.poly;
         in.spt = g.spt;
         Assembler as;
         if (!as.assemble(in)) return fail(PYDSB_ERR_UNSUPPORTED, "assembler: " + as.err);

@@ -52,7 +52,7 @@ class _Control:
 
 class DaeModel:
     def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-12, newton_max_it=25, predictor=False,
-                 quadratures="auto", block_triangular=True):
+                 quadratures="auto", block_triangular=True, polynomial_blocks=True):
         self.graph = T.Graph()
         self.d_names = list(d_names)
         self.p_names = list(p_names)
@@ -66,6 +66,9 @@ class DaeModel:
         # solve the strongly connected components of the state dependency graph one after the other
         # (A -> B -> C kinetics: cA alone, then cB, which is linear given cA) instead of one coupled system
         self.block_triangular = bool(block_triangular)
+        # a one-state block whose right-hand side is a polynomial of degree <= 2 in its own state (mass-action
+        # kinetics) is lowered to its coefficients: the kernel runs that block's Newton loop in registers
+        self.polynomial_blocks = bool(polynomial_blocks)
         self.states: list[_State] = []
         self.controls: list[_Control] = []
         self.constraints = []          # (name, Expr (<= 0 feasible), bigM)
@@ -221,7 +224,19 @@ class DaeModel:
         roots = {"x0": x0, "q0": q0, "z": z_exprs, "g": gk, "fq": fq}
         groups = []
         blk_linear = []
+        blk_poly = []                 # per block: None, or the references [c0, c1, c2] table name
         for b, blk in enumerate(blocks):
+            co = None
+            if self.polynomial_blocks and len(blk) == 1:
+                co = g.poly_coeffs(f[blk[0]], g.x(blk[0]), 2)
+            if co is not None:
+                co = [None if c.is_const(0.0) else c for c in co] + [None] * (3 - len(co))
+                roots[f"c{b}"] = co
+                groups.append((f"pt{b}", [f"c{b}"]))       # the coefficients that depend on earlier blocks' states
+                blk_poly.append(f"c{b}")
+                blk_linear.append(1 if co[2] is None else 0)
+                continue
+            blk_poly.append(None)
             roots[f"f{b}"] = [f[i] for i in blk]
             roots[f"J{b}"] = [J[r * ns + c] for r in blk for c in blk]
             groups.append((f"pt{b}", [f"f{b}", f"J{b}"]))
@@ -252,10 +267,11 @@ class DaeModel:
 
         lows = []
         blk_flops = []
-        programs = [(roots, groups, blocks, blk_linear)]
+        programs = [(roots, groups, blocks, blk_linear, blk_poly)]
         if ns <= 3:          # the sensitivity program is one coupled block: only for <= 3 dynamic states
-            programs.append((roots_s, groups_s, [all_blk], [0]))
-        for prog, (rts, grp, blks, lin) in enumerate(programs):
+            programs.append((roots_s, groups_s, [all_blk], [0], [None]))
+        blk_fixed = []
+        for prog, (rts, grp, blks, lin, pol) in enumerate(programs):
             low = T.lower(g, n_param=self.n_param, n_ctrl_elem=nce, ns=ns, nq=nq, roots=rts, pt_groups=grp, ncp=self.ncp)
             lows.append(low)
             lay = low.layout
@@ -266,12 +282,22 @@ class DaeModel:
             blkt = [len(low.code[f"pt{b}"]) for b in range(len(blks))] + [len(low.code["ptq"]) if "ptq" in low.code else 0]
             blks_tab = []
             flops = []
+            fixed = []                # per block: point-tape flops that run once per element (polynomial blocks)
             for b, blk in enumerate(blks):
-                blks_tab += [len(blk), lin[b]] + list(blk) + [0] * (3 - len(blk))
+                # kind: bit 0 linear, bit 1 polynomial (RF__/RJ__/RP2_ hold the references of c0/c1/c2)
+                blks_tab += [len(blk), lin[b] | (2 if pol[b] else 0)] + list(blk) + [0] * (3 - len(blk))
                 n_b = len(blk) * self.ncp
-                flops.append(low.stats["flops"][f"pt{b}"] * self.ncp + 2 * n_b * (self.ncp + 1) + (2 * n_b ** 3) // 3 + 2 * n_b * n_b)
+                solve = 2 * n_b * (self.ncp + 1) + (2 * n_b ** 3) // 3 + 2 * n_b * n_b
+                if pol[b]:
+                    # Horner f = (c2 x + c1) x + c0 and J = c2 x + (c2 x + c1): three FMAs per point
+                    flops.append(6 * self.ncp + solve)
+                    fixed.append(low.stats["flops"][f"pt{b}"] * self.ncp)
+                else:
+                    flops.append(low.stats["flops"][f"pt{b}"] * self.ncp + solve)
+                    fixed.append(0)
             if not prog:
                 blk_flops = flops
+                blk_fixed = fixed
             sec("HEAD", "u32", [ns, nq, ng, len(self.d_names), len(self.p_names), nz, self.nfe, self.ncp, nce,
                                 lay.n_units, lay.ctrl_slot, lay.xe_slot, lay.qe_slot, lay.x_slot, self.newton_max_it,
                                 0, lay.fq_state_dep, 1 if self.predictor else 0, len(blks)])
@@ -294,8 +320,9 @@ class DaeModel:
             sec("RX0_", "u16", low.refs["x0"])
             sec("RQ0_", "u16", tab(low, "q0", nq))
             sec("RZ__", "u16", tab(low, "z", nz))
-            sec("RF__", "u16", np.concatenate([low.refs[f"f{b}"] for b in range(len(blks))]))
-            sec("RJ__", "u16", np.concatenate([low.refs[f"J{b}"] for b in range(len(blks))]))
+            sec("RF__", "u16", np.concatenate([low.refs[pol[b]][0:1] if pol[b] else low.refs[f"f{b}"] for b in range(len(blks))]))
+            sec("RJ__", "u16", np.concatenate([low.refs[pol[b]][1:2] if pol[b] else low.refs[f"J{b}"] for b in range(len(blks))]))
+            sec("RP2_", "u16", [int(low.refs[pol[b]][2]) if pol[b] else T.REF_NONE for b in range(len(blks))])
             sec("RFQ_", "u16", tab(low, "fq", nq))
             sec("RG__", "u16", low.refs["g"])
             sec("CMAP", "u16", cmap)
@@ -320,7 +347,7 @@ class DaeModel:
             nfe=self.nfe, ncp=self.ncp, n_units=lay.n_units, tapes=low, dyn_states=[self.states[i].name for i in dyn],
             quad_states=[self.states[i].name for i in quad], z_lo=np.asarray(z_lo), z_hi=np.asarray(z_hi),
             tapes_sens=lows[1] if len(lows) > 1 else None, z_init=z_exprs, blocks=[[dyn_names[i] for i in blk] for blk in blocks], block_linear=blk_linear,
-            block_flops=blk_flops,
+            block_flops=blk_flops, block_fixed_flops=blk_fixed, block_poly=[bool(x) for x in blk_poly],
             z_fixed=np.asarray(z_fixed, dtype=bool), big_m=np.asarray([m for _, _, m in self.constraints]),
             constraint_names=[n for n, _, _ in self.constraints], cmap=cmap, newton_rtol=self.newton_rtol,
             newton_max_it=self.newton_max_it)
@@ -345,6 +372,8 @@ class LoweredModel:
     blocks: list
     block_linear: list
     block_flops: list
+    block_fixed_flops: list
+    block_poly: list
     dyn_states: list
     quad_states: list
     z_lo: np.ndarray
@@ -364,7 +393,7 @@ class LoweredModel:
     def fixed_flops_per_evaluation(self):
         """Tape work that does not depend on the Newton iteration count."""
         fl = self.tapes.stats["flops"]
-        return fl["pro"] + fl["g"] + self.nfe * (fl["elem"] + self.ncp * fl.get("ptq", 0))
+        return fl["pro"] + fl["g"] + self.nfe * (fl["elem"] + self.ncp * fl.get("ptq", 0) + sum(self.block_fixed_flops))
 
     def flops_per_evaluation(self, mean_newton_iters_per_element, newton_flops_per_eval=None):
         """F_alg per (d,theta) evaluation.  With block-triangular solves pass the measured

@@ -334,6 +334,58 @@ class Graph:
         raise NotImplementedError(op)
 
 
+    # polynomial structure ---------------------------------------------------------------------------
+    def poly_coeffs(self, e, x, maxdeg=2):
+        """Coefficients ``[c0, c1, ...]`` (expressions free of the leaf ``x``) with ``e == sum_k c_k x**k``, or
+        ``None`` when ``e`` is not a polynomial of degree <= ``maxdeg`` in ``x``.  Mass-action kinetics are: the
+        kernel then solves a one-state block with its Newton loop entirely in registers (csrc/feas_kernel.cuh, POLY1)."""
+        memo = {}
+        zero = self.const(0.0)
+
+        def trim(p):
+            while len(p) > 1 and p[-1].is_const(0.0):
+                p = p[:-1]
+            return p
+
+        def pmul(p, q):
+            if len(p) + len(q) - 2 > maxdeg:
+                return None
+            out = [zero] * (len(p) + len(q) - 1)
+            for i, a in enumerate(p):
+                for j, b in enumerate(q):
+                    out[i + j] = self.add(out[i + j], self.mul(a, b))
+            return trim(out)
+
+        for n in topo_order([e]):
+            if n is x:
+                memo[n.id] = [zero, self.const(1.0)]
+                continue
+            if not n.args:
+                memo[n.id] = [n]
+                continue
+            ps = [memo[a.id] for a in n.args]
+            if any(p is None for p in ps):
+                memo[n.id] = None
+            elif all(len(p) == 1 for p in ps):
+                memo[n.id] = [n]                              # free of x: stays one node
+            elif n.op in ("add", "sub"):
+                p, q = ps
+                m = max(len(p), len(q))
+                p = p + [zero] * (m - len(p)); q = q + [zero] * (m - len(q))
+                memo[n.id] = trim([self.add(a, b) if n.op == "add" else self.sub(a, b) for a, b in zip(p, q)])
+            elif n.op == "neg":
+                memo[n.id] = [self.neg(a) for a in ps[0]]
+            elif n.op == "mul":
+                memo[n.id] = pmul(ps[0], ps[1])
+            elif n.op == "sqr":
+                memo[n.id] = pmul(ps[0], ps[0])
+            elif n.op == "div" and len(ps[1]) == 1:
+                memo[n.id] = [self.div(a, ps[1][0]) for a in ps[0]]
+            else:
+                memo[n.id] = None
+        return memo[e.id]
+
+
 def topo_order(roots):
     """Post-order (dependencies first) list of the nodes reachable from ``roots``."""
     seen, out = set(), []

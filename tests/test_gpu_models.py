@@ -28,6 +28,25 @@ def test_dense9_variant_ns3():
     assert eng.counters()["failed"] == 0
 
 
+def test_generic_block_triangular_path_matches_polynomial_blocks():
+    """polynomial_blocks=False runs the block-triangular kinetics through the generic ops (NB, point ops, NS / NSL)
+    instead of the in-register POLY1 solve; both against the C oracle."""
+    rng = np.random.default_rng(19)
+    n_d, n_t = 29, 301
+    d = np.stack([rng.uniform(250, 350, n_d), rng.uniform(250, 300, n_d), rng.uniform(1500, 2500, n_d), rng.uniform(0, 2.5, n_d)], axis=1)
+    p = K.theta_samples(n_t)
+    go, Po, _ = cbind.kinetics_grid(d, p, np.full(n_t, 1.0 / n_t), tol=1e-13)
+    for poly in (True, False):
+        lm = models.kinetics("design4", polynomial_blocks=poly).lower()
+        assert lm.block_poly == [poly, poly]
+        eng = capi.Engine(lm.blob, 0)
+        g, ind, P = eng.eval_host(d, p, None, want_g=True, want_ind=True)
+        assert np.all(np.abs(g - go) <= 1e-10 * np.maximum(np.abs(go), G_SCALE))
+        np.testing.assert_allclose(P, Po, atol=1e-12)
+        c = eng.counters()
+        assert c["failed"] == 0 and c["scenarios"] == n_d * n_t
+
+
 def _transcendental_model():
     m = DaeModel(["a"], ["b", "c"], nfe=6)
     g = m.graph

@@ -97,7 +97,13 @@ def test_kinetics_structure():
     st = lm.tapes.stats
     assert sec["TPNT"].size == st["pt0"] + st["pt1"] + st["ptq"] <= 8
     assert list(sec["BLKT"]) == [st["pt0"], st["pt1"], st["ptq"]]
-    assert list(sec["BLKS"]) == [1, 0, 0, 0, 0, 1, 1, 1, 0, 0]
+    # both blocks are polynomials in their own state (kind bit 1): f_A = c0 + c2 cA^2, f_B = c0(cA) + c1 cB
+    assert list(sec["BLKS"]) == [1, 2, 0, 0, 0, 1, 3, 1, 0, 0] and lm.block_poly == [True, True]
+    assert [int(r) == T.REF_NONE for r in (sec["RF__"][0], sec["RJ__"][0], sec["RP2_"][0])] == [False, True, False]
+    assert [int(r) == T.REF_NONE for r in (sec["RF__"][1], sec["RJ__"][1], sec["RP2_"][1])] == [False, False, True]
+    assert st["pt0"] == 0                                   # cA's coefficients are parameter / control values
+    lmg = models.kinetics("twostage", polynomial_blocks=False).lower()      # generic point tapes + f / J tables
+    assert list(parse_blob(lmg.blob)["BLKS"]) == [1, 0, 0, 0, 0, 1, 1, 1, 0, 0] and lmg.block_poly == [False, False]
     # the coupled single-block form (what the sensitivity program and dense9 use)
     lmc = models.kinetics("twostage", block_triangular=False).lower()
     assert lmc.blocks == [["cA", "cB"]]
@@ -168,3 +174,32 @@ def test_lowering_rejects_bad_models():
     m.ode(x, -x)
     with pytest.raises(ValueError):
         m.lower()                               # no constraint
+
+
+def test_poly_coeffs():
+    g = T.Graph()
+    x, y, p = g.x(0), g.x(1), g.param(0)
+    vals = {("x", 0): 1.7, ("x", 1): -0.6, ("param", 0): 2.5}
+    e = p * (3.0 * x ** 2 - y * x) / (1.0 + p) + g.exp(y) - 4.0
+    co = g.poly_coeffs(e, x, 2)
+    assert len(co) == 3
+    for c in co:                                            # free of x
+        assert all(not (n.op == "x" and n.value == 0) for n in T.topo_order([c]))
+    xv = vals[("x", 0)]
+    assert abs(sum(_eval(c, vals) * xv ** k for k, c in enumerate(co)) - _eval(e, vals)) < 1e-12
+    assert len(g.poly_coeffs(p * x - y, x, 2)) == 2         # linear in x
+    assert len(g.poly_coeffs(p * y, x, 2)) == 1             # free of x
+    assert g.poly_coeffs(g.exp(x) + y, x, 2) is None        # transcendental in x
+    assert g.poly_coeffs(x ** 3 + y, x, 2) is None          # degree 3
+    assert g.poly_coeffs(y / (1.0 + x), x, 2) is None       # rational in x
+
+
+def test_polynomial_blocks_agree_with_generic_blocks():
+    rng = np.random.default_rng(11)
+    d = np.stack([rng.uniform(250, 350, 12), rng.uniform(250, 300, 12), rng.uniform(1500, 2500, 12), rng.uniform(0, 2.5, 12)], axis=1)
+    p = K.theta_samples()[:20]
+    a = tape_vm.TapeVM(models.kinetics("design4").lower().blob).evaluate(d, p)
+    b = tape_vm.TapeVM(models.kinetics("design4", polynomial_blocks=False).lower().blob).evaluate(d, p)
+    np.testing.assert_allclose(a["g"][..., 0], b["g"][..., 0], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(a["g"][..., 1], b["g"][..., 1], rtol=0, atol=1e-12 * 1e5)
+    assert (a["feasible"] == b["feasible"]).all() and not a["status"].any()
