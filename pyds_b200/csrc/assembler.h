@@ -27,7 +27,8 @@ struct AsmInput {
     const int *blk_npt, *blk_ns, *blk_lin;
     const unsigned* blk_flops;
     int q_npt;
-    int nce, ctrl_slot, nq, qe_slot, n_units;
+    int nce, ctrl_slot, nq, qe_slot, n_units, nfe;
+    const uint16_t* cmap;                      // [nfe][nce] z index of every control on every finite element
     const uint16_t* fq_refs;                   // [nq] reference of every quadrature integrand
     int spt;                                   // scenarios per thread: slot stride = spt * US bytes
     const PolyBlock* poly;                     // [n_blocks]
@@ -47,10 +48,20 @@ public:
         for (int i = 0; i < in.n_pro; ++i)
             if (!scalar_op(in.pro[i])) return false;
         emit(X_INIT);
+        // controls that map every finite element to the same z entry (fixed profiles, constant-in-time controls):
+        // the control loads and the elem tape are element invariant and run once, before the loop
+        bool invariant = true;
+        for (int e = 1; e < in.nfe; ++e)
+            for (int c = 0; c < in.nce; ++c) invariant = invariant && in.cmap[e * in.nce + c] == in.cmap[c];
+        auto ctrl_and_elem = [&]() -> bool {
+            for (int c = 0; c < in.nce; ++c) emit(X_LDCTRL, (uint32_t)(in.ctrl_slot + c) * US * (uint32_t)in.spt, (uint32_t)c);
+            for (int i = 0; i < in.n_elem; ++i)
+                if (!scalar_op(in.elem[i])) return false;
+            return true;
+        };
+        if (invariant && !ctrl_and_elem()) return false;
         const int l_elem = pc();
-        for (int c = 0; c < in.nce; ++c) emit(X_LDCTRL, (uint32_t)(in.ctrl_slot + c) * US * (uint32_t)in.spt, (uint32_t)c);
-        for (int i = 0; i < in.n_elem; ++i)
-            if (!scalar_op(in.elem[i])) return false;
+        if (!invariant && !ctrl_and_elem()) return false;
         int pos = 0;
         for (int b = 0; b < in.n_blocks; ++b) {
             const int nsb = in.blk_ns[b];
@@ -97,15 +108,22 @@ public:
         }
         for (int i = 0; i < in.q_npt; ++i)
             if (!point_op(in.pt[pos++])) return false;
+        // ELEM_END: the quadratures to advance (Radau weights), then back to the element loop
+        std::vector<uint32_t> quad;
         for (int q = 0; q < in.nq; ++q) {
             const unsigned r = in.fq_refs[q];
             if (r == REF_NONE) continue;
             if (r & REF_CONST) return fail("constant reference in the quadrature table");
             const uint32_t o = slot_off(r), st = (r & REF_WIDE) ? US * (uint32_t)in.spt : 0u;
             if (!check_slot(r)) return false;
-            emit(X_QACC, (uint32_t)(in.qe_slot + q) * US * (uint32_t)in.spt, o, o + st, o + 2 * st);
+            const uint32_t v[4] = {(uint32_t)(in.qe_slot + q) * US * (uint32_t)in.spt, o, o + st, o + 2 * st};
+            quad.insert(quad.end(), v, v + 4);
         }
-        emit(X_ELEM_END, (uint32_t)l_elem);
+        {
+            const uint32_t head[4] = {X_ELEM_END, (uint32_t)l_elem, (uint32_t)(quad.size() / 4), 0u};
+            words.insert(words.end(), head, head + 4);
+            words.insert(words.end(), quad.begin(), quad.end());
+        }
         emit(X_XEND);
         for (int i = 0; i < in.n_g; ++i)
             if (!scalar_op(in.g[i])) return false;

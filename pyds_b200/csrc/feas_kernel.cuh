@@ -41,17 +41,17 @@ namespace pydsb {
 // that run once per Newton iteration sit at depth <= 3, the other common point ops at depth <= 5.
 enum XCode : unsigned {
     // tier 1 (op < 4)
-    X_NS1 = 0, X_FMA_NWN, X_MUL_NW, X_SQR_W,
+    X_POLY1 = 0, X_MUL_NW, X_NS1, X_ELEM_END,
     // tier 2 (op < 16)
-    X_FMA_NWW, X_FMA_WWN, X_POLY1, X_FMS_NWN, X_FMS_NWW, X_FNMA_NWN, X_MUL_WW, X_ADD_NW, X_NS1L, X_NS2, X_NB1, X_QACC,
+    X_FMA_NWN, X_FMA_NWW, X_SQR_W, X_FMS_NWW, X_MUL_WW, X_ADD_NW, X_MUL1, X_FMA1, X_ADD1, X_NS1L, X_NS2, X_NB1,
     // tier 3: remaining three-wide point ops, by operand pattern (N narrow, W wide) ...
-    X_FMA_WWW, X_FMS_WWN, X_FMS_WWW, X_FNMA_NWW, X_FNMA_WWN, X_FNMA_WWW, X_ADD_WW, X_SUB_WW, X_SUB_NW, X_SUB_WN, X_DIV_NW, X_DIV_WN, X_DIV_WW,
+    X_FMA_WWN, X_FMA_WWW, X_FMS_NWN, X_FMS_WWN, X_FMS_WWW, X_FNMA_NWN, X_FNMA_NWW, X_FNMA_WWN, X_FNMA_WWW, X_ADD_WW,
+    X_SUB_WW, X_SUB_NW, X_SUB_WN, X_DIV_NW, X_DIV_WN, X_DIV_WW,
     X_NEG_W, X_RCP_W, X_ABS_W, X_MOV_W, X_BC_N, X_MIN_NW, X_MIN_WW, X_MAX_NW, X_MAX_WW, X_COLD_W,
     // ... scalar ops (pro / elem / g tapes; flags: operand a/b/c lives in the constant pool) ...
-    X_FMA1, X_FMS1, X_FNMA1, X_MUL1, X_ADD1, X_SUB1, X_DIV1, X_SQR1, X_NEG1, X_RCP1, X_ABS1, X_MOV1,
-    X_MIN1, X_MAX1, X_COLD1,
+    X_FMS1, X_FNMA1, X_SUB1, X_DIV1, X_SQR1, X_NEG1, X_RCP1, X_ABS1, X_MOV1, X_MIN1, X_MAX1, X_COLD1,
     // ... structure
-    X_INIT, X_LDCTRL, X_NB2, X_NB3, X_NS3, X_NS2L, X_NS3L, X_ELEM_END, X_XEND, X_END,
+    X_INIT, X_LDCTRL, X_NB2, X_NB3, X_NS3, X_NS2L, X_NS3L, X_XEND, X_END,
     X_COUNT
 };
 constexpr unsigned X_TIER1 = 4, X_TIER2 = 16;
@@ -62,8 +62,8 @@ constexpr unsigned X_TIER1 = 4, X_TIER2 = 16;
 //   NSk / NSkL  w0 = { op, target pcw, flops, jmask | max_it << 16 }
 //               then x_o[k], f_o[k][3], j_o[k*k][3] packed word by word                          length 1 + ceil(k(4+3k)/4)
 //   POLY1       w0 = { op, x_o, flops, max_it }   w1 = { c0, c1, c2, wide bits 0-2 | linear << 3 }
-//   QACC        w0 = { op, dst, o0, o1 }          w1 = { o2 }        LDCTRL  w0 = { op, dst, control }
-//   ELEM_END    w0 = { op, target pcw }
+//   LDCTRL      w0 = { op, dst, control }
+//   ELEM_END    w0 = { op, target pcw, n }        then n x { dst, o0, o1, o2 }: quadratures to advance     length 1 + n
 __host__ __device__ constexpr int ns_words(int nsb) { return nsb + 3 * nsb + 3 * nsb * nsb; }
 __host__ __device__ constexpr int ns_length(int nsb) { return 1 + (ns_words(nsb) + 3) / 4; }
 
@@ -536,46 +536,55 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
             const unsigned op = w0.x;
             if (op < X_TIER1) {
                 switch (op) {
-                case X_NS1: X_NS_CASE(1, false)
-                case X_FMA_NWN: X_TER(N, W, N, fma(a, b, c))
+                case X_POLY1: X_POLY1_CASE
                 case X_MUL_NW: X_BIN(N, W, a * b)
-                case X_SQR_W: X_UN(W, a * a)
+                case X_NS1: X_NS_CASE(1, false)
+                case X_ELEM_END: {
+                    // quadratures  x_q += h * sum_j bw_j fq(x_j)  at the converged points, then the next element
+                    const int at = pcw - 2;
+                    const int nquad = (int)w0.z;
+                    for (int qi = 0; qi < nquad; ++qi) {
+                        const uint4 qw = c_prog[at + 1 + qi];
+                        const VecT f0 = LDV(qw.y), f1 = LDV(qw.z), f2 = LDV(qw.w);
+                        VecT q = LDV(qw.x);
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) {
+                            double acc = img.bw[0] * f0.v[s];
+                            acc = fma(img.bw[1], f1.v[s], acc);
+                            acc = fma(img.bw[2], f2.v[s], acc);
+                            q.v[s] = fma(h, acc, q.v[s]);
+                        }
+                        STV(qw.x, q);
+                    }
+                    pcw = (++e < img.nfe) ? (int)w0.y : at + 1 + nquad;
+                    break;
+                }
                 }
             } else if (op < X_TIER2) {
                 switch (op) {
+                case X_FMA_NWN: X_TER(N, W, N, fma(a, b, c))
                 case X_FMA_NWW: X_TER(N, W, W, fma(a, b, c))
-                case X_FMA_WWN: X_TER(W, W, N, fma(a, b, c))
-                case X_POLY1: X_POLY1_CASE
-                case X_FMS_NWN: X_TER(N, W, N, fma(a, b, -c))
+                case X_SQR_W: X_UN(W, a * a)
                 case X_FMS_NWW: X_TER(N, W, W, fma(a, b, -c))
-                case X_FNMA_NWN: X_TER(N, W, N, fma(-a, b, c))
                 case X_MUL_WW: X_BIN(W, W, a * b)
                 case X_ADD_NW: X_BIN(N, W, a + b)
+                case X_MUL1: X1_BIN(a * b)
+                case X_FMA1: X1_TER(fma(a, b, c))
+                case X_ADD1: X1_BIN(a + b)
+                case X_NS1L: X_NSL_CASE(1, false)
                 case X_NS2:
                     if constexpr (MAXNS >= 2) X_NS_CASE(2, true)
                     break;
                 case X_NB1: X_NB_CASE(1)
-                case X_NS1L: X_NSL_CASE(1, false)
-                case X_QACC: {                             // quadrature: x_q += h * sum_j bw_j fq(x_j) at the converged points
-                    const unsigned o2 = c_prog[pcw - 1].x;
-                    const VecT f0 = LDV(w0.z), f1 = LDV(w0.w), f2 = LDV(o2);
-                    VecT q = LDV(w0.y);
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        double acc = img.bw[0] * f0.v[s];
-                        acc = fma(img.bw[1], f1.v[s], acc);
-                        acc = fma(img.bw[2], f2.v[s], acc);
-                        q.v[s] = fma(h, acc, q.v[s]);
-                    }
-                    STV(w0.y, q);
-                    break;
-                }
                 }
             } else {
                 switch (op) {
+                case X_FMA_WWN: X_TER(W, W, N, fma(a, b, c))
                 case X_FMA_WWW: X_TER(W, W, W, fma(a, b, c))
+                case X_FMS_NWN: X_TER(N, W, N, fma(a, b, -c))
                 case X_FMS_WWN: X_TER(W, W, N, fma(a, b, -c))
                 case X_FMS_WWW: X_TER(W, W, W, fma(a, b, -c))
+                case X_FNMA_NWN: X_TER(N, W, N, fma(-a, b, c))
                 case X_FNMA_NWW: X_TER(N, W, W, fma(-a, b, c))
                 case X_FNMA_WWN: X_TER(W, W, N, fma(-a, b, c))
                 case X_FNMA_WWW: X_TER(W, W, W, fma(-a, b, c))
@@ -608,11 +617,8 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                     }
                     break;
                 }
-                case X_FMA1: X1_TER(fma(a, b, c))
                 case X_FMS1: X1_TER(fma(a, b, -c))
                 case X_FNMA1: X1_TER(fma(-a, b, c))
-                case X_MUL1: X1_BIN(a * b)
-                case X_ADD1: X1_BIN(a + b)
                 case X_SUB1: X1_BIN(a - b)
                 case X_DIV1: X1_BIN(a / b)
                 case X_SQR1: X1_UN(a * a)
@@ -662,9 +668,6 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                     break;
                 case X_NS3:
                     if constexpr (MAXNS >= 3) X_NS_CASE(3, true)
-                    break;
-                case X_ELEM_END:
-                    if (++e < img.nfe) pcw = (int)w0.y;
                     break;
                 case X_XEND:                               // end-point states for the CQA tape
 #pragma unroll

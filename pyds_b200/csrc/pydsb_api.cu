@@ -341,6 +341,9 @@ int build_program(const Sections& secs, bool sens, Program& P)
         if ((int)rfq->count < g.nq) return fail(PYDSB_ERR_INVALID, "bad fq reference table");
         in.fq_refs = reinterpret_cast<const uint16_t*>(rfq->data);
         in.img = &g;
+        in.nfe = g.nfe;
+        in.cmap = reinterpret_cast<const uint16_t*>(find(secs, "CMAP")->data);
+        if ((int)find(secs, "CMAP")->count < g.nfe * g.nce) return fail(PYDSB_ERR_INVALID, "control map shorter than nfe x nce");
         in.poly = P.poly;
         in.spt = g.spt;
         Assembler as;
