@@ -108,6 +108,44 @@ def cpu_baseline(n_rows, n_t, threads, tol=1e-10, n_d=10000):
     return n_rows * n_t / dt, dt, P, it
 
 
+class _EfpOwner:
+    """Adapter handed to the nested-sampling driver: ``g`` is never materialised at this size, the driver calls
+    the fused ``efp`` (every rank passes the same proposals; rows are sharded, probabilities all-gathered)."""
+
+    def __init__(self, sharded):
+        self.sharded = sharded
+
+    def efp(self, d, p, w):
+        return self.sharded.efp_global(d, p, w)
+
+    def g(self, d, p):
+        raise NotImplementedError("the bench uses the fused efp path")
+
+
+def ns_iteration_seconds(sharded, n_live, theta, w, iterations):
+    """Seconds per nested-sampling iteration (BASELINE.json's second metric) of pyds_b200.ns at the bench
+    configuration: n_live live points, n_live/10 proposals per iteration drawn from the enlarged bounding
+    ellipsoid of the live set (host, numpy), their P(feasible) over all theta through the host-buffer path
+    (H2D, kernels, D2H, all-gather), live-set update."""
+    from pyds_b200 import ns
+    owner = _EfpOwner(sharded)
+    form = {
+        "activity_type": "ds",
+        "problem": {"design_variables": [{"t_f": [250.0, 350.0]}, {"T": [250.0, 300.0]}, {"cA0": [1500.0, 2500.0]},
+                                         {"Fbar": [0.0, 2.5]}],
+                    "parameters_best_estimate": [2.5e3, 5e3, 6.409e-2, 9.938e3],
+                    "parameters_samples": [{"c": row, "w": float(wi)} for row, wi in zip(theta, w)],
+                    "target_reliability": 0.65},
+        "solver": {"name": "ds-ns",
+                   "settings": {"efp_evaluation": {"constraints_func_ptr": owner.g},
+                                "points_schedule": [(0.0, n_live, max(n_live // 10, 1))],
+                                "stop_criteria": [{"inside_fraction": 1.0}]},
+                   "algorithms": {"sampling": {"settings": {"prng_seed": 1989, "stop_criteria": [{"max_iterations": iterations}]}}}},
+    }
+    res = ns.DEUS(form).solve()
+    return res["seconds_per_iteration"], res["iterations"], max(n_live // 10, 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -151,8 +189,10 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=200, help="design points per step of the CPU reference arm")
     ap.add_argument("--cpu-rows", type=int, default=1000, help="design points of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ns-iterations", type=int, default=5, help="nested-sampling iterations timed for the secondary metric")
     ap.add_argument("--dense9", action="store_true", help="keep cC in the Newton system (9 unknowns, SURVEY A.5 flop count)")
     ap.add_argument("--coupled", action="store_true", help="one coupled 6-unknown Newton system instead of the block-triangular solve")
+    ap.add_argument("--generic-blocks", action="store_true", help="block-triangular solve through the generic point-op / NS path (no POLY1)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -177,7 +217,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    lm = models.kinetics("design4", dense9=args.dense9, **({"block_triangular": False} if args.coupled else {})).lower()
+    kw = {}
+    if args.coupled:
+        kw["block_triangular"] = False
+    if args.generic_blocks:
+        kw["polynomial_blocks"] = False
+    lm = models.kinetics("design4", dense9=args.dense9, **kw).lower()
     eng = capi.Engine(lm.blob, local_rank)
     sharded = ShardedEfp(eng, world, rank)
     n_d, n_t = args.n_d, args.n_theta
@@ -237,11 +282,13 @@ def main():
     k_ms = float(np.mean(kern_ms))
     achieved = n_d * n_t * f_alg / (k_ms * 1e-3) / 1e12
     alg_bytes = 8 * (n_d * lm.d_dim + n_t * (lm.p_dim + 1) + n_d)
-    traffic = None                      # dram bytes per launch from the committed ncu --set full capture of this config
+    kernel_name = f"feas_kernel<{max(len(s) for s in lm.blocks)},{eng.info['scenarios_per_thread']}>"
+    traffic, ncu_pipes = None, None     # per launch, from the committed ncu --set full capture of this config
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_feas_kernel.json")))
-        if tj["kernel"] == f"feas_kernel<{max(len(s) for s in lm.blocks)}>" and tj["n_d"] == n_d and tj["n_theta"] == n_t:
+        if tj["kernel"] == kernel_name and tj["n_d"] == n_d and tj["n_theta"] == n_t:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            ncu_pipes = {k: tj[k] for k in ("fp64_pipe_active_pct", "issue_active_pct", "shared_wavefronts_pct") if k in tj}
     except (OSError, KeyError, ValueError):
         pass
 
@@ -261,6 +308,8 @@ def main():
     h2d = 8 * (n_d * lm.d_dim + n_t * lm.p_dim + n_t)
     d2h = 8 * n_d
     same = bool(np.allclose(P_host[rank * n_d:(rank + 1) * n_d], P_all[rank * n_d:(rank + 1) * n_d].cpu().numpy(), atol=1e-12))
+
+    ns_s, ns_it, ns_rep = ns_iteration_seconds(sharded, world * n_d, th_np, w_np, args.ns_iterations)
 
     if rank == 0:
         cpu = None
@@ -282,13 +331,16 @@ def main():
                        "newton_iters_per_element": I, "flops_per_eval": f_alg,
                        "state_blocks": [{"states": s, "unknowns": len(s) * lm.ncp, "linear": bool(l)} for s, l in zip(lm.blocks, lm.block_linear)]},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": traffic, "kernel": f"feas_kernel<{max(len(s) for s in lm.blocks)}>",
+                         "frac": achieved / peak_tflops, "traffic": traffic, "kernel": kernel_name, "ncu": ncu_pipes,
                          "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "peak_source": "measured in this run: pydsb_dfma_peak (independent-chain DFMA microkernel, best of 5); "
                                         "MEASURED_PEAKS.json carries no fp64 figure"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "matches_device_path": same},
+            "ns_iteration": {"seconds": ns_s, "iterations_timed": ns_it, "n_live": world * n_d, "proposals_per_iteration": ns_rep,
+                             "what": "pyds_b200.ns: ellipsoid proposals (host) + P(feasible) of the proposals over all theta "
+                                     "through the host-buffer path + live-set update"},
             "gpu_launches": cnt["launches"],
             "clocks": clocks,
             "counters": cnt,

@@ -46,7 +46,8 @@ enum {
 enum {
     PYDSB_INFO_NS = 0, PYDSB_INFO_NQ, PYDSB_INFO_NG, PYDSB_INFO_D_DIM, PYDSB_INFO_P_DIM, PYDSB_INFO_NZ,
     PYDSB_INFO_NFE, PYDSB_INFO_NCP, PYDSB_INFO_N_UNITS, PYDSB_INFO_SMEM_BYTES, PYDSB_INFO_BLOCKS_PER_SM,
-    PYDSB_INFO_NUM_SMS, PYDSB_INFO_REGS_PER_THREAD, PYDSB_INFO_COUNT
+    PYDSB_INFO_NUM_SMS, PYDSB_INFO_REGS_PER_THREAD, PYDSB_INFO_SCENARIOS_PER_THREAD, PYDSB_INFO_PROGRAM_LENGTH,
+    PYDSB_INFO_COUNT
 };
 
 /* indices into the array returned by pydsb_get_counters */

@@ -83,10 +83,13 @@ struct Model {
 typedef void (*FeasFn)(const ExecImage, const LaunchArgs);
 typedef void (*SensFn)(const ExecImage, const RecourseArgs);
 
-// MAXNS = largest coupled block, SPT = scenarios per thread.  SPT = 2 (both scenarios of a thread moved by one
-// LDS.128, fetch and dispatch shared) executes ~30 % fewer instructions per scenario but halves the resident
-// warps; the interpreter is bound by its dependent fetch -> dispatch -> load -> math chain, i.e. by warps in
-// flight, and measures 20 % slower on C3 -- kept selectable (PYDSB_SPT=2) for models where that flips.
+// MAXNS = largest coupled block, SPT = scenarios per thread.  SPT = 2: both scenarios of a thread are moved by
+// one LDS.128 and share every fetch, dispatch and address of the interpreter (~30 % fewer instructions per
+// scenario) at half the resident warps.  Measured on C3: 20 % slower than SPT = 1 while the Newton loops ran through
+// the dispatch loop (bound by the dependent fetch -> dispatch -> load -> math chain, i.e. by warps in flight),
+// 7 % faster once the one-state blocks run in registers (POLY1; bound by instruction issue).  Default: 2 when
+// every block is a polynomial one-state block, else 1; PYDSB_SPT=1|2 overrides (2 needs one-state blocks: the two
+// Newton systems have to fit the register file).
 FeasFn feas_for(int ns, int spt)
 {
     switch (ns * 10 + spt) {
@@ -107,9 +110,9 @@ int image_maxns(const ExecImage& g)
 }
 
 // scenarios per thread of the feasibility program; PYDSB_SPT=1|2 overrides (experiments)
-int choose_spt(int maxns)
+int choose_spt(int maxns, bool all_poly)
 {
-    int spt = 1;
+    int spt = (maxns == 1 && all_poly) ? 2 : 1;
     if (const char* e = getenv("PYDSB_SPT")) {
         const int v = atoi(e);
         if (v == 1 || (v == 2 && maxns == 1)) spt = v;
@@ -175,10 +178,14 @@ int build_program(const Sections& secs, bool sens, Program& P)
         // scenarios per thread: the byte offsets below are laid out for slot stride spt*BLOCK doubles
         const Section* bs0 = find(secs, "BLKS");
         int maxns = 1;
+        bool all_poly = bs0 != nullptr;
         if (bs0)
-            for (int b = 0; b < g.n_blocks && 5 * b < (int)bs0->count; ++b)
-                if (reinterpret_cast<const uint16_t*>(bs0->data)[5 * b] > maxns) maxns = reinterpret_cast<const uint16_t*>(bs0->data)[5 * b];
-        g.spt = sens ? 1 : choose_spt(maxns);
+            for (int b = 0; b < g.n_blocks && 5 * b + 1 < (int)bs0->count; ++b) {
+                const uint16_t* B0 = reinterpret_cast<const uint16_t*>(bs0->data);
+                if (B0[5 * b] > maxns) maxns = B0[5 * b];
+                all_poly = all_poly && (B0[5 * b + 1] & 2u);
+            }
+        g.spt = sens ? 1 : choose_spt(maxns, all_poly);
     }
     const unsigned US = (unsigned)g.spt * BLOCK * 8u;      // bytes between consecutive slots
     {
@@ -557,7 +564,7 @@ int pydsb_model_info(void* handle, long long* out, int n)
     if (!m || !out) return fail(PYDSB_ERR_INVALID, "null handle/out");
     const ExecImage& g = m->prog[0].img;
     long long v[PYDSB_INFO_COUNT] = {g.ns, g.nq, g.ng, g.d_dim, g.p_dim, g.nz, g.nfe, 3, g.n_units, g.smem_bytes,
-                                     m->blocks_per_sm, m->num_sms, m->regs};
+                                     m->blocks_per_sm, m->num_sms, m->regs, g.spt, g.n_prog};
     for (int i = 0; i < n && i < PYDSB_INFO_COUNT; ++i) out[i] = v[i];
     return PYDSB_OK;
 }
