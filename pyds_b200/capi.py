@@ -161,26 +161,18 @@ class Engine:
         _check(self._lib.pydsb_eval(self._h, ptr(d), n_d, ptr(theta), ptr(w), n_t, ptr(z), z_mode if z is not None else Z_MODEL,
                                     ptr(g_out), ptr(ind_out), ptr(P_out), ctypes.c_void_p(stream.cuda_stream)))
 
-    def recourse_solve(self, d, theta, w=None, z0=None, per_scenario=False, global_group=False, mu0=0.0, mu_min=0.0, lam0=0.0, step_tol=0.0,
-                       max_iter=0, check_every=0):
-        """Optimise the controls (numpy in / numpy out).  Returns dict(z, phi, status, iters); ``z`` is
-        (n_d, nz) in shared mode and (n_d, n_t, nz) in per-scenario mode."""
+    def recourse_solve_device(self, d, theta, w=None, z0=None, per_scenario=False, global_group=False, mu0=0.0, mu_min=0.0,
+                              lam0=0.0, step_tol=0.0, max_iter=0, check_every=0):
+        """Optimise the controls; contiguous fp64 CUDA tensors in, CUDA tensors out (z (G, nz), phi, status, iters with
+        G = n_d * n_t groups in per-scenario mode, 1 with ``global_group``, else n_d).  Synchronous."""
         import torch
         dev = torch.device("cuda", self.device)
-        d = _np64(d).reshape(-1, self.info["d_dim"])
-        theta = _np64(theta).reshape(-1, self.info["p_dim"])
         n_d, n_t, nz = d.shape[0], theta.shape[0], self.info["nz"]
         mode = 1 if per_scenario else (2 if global_group else 0)
         G = n_d * n_t if per_scenario else (1 if global_group else n_d)
-        td = torch.from_numpy(d).to(dev)
-        tt = torch.from_numpy(theta).to(dev)
-        tw = None if w is None else torch.from_numpy(_np64(w)).to(dev)
-        tz0, rows = None, 0
-        if z0 is not None:
-            z0 = _np64(z0).reshape(-1, nz)
-            if z0.shape[0] not in (1, G):
-                raise ValueError(f"z0 must have 1 or {G} rows")
-            tz0, rows = torch.from_numpy(z0).to(dev), z0.shape[0]
+        rows = 0 if z0 is None else z0.shape[0]
+        if z0 is not None and rows not in (1, G):
+            raise ValueError(f"z0 must have 1 or {G} rows")
         z = torch.empty((max(G, 1), nz), dtype=torch.float64, device=dev)
         phi = torch.empty(max(G, 1), dtype=torch.float64, device=dev)
         st = torch.zeros(max(G, 1), dtype=torch.int32, device=dev)
@@ -189,12 +181,33 @@ class Engine:
         ptr = lambda t: None if t is None else t.data_ptr()
         stream = torch.cuda.current_stream(self.device)
         torch.cuda.synchronize(self.device)
-        _check(self._lib.pydsb_recourse_solve(self._h, mode, ptr(td), n_d, ptr(tt), ptr(tw), n_t, ptr(tz0),
+        _check(self._lib.pydsb_recourse_solve(self._h, mode, ptr(d), n_d, ptr(theta), ptr(w), n_t, ptr(z0),
                                               rows, opts.ctypes.data, ptr(z), ptr(phi), ptr(st), ptr(it),
                                               ctypes.c_void_p(stream.cuda_stream)))
+        return dict(z=z[:G], phi=phi[:G], status=st[:G], iters=it[:G])
+
+    def recourse_solve(self, d, theta, w=None, z0=None, per_scenario=False, global_group=False, **opts):
+        """Optimise the controls (numpy in / numpy out).  Returns dict(z, phi, status, iters); ``z`` is
+        (n_d, nz) in shared mode and (n_d, n_t, nz) in per-scenario mode."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        d = _np64(d).reshape(-1, self.info["d_dim"])
+        theta = _np64(theta).reshape(-1, self.info["p_dim"])
+        n_d, n_t, nz = d.shape[0], theta.shape[0], self.info["nz"]
+        G = n_d * n_t if per_scenario else (1 if global_group else n_d)
+        td = torch.from_numpy(d).to(dev)
+        tt = torch.from_numpy(theta).to(dev)
+        tw = None if w is None else torch.from_numpy(_np64(w)).to(dev)
+        tz0 = None
+        if z0 is not None:
+            z0 = _np64(z0).reshape(-1, nz)
+            if z0.shape[0] not in (1, G):
+                raise ValueError(f"z0 must have 1 or {G} rows")
+            tz0 = torch.from_numpy(z0).to(dev)
+        r = self.recourse_solve_device(td, tt, tw, tz0, per_scenario=per_scenario, global_group=global_group, **opts)
         shape = (n_d, n_t, nz) if per_scenario else ((nz,) if global_group else (n_d, nz))
-        out = dict(z=z[:G].cpu().numpy().reshape(shape), phi=phi[:G].cpu().numpy(), status=st[:G].cpu().numpy(),
-                   iters=it[:G].cpu().numpy())
+        out = dict(z=r["z"].cpu().numpy().reshape(shape), phi=r["phi"].cpu().numpy(), status=r["status"].cpu().numpy(),
+                   iters=r["iters"].cpu().numpy())
         if per_scenario:
             for k in ("phi", "status", "iters"):
                 out[k] = out[k].reshape(n_d, n_t)

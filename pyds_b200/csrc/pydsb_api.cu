@@ -715,13 +715,19 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     const int acc_per_group = (int)acc_per_group_ll;
     // workspace: doubles then ints
     const size_t nd_dbl = (size_t)G * (2 * nz + 2 + nz + (size_t)nz * nz + 2) + (size_t)G * acc_per_group * NV;
-    const size_t nd_int = (size_t)G * 3 + 1;
+    const bool compact = per_scenario == 1;      // running scenarios are compacted after every iteration
+    const size_t nd_int = (size_t)G * 3 + 2;
     double* ws = nullptr;
     int* wsi = nullptr;
+    long long* act = nullptr;                    // two active lists (per-scenario mode)
     CUDA_TRY(cudaMalloc(&ws, nd_dbl * sizeof(double)));
     if (cudaMalloc(&wsi, nd_int * sizeof(int)) != cudaSuccess) {
         cudaFree(ws);
         return fail(PYDSB_ERR_CUDA, "cudaMalloc(workspace)");
+    }
+    if (compact && cudaMalloc(&act, 2 * (size_t)G * sizeof(long long)) != cudaSuccess) {
+        cudaFree(ws); cudaFree(wsi);
+        return fail(PYDSB_ERR_CUDA, "cudaMalloc(active lists)");
     }
     double* z_cur = ws;
     double* z_try = z_cur + (size_t)G * nz;
@@ -735,9 +741,9 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     int* status = wsi;
     int* first = status + G;
     int* iters = first + G;
-    int* n_running = iters + G;
+    int* counts = iters + G;                     // [2]: groups still running after the even / odd iterations
 
-    auto cleanup = [&]() { cudaFree(ws); cudaFree(wsi); };
+    auto cleanup = [&]() { cudaFree(ws); cudaFree(wsi); if (act) cudaFree(act); };
 #define CUDA_TRY_WS(expr)                                                                         \
     do {                                                                                          \
         cudaError_t _e = (expr);                                                                  \
@@ -764,23 +770,33 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     LmArgs la{};
     la.n_groups = G; la.nz = nz; la.n_tiles = acc_per_group; la.acc = acc; la.lo = m->d_zlo; la.hi = m->d_zhi;
     la.zfix = m->d_zfix; la.z_cur = z_cur; la.z_try = z_try; la.F_cur = F_cur; la.raw_cur = raw_cur; la.gr = gr; la.H = Hh;
-    la.lam = lam; la.mu = mu; la.status = status; la.first = first; la.iters = iters; la.n_running = n_running;
+    la.lam = lam; la.mu = mu; la.status = status; la.first = first; la.iters = iters;
     la.mu_min = o[1]; la.lam0 = o[2]; la.step_tol = o[3]; la.max_iter = max_iter;
     const long long total_tiles = n_d * (long long)n_tiles;
-    if (total_tiles > 0x7fffffffLL) { cleanup(); return fail(PYDSB_ERR_INVALID, "grid too large"); }
+    if (total_tiles > 0x7fffffffLL || G > 0x7fffffffLL) { cleanup(); return fail(PYDSB_ERR_INVALID, "grid too large"); }
     // every group stops after max_iter evaluations (status 3) at the latest
+    const long long* act_in = nullptr;           // null: every group (first iteration; always in the shared modes)
+    const int* n_in = nullptr;
+    long long upper = G;                         // host-known upper bound of the groups still running
     for (int it = 0; it < max_iter + 1; ++it) {
-        CUDA_TRY_WS(cudaMemsetAsync(n_running, 0, sizeof(int), st));
-        fn<<<(unsigned)total_tiles, BLOCK, img.smem_bytes, st>>>(img, ra);
+        int* n_out = counts + (it & 1);
+        CUDA_TRY_WS(cudaMemsetAsync(n_out, 0, sizeof(int), st));
+        ra.active = act_in; ra.n_active = n_in;
+        const unsigned sens_grid = compact ? (unsigned)((upper + BLOCK - 1) / BLOCK) : (unsigned)total_tiles;
+        fn<<<sens_grid, BLOCK, img.smem_bytes, st>>>(img, ra);
         CUDA_TRY_WS(cudaGetLastError());
-        lm_update_kernel<<<gb, tb, 0, st>>>(la);
+        la.active_in = act_in; la.n_active_in = n_in; la.n_running = n_out;
+        la.active_out = compact ? act + (size_t)(it & 1) * G : nullptr;
+        lm_update_kernel<<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
         CUDA_TRY_WS(cudaGetLastError());
         m->launches += 2;
+        if (compact) { act_in = la.active_out; n_in = n_out; }
         if ((it + 1) % check_every == 0 || it == max_iter) {
             int running = 0;
-            CUDA_TRY_WS(cudaMemcpyAsync(&running, n_running, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY_WS(cudaMemcpyAsync(&running, n_out, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY_WS(cudaStreamSynchronize(st));
             if (running == 0) break;
+            if (compact) upper = running;
         }
     }
     CUDA_TRY_WS(cudaMemcpyAsync(z_out, z_cur, (size_t)G * nz * sizeof(double), cudaMemcpyDeviceToDevice, st));

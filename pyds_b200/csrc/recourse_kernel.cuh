@@ -43,6 +43,10 @@ struct RecourseArgs {
     double* acc;               // shared: (n_d, n_tiles, NV) tile partials ; per-scenario: (G, NV)
     unsigned long long* counters;
     int sens_slot;             // first unit of the per-thread sensitivity block (after the program's units)
+    // per-scenario mode: the scenarios still running, compacted by lm_update_kernel after every iteration so
+    // that finished scenarios cost nothing (null list = every scenario, the first iteration)
+    const long long* active;
+    const int* n_active;
 };
 
 __host__ __device__ inline int recourse_nv(int nz) { return 2 + nz + nz * (nz + 1) / 2; }
@@ -96,16 +100,29 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
     const int NV = recourse_nv(nz);
 
     const long long t = blockIdx.x;
-    const long long i_d = t / ra.n_tiles;
-    const long long j0 = (t % ra.n_tiles) * (long long)BLOCK;
-    const long long rem = ra.n_t - j0;
-    const int rows = rem < BLOCK ? (int)rem : BLOCK;
-    const bool valid = tid < rows;
-    const int row = valid ? tid : rows - 1;
-    const long long j = j0 + row;
     const bool per_scen = ra.per_scenario == 1;
-    const long long grp = per_scen ? (i_d * ra.n_t + j) : (ra.per_scenario == 2 ? 0 : i_d);
-    if (!per_scen && ra.status[grp] != 0) return;               // block-uniform: group already finished
+    long long i_d, j, grp;
+    bool valid;
+    if (per_scen) {
+        // thread k of the launch owns the k-th running scenario
+        const long long n_run = ra.n_active ? (long long)*ra.n_active : ra.n_d * ra.n_t;
+        const long long k0 = t * (long long)BLOCK;
+        if (k0 >= n_run) return;                                 // block-uniform
+        valid = k0 + tid < n_run;
+        const long long k = valid ? k0 + tid : n_run - 1;        // idle lanes replay the last scenario
+        grp = ra.active ? ra.active[k] : k;
+        i_d = grp / ra.n_t;
+        j = grp % ra.n_t;
+    } else {
+        i_d = t / ra.n_tiles;
+        const long long j0 = (t % ra.n_tiles) * (long long)BLOCK;
+        const long long rem = ra.n_t - j0;
+        const int rows = rem < BLOCK ? (int)rem : BLOCK;
+        valid = tid < rows;
+        j = j0 + (valid ? tid : rows - 1);
+        grp = ra.per_scenario == 2 ? 0 : i_d;
+        if (ra.status[grp] != 0) return;                         // block-uniform: group already finished
+    }
     const bool active = valid && ra.status[grp] == 0;
     if (!__syncthreads_or(active)) return;
 
@@ -315,7 +332,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
             double sm = 0.0;
 #pragma unroll
             for (int wq = 0; wq < BLOCK / 32; ++wq) sm += wsum[wq * NV + v];     // fixed order: deterministic
-            ra.acc[(i_d * ra.n_tiles + (t % ra.n_tiles)) * NV + v] = sm;
+            ra.acc[t * NV + v] = sm;                                 // (i_d, tile) == blockIdx.x in the shared modes
         }
     }
     if (ra.counters) {
@@ -349,16 +366,43 @@ struct LmArgs {
     int* first;
     int* iters;
     int* n_running;            // device counter of groups still running after this update
+    // compaction (per-scenario mode): thread k updates group active_in[k], k < *n_active_in (null = identity over
+    // all groups); groups that keep running are appended to active_out (warp-aggregated atomics on n_running)
+    const long long* active_in;
+    const int* n_active_in;
+    long long* active_out;
     double mu_min, lam0, step_tol;
     int max_iter;
 };
 
-// One thread per group: the accept/reject + step logic of oracle/recourse.py::minimize_hinge.
+__device__ bool lm_update_group(const LmArgs& a, long long g);
+
+// One thread per (running) group.
 __global__ void lm_update_kernel(const LmArgs a)
 {
-    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (g >= a.n_groups) return;
-    if (a.status[g] != 0) return;
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n_in = a.n_active_in ? (long long)*a.n_active_in : a.n_groups;
+    bool done = true;                          // lanes without a running group append nothing
+    long long g = 0;
+    if (k < n_in) {
+        g = a.active_in ? a.active_in[k] : k;
+        if (a.status[g] == 0) done = lm_update_group(a, g);
+    }
+    // running groups: count them, and (per-scenario mode) append them to the next active list
+    const unsigned run_mask = __ballot_sync(0xffffffffu, !done);
+    if (run_mask) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(run_mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(a.n_running, __popc(run_mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (!done && a.active_out) a.active_out[base + __popc(run_mask & ((1u << lane) - 1u))] = g;
+    }
+}
+
+// The accept/reject + step logic of oracle/recourse.py::minimize_hinge for one group; true when it finished.
+__device__ bool lm_update_group(const LmArgs& a, long long g)
+{
     const int nz = a.nz;
     const int NV = recourse_nv(nz);
     double F_t = 0.0, raw_t = 0.0, g_t[MAX_NZ], H_t[MAX_NZ * MAX_NZ];
@@ -482,7 +526,7 @@ __global__ void lm_update_kernel(const LmArgs a)
             done = true;
         }
     }
-    if (!done) atomicAdd(a.n_running, 1);
+    return done;
 }
 
 __global__ void lm_init_kernel(long long n_groups, int nz, const double* z0, int z0_rows, double* z_cur, double* z_try,
