@@ -19,6 +19,7 @@
 #define PYDSB_H
 
 #include <stddef.h>
+#include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -71,6 +72,13 @@ int pydsb_version(void);
  * tape blob (pyds_b200/model.py) and uploaded to the device here. */
 int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handle);
 int pydsb_model_destroy(void* handle);
+/* Host-only half of pydsb_model_create (needs no CUDA device): assembles the blob's tapes into the
+ * pre-decoded per-scenario program feas_kernel interprets (csrc/assembler.h, csrc/feas_kernel.cuh) and copies up
+ * to `cap` 32-bit words of it into `words`; *n_words = the full length.  info = { scenarios per thread,
+ * register-file units, shared-memory bytes per CTA, program length in 16-byte words }.  What it replaces in
+ * the reference: the GAMS model file Pyomo writes for every solve (reference pyds/solver.py:50-55). */
+int pydsb_assemble(const void* blob, size_t nbytes, uint32_t* words, size_t cap, size_t* n_words, long long* info,
+                   int n_info);
 int pydsb_model_info(void* handle, long long* out, int n);
 
 /* The whole hot path in one launch sequence: state solve (collocation Newton), CQAs g, big-M

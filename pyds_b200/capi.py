@@ -22,7 +22,7 @@ COUNTER_NAMES = ["scenarios", "newton_iters", "newton_warp_iters", "failed", "la
 
 EXPORTS = ["pydsb_last_error", "pydsb_version", "pydsb_model_create", "pydsb_model_destroy", "pydsb_model_info",
            "pydsb_eval", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_recourse_solve", "pydsb_get_counters",
-           "pydsb_dfma_peak"]
+           "pydsb_dfma_peak", "pydsb_assemble"]
 
 
 class PydsbError(RuntimeError):
@@ -50,6 +50,9 @@ def load():
     L.pydsb_version.restype = ci
     L.pydsb_model_create.restype = ci
     L.pydsb_model_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ci, ctypes.POINTER(vp)]
+    L.pydsb_assemble.restype = ci
+    L.pydsb_assemble.argtypes = [ctypes.c_char_p, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
+                                 ctypes.POINTER(ll), ci]
     L.pydsb_model_destroy.restype = ci
     L.pydsb_model_destroy.argtypes = [vp]
     L.pydsb_model_info.restype = ci
@@ -217,6 +220,40 @@ class Engine:
         buf = (ctypes.c_ulonglong * len(COUNTER_NAMES))()
         _check(self._lib.pydsb_get_counters(self._h, buf, len(COUNTER_NAMES), 1 if reset else 0))
         return {k: int(v) for k, v in zip(COUNTER_NAMES, buf)}
+
+
+# opcode numbering of the assembled program (csrc/feas_kernel.cuh, enum XCode)
+XCODES = ["POLY1", "MUL_NW", "NS1", "ELEM_END",
+          "FMA_NWN", "FMA_NWW", "SQR_W", "FMS_NWW", "MUL_WW", "ADD_NW", "MUL1", "FMA1", "ADD1", "NS1L", "NS2", "NB1",
+          "FMA_WWN", "FMA_WWW", "FMS_NWN", "FMS_WWN", "FMS_WWW", "FNMA_NWN", "FNMA_NWW", "FNMA_WWN", "FNMA_WWW", "ADD_WW",
+          "SUB_WW", "SUB_NW", "SUB_WN", "DIV_NW", "DIV_WN", "DIV_WW",
+          "NEG_W", "RCP_W", "ABS_W", "MOV_W", "BC_N", "MIN_NW", "MIN_WW", "MAX_NW", "MAX_WW", "COLD_W",
+          "FMS1", "FNMA1", "SUB1", "DIV1", "SQR1", "NEG1", "RCP1", "ABS1", "MOV1", "MIN1", "MAX1", "COLD1",
+          "INIT", "LDCTRL", "NB2", "NB3", "NS3", "NS2L", "NS3L", "XEND", "END"]
+
+
+def assemble(blob: bytes):
+    """Host-only: the pre-decoded program the feasibility kernel runs for ``blob`` (no GPU needed).  Returns
+    ``(ops, info)``: ``ops`` is the list of ``(pcw, name, words)`` in program order, ``info`` the layout figures."""
+    L = load()
+    n = ctypes.c_size_t()
+    info = (ctypes.c_longlong * 4)()
+    _check(L.pydsb_assemble(blob, len(blob), None, 0, ctypes.byref(n), info, 4))
+    words = np.zeros(n.value, dtype=np.uint32)
+    _check(L.pydsb_assemble(blob, len(blob), words.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n), info, 4))
+    ns_len = lambda k: 1 + (k + 3 * k + 3 * k * k + 3) // 4
+    ops, pcw = [], 0
+    while 4 * pcw < len(words):
+        code = int(words[4 * pcw])
+        name = XCODES[code]
+        if name in ("NS1", "NS1L"): length = ns_len(1)
+        elif name in ("NS2", "NS2L"): length = ns_len(2)
+        elif name in ("NS3", "NS3L"): length = ns_len(3)
+        elif name == "ELEM_END": length = 1 + int(words[4 * pcw + 2])
+        else: length = 2
+        ops.append((pcw, name, words[4 * pcw:4 * (pcw + length)].copy()))
+        pcw += length
+    return ops, dict(zip(("scenarios_per_thread", "units", "smem_bytes", "program_length"), (int(v) for v in info)))
 
 
 def dfma_peak(device: int = 0, repeats: int = 5):

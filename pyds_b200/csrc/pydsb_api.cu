@@ -157,7 +157,7 @@ bool resolve_table(const Sections& secs, const char* tag, int n, int cap, unsign
 }
 
 // Parse one program's sections into an ExecImage + device buffers.
-int build_program(const Sections& secs, bool sens, Program& P)
+int build_program(const Sections& secs, bool sens, Program& P, bool upload = true)
 {
     static const char* need[] = {"HEAD", "DBLS", "CNST", "ADOT", "BWTS", "BIGM", "ZFIX", "TPRO", "TELM", "TPNT", "TGEE",
                                  "RPAR", "RX0_", "RQ0_", "RZ__", "RF__", "RJ__", "RFQ_", "RG__", "CMAP"};
@@ -408,6 +408,7 @@ int build_program(const Sections& secs, bool sens, Program& P)
     o += units * g.spt * BLOCK * 8;
     g.smem_bytes = o;
 
+    if (!upload) return PYDSB_OK;                           // host-only assembly (pydsb_assemble)
     cudaError_t e = cudaMalloc(&P.d_code, code.size() * 8 + 8);
     if (e == cudaSuccess) e = cudaMemcpy(P.d_code, code.data(), code.size() * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&P.d_consts, (size_t)g.n_const * 8 + 8);
@@ -419,6 +420,40 @@ int build_program(const Sections& secs, bool sens, Program& P)
     g.consts = static_cast<const double*>(P.d_consts);
     g.tabs = static_cast<const uint16_t*>(P.d_tabs);
     P.present = true;
+    return PYDSB_OK;
+}
+
+// Split a blob into the section lists of its (one or two) programs.
+int split_blob(const void* blob, size_t nbytes, Sections (&progs)[2], int& n_progs)
+{
+    if (!blob || nbytes < 16) return fail(PYDSB_ERR_INVALID, "null or truncated blob");
+    const unsigned char* p = static_cast<const unsigned char*>(blob);
+    uint32_t magic, ver, nsec;
+    memcpy(&magic, p, 4); memcpy(&ver, p + 4, 4); memcpy(&nsec, p + 8, 4);
+    if (magic != 0x42534450u || ver != 1u) return fail(PYDSB_ERR_INVALID, "bad blob magic/version");
+    int cur = 0;
+    size_t off = 16;
+    static const size_t dsz[4] = {4, 8, 8, 2};
+    for (uint32_t i = 0; i < nsec; ++i) {
+        if (off + 16 > nbytes) return fail(PYDSB_ERR_INVALID, "truncated section header");
+        Section s{};
+        memcpy(s.tag, p + off, 4);
+        memcpy(&s.dtype, p + off + 4, 4);
+        memcpy(&s.count, p + off + 8, 4);
+        if (s.dtype > 3) return fail(PYDSB_ERR_INVALID, "bad section dtype");
+        off += 16;
+        size_t nb = (size_t)s.count * dsz[s.dtype];
+        nb = (nb + 7) / 8 * 8;
+        if (off + nb > nbytes) return fail(PYDSB_ERR_INVALID, "truncated section payload");
+        s.data = p + off;
+        off += nb;
+        if (strncmp(s.tag, "PSEP", 4) == 0) {
+            if (++cur > 1) return fail(PYDSB_ERR_INVALID, "more than two programs in blob");
+            continue;
+        }
+        progs[cur].push_back(s);
+    }
+    n_progs = cur + 1;
     return PYDSB_OK;
 }
 
@@ -443,39 +478,19 @@ int pydsb_version(void) { return 1; }
 int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handle)
 {
     if (!blob || !handle || nbytes < 16) return fail(PYDSB_ERR_INVALID, "null or truncated blob");
-    const unsigned char* p = static_cast<const unsigned char*>(blob);
-    uint32_t magic, ver, nsec;
-    memcpy(&magic, p, 4); memcpy(&ver, p + 4, 4); memcpy(&nsec, p + 8, 4);
-    if (magic != 0x42534450u || ver != 1u) return fail(PYDSB_ERR_INVALID, "bad blob magic/version");
+    Sections progs[2];
+    int n_progs = 0;
+    {
+        const int prc = split_blob(blob, nbytes, progs, n_progs);
+        if (prc != PYDSB_OK) return prc;
+    }
+    const int cur = n_progs - 1;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
         return fail(PYDSB_ERR_NO_DEVICE, "no CUDA device visible: pyds_b200 has no CPU fallback");
     }
     if (device < 0 || device >= ndev) return fail(PYDSB_ERR_INVALID, "device index out of range");
-    Sections progs[2];
-    int cur = 0;
-    size_t off = 16;
-    static const size_t dsz[4] = {4, 8, 8, 2};
-    for (uint32_t i = 0; i < nsec; ++i) {
-        if (off + 16 > nbytes) return fail(PYDSB_ERR_INVALID, "truncated section header");
-        Section s{};
-        memcpy(s.tag, p + off, 4);
-        memcpy(&s.dtype, p + off + 4, 4);
-        memcpy(&s.count, p + off + 8, 4);
-        if (s.dtype > 3) return fail(PYDSB_ERR_INVALID, "bad section dtype");
-        off += 16;
-        size_t nb = (size_t)s.count * dsz[s.dtype];
-        nb = (nb + 7) / 8 * 8;
-        if (off + nb > nbytes) return fail(PYDSB_ERR_INVALID, "truncated section payload");
-        s.data = p + off;
-        off += nb;
-        if (strncmp(s.tag, "PSEP", 4) == 0) {
-            if (++cur > 1) return fail(PYDSB_ERR_INVALID, "more than two programs in blob");
-            continue;
-        }
-        progs[cur].push_back(s);
-    }
     CUDA_TRY(cudaSetDevice(device));
     Model* m = new Model();
     m->device = device;
@@ -536,6 +551,24 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
     m->blocks_per_sm = bps > 0 ? bps : 1;
     m->regs = fa.numRegs;
     *handle = m;
+    return PYDSB_OK;
+}
+
+int pydsb_assemble(const void* blob, size_t nbytes, uint32_t* words, size_t cap, size_t* n_words, long long* info, int n_info)
+{
+    Sections progs[2];
+    int n_progs = 0;
+    int rc = split_blob(blob, nbytes, progs, n_progs);
+    if (rc != PYDSB_OK) return rc;
+    Program P;
+    rc = build_program(progs[0], false, P, /*upload=*/false);
+    if (rc != PYDSB_OK) return rc;
+    if (n_words) *n_words = P.xprog.size();
+    if (words)
+        for (size_t i = 0; i < P.xprog.size() && i < cap; ++i) words[i] = P.xprog[i];
+    const ExecImage& g = P.img;
+    const long long v[4] = {g.spt, g.n_units + (g.zero_off ? 1 : 0), g.smem_bytes, g.n_prog};
+    for (int i = 0; info && i < n_info && i < 4; ++i) info[i] = v[i];
     return PYDSB_OK;
 }
 
