@@ -404,7 +404,7 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
     g.off_land = o; o = align_up(o + land, 128);
     g.off_slots = o;
     int units = g.n_units + (g.zero_off ? 1 : 0);
-    if (sens) units += (g.ns + g.nq + g.ng) * g.nz;        // Sx, Sq, Dc blocks of sens_kernel
+    if (sens) units += recourse_sens_rows(g.ns, g.nq, g.ng) * g.nz;     // Sx, Sq (later Dc + one row) of sens_kernel
     o += units * g.spt * BLOCK * 8;
     g.smem_bytes = o;
 

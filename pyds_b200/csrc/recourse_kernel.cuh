@@ -50,9 +50,12 @@ struct RecourseArgs {
 };
 
 __host__ __device__ inline int recourse_nv(int nz) { return 2 + nz + nz * (nz + 1) / 2; }
+// rows (of nz units each) of the per-thread sensitivity block: Sx (ns) and Sq (nq) while the elements are
+// integrated, then Dc (ng) + one spare row
+__host__ __device__ inline int recourse_sens_rows(int ns, int nq, int ng) { return ns + nq > ng + 1 ? ns + nq : ng + 1; }
 
 template <int NS>
-__global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
+__global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
     sens_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ RecourseArgs ra)
 {
     constexpr int N = 3 * NS;
@@ -95,7 +98,9 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
     const int nz = img.nz, nq = img.nq, ng = img.ng;
     double* const Sx = S + (size_t)ra.sens_slot * BLOCK;       // Sx[n*nz + c]
     double* const Sq = Sx + (size_t)NS * nz * BLOCK;           // Sq[q*nz + c]
-    double* const Dc = Sq + (size_t)nq * nz * BLOCK;           // Dc[k*nz + c] = d c_k / d z_c
+    // Dc[k*nz + c] = d c_k / d z_c overwrites the sensitivity block column by column once the CQAs are known
+    // (recourse_sens_rows() rows: the ng rows of Dc plus one spare row for the softmax-weighted gradient)
+    double* const Dc = Sx;
     const double h = 1.0 / (double)img.nfe;
     const int NV = recourse_nv(nz);
 
@@ -267,7 +272,10 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
     for (int k = 0; k < ng; ++k) {
         ck[k] = vm_ld(vm, tab_g[k]) * img.bigm_inv[k];
         cmax = fmax(cmax, ck[k]);
-        for (int c = 0; c < nz; ++c) {
+    }
+    for (int c = 0; c < nz; ++c) {           // column c of Dc needs column c of [Sx; Sq] only: in place
+        double dcv[8];
+        for (int k = 0; k < ng; ++k) {
             double v = 0.0;
             if (!tab_zfix[c]) {
 #pragma unroll
@@ -275,8 +283,9 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
                 for (int q = 0; q < nq; ++q) v = fma(vm_ld(vm, tab_gq[k * nq + q]), Sq[(size_t)(q * nz + c) * BLOCK], v);
                 v *= img.bigm_inv[k];
             }
-            Dc[(size_t)(k * nz + c) * BLOCK] = v;
+            dcv[k] = v;
         }
+        for (int k = 0; k < ng; ++k) Dc[(size_t)(k * nz + c) * BLOCK] = dcv[k];
     }
     // smoothed hinge: phi = m + mu log(e^{-m/mu} + sum_k e^{(c_k-m)/mu}),  p_k = softmax weights
     const double mu = ra.mu[grp];
@@ -298,8 +307,8 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 2 : 1))
         phi = cmax + mu * log(Z);
         raw = cmax;
     }
-    // v_c = sum_k p_k dc_kc kept in the (now free) Sx block
-    double* const Vv = Sx;
+    // v_c = sum_k p_k dc_kc kept in the spare row after Dc
+    double* const Vv = Dc + (size_t)ng * nz * BLOCK;
     for (int c = 0; c < nz; ++c) {
         double v = 0.0;
         for (int k = 0; k < ng; ++k) v = fma(pk[k], Dc[(size_t)(k * nz + c) * BLOCK], v);
