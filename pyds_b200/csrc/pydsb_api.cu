@@ -78,6 +78,10 @@ struct Model {
     size_t h_pin_cap = 0;
     double* d_stage = nullptr;
     cudaStream_t own_stream = nullptr;
+    // recourse workspace kept between calls while it is small (the nested-sampling loop calls with a few hundred
+    // groups, thousands of times): cudaMalloc/cudaFree cost more than the kernels there
+    void* rws[3] = {nullptr, nullptr, nullptr};
+    size_t rws_cap[3] = {0, 0, 0};
 };
 
 typedef void (*FeasFn)(const ExecImage, const LaunchArgs);
@@ -585,6 +589,7 @@ int pydsb_model_destroy(void* handle)
     if (m->d_counters) cudaFree(m->d_counters);
     if (m->d_partial) cudaFree(m->d_partial);
     if (m->d_stage) cudaFree(m->d_stage);
+    for (void* p : m->rws) if (p) cudaFree(p);
     if (m->h_pin) cudaFreeHost(m->h_pin);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     delete m;
@@ -753,15 +758,28 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     double* ws = nullptr;
     int* wsi = nullptr;
     long long* act = nullptr;                    // two active lists (per-scenario mode)
-    CUDA_TRY(cudaMalloc(&ws, nd_dbl * sizeof(double)));
-    if (cudaMalloc(&wsi, nd_int * sizeof(int)) != cudaSuccess) {
-        cudaFree(ws);
-        return fail(PYDSB_ERR_CUDA, "cudaMalloc(workspace)");
+    const size_t want[3] = {nd_dbl * sizeof(double), nd_int * sizeof(int), compact ? 2 * (size_t)G * sizeof(long long) : 0};
+    constexpr size_t KEEP = 64u << 20;           // cache workspaces up to 64 MiB each in the model
+    void* got[3] = {nullptr, nullptr, nullptr};
+    bool owned[3] = {false, false, false};       // allocated for this call only
+    for (int i = 0; i < 3; ++i) {
+        if (want[i] == 0) continue;
+        if (want[i] <= m->rws_cap[i]) { got[i] = m->rws[i]; continue; }
+        void* p = nullptr;
+        if (cudaMalloc(&p, want[i]) != cudaSuccess) {
+            cudaGetLastError();
+            for (int k = 0; k < i; ++k) if (owned[k]) cudaFree(got[k]);
+            return fail(PYDSB_ERR_CUDA, "cudaMalloc(recourse workspace)");
+        }
+        if (want[i] <= KEEP) {
+            if (m->rws[i]) cudaFree(m->rws[i]);
+            m->rws[i] = p; m->rws_cap[i] = want[i];
+        } else {
+            owned[i] = true;
+        }
+        got[i] = p;
     }
-    if (compact && cudaMalloc(&act, 2 * (size_t)G * sizeof(long long)) != cudaSuccess) {
-        cudaFree(ws); cudaFree(wsi);
-        return fail(PYDSB_ERR_CUDA, "cudaMalloc(active lists)");
-    }
+    ws = static_cast<double*>(got[0]); wsi = static_cast<int*>(got[1]); act = static_cast<long long*>(got[2]);
     double* z_cur = ws;
     double* z_try = z_cur + (size_t)G * nz;
     double* F_cur = z_try + (size_t)G * nz;
@@ -776,7 +794,7 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     int* iters = first + G;
     int* counts = iters + G;                     // [2]: groups still running after the even / odd iterations
 
-    auto cleanup = [&]() { cudaFree(ws); cudaFree(wsi); if (act) cudaFree(act); };
+    auto cleanup = [&]() { for (int i = 0; i < 3; ++i) if (owned[i]) cudaFree(got[i]); };
 #define CUDA_TRY_WS(expr)                                                                         \
     do {                                                                                          \
         cudaError_t _e = (expr);                                                                  \

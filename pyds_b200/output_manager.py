@@ -29,3 +29,10 @@ class OutputManager:
     def write_data_to_disk(self):
         with open(self.output_path_fnx, "ab+") as f:
             pickle.dump(self.data, f)
+
+    def write_records_to_disk(self, records):
+        """Append several records with one open(): the same byte stream as ``write_data_to_disk`` once per
+        record (the two-stage manager logs one record per design point, reference run.py:67)."""
+        with open(self.output_path_fnx, "ab+") as f:
+            for rec in records:
+                pickle.dump(rec, f)

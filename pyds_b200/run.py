@@ -120,7 +120,7 @@ class TwoStageManager(Manager):
         inputs = utils.load_input(self.model, self.input_map, {self._stages[0]: d[:1], self._stages[1]: p}) if len(d) else {}
         self._current_inputs = (d, p)
         indicator = self.solver.solve(d, p, w, mode="shared") if len(d) else np.zeros((0, n_p))
-        g_list = []
+        g_list, records = [], []
         for i in range(d.shape[0]):
             g_mat = np.empty((n_p, 1))
             g_mat[:, 0] = -indicator[i]            # DEUS uses g >= 0 as "feasible"
@@ -128,7 +128,9 @@ class TwoStageManager(Manager):
             self.output_manager.clear_buffer()
             self.output_manager.add_input({self._stages[0]: d[i:i + 1], self._stages[1]: p})
             self.output_manager.add_solver_solution(self.solver.output)
-            self.output_manager.write_data_to_disk()        # one record per design point (reference run.py:67)
+            records.append(self.output_manager.data)         # one record per design point (reference run.py:67)
+        if records:
+            self.output_manager.write_records_to_disk(records)
         return g_list
 
 
