@@ -402,7 +402,7 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
     g.off_tabs = o; o = align_up(o + g.n_tabs * 2, 128);
     int land = g.spt * BLOCK * g.p_dim * 8;
     if (sens) {
-        const int need_ws = (BLOCK / 32) * recourse_nv(g.nz) * 8;
+        const int need_ws = (BLOCK / 32) * RECOURSE_STAGES * recourse_nv(g.nz) * 8;
         if (need_ws > land) land = need_ws;
     }
     g.off_land = o; o = align_up(o + land, 128);
@@ -742,7 +742,8 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     if (opts)
         for (int i = 0; i < 6; ++i)
             if (opts[i] > 0) o[i] = opts[i];
-    const int max_iter = (int)o[4], check_every = (int)o[5] < 1 ? 1 : (int)o[5];
+    const int max_iter = (int)o[4];
+    int check_every = (int)o[5] < 1 ? 1 : (int)o[5];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(m->device));
 
@@ -752,7 +753,9 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     if (acc_per_group_ll > 0x7fffffffLL) return fail(PYDSB_ERR_INVALID, "grid too large");
     const int acc_per_group = (int)acc_per_group_ll;
     // workspace: doubles then ints
-    const size_t nd_dbl = (size_t)G * (2 * nz + 2 + nz + (size_t)nz * nz + 2) + (size_t)G * acc_per_group * NV;
+    const int n_stages = RECOURSE_STAGES;
+    const size_t acc_dbl = per_scenario == 1 ? (size_t)G * recourse_nvp(img.ng, nz) : (size_t)G * acc_per_group * n_stages * NV;
+    const size_t nd_dbl = (size_t)G * (2 * nz + 2 + nz + (size_t)nz * nz + 2) + acc_dbl;
     const bool compact = per_scenario == 1;      // running scenarios are compacted after every iteration
     const size_t nd_int = (size_t)G * 3 + 2;
     double* ws = nullptr;
@@ -818,12 +821,16 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     ra.per_scenario = per_scenario;
     ra.z_try = z_try; ra.status = status; ra.mu = mu; ra.acc = acc; ra.counters = m->d_counters;
     ra.sens_slot = img.n_units;
+    ra.mu_min = o[1]; ra.n_stages = n_stages;
     LmArgs la{};
-    la.n_groups = G; la.nz = nz; la.n_tiles = acc_per_group; la.acc = acc; la.lo = m->d_zlo; la.hi = m->d_zhi;
+    la.n_groups = G; la.nz = nz; la.ng = img.ng; la.n_tiles = acc_per_group; la.per_scenario = per_scenario == 1 ? 1 : 0;
+    la.n_stages = n_stages; la.acc = acc; la.lo = m->d_zlo; la.hi = m->d_zhi;
     la.zfix = m->d_zfix; la.z_cur = z_cur; la.z_try = z_try; la.F_cur = F_cur; la.raw_cur = raw_cur; la.gr = gr; la.H = Hh;
     la.lam = lam; la.mu = mu; la.status = status; la.first = first; la.iters = iters;
     la.mu_min = o[1]; la.lam0 = o[2]; la.step_tol = o[3]; la.max_iter = max_iter;
     const long long total_tiles = n_d * (long long)n_tiles;
+    // small grids are bound by the latency of one launch, not by throughput: look at the running count every iteration
+    if (!(opts && opts[5] > 0) && total_tiles <= 4096) check_every = 1;
     if (total_tiles > 0x7fffffffLL || G > 0x7fffffffLL) { cleanup(); return fail(PYDSB_ERR_INVALID, "grid too large"); }
     // every group stops after max_iter evaluations (status 3) at the latest
     const long long* act_in = nullptr;           // null: every group (first iteration; always in the shared modes)

@@ -47,9 +47,35 @@ struct RecourseArgs {
     // that finished scenarios cost nothing (null list = every scenario, the first iteration)
     const long long* active;
     const int* n_active;
+    double mu_min;             // floor of the smoothing continuation
+    int n_stages;              // shared modes: stages of the continuation whose statistics one evaluation emits
 };
 
 __host__ __device__ inline int recourse_nv(int nz) { return 2 + nz + nz * (nz + 1) / 2; }
+// Smoothing continuation mu_0 > mu_1 > ... (mu_{s+1} = max(mu_s / 10, mu_min)): one state + sensitivity solve serves every
+// stage that is evaluated at the same controls (the c_k and their gradients do not depend on mu).  Shared modes: the
+// kernel emits the reduced statistics of up to RECOURSE_STAGES stages per evaluation; per-scenario mode: it stores the
+// scenario's own {failed, c_k, grad c_k} (recourse_nvp values) and lm_update_kernel evaluates any stage itself.
+constexpr int RECOURSE_STAGES = 6;
+__host__ __device__ inline int recourse_nvp(int ng, int nz) { return 1 + ng + ng * nz; }
+
+// smoothed hinge of one scenario: phi = m + mu log(e^{-m/mu} + sum_k e^{(c_k-m)/mu}) with m = max(0, max_k c_k), softmax
+// weights p_k; a failed state solve counts as indicator 1 with no slope
+__device__ __forceinline__ void hinge_point(int ng, const double* ck, double cmax, bool failed, double mu, double* pk,
+                                            double& phi, double& raw)
+{
+    if (failed) {
+        phi = raw = 1.0;
+        for (int k = 0; k < ng; ++k) pk[k] = 0.0;
+        return;
+    }
+    double Z = exp(-cmax / mu);
+    for (int k = 0; k < ng; ++k) { pk[k] = exp((ck[k] - cmax) / mu); Z += pk[k]; }
+    const double zi = 1.0 / Z;
+    for (int k = 0; k < ng; ++k) pk[k] *= zi;
+    phi = cmax + mu * log(Z);
+    raw = cmax;
+}
 // rows (of nz units each) of the per-thread sensitivity block: Sx (ns) and Sq (nq) while the elements are
 // integrated, then Dc (ng) + one spare row
 __host__ __device__ inline int recourse_sens_rows(int ns, int nq, int ng) { return ns + nq > ng + 1 ? ns + nq : ng + 1; }
@@ -287,61 +313,60 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
         }
         for (int k = 0; k < ng; ++k) Dc[(size_t)(k * nz + c) * BLOCK] = dcv[k];
     }
-    // smoothed hinge: phi = m + mu log(e^{-m/mu} + sum_k e^{(c_k-m)/mu}),  p_k = softmax weights
-    const double mu = ra.mu[grp];
-    double wv = 0.0;
-    if (active) {
-        wv = per_scen ? 1.0 : (ra.w ? __ldg(ra.w + j) : 1.0 / (double)ra.n_t);
-        if (ra.per_scenario == 2) wv /= (double)ra.n_d;          // the whole grid is one sample average
-    }
-    double pk[8];
-    double phi, raw;
-    if (failed) {                            // a failed state solve counts as indicator 1 with no slope
-        phi = raw = 1.0;
-        for (int k = 0; k < ng; ++k) pk[k] = 0.0;
+    if (per_scen) {
+        // the scenario's own c_k and grad c_k: lm_update_kernel evaluates the smoothed hinge for any mu
+        if (active) {
+            double* out = ra.acc + grp * recourse_nvp(ng, nz);
+            out[0] = failed ? 1.0 : 0.0;
+            for (int k = 0; k < ng; ++k) out[1 + k] = ck[k];
+            for (int k = 0; k < ng; ++k)
+                for (int c = 0; c < nz; ++c) out[1 + ng + k * nz + c] = Dc[(size_t)(k * nz + c) * BLOCK];
+        }
     } else {
-        double Z = exp(-cmax / mu);
-        for (int k = 0; k < ng; ++k) { pk[k] = exp((ck[k] - cmax) / mu); Z += pk[k]; }
-        const double zi = 1.0 / Z;
-        for (int k = 0; k < ng; ++k) pk[k] *= zi;
-        phi = cmax + mu * log(Z);
-        raw = cmax;
-    }
-    // v_c = sum_k p_k dc_kc kept in the spare row after Dc
-    double* const Vv = Dc + (size_t)ng * nz * BLOCK;
-    for (int c = 0; c < nz; ++c) {
-        double v = 0.0;
-        for (int k = 0; k < ng; ++k) v = fma(pk[k], Dc[(size_t)(k * nz + c) * BLOCK], v);
-        Vv[(size_t)c * BLOCK] = v;
-    }
-    const double wmu = wv / mu;
-    double* out = per_scen ? (ra.acc + grp * NV) : nullptr;
-        auto emit = [&](int idx, double val) {
-        if (per_scen) {
-            if (active) out[idx] = val;
-        } else {
-            const double sm = warp_sum(val);
-            if (lane == 0) wsum[warp * NV + idx] = sm;
+        double wv = 0.0;
+        if (active) {
+            wv = ra.w ? __ldg(ra.w + j) : 1.0 / (double)ra.n_t;
+            if (ra.per_scenario == 2) wv /= (double)ra.n_d;      // the whole grid is one sample average
         }
-    };
-    emit(0, wv * phi);
-    emit(1, wv * raw);
-    for (int c = 0; c < nz; ++c) emit(2 + c, wv * Vv[(size_t)c * BLOCK]);
-    int idx = 2 + nz;
-    for (int a = 0; a < nz; ++a)
-        for (int b = a; b < nz; ++b, ++idx) {
-            double hv = 0.0;
-            for (int k = 0; k < ng; ++k) hv = fma(pk[k] * Dc[(size_t)(k * nz + a) * BLOCK], Dc[(size_t)(k * nz + b) * BLOCK], hv);
-            hv = fma(-Vv[(size_t)a * BLOCK], Vv[(size_t)b * BLOCK], hv);
-            emit(idx, wmu * hv);
+        // v_c = sum_k p_k dc_kc kept in the spare row after Dc
+        double* const Vv = Dc + (size_t)ng * nz * BLOCK;
+        double mu = ra.mu[grp];
+        const int SNV = ra.n_stages * NV;
+        for (int st = 0; st < ra.n_stages; ++st) {
+            double pk[8];
+            double phi, raw;
+            hinge_point(ng, ck, cmax, failed, mu, pk, phi, raw);
+            for (int c = 0; c < nz; ++c) {
+                double v = 0.0;
+                for (int k = 0; k < ng; ++k) v = fma(pk[k], Dc[(size_t)(k * nz + c) * BLOCK], v);
+                Vv[(size_t)c * BLOCK] = v;
+            }
+            const double wmu = wv / mu;
+            double* const ws = wsum + warp * SNV + st * NV;
+            auto emit = [&](int idx, double val) {
+                const double sm = warp_sum(val);
+                if (lane == 0) ws[idx] = sm;
+            };
+            emit(0, wv * phi);
+            emit(1, wv * raw);
+            for (int c = 0; c < nz; ++c) emit(2 + c, wv * Vv[(size_t)c * BLOCK]);
+            int idx = 2 + nz;
+            for (int a = 0; a < nz; ++a)
+                for (int b = a; b < nz; ++b, ++idx) {
+                    double hv = 0.0;
+                    for (int k = 0; k < ng; ++k)
+                        hv = fma(pk[k] * Dc[(size_t)(k * nz + a) * BLOCK], Dc[(size_t)(k * nz + b) * BLOCK], hv);
+                    hv = fma(-Vv[(size_t)a * BLOCK], Vv[(size_t)b * BLOCK], hv);
+                    emit(idx, wmu * hv);
+                }
+            mu = fmax(mu / 10.0, ra.mu_min);
         }
-    if (!per_scen) {
         __syncthreads();
-        for (int v = tid; v < NV; v += BLOCK) {
+        for (int v = tid; v < SNV; v += BLOCK) {
             double sm = 0.0;
 #pragma unroll
-            for (int wq = 0; wq < BLOCK / 32; ++wq) sm += wsum[wq * NV + v];     // fixed order: deterministic
-            ra.acc[t * NV + v] = sm;                                 // (i_d, tile) == blockIdx.x in the shared modes
+            for (int wq = 0; wq < BLOCK / 32; ++wq) sm += wsum[wq * SNV + v];    // fixed order: deterministic
+            ra.acc[t * SNV + v] = sm;                                // (i_d, tile) == blockIdx.x in the shared modes
         }
     }
     if (ra.counters) {
@@ -358,8 +383,10 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
 
 struct LmArgs {
     long long n_groups;
-    int nz, n_tiles;           // n_tiles = partial sums per group (1 in per-scenario mode)
-    const double* acc;         // (G, n_tiles, NV)
+    int nz, ng, n_tiles;       // n_tiles = partial sums per group (shared modes)
+    int per_scenario;          // acc holds the group's own {failed, c_k, grad c_k} instead of reduced statistics
+    int n_stages;              // shared modes: stages per evaluation in acc
+    const double* acc;         // shared: (G, n_tiles, n_stages, NV) ; per-scenario: (G, recourse_nvp)
     const double* lo;
     const double* hi;
     const unsigned char* zfix;
@@ -409,33 +436,68 @@ __global__ void lm_update_kernel(const LmArgs a)
     }
 }
 
-// The accept/reject + step logic of oracle/recourse.py::minimize_hinge for one group; true when it finished.
-__device__ bool lm_update_group(const LmArgs& a, long long g)
+// Statistics {Phi_mu, Phi, grad, Gauss-Newton H} of one group at continuation stage `stage` (mu = the stage's value).
+__device__ void lm_group_stats(const LmArgs& a, long long g, int stage, double mu, double& F_t, double& raw_t, double* g_t,
+                               double* H_t)
 {
     const int nz = a.nz;
-    const int NV = recourse_nv(nz);
-    double F_t = 0.0, raw_t = 0.0, g_t[MAX_NZ], H_t[MAX_NZ * MAX_NZ];
+    F_t = 0.0;
+    raw_t = 0.0;
     for (int c = 0; c < nz; ++c) g_t[c] = 0.0;
     for (int i = 0; i < nz * nz; ++i) H_t[i] = 0.0;
-    for (int t = 0; t < a.n_tiles; ++t) {
-        const double* p = a.acc + (g * a.n_tiles + t) * NV;
-        F_t += p[0];
-        raw_t += p[1];
-        for (int c = 0; c < nz; ++c) g_t[c] += p[2 + c];
-        int idx = 2 + nz;
+    if (a.per_scenario) {
+        // the scenario's own c_k and grad c_k (weight 1): same formulas as the epilogue of sens_kernel
+        const int ng = a.ng;
+        const double* p = a.acc + g * recourse_nvp(ng, nz);
+        const bool failed = p[0] != 0.0;
+        const double* ck = p + 1;
+        const double* Dc = p + 1 + ng;
+        double cmax = 0.0, pk[8];
+        for (int k = 0; k < ng; ++k) cmax = fmax(cmax, ck[k]);
+        hinge_point(ng, ck, cmax, failed, mu, pk, F_t, raw_t);
+        for (int c = 0; c < nz; ++c)
+            for (int k = 0; k < ng; ++k) g_t[c] = fma(pk[k], Dc[k * nz + c], g_t[c]);
         for (int r = 0; r < nz; ++r)
-            for (int c = r; c < nz; ++c, ++idx) H_t[r * nz + c] += p[idx];
+            for (int c = r; c < nz; ++c) {
+                double hv = 0.0;
+                for (int k = 0; k < ng; ++k) hv = fma(pk[k] * Dc[k * nz + r], Dc[k * nz + c], hv);
+                H_t[r * nz + c] = fma(-g_t[r], g_t[c], hv) / mu;
+            }
+    } else {
+        const int NV = recourse_nv(nz);
+        for (int t = 0; t < a.n_tiles; ++t) {
+            const double* p = a.acc + ((g * a.n_tiles + t) * a.n_stages + stage) * NV;
+            F_t += p[0];
+            raw_t += p[1];
+            for (int c = 0; c < nz; ++c) g_t[c] += p[2 + c];
+            int idx = 2 + nz;
+            for (int r = 0; r < nz; ++r)
+                for (int c = r; c < nz; ++c, ++idx) H_t[r * nz + c] += p[idx];
+        }
     }
     for (int r = 0; r < nz; ++r)
         for (int c = 0; c < r; ++c) H_t[r * nz + c] = H_t[c * nz + r];
+}
 
+// The accept/reject + step logic of oracle/recourse.py::minimize_hinge for one group; true when it finished.
+// One call consumes one evaluation (state + sensitivity solve at z_try).  When the group converges at the current
+// mu with z_cur = the evaluated point, the next stage of the continuation needs the statistics at the same controls
+// for the smaller mu -- they are in hand (see RECOURSE_STAGES), so the stage loop continues without a new evaluation.
+__device__ bool lm_update_group(const LmArgs& a, long long g)
+{
+    const int nz = a.nz;
     double* zc = a.z_cur + g * nz;
     double* zt = a.z_try + g * nz;
     double* gr = a.gr + g * nz;
     double* H = a.H + g * nz * nz;
     a.iters[g] += 1;
-    bool converged_here = false;
     bool done = false;
+    const int stages_in_hand = a.per_scenario ? (1 << 30) : a.n_stages;
+    for (int stage = 0;; ++stage) {
+    double F_t, raw_t, g_t[MAX_NZ], H_t[MAX_NZ * MAX_NZ];
+    lm_group_stats(a, g, stage, a.mu[g], F_t, raw_t, g_t, H_t);
+    bool converged_here = false;
+    bool at_eval_point = false;               // z_cur is the point the statistics were evaluated at
     if (raw_t == 0.0) {                       // every scenario of the group is feasible: Phi = 0 exactly
         for (int c = 0; c < nz; ++c) zc[c] = zt[c];
         a.raw_cur[g] = 0.0;
@@ -458,6 +520,7 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
             if (!first) a.lam[g] = fmax(a.lam[g] / 3.0, 1e-12);
             a.first[g] = 0;
             converged_here = small;
+            at_eval_point = true;
         } else {
             a.lam[g] = a.lam[g] * 4.0;
             if (a.lam[g] >= 1e12) converged_here = true;
@@ -528,12 +591,16 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
                 a.first[g] = 1;
                 a.lam[g] = a.lam0;
                 for (int c = 0; c < nz; ++c) zt[c] = zc[c];
+                // the next stage evaluates z_try = z_cur at the smaller mu: in hand if that is the evaluated point
+                if (at_eval_point && stage + 1 < stages_in_hand) continue;
             }
         }
         if (!done && a.iters[g] >= a.max_iter) {
             a.status[g] = 3;
             done = true;
         }
+    }
+    break;
     }
     return done;
 }
