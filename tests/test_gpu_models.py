@@ -47,6 +47,30 @@ def test_generic_block_triangular_path_matches_polynomial_blocks():
         assert c["failed"] == 0 and c["scenarios"] == n_d * n_t
 
 
+def test_scenarios_per_thread_variants_agree(monkeypatch):
+    """PYDSB_SPT selects feas_kernel<1,1> / <1,2> for the all-polynomial model.  A scenario keeps iterating until
+    its whole warp has converged and the two variants group scenarios into warps differently, so g agrees to
+    round-off, not bit for bit."""
+    rng = np.random.default_rng(23)
+    n_d, n_t = 13, 700                       # ragged against both tile sizes (128 and 256)
+    d = np.stack([rng.uniform(250, 350, n_d), rng.uniform(250, 300, n_d), rng.uniform(1500, 2500, n_d), rng.uniform(0, 2.5, n_d)], axis=1)
+    p = K.theta_samples(n_t)
+    w = rng.uniform(0.5, 1.5, n_t); w /= w.sum()
+    blob = models.kinetics("design4").lower().blob
+    out = {}
+    for spt in ("1", "2"):
+        monkeypatch.setenv("PYDSB_SPT", spt)
+        eng = capi.Engine(blob, 0)
+        assert eng.info["scenarios_per_thread"] == int(spt)
+        out[spt] = eng.eval_host(d, p, w, want_g=True, want_ind=True)
+    assert np.all(np.abs(out["1"][0] - out["2"][0]) <= 1e-12 * np.maximum(np.abs(out["2"][0]), G_SCALE))
+    near = np.any(np.abs(out["2"][0]) < 1e-8 * G_SCALE, axis=-1)
+    assert np.all((out["1"][1] == out["2"][1]) | near)
+    np.testing.assert_allclose(out["1"][2], out["2"][2], rtol=0, atol=1e-12 + float(w.max()) * near.sum())
+    go, Po, _ = cbind.kinetics_grid(d, p, w, tol=1e-13)
+    assert np.all(np.abs(out["2"][0] - go) <= 1e-10 * np.maximum(np.abs(go), G_SCALE))
+
+
 def _transcendental_model():
     m = DaeModel(["a"], ["b", "c"], nfe=6)
     g = m.graph
