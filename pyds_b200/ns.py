@@ -14,6 +14,7 @@ managers do), that fused GPU path is used instead and g is never materialised.
 """
 from __future__ import annotations
 
+import heapq
 import time
 
 import numpy as np
@@ -92,6 +93,7 @@ class DEUS:
         live_p = self.efp(live)
         n_evals = len(live)
         history, iter_times = [(live.copy(), live_p.copy())], []
+        heap = None
         it = 0
         while it < self.max_iterations:
             inside = float(np.mean(live_p >= self.target))
@@ -107,14 +109,30 @@ class DEUS:
             cand_p = self.efp(cand)
             n_evals += len(cand)
             history.append((cand.copy(), cand_p.copy()))
+            # replace-the-worst, candidate by candidate; a heap of (P, slot) reproduces np.argmin's choice (lowest
+            # slot among equal minima) in O(log n_live) per candidate instead of a scan -- 1e4 proposals against 1e5
+            # live points (config C5) would spend 0.5 s per iteration in argmin
+            if heap is None:
+                heap = [(float(v), k) for k, v in enumerate(live_p)]
+                heapq.heapify(heap)
+            grown = []
             for c, cp in zip(cand, cand_p):
-                if len(live) < n_live:
-                    if cp >= live_p.min():
-                        live = np.vstack([live, c]); live_p = np.append(live_p, cp)
+                cp = float(cp)
+                if len(live_p) + len(grown) < n_live:
+                    if cp >= heap[0][0]:
+                        grown.append((c, cp))
+                        heapq.heappush(heap, (cp, len(live_p) + len(grown) - 1))
                     continue
-                k = int(np.argmin(live_p))
-                if cp > live_p[k] or (cp == live_p[k] and cp >= self.target):
-                    live[k], live_p[k] = c, cp
+                pk, k = heap[0]
+                if cp > pk or (cp == pk and cp >= self.target):
+                    heapq.heapreplace(heap, (cp, k))
+                    if k < len(live_p):
+                        live[k], live_p[k] = c, cp
+                    else:
+                        grown[k - len(live_p)] = (c, cp)
+            if grown:
+                live = np.vstack([live] + [g[0][None, :] for g in grown])
+                live_p = np.append(live_p, [g[1] for g in grown])
             iter_times.append(time.time() - t0)
             it += 1
         self.result = {
