@@ -24,6 +24,8 @@ from .solver import Solver
 
 
 class Manager:
+    shards_by_design_point = True          # design points are independent: rows can be split over the ranks
+
     def __init__(self, config):
         problem = config["problem"]
         self.stage_rules = problem["stage rules"]
@@ -87,8 +89,14 @@ class Manager:
         except ImportError:
             pass
         from .parallel import ShardedEfp, shard_rows
-        a, b = shard_rows(len(d), world, rank)
         w_arr = np.full(len(p), 1.0 / max(len(p), 1)) if w is None else np.asarray(w, dtype=np.float64)
+        if world > 1 and not self.shards_by_design_point:
+            # one control vector couples every design point (three-stage): each rank solves the whole batch --
+            # identical results on every rank, no speed-up; sharding it needs an all-reduce of the 46-value
+            # {Phi, grad, H} statistics per optimiser iteration
+            ind = self._indicators(d, p, w_arr)
+            return ((1.0 - ind) * w_arr[None, :]).sum(axis=1)
+        a, b = shard_rows(len(d), world, rank)
         if b > a:
             ind = self._indicators(d[a:b], p, w_arr)
             P = ((1.0 - ind) * w_arr[None, :]).sum(axis=1)
@@ -138,6 +146,8 @@ class ThreeStageManager(Manager):
     """Stage 0 = the control profile shared by every design point and theta; stage 1 = design variables;
     stage 2 = theta (reference pyds/run.py:71-98; see examples/threestage_reactor.py for the repaired
     example script)."""
+
+    shards_by_design_point = False         # the stage-0 control couples all design points
 
     def __init__(self, config):
         super().__init__(config)

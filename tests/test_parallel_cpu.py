@@ -69,3 +69,56 @@ def test_sharded_efp_gloo_world2(n_d):
     _, P_ref, _ = cbind.kinetics_grid(d, K.theta_samples(), np.full(50, 0.02), want_g=False)
     for r in range(2):
         np.testing.assert_allclose(res[r], P_ref, atol=1e-15)
+
+
+def _manager_worker(rank, world, port, shards, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from pyds_b200 import run
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Stub(run.Manager):
+        shards_by_design_point = shards
+
+        def __init__(self):
+            self.rows_seen = []
+
+        def _check(self, d, p):
+            return np.asarray(d, dtype=np.float64), np.asarray(p, dtype=np.float64)
+
+        def _indicators(self, d, p, w):
+            self.rows_seen.append(len(d))
+            return (d[:, :1] > p[None, :, 0]).astype(np.float64)         # indicator 1 where d0 > theta0
+
+    rng = np.random.default_rng(9)
+    d, p = rng.uniform(size=(11, 2)), rng.uniform(size=(7, 1))
+    w = np.full(7, 1.0 / 7)
+    m = Stub()
+    P = m.efp(d, p, w)
+    q.put((rank, P, m.rows_seen))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shards", [True, False])
+def test_manager_efp_sharding_rule_gloo_world2(shards):
+    """Two-stage managers split the design points over the ranks; the three-stage manager (one control vector
+    couples every design point) must see the whole batch on every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + int(shards)) % 2000
+    procs = [ctx.Process(target=_manager_worker, args=(r, 2, port, shards, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = {r: (P, rows) for r, P, rows in (q.get(timeout=180) for _ in range(2))}
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    rng = np.random.default_rng(9)
+    d, p = rng.uniform(size=(11, 2)), rng.uniform(size=(7, 1))
+    P_ref = ((1.0 - (d[:, :1] > p[None, :, 0])) / 7.0).sum(axis=1)
+    for r in range(2):
+        np.testing.assert_allclose(res[r][0], P_ref, atol=1e-15)
+    assert sorted(res[r][1][0] for r in range(2)) == ([5, 6] if shards else [11, 11])
