@@ -132,6 +132,27 @@ public:
         return true;
     }
 
+    // Program 1 (sens_kernel): the data ops of the four tapes back to back; seg[k] = where tape k starts, seg[4] = end
+    bool assemble_segments(const AsmInput& in, int n_pt, int (&seg)[5])
+    {
+        in_ = &in;
+        seg[0] = pc();
+        for (int i = 0; i < in.n_pro; ++i)
+            if (!scalar_op(in.pro[i])) return false;
+        seg[1] = pc();
+        for (int i = 0; i < in.n_elem; ++i)
+            if (!scalar_op(in.elem[i])) return false;
+        seg[2] = pc();
+        for (int i = 0; i < n_pt; ++i)
+            if (!point_op(in.pt[i])) return false;
+        seg[3] = pc();
+        for (int i = 0; i < in.n_g; ++i)
+            if (!scalar_op(in.g[i])) return false;
+        seg[4] = pc();
+        if (pc() > 2 * MAX_PROG_S) return fail("sensitivity program longer than the constant-bank window");
+        return true;
+    }
+
 private:
     const AsmInput* in_ = nullptr;
 

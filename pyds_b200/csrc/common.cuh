@@ -14,10 +14,10 @@ constexpr int MAX_STATES = 8;          // dynamic states in total (each block ho
 
 struct ExecImage {
     // global-memory copies made by pydsb_model_create
-    const uint64_t* code;      // pro | elem | g   (narrow tapes; staged in shared memory)
     const double* consts;      // constant pool
     const uint16_t* tabs;      // par[n_param] x0[ns] q0[nq] ztab[nz] zfix[nz] gtab[ng] cmap[nfe*nce] (+ sens tables)
     int n_pro, n_elem, n_pt, n_g, n_const, n_tabs, n_prog;
+    int seg[5];                // program 1: uint4 index where the pro / elem / point / g ops start, and the end
     int ns, nq, ng, d_dim, p_dim, nz, nfe, nce, n_units;
     int ctrl_slot, xe_slot, qe_slot, x_slot;
     int fq_state_dep;
@@ -49,7 +49,7 @@ struct ExecImage {
     unsigned fqz_o[32][3], fqz_mask;
     double bigm_inv[8];        // 1 / M_k
     // shared-memory carve-up (bytes from the start of dynamic smem)
-    int off_code, off_const, off_tabs, off_land, off_slots, smem_bytes;
+    int off_const, off_tabs, off_land, off_slots, smem_bytes;
 };
 
 struct LaunchArgs {
@@ -75,10 +75,11 @@ struct LaunchArgs {
 // fetch is a uniform LDCU and every access is LDS/STS [thread base + uniform offset (+ point * 1 KiB)].
 constexpr int MAX_PROG = 768;
 __constant__ uint4 c_prog[2 * MAX_PROG];
-// Program 1 (feasibility + control sensitivities, sens_kernel): the point tape alone, pre-decoded as
-//   word 0: op | words 1-3: dst offsets (points 0,1,2) | 4-6: a | 7-9: b | 10-12: c | 13-15: pad
-constexpr int MAX_PT = 320;
-__constant__ uint4 c_pt_s[4 * MAX_PT];
+// Program 1 (feasibility + control sensitivities, sens_kernel): the data ops of its four tapes (pro | elem | point
+// tape | g) in the same instruction format; segment boundaries in ExecImage::seg.  The Newton loop, the sensitivity
+// systems and the objective statistics around them are hand-written (recourse_kernel.cuh).
+constexpr int MAX_PROG_S = 512;
+__constant__ uint4 c_prog_s[2 * MAX_PROG_S];
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier / bulk-TMA helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP)

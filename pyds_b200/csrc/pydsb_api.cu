@@ -52,11 +52,9 @@ const Section* find(const Sections& secs, const char* tag)
 // One lowered program (0: feasibility, 1: feasibility + control sensitivities) on the device.
 struct Program {
     ExecImage img{};
-    void* d_code = nullptr;
     void* d_consts = nullptr;
     void* d_tabs = nullptr;
-    std::vector<uint32_t> xpt;          // program 1: pre-decoded point tape (16 words per instruction)
-    std::vector<uint32_t> xprog;        // program 0: the assembled per-scenario program (8 words per instruction)
+    std::vector<uint32_t> xprog;        // the assembled program (program 0: whole scenario; program 1: tape segments)
     PolyBlock poly[MAX_BLOCKS];         // program 0: blocks lowered to polynomial coefficients
     bool present = false;
 };
@@ -137,10 +135,9 @@ int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 void free_program(Program& p)
 {
-    if (p.d_code) cudaFree(p.d_code);
     if (p.d_consts) cudaFree(p.d_consts);
     if (p.d_tabs) cudaFree(p.d_tabs);
-    p.d_code = p.d_consts = p.d_tabs = nullptr;
+    p.d_consts = p.d_tabs = nullptr;
 }
 
 bool resolve_table(const Sections& secs, const char* tag, int n, int cap, unsigned (*off)[3], unsigned* mask, unsigned US)
@@ -290,40 +287,17 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
         if ((w & 0xFF) >= OP_COUNT) return fail(PYDSB_ERR_INVALID, "unknown opcode in tape");
     // pre-decode the point tape: per operand the byte offsets of the three collocation points
     if (sens) {
-        if (g.n_pt + 1 > MAX_PT) return fail(PYDSB_ERR_UNSUPPORTED, "point tape longer than the constant-bank window");
-        static const int xmap[OP_COUNT] = {/*MOV*/ XOP_MOV, /*NEG*/ XOP_NEG, /*ADD*/ XOP_ADD, /*SUB*/ XOP_SUB, /*MUL*/ XOP_MUL,
-                                           /*DIV*/ XOP_DIV, /*FMA*/ XOP_FMA, /*FMS*/ XOP_FMS, /*FNMA*/ XOP_FNMA, /*SQR*/ XOP_SQR,
-                                           /*RCP*/ XOP_RCP, /*EXP*/ XOP_COLD, /*LOG*/ XOP_COLD, /*SQRT*/ XOP_COLD, /*SIN*/ XOP_COLD,
-                                           /*COS*/ XOP_COLD, /*TANH*/ XOP_COLD, /*POW*/ XOP_COLD, /*ABS*/ XOP_ABS, /*MIN*/ XOP_MIN,
-                                           /*MAX*/ XOP_MAX, /*BC3*/ XOP_NOP};
-        const uint64_t* c = reinterpret_cast<const uint64_t*>(tn->data);
-        P.xpt.assign((size_t)16 * (g.n_pt + 1), 0u);                 // + one padding entry (prefetched, never run)
-        P.xpt[(size_t)16 * g.n_pt] = XOP_NOP;
-        for (int i = 0; i < g.n_pt; ++i) {
-            const uint64_t w = c[i];
-            const unsigned op = (unsigned)(w & 0xFF);
-            const unsigned refs[4] = {(unsigned)(w >> 8) & 0x3FFFu, (unsigned)(w >> 22) & 0x3FFFu,
-                                      (unsigned)(w >> 36) & 0x3FFFu, (unsigned)(w >> 50) & 0x3FFFu};
-            if (op >= OP_BC3) return fail(PYDSB_ERR_INVALID, "opcode not allowed in the point tape");
-            const int nops = (op == OP_FMA || op == OP_FMS || op == OP_FNMA) ? 3
-                             : (op == OP_ADD || op == OP_SUB || op == OP_MUL || op == OP_DIV || op == OP_POW ||
-                                op == OP_MIN || op == OP_MAX) ? 2 : 1;
-            uint32_t* x = &P.xpt[(size_t)16 * i];
-            x[0] = (uint32_t)xmap[op] | (op << 8);
-            for (int k = 1; k <= nops; ++k)
-                if (!(refs[k] & REF_WIDE)) x[0] |= 1u << (3 + k);          // bits 4,5,6: operand a,b,c is narrow
-            const bool cold_unary = (xmap[op] == XOP_COLD && nops == 1);
-            for (int k = 0; k <= nops; ++k) {
-                const unsigned r = refs[k];
-                if (r & REF_CONST) return fail(PYDSB_ERR_INVALID, "constant operand in the point tape");
-                if ((int)(r & REF_MASK) + ((r & REF_WIDE) ? 2 : 0) >= g.n_units) return fail(PYDSB_ERR_INVALID, "slot out of range");
-                for (int p3 = 0; p3 < 3; ++p3)
-                    x[1 + 3 * k + p3] = ((r & REF_MASK) + ((r & REF_WIDE) ? p3 : 0)) * BLOCK * 8u;
-            }
-            if (cold_unary)
-                for (int p3 = 0; p3 < 3; ++p3) x[7 + p3] = x[4 + p3];
-            if (!(refs[0] & REF_WIDE)) return fail(PYDSB_ERR_INVALID, "point tape writes a narrow slot");
-        }
+        // program 1: the data ops of the four tapes for sens_kernel's interpreter
+        AsmInput in{};
+        in.pro = reinterpret_cast<const uint64_t*>(tp->data); in.n_pro = g.n_pro;
+        in.elem = reinterpret_cast<const uint64_t*>(te->data); in.n_elem = g.n_elem;
+        in.g = reinterpret_cast<const uint64_t*>(tg->data); in.n_g = g.n_g;
+        in.pt = reinterpret_cast<const uint64_t*>(tn->data);
+        in.n_units = g.n_units; in.spt = 1; in.img = &g;
+        Assembler as;
+        if (!as.assemble_segments(in, g.n_pt, g.seg)) return fail(PYDSB_ERR_UNSUPPORTED, "assembler: " + as.err);
+        P.xprog.swap(as.words);
+        g.n_prog = (int)(P.xprog.size() / 4);
     }
     g.zero_off = 0; g.zero_slot = 0;
     if (!sens) {
@@ -397,13 +371,14 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
 
     // shared-memory carve-up
     int o = 128;                                            // mbarrier + reduction scratch
-    g.off_code = o; o += sens ? (int)code.size() * 8 : 0;     // program 0 keeps no tape in shared memory
     g.off_const = o; o += (g.n_const + 1) * 8;
     g.off_tabs = o; o = align_up(o + g.n_tabs * 2, 128);
     int land = g.spt * BLOCK * g.p_dim * 8;
     if (sens) {
-        const int need_ws = (BLOCK / 32) * RECOURSE_STAGES * recourse_nv(g.nz) * 8;
-        if (need_ws > land) land = need_ws;
+        land = 0;                                           // sens_kernel loads theta directly
+        // the cross-warp scratch of the shared modes overlays the program's slots
+        if ((BLOCK / 32) * RECOURSE_STAGES * recourse_nv(g.nz) > g.n_units * BLOCK)
+            return fail(PYDSB_ERR_UNSUPPORTED, "sensitivity program too small for the reduction scratch");
     }
     g.off_land = o; o = align_up(o + land, 128);
     g.off_slots = o;
@@ -413,14 +388,11 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
     g.smem_bytes = o;
 
     if (!upload) return PYDSB_OK;                           // host-only assembly (pydsb_assemble)
-    cudaError_t e = cudaMalloc(&P.d_code, code.size() * 8 + 8);
-    if (e == cudaSuccess) e = cudaMemcpy(P.d_code, code.data(), code.size() * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&P.d_consts, (size_t)g.n_const * 8 + 8);
+    cudaError_t e = cudaMalloc(&P.d_consts, (size_t)g.n_const * 8 + 8);
     if (e == cudaSuccess) e = cudaMemcpy(P.d_consts, cn->data, (size_t)g.n_const * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&P.d_tabs, tabs.size() * 2 + 8);
     if (e == cudaSuccess) e = cudaMemcpy(P.d_tabs, tabs.data(), tabs.size() * 2, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return fail(PYDSB_ERR_CUDA, std::string("model upload: ") + cudaGetErrorString(e));
-    g.code = static_cast<const uint64_t*>(P.d_code);
     g.consts = static_cast<const double*>(P.d_consts);
     g.tabs = static_cast<const uint16_t*>(P.d_tabs);
     P.present = true;
@@ -814,7 +786,7 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     CUDA_TRY_WS(cudaGetLastError());
     SensFn fn = sens_for(img.ns);
     CUDA_TRY_WS(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
-    CUDA_TRY_WS(cudaMemcpyToSymbolAsync(c_pt_s, m->prog[1].xpt.data(), m->prog[1].xpt.size() * sizeof(uint32_t), 0,
+    CUDA_TRY_WS(cudaMemcpyToSymbolAsync(c_prog_s, m->prog[1].xprog.data(), m->prog[1].xprog.size() * sizeof(uint32_t), 0,
                                         cudaMemcpyHostToDevice, st));
     RecourseArgs ra{};
     ra.d = d; ra.theta = theta; ra.w = w; ra.n_d = n_d; ra.n_t = n_t; ra.n_tiles = n_tiles;

@@ -21,11 +21,37 @@
 // Groups: shared mode -> one group per design point (the reference's two-stage formulation: stage-0
 // F_in shared by every theta); per-scenario mode -> one group per (d, theta).
 #pragma once
-#include "point_tape.cuh"
+#include "xvm_ops.cuh"
 
 namespace pydsb {
 
 #define PT_LD(off) (*reinterpret_cast<const double*>(base + (off)))
+
+// The data ops [pcw, pcw_end) of the sensitivity program: same pre-decoded format and op bodies as feas_kernel
+// (uniform fetch, pattern-specialised point ops).  Inlined at its four call sites: as an out-of-line function the
+// program counter arrives in a vector register and the fetch, dispatch and operand addresses leave the uniform datapath.
+__device__ __forceinline__ void run_ops(char* __restrict__ base, const char* __restrict__ cz, int pcw, int pcw_end)
+{
+    typedef Vec<1> VecT;
+    constexpr int SPT = 1;
+    constexpr unsigned USP = US;
+    const uint4* const c_prog = c_prog_s;
+    while (pcw < pcw_end) {
+        const uint4 w0 = c_prog[pcw];
+        pcw += 2;
+        if (w0.x < X_TIER2) {
+            switch (w0.x) {
+            X_DATA_OP_CASES_HOT
+            default: break;
+            }
+        } else {
+            switch (w0.x) {
+            X_DATA_OP_CASES_REST
+            default: break;
+            }
+        }
+    }
+}
 
 constexpr int MAX_NZ = 16;
 
@@ -89,22 +115,18 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 
-    uint64_t* code = reinterpret_cast<uint64_t*>(smem + img.off_code);
     double* cpool = reinterpret_cast<double*>(smem + img.off_const) + 1;
     uint16_t* tabs = reinterpret_cast<uint16_t*>(smem + img.off_tabs);
-    double* wsum = reinterpret_cast<double*>(smem + img.off_land);      // [BLOCK/32][NV] (reuses the landing area)
+    // [BLOCK/32][n_stages][NV] cross-warp scratch of the shared modes: overlays the program's own slots, which are
+    // dead once the CQA gradients are in the sensitivity block (needs (BLOCK/32) * n_stages * NV <= n_units * BLOCK)
+    double* wsum = reinterpret_cast<double*>(smem + img.off_slots);
     double* S = reinterpret_cast<double*>(smem + img.off_slots) + tid;
 
-    const int n_code = img.n_pro + img.n_elem + img.n_g;
-    for (int i = tid; i < n_code; i += BLOCK) code[i] = img.code[i];
     for (int i = tid; i < img.n_const; i += BLOCK) cpool[i] = img.consts[i];
     for (int i = tid; i < img.n_tabs; i += BLOCK) tabs[i] = img.tabs[i];
     if (tid == 0) cpool[-1] = 0.0;
     __syncthreads();
 
-    const uint64_t* code_pro = code;
-    const uint64_t* code_elem = code_pro + img.n_pro;
-    const uint64_t* code_g = code_elem + img.n_elem;
     const uint16_t* tab_par = tabs;
     const uint16_t* tab_x0 = tab_par + img.d_dim + img.p_dim;
     const uint16_t* tab_q0 = tab_x0 + img.ns;
@@ -120,6 +142,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
     vm.S = S;
     vm.cpool = cpool;
     char* const base = reinterpret_cast<char*>(S);
+    const char* const cz = reinterpret_cast<const char*>(cpool - 1);    // constant operands: (index + 1) * 8
     double* const Xs = S + img.x_slot * BLOCK;
     const int nz = img.nz, nq = img.nq, ng = img.ng;
     double* const Sx = S + (size_t)ra.sens_slot * BLOCK;       // Sx[n*nz + c]
@@ -161,7 +184,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
     for (int c = 0; c < img.d_dim; ++c) S[tab_par[c] * BLOCK] = __ldg(ra.d + i_d * img.d_dim + c);
     const double* zg = ra.z_try + grp * nz;
 
-    run_narrow_tape(S, cpool, code_pro, img.n_pro);
+    run_ops(base, cz, img.seg[0], img.seg[1]);
     double xs[NS];
 #pragma unroll
     for (int n = 0; n < NS; ++n) xs[n] = vm_ld(vm, tab_x0[n]);
@@ -175,7 +198,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
             const int zi = tab_cmap[e * img.nce + c];
             S[(img.ctrl_slot + c) * BLOCK] = tab_zfix[zi] ? vm_ld(vm, tab_z[zi]) : __ldg(zg + zi);
         }
-        run_narrow_tape(S, cpool, code_elem, img.n_elem);
+        run_ops(base, cz, img.seg[1], img.seg[2]);
         double xv[3][NS];
 #pragma unroll
         for (int n = 0; n < NS; ++n) {
@@ -188,7 +211,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
         double s_prev = 0.0;
         double M[N][N], inv[N], r[N];
         for (int it = 0;; ++it) {
-            run_point_tape<true>(base, 0, img.n_pt);
+            run_ops(base, cz, img.seg[2], img.seg[3]);
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj)
 #pragma unroll
@@ -292,7 +315,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
     // ---- scaled constraints c_k = g_k / M_k and their control gradients ----
 #pragma unroll
     for (int n = 0; n < NS; ++n) S[(img.xe_slot + n) * BLOCK] = xs[n];
-    run_narrow_tape(S, cpool, code_g, img.n_g);
+    run_ops(base, cz, img.seg[3], img.seg[4]);
     double cmax = 0.0;                       // max(0, max_k c_k)
     double ck[8];
     for (int k = 0; k < ng; ++k) {
@@ -332,6 +355,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
         double* const Vv = Dc + (size_t)ng * nz * BLOCK;
         double mu = ra.mu[grp];
         const int SNV = ra.n_stages * NV;
+        __syncthreads();                                         // every thread is done with the program's slots
         for (int st = 0; st < ra.n_stages; ++st) {
             double pk[8];
             double phi, raw;
@@ -436,15 +460,16 @@ __global__ void lm_update_kernel(const LmArgs a)
     }
 }
 
-// Statistics {Phi_mu, Phi, grad, Gauss-Newton H} of one group at continuation stage `stage` (mu = the stage's value).
+// Statistics of one group at continuation stage `stage` (mu = the stage's value): {Phi_mu, Phi, grad} here, the
+// Gauss-Newton H on demand (lm_group_hessian) -- it is only needed when a step is computed on a non-empty free set,
+// and the bang-bang optima of the shipped problems end every stage with all controls on their bounds.
 __device__ void lm_group_stats(const LmArgs& a, long long g, int stage, double mu, double& F_t, double& raw_t, double* g_t,
-                               double* H_t)
+                               double* pk)
 {
     const int nz = a.nz;
     F_t = 0.0;
     raw_t = 0.0;
     for (int c = 0; c < nz; ++c) g_t[c] = 0.0;
-    for (int i = 0; i < nz * nz; ++i) H_t[i] = 0.0;
     if (a.per_scenario) {
         // the scenario's own c_k and grad c_k (weight 1): same formulas as the epilogue of sens_kernel
         const int ng = a.ng;
@@ -452,11 +477,30 @@ __device__ void lm_group_stats(const LmArgs& a, long long g, int stage, double m
         const bool failed = p[0] != 0.0;
         const double* ck = p + 1;
         const double* Dc = p + 1 + ng;
-        double cmax = 0.0, pk[8];
+        double cmax = 0.0;
         for (int k = 0; k < ng; ++k) cmax = fmax(cmax, ck[k]);
         hinge_point(ng, ck, cmax, failed, mu, pk, F_t, raw_t);
         for (int c = 0; c < nz; ++c)
             for (int k = 0; k < ng; ++k) g_t[c] = fma(pk[k], Dc[k * nz + c], g_t[c]);
+    } else {
+        const int NV = recourse_nv(nz);
+        for (int t = 0; t < a.n_tiles; ++t) {
+            const double* p = a.acc + ((g * a.n_tiles + t) * a.n_stages + stage) * NV;
+            F_t += p[0];
+            raw_t += p[1];
+            for (int c = 0; c < nz; ++c) g_t[c] += p[2 + c];
+        }
+    }
+}
+
+__device__ void lm_group_hessian(const LmArgs& a, long long g, int stage, double mu, const double* g_t, const double* pk,
+                                 double* H_t)
+{
+    const int nz = a.nz;
+    for (int i = 0; i < nz * nz; ++i) H_t[i] = 0.0;
+    if (a.per_scenario) {
+        const int ng = a.ng;
+        const double* Dc = a.acc + g * recourse_nvp(ng, nz) + 1 + ng;
         for (int r = 0; r < nz; ++r)
             for (int c = r; c < nz; ++c) {
                 double hv = 0.0;
@@ -467,9 +511,6 @@ __device__ void lm_group_stats(const LmArgs& a, long long g, int stage, double m
         const int NV = recourse_nv(nz);
         for (int t = 0; t < a.n_tiles; ++t) {
             const double* p = a.acc + ((g * a.n_tiles + t) * a.n_stages + stage) * NV;
-            F_t += p[0];
-            raw_t += p[1];
-            for (int c = 0; c < nz; ++c) g_t[c] += p[2 + c];
             int idx = 2 + nz;
             for (int r = 0; r < nz; ++r)
                 for (int c = r; c < nz; ++c, ++idx) H_t[r * nz + c] += p[idx];
@@ -494,8 +535,9 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
     bool done = false;
     const int stages_in_hand = a.per_scenario ? (1 << 30) : a.n_stages;
     for (int stage = 0;; ++stage) {
-    double F_t, raw_t, g_t[MAX_NZ], H_t[MAX_NZ * MAX_NZ];
-    lm_group_stats(a, g, stage, a.mu[g], F_t, raw_t, g_t, H_t);
+    double F_t, raw_t, g_t[MAX_NZ], pk[8];
+    const double mu_stage = a.mu[g];
+    lm_group_stats(a, g, stage, mu_stage, F_t, raw_t, g_t, pk);
     bool converged_here = false;
     bool at_eval_point = false;               // z_cur is the point the statistics were evaluated at
     if (raw_t == 0.0) {                       // every scenario of the group is feasible: Phi = 0 exactly
@@ -514,7 +556,6 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
             }
             const bool small = !first && (moved <= a.step_tol || a.F_cur[g] - F_t <= 1e-13 * fmax(F_t, 1e-300));
             for (int c = 0; c < nz; ++c) { zc[c] = zt[c]; gr[c] = g_t[c]; }
-            for (int i = 0; i < nz * nz; ++i) H[i] = H_t[i];
             a.F_cur[g] = F_t;
             a.raw_cur[g] = raw_t;
             if (!first) a.lam[g] = fmax(a.lam[g] / 3.0, 1e-12);
@@ -536,6 +577,11 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
             double step[MAX_NZ];
             for (int c = 0; c < nz; ++c) step[c] = 0.0;
             if (nf > 0) {
+                if (at_eval_point) {                       // z_cur was just accepted: its H is not in global memory yet
+                    double H_t[MAX_NZ * MAX_NZ];
+                    lm_group_hessian(a, g, stage, mu_stage, g_t, pk, H_t);
+                    for (int i = 0; i < nz * nz; ++i) H[i] = H_t[i];
+                }
                 double dmax = 0.0;
                 for (int i = 0; i < nf; ++i) dmax = fmax(dmax, H[idx[i] * nz + idx[i]]);
                 const double floor_ = 1e-8 * fmax(dmax, 0.0) + 1e-300;

@@ -1,9 +1,10 @@
-// Tape interpreter for the pyds_b200 feasibility kernels (sm_100a).
+// Tape encoding shared by the host-side lowering (pyds_b200/tape.py), the assembler (assembler.h) and the cold
+// paths of the kernels (reference tables are 14-bit references decoded with vm_ld).
 //
 // One thread owns one (design point, theta) scenario.  Its register file lives in shared memory
 // as S[slot][thread] (consecutive threads -> consecutive 8-byte words: every warp access is two
-// conflict-free 128-byte wavefronts).  The instruction stream is block-uniform, so every fetch
-// is a shared-memory broadcast and every branch of the dispatch is warp-uniform.
+// conflict-free 128-byte wavefronts).  The kernels do not interpret this encoding directly: pydsb_model_create
+// assembles it into the pre-decoded programs of xvm_ops.cuh.
 //
 // Instruction word (host side: pyds_b200/tape.py):
 //     op[7:0] | dst[21:8] | a[35:22] | b[49:36] | c[63:50]
@@ -69,82 +70,5 @@ __device__ __forceinline__ double fast_rcp(double x)
     const double e2 = fma(e, e, e);
     return fma(y, e2, y);
 }
-
-#define PYDSB_UNARY(expr)                                                        \
-    _Pragma("unroll") for (int w = 0; w < W; ++w) {                              \
-        const double a = A.p[w * A.stride];                                      \
-        D[w * dstride] = (expr);                                                 \
-    }                                                                            \
-    break;
-#define PYDSB_BINARY(expr)                                                       \
-    {                                                                            \
-        const Opnd B = vm_resolve(vm, rb);                                       \
-        _Pragma("unroll") for (int w = 0; w < W; ++w) {                          \
-            const double a = A.p[w * A.stride], b = B.p[w * B.stride];           \
-            D[w * dstride] = (expr);                                             \
-        }                                                                        \
-    }                                                                            \
-    break;
-#define PYDSB_TERNARY(expr)                                                      \
-    {                                                                            \
-        const Opnd B = vm_resolve(vm, rb);                                       \
-        const Opnd C = vm_resolve(vm, rc);                                       \
-        _Pragma("unroll") for (int w = 0; w < W; ++w) {                          \
-            const double a = A.p[w * A.stride], b = B.p[w * B.stride], c = C.p[w * C.stride]; \
-            D[w * dstride] = (expr);                                             \
-        }                                                                        \
-    }                                                                            \
-    break;
-
-// Run `n` instructions, each on W collocation points at once (W = 1 for the narrow tapes).
-template <int W>
-__device__ __forceinline__ void run_tape(const VM& vm, const uint64_t* __restrict__ code, int n)
-{
-    for (int pc = 0; pc < n; ++pc) {
-        const uint64_t ins = code[pc];
-        const unsigned lo = (unsigned)ins, hi = (unsigned)(ins >> 32);
-        const unsigned op = lo & 0xFFu;
-        const unsigned rd = (lo >> 8) & 0x3FFFu;
-        const unsigned ra = (unsigned)(ins >> 22) & 0x3FFFu;
-        const unsigned rb = (hi >> 4) & 0x3FFFu;
-        const unsigned rc = (hi >> 18) & 0x3FFFu;
-        double* D = vm.S + (rd & REF_MASK) * BLOCK;
-        const int dstride = (rd & REF_WIDE) ? BLOCK : 0;
-        const Opnd A = vm_resolve(vm, ra);
-        switch (op) {
-        case OP_MOV: PYDSB_UNARY(a)
-        case OP_NEG: PYDSB_UNARY(-a)
-        case OP_ADD: PYDSB_BINARY(a + b)
-        case OP_SUB: PYDSB_BINARY(a - b)
-        case OP_MUL: PYDSB_BINARY(a * b)
-        case OP_DIV: PYDSB_BINARY(a / b)
-        case OP_FMA: PYDSB_TERNARY(fma(a, b, c))
-        case OP_FMS: PYDSB_TERNARY(fma(a, b, -c))
-        case OP_FNMA: PYDSB_TERNARY(fma(-a, b, c))
-        case OP_SQR: PYDSB_UNARY(a * a)
-        case OP_RCP: PYDSB_UNARY(1.0 / a)
-        case OP_EXP: PYDSB_UNARY(exp(a))
-        case OP_LOG: PYDSB_UNARY(log(a))
-        case OP_SQRT: PYDSB_UNARY(sqrt(a))
-        case OP_SIN: PYDSB_UNARY(sin(a))
-        case OP_COS: PYDSB_UNARY(cos(a))
-        case OP_TANH: PYDSB_UNARY(tanh(a))
-        case OP_POW: PYDSB_BINARY(pow(a, b))
-        case OP_ABS: PYDSB_UNARY(fabs(a))
-        case OP_MIN: PYDSB_BINARY(fmin(a, b))
-        case OP_MAX: PYDSB_BINARY(fmax(a, b))
-        case OP_BC3: {
-            const double a = *A.p;
-            D[0] = a; D[BLOCK] = a; D[2 * BLOCK] = a;
-            break;
-        }
-        default: break;
-        }
-    }
-}
-
-#undef PYDSB_UNARY
-#undef PYDSB_BINARY
-#undef PYDSB_TERNARY
 
 }  // namespace pydsb

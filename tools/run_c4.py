@@ -18,7 +18,8 @@ rng = np.random.default_rng(1989)
 eng = capi.Engine(models.kinetics("twostage").lower().blob, 0)
 d = np.stack([rng.uniform(250, 350, n_d), rng.uniform(250, 300, n_d)], axis=1)
 _, p, _ = make_inputs(10, n_t)
-eng.recourse_solve(d[:4], p[:256], per_scenario=True)
+if not os.environ.get("PYDSB_NO_WARM"):
+    eng.recourse_solve(d[:4], p[:256], per_scenario=True)
 torch.cuda.synchronize()
 eng.counters(reset=True)
 td, tp = torch.from_numpy(d).cuda(), torch.from_numpy(p).cuda()
