@@ -12,6 +12,12 @@ namespace pydsb {
 constexpr int MAX_BLOCKS = 4;          // blocks of the block-triangular state solve
 constexpr int MAX_STATES = 8;          // dynamic states in total (each block holds at most 3)
 
+constexpr int MAX_SENS_ENTRIES = 48;
+struct SensEntry {
+    unsigned short row, col;
+    unsigned o[3];
+};
+
 struct ExecImage {
     // global-memory copies made by pydsb_model_create
     const double* consts;      // constant pool
@@ -42,11 +48,11 @@ struct ExecImage {
     unsigned blk_jmask[MAX_BLOCKS];            // bit r*nsb+c: entry not structurally zero
     unsigned fq_o[8][3];
     unsigned fq_mask;
-    // program 1 only (one block): dfq/dx (nq x ns), df/dz (ns x nce), dfq/dz (nq x nce);
-    // dg/dxe (ng x ns) and dg/dqe (ng x nq) are narrow references in `tabs` after cmap
-    unsigned fqx_o[24][3], fqx_mask;
-    unsigned fz_o[12][3], fz_mask;
-    unsigned fqz_o[32][3], fqz_mask;
+    // program 1 only (one block): the non-zero entries of df/dz (row = state, col = control function), then dfq/dx
+    // (row = quadrature, col = state), then dfq/dz (row = quadrature, col = control function), with their byte
+    // offsets at the three points; dg/dxe (ng x ns) and dg/dqe (ng x nq) are narrow references in `tabs` after cmap
+    int n_fz, n_fqx, n_fqz;
+    SensEntry sens_e[MAX_SENS_ENTRIES];
     double bigm_inv[8];        // 1 / M_k
     // shared-memory carve-up (bytes from the start of dynamic smem)
     int off_const, off_tabs, off_land, off_slots, smem_bytes;

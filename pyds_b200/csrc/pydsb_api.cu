@@ -353,10 +353,26 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
     if (sens) {
         if (g.nz > MAX_NZ) return fail(PYDSB_ERR_UNSUPPORTED, "at most 16 control values for the recourse optimiser");
         if (g.n_blocks != 1 || g.ns > 3) return fail(PYDSB_ERR_UNSUPPORTED, "the sensitivity program is one coupled block of <= 3 states");
-        if (!resolve_table(secs, "RFQX", g.nq * g.ns, 24, g.fqx_o, &g.fqx_mask, US) ||
-            !resolve_table(secs, "RFZ_", g.ns * g.nce, 12, g.fz_o, &g.fz_mask, US) ||
-            !resolve_table(secs, "RFQZ", g.nq * g.nce, 32, g.fqz_o, &g.fqz_mask, US))
-            return fail(PYDSB_ERR_INVALID, "bad sensitivity reference table");
+        {
+            // compact lists of the non-zero sensitivity integrands: df/dz (ns x nce), dfq/dx (nq x ns), dfq/dz (nq x nce)
+            unsigned tmp[32][3], mask = 0;
+            int n_e = 0;
+            auto add = [&](const char* tag, int rows, int cols, int& count) -> bool {
+                if (rows * cols > 32 || !resolve_table(secs, tag, rows * cols, 32, tmp, &mask, US)) return false;
+                count = 0;
+                for (int i = 0; i < rows * cols; ++i) {
+                    if (!((mask >> i) & 1u)) continue;
+                    if (n_e >= MAX_SENS_ENTRIES) return false;
+                    SensEntry& en = g.sens_e[n_e++];
+                    en.row = (unsigned short)(i / cols); en.col = (unsigned short)(i % cols);
+                    for (int p3 = 0; p3 < 3; ++p3) en.o[p3] = tmp[i][p3];
+                    ++count;
+                }
+                return true;
+            };
+            if (!add("RFZ_", g.ns, g.nce, g.n_fz) || !add("RFQX", g.nq, g.ns, g.n_fqx) || !add("RFQZ", g.nq, g.nce, g.n_fqz))
+                return fail(PYDSB_ERR_INVALID, "bad sensitivity reference table");
+        }
         if (!push("RGX_", (size_t)g.ng * g.ns) || !push("RGQ_", (size_t)g.ng * g.nq))
             return fail(PYDSB_ERR_INVALID, "bad dg reference table");
         // live[e]: controls that have acted in an element <= e

@@ -265,47 +265,50 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
             acc = fma(img.bw[2], PT_LD(img.fq_o[q][2]), acc);
             S[(img.qe_slot + q) * BLOCK] = fma(h, acc, S[(img.qe_slot + q) * BLOCK]);
         }
-        // forward sensitivities of this element with respect to every control that has acted so far
+        // forward sensitivities of this element with respect to every control that has acted so far.  The non-zero
+        // entries of df/dz, dfq/dx and dfq/dz are compact lists in the image (sens_e): no mask or table walking here.
         const unsigned live = tab_live[e];
+        int cact[4];                                            // z index of control function k on this element
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cact[k] = k < img.nce ? (int)tab_cmap[e * img.nce + k] : -1;
+        auto ctrl_of = [&](int k) { return k == 0 ? cact[0] : (k == 1 ? cact[1] : (k == 2 ? cact[2] : cact[3])); };
+        // direct control terms of the quadratures (independent of the state sensitivities)
+        for (int i = img.n_fz + img.n_fqx; i < img.n_fz + img.n_fqx + img.n_fqz; ++i) {
+            const SensEntry en = img.sens_e[i];
+            double acc = img.bw[0] * PT_LD(en.o[0]);
+            acc = fma(img.bw[1], PT_LD(en.o[1]), acc);
+            acc = fma(img.bw[2], PT_LD(en.o[2]), acc);
+            double* sq = Sq + (size_t)(en.row * nz + ctrl_of(en.col)) * BLOCK;
+            *sq = fma(h, acc, *sq);
+        }
         for (int c = 0; c < nz; ++c) {
             if (!((live >> c) & 1u)) continue;
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj)
 #pragma unroll
                 for (int n = 0; n < NS; ++n) r[jj * NS + n] = -img.adot[jj + 1] * Sx[(size_t)(n * nz + c) * BLOCK];
-            for (int k = 0; k < img.nce; ++k) {
-                if (tab_cmap[e * img.nce + k] != c) continue;
+            for (int i = 0; i < img.n_fz; ++i) {                 // h * df_n/dz_c where control c acts on this element
+                const SensEntry en = img.sens_e[i];
+                if (ctrl_of(en.col) != c) continue;
+                const double f0 = h * PT_LD(en.o[0]), f1 = h * PT_LD(en.o[1]), f2 = h * PT_LD(en.o[2]);
 #pragma unroll
-                for (int n = 0; n < NS; ++n) {
-                    const int idx = n * img.nce + k;
-                    if (!((img.fz_mask >> idx) & 1u)) continue;
-#pragma unroll
-                    for (int jj = 0; jj < 3; ++jj)
-                        r[jj * NS + n] = fma(h, PT_LD(img.fz_o[idx][jj]), r[jj * NS + n]);
-                }
+                for (int n = 0; n < NS; ++n)
+                    if (n == en.row) { r[n] += f0; r[NS + n] += f1; r[2 * NS + n] += f2; }
             }
             lu_apply<N>(M, inv, r);
 #pragma unroll
             for (int n = 0; n < NS; ++n) Sx[(size_t)(n * nz + c) * BLOCK] = r[2 * NS + n];
-            for (int q = 0; q < nq; ++q) {
-                double acc = 0.0;
+            for (int i = img.n_fz; i < img.n_fz + img.n_fqx; ++i) {      // quadratures: h * sum_j bw_j dfq/dx_n dX_n(j)
+                const SensEntry en = img.sens_e[i];
+                double d0 = 0.0, d1 = 0.0, d2 = 0.0;
 #pragma unroll
-                for (int jj = 0; jj < 3; ++jj) {
-                    double tq = 0.0;
-#pragma unroll
-                    for (int n = 0; n < NS; ++n) {
-                        const int idx = q * NS + n;
-                        if ((img.fqx_mask >> idx) & 1u)
-                            tq = fma(PT_LD(img.fqx_o[idx][jj]), r[jj * NS + n], tq);
-                    }
-                    for (int k = 0; k < img.nce; ++k) {
-                        const int idx = q * img.nce + k;
-                        if (tab_cmap[e * img.nce + k] == c && ((img.fqz_mask >> idx) & 1u))
-                            tq += PT_LD(img.fqz_o[idx][jj]);
-                    }
-                    acc = fma(img.bw[jj], tq, acc);
-                }
-                Sq[(size_t)(q * nz + c) * BLOCK] = fma(h, acc, Sq[(size_t)(q * nz + c) * BLOCK]);
+                for (int n = 0; n < NS; ++n)
+                    if (n == en.col) { d0 = r[n]; d1 = r[NS + n]; d2 = r[2 * NS + n]; }
+                double acc = img.bw[0] * PT_LD(en.o[0]) * d0;
+                acc = fma(img.bw[1] * PT_LD(en.o[1]), d1, acc);
+                acc = fma(img.bw[2] * PT_LD(en.o[2]), d2, acc);
+                double* sq = Sq + (size_t)(en.row * nz + c) * BLOCK;
+                *sq = fma(h, acc, *sq);
             }
         }
 #pragma unroll
