@@ -45,7 +45,7 @@ def group_terms(c, dc, w, mu):
     return (phi * w).sum(axis=1), (raw * w).sum(axis=1), grad, H
 
 
-def lm_step(gr, H, lam, z, lo, hi):
+def lm_step(gr, H, lam, z, lo, hi, mu):
     """Projected LM step for one group."""
     nz = len(z)
     free = ~(((z <= lo) & (gr > 0)) | ((z >= hi) & (gr < 0)))
@@ -53,9 +53,15 @@ def lm_step(gr, H, lam, z, lo, hi):
     if not free.any():
         return z.copy()
     idx = np.nonzero(free)[0]
-    Hf = H[np.ix_(idx, idx)]
-    dg = np.diag(Hf).copy()
-    floor = 1e-8 * max(dg.max(), 0.0) + 1e-300
+    Hf = H[np.ix_(idx, idx)].copy()
+    # H is positive semi-definite in exact arithmetic; where one constraint dominates every scenario it is zero up to
+    # round-off of either sign (~1e-16 gr_i^2 / mu): a diagonal entry below 1e-10 gr_i^2 / mu counts as "no curvature";
+    # those directions are dropped (the damped matrix stays positive definite and the step along them goes to the bound)
+    dg = np.where(np.diag(Hf) > 1e-10 * gr[idx] ** 2 / mu, np.diag(Hf), 0.0)
+    flat = dg <= 0.0
+    Hf[flat, :] = 0.0; Hf[:, flat] = 0.0
+    np.fill_diagonal(Hf, dg)
+    floor = 1e-8 * dg.max() + 1e-300
     l = lam
     for _ in range(12):
         A = Hf + np.diag(l * (dg + floor) + 1e-30)
@@ -115,7 +121,7 @@ def minimize_hinge(eval_c, z0, lo, hi, w, mu0=1e-4, mu_min=1e-9, max_iter=200, l
                 if lam[g] >= 1e12:
                     converged_here = True
             if not converged_here:
-                z_new = lm_step(gr[g], H[g], lam[g], z_cur[g], lo, hi)
+                z_new = lm_step(gr[g], H[g], lam[g], z_cur[g], lo, hi, mu[g])
                 if np.all(z_new == z_cur[g]):
                     converged_here = True
                 else:

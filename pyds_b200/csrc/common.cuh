@@ -52,6 +52,7 @@ struct ExecImage {
     // (row = quadrature, col = state), then dfq/dz (row = quadrature, col = control function), with their byte
     // offsets at the three points; dg/dxe (ng x ns) and dg/dqe (ng x nq) are narrow references in `tabs` after cmap
     int n_fz, n_fqx, n_fqz;
+    int tri;                   // df/dx is lower triangular in the state order (forward substitution over 3x3 systems)
     SensEntry sens_e[MAX_SENS_ENTRIES];
     double bigm_inv[8];        // 1 / M_k
     // shared-memory carve-up (bytes from the start of dynamic smem)

@@ -121,12 +121,14 @@ int choose_spt(int maxns, bool all_poly)
     }
     return spt;
 }
-SensFn sens_for(int ns)
+SensFn sens_for(int ns, bool tri)
 {
-    switch (ns) {
-    case 1: return sens_kernel<1>;
-    case 2: return sens_kernel<2>;
-    case 3: return sens_kernel<3>;
+    switch (ns * 2 + (tri && ns > 1 ? 1 : 0)) {
+    case 2: return sens_kernel<1, false>;
+    case 4: return sens_kernel<2, false>;
+    case 5: return sens_kernel<2, true>;
+    case 6: return sens_kernel<3, false>;
+    case 7: return sens_kernel<3, true>;
     default: return nullptr;
     }
 }
@@ -353,6 +355,10 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
     if (sens) {
         if (g.nz > MAX_NZ) return fail(PYDSB_ERR_UNSUPPORTED, "at most 16 control values for the recourse optimiser");
         if (g.n_blocks != 1 || g.ns > 3) return fail(PYDSB_ERR_UNSUPPORTED, "the sensitivity program is one coupled block of <= 3 states");
+        g.tri = 1;                                          // no Jacobian entry above the diagonal?
+        for (int n = 0; n < g.ns; ++n)
+            for (int m2 = n + 1; m2 < g.ns; ++m2)
+                if ((g.blk_jmask[0] >> (n * g.ns + m2)) & 1u) g.tri = 0;
         {
             // compact lists of the non-zero sensitivity integrands: df/dz (ns x nce), dfq/dx (nq x ns), dfq/dz (nq x nce)
             unsigned tmp[32][3], mask = 0;
@@ -800,7 +806,7 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     lm_init_kernel<<<gb, tb, 0, st>>>(G, nz, z0, (int)(z0 ? z0_rows : 0), z_cur, z_try, F_cur, raw_cur, lam, mu, status,
                                       first, iters, o[2], o[0]);
     CUDA_TRY_WS(cudaGetLastError());
-    SensFn fn = sens_for(img.ns);
+    SensFn fn = sens_for(img.ns, img.tri != 0);
     CUDA_TRY_WS(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
     CUDA_TRY_WS(cudaMemcpyToSymbolAsync(c_prog_s, m->prog[1].xprog.data(), m->prog[1].xprog.size() * sizeof(uint32_t), 0,
                                         cudaMemcpyHostToDevice, st));

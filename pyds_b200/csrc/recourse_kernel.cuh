@@ -106,7 +106,10 @@ __device__ __forceinline__ void hinge_point(int ng, const double* ck, double cma
 // integrated, then Dc (ng) + one spare row
 __host__ __device__ inline int recourse_sens_rows(int ns, int nq, int ng) { return ns + nq > ng + 1 ? ns + nq : ng + 1; }
 
-template <int NS>
+// TRI: the Jacobian df/dx is lower triangular in the state order (every state depends on itself and on earlier
+// states only -- A -> B -> C kinetics): the 3*NS Newton system is solved by forward substitution over NS 3x3 systems
+// (the same Newton step as the dense LU, a third of the flops for NS = 2) and so are the sensitivity systems.
+template <int NS, bool TRI>
 __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
     sens_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ RecourseArgs ra)
 {
@@ -209,7 +212,28 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
         }
         bool conv = !active, stop = false;
         double s_prev = 0.0;
-        double M[N][N], inv[N], r[N];
+        double M[TRI ? 1 : N][TRI ? 1 : N], inv[TRI ? 1 : N], r[N];
+        double T[TRI ? NS : 1][3][3], tinv[TRI ? NS : 1][3], Joff[TRI ? NS : 1][TRI ? NS : 1][3];
+        // solve the Newton matrix (factors of the last assembly) for the right-hand side r, in place
+        auto solve = [&](double (&rr)[N]) {
+            if constexpr (TRI) {
+#pragma unroll
+                for (int n = 0; n < NS; ++n) {
+                    double rn[3];
+#pragma unroll
+                    for (int jj = 0; jj < 3; ++jj) {
+                        rn[jj] = rr[jj * NS + n];
+#pragma unroll
+                        for (int m = 0; m < n; ++m) rn[jj] = fma(Joff[n][m][jj], rr[jj * NS + m], rn[jj]);
+                    }
+                    lu_apply<3>(T[n], tinv[n], rn);
+#pragma unroll
+                    for (int jj = 0; jj < 3; ++jj) rr[jj * NS + n] = rn[jj];
+                }
+            } else {
+                lu_apply<N>(M, inv, rr);
+            }
+        };
         for (int it = 0;; ++it) {
             run_ops(base, cz, img.seg[2], img.seg[3]);
 #pragma unroll
@@ -220,20 +244,36 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
 #pragma unroll
                     for (int kk = 0; kk < 3; ++kk) lin = fma(img.adot[4 * (kk + 1) + jj + 1], xv[kk][n], lin);
                     r[jj * NS + n] = fma(h, PT_LD(img.blk_f_o[0][n][jj]), -lin);
+                    if constexpr (TRI) {
 #pragma unroll
-                    for (int kk = 0; kk < 3; ++kk)
+                        for (int kk = 0; kk < 3; ++kk) T[n][jj][kk] = img.adot[4 * (kk + 1) + jj + 1];
+                        if ((img.blk_jmask[0] >> (n * NS + n)) & 1u)
+                            T[n][jj][jj] = fma(-h, PT_LD(img.blk_j_o[0][n * NS + n][jj]), T[n][jj][jj]);
 #pragma unroll
-                        for (int m = 0; m < NS; ++m) {
-                            const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
-                            M[jj * NS + n][kk * NS + m] = a;
-                            if (kk == jj && ((img.blk_jmask[0] >> (n * NS + m)) & 1u))
-                                M[jj * NS + n][kk * NS + m] =
-                                    fma(-h, PT_LD(img.blk_j_o[0][n * NS + m][jj]), a);
-                        }
+                        for (int m = 0; m < n; ++m)
+                            Joff[n][m][jj] = ((img.blk_jmask[0] >> (n * NS + m)) & 1u) ? h * PT_LD(img.blk_j_o[0][n * NS + m][jj]) : 0.0;
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+                            for (int m = 0; m < NS; ++m) {
+                                const double a = (n == m) ? img.adot[4 * (kk + 1) + jj + 1] : 0.0;
+                                M[jj * NS + n][kk * NS + m] = a;
+                                if (kk == jj && ((img.blk_jmask[0] >> (n * NS + m)) & 1u))
+                                    M[jj * NS + n][kk * NS + m] =
+                                        fma(-h, PT_LD(img.blk_j_o[0][n * NS + m][jj]), a);
+                            }
+                    }
                 }
-            lu_factor<N>(M, inv);                       // at the last pass: factors at the converged point
+            // at the last pass: factors at the converged point
+            if constexpr (TRI) {
+#pragma unroll
+                for (int n = 0; n < NS; ++n) lu_factor<3>(T[n], tinv[n]);
+            } else {
+                lu_factor<N>(M, inv);
+            }
             if (stop) break;
-            lu_apply<N>(M, inv, r);
+            solve(r);
             double s = 0.0, sc = 0.0;
 #pragma unroll
             for (int kk = 0; kk < 3; ++kk)
@@ -295,7 +335,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
                 for (int n = 0; n < NS; ++n)
                     if (n == en.row) { r[n] += f0; r[NS + n] += f1; r[2 * NS + n] += f2; }
             }
-            lu_apply<N>(M, inv, r);
+            solve(r);
 #pragma unroll
             for (int n = 0; n < NS; ++n) Sx[(size_t)(n * nz + c) * BLOCK] = r[2 * NS + n];
             for (int i = img.n_fz; i < img.n_fz + img.n_fqx; ++i) {      // quadratures: h * sum_j bw_j dfq/dx_n dX_n(j)
@@ -585,15 +625,25 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
                     lm_group_hessian(a, g, stage, mu_stage, g_t, pk, H_t);
                     for (int i = 0; i < nz * nz; ++i) H[i] = H_t[i];
                 }
-                double dmax = 0.0;
-                for (int i = 0; i < nf; ++i) dmax = fmax(dmax, H[idx[i] * nz + idx[i]]);
-                const double floor_ = 1e-8 * fmax(dmax, 0.0) + 1e-300;
+                // H is a weighted covariance of the constraint gradients divided by mu: positive semi-definite in exact
+                // arithmetic.  Where one constraint dominates every scenario it is zero up to round-off of either
+                // sign (~1e-16 gr_i^2 / mu): treat a diagonal entry below 1e-10 gr_i^2 / mu as "no curvature", drop the
+                // rows / columns of those directions, so that the damped matrix stays positive definite and the step
+                // along them goes to the bound.
+                double hd[MAX_NZ], dmax = 0.0;
+                for (int i = 0; i < nf; ++i) {
+                    const double hii = H[idx[i] * nz + idx[i]], gi = gr[idx[i]];
+                    hd[i] = hii > 1e-10 * gi * gi / a.mu[g] ? hii : 0.0;
+                    dmax = fmax(dmax, hd[i]);
+                }
+                const double floor_ = 1e-8 * dmax + 1e-300;
                 double l = a.lam[g];
                 for (int attempt = 0; attempt < 12; ++attempt) {
                     double A[MAX_NZ * MAX_NZ];
                     for (int i = 0; i < nf; ++i)
-                        for (int jx = 0; jx < nf; ++jx) A[i * nf + jx] = H[idx[i] * nz + idx[jx]];
-                    for (int i = 0; i < nf; ++i) A[i * nf + i] += l * (H[idx[i] * nz + idx[i]] + floor_) + 1e-30;
+                        for (int jx = 0; jx < nf; ++jx)
+                            A[i * nf + jx] = (hd[i] > 0.0 && hd[jx] > 0.0) ? H[idx[i] * nz + idx[jx]] : 0.0;
+                    for (int i = 0; i < nf; ++i) A[i * nf + i] = hd[i] + l * (hd[i] + floor_) + 1e-30;
                     bool okc = true;                       // in-place Cholesky A = L L^T
                     for (int i = 0; i < nf && okc; ++i)
                         for (int jx = 0; jx <= i; ++jx) {

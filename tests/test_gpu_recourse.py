@@ -79,3 +79,47 @@ def test_recourse_larger_theta_set_multi_tile(setup):
     ref = RC.shared_control_problem(vm, d, p, w)
     out = eng.recourse_solve(d, p, w)
     np.testing.assert_allclose(out["phi"], ref["phi_raw"], rtol=1e-6, atol=1e-9)
+
+
+def _coupled_model():
+    """Two mutually coupled states (no triangular structure) with a piecewise-constant control: exercises the
+    dense 6x6 Newton + sensitivity path of sens_kernel (the kinetics models take the triangular path)."""
+    from pyds_b200.model import DaeModel
+    m = DaeModel(["a"], ["b", "c"], nfe=4)
+    a, b, c = m.d["a"], m.p["b"], m.p["c"]
+    x, y = m.state("x", 1.0), m.state("y", 0.5)
+    q = m.state("q", 0.0)
+    u = m.control("u", -1.0, 1.0, init=0.0)
+    m.ode(x, a * x - b * x * y + u)
+    m.ode(y, -c * y + 0.5 * b * x * y)
+    m.ode(q, u * u + 0.1 * x)                      # quadrature with a control-dependent integrand
+    m.constraint("c1", m.end(x) - 1.6, 10.0)
+    m.constraint("c2", 0.9 - m.end(y) + 0.05 * m.end(q), 10.0)
+    return m
+
+
+def test_dense_coupled_block_sensitivities_and_optimum():
+    lm = _coupled_model().lower()
+    assert lm.blocks == [["x", "y"]] and lm.nz == 4
+    eng = capi.Engine(lm.blob, 0)
+    vm = tape_vm.TapeVM(lm.blob, program=1)
+    rng = np.random.default_rng(3)
+    d = rng.uniform(0.4, 0.9, (5, 1))
+    p = np.stack([rng.uniform(0.8, 1.2, 40), rng.uniform(0.3, 0.6, 40)], axis=1)
+    w = np.full(40, 1 / 40)
+    # interior optimum on a kink of the hinge: the trust region collapses stage after stage (~160 evaluations)
+    ref = RC.shared_control_problem(vm, d, p, w, max_iter=500)
+    out = eng.recourse_solve(d, p, w, max_iter=500)
+    assert set(out["status"]) <= {1, 2} and set(ref["status"]) <= {1, 2}
+    np.testing.assert_allclose(out["phi"], ref["phi_raw"], rtol=1e-6, atol=1e-9)
+    g0 = vm.evaluate(d, p)["g"] / vm.big_m          # never worse than the warm start u = 0, better where it can be
+    phi0 = (np.maximum(0.0, g0.max(-1)) * w).sum(1)
+    assert np.all(out["phi"] <= phi0 + 1e-15) and out["phi"][0] < 0.8 * phi0[0]
+    # the state solve itself (feasibility program, generic NB2 / NS2 path) at the optimised controls
+    g, _, _ = eng.eval_host(d, p, w, z=out["z"], want_g=True)
+    r = tape_vm.TapeVM(lm.blob).evaluate(d, p, z=out["z"], tol=1e-13)
+    assert np.all(np.abs(g - r["g"]) <= 1e-10 * np.maximum(np.abs(r["g"]), 1.0))
+    # per-scenario mode on the same model
+    ref_ps = RC.per_scenario_problem(vm, d[:2], p[:5], max_iter=500)
+    out_ps = eng.recourse_solve(d[:2], p[:5], per_scenario=True, max_iter=500)
+    np.testing.assert_allclose(out_ps["phi"], ref_ps["phi_raw"], rtol=1e-6, atol=1e-9)
