@@ -20,10 +20,12 @@ struct SensEntry {
 
 struct ExecImage {
     // global-memory copies made by pydsb_model_create
+    // (field order matters more than it should: shifting the offsets of the fields below by 8 or 20 bytes made ptxas
+    //  spend 8 more registers on feas_kernel<1,2> and cost 5 % -- sens-only fields go to the end of the struct)
+    const void* reserved_;
     const double* consts;      // constant pool
     const uint16_t* tabs;      // par[n_param] x0[ns] q0[nq] ztab[nz] zfix[nz] gtab[ng] cmap[nfe*nce] (+ sens tables)
     int n_pro, n_elem, n_pt, n_g, n_const, n_tabs, n_prog;
-    int seg[5];                // program 1: uint4 index where the pro / elem / point / g ops start, and the end
     int ns, nq, ng, d_dim, p_dim, nz, nfe, nce, n_units;
     int ctrl_slot, xe_slot, qe_slot, x_slot;
     int fq_state_dep;
@@ -57,6 +59,7 @@ struct ExecImage {
     double bigm_inv[8];        // 1 / M_k
     // shared-memory carve-up (bytes from the start of dynamic smem)
     int off_const, off_tabs, off_land, off_slots, smem_bytes;
+    int seg[5];                // program 1: uint4 index where the pro / elem / point / g ops start, and the end
 };
 
 struct LaunchArgs {

@@ -475,7 +475,19 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 case X_MIN_WW: X_BIN(W, W, fmin(a, b))
                 case X_MAX_NW: X_BIN(N, W, fmax(a, b))
                 case X_MAX_WW: X_BIN(W, W, fmax(a, b))
-                case X_COLD_W: X_COLD_W_BODY
+                case X_COLD_W: {                           // transcendental, 3-wide; flag bit 0/1: a/b is wide
+                    const uint4 w1 = c_prog[pcw - 1];
+                    const unsigned sa = (w1.y & 1u) ? USP : 0u, sb = (w1.y & 2u) ? USP : 0u;
+#pragma unroll 1
+                    for (unsigned p = 0; p < 3; ++p) {
+                        const VecT a = LDV(w0.z + p * sa), b = LDV(w0.w + p * sb);
+                        VecT r;
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) r.v[s] = cold_op(w1.z, a.v[s], b.v[s]);
+                        STV(w0.y + p * USP, r);
+                    }
+                    break;
+                }
                 case X_FMS1: X1_TER(fma(a, b, -c))
                 case X_FNMA1: X1_TER(fma(-a, b, c))
                 case X_SUB1: X1_BIN(a - b)
