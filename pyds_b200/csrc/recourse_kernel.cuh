@@ -563,6 +563,25 @@ __device__ void lm_group_hessian(const LmArgs& a, long long g, int stage, double
         for (int c = 0; c < r; ++c) H_t[r * nz + c] = H_t[c * nz + r];
 }
 
+// Per-scenario mode: is the softmax over {0, c_1..c_K} / mu one-hot to far below round-off (every other term < 1e-30
+// of the largest)?  Then it stays so for every smaller mu.
+__device__ bool lm_softmax_saturated(const LmArgs& a, long long g, double mu)
+{
+    const int ng = a.ng;
+    const double* p = a.acc + g * recourse_nvp(ng, a.nz);
+    if (p[0] != 0.0) return false;                        // failed state solve
+    const double* ck = p + 1;
+    double cmax = 0.0;
+    int kmax = -1;
+    for (int k = 0; k < ng; ++k)
+        if (ck[k] > cmax) { cmax = ck[k]; kmax = k; }
+    if (kmax < 0) return false;
+    double rest = exp(-cmax / mu);
+    for (int k = 0; k < ng; ++k)
+        if (k != kmax) rest += exp((ck[k] - cmax) / mu);
+    return rest < 1e-30;
+}
+
 // The accept/reject + step logic of oracle/recourse.py::minimize_hinge for one group; true when it finished.
 // One call consumes one evaluation (state + sensitivity solve at z_try).  When the group converges at the current
 // mu with z_cur = the evaluated point, the next stage of the continuation needs the statistics at the same controls
@@ -583,6 +602,7 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
     lm_group_stats(a, g, stage, mu_stage, F_t, raw_t, g_t, pk);
     bool converged_here = false;
     bool at_eval_point = false;               // z_cur is the point the statistics were evaluated at
+    bool pinned = false;                      // converged with every control on a bound (empty free set)
     if (raw_t == 0.0) {                       // every scenario of the group is feasible: Phi = 0 exactly
         for (int c = 0; c < nz; ++c) zc[c] = zt[c];
         a.raw_cur[g] = 0.0;
@@ -678,11 +698,17 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
                 if (zn != zc[c]) same = false;
                 step[c] = zn;
             }
-            if (same) converged_here = true;
+            if (same) { converged_here = true; pinned = nf == 0; }
             else for (int c = 0; c < nz; ++c) zt[c] = step[c];
         }
         if (converged_here) {
             if (a.mu[g] <= a.mu_min * 1.0001) {
+                a.status[g] = 2;
+                done = true;
+            } else if (a.per_scenario && pinned && at_eval_point && lm_softmax_saturated(a, g, a.mu[g])) {
+                // bang-bang scenario whose softmax is one-hot already: a smaller mu changes neither the gradient nor
+                // the (empty) free set, every remaining stage would converge on the spot
+                a.mu[g] = a.mu_min;
                 a.status[g] = 2;
                 done = true;
             } else {
