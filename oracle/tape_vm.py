@@ -289,6 +289,10 @@ class TapeVM:
         out = dict(g=g.reshape(n_d, n_p, self.ng), y=y.reshape(n_d, n_p), feasible=feas.reshape(n_d, n_p),
                    iters=iters.reshape(n_d, n_p), status=failed.reshape(n_d, n_p).astype(np.int32),
                    x_end=x0.reshape(n_d, n_p, ns), q_end=q.reshape(n_d, n_p, nq))
+        if "RGEE" in s and want_sens:
+            ne = ns + nq                                 # second derivatives of the CQAs over e = (x(1), q(1))
+            out["gee"] = np.stack([self._ld(R, r, 0) * one for r in s["RGEE"]], axis=1).reshape(n_d, n_p, self.ng, ne, ne)
+            out["fxx_end"] = np.stack([self._ld(R, r, ncp - 1) * one for r in s["RFXX"]], axis=1).reshape(n_d, n_p, ns, ns, ns)
         if want_sens:
             dg = np.zeros((S, self.ng, self.nz))
             for k in range(self.ng):

@@ -52,7 +52,7 @@ class _Control:
 
 class DaeModel:
     def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-12, newton_max_it=25, predictor=False,
-                 quadratures="auto", block_triangular=True, polynomial_blocks=True):
+                 quadratures="auto", block_triangular=True, polynomial_blocks=True, second_derivatives=False):
         self.graph = T.Graph()
         self.d_names = list(d_names)
         self.p_names = list(p_names)
@@ -69,6 +69,10 @@ class DaeModel:
         # a one-state block whose right-hand side is a polynomial of degree <= 2 in its own state (mass-action
         # kinetics) is lowered to its coefficients: the kernel runs that block's Newton loop in registers
         self.polynomial_blocks = bool(polynomial_blocks)
+        # analytic second derivatives in the sensitivity program (opt-in: the batched optimiser is Gauss-Newton and
+        # does not consume them, so by default the tapes stay short): d2g_k/de_a de_b over the end values
+        # e = (x(1), q(1)) after the g tape, d2f_r/dx_a dx_b in the point tape
+        self.second_derivatives = bool(second_derivatives)
         self.states: list[_State] = []
         self.controls: list[_Control] = []
         self.constraints = []          # (name, Expr (<= 0 feasible), bigM)
@@ -255,6 +259,11 @@ class DaeModel:
                    "gx": [g.diff(gk[k], g.xe(c)) for k in range(ng) for c in range(ns)],
                    "gq": [g.diff(gk[k], g.qe(q)) for k in range(ng) for q in range(nq)]}
         groups_s = [("pt0", ["f0", "J0", "fq", "fqx", "fz", "fqz"])]
+        if self.second_derivatives:
+            ends = [g.xe(c) for c in range(ns)] + [g.qe(q) for q in range(nq)]
+            roots_s["gee"] = [g.diff(g.diff(gk[k], ea), eb) for k in range(ng) for ea in ends for eb in ends]
+            roots_s["fxx"] = [g.diff(J[r * ns + a], g.x(b)) for r in range(ns) for a in range(ns) for b in range(ns)]
+            groups_s = [("pt0", ["f0", "J0", "fq", "fqx", "fz", "fqz", "fxx"])]
         tau, adot, bw = radau_tables(self.ncp)
         secs = []
 
@@ -332,6 +341,9 @@ class DaeModel:
                 sec("RFQZ", "u16", tab(low, "fqz", nq * nce))
                 sec("RGX_", "u16", tab(low, "gx", ng * ns))
                 sec("RGQ_", "u16", tab(low, "gq", ng * nq))
+                if self.second_derivatives:
+                    sec("RGEE", "u16", low.refs["gee"])          # (ng, ns+nq, ns+nq)
+                    sec("RFXX", "u16", low.refs["fxx"])          # (ns, ns, ns), wide references
         low = lows[0]
         lay = low.layout
 

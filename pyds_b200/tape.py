@@ -2,8 +2,9 @@
 
 The reference hands its model to Pyomo, which expands every constraint of every scenario
 block into a GAMS file per solve (reference ``pyds/utils.py:92-112``, ``pyds/solver.py:50-55``).
-Here the model is lowered ONCE into four straight-line tapes that the CUDA interpreter
-(``csrc/feas_kernel.cu``) runs per (design point, theta) scenario:
+Here the model is lowered ONCE into straight-line tapes; ``pydsb_model_create`` assembles them into the
+pre-decoded per-scenario program (``csrc/assembler.h``) that the CUDA interpreter (``csrc/feas_kernel.cuh``)
+runs per (design point, theta) scenario:
 
 ==========  ========================================  =========================================
 tape        depends on                                runs
@@ -502,7 +503,7 @@ def lower(graph: Graph, *, n_param, n_ctrl_elem, ns, nq, roots: dict, pt_groups=
         raise NotImplementedError("the kernel evaluates the point tapes 3-wide (ncp = 3)")
     if pt_groups is None:
         pt_groups = [("pt", [t for t in ("f", "J", "fq") if t in roots])]
-    slot_tables = set(t for _, tabs in pt_groups for t in tabs) | {"gx", "gq"}      # read through per-thread slots
+    slot_tables = set(t for _, tabs in pt_groups for t in tabs) | {"gx", "gq", "gee"}      # read through per-thread slots
     pt_names = [name for name, _ in pt_groups]
     all_roots = [e for lst in roots.values() for e in lst if e is not None]
     order = topo_order(all_roots)

@@ -123,3 +123,17 @@ def test_dense_coupled_block_sensitivities_and_optimum():
     ref_ps = RC.per_scenario_problem(vm, d[:2], p[:5], max_iter=500)
     out_ps = eng.recourse_solve(d[:2], p[:5], per_scenario=True, max_iter=500)
     np.testing.assert_allclose(out_ps["phi"], ref_ps["phi_raw"], rtol=1e-6, atol=1e-9)
+
+
+def test_blob_with_second_derivative_tapes_runs_and_agrees(setup):
+    """The opt-in second-derivative tables ride in the sensitivity program (longer tapes, more slots); the
+    optimiser ignores them and must return the same optimum."""
+    lm, eng, vm = setup
+    lm2 = models.kinetics("twostage", second_derivatives=True).lower()
+    eng2 = capi.Engine(lm2.blob, 0)
+    p = K.theta_samples(50)
+    w = np.full(50, 1 / 50)
+    a = eng.recourse_solve(D6, p, w)
+    b = eng2.recourse_solve(D6, p, w)
+    np.testing.assert_allclose(a["phi"], b["phi"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(a["z"], b["z"], atol=1e-7)

@@ -203,3 +203,37 @@ def test_polynomial_blocks_agree_with_generic_blocks():
     np.testing.assert_allclose(a["g"][..., 0], b["g"][..., 0], rtol=0, atol=1e-12)
     np.testing.assert_allclose(a["g"][..., 1], b["g"][..., 1], rtol=0, atol=1e-12 * 1e5)
     assert (a["feasible"] == b["feasible"]).all() and not a["status"].any()
+
+
+def test_second_derivative_tapes_opt_in():
+    """second_derivatives=True adds d2g/de2 (end values) and d2f/dx2 to the sensitivity program; checked against
+    central differences of the first-derivative tables the same blob carries."""
+    lm0 = models.kinetics("twostage").lower()
+    lm2 = models.kinetics("twostage", second_derivatives=True).lower()
+    assert "RGEE" not in parse_blob(lm0.blob)["sens"] and "RGEE" in parse_blob(lm2.blob)["sens"]
+    assert lm2.blob != lm0.blob and parse_blob(lm2.blob)["TPNT"].tolist() == parse_blob(lm0.blob)["TPNT"].tolist()   # program 0 untouched
+    lm = lm2
+    ns, nq, ng = lm.ns, lm.nq, lm.ng
+    vm = tape_vm.TapeVM(lm.blob, program=1)
+    r = vm.evaluate(np.array([[300.0, 280.0]]), np.array([[2500.0, 5000.0, 0.064, 9900.0]]), z=np.full(8, 0.5), want_sens=True)
+    gee = r["gee"][0, 0]
+    assert gee.shape == (ng, ns + nq, ns + nq)
+    np.testing.assert_allclose(gee, gee.transpose(0, 2, 1), rtol=1e-12, atol=0)           # symmetric
+    assert np.abs(gee[0]).max() > 0 and np.abs(gee[1]).max() == 0                          # g1 rational, g2 linear in e
+    # d2g1/de2 against central differences of g1 = 0.8 - (cB + 1e-2)/(cA + cB + cC + 1e-2) at the VM's end values
+    xe, qe = r["x_end"][0, 0], r["q_end"][0, 0]
+    e0 = np.array([xe[0], xe[1], qe[0], qe[1]])                                            # (cA, cB, u, cC)
+    g1 = lambda e: 0.8 - (e[1] + 1e-2) / (e[0] + e[1] + e[3] + 1e-2)
+    h = 1e-3 * np.maximum(np.abs(e0), 1.0)
+    H = np.zeros((4, 4))
+    for a in range(4):
+        for b in range(4):
+            ea, eb = np.eye(4)[a] * h[a], np.eye(4)[b] * h[b]
+            H[a, b] = (g1(e0 + ea + eb) - g1(e0 + ea - eb) - g1(e0 - ea + eb) + g1(e0 - ea - eb)) / (4 * h[a] * h[b])
+    np.testing.assert_allclose(gee[0], H, rtol=1e-5, atol=1e-12)
+    # d2f/dx2 at the end point: f_A = t_f(-2 K1 cA^2 + F) -> d2f_A/dcA2 = -4 t_f K1, everything else zero but d2f_B/dcA2
+    fxx = r["fxx_end"][0, 0]
+    K1 = 0.064 * np.exp(-2500.0 / 280.0)
+    np.testing.assert_allclose(fxx[0, 0, 0], -4 * 300.0 * K1, rtol=1e-12)
+    np.testing.assert_allclose(fxx[1, 0, 0], 2 * 300.0 * K1, rtol=1e-12)
+    assert np.count_nonzero(fxx) == 2
