@@ -214,8 +214,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"         # keep NCCL's version banner off stdout: one JSON line only
+        # NCCL writes its version banner / debug lines to stdout: send them to a file, stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pyds_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
