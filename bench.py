@@ -29,6 +29,22 @@ sys.path.insert(0, ROOT)
 METRIC = "(d,theta) constraint evaluations per second (fp64)"
 UNIT = "evals/s"
 
+# stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner under torchrun) are sent
+# to stderr, the line itself is written to the saved descriptor
+_STDOUT_FD = None
+
+
+def claim_stdout():
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
 
 def make_inputs(n_d, n_t, rank=0, rows=None):
     """Config C3 inputs (SURVEY.md 8d): d = (t_f, T, cA0, Fbar) uniform in the box, seed 1989 (+rank);
@@ -175,7 +191,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -194,6 +210,7 @@ def main():
     ap.add_argument("--coupled", action="store_true", help="one coupled 6-unknown Newton system instead of the block-triangular solve")
     ap.add_argument("--generic-blocks", action="store_true", help="block-triangular solve through the generic point-op / NS path (no POLY1)")
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
 
@@ -214,8 +231,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version banner / debug lines to stdout: send them to a file, stdout carries ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pyds_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -347,7 +362,7 @@ def main():
             "clocks": clocks,
             "counters": cnt,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
