@@ -144,3 +144,44 @@ def test_unsupported_shapes_fail_loudly():
     r = tape_vm.TapeVM(lm2.blob).evaluate(d, p, tol=1e-13)
     np.testing.assert_allclose(g, r["g"], rtol=1e-10, atol=1e-12)
     assert eng.counters()["failed"] == 0
+
+
+def _mixed_chain_model():
+    """A -> B -> C -> D chain, three dynamic states + one quadrature: block A is a quadratic polynomial (POLY1),
+    block B has a cubic rate (not a polynomial of degree <= 2 in its own state: generic NB1 / point ops / NS1),
+    block C is linear in its own state with a state-dependent coefficient (POLY1, linear)."""
+    m = DaeModel(["tf"], ["k1", "k2", "k3"], nfe=5)
+    tf = m.d["tf"]
+    k1, k2, k3 = m.p["k1"], m.p["k2"], m.p["k3"]
+    a, b, c = m.state("a", 1.0), m.state("b", 0.2), m.state("c", 0.0)
+    dq = m.state("dq", 0.0)
+    m.ode(a, tf * (-k1 * a * a))
+    m.ode(b, tf * (k1 * a * a - k2 * b ** 3))
+    m.ode(c, tf * (k2 * b ** 3 - k3 * (1.0 + a) * c))
+    m.ode(dq, tf * k3 * (1.0 + a) * c)
+    m.constraint("yield", 0.25 - m.end(dq), 1.0)
+    m.constraint("residual", m.end(b) - 0.6, 1.0)
+    return m
+
+
+def test_mixed_polynomial_and_generic_blocks_in_one_program():
+    lm = _mixed_chain_model().lower()
+    assert lm.blocks == [["a"], ["b"], ["c"]] and lm.block_poly == [True, False, True] and lm.block_linear == [0, 0, 1]
+    ops, info = capi.assemble(lm.blob)
+    names = [o[1] for o in ops]
+    assert names.count("POLY1") == 2 and names.count("NB1") == 1 and names.count("NS1") == 1
+    assert info["scenarios_per_thread"] == 1                 # not every block is polynomial
+    eng = capi.Engine(lm.blob, 0)
+    vm = tape_vm.TapeVM(lm.blob)
+    rng = np.random.default_rng(31)
+    d = rng.uniform(0.5, 3.0, (19, 1))
+    p = np.stack([rng.uniform(0.5, 2.0, 211), rng.uniform(0.5, 3.0, 211), rng.uniform(0.2, 1.5, 211)], axis=1)
+    w = np.full(211, 1 / 211)
+    g, ind, P = eng.eval_host(d, p, w, want_g=True, want_ind=True)
+    r = vm.evaluate(d, p, tol=1e-13)
+    assert not r["status"].any() and eng.counters()["failed"] == 0
+    assert np.all(np.abs(g - r["g"]) <= 1e-10 * np.maximum(np.abs(r["g"]), 1.0))
+    near = np.any(np.abs(r["g"]) < 1e-8, axis=-1)
+    assert np.all(((ind == 0.0) == r["feasible"]) | near)
+    np.testing.assert_allclose(P, (r["feasible"] * w[None, :]).sum(1), atol=1e-12 + near.sum() / 211)
+    assert 0.02 < P.mean() < 0.98
