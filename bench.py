@@ -312,11 +312,11 @@ def main():
     # end to end through the host-buffer C-ABI call (pinned staging, H2D, kernels, D2H inside the timed region)
     P_host = None
     for _ in range(2):
-        P_host = sharded.efp_host(d_np, th_np, w_np)
+        P_host = sharded.efp_host(d_np, th_np, w_np, equal_shards=True)
     barrier()
     te0 = time.perf_counter()
     for _ in range(args.steps):
-        P_host = sharded.efp_host(d_np, th_np, w_np)
+        P_host = sharded.efp_host(d_np, th_np, w_np, equal_shards=True)
     barrier()
     e2e_s = torch.tensor([(time.perf_counter() - te0) / args.steps], dtype=torch.float64, device=dev)
     if world > 1:

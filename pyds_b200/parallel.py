@@ -51,21 +51,27 @@ class ShardedEfp:
         return self.gather(P_all)
 
     # -- host inputs: the user-facing call (numpy in, numpy out) -------------------------------------
-    def efp_host(self, d_local, theta, w=None, z=None):
-        """``d_local`` are THIS rank's rows; returns the probabilities of all ranks' rows, rank order."""
+    def efp_host(self, d_local, theta, w=None, z=None, equal_shards=False):
+        """``d_local`` are THIS rank's rows; returns the probabilities of all ranks' rows, rank order.
+        ``equal_shards``: every rank passes the same number of rows (no size exchange needed)."""
         _, _, P = self.engine.eval_host(d_local, theta, w, z=z, want_P=True)
         if self.world == 1:
             return P
-        return self.all_gather_host(P)
+        return self.all_gather_host(P, [len(P)] * self.world if equal_shards else None)
 
-    def all_gather_host(self, P_local):
+    def all_gather_host(self, P_local, sizes=None):
+        """Concatenate every rank's block.  ``sizes``: the block lengths when every rank can compute them (rows split
+        with ``shard_rows``) -- saves the pickled all_gather_object round trip per call."""
         import torch
         import torch.distributed as dist
         backend = dist.get_backend(self.group)
         dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         t = torch.from_numpy(np.ascontiguousarray(P_local, dtype=np.float64)).to(dev)
-        sizes = [None] * self.world
-        dist.all_gather_object(sizes, int(t.numel()), group=self.group)
+        if sizes is None:
+            sizes = [None] * self.world
+            dist.all_gather_object(sizes, int(t.numel()), group=self.group)
+        elif sizes[self.rank] != t.numel():
+            raise ValueError("all_gather_host: this rank's block does not have the announced length")
         if len(set(sizes)) == 1:
             out = torch.empty(self.world * t.numel(), dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(out, t, group=self.group)
@@ -91,4 +97,4 @@ class ShardedEfp:
             P = np.empty(0)
         if self.world == 1:
             return P
-        return self.all_gather_host(P)
+        return self.all_gather_host(P, shard_sizes(len(d_global), self.world))

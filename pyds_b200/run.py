@@ -88,7 +88,7 @@ class Manager:
                 world, rank = dist.get_world_size(), dist.get_rank()
         except ImportError:
             pass
-        from .parallel import ShardedEfp, shard_rows
+        from .parallel import ShardedEfp, shard_rows, shard_sizes
         w_arr = np.full(len(p), 1.0 / max(len(p), 1)) if w is None else np.asarray(w, dtype=np.float64)
         if world > 1 and not self.shards_by_design_point:
             # one control vector couples every design point (three-stage): each rank solves the whole batch --
@@ -104,7 +104,7 @@ class Manager:
             P = np.empty(0)
         if world == 1:
             return P
-        return ShardedEfp(None, world, rank).all_gather_host(P)
+        return ShardedEfp(None, world, rank).all_gather_host(P, shard_sizes(len(d), world))
 
     def _indicators(self, d, p, w):
         raise NotImplementedError
