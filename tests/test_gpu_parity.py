@@ -200,3 +200,26 @@ def test_full_size_properties_c3(eng4):
     _, Po, _ = cbind.kinetics_grid(d[rows], p, np.full(n_t, 1.0 / n_t), tol=1e-13, want_g=False)
     np.testing.assert_allclose(outs[0][rows], Po, atol=1e-12)
     assert 0.01 < outs[0].mean() < 0.9                                    # the grid straddles the feasible band
+
+
+@pytest.mark.parametrize("kw", [{}, {"polynomial_blocks": False}, {"block_triangular": False}])
+def test_far_outside_the_design_box_same_failures_same_values(kw):
+    """Long horizons, hot reactor, large feeds: the first finite elements are stiff and Newton from x_0 does not
+    converge for a third of the scenarios.  The kernel must fail exactly where the C oracle fails (iteration cap,
+    reported as NaN g / infeasible) and agree to round-off everywhere else -- for all three formulations."""
+    rng = np.random.default_rng(77)
+    n_d, n_t = 60, 256
+    d = np.stack([rng.uniform(50, 2000, n_d), rng.uniform(230, 400, n_d), rng.uniform(100, 5000, n_d), rng.uniform(0, 10, n_d)], axis=1)
+    p = K.theta_samples(n_t) * rng.uniform(0.7, 1.3, (n_t, 4))
+    w = np.full(n_t, 1.0 / n_t)
+    go, Po, _ = cbind.kinetics_grid(d, p, w, tol=1e-13)
+    eng = capi.Engine(models.kinetics("design4", **kw).lower().blob, 0)
+    g, ind, P = eng.eval_host(d, p, w, want_g=True, want_ind=True)
+    bad_o, bad_g = ~np.isfinite(go).all(-1), ~np.isfinite(g).all(-1)
+    assert 0.1 < bad_o.mean() < 0.9
+    assert np.array_equal(bad_o, bad_g)
+    assert eng.counters()["failed"] == int(bad_g.sum())
+    ok = ~bad_o
+    assert np.all(np.abs(g - go)[ok] <= 1e-10 * np.maximum(np.abs(go)[ok], G_SCALE))
+    assert np.all(ind[bad_g] == -1.0)                          # a failed state solve is reported infeasible
+    np.testing.assert_allclose(P, Po, atol=1e-12)
