@@ -224,8 +224,8 @@ class Engine:
 
 # opcode numbering of the assembled program (csrc/feas_kernel.cuh, enum XCode)
 XCODES = ["POLY1", "MUL_NW", "NS1", "ELEM_END",
-          "FMA_NWN", "FMA_NWW", "SQR_W", "FMS_NWW", "MUL_WW", "ADD_NW", "MUL1", "FMA1", "ADD1", "NS1L", "NS2", "NB1",
-          "FMA_WWN", "FMA_WWW", "FMS_NWN", "FMS_WWN", "FMS_WWW", "FNMA_NWN", "FNMA_NWW", "FNMA_WWN", "FNMA_WWW", "ADD_WW",
+          "FMA_NWN", "FMA_NWW", "SQR_W", "FMS_NWW", "MUL_WW", "MULSQ_NW", "MUL1", "FMA1", "ADD1", "NS1L", "NS2", "NB1",
+          "ADD_NW", "FMA_WWN", "FMA_WWW", "FMS_NWN", "FMS_WWN", "FMS_WWW", "FNMA_NWN", "FNMA_NWW", "FNMA_WWN", "FNMA_WWW", "ADD_WW",
           "SUB_WW", "SUB_NW", "SUB_WN", "DIV_NW", "DIV_WN", "DIV_WW",
           "NEG_W", "RCP_W", "ABS_W", "MOV_W", "BC_N", "MIN_NW", "MIN_WW", "MAX_NW", "MAX_WW", "COLD_W",
           "FMS1", "FNMA1", "SUB1", "DIV1", "SQR1", "NEG1", "RCP1", "ABS1", "MOV1", "MIN1", "MAX1", "COLD1",
@@ -249,7 +249,7 @@ def assemble(blob: bytes):
         if name in ("NS1", "NS1L"): length = ns_len(1)
         elif name in ("NS2", "NS2L"): length = ns_len(2)
         elif name in ("NS3", "NS3L"): length = ns_len(3)
-        elif name == "ELEM_END": length = 1 + int(words[4 * pcw + 2])
+        elif name == "ELEM_END": length = 1 + 2 * int(words[4 * pcw + 2])
         else: length = 2
         ops.append((pcw, name, words[4 * pcw:4 * (pcw + length)].copy()))
         pcw += length

@@ -72,8 +72,13 @@ public:
             if (g.max_it < 1 || g.max_it > 0xFFFF) return fail("Newton iteration cap out of range");
             if (in.poly[b].is_poly) {
                 // the coefficients that depend on earlier blocks' states (once per element), then the whole solve
-                for (int i = 0; i < in.blk_npt[b]; ++i)
-                    if (!point_op(in.pt[pos++])) return false;
+                {
+                    std::vector<unsigned> live;                      // slots POLY1 reads: the coefficients
+                    for (int k = 0; k < 3; ++k)
+                        if (in.poly[b].present[k]) live.push_back(in.poly[b].off[k] / (US * (uint32_t)in.spt));
+                    if (!point_tape(in.pt + pos, in.blk_npt[b], live)) return false;
+                    pos += in.blk_npt[b];
+                }
                 const PolyBlock& pb = in.poly[b];
                 uint32_t off[3], flags = in.blk_lin[b] ? 8u : 0u;
                 for (int k = 0; k < 3; ++k) {
@@ -86,8 +91,15 @@ public:
             }
             emit(nb_code[nsb - 1], g.blk_x_o[b][0][0], nsb > 1 ? g.blk_x_o[b][1][0] : 0u, nsb > 2 ? g.blk_x_o[b][2][0] : 0u);
             const int l_blk = pc();
-            for (int i = 0; i < in.blk_npt[b]; ++i)
-                if (!point_op(in.pt[pos++])) return false;
+            {
+                std::vector<unsigned> live;                          // slots NS reads: f and J of the block
+                const uint32_t usp = US * (uint32_t)in.spt;
+                for (int n = 0; n < nsb; ++n) live.push_back(g.blk_f_o[b][n][0] / usp);
+                for (int i = 0; i < nsb * nsb; ++i)
+                    if ((g.blk_jmask[b] >> i) & 1u) live.push_back(g.blk_j_o[b][i][0] / usp);
+                if (!point_tape(in.pt + pos, in.blk_npt[b], live)) return false;
+                pos += in.blk_npt[b];
+            }
             // NS: first uint4, then the operand table x_o[k] | f_o[k][3] | j_o[k*k][3], padded to whole uint4s
             const uint32_t head[4] = {in.blk_lin[b] ? nsl_code[nsb - 1] : ns_code[nsb - 1], (uint32_t)l_blk, in.blk_flops[b],
                                       (g.blk_jmask[b] & 0xFFFFu) | ((uint32_t)g.max_it << 16)};
@@ -106,21 +118,45 @@ public:
             tab.resize((size_t)(ns_length(nsb) - 1) * 4, 0u);
             words.insert(words.end(), tab.begin(), tab.end());
         }
-        for (int i = 0; i < in.q_npt; ++i)
-            if (!point_op(in.pt[pos++])) return false;
-        // ELEM_END: the quadratures to advance (Radau weights), then back to the element loop
-        std::vector<uint32_t> quad;
-        for (int q = 0; q < in.nq; ++q) {
-            const unsigned r = in.fq_refs[q];
-            if (r == REF_NONE) continue;
-            if (r & REF_CONST) return fail("constant reference in the quadrature table");
-            const uint32_t o = slot_off(r), st = (r & REF_WIDE) ? US * (uint32_t)in.spt : 0u;
-            if (!check_slot(r)) return false;
-            const uint32_t v[4] = {(uint32_t)(in.qe_slot + q) * US * (uint32_t)in.spt, o, o + st, o + 2 * st};
-            quad.insert(quad.end(), v, v + 4);
-        }
+        // quadrature tape and ELEM_END (advances the quadratures with the Radau weights, then loops).  An integrand that
+        // is `narrow * wide` computed by the tape's own MUL and read by nothing else is folded into its ELEM_END entry
+        // as a scale factor (mass-action rates: k * c): one dispatch and a store / reload less per element.
         {
-            const uint32_t head[4] = {X_ELEM_END, (uint32_t)l_elem, (uint32_t)(quad.size() / 4), 0u};
+            std::vector<uint64_t> qt(in.pt + pos, in.pt + pos + in.q_npt);
+            pos += in.q_npt;
+            std::vector<uint32_t> quad;                              // 8 words per entry
+            for (int q = 0; q < in.nq; ++q) {
+                const unsigned r = in.fq_refs[q];
+                if (r == REF_NONE) continue;
+                if (r & REF_CONST) return fail("constant reference in the quadrature table");
+                if (!check_slot(r)) return false;
+                uint32_t o = slot_off(r), st = (r & REF_WIDE) ? US * (uint32_t)in.spt : 0u, scale = 0, has_scale = 0;
+                if (r & REF_WIDE) {
+                    int producer = -1, readers = 0, others = 0;
+                    for (size_t i = 0; i < qt.size(); ++i) {
+                        unsigned op, refs[4];
+                        split(qt[i], op, refs);
+                        if ((refs[0] & REF_MASK) == (r & REF_MASK)) producer = (int)i;
+                        for (int k = 1; k <= arity(op); ++k) readers += (refs[k] & REF_MASK) == (r & REF_MASK) && !(refs[k] & REF_CONST);
+                    }
+                    for (int q2 = 0; q2 < in.nq; ++q2) others += q2 != q && in.fq_refs[q2] == r;
+                    if (producer >= 0 && readers == 0 && others == 0) {
+                        unsigned op, refs[4];
+                        split(qt[producer], op, refs);
+                        unsigned na = refs[1], wb = refs[2];
+                        if (op == OP_MUL && (na & REF_WIDE) && !(wb & REF_WIDE)) { const unsigned t = na; na = wb; wb = t; }
+                        if (op == OP_MUL && !(na & (REF_WIDE | REF_CONST)) && (wb & REF_WIDE) && !(wb & REF_CONST) &&
+                            check_slot(na) && check_slot(wb)) {
+                            o = slot_off(wb); scale = slot_off(na); has_scale = 1;
+                            qt.erase(qt.begin() + producer);
+                        }
+                    }
+                }
+                const uint32_t v[8] = {(uint32_t)(in.qe_slot + q) * US * (uint32_t)in.spt, o, o + st, o + 2 * st, scale, has_scale, 0, 0};
+                quad.insert(quad.end(), v, v + 8);
+            }
+            if (!point_tape(qt.data(), (int)qt.size(), std::vector<unsigned>())) return false;
+            const uint32_t head[4] = {X_ELEM_END, (uint32_t)l_elem, (uint32_t)(quad.size() / 8), 0u};
             words.insert(words.end(), head, head + 4);
             words.insert(words.end(), quad.begin(), quad.end());
         }
@@ -143,7 +179,7 @@ public:
         for (int i = 0; i < in.n_elem; ++i)
             if (!scalar_op(in.elem[i])) return false;
         seg[2] = pc();
-        for (int i = 0; i < n_pt; ++i)
+        for (int i = 0; i < n_pt; ++i)                           // (no peephole: sens_kernel reads most of these slots)
             if (!point_op(in.pt[i])) return false;
         seg[3] = pc();
         for (int i = 0; i < in.n_g; ++i)
@@ -221,6 +257,40 @@ private:
             if (flags & 1u) flags |= 2u;
         }
         emit((uint32_t)map[op], slot_off(refs[0]), off[0], off[1], off[2], flags, is_cold(op) ? op : 0u);
+        return true;
+    }
+
+    // One point tape.  Peephole: `t = x^2` followed by `d = n * t` with t read by nothing else (not later in the tape, not by
+    // the op that consumes the tape's outputs: `live`) becomes one MULSQ op (second-order mass-action rates k * c^2).
+    bool point_tape(const uint64_t* code, int n, const std::vector<unsigned>& live)
+    {
+        for (int i = 0; i < n; ++i) {
+            unsigned op, refs[4];
+            split(code[i], op, refs);
+            if (op == OP_SQR && i + 1 < n && (refs[0] & REF_WIDE) && (refs[1] & REF_WIDE)) {
+                unsigned op2, r2[4];
+                split(code[i + 1], op2, r2);
+                const unsigned t = refs[0] & REF_MASK;
+                unsigned na = r2[1], wb = r2[2];
+                if ((na & REF_WIDE) && !(wb & REF_WIDE)) { const unsigned s = na; na = wb; wb = s; }
+                bool fuse = op2 == OP_MUL && (r2[0] & REF_WIDE) && !(na & (REF_WIDE | REF_CONST)) && (wb & REF_WIDE) &&
+                            (wb & REF_MASK) == t;
+                for (size_t k = 0; fuse && k < live.size(); ++k) fuse = live[k] != t || (r2[0] & REF_MASK) == t;
+                for (int j = i + 2; fuse && j < n; ++j) {
+                    unsigned opj, rj[4];
+                    split(code[j], opj, rj);
+                    for (int k = 1; k <= arity(opj); ++k) fuse = fuse && ((rj[k] & REF_CONST) || (rj[k] & REF_MASK) != t);
+                    if ((rj[0] & REF_MASK) == t) break;              // overwritten before any later read
+                }
+                if (fuse) {
+                    if (!check_slot(r2[0]) || !check_slot(na) || !check_slot(refs[1])) return false;
+                    emit(X_MULSQ_NW, slot_off(r2[0]), slot_off(na), slot_off(refs[1]));
+                    ++i;
+                    continue;
+                }
+            }
+            if (!point_op(code[i])) return false;
+        }
         return true;
     }
 

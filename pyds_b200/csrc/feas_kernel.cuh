@@ -415,19 +415,22 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                     const int at = pcw - 2;
                     const int nquad = (int)w0.z;
                     for (int qi = 0; qi < nquad; ++qi) {
-                        const uint4 qw = c_prog[at + 1 + qi];
+                        const uint4 qw = c_prog[at + 1 + 2 * qi];
+                        const uint4 qs = c_prog[at + 2 + 2 * qi];      // { scale offset, has scale }
                         const VecT f0 = LDV(qw.y), f1 = LDV(qw.z), f2 = LDV(qw.w);
-                        VecT q = LDV(qw.x);
+                        VecT q = LDV(qw.x), sc;
+                        if (qs.y) sc = LDV(qs.x);
 #pragma unroll
                         for (int s = 0; s < SPT; ++s) {
                             double acc = img.bw[0] * f0.v[s];
                             acc = fma(img.bw[1], f1.v[s], acc);
                             acc = fma(img.bw[2], f2.v[s], acc);
+                            if (qs.y) acc *= sc.v[s];
                             q.v[s] = fma(h, acc, q.v[s]);
                         }
                         STV(qw.x, q);
                     }
-                    pcw = (++e < img.nfe) ? (int)w0.y : at + 1 + nquad;
+                    pcw = (++e < img.nfe) ? (int)w0.y : at + 1 + 2 * nquad;
                     break;
                 }
                 }
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 case X_SQR_W: X_UN(W, a * a)
                 case X_FMS_NWW: X_TER(N, W, W, fma(a, b, -c))
                 case X_MUL_WW: X_BIN(W, W, a * b)
-                case X_ADD_NW: X_BIN(N, W, a + b)
+                case X_MULSQ_NW: X_BIN(N, W, a * b * b)
                 case X_MUL1: X1_BIN(a * b)
                 case X_FMA1: X1_TER(fma(a, b, c))
                 case X_ADD1: X1_BIN(a + b)
@@ -450,6 +453,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 }
             } else {
                 switch (op) {
+                case X_ADD_NW: X_BIN(N, W, a + b)
                 case X_FMA_WWN: X_TER(W, W, N, fma(a, b, c))
                 case X_FMA_WWW: X_TER(W, W, W, fma(a, b, c))
                 case X_FMS_NWN: X_TER(N, W, N, fma(a, b, -c))

@@ -13,9 +13,9 @@ enum XCode : unsigned {
     // tier 1 (op < 4)
     X_POLY1 = 0, X_MUL_NW, X_NS1, X_ELEM_END,
     // tier 2 (op < 16)
-    X_FMA_NWN, X_FMA_NWW, X_SQR_W, X_FMS_NWW, X_MUL_WW, X_ADD_NW, X_MUL1, X_FMA1, X_ADD1, X_NS1L, X_NS2, X_NB1,
+    X_FMA_NWN, X_FMA_NWW, X_SQR_W, X_FMS_NWW, X_MUL_WW, X_MULSQ_NW, X_MUL1, X_FMA1, X_ADD1, X_NS1L, X_NS2, X_NB1,
     // tier 3: remaining three-wide point ops, by operand pattern (N narrow, W wide) ...
-    X_FMA_WWN, X_FMA_WWW, X_FMS_NWN, X_FMS_WWN, X_FMS_WWW, X_FNMA_NWN, X_FNMA_NWW, X_FNMA_WWN, X_FNMA_WWW, X_ADD_WW,
+    X_ADD_NW, X_FMA_WWN, X_FMA_WWW, X_FMS_NWN, X_FMS_WWN, X_FMS_WWW, X_FNMA_NWN, X_FNMA_NWW, X_FNMA_WWN, X_FNMA_WWW, X_ADD_WW,
     X_SUB_WW, X_SUB_NW, X_SUB_WN, X_DIV_NW, X_DIV_WN, X_DIV_WW,
     X_NEG_W, X_RCP_W, X_ABS_W, X_MOV_W, X_BC_N, X_MIN_NW, X_MIN_WW, X_MAX_NW, X_MAX_WW, X_COLD_W,
     // ... scalar ops (pro / elem / g tapes; flags: operand a/b/c lives in the constant pool) ...
@@ -33,7 +33,8 @@ constexpr unsigned X_TIER1 = 4, X_TIER2 = 16;
 //               then x_o[k], f_o[k][3], j_o[k*k][3] packed word by word                          length 1 + ceil(k(4+3k)/4)
 //   POLY1       w0 = { op, x_o, flops, max_it }   w1 = { c0, c1, c2, wide bits 0-2 | linear << 3 }
 //   LDCTRL      w0 = { op, dst, control }
-//   ELEM_END    w0 = { op, target pcw, n }        then n x { dst, o0, o1, o2 }: quadratures to advance     length 1 + n
+//   ELEM_END    w0 = { op, target pcw, n }        then n x { dst, o0, o1, o2 | scale, has_scale, -, - }: quadratures
+//               to advance, optionally times a narrow scale factor                                 length 1 + 2n
 __host__ __device__ constexpr int ns_words(int nsb) { return nsb + 3 * nsb + 3 * nsb * nsb; }
 __host__ __device__ constexpr int ns_length(int nsb) { return 1 + (ns_words(nsb) + 3) / 4; }
 
@@ -159,11 +160,12 @@ struct alignas(8 * SPT) Vec {
     case X_SQR_W: X_UN(W, a * a)                                          \
     case X_FMS_NWW: X_TER(N, W, W, fma(a, b, -c))                         \
     case X_MUL_WW: X_BIN(W, W, a * b)                                     \
-    case X_ADD_NW: X_BIN(N, W, a + b)                                     \
+    case X_MULSQ_NW: X_BIN(N, W, a * b * b)                               \
     case X_MUL1: X1_BIN(a * b)                                            \
     case X_FMA1: X1_TER(fma(a, b, c))                                     \
     case X_ADD1: X1_BIN(a + b)
 #define X_DATA_OP_CASES_REST                                              \
+    case X_ADD_NW: X_BIN(N, W, a + b)                                     \
     case X_FMA_WWN: X_TER(W, W, N, fma(a, b, c))                          \
     case X_FMA_WWW: X_TER(W, W, W, fma(a, b, c))                          \
     case X_FMS_NWN: X_TER(N, W, N, fma(a, b, -c))                         \
