@@ -418,16 +418,20 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                         const uint4 qw = c_prog[at + 1 + 2 * qi];
                         const uint4 qs = c_prog[at + 2 + 2 * qi];      // { scale offset, has scale }
                         const VecT f0 = LDV(qw.y), f1 = LDV(qw.z), f2 = LDV(qw.w);
-                        VecT q = LDV(qw.x), sc;
-                        if (qs.y) sc = LDV(qs.x);
+                        VecT q = LDV(qw.x), acc;
 #pragma unroll
                         for (int s = 0; s < SPT; ++s) {
-                            double acc = img.bw[0] * f0.v[s];
-                            acc = fma(img.bw[1], f1.v[s], acc);
-                            acc = fma(img.bw[2], f2.v[s], acc);
-                            if (qs.y) acc *= sc.v[s];
-                            q.v[s] = fma(h, acc, q.v[s]);
+                            acc.v[s] = img.bw[0] * f0.v[s];
+                            acc.v[s] = fma(img.bw[1], f1.v[s], acc.v[s]);
+                            acc.v[s] = fma(img.bw[2], f2.v[s], acc.v[s]);
                         }
+                        if (qs.y) {                                    // uniform branch: integrand = scale * (wide value)
+                            const VecT sc = LDV(qs.x);
+#pragma unroll
+                            for (int s = 0; s < SPT; ++s) acc.v[s] *= sc.v[s];
+                        }
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) q.v[s] = fma(h, acc.v[s], q.v[s]);
                         STV(qw.x, q);
                     }
                     pcw = (++e < img.nfe) ? (int)w0.y : at + 1 + 2 * nquad;
