@@ -13,7 +13,9 @@
  *   - unless the name ends in _host, array arguments are DEVICE pointers to contiguous row-major
  *     fp64 on the handle's device, and `stream` is a cudaStream_t passed as void* (NULL = legacy
  *     default stream); calls are asynchronous with respect to the host;
- *   - one handle per (process, device); a handle is not thread-safe.
+ *   - one handle per (process, device); a handle is not thread-safe.  The handles of one process share the
+ *     program window in constant memory (every evaluation call re-uploads its model's program, stream ordered):
+ *     calls on DIFFERENT handles of the same device must be issued on the same stream or be synchronised.
  */
 #ifndef PYDSB_H
 #define PYDSB_H
