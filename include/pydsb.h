@@ -129,6 +129,19 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
                          const double* w, long long n_t, const double* z0, long long z0_rows, const double* opts,
                          double* z_out, double* phi_out, int* status_out, int* iters_out, void* stream);
 
+/* The three-stage formulation on several GPUs: the ONE control vector couples every design point (reference
+ * pyds/run.py:76-91), so with the design points sharded over processes each optimiser iteration sums the
+ * {Phi_mu, Phi, grad, H} statistics of all processes.  `reduce(buf, n, user)` must all-reduce (sum) the n doubles at the
+ * DEVICE pointer `buf` (= reduce_buf) over the processes and return 0 once the result is in place (NCCL / MPI in the
+ * caller's hands; the stream is synchronised before the call).  Every process passes its own n_d_local rows (0 is
+ * allowed), the same theta / w / z0 / opts, and receives the same z_out (nz), phi_out, status_out, iters_out (1 each).
+ * reduce_buf: device buffer of at least 6 * (2 + nz + nz (nz + 1) / 2) doubles. */
+typedef int (*pydsb_allreduce_fn)(double* device_buf, int n, void* user);
+int pydsb_recourse_solve_global_dist(void* handle, const double* d, long long n_d_local, long long n_d_total,
+                                     const double* theta, const double* w, long long n_t, const double* z0,
+                                     const double* opts, double* z_out, double* phi_out, int* status_out, int* iters_out,
+                                     double* reduce_buf, pydsb_allreduce_fn reduce, void* user, void* stream);
+
 /* Counters since the last reset (device-side totals; synchronises the handle's work). */
 int pydsb_get_counters(void* handle, unsigned long long* out, int n, int reset);
 

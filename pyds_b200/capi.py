@@ -21,8 +21,10 @@ INFO_NAMES = ["ns", "nq", "ng", "d_dim", "p_dim", "nz", "nfe", "ncp", "n_units",
 COUNTER_NAMES = ["scenarios", "newton_iters", "newton_warp_iters", "failed", "launches", "newton_flops"]
 
 EXPORTS = ["pydsb_last_error", "pydsb_version", "pydsb_model_create", "pydsb_model_destroy", "pydsb_model_info",
-           "pydsb_eval", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_recourse_solve", "pydsb_get_counters",
-           "pydsb_dfma_peak", "pydsb_assemble"]
+           "pydsb_eval", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_recourse_solve",
+           "pydsb_recourse_solve_global_dist", "pydsb_get_counters", "pydsb_dfma_peak", "pydsb_assemble"]
+# int (*pydsb_allreduce_fn)(double* device_buf, int n, void* user)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
 
 
 class PydsbError(RuntimeError):
@@ -67,6 +69,8 @@ def load():
     L.pydsb_eval_host.argtypes = [vp, dp, ll, dp, dp, ll, dp, ci, dp, dp, dp]
     L.pydsb_recourse_solve.restype = ci
     L.pydsb_recourse_solve.argtypes = [vp, ci, dp, ll, dp, dp, ll, dp, ll, dp, dp, dp, vp, vp, vp]
+    L.pydsb_recourse_solve_global_dist.restype = ci
+    L.pydsb_recourse_solve_global_dist.argtypes = [vp, dp, ll, ll, dp, dp, ll, dp, dp, dp, dp, vp, vp, dp, ALLREDUCE_FN, vp, vp]
     L.pydsb_get_counters.restype = ci
     L.pydsb_get_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong), ci, ci]
     L.pydsb_dfma_peak.restype = ci
@@ -188,6 +192,54 @@ class Engine:
                                               rows, opts.ctypes.data, ptr(z), ptr(phi), ptr(st), ptr(it),
                                               ctypes.c_void_p(stream.cuda_stream)))
         return dict(z=z[:G], phi=phi[:G], status=st[:G], iters=it[:G])
+
+    def recourse_solve_global_dist(self, d_local, n_d_total, theta, w=None, z0=None, group=None, mu0=0.0, mu_min=0.0,
+                                   lam0=0.0, step_tol=0.0, max_iter=0):
+        """The global-control solve with the design points sharded over the ranks of ``group`` (torch.distributed, NCCL):
+        ``d_local`` are this rank's rows (CUDA fp64, may be empty), ``n_d_total`` the rows of all ranks; theta / w / z0
+        are replicated.  Every rank gets the same dict(z (1, nz), phi, status, iters).  One all-reduce of the
+        6 x NV statistics per optimiser iteration is the only exchange."""
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.device)
+        n_d, n_t, nz = d_local.shape[0], theta.shape[0], self.info["nz"]
+        z = torch.empty((1, nz), dtype=torch.float64, device=dev)
+        phi = torch.empty(1, dtype=torch.float64, device=dev)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        it = torch.zeros(1, dtype=torch.int32, device=dev)
+        nv = 2 + nz + nz * (nz + 1) // 2
+        buf = torch.zeros(6 * nv, dtype=torch.float64, device=dev)
+        opts = np.array([mu0, mu_min, lam0, step_tol, max_iter, 1], dtype=np.float64)
+        ptr = lambda t: None if t is None or t.numel() == 0 else t.data_ptr()
+        stream = torch.cuda.current_stream(self.device)
+        err = []
+
+        def reduce(p, n, _user):
+            try:
+                if n != buf.numel():                     # the library and this wrapper must agree on the layout
+                    raise RuntimeError(f"reduction of {n} doubles, buffer holds {buf.numel()}")
+                if dist.get_backend(group) == "nccl":
+                    dist.all_reduce(buf, group=group)
+                    torch.cuda.current_stream(self.device).synchronize()
+                else:                                    # host-side backends (gloo): 276 doubles through the host
+                    h = buf.cpu()
+                    dist.all_reduce(h, group=group)
+                    buf.copy_(h)
+                    torch.cuda.synchronize(self.device)
+                return 0
+            except Exception as e:                       # an exception must not unwind through the C frames
+                err.append(e)
+                return 1
+
+        cb = ALLREDUCE_FN(reduce)
+        torch.cuda.synchronize(self.device)
+        rc = self._lib.pydsb_recourse_solve_global_dist(self._h, ptr(d_local), n_d, int(n_d_total), ptr(theta), ptr(w), n_t,
+                                                        ptr(z0), opts.ctypes.data, ptr(z), ptr(phi), ptr(st), ptr(it),
+                                                        ptr(buf), cb, None, ctypes.c_void_p(stream.cuda_stream))
+        if err:
+            raise err[0]
+        _check(rc)
+        return dict(z=z, phi=phi, status=st, iters=it)
 
     def recourse_solve(self, d, theta, w=None, z0=None, per_scenario=False, global_group=False, **opts):
         """Optimise the controls (numpy in / numpy out).  Returns dict(z, phi, status, iters); ``z`` is

@@ -714,9 +714,17 @@ int pydsb_eval_host(void* handle, const double* d, long long n_d, const double* 
     return PYDSB_OK;
 }
 
-int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long long n_d, const double* theta,
-                         const double* w, long long n_t, const double* z0, long long z0_rows, const double* opts,
-                         double* z_out, double* phi_out, int* status_out, int* iters_out, void* stream)
+}  // extern "C"
+
+namespace {
+
+// Shared body of pydsb_recourse_solve and pydsb_recourse_solve_global_dist.  `reduce` != NULL: the design points of the
+// ONE global group are spread over several processes -- n_d rows here, n_d_total in all -- and after every evaluation
+// the (stages x NV) statistics are summed over the processes through the callback before the (identical) update.
+int recourse_solve_impl(void* handle, int per_scenario, const double* d, long long n_d, long long n_d_total,
+                        const double* theta, const double* w, long long n_t, const double* z0, long long z0_rows,
+                        const double* opts, double* z_out, double* phi_out, int* status_out, int* iters_out,
+                        double* reduce_buf, pydsb_allreduce_fn reduce, void* user, void* stream)
 {
     Model* m = static_cast<Model*>(handle);
     if (!m) return fail(PYDSB_ERR_INVALID, "null handle");
@@ -725,10 +733,12 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     const int nz = img.nz;
     if (nz < 1) return fail(PYDSB_ERR_INVALID, "model has no control to optimise");
     if (n_d < 0 || n_t < 1) return fail(PYDSB_ERR_INVALID, "bad sizes");
-    if (n_d == 0) return PYDSB_OK;
-    if (!d && img.d_dim > 0) return fail(PYDSB_ERR_INVALID, "null d");
+    if (n_d == 0 && !reduce) return PYDSB_OK;
+    if (!d && img.d_dim > 0 && n_d > 0) return fail(PYDSB_ERR_INVALID, "null d");
     if (!theta || !z_out) return fail(PYDSB_ERR_INVALID, "null theta/z_out");
     if (per_scenario < 0 || per_scenario > 2) return fail(PYDSB_ERR_INVALID, "mode must be 0, 1 or 2");
+    if (reduce && (per_scenario != 2 || !reduce_buf || n_d_total < n_d || n_d_total < 1))
+        return fail(PYDSB_ERR_INVALID, "the distributed solve is the global-control mode with a reduction buffer");
     const long long G = per_scenario == 1 ? n_d * n_t : (per_scenario == 2 ? 1 : n_d);
     if (z0 && !(z0_rows == 1 || z0_rows == G)) return fail(PYDSB_ERR_INVALID, "z0 must have 1 or G rows");
     // options: mu0, mu_min, lam0, step_tol, max_iter, check_every
@@ -743,13 +753,14 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
 
     const int n_tiles = (int)((n_t + BLOCK - 1) / BLOCK);
     const int NV = recourse_nv(nz);
-    const long long acc_per_group_ll = per_scenario == 1 ? 1 : (per_scenario == 2 ? n_d * (long long)n_tiles : n_tiles);
+    const long long acc_per_group_ll = per_scenario == 1 ? 1 : (per_scenario == 2 ? (n_d > 0 ? n_d : 1) * (long long)n_tiles : n_tiles);
     if (acc_per_group_ll > 0x7fffffffLL) return fail(PYDSB_ERR_INVALID, "grid too large");
     const int acc_per_group = (int)acc_per_group_ll;
     // workspace: doubles then ints
     const int n_stages = RECOURSE_STAGES;
     const size_t acc_dbl = per_scenario == 1 ? (size_t)G * recourse_nvp(img.ng, nz) : (size_t)G * acc_per_group * n_stages * NV;
-    const size_t nd_dbl = (size_t)G * (2 * nz + 2 + nz + (size_t)nz * nz + 2) + acc_dbl;
+    const size_t red_dbl = per_scenario == 2 ? (size_t)n_stages * NV : 0;   // the global group's summed statistics
+    const size_t nd_dbl = (size_t)G * (2 * nz + 2 + nz + (size_t)nz * nz + 2) + acc_dbl + red_dbl;
     const bool compact = per_scenario == 1;      // running scenarios are compacted after every iteration
     const size_t nd_int = (size_t)G * 3 + 2;
     double* ws = nullptr;
@@ -786,6 +797,7 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     double* lam = Hh + (size_t)G * nz * nz;
     double* mu = lam + G;
     double* acc = mu + G;
+    double* red = reduce_buf ? reduce_buf : acc + acc_dbl;
     int* status = wsi;
     int* first = status + G;
     int* iters = first + G;
@@ -811,7 +823,7 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     CUDA_TRY_WS(cudaMemcpyToSymbolAsync(c_prog_s, m->prog[1].xprog.data(), m->prog[1].xprog.size() * sizeof(uint32_t), 0,
                                         cudaMemcpyHostToDevice, st));
     RecourseArgs ra{};
-    ra.d = d; ra.theta = theta; ra.w = w; ra.n_d = n_d; ra.n_t = n_t; ra.n_tiles = n_tiles;
+    ra.d = d; ra.theta = theta; ra.w = w; ra.n_d = n_d; ra.n_d_total = n_d_total; ra.n_t = n_t; ra.n_tiles = n_tiles;
     ra.per_scenario = per_scenario;
     ra.z_try = z_try; ra.status = status; ra.mu = mu; ra.acc = acc; ra.counters = m->d_counters;
     ra.sens_slot = img.n_units;
@@ -825,6 +837,7 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     const long long total_tiles = n_d * (long long)n_tiles;
     // small grids are bound by the latency of one launch, not by throughput: look at the running count every iteration
     if (!(opts && opts[5] > 0) && total_tiles <= 4096) check_every = 1;
+    if (reduce) check_every = 1;                 // every process must take the same decisions at the same iterations
     if (total_tiles > 0x7fffffffLL || G > 0x7fffffffLL) { cleanup(); return fail(PYDSB_ERR_INVALID, "grid too large"); }
     // every group stops after max_iter evaluations (status 3) at the latest
     const long long* act_in = nullptr;           // null: every group (first iteration; always in the shared modes)
@@ -835,8 +848,23 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
         CUDA_TRY_WS(cudaMemsetAsync(n_out, 0, sizeof(int), st));
         ra.active = act_in; ra.n_active = n_in;
         const unsigned sens_grid = compact ? (unsigned)((upper + BLOCK - 1) / BLOCK) : (unsigned)total_tiles;
-        fn<<<sens_grid, BLOCK, img.smem_bytes, st>>>(img, ra);
-        CUDA_TRY_WS(cudaGetLastError());
+        if (sens_grid > 0) {
+            fn<<<sens_grid, BLOCK, img.smem_bytes, st>>>(img, ra);
+            CUDA_TRY_WS(cudaGetLastError());
+        }
+        if (per_scenario == 2) {
+            // the tile partials of the one global group -> one (stages x NV) vector; with several processes the
+            // caller then sums it over the processes
+            const int snv = n_stages * NV;
+            sum_tiles_kernel<<<snv, 128, 0, st>>>(acc, (int)total_tiles, snv, red);
+            CUDA_TRY_WS(cudaGetLastError());
+            if (reduce) {
+                CUDA_TRY_WS(cudaStreamSynchronize(st));
+                if (reduce(red, snv, user) != 0) { cleanup(); return fail(PYDSB_ERR_INVALID, "all-reduce callback failed"); }
+            }
+            la.acc = red; la.n_tiles = 1;
+            m->launches += 1;
+        }
         la.active_in = act_in; la.n_active_in = n_in; la.n_running = n_out;
         la.active_out = compact ? act + (size_t)(it & 1) * G : nullptr;
         lm_update_kernel<<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
@@ -859,6 +887,28 @@ int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long l
     cleanup();
 #undef CUDA_TRY_WS
     return PYDSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pydsb_recourse_solve(void* handle, int per_scenario, const double* d, long long n_d, const double* theta,
+                         const double* w, long long n_t, const double* z0, long long z0_rows, const double* opts,
+                         double* z_out, double* phi_out, int* status_out, int* iters_out, void* stream)
+{
+    return recourse_solve_impl(handle, per_scenario, d, n_d, n_d, theta, w, n_t, z0, z0_rows, opts, z_out, phi_out, status_out,
+                               iters_out, nullptr, nullptr, nullptr, stream);
+}
+
+int pydsb_recourse_solve_global_dist(void* handle, const double* d, long long n_d_local, long long n_d_total,
+                                     const double* theta, const double* w, long long n_t, const double* z0,
+                                     const double* opts, double* z_out, double* phi_out, int* status_out, int* iters_out,
+                                     double* reduce_buf, pydsb_allreduce_fn reduce, void* user, void* stream)
+{
+    if (!reduce) return fail(PYDSB_ERR_INVALID, "null all-reduce callback");
+    return recourse_solve_impl(handle, 2, d, n_d_local, n_d_total, theta, w, n_t, z0, z0 ? 1 : 0, opts, z_out, phi_out,
+                               status_out, iters_out, reduce_buf, reduce, user, stream);
 }
 
 int pydsb_get_counters(void* handle, unsigned long long* out, int n, int reset)

@@ -60,6 +60,7 @@ struct RecourseArgs {
     const double* theta;
     const double* w;           // may be null -> 1/n_t (shared) ; per-scenario mode uses weight 1
     long long n_d, n_t;
+    long long n_d_total;       // design points of the whole batch (> n_d when the global group spans several processes)
     int n_tiles;
     int per_scenario;          // 0: group = design point, 1: group = scenario, 2: one group for the whole grid
     // per-group optimiser state
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
         double wv = 0.0;
         if (active) {
             wv = ra.w ? __ldg(ra.w + j) : 1.0 / (double)ra.n_t;
-            if (ra.per_scenario == 2) wv /= (double)ra.n_d;      // the whole grid is one sample average
+            if (ra.per_scenario == 2) wv /= (double)ra.n_d_total;   // the whole grid is one sample average
         }
         // v_c = sum_k p_k dc_kc kept in the spare row after Dc
         double* const Vv = Dc + (size_t)ng * nz * BLOCK;
@@ -728,6 +729,24 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
     break;
     }
     return done;
+}
+
+// Sum the tile partials of the (single) global group: out[v] = sum_t acc[t * snv + v].  One CTA per value, a strided
+// pass then a fixed-shape tree, so the result does not depend on scheduling.  (The per-group thread of
+// lm_update_kernel would otherwise walk n_d * n_tiles * stages * NV values alone.)
+__global__ void sum_tiles_kernel(const double* __restrict__ acc, int n_tiles, int snv, double* __restrict__ out)
+{
+    __shared__ double sh[128];
+    const int v = blockIdx.x;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < n_tiles; t += 128) s += acc[(size_t)t * snv + v];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 64; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[v] = sh[0];
 }
 
 __global__ void lm_init_kernel(long long n_groups, int nz, const double* z0, int z0_rows, double* z_cur, double* z_try,

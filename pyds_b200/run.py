@@ -24,7 +24,8 @@ from .solver import Solver
 
 
 class Manager:
-    shards_by_design_point = True          # design points are independent: rows can be split over the ranks
+    shards_by_design_point = True          # rows can be split over the ranks
+    couples_design_points = False          # True: the ranks optimise one control vector together (three-stage)
 
     def __init__(self, config):
         problem = config["problem"]
@@ -91,13 +92,16 @@ class Manager:
         from .parallel import ShardedEfp, shard_rows, shard_sizes
         w_arr = np.full(len(p), 1.0 / max(len(p), 1)) if w is None else np.asarray(w, dtype=np.float64)
         if world > 1 and not self.shards_by_design_point:
-            # one control vector couples every design point (three-stage): each rank solves the whole batch --
-            # identical results on every rank, no speed-up; sharding it needs an all-reduce of the 46-value
-            # {Phi, grad, H} statistics per optimiser iteration
+            # a manager that cannot split its rows: each rank evaluates the whole batch (identical results, no speed-up)
             ind = self._indicators(d, p, w_arr)
             return ((1.0 - ind) * w_arr[None, :]).sum(axis=1)
         a, b = shard_rows(len(d), world, rank)
-        if b > a:
+        if world > 1 and self.couples_design_points:
+            # one control vector couples every design point (three-stage): the ranks optimise it together -- an
+            # all-reduce of the {Phi, grad, H} statistics per iteration -- so every rank calls, rows or not
+            ind = self._indicators(d[a:b], p, w_arr, n_d_total=len(d))
+            P = ((1.0 - ind) * w_arr[None, :]).sum(axis=1)
+        elif b > a:
             ind = self._indicators(d[a:b], p, w_arr)
             P = ((1.0 - ind) * w_arr[None, :]).sum(axis=1)
         else:
@@ -147,13 +151,13 @@ class ThreeStageManager(Manager):
     stage 2 = theta (reference pyds/run.py:71-98; see examples/threestage_reactor.py for the repaired
     example script)."""
 
-    shards_by_design_point = False         # the stage-0 control couples all design points
+    couples_design_points = True           # the stage-0 control couples all design points
 
     def __init__(self, config):
         super().__init__(config)
 
-    def _indicators(self, d, p, w):
-        return self.solver.solve(d, p, w, mode="global")
+    def _indicators(self, d, p, w, n_d_total=None):
+        return self.solver.solve(d, p, w, mode="global", n_d_total=n_d_total)
 
     def g(self, d, p):
         d, p = self._check(d, p)

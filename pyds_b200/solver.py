@@ -42,32 +42,45 @@ class Solver:
         self.controls = None
 
     # ------------------------------------------------------------------------------------------------
-    def solve(self, d=None, p=None, w=None, mode="shared"):
+    def solve(self, d=None, p=None, w=None, mode="shared", n_d_total=None, group=None):
         """Optimise the controls for the current batch and classify every scenario.
 
         ``mode``: ``"shared"`` one control vector per design point (two-stage, reference run.py:55-67),
         ``"global"`` one for the whole grid (three-stage, reference run.py:76-91), ``"per_scenario"``.
+        ``n_d_total`` (global mode under torch.distributed): ``d`` holds only this rank's rows of a batch of
+        ``n_d_total`` design points; the ranks of ``group`` optimise the one control vector together (an all-reduce of
+        the optimiser statistics per iteration) and every rank must make this call, with zero rows if it has none.
         Returns the indicator matrix (n_d, n_p) in {0, 1}."""
         sim = self.parent.simulator
         eng = sim.engine
         if d is None:
             d, p = self.parent._current_inputs
-        d = np.atleast_2d(np.asarray(d, dtype=np.float64))
+        d = np.asarray(d, dtype=np.float64)
+        d = d.reshape(-1, sim.lowered.d_dim) if d.size == 0 else np.atleast_2d(d)
         p = np.atleast_2d(np.asarray(p, dtype=np.float64))
+        if n_d_total is not None and mode != "global":
+            raise ValueError("only the global-control mode couples the ranks")
         self.output = {"relaxation": None, "trajectories": None}
         n_free = int((~sim.lowered.z_fixed).sum()) if sim.lowered.nz else 0
         z, z_mode, tol = None, None, 0.0
         self.result = {"status": None, "iters": None, "phi": None}
         if self.use_relaxation and self.optimise_controls and n_free > 0:
             z0 = sim.default_controls()[None, :]
-            res = eng.recourse_solve(d, p, w, z0=z0, per_scenario=(mode == "per_scenario"), global_group=(mode == "global"),
-                                     **self.lm_options)
+            if n_d_total is not None:
+                res = self._solve_global_sharded(eng, d, int(n_d_total), p, w, z0, group)
+            else:
+                res = eng.recourse_solve(d, p, w, z0=z0, per_scenario=(mode == "per_scenario"),
+                                         global_group=(mode == "global"), **self.lm_options)
             z = res["z"]
             self.result = {"status": res["status"], "iters": res["iters"], "phi": res["phi"]}
             tol = self.feas_tol
         elif n_free > 0:
             z = sim.default_controls()
         self.controls = z
+        if d.shape[0] == 0:                              # a rank without rows (sharded global mode)
+            self._indicator = np.zeros((0, p.shape[0]))
+            self._g = np.zeros((0, p.shape[0], sim.lowered.ng))
+            return self._indicator
         g, ind, _ = eng.eval_host(d, p, None, z=z, want_g=True, want_ind=False, want_P=False)
         c = g / sim.lowered.big_m[None, None, :]
         with np.errstate(invalid="ignore"):
@@ -84,6 +97,15 @@ class Solver:
         if self.save_output:
             self.output["relaxation"] = self._collect_output()
         return indicator
+
+    def _solve_global_sharded(self, eng, d_local, n_d_total, p, w, z0, group):
+        import torch
+        dev = torch.device("cuda", eng.device)
+        up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        opts = {k: v for k, v in self.lm_options.items() if k != "check_every"}
+        r = eng.recourse_solve_global_dist(up(d_local), n_d_total, up(p), up(w), up(z0), group=group, **opts)
+        return dict(z=r["z"].cpu().numpy().reshape(-1), phi=r["phi"].cpu().numpy(), status=r["status"].cpu().numpy(),
+                    iters=r["iters"].cpu().numpy())
 
     def _get_indicator_var_values(self):
         """Indicators of the final-stage scenarios in leaf (product) order (reference solver.py:91-98)."""

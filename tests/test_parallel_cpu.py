@@ -71,7 +71,7 @@ def test_sharded_efp_gloo_world2(n_d):
         np.testing.assert_allclose(res[r], P_ref, atol=1e-15)
 
 
-def _manager_worker(rank, world, port, shards, q):
+def _manager_worker(rank, world, port, shards, q, n_d=11):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from pyds_b200 import run
@@ -80,7 +80,8 @@ def _manager_worker(rank, world, port, shards, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
 
     class Stub(run.Manager):
-        shards_by_design_point = shards
+        shards_by_design_point = shards != False                          # noqa: E712  ("coupled" shards too)
+        couples_design_points = shards == "coupled"
 
         def __init__(self):
             self.rows_seen = []
@@ -88,12 +89,17 @@ def _manager_worker(rank, world, port, shards, q):
         def _check(self, d, p):
             return np.asarray(d, dtype=np.float64), np.asarray(p, dtype=np.float64)
 
-        def _indicators(self, d, p, w):
-            self.rows_seen.append(len(d))
+        def _indicators(self, d, p, w, n_d_total=None):
+            self.rows_seen.append(len(d) if n_d_total is None else (len(d), n_d_total))
+            if n_d_total is not None:                                     # the ranks meet once per optimiser iteration
+                import torch
+                t = torch.tensor([float(len(d))], dtype=torch.float64)
+                dist.all_reduce(t)
+                assert int(t.item()) == n_d_total
             return (d[:, :1] > p[None, :, 0]).astype(np.float64)         # indicator 1 where d0 > theta0
 
     rng = np.random.default_rng(9)
-    d, p = rng.uniform(size=(11, 2)), rng.uniform(size=(7, 1))
+    d, p = rng.uniform(size=(n_d, 2)), rng.uniform(size=(7, 1))
     w = np.full(7, 1.0 / 7)
     m = Stub()
     P = m.efp(d, p, w)
@@ -104,8 +110,7 @@ def _manager_worker(rank, world, port, shards, q):
 
 @pytest.mark.parametrize("shards", [True, False])
 def test_manager_efp_sharding_rule_gloo_world2(shards):
-    """Two-stage managers split the design points over the ranks; the three-stage manager (one control vector
-    couples every design point) must see the whole batch on every rank."""
+    """Managers split the design points over the ranks unless they opt out (then every rank sees the whole batch)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 31500 + (os.getpid() + int(shards)) % 2000
@@ -122,3 +127,25 @@ def test_manager_efp_sharding_rule_gloo_world2(shards):
     for r in range(2):
         np.testing.assert_allclose(res[r][0], P_ref, atol=1e-15)
     assert sorted(res[r][1][0] for r in range(2)) == ([5, 6] if shards else [11, 11])
+
+
+@pytest.mark.parametrize("n_d", [11, 1])
+def test_manager_efp_coupled_design_points_gloo_world2(n_d):
+    """The three-stage manager shards its rows AND calls the solver on every rank -- also on a rank without rows --
+    because the ranks all-reduce the optimiser statistics of the one global control vector."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() + n_d) % 2000
+    procs = [ctx.Process(target=_manager_worker, args=(r, 2, port, "coupled", q, n_d)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = {r: (P, rows) for r, P, rows in (q.get(timeout=180) for _ in range(2))}
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    rng = np.random.default_rng(9)
+    d, p = rng.uniform(size=(n_d, 2)), rng.uniform(size=(7, 1))
+    P_ref = ((1.0 - (d[:, :1] > p[None, :, 0])) / 7.0).sum(axis=1)
+    for r in range(2):
+        np.testing.assert_allclose(res[r][0], P_ref, atol=1e-15)
+    assert sorted(res[r][1][0] for r in range(2)) == ([(5, 11), (6, 11)] if n_d == 11 else [(0, 1), (1, 1)])
