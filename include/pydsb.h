@@ -98,6 +98,16 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
                long long n_t, const double* z, int z_mode, double* g_out, double* ind_out, double* P_out,
                void* stream);
 
+/* The state trajectories behind g: the converged collocation solution of every scenario, what the reference reads back
+ * from the solved Pyomo model with utils.parse_value(scen, 'c') for its output records (reference pyds/solver.py:100-117,
+ * pyds/utils.py:136-156) and what pyomo.dae.Simulator returns for the warm start (reference pyds/simulator.py:112-119).
+ * x_out: (n_d, n_t, 1 + ncp * nfe, ns + nq) -- time points tau = 0, then the ncp Radau points of every finite element
+ * in order; columns: the ns dynamic states, then the nq quadrature states (model order within each; pydsb_model_info
+ * gives ns, nq, nfe, ncp).  failed_out (n_d, n_t), optional: 1.0 where the Newton solve failed, else 0.0.
+ * z / z_mode as pydsb_eval.  Cold path: same kernels and program as pydsb_eval with the stores added. */
+int pydsb_state_solve(void* handle, const double* d, long long n_d, const double* theta, long long n_t, const double* z,
+                      int z_mode, double* x_out, double* failed_out, void* stream);
+
 /* Convenience forms with the names SURVEY.md section 8b proposes. */
 int pydsb_eval_g(void* handle, const double* d, long long n_d, const double* theta, long long n_t,
                  double* g_out, void* stream);

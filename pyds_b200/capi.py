@@ -21,7 +21,7 @@ INFO_NAMES = ["ns", "nq", "ng", "d_dim", "p_dim", "nz", "nfe", "ncp", "n_units",
 COUNTER_NAMES = ["scenarios", "newton_iters", "newton_warp_iters", "failed", "launches", "newton_flops"]
 
 EXPORTS = ["pydsb_last_error", "pydsb_version", "pydsb_model_create", "pydsb_model_destroy", "pydsb_model_info",
-           "pydsb_eval", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_recourse_solve",
+           "pydsb_eval", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_state_solve", "pydsb_recourse_solve",
            "pydsb_recourse_solve_global_dist", "pydsb_get_counters", "pydsb_dfma_peak", "pydsb_assemble"]
 # int (*pydsb_allreduce_fn)(double* device_buf, int n, void* user)
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
@@ -67,6 +67,8 @@ def load():
     L.pydsb_efp.argtypes = [vp, dp, ll, dp, dp, ll, dp, vp]
     L.pydsb_eval_host.restype = ci
     L.pydsb_eval_host.argtypes = [vp, dp, ll, dp, dp, ll, dp, ci, dp, dp, dp]
+    L.pydsb_state_solve.restype = ci
+    L.pydsb_state_solve.argtypes = [vp, dp, ll, dp, ll, dp, ci, dp, dp, vp]
     L.pydsb_recourse_solve.restype = ci
     L.pydsb_recourse_solve.argtypes = [vp, ci, dp, ll, dp, dp, ll, dp, ll, dp, dp, dp, vp, vp, vp]
     L.pydsb_recourse_solve_global_dist.restype = ci
@@ -167,6 +169,39 @@ class Engine:
         ptr = lambda t: None if t is None else t.data_ptr()
         _check(self._lib.pydsb_eval(self._h, ptr(d), n_d, ptr(theta), ptr(w), n_t, ptr(z), z_mode if z is not None else Z_MODEL,
                                     ptr(g_out), ptr(ind_out), ptr(P_out), ctypes.c_void_p(stream.cuda_stream)))
+
+    def state_solve(self, d, theta, z=None, z_mode=None):
+        """The collocation solution behind g (numpy in / numpy out): ``x`` (n_d, n_t, 1 + ncp * nfe, ns + nq) -- tau = 0
+        then the Radau points of every finite element; dynamic states first, then quadrature states -- and ``failed``
+        (n_d, n_t) bool.  ``time_grid()`` gives the tau values of axis 2."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        d = _np64(d)
+        d = d.reshape(-1, self.info["d_dim"]) if self.info["d_dim"] else d.reshape(len(d), 0)
+        theta = _np64(theta).reshape(-1, self.info["p_dim"])
+        n_d, n_t = d.shape[0], theta.shape[0]
+        z, z_mode = self._norm_z(z, z_mode, n_d, n_t)
+        n_time = 1 + self.info["ncp"] * self.info["nfe"]
+        n_col = self.info["ns"] + self.info["nq"]
+        if n_d == 0 or n_t == 0:
+            return np.zeros((n_d, n_t, n_time, n_col)), np.zeros((n_d, n_t), dtype=bool)
+        up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        td, tt, tz = up(d), up(theta), up(z)
+        x = torch.empty((n_d, n_t, n_time, n_col), dtype=torch.float64, device=dev)
+        failed = torch.empty((n_d, n_t), dtype=torch.float64, device=dev)
+        ptr = lambda t: None if t is None or t.numel() == 0 else t.data_ptr()
+        stream = torch.cuda.current_stream(self.device)
+        _check(self._lib.pydsb_state_solve(self._h, ptr(td), n_d, ptr(tt), n_t, ptr(tz), z_mode, ptr(x), ptr(failed),
+                                           ctypes.c_void_p(stream.cuda_stream)))
+        stream.synchronize()
+        return x.cpu().numpy(), failed.cpu().numpy() != 0.0
+
+    def time_grid(self):
+        """Normalised time of the trajectory rows: 0, then (e + c_j) / nfe for the Radau roots c_j."""
+        from .collocation import radau_tables
+        nfe, ncp = self.info["nfe"], self.info["ncp"]
+        c = radau_tables(ncp)[0][1:]
+        return np.concatenate([[0.0], ((np.arange(nfe)[:, None] + c[None, :]) / nfe).reshape(-1)])
 
     def recourse_solve_device(self, d, theta, w=None, z0=None, per_scenario=False, global_group=False, mu0=0.0, mu_min=0.0,
                               lam0=0.0, step_tol=0.0, max_iter=0, check_every=0):

@@ -158,7 +158,10 @@ __device__ __forceinline__ void newton_step(const ExecImage& img, int at, unsign
 
 // MAXNS = largest block of coupled states (1..3); SPT = scenarios per thread (2 only with MAXNS = 1: the
 // Newton matrices of two scenarios have to fit the register file).
-template <int MAXNS, int SPT>
+// TRAJ (pydsb_state_solve, cold): the same program, but instead of g the state trajectories are written --
+// la.g_out is (n_d, n_t, 1 + 3 nfe, ns + nq): row 0 the initial values, then the collocation points of every
+// element (dynamic states first, quadrature states after them); la.ind_out receives 1.0 for a failed solve.
+template <int MAXNS, int SPT, bool TRAJ = false>
 __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))))
     feas_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ LaunchArgs la)
 {
@@ -206,6 +209,24 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
 
     const double h = 1.0 / (double)img.nfe;
     const int p_dim = img.p_dim, d_dim = img.d_dim;
+    // TRAJ: quadrature states at the inner collocation points need the integration matrix = inverse of the
+    // differentiation matrix the Newton systems use (its last row are the quadrature weights bw)
+    double aint[TRAJ ? 2 : 1][3];
+    if constexpr (TRAJ) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double M[3][3], r[3] = {c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? 1.0 : 0.0};
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) M[jj][kk] = img.adot[4 * (kk + 1) + jj + 1];
+            lu_solve_inplace<3>(M, r);
+            aint[0][c] = r[0];
+            aint[1][c] = r[1];
+        }
+    }
+    const int traj_w = img.ns + img.nq;                                 // TRAJ: values per time point
+    const long long traj_rows = 1 + 3 * (long long)img.nfe;
 
     const long long total = la.n_d * (long long)la.n_tiles;
     unsigned phase = 0;
@@ -414,6 +435,19 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                     // quadratures  x_q += h * sum_j bw_j fq(x_j)  at the converged points, then the next element
                     const int at = pcw - 2;
                     const int nquad = (int)w0.z;
+                    if constexpr (TRAJ) {
+                        // converged collocation points of the dynamic states; quadrature states without an entry
+                        // below (zero integrand) keep their value
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) {
+                            if (!valid[s]) continue;
+                            double* o = la.g_out + ((i_d * la.n_t + jj_[s]) * traj_rows + 1 + 3 * e) * traj_w;
+                            for (int p = 0; p < 3; ++p) {
+                                for (int n = 0; n < img.ns; ++n) o[p * traj_w + n] = slot(img.x_slot + 3 * n + p, s);
+                                for (int qn = 0; qn < img.nq; ++qn) o[p * traj_w + img.ns + qn] = slot(img.qe_slot + qn, s);
+                            }
+                        }
+                    }
                     for (int qi = 0; qi < nquad; ++qi) {
                         const uint4 qw = c_prog[at + 1 + 2 * qi];
                         const uint4 qs = c_prog[at + 2 + 2 * qi];      // { scale offset, has scale }
@@ -425,10 +459,28 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                             acc.v[s] = fma(img.bw[1], f1.v[s], acc.v[s]);
                             acc.v[s] = fma(img.bw[2], f2.v[s], acc.v[s]);
                         }
+                        VecT sc;
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) sc.v[s] = 1.0;
                         if (qs.y) {                                    // uniform branch: integrand = scale * (wide value)
-                            const VecT sc = LDV(qs.x);
+                            sc = LDV(qs.x);
 #pragma unroll
                             for (int s = 0; s < SPT; ++s) acc.v[s] *= sc.v[s];
+                        }
+                        if constexpr (TRAJ) {
+                            const int qn = (int)(qw.x / USP) - img.qe_slot;
+#pragma unroll
+                            for (int s = 0; s < SPT; ++s) {
+                                if (!valid[s]) continue;
+                                double* o = la.g_out + ((i_d * la.n_t + jj_[s]) * traj_rows + 1 + 3 * e) * traj_w + img.ns + qn;
+                                for (int p = 0; p < 2; ++p) {
+                                    double a = aint[p][0] * f0.v[s];
+                                    a = fma(aint[p][1], f1.v[s], a);
+                                    a = fma(aint[p][2], f2.v[s], a);
+                                    o[p * traj_w] = fma(h, a * sc.v[s], q.v[s]);
+                                }
+                                o[2 * traj_w] = fma(h, acc.v[s], q.v[s]);
+                            }
                         }
 #pragma unroll
                         for (int s = 0; s < SPT; ++s) q.v[s] = fma(h, acc.v[s], q.v[s]);
@@ -516,6 +568,13 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                         for (int n = 0; n < img.ns; ++n) slot(img.x_slot + 3 * n + 2, s) = x0v[n];
                         for (int q = 0; q < img.nq; ++q) slot(img.qe_slot + q, s) = ref_ld(tab_q0[q], s);
                         if (img.zero_slot) slot(img.zero_slot, s) = 0.0;
+                        if constexpr (TRAJ) {
+                            if (valid[s]) {
+                                double* o = la.g_out + (i_d * la.n_t + jj_[s]) * traj_rows * traj_w;
+                                for (int n = 0; n < img.ns; ++n) o[n] = x0v[n];
+                                for (int qn = 0; qn < img.nq; ++qn) o[img.ns + qn] = slot(img.qe_slot + qn, s);
+                            }
+                        }
                     }
                     break;
                 case X_LDCTRL: {                           // control w0.z of finite element e -> slot w0.y
@@ -573,9 +632,10 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 double gv = ref_ld(tab_g[c], s);
                 if (failed[s]) gv = __longlong_as_double(0x7ff8000000000000LL);
                 feasible = feasible && (gv <= 0.0);
-                if (la.g_out && valid[s]) la.g_out[(i_d * la.n_t + j) * img.ng + c] = gv;
+                if constexpr (!TRAJ)
+                    if (la.g_out && valid[s]) la.g_out[(i_d * la.n_t + j) * img.ng + c] = gv;
             }
-            if (la.ind_out && valid[s]) la.ind_out[i_d * la.n_t + j] = feasible ? -0.0 : -1.0;
+            if (la.ind_out && valid[s]) la.ind_out[i_d * la.n_t + j] = TRAJ ? (failed[s] ? 1.0 : 0.0) : (feasible ? -0.0 : -1.0);
             if (valid[s] && feasible) wv += la.w ? __ldg(la.w + j) : 1.0 / (double)la.n_t;
             if (valid[s]) {
                 cnt_iters += my_acc[s] >> 40;

@@ -103,6 +103,18 @@ FeasFn feas_for(int ns, int spt)
     }
 }
 
+// the trajectory-writing variants of the same kernels (pydsb_state_solve)
+FeasFn traj_for(int ns, int spt)
+{
+    switch (ns * 10 + spt) {
+    case 11: return feas_kernel<1, 1, true>;
+    case 12: return feas_kernel<1, 2, true>;
+    case 21: return feas_kernel<2, 1, true>;
+    case 31: return feas_kernel<3, 1, true>;
+    default: return nullptr;
+    }
+}
+
 int image_maxns(const ExecImage& g)
 {
     int maxns = 1;
@@ -601,8 +613,13 @@ int pydsb_model_info(void* handle, long long* out, int n)
     return PYDSB_OK;
 }
 
-int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta, const double* w, long long n_t,
-               const double* z, int z_mode, double* g_out, double* ind_out, double* P_out, void* stream)
+}  // extern "C"
+
+namespace {
+
+// pydsb_eval, or with `traj` the trajectory variant (g_out = x_out, ind_out = failed_out)
+int eval_impl(void* handle, const double* d, long long n_d, const double* theta, const double* w, long long n_t,
+              const double* z, int z_mode, double* g_out, double* ind_out, double* P_out, bool traj, void* stream)
 {
     Model* m = static_cast<Model*>(handle);
     if (!m) return fail(PYDSB_ERR_INVALID, "null handle");
@@ -634,7 +651,7 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
 
     const long long max_ctas = (long long)m->num_sms * m->blocks_per_sm;
     const int grid = (int)(total < max_ctas ? total : max_ctas);
-    FeasFn fn = feas_for(image_maxns(img), img.spt);
+    FeasFn fn = traj ? traj_for(image_maxns(img), img.spt) : feas_for(image_maxns(img), img.spt);
     // several models may share one template instantiation: (re)assert this model's smem size and
     // (re)load its point tape into the constant bank (stream ordered)
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
@@ -650,6 +667,23 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
         m->launches += 1;
     }
     return PYDSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta, const double* w, long long n_t,
+               const double* z, int z_mode, double* g_out, double* ind_out, double* P_out, void* stream)
+{
+    return eval_impl(handle, d, n_d, theta, w, n_t, z, z_mode, g_out, ind_out, P_out, false, stream);
+}
+
+int pydsb_state_solve(void* handle, const double* d, long long n_d, const double* theta, long long n_t, const double* z,
+                      int z_mode, double* x_out, double* failed_out, void* stream)
+{
+    if (!x_out) return fail(PYDSB_ERR_INVALID, "null x_out");
+    return eval_impl(handle, d, n_d, theta, nullptr, n_t, z, z_mode, x_out, failed_out, nullptr, true, stream);
 }
 
 int pydsb_eval_g(void* handle, const double* d, long long n_d, const double* theta, long long n_t, double* g_out,

@@ -139,7 +139,7 @@ class TwoStageManager(Manager):
             g_list.append(g_mat)
             self.output_manager.clear_buffer()
             self.output_manager.add_input({self._stages[0]: d[i:i + 1], self._stages[1]: p})
-            self.output_manager.add_solver_solution(self.solver.output)
+            self.output_manager.add_solver_solution(self.solver.output_for(i))
             records.append(self.output_manager.data)         # one record per design point (reference run.py:67)
         if records:
             self.output_manager.write_records_to_disk(records)

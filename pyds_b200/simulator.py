@@ -41,6 +41,7 @@ def lower_stage_model(model, input_map, f_profile_suffix=None, **model_kw):
         raise LoweringError("the model transformation must apply 'dae.collocation'")
     nfe, ncp = model._collocation["nfe"], model._collocation["ncp"]
     dm = DaeModel(d_names, p_names, nfe=nfe, ncp=ncp, **model_kw)
+    dm.state_keys = {}                 # state name -> (Var name, index key, (t0, t1)): for the output records
     g_src, g = model._graph, dm.graph
 
     tok = model._tokens
@@ -151,6 +152,7 @@ def lower_stage_model(model, input_map, f_profile_suffix=None, **model_kw):
         if hasattr(fx, "_as_expr") or isinstance(fx, T.Expr):
             x0 = translate(g_src.wrap(fx), {})
         state_handle[(vid, key)] = dm.state(f"{sv.name}{list(key) if key else ''}", x0)
+        dm.state_keys[f"{sv.name}{list(key) if key else ''}"] = (sv.name, key, sv.contset.bounds)
 
     # --- equations -------------------------------------------------------------------------------------
     alg_defs = {}

@@ -94,7 +94,11 @@ class Solver:
                 print("Warning: Infeasible relaxation. Total number of infeasible solves: {}".format(self.no_infeasible))
         self._indicator = indicator
         self._g = g
+        self._traj = None
         if self.save_output:
+            # the solved state profiles the reference reads back with utils.parse_value (pyds/solver.py:100-117)
+            self._traj = eng.state_solve(d, p, z=z)[0]
+            self._time = eng.time_grid()
             self.output["relaxation"] = self._collect_output()
         return indicator
 
@@ -111,8 +115,57 @@ class Solver:
         """Indicators of the final-stage scenarios in leaf (product) order (reference solver.py:91-98)."""
         return self._indicator.reshape(-1).copy()
 
+    def _scenario_values(self, i, j):
+        """``{name: {index + (t,): value}}`` of scenario (i, j) for the last stage's names of the output map -- what
+        ``utils.parse_value(scen, name)`` returns for an indexed Var (reference pyds/utils.py:149-155).  Time keys
+        are the discretised ContinuousSet points, rounded to 6 decimals as Pyomo's collocation does [from memory]."""
+        sim = self.parent.simulator
+        lm = sim.lowered
+        names = lm.dyn_states + lm.quad_states
+        keys = getattr(sim.dae_model, "state_keys", {})
+        out_map = self.parent.output_map
+        wanted = out_map[max(out_map)] if out_map else []
+        v = {}
+        for name in wanted:
+            vals = None
+            for col, sname in enumerate(names):
+                var, key, (t0, t1) = keys.get(sname, (sname, (), (0.0, 1.0)))
+                if var != name:
+                    continue
+                vals = {} if vals is None else vals
+                for k, tau in enumerate(self._time):
+                    t = round(t0 + (t1 - t0) * float(tau), 6)
+                    vals[tuple(key) + (t,) if key else t] = float(self._traj[i, j, k, col])
+            v[name] = vals                                   # None: no such component (parse_value's answer too)
+        return v
+
+    def _record(self, rows):
+        """One output container over the design points ``rows`` (leaf order: design point major, theta minor)."""
+        rows = list(rows)
+        n_p = self._g.shape[1]
+        phi = self.result["phi"]
+        data = []
+        for i in rows:
+            for j in range(n_p):
+                v = self._scenario_values(i, j) if self._traj is not None else {}
+                v["g"] = self._g[i, j].copy()
+                data.append(v)
+        z = None if self.controls is None else np.asarray(self.controls)
+        if z is not None and z.ndim > 1:
+            z = z[list(rows)] if len(rows) > 1 else z[list(rows)[0]]
+        if phi is None:
+            objective = None
+        else:
+            objective = np.asarray(phi).reshape(-1)[list(rows)] if np.size(phi) == self._g.shape[0] else np.asarray(phi).copy()
+        return {"data": data, "objective": objective, "controls": None if z is None else z.copy(), "user time": None,
+                "infeasible": bool((self._indicator[list(rows)] == 1).all())}
+
     def _collect_output(self):
-        return {"data": [{"g": self._g[i].copy(), "controls": None if self.controls is None else np.asarray(self.controls).copy()}
-                         for i in range(self._g.shape[0])],
-                "objective": None if self.result["phi"] is None else np.asarray(self.result["phi"]).copy(),
-                "user time": None, "infeasible": bool((self._indicator == 1).all())}
+        return self._record(range(self._g.shape[0]))
+
+    def output_for(self, i):
+        """The solver output of design point ``i`` alone (the two-stage manager writes one record per design point,
+        reference pyds/run.py:55-67)."""
+        if not self.save_output or self.output["relaxation"] is None:
+            return self.output
+        return {"relaxation": self._record([i]), "trajectories": None}

@@ -113,3 +113,36 @@ def test_nested_sampling_on_the_twostage_problem(tmp_path):
     assert res["live_efp"].mean() > res["samples_efp"][:40].mean()
     best = res["live_points"][np.argmax(res["live_efp"])]
     assert 255.0 <= best[1] <= 300.0
+
+
+def test_saved_output_records_carry_the_state_profiles(tmp_path):
+    """'save output': True -- every record holds, per theta scenario, the value dict the reference builds with
+    utils.parse_value(scen, 'c') (pyds/solver.py:100-117): {('A', t): value, ...} over the 25 collocation times."""
+    from examples import twostage_reactor as ex
+    cfg = ex.build_config(str(tmp_path))
+    cfg["solver"]["save output"] = True
+    m = TwoStageManager(cfg)
+    rng = np.random.default_rng(11)
+    d = np.stack([rng.uniform(250, 350, 3), rng.uniform(250, 300, 3)], axis=1)
+    p = K.theta_samples(7)
+    g_list = m.g(d, p)
+    recs = read_output_file(str(tmp_path / "pyds_output.pkl"))
+    assert len(recs) == 3
+    eng = m.simulator.engine
+    x, failed = eng.state_solve(d, p, z=m.solver.controls)
+    names = m.simulator.lowered.dyn_states + m.simulator.lowered.quad_states
+    col = {"A": names.index("c['A']"), "B": names.index("c['B']"), "C": names.index("c['C']")}
+    tg = eng.time_grid()
+    for i, rec in enumerate(recs):
+        np.testing.assert_array_equal(rec["input"][0], d[i:i + 1])
+        rel = rec["solver"]["relaxation"]
+        assert len(rel["data"]) == 7 and rel["controls"].shape == (8,)
+        for j, v in enumerate(rel["data"]):
+            c = v["c"]
+            assert len(c) == 75 and ("A", 0.0) in c and ("C", 1.0) in c
+            assert ("B", round(0.155051 / 8, 6)) in c                      # first Radau point of the first element
+            for sp, cc in col.items():
+                got = np.array([c[(sp, round(float(t), 6))] for t in tg])
+                np.testing.assert_array_equal(got, x[i, j, :, cc])
+            np.testing.assert_array_equal(v["g"], m.solver._g[i, j])
+        assert rel["infeasible"] == bool((g_list[i] == -1.0).all())

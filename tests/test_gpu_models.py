@@ -185,3 +185,48 @@ def test_mixed_polynomial_and_generic_blocks_in_one_program():
     assert np.all(((ind == 0.0) == r["feasible"]) | near)
     np.testing.assert_allclose(P, (r["feasible"] * w[None, :]).sum(1), atol=1e-12 + near.sum() / 211)
     assert 0.02 < P.mean() < 0.98
+
+
+def test_state_solve_trajectories_against_two_cpu_restatements():
+    """pydsb_state_solve: dynamic states against the tape interpreter's trajectories, and the quadrature state (cC is
+    integrated, not solved for, in the default lowering) against the independent 9-unknown kinetics solve in which cC
+    is an ordinary collocation unknown -- that pins the integration-matrix rows used for the inner points."""
+    from oracle import kinetics as K, tape_vm
+    lm = models.kinetics("twostage").lower()
+    eng = capi.Engine(lm.blob, 0)
+    rng = np.random.default_rng(3)
+    d = np.stack([rng.uniform(250, 350, 5), rng.uniform(250, 300, 5)], axis=1)
+    p = K.theta_samples(37)
+    z = rng.uniform(0.0, 2.5, size=(5, lm.nz))
+    x, failed = eng.state_solve(d, p, z=z)
+    ns, nq = lm.ns, lm.nq
+    assert x.shape == (5, 37, 25, ns + nq) and failed.shape == (5, 37) and not failed.any()
+    tg = eng.time_grid()
+    assert tg.shape == (25,) and tg[0] == 0.0 and tg[-1] == 1.0 and np.all(np.diff(tg) > 0)
+    vm = tape_vm.TapeVM(lm.blob)
+    ref = vm.evaluate(d, p, z=z, return_traj=True)["traj"]
+    np.testing.assert_allclose(x[..., :ns], ref, rtol=1e-10, atol=1e-9)
+    # all three concentrations from the dense restatement (columns A, B, C)
+    names = lm.dyn_states + lm.quad_states
+    col = {n: names.index(n) for n in names}
+    for i in range(5):
+        traj = K.solve_states(d[i, 0], d[i, 1], p[:, 0], p[:, 1], p[:, 2], p[:, 3], F=z[i], return_traj=True)[3]
+        for k, nm in enumerate(("cA", "cB", "cC")):
+            np.testing.assert_allclose(x[i, :, :, col[nm]], traj[:, :, k], rtol=1e-9, atol=1e-8)
+        # u' = F_in / t_f with a piecewise-constant feed: exact piecewise-linear integral
+        e_of = np.minimum((tg * 8 - 1e-12).astype(int).clip(0), 7)
+        u_ref = (np.concatenate([[0.0], np.cumsum(z[i])])[e_of] / 8 + z[i][e_of] * (tg - e_of / 8)) / d[i, 0]
+        np.testing.assert_allclose(x[i, :, :, col["u"]], np.broadcast_to(u_ref, (37, 25)), rtol=1e-12, atol=1e-14)
+    # the end point of the trajectory is what g is computed from: same solve as the feasibility kernel
+    g = eng.eval_host(d, p, None, z=z, want_g=True, want_P=False)[0]
+    g_ref = vm.evaluate(d, p, z=z)["g"]
+    np.testing.assert_allclose(g, g_ref, rtol=1e-10, atol=1e-9)
+    # no-control model, two scenarios per thread, ragged tile
+    lm3 = models.kinetics("design4").lower()
+    eng3 = capi.Engine(lm3.blob, 0)
+    assert eng3.info["scenarios_per_thread"] == 2
+    d3, p3, _ = __import__("bench").make_inputs(3, 301)
+    x3, f3 = eng3.state_solve(d3, p3)
+    ref3 = tape_vm.TapeVM(lm3.blob).evaluate(d3, p3, return_traj=True)["traj"]
+    np.testing.assert_allclose(x3[..., :lm3.ns], ref3, rtol=1e-10, atol=1e-9)
+    assert not f3.any()
