@@ -98,6 +98,14 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
                long long n_t, const double* z, int z_mode, double* g_out, double* ind_out, double* P_out,
                void* stream);
 
+/* pydsb_eval with the classification rule of the relaxed big-M problem: a scenario is feasible when
+ * g_k / M_k <= feas_tol for every k (big-M-scaled units; reference pyds/solver.py:71-80 snaps the relaxed indicator
+ * `value == 0 -> 0 else 1`, and a solver returns an indicator on its bound as exactly 0 while the big-M rows hold to its
+ * feasibility tolerance).  feas_tol = 0 is pydsb_eval.  Lets the managers reduce P(feasible) at the optimised controls
+ * on the device instead of copying g to the host. */
+int pydsb_eval_tol(void* handle, const double* d, long long n_d, const double* theta, const double* w, long long n_t,
+                   const double* z, int z_mode, double feas_tol, double* g_out, double* ind_out, double* P_out, void* stream);
+
 /* The state trajectories behind g: the converged collocation solution of every scenario, what the reference reads back
  * from the solved Pyomo model with utils.parse_value(scen, 'c') for its output records (reference pyds/solver.py:100-117,
  * pyds/utils.py:136-156) and what pyomo.dae.Simulator returns for the warm start (reference pyds/simulator.py:112-119).

@@ -21,7 +21,7 @@ INFO_NAMES = ["ns", "nq", "ng", "d_dim", "p_dim", "nz", "nfe", "ncp", "n_units",
 COUNTER_NAMES = ["scenarios", "newton_iters", "newton_warp_iters", "failed", "launches", "newton_flops"]
 
 EXPORTS = ["pydsb_last_error", "pydsb_version", "pydsb_model_create", "pydsb_model_destroy", "pydsb_model_info",
-           "pydsb_eval", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_state_solve", "pydsb_recourse_solve",
+           "pydsb_eval", "pydsb_eval_tol", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_state_solve", "pydsb_recourse_solve",
            "pydsb_recourse_solve_global_dist", "pydsb_get_counters", "pydsb_dfma_peak", "pydsb_assemble"]
 # int (*pydsb_allreduce_fn)(double* device_buf, int n, void* user)
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
@@ -67,6 +67,8 @@ def load():
     L.pydsb_efp.argtypes = [vp, dp, ll, dp, dp, ll, dp, vp]
     L.pydsb_eval_host.restype = ci
     L.pydsb_eval_host.argtypes = [vp, dp, ll, dp, dp, ll, dp, ci, dp, dp, dp]
+    L.pydsb_eval_tol.restype = ci
+    L.pydsb_eval_tol.argtypes = [vp, dp, ll, dp, dp, ll, dp, ci, ctypes.c_double, dp, dp, dp, vp]
     L.pydsb_state_solve.restype = ci
     L.pydsb_state_solve.argtypes = [vp, dp, ll, dp, ll, dp, ci, dp, dp, vp]
     L.pydsb_recourse_solve.restype = ci
@@ -152,8 +154,10 @@ class Engine:
         return z, z_mode
 
     # -- device (torch tensor) path ----------------------------------------------------------------
-    def eval_device(self, d, theta, w=None, z=None, z_mode=Z_MODEL, g_out=None, ind_out=None, P_out=None, stream=None):
-        """All arguments are contiguous fp64 CUDA tensors (or None); asynchronous on ``stream``."""
+    def eval_device(self, d, theta, w=None, z=None, z_mode=Z_MODEL, g_out=None, ind_out=None, P_out=None, stream=None,
+                    feas_tol=0.0):
+        """All arguments are contiguous fp64 CUDA tensors (or None); asynchronous on ``stream``.  ``feas_tol`` > 0:
+        a scenario counts as feasible when ``g_k / M_k <= feas_tol`` for every k (the relaxed big-M rule)."""
         import torch
         for name, t in (("d", d), ("theta", theta), ("w", w), ("z", z), ("g_out", g_out), ("ind_out", ind_out), ("P_out", P_out)):
             if t is None:
@@ -167,8 +171,9 @@ class Engine:
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
         ptr = lambda t: None if t is None else t.data_ptr()
-        _check(self._lib.pydsb_eval(self._h, ptr(d), n_d, ptr(theta), ptr(w), n_t, ptr(z), z_mode if z is not None else Z_MODEL,
-                                    ptr(g_out), ptr(ind_out), ptr(P_out), ctypes.c_void_p(stream.cuda_stream)))
+        _check(self._lib.pydsb_eval_tol(self._h, ptr(d), n_d, ptr(theta), ptr(w), n_t, ptr(z),
+                                        z_mode if z is not None else Z_MODEL, float(feas_tol), ptr(g_out), ptr(ind_out),
+                                        ptr(P_out), ctypes.c_void_p(stream.cuda_stream)))
 
     def state_solve(self, d, theta, z=None, z_mode=None):
         """The collocation solution behind g (numpy in / numpy out): ``x`` (n_d, n_t, 1 + ncp * nfe, ns + nq) -- tau = 0

@@ -75,6 +75,7 @@ struct LaunchArgs {
     double* g_out;
     double* ind_out;
     unsigned long long* counters;
+    double gtol[8];            // scenario feasible <=> g_k <= gtol[k] for every k (0: the plain rule g <= 0)
 };
 
 // Program 0 (feasibility): the whole per-scenario program -- parameter tape, element loop, Newton

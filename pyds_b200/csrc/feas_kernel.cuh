@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
             for (int c = 0; c < img.ng; ++c) {
                 double gv = ref_ld(tab_g[c], s);
                 if (failed[s]) gv = __longlong_as_double(0x7ff8000000000000LL);
-                feasible = feasible && (gv <= 0.0);
+                feasible = feasible && (gv <= la.gtol[c]);
                 if constexpr (!TRAJ)
                     if (la.g_out && valid[s]) la.g_out[(i_d * la.n_t + j) * img.ng + c] = gv;
             }

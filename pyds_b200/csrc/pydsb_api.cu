@@ -619,7 +619,8 @@ namespace {
 
 // pydsb_eval, or with `traj` the trajectory variant (g_out = x_out, ind_out = failed_out)
 int eval_impl(void* handle, const double* d, long long n_d, const double* theta, const double* w, long long n_t,
-              const double* z, int z_mode, double* g_out, double* ind_out, double* P_out, bool traj, void* stream)
+              const double* z, int z_mode, double* g_out, double* ind_out, double* P_out, bool traj, void* stream,
+              double feas_tol = 0.0)
 {
     Model* m = static_cast<Model*>(handle);
     if (!m) return fail(PYDSB_ERR_INVALID, "null handle");
@@ -648,6 +649,8 @@ int eval_impl(void* handle, const double* d, long long n_d, const double* theta,
     la.n_d = n_d; la.n_t = n_t; la.n_tiles = n_tiles;
     la.theta_tma_ok = (reinterpret_cast<uintptr_t>(theta) % 16 == 0) ? 1 : 0;
     la.partial = m->d_partial; la.g_out = g_out; la.ind_out = ind_out; la.counters = m->d_counters;
+    if (!(feas_tol >= 0.0)) return fail(PYDSB_ERR_INVALID, "feasibility tolerance must be >= 0");
+    for (int k = 0; k < img.ng; ++k) la.gtol[k] = feas_tol > 0.0 ? feas_tol / img.bigm_inv[k] : 0.0;
 
     const long long max_ctas = (long long)m->num_sms * m->blocks_per_sm;
     const int grid = (int)(total < max_ctas ? total : max_ctas);
@@ -677,6 +680,12 @@ int pydsb_eval(void* handle, const double* d, long long n_d, const double* theta
                const double* z, int z_mode, double* g_out, double* ind_out, double* P_out, void* stream)
 {
     return eval_impl(handle, d, n_d, theta, w, n_t, z, z_mode, g_out, ind_out, P_out, false, stream);
+}
+
+int pydsb_eval_tol(void* handle, const double* d, long long n_d, const double* theta, const double* w, long long n_t,
+                   const double* z, int z_mode, double feas_tol, double* g_out, double* ind_out, double* P_out, void* stream)
+{
+    return eval_impl(handle, d, n_d, theta, w, n_t, z, z_mode, g_out, ind_out, P_out, false, stream, feas_tol);
 }
 
 int pydsb_state_solve(void* handle, const double* d, long long n_d, const double* theta, long long n_t, const double* z,

@@ -93,22 +93,24 @@ class Manager:
         w_arr = np.full(len(p), 1.0 / max(len(p), 1)) if w is None else np.asarray(w, dtype=np.float64)
         if world > 1 and not self.shards_by_design_point:
             # a manager that cannot split its rows: each rank evaluates the whole batch (identical results, no speed-up)
-            ind = self._indicators(d, p, w_arr)
-            return ((1.0 - ind) * w_arr[None, :]).sum(axis=1)
+            return self._efp_rows(d, p, w_arr)
         a, b = shard_rows(len(d), world, rank)
         if world > 1 and self.couples_design_points:
             # one control vector couples every design point (three-stage): the ranks optimise it together -- an
             # all-reduce of the {Phi, grad, H} statistics per iteration -- so every rank calls, rows or not
-            ind = self._indicators(d[a:b], p, w_arr, n_d_total=len(d))
-            P = ((1.0 - ind) * w_arr[None, :]).sum(axis=1)
+            P = self._efp_rows(d[a:b], p, w_arr, n_d_total=len(d))
         elif b > a:
-            ind = self._indicators(d[a:b], p, w_arr)
-            P = ((1.0 - ind) * w_arr[None, :]).sum(axis=1)
+            P = self._efp_rows(d[a:b], p, w_arr)
         else:
             P = np.empty(0)
         if world == 1:
             return P
         return ShardedEfp(None, world, rank).all_gather_host(P, shard_sizes(len(d), world))
+
+    def _efp_rows(self, d, p, w, **kw):
+        """P(feasible) of these rows.  Default: from the indicator matrix; the shipped managers reduce on the device."""
+        ind = self._indicators(d, p, w, **kw)
+        return ((1.0 - ind) * w[None, :]).sum(axis=1)
 
     def _indicators(self, d, p, w):
         raise NotImplementedError
@@ -122,6 +124,9 @@ class TwoStageManager(Manager):
 
     def _indicators(self, d, p, w):
         return self.solver.solve(d, p, w, mode="shared")
+
+    def _efp_rows(self, d, p, w):
+        return self.solver.efp(d, p, w, mode="shared")
 
     def g(self, d, p):
         d, p = self._check(d, p)
@@ -158,6 +163,9 @@ class ThreeStageManager(Manager):
 
     def _indicators(self, d, p, w, n_d_total=None):
         return self.solver.solve(d, p, w, mode="global", n_d_total=n_d_total)
+
+    def _efp_rows(self, d, p, w, n_d_total=None):
+        return self.solver.efp(d, p, w, mode="global", n_d_total=n_d_total)
 
     def g(self, d, p):
         d, p = self._check(d, p)

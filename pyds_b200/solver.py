@@ -102,6 +102,60 @@ class Solver:
             self.output["relaxation"] = self._collect_output()
         return indicator
 
+    def efp(self, d, p, w, mode="shared", n_d_total=None, group=None):
+        """P(feasible) per design point with everything on the device: control optimisation, one feasibility pass at
+        the optimised controls with the same classification rule as ``solve`` (``g_k / M_k <= feasibility tolerance``),
+        weighted reduction; only the n_d probabilities come back.  ``solve`` + a host-side sum gives the same numbers
+        (tested) but copies g for every scenario to the host -- 1.6 GB at 1e4 x 1e4."""
+        import torch
+        from . import capi
+        sim = self.parent.simulator
+        eng = sim.engine
+        dev = torch.device("cuda", eng.device)
+        d = np.asarray(d, dtype=np.float64)
+        d = d.reshape(-1, sim.lowered.d_dim) if d.size == 0 else np.atleast_2d(d)
+        p = np.atleast_2d(np.asarray(p, dtype=np.float64))
+        n_d, n_p = d.shape[0], p.shape[0]
+        if n_d_total is not None and mode != "global":
+            raise ValueError("only the global-control mode couples the ranks")
+        up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        td, tp, tw = up(d), up(p), up(w)
+        n_free = int((~sim.lowered.z_fixed).sum()) if sim.lowered.nz else 0
+        tz, z_mode, tol = None, capi.Z_MODEL, 0.0
+        self.result = {"status": None, "iters": None, "phi": None}
+        if self.use_relaxation and self.optimise_controls and n_free > 0:
+            tz0 = up(sim.default_controls()[None, :])
+            if n_d_total is not None:
+                opts = {k: v for k, v in self.lm_options.items() if k != "check_every"}
+                r = eng.recourse_solve_global_dist(td, int(n_d_total), tp, tw, tz0, group=group, **opts)
+            elif n_d == 0:
+                r = None
+            else:
+                r = eng.recourse_solve_device(td, tp, tw, tz0, per_scenario=(mode == "per_scenario"),
+                                              global_group=(mode == "global"), **self.lm_options)
+            if r is not None:
+                tz = r["z"].contiguous()
+                z_mode = {"shared": capi.Z_PER_DESIGN, "global": capi.Z_SHARED, "per_scenario": capi.Z_PER_SCENARIO}[mode]
+                self.result = {k: r[k].cpu().numpy() for k in ("status", "iters", "phi")}
+                self.controls = tz.cpu().numpy().reshape((-1,) if mode == "global" else (n_d, n_p, -1) if mode == "per_scenario" else (n_d, -1))
+                tol = self.feas_tol
+        elif n_free > 0:
+            tz = up(sim.default_controls())
+            z_mode = capi.Z_SHARED
+            self.controls = sim.default_controls()
+        if n_d == 0:
+            return np.empty(0)
+        P = torch.empty(n_d, dtype=torch.float64, device=dev)
+        before = eng.counters()["failed"]
+        eng.eval_device(td, tp, tw, z=tz, z_mode=z_mode, P_out=P, feas_tol=tol)
+        out = P.cpu().numpy()
+        failed = eng.counters()["failed"] - before
+        if failed:
+            self.no_infeasible += int(failed)
+            if self.warn_infeasible:
+                print("Warning: Infeasible relaxation. Total number of infeasible solves: {}".format(self.no_infeasible))
+        return out
+
     def _solve_global_sharded(self, eng, d_local, n_d_total, p, w, z0, group):
         import torch
         dev = torch.device("cuda", eng.device)

@@ -95,6 +95,10 @@ def test_threestage_manager_global_control(tmp_path):
         np.testing.assert_array_equal(-g_list[i][:, 0], flat[20 * i:20 * (i + 1)])
     recs = read_output_file(str(tmp_path / "pyds_output.pkl"))
     assert len(recs) == 1                                            # one record per call (reference run.py:97)
+    # the device-side reduction (control optimisation + classification with the big-M tolerance + weighted sum on the
+    # GPU) gives what DEUS computes from the returned list
+    np.testing.assert_allclose(m.efp(d, p, w), ns.efp_from_g(g_list, w), atol=1e-15)
+    assert m.solver.controls.shape == (8,)
 
 
 def test_nested_sampling_on_the_twostage_problem(tmp_path):
