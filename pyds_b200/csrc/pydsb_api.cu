@@ -796,7 +796,9 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
 
     const int n_tiles = (int)((n_t + BLOCK - 1) / BLOCK);
     const int NV = recourse_nv(nz);
-    const long long acc_per_group_ll = per_scenario == 1 ? 1 : (per_scenario == 2 ? (n_d > 0 ? n_d : 1) * (long long)n_tiles : n_tiles);
+    // tiles of the one global group run over the flattened (d, theta) index
+    const long long global_tiles = (n_d * n_t + BLOCK - 1) / BLOCK;
+    const long long acc_per_group_ll = per_scenario == 1 ? 1 : (per_scenario == 2 ? (global_tiles > 0 ? global_tiles : 1) : n_tiles);
     if (acc_per_group_ll > 0x7fffffffLL) return fail(PYDSB_ERR_INVALID, "grid too large");
     const int acc_per_group = (int)acc_per_group_ll;
     // workspace: doubles then ints
@@ -877,7 +879,7 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
     la.zfix = m->d_zfix; la.z_cur = z_cur; la.z_try = z_try; la.F_cur = F_cur; la.raw_cur = raw_cur; la.gr = gr; la.H = Hh;
     la.lam = lam; la.mu = mu; la.status = status; la.first = first; la.iters = iters;
     la.mu_min = o[1]; la.lam0 = o[2]; la.step_tol = o[3]; la.max_iter = max_iter;
-    const long long total_tiles = n_d * (long long)n_tiles;
+    const long long total_tiles = per_scenario == 2 ? global_tiles : n_d * (long long)n_tiles;
     // small grids are bound by the latency of one launch, not by throughput: look at the running count every iteration
     if (!(opts && opts[5] > 0) && total_tiles <= 4096) check_every = 1;
     if (reduce) check_every = 1;                 // every process must take the same decisions at the same iterations

@@ -171,6 +171,18 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
         grp = ra.active ? ra.active[k] : k;
         i_d = grp / ra.n_t;
         j = grp % ra.n_t;
+    } else if (ra.per_scenario == 2) {
+        // one group over the whole grid: tiles run over the flattened (design point, theta) index, so a small theta
+        // set (50 in the shipped scripts) does not leave most lanes of a tile idle
+        const long long k0 = t * (long long)BLOCK;
+        const long long rem = ra.n_d * ra.n_t - k0;
+        const int rows = rem < BLOCK ? (int)rem : BLOCK;
+        valid = tid < rows;
+        const long long k = k0 + (valid ? tid : rows - 1);
+        i_d = k / ra.n_t;
+        j = k % ra.n_t;
+        grp = 0;
+        if (ra.status[0] != 0) return;
     } else {
         i_d = t / ra.n_tiles;
         const long long j0 = (t % ra.n_tiles) * (long long)BLOCK;
@@ -178,7 +190,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
         const int rows = rem < BLOCK ? (int)rem : BLOCK;
         valid = tid < rows;
         j = j0 + (valid ? tid : rows - 1);
-        grp = ra.per_scenario == 2 ? 0 : i_d;
+        grp = i_d;
         if (ra.status[grp] != 0) return;                         // block-uniform: group already finished
     }
     const bool active = valid && ra.status[grp] == 0;

@@ -53,10 +53,12 @@ z_dist = np.asarray(m.solver.controls).copy()
 it_dist = int(m.solver.result["iters"][0])
 phi_dist = float(m.solver.result["phi"][0])
 
+m.solver.efp(d[:4], p, w, mode="global")
+torch.cuda.synchronize()
 t0 = time.time()
-ind = m.solver.solve(d, p, w, mode="global")            # the whole batch on this GPU alone
+P_single = m.solver.efp(d, p, w, mode="global")         # the whole batch on this GPU alone, same device-side path
+torch.cuda.synchronize()
 t_single = time.time() - t0
-P_single = ((1.0 - ind) * w[None, :]).sum(axis=1)
 z_single = np.asarray(m.solver.controls).copy()
 phi_single = float(m.solver.result["phi"][0])
 
