@@ -912,7 +912,8 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
         }
         la.active_in = act_in; la.n_active_in = n_in; la.n_running = n_out;
         la.active_out = compact ? act + (size_t)(it & 1) * G : nullptr;
-        lm_update_kernel<<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
+        if (nz <= 8) lm_update_kernel<8><<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
+        else lm_update_kernel<0><<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
         CUDA_TRY_WS(cudaGetLastError());
         m->launches += 2;
         if (compact) { act_in = la.active_out; n_in = n_out; }

@@ -492,9 +492,13 @@ struct LmArgs {
 };
 
 __device__ bool lm_update_group(const LmArgs& a, long long g);
+template <int NZC>
+__device__ bool lm_update_group_regs(const LmArgs& a, long long g);
 
-// One thread per (running) group.
-__global__ void lm_update_kernel(const LmArgs a)
+// One thread per (running) group.  NZC > 0: the register-resident update for nz <= NZC controls (lm_update_group_regs);
+// NZC = 0: the generic one (local-memory arrays, any nz <= MAX_NZ).
+template <int NZC>
+__global__ void __launch_bounds__(128) lm_update_kernel(const LmArgs a)
 {
     const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long n_in = a.n_active_in ? (long long)*a.n_active_in : a.n_groups;
@@ -502,7 +506,10 @@ __global__ void lm_update_kernel(const LmArgs a)
     long long g = 0;
     if (k < n_in) {
         g = a.active_in ? a.active_in[k] : k;
-        if (a.status[g] == 0) done = lm_update_group(a, g);
+        if (a.status[g] == 0) {
+            if constexpr (NZC > 0) done = lm_update_group_regs<NZC>(a, g);
+            else done = lm_update_group(a, g);
+        }
     }
     // running groups: count them, and (per-scenario mode) append them to the next active list
     const unsigned run_mask = __ballot_sync(0xffffffffu, !done);
@@ -740,6 +747,295 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
     }
     break;
     }
+    return done;
+}
+
+// lm_update_group with the group's whole state in registers (nz <= NZC): every per-group value is loaded up front
+// (independent loads in flight together instead of a chain of dependent global accesses ordered by possible aliasing),
+// all arrays are statically indexed (the free set is a bit mask, the damped system is the full nz x nz matrix with
+// identity rows for the controls that are not free -- the same factors and the same step as the compacted system),
+// and the state is written back once at the end.  Same decisions and, up to FMA contraction, the same numbers.
+template <int NZC>
+__device__ bool lm_update_group_regs(const LmArgs& a, long long g)
+{
+    const int nz = a.nz, ng = a.ng;
+    const double* __restrict__ acc = a.acc;
+    double zc[NZC], zt[NZC], gr[NZC], lo[NZC], hi[NZC];
+    bool fixd[NZC];
+#pragma unroll
+    for (int c = 0; c < NZC; ++c) {
+        const bool in = c < nz;
+        zc[c] = in ? a.z_cur[g * nz + c] : 0.0;
+        zt[c] = in ? a.z_try[g * nz + c] : 0.0;
+        gr[c] = in ? a.gr[g * nz + c] : 0.0;
+        lo[c] = in ? a.lo[c] : 0.0;
+        hi[c] = in ? a.hi[c] : 0.0;
+        fixd[c] = in ? a.zfix[c] != 0 : true;
+    }
+    const int iters = a.iters[g] + 1;
+    int first = a.first[g], status = 0;
+    double F_cur = a.F_cur[g], raw_cur = a.raw_cur[g], lam = a.lam[g], mu = a.mu[g];
+    double* const H = a.H + g * nz * nz;
+    // per-scenario mode: the scenario's own record
+    const double* const rec = acc + g * recourse_nvp(ng, nz);
+    bool rec_failed = false;
+    double ck[8], cmax = 0.0;
+    if (a.per_scenario) {
+        rec_failed = rec[0] != 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            ck[k] = k < ng ? rec[1 + k] : 0.0;
+            if (k < ng) cmax = fmax(cmax, ck[k]);
+        }
+    }
+    const double* const Dc = rec + 1 + ng;
+    const int NV = recourse_nv(nz);
+
+    bool done = false;
+    const int stages_in_hand = a.per_scenario ? (1 << 30) : a.n_stages;
+    for (int stage = 0;; ++stage) {
+        // ---- statistics of this stage: {Phi_mu, Phi, grad} ----
+        double F_t = 0.0, raw_t = 0.0, g_t[NZC], pk[8];
+#pragma unroll
+        for (int c = 0; c < NZC; ++c) g_t[c] = 0.0;
+        const double mu_stage = mu;
+        if (a.per_scenario) {
+            if (rec_failed) {
+                F_t = raw_t = 1.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pk[k] = 0.0;
+            } else {
+                double Z = exp(-cmax / mu_stage);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    pk[k] = k < ng ? exp((ck[k] - cmax) / mu_stage) : 0.0;
+                    if (k < ng) Z += pk[k];
+                }
+                const double zi = 1.0 / Z;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pk[k] *= zi;
+                F_t = cmax + mu_stage * log(Z);
+                raw_t = cmax;
+            }
+#pragma unroll
+            for (int c = 0; c < NZC; ++c)
+                if (c < nz) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < ng) g_t[c] = fma(pk[k], Dc[k * nz + c], g_t[c]);
+                }
+        } else {
+            for (int t = 0; t < a.n_tiles; ++t) {
+                const double* p = acc + ((g * a.n_tiles + t) * a.n_stages + stage) * NV;
+                F_t += p[0];
+                raw_t += p[1];
+#pragma unroll
+                for (int c = 0; c < NZC; ++c)
+                    if (c < nz) g_t[c] += p[2 + c];
+            }
+        }
+        bool converged_here = false, at_eval_point = false, pinned = false;
+        if (raw_t == 0.0) {                       // every scenario of the group is feasible: Phi = 0 exactly
+#pragma unroll
+            for (int c = 0; c < NZC; ++c) zc[c] = zt[c];
+            raw_cur = 0.0;
+            status = 1;
+            done = true;
+        }
+        if (!done) {
+            if (first || F_t < F_cur) {
+                double moved = 0.0;
+#pragma unroll
+                for (int c = 0; c < NZC; ++c)
+                    if (c < nz) {
+                        const double span = (hi[c] - lo[c] <= DBL_MAX) ? (hi[c] - lo[c]) : 1.0;
+                        moved = fmax(moved, fabs(zt[c] - zc[c]) / span);
+                    }
+                const bool small = !first && (moved <= a.step_tol || F_cur - F_t <= 1e-13 * fmax(F_t, 1e-300));
+#pragma unroll
+                for (int c = 0; c < NZC; ++c) { zc[c] = zt[c]; gr[c] = g_t[c]; }
+                F_cur = F_t;
+                raw_cur = raw_t;
+                if (!first) lam = fmax(lam / 3.0, 1e-12);
+                first = 0;
+                converged_here = small;
+                at_eval_point = true;
+            } else {
+                lam = lam * 4.0;
+                if (lam >= 1e12) converged_here = true;
+            }
+            if (!converged_here) {
+                // projected LM step on the free set
+                unsigned fm = 0;
+#pragma unroll
+                for (int c = 0; c < NZC; ++c) {
+                    const bool at_lo = zc[c] <= lo[c] && gr[c] > 0.0;
+                    const bool at_hi = zc[c] >= hi[c] && gr[c] < 0.0;
+                    if (!fixd[c] && !at_lo && !at_hi) fm |= 1u << c;
+                }
+                double step[NZC];
+#pragma unroll
+                for (int c = 0; c < NZC; ++c) step[c] = 0.0;
+                if (fm) {
+                    if (at_eval_point) {                   // z_cur was just accepted: its H is not in global memory yet
+                        if (a.per_scenario) {
+#pragma unroll
+                            for (int r = 0; r < NZC; ++r)
+#pragma unroll
+                                for (int c = r; c < NZC; ++c)
+                                    if (c < nz) {
+                                        double hv = 0.0;
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k)
+                                            if (k < ng) hv = fma(pk[k] * Dc[k * nz + r], Dc[k * nz + c], hv);
+                                        const double v = fma(-g_t[r], g_t[c], hv) / mu_stage;
+                                        H[r * nz + c] = v;
+                                        H[c * nz + r] = v;
+                                    }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < NZC; ++r)
+#pragma unroll
+                                for (int c = r; c < NZC; ++c)
+                                    if (c < nz) {
+                                        const int idx = 2 + nz + r * nz - (r * (r - 1)) / 2 + (c - r);   // packed upper triangle
+                                        double s = 0.0;
+                                        for (int t = 0; t < a.n_tiles; ++t)
+                                            s += acc[((g * a.n_tiles + t) * a.n_stages + stage) * NV + idx];
+                                        H[r * nz + c] = s;
+                                        H[c * nz + r] = s;
+                                    }
+                        }
+                    }
+                    // see lm_update_group for the "no curvature" rule on the diagonal
+                    double hd[NZC], dmax = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NZC; ++c) {
+                        hd[c] = 0.0;
+                        if ((fm >> c) & 1u) {
+                            const double hii = H[c * nz + c];
+                            hd[c] = hii > 1e-10 * gr[c] * gr[c] / mu ? hii : 0.0;
+                            dmax = fmax(dmax, hd[c]);
+                        }
+                    }
+                    const double floor_ = 1e-8 * dmax + 1e-300;
+                    double l = lam;
+                    for (int attempt = 0; attempt < 12; ++attempt) {
+                        double A[NZC][NZC];                // lower triangle used
+#pragma unroll
+                        for (int i = 0; i < NZC; ++i)
+#pragma unroll
+                            for (int jx = 0; jx <= i; ++jx) {
+                                const bool fi = (fm >> i) & 1u, fj = (fm >> jx) & 1u;
+                                double v = 0.0;
+                                if (i == jx) v = fi ? hd[i] + l * (hd[i] + floor_) + 1e-30 : 1.0;
+                                else if (fi && fj && hd[i] > 0.0 && hd[jx] > 0.0) v = H[i * nz + jx];
+                                A[i][jx] = v;
+                            }
+                        bool okc = true;                   // in-place Cholesky A = L L^T
+#pragma unroll
+                        for (int i = 0; i < NZC; ++i)
+#pragma unroll
+                            for (int jx = 0; jx <= i; ++jx) {
+                                double sum = A[i][jx];
+#pragma unroll
+                                for (int k = 0; k < jx; ++k) sum -= A[i][k] * A[jx][k];
+                                if (i == jx) {
+                                    if (!(sum > 0.0)) okc = false;
+                                    A[i][i] = sqrt(sum);
+                                } else {
+                                    A[i][jx] = sum / A[jx][jx];
+                                }
+                            }
+                        if (!okc) { l *= 10.0; continue; }
+                        double y[NZC];
+#pragma unroll
+                        for (int i = 0; i < NZC; ++i) {
+                            double sum = ((fm >> i) & 1u) ? -gr[i] : 0.0;
+#pragma unroll
+                            for (int k = 0; k < i; ++k) sum -= A[i][k] * y[k];
+                            y[i] = sum / A[i][i];
+                        }
+#pragma unroll
+                        for (int i = NZC - 1; i >= 0; --i) {
+                            double sum = y[i];
+#pragma unroll
+                            for (int k = i + 1; k < NZC; ++k) sum -= A[k][i] * y[k];
+                            y[i] = sum / A[i][i];
+                        }
+#pragma unroll
+                        for (int c = 0; c < NZC; ++c) step[c] = ((fm >> c) & 1u) ? y[c] : 0.0;
+                        break;
+                    }
+                }
+                bool same = true;
+#pragma unroll
+                for (int c = 0; c < NZC; ++c) {
+                    const double zn = fmin(fmax(zc[c] + step[c], lo[c]), hi[c]);
+                    if (zn != zc[c]) same = false;
+                    step[c] = zn;
+                }
+                if (same) { converged_here = true; pinned = fm == 0; }
+                else {
+#pragma unroll
+                    for (int c = 0; c < NZC; ++c) zt[c] = step[c];
+                }
+            }
+            if (converged_here) {
+                bool saturated = false;
+                if (a.per_scenario && pinned && at_eval_point && !rec_failed && mu > a.mu_min * 1.0001) {
+                    // lm_softmax_saturated on the values in hand
+                    int kmax = -1;
+                    double cm = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < ng && ck[k] > cm) { cm = ck[k]; kmax = k; }
+                    if (kmax >= 0) {
+                        double rest = exp(-cm / mu);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (k < ng && k != kmax) rest += exp((ck[k] - cm) / mu);
+                        saturated = rest < 1e-30;
+                    }
+                }
+                if (mu <= a.mu_min * 1.0001) {
+                    status = 2;
+                    done = true;
+                } else if (saturated) {
+                    mu = a.mu_min;
+                    status = 2;
+                    done = true;
+                } else {
+                    mu = fmax(mu / 10.0, a.mu_min);
+                    first = 1;
+                    lam = a.lam0;
+#pragma unroll
+                    for (int c = 0; c < NZC; ++c) zt[c] = zc[c];
+                    if (at_eval_point && stage + 1 < stages_in_hand) continue;
+                }
+            }
+            if (!done && iters >= a.max_iter) {
+                status = 3;
+                done = true;
+            }
+        }
+        break;
+    }
+    // ---- write the group's state back ----
+#pragma unroll
+    for (int c = 0; c < NZC; ++c)
+        if (c < nz) {
+            a.z_cur[g * nz + c] = zc[c];
+            a.z_try[g * nz + c] = zt[c];
+            a.gr[g * nz + c] = gr[c];
+        }
+    a.iters[g] = iters;
+    a.first[g] = first;
+    a.status[g] = status;
+    a.F_cur[g] = F_cur;
+    a.raw_cur[g] = raw_cur;
+    a.lam[g] = lam;
+    a.mu[g] = mu;
     return done;
 }
 
