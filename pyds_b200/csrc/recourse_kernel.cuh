@@ -498,7 +498,7 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g);
 // One thread per (running) group.  NZC > 0: the register-resident update for nz <= NZC controls (lm_update_group_regs);
 // NZC = 0: the generic one (local-memory arrays, any nz <= MAX_NZ).
 template <int NZC>
-__global__ void __launch_bounds__(128) lm_update_kernel(const LmArgs a)
+__global__ void __launch_bounds__(128, NZC > 0 ? 3 : 1) lm_update_kernel(const LmArgs a)
 {
     const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long n_in = a.n_active_in ? (long long)*a.n_active_in : a.n_groups;
@@ -760,7 +760,10 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
 {
     const int nz = a.nz, ng = a.ng;
     const double* __restrict__ acc = a.acc;
-    double zc[NZC], zt[NZC], gr[NZC], lo[NZC], hi[NZC];
+    double zc[NZC], zt[NZC], gr[NZC];
+    // bounds: uniform across the threads, read where they are used (L1-resident) instead of held in 32 registers
+    auto lo = [&](int c) { return c < nz ? __ldg(a.lo + c) : 0.0; };
+    auto hi = [&](int c) { return c < nz ? __ldg(a.hi + c) : 0.0; };
     bool fixd[NZC];
 #pragma unroll
     for (int c = 0; c < NZC; ++c) {
@@ -768,8 +771,6 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
         zc[c] = in ? a.z_cur[g * nz + c] : 0.0;
         zt[c] = in ? a.z_try[g * nz + c] : 0.0;
         gr[c] = in ? a.gr[g * nz + c] : 0.0;
-        lo[c] = in ? a.lo[c] : 0.0;
-        hi[c] = in ? a.hi[c] : 0.0;
         fixd[c] = in ? a.zfix[c] != 0 : true;
     }
     const int iters = a.iters[g] + 1;
@@ -848,7 +849,7 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
 #pragma unroll
                 for (int c = 0; c < NZC; ++c)
                     if (c < nz) {
-                        const double span = (hi[c] - lo[c] <= DBL_MAX) ? (hi[c] - lo[c]) : 1.0;
+                        const double span = (hi(c) - lo(c) <= DBL_MAX) ? (hi(c) - lo(c)) : 1.0;
                         moved = fmax(moved, fabs(zt[c] - zc[c]) / span);
                     }
                 const bool small = !first && (moved <= a.step_tol || F_cur - F_t <= 1e-13 * fmax(F_t, 1e-300));
@@ -869,8 +870,8 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
                 unsigned fm = 0;
 #pragma unroll
                 for (int c = 0; c < NZC; ++c) {
-                    const bool at_lo = zc[c] <= lo[c] && gr[c] > 0.0;
-                    const bool at_hi = zc[c] >= hi[c] && gr[c] < 0.0;
+                    const bool at_lo = zc[c] <= lo(c) && gr[c] > 0.0;
+                    const bool at_hi = zc[c] >= hi(c) && gr[c] < 0.0;
                     if (!fixd[c] && !at_lo && !at_hi) fm |= 1u << c;
                 }
                 double step[NZC];
@@ -879,30 +880,28 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
                 if (fm) {
                     if (at_eval_point) {                   // z_cur was just accepted: its H is not in global memory yet
                         if (a.per_scenario) {
+                            const double inv_mu = 1.0 / mu_stage;
 #pragma unroll
                             for (int r = 0; r < NZC; ++r)
 #pragma unroll
                                 for (int c = r; c < NZC; ++c)
-                                    if (c < nz) {
-                                        double hv = 0.0;
+                                    if (((fm >> r) & (fm >> c)) & 1u) {    // only free x free entries are ever read,
+                                        double hv = 0.0;                   // and only from the lower triangle
 #pragma unroll
                                         for (int k = 0; k < 8; ++k)
                                             if (k < ng) hv = fma(pk[k] * Dc[k * nz + r], Dc[k * nz + c], hv);
-                                        const double v = fma(-g_t[r], g_t[c], hv) / mu_stage;
-                                        H[r * nz + c] = v;
-                                        H[c * nz + r] = v;
+                                        H[c * nz + r] = fma(-g_t[r], g_t[c], hv) * inv_mu;
                                     }
                         } else {
 #pragma unroll
                             for (int r = 0; r < NZC; ++r)
 #pragma unroll
                                 for (int c = r; c < NZC; ++c)
-                                    if (c < nz) {
+                                    if (((fm >> r) & (fm >> c)) & 1u) {
                                         const int idx = 2 + nz + r * nz - (r * (r - 1)) / 2 + (c - r);   // packed upper triangle
                                         double s = 0.0;
                                         for (int t = 0; t < a.n_tiles; ++t)
                                             s += acc[((g * a.n_tiles + t) * a.n_stages + stage) * NV + idx];
-                                        H[r * nz + c] = s;
                                         H[c * nz + r] = s;
                                     }
                         }
@@ -932,7 +931,9 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
                                 else if (fi && fj && hd[i] > 0.0 && hd[jx] > 0.0) v = H[i * nz + jx];
                                 A[i][jx] = v;
                             }
-                        bool okc = true;                   // in-place Cholesky A = L L^T
+                        // in-place Cholesky A = L L^T; the diagonal holds 1 / L_ii (one rsqrt per row instead of a
+                        // square root and a division per entry)
+                        bool okc = true;
 #pragma unroll
                         for (int i = 0; i < NZC; ++i)
 #pragma unroll
@@ -942,9 +943,9 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
                                 for (int k = 0; k < jx; ++k) sum -= A[i][k] * A[jx][k];
                                 if (i == jx) {
                                     if (!(sum > 0.0)) okc = false;
-                                    A[i][i] = sqrt(sum);
+                                    A[i][i] = rsqrt(sum);
                                 } else {
-                                    A[i][jx] = sum / A[jx][jx];
+                                    A[i][jx] = sum * A[jx][jx];
                                 }
                             }
                         if (!okc) { l *= 10.0; continue; }
@@ -954,14 +955,14 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
                             double sum = ((fm >> i) & 1u) ? -gr[i] : 0.0;
 #pragma unroll
                             for (int k = 0; k < i; ++k) sum -= A[i][k] * y[k];
-                            y[i] = sum / A[i][i];
+                            y[i] = sum * A[i][i];
                         }
 #pragma unroll
                         for (int i = NZC - 1; i >= 0; --i) {
                             double sum = y[i];
 #pragma unroll
                             for (int k = i + 1; k < NZC; ++k) sum -= A[k][i] * y[k];
-                            y[i] = sum / A[i][i];
+                            y[i] = sum * A[i][i];
                         }
 #pragma unroll
                         for (int c = 0; c < NZC; ++c) step[c] = ((fm >> c) & 1u) ? y[c] : 0.0;
@@ -971,7 +972,7 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
                 bool same = true;
 #pragma unroll
                 for (int c = 0; c < NZC; ++c) {
-                    const double zn = fmin(fmax(zc[c] + step[c], lo[c]), hi[c]);
+                    const double zn = fmin(fmax(zc[c] + step[c], lo(c)), hi(c));
                     if (zn != zc[c]) same = false;
                     step[c] = zn;
                 }
