@@ -82,6 +82,13 @@ int pydsb_model_destroy(void* handle);
 int pydsb_assemble(const void* blob, size_t nbytes, uint32_t* words, size_t cap, size_t* n_words, long long* info,
                    int n_info);
 int pydsb_model_info(void* handle, long long* out, int n);
+/* Host-only: the replace-the-worst pass of one nested-sampling iteration (the live-point bookkeeping DEUS does around
+ * the constraint function, reference run_twostage.py:167-180 `points_schedule` / nlive / nreplacements [3P]).  For each
+ * candidate in order: if its probability cand_p[c] is above the worst live value -- or equal to it and at least `target`
+ * -- it takes the slot of the worst live point (lowest slot among equal minima): live_p is updated in place and
+ * slot_out[c] = that slot, else slot_out[c] = -1.  A candidate accepted early can be evicted by a later one. */
+int pydsb_ns_replace_worst(double* live_p, long long n_live, const double* cand_p, long long n_cand, double target,
+                           long long* slot_out);
 
 /* The whole hot path in one launch sequence: state solve (collocation Newton), CQAs g, big-M
  * indicator and the weighted P(feasible) reduction over theta.

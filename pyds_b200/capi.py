@@ -22,7 +22,8 @@ COUNTER_NAMES = ["scenarios", "newton_iters", "newton_warp_iters", "failed", "la
 
 EXPORTS = ["pydsb_last_error", "pydsb_version", "pydsb_model_create", "pydsb_model_destroy", "pydsb_model_info",
            "pydsb_eval", "pydsb_eval_tol", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_state_solve", "pydsb_recourse_solve",
-           "pydsb_recourse_solve_global_dist", "pydsb_get_counters", "pydsb_dfma_peak", "pydsb_assemble"]
+           "pydsb_recourse_solve_global_dist", "pydsb_get_counters", "pydsb_dfma_peak", "pydsb_assemble",
+           "pydsb_ns_replace_worst"]
 # int (*pydsb_allreduce_fn)(double* device_buf, int n, void* user)
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
 
@@ -55,6 +56,8 @@ def load():
     L.pydsb_assemble.restype = ci
     L.pydsb_assemble.argtypes = [ctypes.c_char_p, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
                                  ctypes.POINTER(ll), ci]
+    L.pydsb_ns_replace_worst.restype = ci
+    L.pydsb_ns_replace_worst.argtypes = [vp, ll, vp, ll, ctypes.c_double, vp]
     L.pydsb_model_destroy.restype = ci
     L.pydsb_model_destroy.argtypes = [vp]
     L.pydsb_model_info.restype = ci
@@ -312,6 +315,18 @@ class Engine:
         buf = (ctypes.c_ulonglong * len(COUNTER_NAMES))()
         _check(self._lib.pydsb_get_counters(self._h, buf, len(COUNTER_NAMES), 1 if reset else 0))
         return {k: int(v) for k, v in zip(COUNTER_NAMES, buf)}
+
+
+def ns_replace_worst(live_p, cand_p, target):
+    """The live-set update of one nested-sampling iteration in native code (host only, no device needed): ``live_p`` (a
+    contiguous float64 array) is updated in place; returns the slot each candidate took, or -1."""
+    if not (isinstance(live_p, np.ndarray) and live_p.dtype == np.float64 and live_p.flags.c_contiguous):
+        raise ValueError("live_p must be a contiguous float64 array (it is updated in place)")
+    cand_p = np.ascontiguousarray(cand_p, dtype=np.float64)
+    slots = np.empty(len(cand_p), dtype=np.int64)
+    _check(load().pydsb_ns_replace_worst(live_p.ctypes.data, len(live_p), cand_p.ctypes.data, len(cand_p), float(target),
+                                         slots.ctypes.data))
+    return slots
 
 
 # opcode numbering of the assembled program (csrc/feas_kernel.cuh, enum XCode)

@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <string>
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "../../include/pydsb.h"
@@ -561,6 +563,37 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
     m->blocks_per_sm = bps > 0 ? bps : 1;
     m->regs = fa.numRegs;
     *handle = m;
+    return PYDSB_OK;
+}
+
+// Host-only: the live-set update of one nested-sampling iteration (pyds_b200/ns.py), candidate by candidate.
+int pydsb_ns_replace_worst(double* live_p, long long n_live, const double* cand_p, long long n_cand, double target,
+                           long long* slot_out)
+{
+    if (n_live < 0 || n_cand < 0 || (n_live > 0 && !live_p) || (n_cand > 0 && (!cand_p || !slot_out)))
+        return fail(PYDSB_ERR_INVALID, "bad live set / candidate arrays");
+    if (n_live == 0) {
+        for (long long c = 0; c < n_cand; ++c) slot_out[c] = -1;
+        return PYDSB_OK;
+    }
+    // min-heap of (P, slot): the worst live point, the lowest slot among equal minima (what np.argmin would pick)
+    typedef std::pair<double, long long> Entry;
+    std::vector<Entry> heap((size_t)n_live);
+    for (long long k = 0; k < n_live; ++k) heap[(size_t)k] = Entry(live_p[k], k);
+    auto worse_last = [](const Entry& a, const Entry& b) { return a > b; };
+    std::make_heap(heap.begin(), heap.end(), worse_last);
+    for (long long c = 0; c < n_cand; ++c) {
+        const double cp = cand_p[c];
+        const Entry top = heap.front();
+        slot_out[c] = -1;
+        if (cp > top.first || (cp == top.first && cp >= target)) {
+            std::pop_heap(heap.begin(), heap.end(), worse_last);
+            heap.back() = Entry(cp, top.second);
+            std::push_heap(heap.begin(), heap.end(), worse_last);
+            live_p[top.second] = cp;
+            slot_out[c] = top.second;
+        }
+    }
     return PYDSB_OK;
 }
 

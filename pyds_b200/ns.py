@@ -55,6 +55,7 @@ class DEUS:
         for c in alg.get("stop_criteria", []):
             self.max_iterations = int(c.get("max_iterations", self.max_iterations))
         self.use_fast_path = bool(st["efp_evaluation"].get("use_fused_efp", True))
+        self.native_update = True                 # live-set update in libpyds_b200 (False: the Python loop)
         self.result = None
 
     # ----------------------------------------------------------------------------------------------
@@ -75,15 +76,46 @@ class DEUS:
         y = (u - mu) @ np.linalg.inv(L).T                 # dim x dim inverse + one matmul (LAPACK gesv on 1e4+ right-hand
         r = np.sqrt((y * y).sum(axis=1)).max() * (1.0 + enlarge)          # sides costs milliseconds); smallest scaled
                                                                           # ellipsoid holding all points
-        out = []
-        while len(out) < n:
+        chunks, have = [], 0
+        while have < n:
             z = rng.normal(size=(4 * n, dim))
             z /= np.linalg.norm(z, axis=1)[:, None]
             z *= rng.uniform(size=(4 * n, 1)) ** (1.0 / dim) * r
             cand = mu + z @ L.T
             ok = np.all((cand >= 0.0) & (cand <= 1.0), axis=1)
-            out.extend(cand[ok])
-        return self.lo + np.array(out[:n]) * span
+            chunks.append(cand[ok])                       # arrays, not rows: 1e4 proposals per iteration at config C5
+            have += len(chunks[-1])
+        return self.lo + np.concatenate(chunks)[:n] * span
+
+    def _replace_worst_py(self, live, live_p, cand, cand_p, n_live, heap=None):
+        """The update rule in plain Python (growth phase; also the cross-check of the native pass in the tests)."""
+        if heap is None:
+            heap = [(float(v), k) for k, v in enumerate(live_p)]
+            heapq.heapify(heap)
+        grown = []
+        order = range(len(cand))
+        if len(live_p) >= n_live:
+            # the worst live value only rises during the pass: a proposal below the worst at the start of the pass
+            # can never be accepted -- drop those with one vectorised comparison, keep the order of the rest
+            order = np.flatnonzero(cand_p >= heap[0][0])
+        for ci in order:
+            c, cp = cand[ci], float(cand_p[ci])
+            if len(live_p) + len(grown) < n_live:
+                if cp >= heap[0][0]:
+                    grown.append((c, cp))
+                    heapq.heappush(heap, (cp, len(live_p) + len(grown) - 1))
+                continue
+            pk, k = heap[0]
+            if cp > pk or (cp == pk and cp >= self.target):
+                heapq.heapreplace(heap, (cp, k))
+                if k < len(live_p):
+                    live[k], live_p[k] = c, cp
+                else:
+                    grown[k - len(live_p)] = (c, cp)
+        if grown:
+            live = np.vstack([live] + [g[0][None, :] for g in grown])
+            live_p = np.append(live_p, [g[1] for g in grown])
+        return live, live_p, heap
 
     def solve(self):
         rng = np.random.default_rng(self.seed)
@@ -110,35 +142,20 @@ class DEUS:
             cand_p = self.efp(cand)
             n_evals += len(cand)
             history.append((cand.copy(), cand_p.copy()))
-            # replace-the-worst, candidate by candidate; a heap of (P, slot) reproduces np.argmin's choice (lowest
-            # slot among equal minima) in O(log n_live) per candidate instead of a scan -- 1e4 proposals against 1e5
-            # live points (config C5) would spend 0.5 s per iteration in argmin
-            if heap is None:
-                heap = [(float(v), k) for k, v in enumerate(live_p)]
-                heapq.heapify(heap)
-            grown = []
-            order = range(len(cand))
-            if len(live_p) >= n_live:
-                # the worst live value only rises during the pass: a proposal below the worst at the start of the pass
-                # can never be accepted -- drop those with one vectorised comparison, keep the order of the rest
-                order = np.flatnonzero(cand_p >= heap[0][0])
-            for ci in order:
-                c, cp = cand[ci], float(cand_p[ci])
-                if len(live_p) + len(grown) < n_live:
-                    if cp >= heap[0][0]:
-                        grown.append((c, cp))
-                        heapq.heappush(heap, (cp, len(live_p) + len(grown) - 1))
-                    continue
-                pk, k = heap[0]
-                if cp > pk or (cp == pk and cp >= self.target):
-                    heapq.heapreplace(heap, (cp, k))
-                    if k < len(live_p):
-                        live[k], live_p[k] = c, cp
-                    else:
-                        grown[k - len(live_p)] = (c, cp)
-            if grown:
-                live = np.vstack([live] + [g[0][None, :] for g in grown])
-                live_p = np.append(live_p, [g[1] for g in grown])
+            # replace-the-worst, candidate by candidate.  Full live set: one native pass (pydsb_ns_replace_worst: a heap of
+            # (P, slot) reproduces np.argmin's choice -- lowest slot among equal minima -- in O(log n_live) per candidate;
+            # 1e4 proposals against 1e5 live points, config C5, cost 0.5 s per iteration with an argmin scan and 60 ms
+            # in a Python loop over heapq).  While the set still grows towards the schedule's n_live: the same rule in
+            # Python.
+            if len(live_p) >= n_live and self.native_update:
+                from .capi import ns_replace_worst
+                live_p = np.ascontiguousarray(live_p, dtype=np.float64)
+                slots = ns_replace_worst(live_p, cand_p, self.target)
+                taken = slots >= 0
+                live[slots[taken]] = cand[taken]          # repeated slots: the last candidate written stays
+                heap = None
+            else:
+                live, live_p, heap = self._replace_worst_py(live, live_p, cand, cand_p, n_live, heap)
             iter_times.append(time.time() - t0)
             it += 1
         self.result = {

@@ -167,3 +167,28 @@ def test_ns_driver_with_a_cpu_constraint_function():
     assert res["evaluations"] == sum(calls)
     # efp reduction: -0.0 >= 0 counts as feasible
     assert ns.efp_from_g([np.array([[-0.0], [-1.0]])], np.array([0.25, 0.75]))[0] == 0.25
+
+
+def test_native_live_set_update_matches_the_python_rule():
+    """pydsb_ns_replace_worst (host-only C++) against the driver's Python loop, on probabilities with many ties (P is a
+    sum of a few equal weights, as in the shipped scripts) on both sides of the target."""
+    from pyds_b200 import capi
+    rng = np.random.default_rng(5)
+    drv = ns.DEUS.__new__(ns.DEUS)
+    for n_live, n_cand, levels, target in ((50, 40, 5, 0.5), (1000, 700, 11, 0.65), (7, 30, 3, 0.0), (64, 0, 4, 0.5)):
+        drv.target = target
+        live = rng.uniform(size=(n_live, 3))
+        live_p = rng.integers(0, levels, n_live) / (levels - 1)
+        cand = rng.uniform(size=(n_cand, 3))
+        cand_p = rng.integers(0, levels, n_cand) / (levels - 1)
+        a_live, a_p = live.copy(), live_p.copy()
+        a_live, a_p, _ = drv._replace_worst_py(a_live, a_p, cand, cand_p, n_live)
+        b_live, b_p = live.copy(), live_p.copy()
+        slots = capi.ns_replace_worst(b_p, cand_p, target)
+        taken = slots >= 0
+        b_live[slots[taken]] = cand[taken]
+        np.testing.assert_array_equal(a_p, b_p)
+        np.testing.assert_array_equal(a_live, b_live)
+        assert slots.shape == (n_cand,) and np.all(slots < n_live)
+    with pytest.raises(ValueError):
+        capi.ns_replace_worst(np.zeros(4, dtype=np.float32), np.zeros(2), 0.5)
