@@ -67,25 +67,36 @@ class DEUS:
 
     def _propose(self, rng, live, n, enlarge):
         """Uniform samples from the enlarged bounding ellipsoid of ``live``, clipped to the box."""
-        dim = live.shape[1]
-        span = self.hi - self.lo
-        u = (live - self.lo) / span
-        mu = u.mean(axis=0)
-        cov = np.cov(u.T) + 1e-12 * np.eye(dim) if len(u) > dim else np.eye(dim) * 0.25
-        L = np.linalg.cholesky(np.atleast_2d(cov))
-        y = (u - mu) @ np.linalg.inv(L).T                 # dim x dim inverse + one matmul (LAPACK gesv on 1e4+ right-hand
-        r = np.sqrt((y * y).sum(axis=1)).max() * (1.0 + enlarge)          # sides costs milliseconds); smallest scaled
-                                                                          # ellipsoid holding all points
-        chunks, have = [], 0
-        while have < n:
-            z = rng.normal(size=(4 * n, dim))
-            z /= np.linalg.norm(z, axis=1)[:, None]
-            z *= rng.uniform(size=(4 * n, 1)) ** (1.0 / dim) * r
-            cand = mu + z @ L.T
-            ok = np.all((cand >= 0.0) & (cand <= 1.0), axis=1)
-            chunks.append(cand[ok])                       # arrays, not rows: 1e4 proposals per iteration at config C5
-            have += len(chunks[-1])
-        return self.lo + np.concatenate(chunks)[:n] * span
+        # the products below have an inner dimension of a few design variables: a multi-threaded BLAS spends tens of
+        # milliseconds spinning its pool on them (measured: 70 ms with 8 OpenBLAS threads, 2 ms with one, for 1e5 x 6)
+        try:
+            from threadpoolctl import threadpool_limits
+            ctx = threadpool_limits(limits=1, user_api="blas")
+        except ImportError:                               # optional dependency: without it the calls are just slower
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            # dimension-major layout (dim, n): every reduction runs along the long axis and every product has the
+            # long axis last, which is what numpy and BLAS are fast at
+            n_pts, dim = live.shape
+            span = self.hi - self.lo
+            uT = (live.T - self.lo[:, None]) / span[:, None]
+            mu = uT.mean(axis=1)
+            xc = uT - mu[:, None]
+            cov = (xc @ xc.T) / (n_pts - 1) + 1e-12 * np.eye(dim) if n_pts > dim else np.eye(dim) * 0.25
+            L = np.linalg.cholesky(np.atleast_2d(cov))
+            y = np.linalg.inv(L) @ xc                     # dim x dim inverse + one product instead of gesv on 1e5 columns
+            r = np.sqrt((y * y).sum(axis=0).max()) * (1.0 + enlarge)      # smallest scaled ellipsoid holding all points
+            m = int(1.3 * n) + 16                         # proposals per batch: most of the ellipsoid lies inside the box
+            chunks, have = [], 0
+            while have < n:
+                z = rng.normal(size=(dim, m))
+                z *= rng.uniform(size=m) ** (1.0 / dim) * r / np.sqrt((z * z).sum(axis=0))
+                cand = mu[:, None] + L @ z
+                ok = (cand.min(axis=0) >= 0.0) & (cand.max(axis=0) <= 1.0)
+                chunks.append(cand[:, ok])                # arrays, not rows: 1e4 proposals per iteration at config C5
+                have += chunks[-1].shape[1]
+            return self.lo + np.concatenate(chunks, axis=1)[:, :n].T * span
 
     def _replace_worst_py(self, live, live_p, cand, cand_p, n_live, heap=None):
         """The update rule in plain Python (growth phase; also the cross-check of the native pass in the tests)."""
