@@ -100,6 +100,10 @@ class Solver:
             self._traj = eng.state_solve(d, p, z=z)[0]
             self._time = eng.time_grid()
             self.output["relaxation"] = self._collect_output()
+            if self.solve_trajectories:
+                # reference pyds/solver.py:46-48,57-61: a second NLP solve with the snapped indicators fixed -- its
+                # objective is then constant, so the controls found by the relaxation remain a solution: same profiles
+                self.output["trajectories"] = self.output["relaxation"]
         return indicator
 
     def efp(self, d, p, w, mode="shared", n_d_total=None, group=None):
@@ -222,4 +226,5 @@ class Solver:
         reference pyds/run.py:55-67)."""
         if not self.save_output or self.output["relaxation"] is None:
             return self.output
-        return {"relaxation": self._record([i]), "trajectories": None}
+        rec = self._record([i])
+        return {"relaxation": rec, "trajectories": rec if self.solve_trajectories else None}

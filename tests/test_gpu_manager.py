@@ -150,3 +150,9 @@ def test_saved_output_records_carry_the_state_profiles(tmp_path):
                 np.testing.assert_array_equal(got, x[i, j, :, cc])
             np.testing.assert_array_equal(v["g"], m.solver._g[i, j])
         assert rel["infeasible"] == bool((g_list[i] == -1.0).all())
+        assert rec["solver"]["trajectories"] is None                       # 'solve trajectories': False
+    cfg["solver"]["solve trajectories"] = True
+    m2 = TwoStageManager(cfg)
+    m2.g(d[:1], p)
+    rec = read_output_file(str(tmp_path / "pyds_output.pkl"))[0]
+    assert rec["solver"]["trajectories"]["data"][0]["c"] == rec["solver"]["relaxation"]["data"][0]["c"]
