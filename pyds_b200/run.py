@@ -136,6 +136,8 @@ class TwoStageManager(Manager):
         w = np.full(n_p, 1.0 / n_p)
         inputs = utils.load_input(self.model, self.input_map, {self._stages[0]: d[:1], self._stages[1]: p}) if len(d) else {}
         self._current_inputs = (d, p)
+        if self.simulator.save_output and len(d):            # warm-start simulation records (reference run.py:61-62)
+            self.simulator.simulate_all_scenarios(self.model, {self._stages[0]: d, self._stages[1]: p})
         indicator = self.solver.solve(d, p, w, mode="shared") if len(d) else np.zeros((0, n_p))
         g_list, records = [], []
         for i in range(d.shape[0]):
@@ -145,6 +147,8 @@ class TwoStageManager(Manager):
             self.output_manager.clear_buffer()
             self.output_manager.add_input({self._stages[0]: d[i:i + 1], self._stages[1]: p})
             self.output_manager.add_solver_solution(self.solver.output_for(i))
+            if self.simulator.save_output:
+                self.output_manager.add_simulator_solution(self.simulator.output_for([i]))
             records.append(self.output_manager.data)         # one record per design point (reference run.py:67)
         if records:
             self.output_manager.write_records_to_disk(records)
@@ -175,6 +179,8 @@ class ThreeStageManager(Manager):
             self._build_model(BFs)
         w = np.full(n_p, 1.0 / n_p)
         self._current_inputs = (d, p)
+        if self.simulator.save_output and n_d:               # reference run.py:89-90
+            self.simulator.simulate_all_scenarios(self.model, {self._stages[0]: d, self._stages[1]: p})
         indicator = self.solver.solve(d, p, w, mode="global") if n_d else np.zeros((0, n_p))
         flat = indicator.reshape(-1)
         g_list = []
@@ -185,5 +191,7 @@ class ThreeStageManager(Manager):
         self.output_manager.clear_buffer()
         self.output_manager.add_input({self._stages[0]: d, self._stages[1]: p})
         self.output_manager.add_solver_solution(self.solver.output)
+        if self.simulator.save_output and n_d:
+            self.output_manager.add_simulator_solution(self.simulator.output)
         self.output_manager.write_data_to_disk()            # one record per call (reference run.py:97)
         return g_list

@@ -227,6 +227,7 @@ class Simulator:
         self._engine = None
         self.user_time = None
         self.output = []
+        self._traj = None
         self.device = int(config.get("device", 0))
         self._build_model()
         self.input_names = []
@@ -272,14 +273,27 @@ class Simulator:
         d, p = self.parent._split_inputs(input_values)
         g, ind, _ = self.engine.eval_host(d, p, None, z=self.default_controls() if self.lowered.nz and not self.lowered.z_fixed.all() else None,
                                           want_g=True, want_ind=True, want_P=False)
-        self.user_time = time.time() - t0
         self.last_g = g
+        self._traj = None
         if self.save_output:
-            self.output.append(self._collect_output())
+            # the simulated profiles of every scenario at the warm-start controls (reference simulator.py:49-51,112-119)
+            z = self.default_controls() if self.lowered.nz and not self.lowered.z_fixed.all() else None
+            self._traj = self.engine.state_solve(d, p, z=z)[0]
+            self._tsim = self.engine.time_grid()
+        self.user_time = time.time() - t0
+        if self.save_output:
+            self.output = self.output_for(range(d.shape[0]))
         return g
 
-    def _collect_output(self):
-        return {"user time": self.user_time, "var_names": self.lowered.constraint_names, "g": None if not hasattr(self, "last_g") else self.last_g.copy()}
+    def output_for(self, rows):
+        """The per-scenario containers (reference simulator.py:112-119: user time, tsim, var_names, simsolution) of the
+        design points ``rows``, theta scenarios in order; ``simsolution`` is (n_times, n_vars) at the collocation times."""
+        if not self.save_output or self._traj is None:
+            return []
+        names = self.lowered.dyn_states + self.lowered.quad_states
+        return [{"user time": self.user_time, "tsim": self._tsim.copy(), "var_names": list(names),
+                 "simsolution": self._traj[i, j].copy(), "g": self.last_g[i, j].copy()}
+                for i in rows for j in range(self._traj.shape[1])]
 
     def get_sim_result(self):
         return getattr(self, "last_g", None)

@@ -152,7 +152,14 @@ def test_saved_output_records_carry_the_state_profiles(tmp_path):
         assert rel["infeasible"] == bool((g_list[i] == -1.0).all())
         assert rec["solver"]["trajectories"] is None                       # 'solve trajectories': False
     cfg["solver"]["solve trajectories"] = True
+    cfg["simulator"]["save output"] = True
     m2 = TwoStageManager(cfg)
     m2.g(d[:1], p)
     rec = read_output_file(str(tmp_path / "pyds_output.pkl"))[0]
     assert rec["solver"]["trajectories"]["data"][0]["c"] == rec["solver"]["relaxation"]["data"][0]["c"]
+    # simulator records: one container per theta scenario with the profiles at the warm-start controls (F_in = 0)
+    sims = rec["simulator"]
+    assert len(sims) == 7 and set(sims[0]) >= {"user time", "tsim", "var_names", "simsolution"}
+    x0, _ = m2.simulator.engine.state_solve(d[:1], p, z=np.zeros(8))
+    np.testing.assert_array_equal(sims[3]["simsolution"], x0[0, 3])
+    assert sims[0]["simsolution"].shape == (25, 4) and sims[0]["tsim"][-1] == 1.0
