@@ -82,6 +82,13 @@ int pydsb_model_destroy(void* handle);
 int pydsb_assemble(const void* blob, size_t nbytes, uint32_t* words, size_t cap, size_t* n_words, long long* info,
                    int n_info);
 int pydsb_model_info(void* handle, long long* out, int n);
+/* Host-only: the bounding ellipsoid the nested-sampling proposals are drawn from ("suob-ellipsoid" sampling of the DEUS
+ * activity form, reference run_twostage.py:182-200 [3P]).  live: (n, dim) design points, lo / hi: the design box.  In
+ * box-scaled coordinates u = (d - lo) / (hi - lo): mu_out (dim) = mean, L_out (dim x dim, row-major, lower) = Cholesky
+ * factor of the sample covariance (+ 1e-12 I; 0.25 I when n <= dim), *r_out = max_i |L^-1 (u_i - mu)|, so that
+ * { mu + L z : |z| <= r } is the smallest ellipsoid of that shape holding every live point. */
+int pydsb_ns_ellipsoid(const double* live, long long n, int dim, const double* lo, const double* hi, double* mu_out,
+                       double* L_out, double* r_out);
 /* Host-only: the replace-the-worst pass of one nested-sampling iteration (the live-point bookkeeping DEUS does around
  * the constraint function, reference run_twostage.py:167-180 `points_schedule` / nlive / nreplacements [3P]).  For each
  * candidate in order: if its probability cand_p[c] is above the worst live value -- or equal to it and at least `target`

@@ -23,7 +23,7 @@ COUNTER_NAMES = ["scenarios", "newton_iters", "newton_warp_iters", "failed", "la
 EXPORTS = ["pydsb_last_error", "pydsb_version", "pydsb_model_create", "pydsb_model_destroy", "pydsb_model_info",
            "pydsb_eval", "pydsb_eval_tol", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_state_solve", "pydsb_recourse_solve",
            "pydsb_recourse_solve_global_dist", "pydsb_get_counters", "pydsb_dfma_peak", "pydsb_assemble",
-           "pydsb_ns_replace_worst"]
+           "pydsb_ns_replace_worst", "pydsb_ns_ellipsoid"]
 # int (*pydsb_allreduce_fn)(double* device_buf, int n, void* user)
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
 
@@ -56,6 +56,8 @@ def load():
     L.pydsb_assemble.restype = ci
     L.pydsb_assemble.argtypes = [ctypes.c_char_p, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
                                  ctypes.POINTER(ll), ci]
+    L.pydsb_ns_ellipsoid.restype = ci
+    L.pydsb_ns_ellipsoid.argtypes = [vp, ll, ci, vp, vp, vp, vp, vp]
     L.pydsb_ns_replace_worst.restype = ci
     L.pydsb_ns_replace_worst.argtypes = [vp, ll, vp, ll, ctypes.c_double, vp]
     L.pydsb_model_destroy.restype = ci
@@ -315,6 +317,18 @@ class Engine:
         buf = (ctypes.c_ulonglong * len(COUNTER_NAMES))()
         _check(self._lib.pydsb_get_counters(self._h, buf, len(COUNTER_NAMES), 1 if reset else 0))
         return {k: int(v) for k, v in zip(COUNTER_NAMES, buf)}
+
+
+def ns_ellipsoid(live, lo, hi):
+    """Bounding ellipsoid of the live points in box-scaled coordinates (host only): returns (mu, L, r)."""
+    live = np.ascontiguousarray(live, dtype=np.float64)
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    n, dim = live.shape
+    mu, L, r = np.empty(dim), np.empty((dim, dim)), ctypes.c_double(0.0)
+    _check(load().pydsb_ns_ellipsoid(live.ctypes.data, n, dim, lo.ctypes.data, hi.ctypes.data, mu.ctypes.data, L.ctypes.data,
+                                     ctypes.addressof(r)))
+    return mu, L, r.value
 
 
 def ns_replace_worst(live_p, cand_p, target):

@@ -566,6 +566,67 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
     return PYDSB_OK;
 }
 
+// Host-only: the bounding ellipsoid of the live points (pyds_b200/ns.py): mean, Cholesky factor of the covariance and the
+// largest Mahalanobis radius of the points scaled to the unit box.  Two passes over the points.
+int pydsb_ns_ellipsoid(const double* live, long long n, int dim, const double* lo, const double* hi, double* mu_out,
+                       double* L_out, double* r_out)
+{
+    constexpr int MAXD = 32;
+    if (!live || !lo || !hi || !mu_out || !L_out || !r_out || n < 1 || dim < 1 || dim > MAXD)
+        return fail(PYDSB_ERR_INVALID, "bad ellipsoid arguments (1..32 design variables, at least one live point)");
+    double inv_span[MAXD], mu[MAXD], C[MAXD][MAXD], L[MAXD][MAXD];
+    for (int k = 0; k < dim; ++k) {
+        if (!(hi[k] > lo[k])) return fail(PYDSB_ERR_INVALID, "empty design box");
+        inv_span[k] = 1.0 / (hi[k] - lo[k]);
+        mu[k] = 0.0;
+    }
+    for (long long i = 0; i < n; ++i)
+        for (int k = 0; k < dim; ++k) mu[k] += (live[i * dim + k] - lo[k]) * inv_span[k];
+    for (int k = 0; k < dim; ++k) mu[k] /= (double)n;
+    for (int a = 0; a < dim; ++a)
+        for (int b = 0; b < dim; ++b) C[a][b] = 0.0;
+    if (n > dim) {
+        for (long long i = 0; i < n; ++i) {
+            double x[MAXD];
+            for (int k = 0; k < dim; ++k) x[k] = (live[i * dim + k] - lo[k]) * inv_span[k] - mu[k];
+            for (int a = 0; a < dim; ++a)
+                for (int b = 0; b <= a; ++b) C[a][b] += x[a] * x[b];
+        }
+        for (int a = 0; a < dim; ++a)
+            for (int b = 0; b <= a; ++b) C[a][b] = C[a][b] / (double)(n - 1) + (a == b ? 1e-12 : 0.0);
+    } else {
+        for (int a = 0; a < dim; ++a) C[a][a] = 0.25;       // too few points for a covariance: a fixed ball
+    }
+    for (int a = 0; a < dim; ++a)
+        for (int b = 0; b <= a; ++b) {
+            double s = C[a][b];
+            for (int k = 0; k < b; ++k) s -= L[a][k] * L[b][k];
+            if (a == b) {
+                if (!(s > 0.0)) return fail(PYDSB_ERR_INVALID, "live-point covariance is not positive definite");
+                L[a][a] = sqrt(s);
+            } else {
+                L[a][b] = s / L[b][b];
+            }
+        }
+    double r2 = 0.0;                                         // max |L^-1 (u - mu)|^2 by forward substitution
+    for (long long i = 0; i < n; ++i) {
+        double y[MAXD], q = 0.0;
+        for (int a = 0; a < dim; ++a) {
+            double s = (live[i * dim + a] - lo[a]) * inv_span[a] - mu[a];
+            for (int k = 0; k < a; ++k) s -= L[a][k] * y[k];
+            y[a] = s / L[a][a];
+            q += y[a] * y[a];
+        }
+        if (q > r2) r2 = q;
+    }
+    for (int a = 0; a < dim; ++a) {
+        mu_out[a] = mu[a];
+        for (int b = 0; b < dim; ++b) L_out[a * dim + b] = b <= a ? L[a][b] : 0.0;
+    }
+    *r_out = sqrt(r2);
+    return PYDSB_OK;
+}
+
 // Host-only: the live-set update of one nested-sampling iteration (pyds_b200/ns.py), candidate by candidate.
 int pydsb_ns_replace_worst(double* live_p, long long n_live, const double* cand_p, long long n_cand, double target,
                            long long* slot_out)

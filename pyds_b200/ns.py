@@ -26,6 +26,8 @@ def efp_from_g(g_list, w):
 
 
 class DEUS:
+    _blas = None                                  # threadpoolctl controller, created on first use
+
     def __init__(self, form):
         if form.get("activity_type") != "ds":
             raise NotImplementedError("only the design-space ('ds') activity is implemented")
@@ -67,27 +69,40 @@ class DEUS:
 
     def _propose(self, rng, live, n, enlarge):
         """Uniform samples from the enlarged bounding ellipsoid of ``live``, clipped to the box."""
-        # the products below have an inner dimension of a few design variables: a multi-threaded BLAS spends tens of
-        # milliseconds spinning its pool on them (measured: 70 ms with 8 OpenBLAS threads, 2 ms with one, for 1e5 x 6)
-        try:
-            from threadpoolctl import threadpool_limits
-            ctx = threadpool_limits(limits=1, user_api="blas")
-        except ImportError:                               # optional dependency: without it the calls are just slower
-            import contextlib
-            ctx = contextlib.nullcontext()
+        # numpy path only: its products have an inner dimension of a few design variables, on which a multi-threaded
+        # BLAS spends tens of milliseconds spinning its pool (measured: 70 ms with 8 OpenBLAS threads, 2 ms with one, for
+        # 1e5 x 6).  The controller is created once: building it walks every loaded shared library (25 ms with torch).
+        import contextlib
+        ctx = contextlib.nullcontext()
+        if not self.native_update:
+            try:
+                if DEUS._blas is None:
+                    from threadpoolctl import ThreadpoolController
+                    DEUS._blas = ThreadpoolController()
+                ctx = DEUS._blas.limit(limits=1, user_api="blas")
+            except ImportError:                           # optional dependency: without it the calls are just slower
+                pass
         with ctx:
-            # dimension-major layout (dim, n): every reduction runs along the long axis and every product has the
-            # long axis last, which is what numpy and BLAS are fast at
             n_pts, dim = live.shape
             span = self.hi - self.lo
-            uT = (live.T - self.lo[:, None]) / span[:, None]
-            mu = uT.mean(axis=1)
-            xc = uT - mu[:, None]
-            cov = (xc @ xc.T) / (n_pts - 1) + 1e-12 * np.eye(dim) if n_pts > dim else np.eye(dim) * 0.25
-            L = np.linalg.cholesky(np.atleast_2d(cov))
-            y = np.linalg.inv(L) @ xc                     # dim x dim inverse + one product instead of gesv on 1e5 columns
-            r = np.sqrt((y * y).sum(axis=0).max()) * (1.0 + enlarge)      # smallest scaled ellipsoid holding all points
-            m = int(1.3 * n) + 16                         # proposals per batch: most of the ellipsoid lies inside the box
+            if self.native_update:
+                # mean, covariance factor and largest Mahalanobis radius in two native passes over the live points
+                from .capi import ns_ellipsoid
+                mu, L, r = ns_ellipsoid(live, self.lo, self.hi)
+            else:
+                # numpy, dimension-major layout (dim, n): every reduction runs along the long axis and every product has
+                # the long axis last, which is what numpy and BLAS are fast at
+                uT = (live.T - self.lo[:, None]) / span[:, None]
+                mu = uT.mean(axis=1)
+                xc = uT - mu[:, None]
+                cov = (xc @ xc.T) / (n_pts - 1) + 1e-12 * np.eye(dim) if n_pts > dim else np.eye(dim) * 0.25
+                L = np.linalg.cholesky(np.atleast_2d(cov))
+                y = np.linalg.inv(L) @ xc
+                r = np.sqrt((y * y).sum(axis=0).max())
+            r = r * (1.0 + enlarge)                       # the smallest ellipsoid of that shape holding all points, enlarged
+            # proposals per batch: cache-sized (one batch of 2e5 x 6 for a wide early live set, of which ~5 % lies in the
+            # box, measured 6x slower than 15 batches of 1.3e4: page faults on fresh 10 MB temporaries)
+            m = min(int(1.3 * n) + 16, 16384)
             chunks, have = [], 0
             while have < n:
                 z = rng.normal(size=(dim, m))

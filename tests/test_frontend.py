@@ -192,3 +192,33 @@ def test_native_live_set_update_matches_the_python_rule():
         assert slots.shape == (n_cand,) and np.all(slots < n_live)
     with pytest.raises(ValueError):
         capi.ns_replace_worst(np.zeros(4, dtype=np.float32), np.zeros(2), 0.5)
+
+
+def test_native_bounding_ellipsoid_matches_numpy():
+    from pyds_b200 import capi
+    rng = np.random.default_rng(8)
+    lo, hi = np.array([250.0, 250.0, 1500.0, 0.0, -1.0]), np.array([350.0, 300.0, 2500.0, 2.5, 1.0])
+    A = rng.normal(size=(5, 5)) * 0.1
+    live = np.clip(lo + (0.5 + rng.normal(size=(4000, 5)) @ A) * (hi - lo), lo, hi)
+    mu, L, r = capi.ns_ellipsoid(live, lo, hi)
+    u = (live - lo) / (hi - lo)
+    np.testing.assert_allclose(mu, u.mean(axis=0), rtol=1e-12)
+    cov = np.cov(u.T) + 1e-12 * np.eye(5)
+    np.testing.assert_allclose(L @ L.T, cov, rtol=1e-10, atol=1e-15)
+    assert np.all(np.triu(L, 1) == 0.0)
+    y = np.linalg.solve(L, (u - mu).T)
+    np.testing.assert_allclose(r, np.sqrt((y * y).sum(axis=0).max()), rtol=1e-10)
+    # fewer points than dimensions: the fixed ball
+    mu2, L2, _ = capi.ns_ellipsoid(live[:3], lo, hi)
+    np.testing.assert_array_equal(L2, 0.5 * np.eye(5))
+    # both proposal paths draw the same points from the same generator state (up to round-off of the statistics)
+    drv = ns.DEUS.__new__(ns.DEUS)
+    drv.lo, drv.hi = lo, hi
+    out = []
+    for native in (True, False):
+        drv.native_update = native
+        out.append(drv._propose(np.random.default_rng(3), live, 500, 0.1))
+    assert out[0].shape == (500, 5)
+    np.testing.assert_allclose(out[0], out[1], rtol=1e-9, atol=1e-9)
+    with pytest.raises(capi.PydsbError):
+        capi.ns_ellipsoid(live, hi, lo)
