@@ -15,6 +15,7 @@ managers do), that fused GPU path is used instead and g is never materialised.
 from __future__ import annotations
 
 import heapq
+import math
 import time
 
 import numpy as np
@@ -67,8 +68,9 @@ class DEUS:
             return np.asarray(owner.efp(d, self.p, self.w), dtype=np.float64)
         return efp_from_g(self.g_func(d, self.p), self.w)
 
-    def _propose(self, rng, live, n, enlarge):
-        """Uniform samples from the enlarged bounding ellipsoid of ``live``, clipped to the box."""
+    def _propose(self, rng, live, n, enlarge, method=None):
+        """Uniform samples from the enlarged bounding ellipsoid of ``live``, clipped to the box.  ``method``: None picks
+        the rejection scheme with the higher acceptance, "ellipsoid" / "box" force one (tests)."""
         # numpy path only: its products have an inner dimension of a few design variables, on which a multi-threaded
         # BLAS spends tens of milliseconds spinning its pool (measured: 70 ms with 8 OpenBLAS threads, 2 ms with one, for
         # 1e5 x 6).  The controller is created once: building it walks every loaded shared library (25 ms with torch).
@@ -103,14 +105,35 @@ class DEUS:
             # proposals per batch: cache-sized (one batch of 2e5 x 6 for a wide early live set, of which ~5 % lies in the
             # box, measured 6x slower than 15 batches of 1.3e4: page faults on fresh 10 MB temporaries)
             m = min(int(1.3 * n) + 16, 16384)
-            chunks, have = [], 0
+            # Uniform samples of (ellipsoid intersected with the unit box), by rejection from whichever is tighter: the
+            # ellipsoid (directions from normals; rejects what falls outside the box -- 95 % for a wide early live set in
+            # 6 dimensions, whose ellipsoid contains the whole box) or the ellipsoid's bounding box clipped to the unit
+            # box (rejects what falls outside the ellipsoid -- 92 % for a concentrated set in 6 dimensions).  The first
+            # batch uses the ellipsoid and measures its acceptance; the volumes then tell which one wins.
+            ext = r * np.sqrt((L * L).sum(axis=1))
+            blo, bhi = np.maximum(mu - ext, 0.0), np.minimum(mu + ext, 1.0)
+            vol_box = float(np.prod(np.maximum(bhi - blo, 0.0)))
+            vol_ell = math.pi ** (dim / 2.0) / math.gamma(dim / 2.0 + 1.0) * r ** dim * float(np.prod(np.diag(L)))
+            Linv = None
+            chunks, have, from_box = [], 0, method == "box"
+            if from_box:
+                Linv = np.linalg.inv(L)
             while have < n:
-                z = rng.normal(size=(dim, m))
-                z *= rng.uniform(size=m) ** (1.0 / dim) * r / np.sqrt((z * z).sum(axis=0))
-                cand = mu[:, None] + L @ z
-                ok = (cand.min(axis=0) >= 0.0) & (cand.max(axis=0) <= 1.0)
+                if from_box:
+                    cand = blo[:, None] + (bhi - blo)[:, None] * rng.uniform(size=(dim, m))
+                    y = Linv @ (cand - mu[:, None])
+                    ok = (y * y).sum(axis=0) <= r * r
+                else:
+                    z = rng.normal(size=(dim, m))
+                    z *= rng.uniform(size=m) ** (1.0 / dim) * r / np.sqrt((z * z).sum(axis=0))
+                    cand = mu[:, None] + L @ z
+                    ok = (cand.min(axis=0) >= 0.0) & (cand.max(axis=0) <= 1.0)
                 chunks.append(cand[:, ok])                # arrays, not rows: 1e4 proposals per iteration at config C5
                 have += chunks[-1].shape[1]
+                if method is None and len(chunks) == 1 and have < n and vol_box > 0.0:
+                    a_ell = max(have / m, 1.0 / m)        # share of the ellipsoid inside the box
+                    if a_ell * vol_ell / vol_box > a_ell:  # = share of the clipped bounding box inside the ellipsoid
+                        from_box, Linv = True, np.linalg.inv(L)
             return self.lo + np.concatenate(chunks, axis=1)[:, :n].T * span
 
     def _replace_worst_py(self, live, live_p, cand, cand_p, n_live, heap=None):

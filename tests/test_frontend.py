@@ -222,3 +222,26 @@ def test_native_bounding_ellipsoid_matches_numpy():
     np.testing.assert_allclose(out[0], out[1], rtol=1e-9, atol=1e-9)
     with pytest.raises(capi.PydsbError):
         capi.ns_ellipsoid(live, hi, lo)
+
+
+def test_proposal_samplers_draw_from_the_same_distribution():
+    """Rejection from the ellipsoid and rejection from its clipped bounding box both give uniform samples of
+    (ellipsoid intersected with the box): same first and second moments within Monte Carlo error, all inside both."""
+    from pyds_b200 import capi
+    rng = np.random.default_rng(2)
+    lo, hi = np.zeros(3), np.ones(3)
+    live = np.clip(np.array([0.15, 0.8, 0.5]) + rng.normal(size=(400, 3)) @ np.diag([0.12, 0.1, 0.3]), 0.0, 1.0)
+    drv = ns.DEUS.__new__(ns.DEUS)
+    drv.lo, drv.hi, drv.native_update = lo, hi, True
+    a = drv._propose(np.random.default_rng(10), live, 150000, 0.2, method="ellipsoid")
+    b = drv._propose(np.random.default_rng(11), live, 150000, 0.2, method="box")
+    c = drv._propose(np.random.default_rng(12), live, 20000, 0.2)
+    mu, L, r = capi.ns_ellipsoid(live, lo, hi)
+    for pts in (a, b, c):
+        assert pts.min() >= 0.0 and pts.max() <= 1.0
+        y = np.linalg.solve(L, (pts - mu).T)
+        assert np.sqrt((y * y).sum(axis=0)).max() <= r * 1.2 * (1 + 1e-12)
+    assert (a.min(axis=0) < 0.01).any() or (a.max(axis=0) > 0.99).any()        # the box does cut the ellipsoid
+    np.testing.assert_allclose(a.mean(axis=0), b.mean(axis=0), atol=4e-3)
+    np.testing.assert_allclose(np.cov(a.T), np.cov(b.T), atol=2e-3)
+    np.testing.assert_allclose(c.mean(axis=0), a.mean(axis=0), atol=1e-2)
