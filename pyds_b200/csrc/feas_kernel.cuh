@@ -161,7 +161,10 @@ __device__ __forceinline__ void newton_step(const ExecImage& img, int at, unsign
 // TRAJ (pydsb_state_solve, cold): the same program, but instead of g the state trajectories are written --
 // la.g_out is (n_d, n_t, 1 + 3 nfe, ns + nq): row 0 the initial values, then the collocation points of every
 // element (dynamic states first, quadrature states after them); la.ind_out receives 1.0 for a failed solve.
-template <int MAXNS, int SPT, bool TRAJ = false>
+// PACK (small theta sets, n_t <= TILE / 2 -- the shipped scripts use 50 samples): a tile holds the whole theta set of
+// TILE / n_t consecutive design points instead of one design point's slice, so the lanes are not left idle; the
+// weighted indicator is summed per design point through shared memory in scenario order (deterministic).
+template <int MAXNS, int SPT, bool TRAJ = false, bool PACK = false>
 __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))))
     feas_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ LaunchArgs la)
 {
@@ -228,10 +231,13 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
     const int traj_w = img.ns + img.nq;                                 // TRAJ: values per time point
     const long long traj_rows = 1 + 3 * (long long)img.nfe;
 
-    const long long total = la.n_d * (long long)la.n_tiles;
+    const int pack_k = PACK ? TILE / (int)la.n_t : 1;                   // PACK: design points per tile
+    const long long total = PACK ? (la.n_d + pack_k - 1) / pack_k : la.n_d * (long long)la.n_tiles;
     unsigned phase = 0;
 
+    // theta rows a tile needs in the landing buffer (PACK: the whole set, every tile)
     auto tile_rows = [&](long long t) -> int {
+        if constexpr (PACK) return (int)la.n_t;
         const long long j0 = (t % la.n_tiles) * (long long)TILE;
         const long long rem = la.n_t - j0;
         return rem < TILE ? (int)rem : TILE;
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
     auto issue = [&](long long t) {
         const int rows = tile_rows(t);
         if (tile_tma(rows)) {
-            const long long j0 = (t % la.n_tiles) * (long long)TILE;
+            const long long j0 = PACK ? 0 : (t % la.n_tiles) * (long long)TILE;
             const unsigned bytes = (unsigned)(rows * p_dim * sizeof(double));
             mbar_expect_tx(&mbar[0], bytes);
             tma_load_1d(land, la.theta + j0 * p_dim, bytes, &mbar[0]);
@@ -256,19 +262,41 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
     unsigned cnt_warp_iters = 0, cnt_failed = 0, cnt_done = 0;
 
     for (; t < total; t += gridDim.x) {
-        const long long i_d = t / la.n_tiles;
-        const long long j0 = (t % la.n_tiles) * (long long)TILE;
+        const long long i_d = PACK ? t * pack_k : t / la.n_tiles;      // PACK: the tile's first design point
+        const long long j0 = PACK ? 0 : (t % la.n_tiles) * (long long)TILE;
         const int rows = tile_rows(t);
         bool valid[SPT];
         long long jj_[SPT];
-        int row[SPT];
+        int row[SPT];                                      // row of the landing buffer
+        int dl[PACK ? SPT : 1];                            // PACK: design point within the tile
+        int pack_here = 1;                                 // PACK: design points in this tile
+        if constexpr (PACK) {
+            const long long left = la.n_d - i_d;
+            pack_here = left < pack_k ? (int)left : pack_k;
+            const int n_scen = pack_here * (int)la.n_t;
 #pragma unroll
-        for (int s = 0; s < SPT; ++s) {
-            const int r = tid * SPT + s;                   // a thread's scenarios are consecutive theta rows
-            valid[s] = r < rows;
-            row[s] = valid[s] ? r : rows - 1;              // idle lanes replay the last row
-            jj_[s] = j0 + row[s];
+            for (int s = 0; s < SPT; ++s) {
+                const int r = tid * SPT + s;
+                valid[s] = r < n_scen;
+                const int rr = valid[s] ? r : n_scen - 1;  // idle lanes replay the last scenario
+                dl[s] = rr / (int)la.n_t;
+                row[s] = rr - dl[s] * (int)la.n_t;
+                jj_[s] = row[s];
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) {
+                const int r = tid * SPT + s;               // a thread's scenarios are consecutive theta rows
+                valid[s] = r < rows;
+                row[s] = valid[s] ? r : rows - 1;          // idle lanes replay the last row
+                jj_[s] = j0 + row[s];
+            }
         }
+        // design point of the thread's scenario s
+        auto id_of = [&](int s) -> long long {
+            if constexpr (PACK) return i_d + dl[s];
+            else return i_d;
+        };
 
         // ---- parameters into the register file (theta from the TMA landing buffer) ----
         if (tile_tma(rows)) {
@@ -286,10 +314,16 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 for (int c = 0; c < p_dim; ++c) slot(tab_par[d_dim + c], s) = __ldg(src + c);
             }
         }
-        for (int c = 0; c < d_dim; ++c) {
-            const double dv = __ldg(la.d + i_d * d_dim + c);
+        if constexpr (PACK) {
 #pragma unroll
-            for (int s = 0; s < SPT; ++s) slot(tab_par[c], s) = dv;
+            for (int s = 0; s < SPT; ++s)
+                for (int c = 0; c < d_dim; ++c) slot(tab_par[c], s) = __ldg(la.d + id_of(s) * d_dim + c);
+        } else {
+            for (int c = 0; c < d_dim; ++c) {
+                const double dv = __ldg(la.d + i_d * d_dim + c);
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) slot(tab_par[c], s) = dv;
+            }
         }
         __syncthreads();                                   // landing buffer and `red` are free again
         {
@@ -441,7 +475,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
 #pragma unroll
                         for (int s = 0; s < SPT; ++s) {
                             if (!valid[s]) continue;
-                            double* o = la.g_out + ((i_d * la.n_t + jj_[s]) * traj_rows + 1 + 3 * e) * traj_w;
+                            double* o = la.g_out + ((id_of(s) * la.n_t + jj_[s]) * traj_rows + 1 + 3 * e) * traj_w;
                             for (int p = 0; p < 3; ++p) {
                                 for (int n = 0; n < img.ns; ++n) o[p * traj_w + n] = slot(img.x_slot + 3 * n + p, s);
                                 for (int qn = 0; qn < img.nq; ++qn) o[p * traj_w + img.ns + qn] = slot(img.qe_slot + qn, s);
@@ -472,7 +506,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
 #pragma unroll
                             for (int s = 0; s < SPT; ++s) {
                                 if (!valid[s]) continue;
-                                double* o = la.g_out + ((i_d * la.n_t + jj_[s]) * traj_rows + 1 + 3 * e) * traj_w + img.ns + qn;
+                                double* o = la.g_out + ((id_of(s) * la.n_t + jj_[s]) * traj_rows + 1 + 3 * e) * traj_w + img.ns + qn;
                                 for (int p = 0; p < 2; ++p) {
                                     double a = aint[p][0] * f0.v[s];
                                     a = fma(aint[p][1], f1.v[s], a);
@@ -570,7 +604,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                         if (img.zero_slot) slot(img.zero_slot, s) = 0.0;
                         if constexpr (TRAJ) {
                             if (valid[s]) {
-                                double* o = la.g_out + (i_d * la.n_t + jj_[s]) * traj_rows * traj_w;
+                                double* o = la.g_out + (id_of(s) * la.n_t + jj_[s]) * traj_rows * traj_w;
                                 for (int n = 0; n < img.ns; ++n) o[n] = x0v[n];
                                 for (int qn = 0; qn < img.nq; ++qn) o[img.ns + qn] = slot(img.qe_slot + qn, s);
                             }
@@ -585,8 +619,8 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                         double zv1;
                         if (la.z_mode == 0 || tab_zfix[zi]) zv1 = ref_ld(tab_z[zi], s);
                         else if (la.z_mode == 1) zv1 = __ldg(la.z + zi);
-                        else if (la.z_mode == 2) zv1 = __ldg(la.z + i_d * img.nz + zi);
-                        else zv1 = __ldg(la.z + (i_d * la.n_t + jj_[s]) * img.nz + zi);
+                        else if (la.z_mode == 2) zv1 = __ldg(la.z + id_of(s) * img.nz + zi);
+                        else zv1 = __ldg(la.z + (id_of(s) * la.n_t + jj_[s]) * img.nz + zi);
                         zv_.v[s] = zv1;
                     }
                     STV(w0.y, zv_);
@@ -633,10 +667,12 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 if (failed[s]) gv = __longlong_as_double(0x7ff8000000000000LL);
                 feasible = feasible && (gv <= la.gtol[c]);
                 if constexpr (!TRAJ)
-                    if (la.g_out && valid[s]) la.g_out[(i_d * la.n_t + j) * img.ng + c] = gv;
+                    if (la.g_out && valid[s]) la.g_out[(id_of(s) * la.n_t + j) * img.ng + c] = gv;
             }
-            if (la.ind_out && valid[s]) la.ind_out[i_d * la.n_t + j] = TRAJ ? (failed[s] ? 1.0 : 0.0) : (feasible ? -0.0 : -1.0);
-            if (valid[s] && feasible) wv += la.w ? __ldg(la.w + j) : 1.0 / (double)la.n_t;
+            if (la.ind_out && valid[s]) la.ind_out[id_of(s) * la.n_t + j] = TRAJ ? (failed[s] ? 1.0 : 0.0) : (feasible ? -0.0 : -1.0);
+            const double w1 = (valid[s] && feasible) ? (la.w ? __ldg(la.w + j) : 1.0 / (double)la.n_t) : 0.0;
+            if constexpr (PACK) slot(0, s) = w1;           // the program is over: the first register-file unit is scratch
+            else wv += w1;
             if (valid[s]) {
                 cnt_iters += my_acc[s] >> 40;
                 cnt_flops += my_acc[s] & ((1ull << 40) - 1);
@@ -644,14 +680,26 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 cnt_done += 1u;
             }
         }
-        wv = warp_sum(wv);
-        if (lane == 0) red[warp] = wv;
-        __syncthreads();
-        if (tid == 0) {
-            double sum = 0.0;
+        if constexpr (PACK) {
+            // per design point: its n_t weighted indicators in scenario order, one thread each
+            __syncthreads();
+            for (int q = tid; q < pack_here; q += BLOCK) {
+                const double* wr = reinterpret_cast<const double*>(smem + img.off_slots) + q * (int)la.n_t;
+                double sum = 0.0;
+                for (int j = 0; j < (int)la.n_t; ++j) sum += wr[j];
+                la.partial[i_d + q] = sum;
+            }
+            __syncthreads();                               // before the next tile's parameters overwrite the unit
+        } else {
+            wv = warp_sum(wv);
+            if (lane == 0) red[warp] = wv;
+            __syncthreads();
+            if (tid == 0) {
+                double sum = 0.0;
 #pragma unroll
-            for (int i = 0; i < BLOCK / 32; ++i) sum += red[i];
-            la.partial[t] = sum;
+                for (int i = 0; i < BLOCK / 32; ++i) sum += red[i];
+                la.partial[t] = sum;
+            }
         }
     }
 

@@ -117,6 +117,18 @@ FeasFn traj_for(int ns, int spt)
     }
 }
 
+// small theta sets: several design points per tile
+FeasFn pack_for(int ns, int spt)
+{
+    switch (ns * 10 + spt) {
+    case 11: return feas_kernel<1, 1, false, true>;
+    case 12: return feas_kernel<1, 2, false, true>;
+    case 21: return feas_kernel<2, 1, false, true>;
+    case 31: return feas_kernel<3, 1, false, true>;
+    default: return nullptr;
+    }
+}
+
 int image_maxns(const ExecImage& g)
 {
     int maxns = 1;
@@ -731,11 +743,14 @@ int eval_impl(void* handle, const double* d, long long n_d, const double* theta,
         return PYDSB_OK;
     }
     const long long tile = (long long)img.spt * BLOCK;               // theta rows per tile
-    const long long n_tiles_ll = (n_t + tile - 1) / tile;
+    // a theta set of at most half a tile (the shipped scripts use 50 samples): tile / n_t design points share a tile
+    const bool pack = !traj && 2 * n_t <= tile;
+    const long long pack_k = pack ? tile / n_t : 1;
+    const long long n_tiles_ll = pack ? 1 : (n_t + tile - 1) / tile;
     if (n_tiles_ll > 0x7fffffffLL) return fail(PYDSB_ERR_INVALID, "n_t too large");
-    const int n_tiles = (int)n_tiles_ll;
-    const long long total = n_d * n_tiles_ll;
-    int rc = ensure_partial(m, (size_t)total);
+    const int n_tiles = (int)n_tiles_ll;                              // partial sums per design point
+    const long long total = pack ? (n_d + pack_k - 1) / pack_k : n_d * n_tiles_ll;   // tiles = CTAs' work items
+    int rc = ensure_partial(m, (size_t)(n_d * n_tiles_ll));
     if (rc) return rc;
 
     LaunchArgs la{};
@@ -748,7 +763,7 @@ int eval_impl(void* handle, const double* d, long long n_d, const double* theta,
 
     const long long max_ctas = (long long)m->num_sms * m->blocks_per_sm;
     const int grid = (int)(total < max_ctas ? total : max_ctas);
-    FeasFn fn = traj ? traj_for(image_maxns(img), img.spt) : feas_for(image_maxns(img), img.spt);
+    FeasFn fn = traj ? traj_for(image_maxns(img), img.spt) : (pack ? pack_for(image_maxns(img), img.spt) : feas_for(image_maxns(img), img.spt));
     // several models may share one template instantiation: (re)assert this model's smem size and
     // (re)load its point tape into the constant bank (stream ordered)
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));

@@ -223,3 +223,27 @@ def test_far_outside_the_design_box_same_failures_same_values(kw):
     assert np.all(np.abs(g - go)[ok] <= 1e-10 * np.maximum(np.abs(go)[ok], G_SCALE))
     assert np.all(ind[bad_g] == -1.0)                          # a failed state solve is reported infeasible
     np.testing.assert_allclose(P, Po, atol=1e-12)
+
+
+@pytest.mark.parametrize("n_d,n_t", [(301, 1), (13, 50), (257, 2), (40, 64), (7, 128)])
+def test_small_theta_sets_share_tiles(eng2, eng4, n_d, n_t):
+    """n_t <= half a tile: several design points per tile (the PACK instantiation), every output and control mode."""
+    rng = np.random.default_rng(7 * n_d + n_t)
+    p = K.theta_samples(n_t, seed=3 + n_t)
+    w = rng.uniform(0.5, 1.5, n_t); w /= w.sum()
+    d2 = np.stack([rng.uniform(250, 350, n_d), rng.uniform(250, 300, n_d)], axis=1)
+    vm = tape_vm.TapeVM(models.kinetics("twostage").lower().blob)
+    for z in (rng.uniform(0, 2.5, (n_d, 8)), rng.uniform(0, 2.5, (n_d, n_t, 8))):
+        g, ind, P = eng2.eval_host(d2, p, w, z=z, want_g=True, want_ind=True)
+        r = vm.evaluate(d2, p, z=z, tol=1e-13)
+        _assert_g_close(g, r["g"])
+        _assert_class_equal(ind, r["g"])
+        np.testing.assert_allclose(P, ((r["g"] <= 0).all(-1) * w).sum(1), atol=1e-12)
+    d4 = np.concatenate([d2, np.stack([rng.uniform(1500, 2500, n_d), rng.uniform(0, 2.5, n_d)], axis=1)], axis=1)
+    g, ind, P = eng4.eval_host(d4, p, w, want_g=True, want_ind=True)
+    go, Po, _ = cbind.kinetics_grid(d4, p, w, tol=1e-13)
+    _assert_g_close(g, go)
+    _assert_class_equal(ind, go)
+    np.testing.assert_allclose(P, Po, atol=1e-12)
+    # the fused P-only call (what the managers and the nested-sampling driver use)
+    np.testing.assert_array_equal(eng4.eval_host(d4, p, w)[2], P)
