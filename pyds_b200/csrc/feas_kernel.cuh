@@ -394,6 +394,35 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
 // parameter / control values or functions of earlier blocks' states, fixed during this solve).  The whole
 // Newton loop runs here, in registers: no dispatch, no register-file traffic until the converged points are
 // stored.  Same equations, start and stop rule as NB + point ops + NS.
+#ifndef PYDSB_POLY1_ZFORM
+// state = the point values x_j themselves; the linear part uses all four differentiation weights (one more FMA per
+// point than the increment form below, but no x_s + z_j additions: 3 fewer FP64 instructions per iteration, +2.5 % on C3)
+#define POLY1_STATE_DECL double xq[SPT][3];
+#define POLY1_STATE_INIT xq[s][0] = xq[s][1] = xq[s][2] = xsv.v[s];
+#define POLY1_X_AND_LIN                                                                                         \
+    const double x = xq[s][jj];                                                                                 \
+    double lin = img.adot[jj + 1] * xsv.v[s];                                                                   \
+    lin = fma(img.adot[4 + jj + 1], xq[s][0], lin);                                                             \
+    lin = fma(img.adot[8 + jj + 1], xq[s][1], lin);                                                             \
+    lin = fma(img.adot[12 + jj + 1], xq[s][2], lin);
+#define POLY1_UPDATE                                                                                            \
+    xq[s][kk] += r[kk];                                                                                         \
+    const double x = xq[s][kk];
+#define POLY1_X_OUT xq[s][kk]
+#else
+// state = the increments z_j = x_j - x_s (the rows of the differentiation matrix sum to zero)
+#define POLY1_STATE_DECL double z[SPT][3];
+#define POLY1_STATE_INIT z[s][0] = z[s][1] = z[s][2] = 0.0;
+#define POLY1_X_AND_LIN                                                                                         \
+    const double x = xsv.v[s] + z[s][jj];                                                                       \
+    double lin = img.adot[4 + jj + 1] * z[s][0];                                                                \
+    lin = fma(img.adot[8 + jj + 1], z[s][1], lin);                                                              \
+    lin = fma(img.adot[12 + jj + 1], z[s][2], lin);
+#define POLY1_UPDATE                                                                                            \
+    z[s][kk] += r[kk];                                                                                          \
+    const double x = xsv.v[s] + z[s][kk];
+#define POLY1_X_OUT (xsv.v[s] + z[s][kk])
+#endif
 #define X_POLY1_CASE                                                                                            \
     {                                                                                                           \
         const uint4 w1 = c_prog[pcw - 1];                                                                       \
@@ -406,9 +435,9 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
             c2v[p] = LDV(w1.z + p * st2);                                                                       \
         }                                                                                                       \
         const VecT xsv = LDVP(w0.y, 2);                                                                         \
-        double z[SPT][3];                                                                                       \
+        POLY1_STATE_DECL                                                                                        \
         _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                                       \
-            z[s][0] = z[s][1] = z[s][2] = 0.0;                                                                  \
+            POLY1_STATE_INIT                                                                                    \
             conv[s] = false;                                                                                    \
             s_prev[s] = 0.0;                                                                                    \
         }                                                                                                       \
@@ -418,13 +447,10 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 if (!conv[s]) my_acc[s] += ((1ull << 40) | w0.z);                                               \
                 double M[3][3], r[3];                                                                           \
                 _Pragma("unroll") for (int jj = 0; jj < 3; ++jj) {                                              \
-                    const double x = xsv.v[s] + z[s][jj];                                                       \
+                    POLY1_X_AND_LIN                                                                             \
                     const double t = fma(c2v[jj].v[s], x, c1v[jj].v[s]);                                        \
                     const double fx = fma(t, x, c0v[jj].v[s]);                                                  \
                     const double jx = fma(c2v[jj].v[s], x, t);                                                  \
-                    double lin = img.adot[4 + jj + 1] * z[s][0];                                                \
-                    lin = fma(img.adot[8 + jj + 1], z[s][1], lin);                                              \
-                    lin = fma(img.adot[12 + jj + 1], z[s][2], lin);                                             \
                     r[jj] = fma(h, fx, -lin);                                                                   \
                     _Pragma("unroll") for (int kk = 0; kk < 3; ++kk) M[jj][kk] = img.adot[4 * (kk + 1) + jj + 1]; \
                     M[jj][jj] = fma(-h, jx, M[jj][jj]);                                                         \
@@ -432,8 +458,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 lu_solve_inplace<3>(M, r);                                                                      \
                 double sq = 0.0, sc = 0.0;                                                                      \
                 _Pragma("unroll") for (int kk = 0; kk < 3; ++kk) {                                              \
-                    z[s][kk] += r[kk];                                                                          \
-                    const double x = xsv.v[s] + z[s][kk];                                                       \
+                    POLY1_UPDATE                                                                                \
                     sq = fma(r[kk], r[kk], sq);                                                                 \
                     sc = fma(x, x, sc);                                                                         \
                 }                                                                                               \
@@ -451,7 +476,7 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
         VecT xo[3];                                                                                             \
         _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                                       \
             failed[s] = failed[s] | !conv[s];                                                                   \
-            _Pragma("unroll") for (int kk = 0; kk < 3; ++kk) xo[kk].v[s] = xsv.v[s] + z[s][kk];                 \
+            _Pragma("unroll") for (int kk = 0; kk < 3; ++kk) xo[kk].v[s] = POLY1_X_OUT;                         \
         }                                                                                                       \
         STVP(w0.y, 0, xo[0]); STVP(w0.y, 1, xo[1]); STVP(w0.y, 2, xo[2]);                                       \
     }                                                                                                           \
