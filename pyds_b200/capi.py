@@ -371,6 +371,7 @@ def assemble(blob: bytes):
         elif name in ("NS2", "NS2L"): length = ns_len(2)
         elif name in ("NS3", "NS3L"): length = ns_len(3)
         elif name == "ELEM_END": length = 1 + 2 * int(words[4 * pcw + 2])
+        elif name == "POLY1": length = 3 if int(words[4 * pcw + 7]) & 16 else 2      # c0 = narrow * wide^2: a third word
         else: length = 2
         ops.append((pcw, name, words[4 * pcw:4 * (pcw + length)].copy()))
         pcw += length

@@ -86,7 +86,24 @@ public:
                     off[k] = pb.present[k] ? pb.off[k] : g.zero_off;
                     if (pb.present[k] && pb.wide[k]) flags |= 1u << k;
                 }
-                emit(X_POLY1, g.blk_x_o[b][0][0], in.blk_flops[b], (uint32_t)g.max_it, off[0], off[1], off[2], flags);
+                // c0 = narrow * wide^2 computed by the block's own coefficient tape (the MULSQ just emitted) and read by
+                // nothing else: POLY1 forms it in registers (flag 16, a third word {narrow, wide}) -- one dispatch and a
+                // store / reload of three values less per element (second-order rate k * c^2 feeding the next species)
+                bool fused = false;
+                const size_t nw = words.size();
+#ifndef PYDSB_NO_C0SQ                                         /* development switch: A/B of the fusion */
+                if (pb.present[0] && pb.wide[0] && in.blk_npt[b] >= 2 && nw >= 8 && words[nw - 8] == (uint32_t)X_MULSQ_NW &&
+                    words[nw - 7] == pb.off[0] && !reads_units_elsewhere(in, pb.off[0] / (US * (uint32_t)in.spt), pos - 2, b)) {
+                    const uint32_t a_off = words[nw - 6], b_off = words[nw - 5];
+                    words.resize(nw - 8);
+                    emit(X_POLY1, g.blk_x_o[b][0][0], in.blk_flops[b], (uint32_t)g.max_it, 0u, off[1], off[2], flags | 16u);
+                    const uint32_t w2[4] = {a_off, b_off, 0u, 0u};
+                    words.insert(words.end(), w2, w2 + 4);
+                    fused = true;
+                }
+#endif
+                if (!fused)
+                    emit(X_POLY1, g.blk_x_o[b][0][0], in.blk_flops[b], (uint32_t)g.max_it, off[0], off[1], off[2], flags);
                 continue;
             }
             emit(nb_code[nsb - 1], g.blk_x_o[b][0][0], nsb > 1 ? g.blk_x_o[b][1][0] : 0u, nsb > 2 ? g.blk_x_o[b][2][0] : 0u);
@@ -197,6 +214,44 @@ private:
         err = m;
         return false;
     }
+    // Is any of the wide value's three register-file units [unit, unit + 2] read by anything but the two point-tape ops
+    // at skip, skip + 1 (the SQR / MUL pair that produces it) and coefficient 0 of block own_block?  Readers: every
+    // point-tape op (all blocks + the quadrature tape), the quadrature integrand table, the other polynomial
+    // coefficients and the f / J tables of the generic blocks.
+    bool reads_units_elsewhere(const AsmInput& in, unsigned unit, int skip, int own_block) const
+    {
+        auto hit = [&](unsigned ref) { return !(ref & REF_CONST) && (ref & REF_MASK) + ((ref & REF_WIDE) ? 2u : 0u) >= unit && (ref & REF_MASK) <= unit + 2u; };
+        int total = in.q_npt;
+        for (int b = 0; b < in.n_blocks; ++b) total += in.blk_npt[b];
+        for (int j = 0; j < total; ++j) {
+            if (j == skip || j == skip + 1) continue;
+            unsigned op, refs[4];
+            split(in.pt[j], op, refs);
+            for (int k = 1; k <= arity(op); ++k)
+                if (hit(refs[k])) return true;
+        }
+        for (int q = 0; q < in.nq; ++q)
+            if (in.fq_refs[q] != REF_NONE && hit(in.fq_refs[q])) return true;
+        const uint32_t usp = US * (uint32_t)in.spt;
+        auto hit_off = [&](uint32_t off, bool wide) { return off / usp + (wide ? 2u : 0u) >= unit && off / usp <= unit + 2u; };
+        for (int b = 0; b < in.n_blocks; ++b) {
+            if (in.poly[b].is_poly) {
+                for (int k = 0; k < 3; ++k)
+                    if (in.poly[b].present[k] && !(b == own_block && k == 0) && hit_off(in.poly[b].off[k], in.poly[b].wide[k])) return true;
+            } else {
+                const ExecImage& g = *in.img;
+                for (int n = 0; n < in.blk_ns[b]; ++n)
+                    for (int p3 = 0; p3 < 3; ++p3)
+                        if (hit_off(g.blk_f_o[b][n][p3], false)) return true;
+                for (int i = 0; i < in.blk_ns[b] * in.blk_ns[b]; ++i)
+                    if ((g.blk_jmask[b] >> i) & 1u)
+                        for (int p3 = 0; p3 < 3; ++p3)
+                            if (hit_off(g.blk_j_o[b][i][p3], false)) return true;
+            }
+        }
+        return false;
+    }
+
     void emit(uint32_t x, uint32_t y = 0, uint32_t z = 0, uint32_t w = 0, uint32_t x1 = 0, uint32_t y1 = 0, uint32_t z1 = 0,
               uint32_t w1 = 0)
     {

@@ -430,9 +430,19 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
         const bool linear = (w1.w & 8u) != 0;                                                                   \
         VecT c0v[3], c1v[3], c2v[3];                                                                            \
         _Pragma("unroll") for (unsigned p = 0; p < 3; ++p) {                                                    \
-            c0v[p] = LDV(w1.x + p * st0);                                                                       \
             c1v[p] = LDV(w1.y + p * st1);                                                                       \
             c2v[p] = LDV(w1.z + p * st2);                                                                       \
+        }                                                                                                       \
+        if (w1.w & 16u) {                          /* c0 = narrow * wide^2, operands in a third word */         \
+            const uint4 w2 = c_prog[pcw];                                                                       \
+            pcw += 1;                                                                                           \
+            const VecT ka = LDV(w2.x);                                                                          \
+            _Pragma("unroll") for (unsigned p = 0; p < 3; ++p) {                                                \
+                const VecT cb = LDV(w2.y + p * USP);                                                            \
+                _Pragma("unroll") for (int s = 0; s < SPT; ++s) c0v[p].v[s] = ka.v[s] * cb.v[s] * cb.v[s];      \
+            }                                                                                                   \
+        } else {                                                                                                \
+            _Pragma("unroll") for (unsigned p = 0; p < 3; ++p) c0v[p] = LDV(w1.x + p * st0);                    \
         }                                                                                                       \
         const VecT xsv = LDVP(w0.y, 2);                                                                         \
         POLY1_STATE_DECL                                                                                        \

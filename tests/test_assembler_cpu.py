@@ -31,14 +31,17 @@ def test_polynomial_blocks_program_c3():
     a, b = _elem_loop(ops)
     # Fbar is one control entry for every element: its load and the elem tape are hoisted out of the loop
     assert "LDCTRL" in names[:a] and "LDCTRL" not in names[a:b]
-    # k * cA^2 is one fused op; the cC integrand k * cB is folded into its ELEM_END entry as a scale factor
-    assert names[a:b + 1] == ["POLY1", "MULSQ_NW", "POLY1", "ELEM_END"]
+    # k * cA^2 (the coefficient c0 of the cB block) is formed inside its POLY1 (flag 16, a third word with the narrow and
+    # the wide operand); the cC integrand k * cB is folded into its ELEM_END entry as a scale factor: 3 dispatches
+    assert names[a:b + 1] == ["POLY1", "POLY1", "ELEM_END"]
     # ELEM_END advances the two quadratures (u and cC) itself: two uint4 per entry, the second with a scale
     assert int(ops[b][2][2]) == 2 and len(ops[b][2]) == 4 * (1 + 2 * 2)
     assert [int(ops[b][2][4 + 8 * q + 5]) for q in range(2)] == [0, 1]
     # POLY1 of cA: nonlinear, c1 absent (-> zero slot); of cB: linear (flag bit 3), c0 wide (flag bit 0)
     pa, pb = [o for o in ops if o[1] == "POLY1"]
     assert int(pa[2][7]) & 8 == 0 and int(pb[2][7]) & 8 == 8 and int(pb[2][7]) & 1 == 1
+    assert int(pa[2][7]) & 16 == 0 and len(pa[2]) == 8 and int(pb[2][7]) & 16 == 16 and len(pb[2]) == 12
+    assert int(pb[2][9]) == int(pa[2][1])                      # the wide operand is the cA block's state (its x offset)
     assert int(pa[2][3]) == lm.newton_max_it and int(pa[2][2]) == lm.block_flops[0]
     # program length in 16-byte words == position after END
     assert info["program_length"] == ops[-1][0] + 2
