@@ -245,3 +245,31 @@ def test_proposal_samplers_draw_from_the_same_distribution():
     np.testing.assert_allclose(a.mean(axis=0), b.mean(axis=0), atol=4e-3)
     np.testing.assert_allclose(np.cov(a.T), np.cov(b.T), atol=2e-3)
     np.testing.assert_allclose(c.mean(axis=0), a.mean(axis=0), atol=1e-2)
+
+
+def test_ns_driver_native_and_python_updates_follow_the_same_trajectory():
+    """The whole driver with the native host passes against the pure-numpy / Python-loop version: same seeds, same
+    constraint function -> the same live set after every schedule level (growth phases included), up to round-off of
+    the ellipsoid statistics."""
+    def g(d, p):
+        r = np.hypot(d[:, 0] - 0.4, (d[:, 1] - 0.6) * 1.5)
+        lvl = np.clip(np.round((0.6 - r) * 10) / 4, 0.0, 1.0)            # tie-heavy probabilities 0, .25, .5, .75, 1
+        return [np.where(np.arange(len(p))[:, None] < lv * len(p), 0.0, -1.0) for lv in lvl]
+
+    def run(native):
+        form = {"activity_type": "ds", "problem": {"parameters_best_estimate": [0.0],
+                                                  "parameters_samples": [{"c": [float(k)], "w": 0.25} for k in range(4)],
+                                                  "target_reliability": 0.75, "design_variables": [{"a": [0, 1]}, {"b": [0, 1]}]},
+                "solver": {"name": "ds-ns", "settings": {"efp_evaluation": {"constraints_func_ptr": g},
+                                                         "points_schedule": [(0.0, 30, 6), (0.25, 45, 9), (0.5, 60, 12)],
+                                                         "stop_criteria": [{"inside_fraction": 1.0}]},
+                           "algorithms": {"sampling": {"settings": {"prng_seed": 7, "stop_criteria": [{"max_iterations": 400}]}}}}}
+        drv = ns.DEUS(form)
+        drv.native_update = native
+        return drv.solve()
+
+    a, b = run(True), run(False)
+    assert a["iterations"] == b["iterations"] and a["evaluations"] == b["evaluations"]
+    assert a["inside_fraction"] == 1.0 and len(a["live_points"]) == len(b["live_points"]) >= 45
+    np.testing.assert_array_equal(a["live_efp"], b["live_efp"])
+    np.testing.assert_allclose(a["live_points"], b["live_points"], rtol=0, atol=1e-9)
