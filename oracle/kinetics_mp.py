@@ -11,7 +11,8 @@ import mpmath as mp
 from .radau import radau_adot, radau_weights
 
 
-def g_values_mp(tf, T, E1, E2, k1, k2, F, cA0=2000, pB=100, pA=20, nfe=8, dps=50):
+def g_values_mp(tf, T, E1, E2, k1, k2, F, cA0=2000, pB=100, pA=20, nfe=8, dps=50, return_traj=False):
+    """``return_traj``: also the state profiles at tau = 0 and the collocation points, rows [cA, cB, cC, u]."""
     with mp.workdps(dps):
         A = radau_adot(3, dps)
         b = radau_weights(3, dps)
@@ -22,6 +23,8 @@ def g_values_mp(tf, T, E1, E2, k1, k2, F, cA0=2000, pB=100, pA=20, nfe=8, dps=50
         h = mp.mpf(1) / nfe
         x0 = [cA0, mp.mpf(0), mp.mpf(0)]
         u = mp.mpf(0)
+        traj = [[cA0, mp.mpf(0), mp.mpf(0), mp.mpf(0)]]
+        tau = [(4 - mp.sqrt(6)) / 10, (4 + mp.sqrt(6)) / 10, mp.mpf(1)]
 
         def f(c, Fe):
             r1 = K1 * c[0] ** 2
@@ -50,9 +53,13 @@ def g_values_mp(tf, T, E1, E2, k1, k2, F, cA0=2000, pB=100, pA=20, nfe=8, dps=50
                         X[j][n] += dX[3 * j + n]
                 if max(abs(v) for v in dX) < mp.mpf(10) ** (-(dps - 10)):
                     break
+            for j in range(3):                       # u' = F_in / t_f with a piecewise-constant feed: linear in the element
+                traj.append([X[j][0], X[j][1], X[j][2], u + h * tau[j] * F[e] / tf])
             u += h * sum(b) * F[e] / tf
             x0 = list(X[2])
         cA, cB, cC = x0
         g1 = mp.mpf("0.8") - (cB + mp.mpf("1e-2")) / (cA + cB + cC + mp.mpf("1e-2"))
         g2 = -(pB * cB - pA * (cA0 + u * tf) - 128 * (tf + 30))
+        if return_traj:
+            return g1, g2, x0, traj
         return g1, g2, x0

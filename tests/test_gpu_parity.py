@@ -247,3 +247,16 @@ def test_small_theta_sets_share_tiles(eng2, eng4, n_d, n_t):
     np.testing.assert_allclose(P, Po, atol=1e-12)
     # the fused P-only call (what the managers and the nested-sampling driver use)
     np.testing.assert_array_equal(eng4.eval_host(d4, p, w)[2], P)
+
+
+def test_state_solve_against_the_mpmath_golden_profiles(golden_dir, eng2):
+    """pydsb_state_solve -- dynamic states, the cC quadrature at the inner points (integration-matrix rows) and u --
+    against 50-digit arithmetic at tau = 0 and the 24 collocation points."""
+    lm = models.kinetics("twostage").lower()
+    names = lm.dyn_states + lm.quad_states
+    for c in json.load(open(os.path.join(golden_dir, "kinetics_traj_mp.json")))["cases"]:
+        ref = np.array(c["traj"])
+        x, failed = eng2.state_solve(np.array(c["d"])[None, :], np.array(c["theta"])[None, :], z=np.array(c["F"]))
+        assert not failed.any() and x.shape == (1, 1, 25, 4)
+        for k, nm in enumerate(c["columns"]):
+            np.testing.assert_allclose(x[0, 0, :, names.index(nm)], ref[:, k], rtol=1e-10, atol=1e-9, err_msg=nm)

@@ -133,3 +133,23 @@ def test_indicator_rule_and_negative_zero():
     yy, ind = K.indicator(np.array([-0.1, 0.05, -0.1]), np.array([-5.0, -5.0, 3.0]))
     np.testing.assert_array_equal(ind, [0.0, 1.0, 1.0])
     np.testing.assert_allclose(yy, [0.0, 0.05 / 1e2, 3.0 / 1e7])
+
+
+def test_state_profiles_against_the_mpmath_golden(golden_dir):
+    """Both fp64 restatements (the dense 9-unknown solve and the tape interpreter with cC / u as quadratures) against
+    the 50-digit profiles at tau = 0 and the 24 collocation points."""
+    from oracle import tape_vm
+    from pyds_b200 import models
+    lm = models.kinetics("twostage").lower()
+    vm = tape_vm.TapeVM(lm.blob)
+    names = lm.dyn_states + lm.quad_states
+    for c in _load(golden_dir, "kinetics_traj_mp.json")["cases"]:
+        ref = np.array(c["traj"])                                   # (25, 4): cA, cB, cC, u
+        assert ref.shape == (25, 4) and c["columns"] == ["cA", "cB", "cC", "u"]
+        d, th, F = np.array(c["d"]), np.array(c["theta"]), np.array(c["F"])
+        traj = K.solve_states(d[0], d[1], *th, F=F, return_traj=True)[3][0]
+        np.testing.assert_allclose(traj, ref[:, :3], rtol=1e-11, atol=1e-9)
+        tv = vm.evaluate(d[None, :], th[None, :], z=F, return_traj=True)["traj"][0, 0]
+        for k, nm in enumerate(lm.dyn_states):
+            np.testing.assert_allclose(tv[:, k], ref[:, ["cA", "cB", "cC", "u"].index(nm)], rtol=1e-11, atol=1e-9)
+        assert set(names) == {"cA", "cB", "cC", "u"}

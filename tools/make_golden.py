@@ -60,3 +60,14 @@ for _ in range(12):
 json.dump({"source": "oracle/kinetics_mp.py (mpmath, 50 digits), equations run_twostage.py:49-65, Radau 8x3",
            "cases": cases}, open(os.path.join(out_dir, "kinetics_g_mp.json"), "w"), indent=1)
 print(len(cases), "cases written")
+
+# state profiles at the 25 collocation times (pins pydsb_state_solve and the oracles' trajectories)
+traj_cases = []
+for (tf, T), F, th in (((300.0, 275.0), profiles[3], np.array(K.P_BEST)), ((350.0, 282.5), profiles[1], p[0]),
+                       ((275.0, 292.0), profiles[2], p[17]), ((340.0, 285.0), profiles[0], p[5])):
+    g1, g2, xe, traj = MP.g_values_mp(tf, T, *th, F, return_traj=True)
+    traj_cases.append({"d": [tf, T], "theta": th.tolist(), "F": F.tolist(), "columns": ["cA", "cB", "cC", "u"],
+                       "traj": [[float(v) for v in row] for row in traj]})
+json.dump({"source": "oracle/kinetics_mp.py (mpmath, 50 digits): states at tau = 0 and the 24 Radau points, 8 x 3",
+           "cases": traj_cases}, open(os.path.join(out_dir, "kinetics_traj_mp.json"), "w"), indent=1)
+print(len(traj_cases), "trajectory cases written")
