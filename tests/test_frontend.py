@@ -273,3 +273,30 @@ def test_ns_driver_native_and_python_updates_follow_the_same_trajectory():
     assert a["inside_fraction"] == 1.0 and len(a["live_points"]) == len(b["live_points"]) >= 45
     np.testing.assert_array_equal(a["live_efp"], b["live_efp"])
     np.testing.assert_allclose(a["live_points"], b["live_points"], rtol=0, atol=1e-9)
+
+
+def test_output_record_value_dicts_have_the_reference_shape():
+    """``Solver._scenario_values``: what ``utils.parse_value(scen, 'c')`` returns in the reference for an indexed Var over
+    (species, t) -- {('A', t): value} with t the discretised ContinuousSet points rounded to 6 decimals -- built here
+    from a trajectory array; no device needed."""
+    import types
+    from pyds_b200.collocation import radau_tables
+    from pyds_b200.solver import Solver
+    tau = radau_tables(3)[0][1:]
+    tgrid = np.concatenate([[0.0], ((np.arange(8)[:, None] + tau[None, :]) / 8).reshape(-1)])
+    lowered = types.SimpleNamespace(dyn_states=["c['A']", "c['B']"], quad_states=["u", "c['C']"])
+    dae_model = types.SimpleNamespace(state_keys={"u": ("u", (), (0, 1)), "c['A']": ("c", ("A",), (0, 1)),
+                                                  "c['B']": ("c", ("B",), (0, 1)), "c['C']": ("c", ("C",), (0, 2))})
+    parent = types.SimpleNamespace(simulator=types.SimpleNamespace(lowered=lowered, dae_model=dae_model),
+                                   output_map={1: ["c", "u", "nope"]})
+    s = Solver.__new__(Solver)
+    s.parent = parent
+    s._time = tgrid
+    s._traj = np.arange(2 * 3 * 25 * 4, dtype=np.float64).reshape(2, 3, 25, 4)
+    v = s._scenario_values(1, 2)
+    assert set(v) == {"c", "u", "nope"} and v["nope"] is None
+    assert len(v["c"]) == 75 and len(v["u"]) == 25
+    assert v["c"][("A", 0.0)] == s._traj[1, 2, 0, 0] and v["c"][("B", 1.0)] == s._traj[1, 2, 24, 1]
+    assert v["c"][("A", round(0.155051 / 8, 6))] == s._traj[1, 2, 1, 0]
+    assert v["c"][("C", 2.0)] == s._traj[1, 2, 24, 3]                # a state on a [0, 2] time set keeps its own bounds
+    assert v["u"][0.125] == s._traj[1, 2, 3, 2]                      # scalar-indexed Var: keyed by t alone
