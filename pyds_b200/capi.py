@@ -350,7 +350,7 @@ XCODES = ["POLY1", "MUL_NW", "NS1", "ELEM_END",
           "SUB_WW", "SUB_NW", "SUB_WN", "DIV_NW", "DIV_WN", "DIV_WW",
           "NEG_W", "RCP_W", "ABS_W", "MOV_W", "BC_N", "MIN_NW", "MIN_WW", "MAX_NW", "MAX_WW", "COLD_W",
           "FMS1", "FNMA1", "SUB1", "DIV1", "SQR1", "NEG1", "RCP1", "ABS1", "MOV1", "MIN1", "MAX1", "COLD1",
-          "INIT", "LDCTRL", "NB2", "NB3", "NS3", "NS2L", "NS3L", "XEND", "END"]
+          "INIT", "LDCTRL", "NB2", "NB3", "NS3", "NS2L", "NS3L", "XEND", "END", "PCHAIN", "FMAG"]
 
 
 def assemble(blob: bytes):
@@ -358,10 +358,10 @@ def assemble(blob: bytes):
     ``(ops, info)``: ``ops`` is the list of ``(pcw, name, words)`` in program order, ``info`` the layout figures."""
     L = load()
     n = ctypes.c_size_t()
-    info = (ctypes.c_longlong * 4)()
-    _check(L.pydsb_assemble(blob, len(blob), None, 0, ctypes.byref(n), info, 4))
+    info = (ctypes.c_longlong * 8)()
+    _check(L.pydsb_assemble(blob, len(blob), None, 0, ctypes.byref(n), info, 8))
     words = np.zeros(n.value, dtype=np.uint32)
-    _check(L.pydsb_assemble(blob, len(blob), words.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n), info, 4))
+    _check(L.pydsb_assemble(blob, len(blob), words.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n), info, 8))
     ns_len = lambda k: 1 + (k + 3 * k + 3 * k * k + 3) // 4
     ops, pcw = [], 0
     while 4 * pcw < len(words):
@@ -372,10 +372,12 @@ def assemble(blob: bytes):
         elif name in ("NS3", "NS3L"): length = ns_len(3)
         elif name == "ELEM_END": length = 1 + 2 * int(words[4 * pcw + 2])
         elif name == "POLY1": length = 3 if int(words[4 * pcw + 7]) & 16 else 2      # c0 = narrow * wide^2: a third word
+        elif name == "PCHAIN": length = 2 + 3 * (int(words[4 * pcw + 1]) & 0xFF) + ((int(words[4 * pcw + 1]) >> 8) & 0xFF)
         else: length = 2
         ops.append((pcw, name, words[4 * pcw:4 * (pcw + length)].copy()))
         pcw += length
-    return ops, dict(zip(("scenarios_per_thread", "units", "smem_bytes", "program_length"), (int(v) for v in info)))
+    return ops, dict(zip(("scenarios_per_thread", "units", "smem_bytes", "program_length", "chain_blocks", "chain_shape_sb",
+                          "chain_shape_sq", "chain_shape_registered"), (int(v) for v in info)))
 
 
 def dfma_peak(device: int = 0, repeats: int = 5):

@@ -33,32 +33,49 @@ struct AsmInput {
     int spt;                                   // scenarios per thread: slot stride = spt * US bytes
     const PolyBlock* poly;                     // [n_blocks]
     const ExecImage* img;                      // resolved per-block offsets: blk_x_o, blk_f_o, blk_j_o, blk_jmask
+    bool allow_chain = false;                  // fuse the element loop into one X_PCHAIN when the model has that shape
 };
 
 class Assembler {
 public:
     std::vector<uint32_t> words;               // 8 per instruction
     std::string err;
+    int chain_nb = 0;                          // blocks of the fused chain (0: the element loop is interpreted)
 
     int pc() const { return (int)(words.size() / 4); }      // uint4 index of the next instruction
 
     bool assemble(const AsmInput& in)
     {
         in_ = &in;
-        for (int i = 0; i < in.n_pro; ++i)
-            if (!scalar_op(in.pro[i])) return false;
-        emit(X_INIT);
         // controls that map every finite element to the same z entry (fixed profiles, constant-in-time controls):
         // the control loads and the elem tape are element invariant and run once, before the loop
         bool invariant = true;
         for (int e = 1; e < in.nfe; ++e)
             for (int c = 0; c < in.nce; ++c) invariant = invariant && in.cmap[e * in.nce + c] == in.cmap[c];
+        std::vector<uint32_t> chain;
+        int nb = 0;
+        chain_mode_ = in.allow_chain && try_chain(in, invariant, chain, nb);
+        for (int i = 0; i < in.n_pro; ++i)
+            if (!scalar_op(in.pro[i])) return false;
+        emit(X_INIT);
         auto ctrl_and_elem = [&]() -> bool {
             for (int c = 0; c < in.nce; ++c) emit(X_LDCTRL, (uint32_t)(in.ctrl_slot + c) * US * (uint32_t)in.spt, (uint32_t)c);
             for (int i = 0; i < in.n_elem; ++i)
                 if (!scalar_op(in.elem[i])) return false;
             return true;
         };
+        if (chain_mode_) {
+            // scalar ops | PCHAIN | XEND | scalar ops | END  (the shape feas_kernel<.., CHAIN> relies on)
+            if (invariant && !ctrl_and_elem()) return false;
+            words.insert(words.end(), chain.begin(), chain.end());
+            chain_nb = nb;
+            emit(X_XEND);
+            for (int i = 0; i < in.n_g; ++i)
+                if (!scalar_op(in.g[i])) return false;
+            emit(X_END);
+            if (pc() > 2 * MAX_PROG - 2) return fail("program longer than the constant-bank window");
+            return true;
+        }
         if (invariant && !ctrl_and_elem()) return false;
         const int l_elem = pc();
         if (!invariant && !ctrl_and_elem()) return false;
@@ -208,6 +225,189 @@ public:
 
 private:
     const AsmInput* in_ = nullptr;
+    bool chain_mode_ = false;                  // chain programs: FMAG scalar ops, SPT-wide constant pool
+
+    // ---- fused polynomial chain (poly_chain.cuh) ----------------------------------------------------------------
+    struct Term {
+        bool present = false, has_n = false, has_ctrl = false;
+        uint32_t n_off = 0, ctrl = 0, p = 0, src = 0;
+        uint32_t meta() const { return present ? chain_meta(has_n, has_ctrl, ctrl, p, src) : 0u; }
+    };
+    struct ElemVal {                           // value of the elem tape:  (narrow slot a, or 1) * control c
+        unsigned dst;
+        bool has_a;
+        unsigned a;
+        unsigned c;
+    };
+
+    // Is `ref` the wide reference of a dynamic state's collocation points?  -> the block that owns the state
+    static int state_block(const AsmInput& in, unsigned ref)
+    {
+        if ((ref & REF_CONST) || !(ref & REF_WIDE)) return -1;
+        const ExecImage& g = *in.img;
+        const uint32_t off = (ref & REF_MASK) * US * (uint32_t)in.spt;
+        for (int b = 0; b < in.n_blocks; ++b)
+            if (in.blk_ns[b] == 1 && g.blk_x_o[b][0][0] == off) return b;
+        return -1;
+    }
+
+    // narrow factor: a plain persistent slot, or (controls that differ between the elements) a control value / an
+    // elem-tape value `a * control`
+    static bool narrow_factor(const AsmInput& in, unsigned ref, bool invariant, const std::vector<ElemVal>& ev, Term& t)
+    {
+        if (ref & (REF_CONST | REF_WIDE)) return false;
+        const unsigned idx = ref & REF_MASK;
+        if ((int)idx >= in.img->x_slot) return false;                  // not in the persistent region
+        const uint32_t usp = US * (uint32_t)in.spt;
+        if (!invariant) {
+            if ((int)idx >= in.ctrl_slot && (int)idx < in.ctrl_slot + in.nce) {
+                t.has_ctrl = true; t.ctrl = idx - (unsigned)in.ctrl_slot;
+                return true;
+            }
+            for (const ElemVal& v : ev)
+                if (v.dst == idx) {
+                    t.has_ctrl = true; t.ctrl = v.c;
+                    t.has_n = v.has_a; t.n_off = v.a * usp;
+                    return true;
+                }
+        }
+        t.has_n = true; t.n_off = idx * usp;
+        return true;
+    }
+
+    // A wide value of the tape `code[0..n)` as ONE term  narrow * (earlier state)^p: the state itself (p = 1), its SQR
+    // (p = 2), MUL narrow x state (p = 1) or MUL narrow x SQR(state) (p = 2).  Marks the tape ops it stands for.
+    static bool wide_term(const AsmInput& in, const uint64_t* code, int n, unsigned ref, int own_block, bool invariant,
+                          const std::vector<ElemVal>& ev, std::vector<char>& used, Term& t)
+    {
+        auto src_of = [&](unsigned r, unsigned& p) -> int {            // state, or SQR of a state computed by this tape
+            int b = state_block(in, r);
+            if (b >= 0) { p = 1; return b; }
+            for (int i = 0; i < n; ++i) {
+                unsigned op, refs[4];
+                split(code[i], op, refs);
+                if (op == OP_SQR && refs[0] == r) {
+                    b = state_block(in, refs[1]);
+                    if (b >= 0) { p = 2; used[i] = 1; return b; }
+                }
+            }
+            return -1;
+        };
+        unsigned p = 0;
+        int b = src_of(ref, p);
+        if (b < 0) {
+            for (int i = 0; i < n && b < 0; ++i) {
+                unsigned op, refs[4];
+                split(code[i], op, refs);
+                if (op != OP_MUL || refs[0] != ref) continue;
+                unsigned na = refs[1], wb = refs[2];
+                if ((na & REF_WIDE) && !(wb & REF_WIDE)) { const unsigned s = na; na = wb; wb = s; }
+                if ((na & (REF_WIDE | REF_CONST)) || !(wb & REF_WIDE)) return false;
+                if (!narrow_factor(in, na, invariant, ev, t)) return false;
+                b = src_of(wb, p);
+                if (b < 0) return false;
+                used[i] = 1;
+            }
+        }
+        if (b < 0 || b >= own_block) return false;                     // only states of earlier blocks
+        t.present = true; t.p = p; t.src = (uint32_t)b;
+        return true;
+    }
+
+    // The element loop as one X_PCHAIN instruction, or false when the model does not have that shape.
+    bool try_chain(const AsmInput& in, bool invariant, std::vector<uint32_t>& out, int& nb_out)
+    {
+        const ExecImage& g = *in.img;
+        const uint32_t usp = US * (uint32_t)in.spt;
+        if (in.n_blocks < 1 || in.n_blocks > CHAIN_MAXB) return false;
+        for (int b = 0; b < in.n_blocks; ++b)
+            if (!in.poly[b].is_poly || in.blk_ns[b] != 1) return false;
+        // controls that differ between the elements: every elem-tape value must be  narrow * control
+        std::vector<ElemVal> ev;
+        if (!invariant) {
+            for (int i = 0; i < in.n_elem; ++i) {
+                unsigned op, refs[4];
+                split(in.elem[i], op, refs);
+                if (op != OP_MUL) return false;
+                ElemVal v{refs[0] & REF_MASK, false, 0u, 0u};
+                int n_ctrl = 0;
+                for (int k = 1; k <= 2; ++k) {
+                    const unsigned r = refs[k];
+                    if (r & (REF_CONST | REF_WIDE)) return false;
+                    const int idx = (int)(r & REF_MASK);
+                    if (idx >= in.ctrl_slot && idx < in.ctrl_slot + in.nce) { v.c = (unsigned)(idx - in.ctrl_slot); ++n_ctrl; }
+                    else {
+                        for (const ElemVal& o : ev)
+                            if ((int)o.dst == idx) return false;       // product of elem values: not a single term
+                        if (idx >= g.x_slot) return false;
+                        v.has_a = true; v.a = (unsigned)idx;
+                    }
+                }
+                if (n_ctrl != 1) return false;
+                ev.push_back(v);
+            }
+        }
+        std::vector<uint32_t> blkw, quadw;
+        int pos = 0, scratch = g.x_slot;                               // units [x_slot, n_units) are dead during the loop
+        for (int b = 0; b < in.n_blocks; ++b) {
+            const PolyBlock& pb = in.poly[b];
+            const uint64_t* code = in.pt + pos;
+            const int n = in.blk_npt[b];
+            pos += n;
+            std::vector<char> used((size_t)n, 0);
+            Term t[3];
+            for (int k = 0; k < 3; ++k) {
+                if (!pb.present[k]) continue;
+                const unsigned ref = (pb.off[k] / usp) | (pb.wide[k] ? REF_WIDE : 0u);
+                if (pb.wide[k]) {
+                    if (k == 2 || !wide_term(in, code, n, ref, b, invariant, ev, used, t[k])) return false;
+                } else {
+                    if (!narrow_factor(in, ref, invariant, ev, t[k])) return false;
+                    t[k].present = true;
+                }
+            }
+            for (int i = 0; i < n; ++i)
+                if (!used[i]) return false;                            // a point op the terms do not account for
+            uint32_t kind = in.blk_lin[b] ? CHAIN_LINEAR : CHAIN_NEWTON, minv = 0, flops = in.blk_flops[b];
+            if (in.blk_lin[b] && (!t[1].present || (t[1].p == 0 && !t[1].has_ctrl)) && scratch + 9 <= in.n_units) {
+                kind = CHAIN_LINCONST; minv = (uint32_t)scratch * usp; scratch += 9; flops = CHAIN_LINCONST_FLOPS;
+            }
+            const uint32_t w[12] = {g.blk_x_o[b][0][0], flops, kind, minv, t[0].n_off, t[0].meta(), t[1].n_off, t[1].meta(),
+                                    t[2].n_off, t[2].meta(), 0u, 0u};
+            blkw.insert(blkw.end(), w, w + 12);
+        }
+        // quadrature integrands
+        {
+            const uint64_t* code = in.pt + pos;
+            const int n = in.q_npt;
+            std::vector<char> used((size_t)n, 0);
+            int nq = 0;
+            for (int q = 0; q < in.nq; ++q) {
+                const unsigned r = in.fq_refs[q];
+                if (r == REF_NONE) continue;
+                Term t;
+                if (r & REF_CONST) return false;
+                if (r & REF_WIDE) {
+                    if (!wide_term(in, code, n, r, in.n_blocks, invariant, ev, used, t)) return false;
+                } else {
+                    if (!narrow_factor(in, r, invariant, ev, t)) return false;
+                    t.present = true;
+                }
+                if (++nq > CHAIN_MAXQ) return false;
+                const uint32_t w[4] = {(uint32_t)(in.qe_slot + q) * usp, t.n_off, t.meta(), 0u};
+                quadw.insert(quadw.end(), w, w + 4);
+            }
+            for (int i = 0; i < n; ++i)
+                if (!used[i]) return false;
+            if (g.max_it < 1 || g.max_it > 0xFFFF) return false;
+            const uint32_t head[8] = {X_PCHAIN, (uint32_t)in.n_blocks | ((uint32_t)nq << 8), (uint32_t)g.max_it, 0u, 0u, 0u, 0u, 0u};
+            out.assign(head, head + 8);
+        }
+        out.insert(out.end(), blkw.begin(), blkw.end());
+        out.insert(out.end(), quadw.begin(), quadw.end());
+        nb_out = in.n_blocks;
+        return true;
+    }
 
     bool fail(const std::string& m)
     {
@@ -297,14 +497,43 @@ private:
         if (refs[0] & REF_CONST) return fail("scalar tape writes a constant");
         if (!check_slot(refs[0] & ~REF_WIDE)) return false;
         uint32_t off[3] = {0, 0, 0}, flags = 0;
+        // constant operands: relative to cpool - 1 (cpool[-1] = 0.0); chain programs: SPT-wide entries after the three
+        // specials 1.0, -0.0, 0.0
+        const uint32_t cw = chain_mode_ ? 8u * (uint32_t)in_->spt : 8u, cpre = chain_mode_ ? 3u : 1u;
         for (int k = 0; k < n; ++k) {
             const unsigned r = refs[k + 1];
             if (r & REF_CONST) {
                 flags |= 1u << k;
-                off[k] = (r == REF_NONE) ? 0u : ((r & REF_MASK) + 1u) * 8u;      // relative to cpool - 1 (cpool[-1] = 0.0)
+                off[k] = (r == REF_NONE) ? (cpre - 1u) * cw : ((r & REF_MASK) + cpre) * cw;
             } else {
                 if (!check_slot(r & ~REF_WIDE)) return false;
                 off[k] = slot_off(r);
+            }
+        }
+        if (chain_mode_) {
+            // every FMA-class op is FMAG: r = fma(+-a, b, +-c) with 1.0 / -0.0 from the pool (bit-identical results)
+            const uint32_t ONE = 0u, NEGZERO = cw;
+            struct Opnd { uint32_t off; bool cst; };
+            const Opnd A{off[0], (flags & 1u) != 0}, B{off[1], (flags & 2u) != 0}, C{off[2], (flags & 4u) != 0};
+            const Opnd one{ONE, true}, nz{NEGZERO, true};
+            Opnd a = A, b = one, c = nz;
+            bool neg_a = false, neg_c = false, fmag = true;
+            switch (op) {
+            case OP_MOV: break;
+            case OP_NEG: neg_a = true; break;
+            case OP_ADD: c = B; break;
+            case OP_SUB: a = B; neg_a = true; c = A; break;
+            case OP_MUL: b = B; break;
+            case OP_SQR: b = A; break;
+            case OP_FMA: b = B; c = C; break;
+            case OP_FMS: b = B; c = C; neg_c = true; break;
+            case OP_FNMA: b = B; c = C; neg_a = true; break;
+            default: fmag = false; break;
+            }
+            if (fmag) {
+                const uint32_t f = (a.cst ? 1u : 0u) | (b.cst ? 2u : 0u) | (c.cst ? 4u : 0u) | (neg_a ? 8u : 0u) | (neg_c ? 16u : 0u);
+                emit(X_FMAG, slot_off(refs[0]), a.off, b.off, c.off, f, 0u);
+                return true;
             }
         }
         if (n == 1) {                                     // cold unary ops are dispatched as binary: b = a

@@ -34,6 +34,7 @@
 // for tile k+1 is in flight while tile k is computed.
 #pragma once
 #include "xvm_ops.cuh"
+#include "poly_chain.cuh"
 
 namespace pydsb {
 
@@ -164,8 +165,14 @@ __device__ __forceinline__ void newton_step(const ExecImage& img, int at, unsign
 // PACK (small theta sets, n_t <= TILE / 2 -- the shipped scripts use 50 samples): a tile holds the whole theta set of
 // TILE / n_t consecutive design points instead of one design point's slice, so the lanes are not left idle; the
 // weighted indicator is summed per design point through shared memory in scenario order (deterministic).
-template <int MAXNS, int SPT, bool TRAJ = false, bool PACK = false>
-__global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))))
+// CHAIN (0, 2 or 3): the program's element loop is one X_PCHAIN instruction over at most CHAIN blocks (poly_chain.cuh);
+// such a program holds nothing but scalar ops, INIT, LDCTRL, PCHAIN, XEND, END, and this instantiation nothing else.
+// SB / SQ: compile-time shape of the chain (chain_shapes.h lists the registered ones; 0 = decoded at run time).
+template <int MAXNS, int SPT, bool TRAJ = false, bool PACK = false, int CHAIN = 0, unsigned long long SB = 0ull, unsigned SQ = 0u>
+#ifndef PYDSB_CHAIN_CTAS
+#define PYDSB_CHAIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CTAS : 3) : (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))))
     feas_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ LaunchArgs la)
 {
     typedef Vec<SPT> VecT;
@@ -177,16 +184,20 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);                 // [1]
     double* red = reinterpret_cast<double*>(smem + 16);                 // [BLOCK/32]
-    double* cpool = reinterpret_cast<double*>(smem + img.off_const) + 1;   // cpool[-1] = 0.0
+    // constant pool; CHAIN: every entry SPT-wide (one VecT load serves both scenarios) after the specials 1.0, -0.0, 0.0
+    constexpr int CW = CHAIN > 0 ? SPT : 1, CPRE = CHAIN > 0 ? 3 : 1;
+    double* cpool = reinterpret_cast<double*>(smem + img.off_const) + CPRE * CW;   // cpool[-1] = 0.0
     uint16_t* tabs = reinterpret_cast<uint16_t*>(smem + img.off_tabs);
     double* land = reinterpret_cast<double*>(smem + img.off_land);      // [TILE*p_dim]
     double* S = reinterpret_cast<double*>(smem + img.off_slots) + tid * SPT;   // S[slot * TILE + s]
 
     // ---- stage constants and reference tables in shared memory (once per CTA) ----
-    for (int i = tid; i < img.n_const; i += BLOCK) cpool[i] = img.consts[i];
+    for (int i = tid; i < img.n_const * CW; i += BLOCK) cpool[i] = img.consts[i / CW];
     for (int i = tid; i < img.n_tabs; i += BLOCK) tabs[i] = img.tabs[i];
     if (tid == 0) {
-        cpool[-1] = 0.0;
+        for (int s = 0; s < CW; ++s) cpool[-1 * CW + s] = 0.0;
+        if constexpr (CHAIN > 0)
+            for (int s = 0; s < CW; ++s) { cpool[-3 * CW + s] = 1.0; cpool[-2 * CW + s] = -0.0; }
         mbar_init(&mbar[0], 1);
         mbar_fence_init();
     }
@@ -203,12 +214,12 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
     // cold-path access through 14-bit references (tape_vm.cuh): slot of scenario s, or constant pool
     auto slot = [&](int idx, int s) -> double& { return S[(size_t)idx * TILE + s]; };
     auto ref_ld = [&](unsigned ref, int s) -> double {
-        if (ref & REF_CONST) return (ref == REF_NONE) ? 0.0 : cpool[ref & REF_MASK];
+        if (ref & REF_CONST) return (ref == REF_NONE) ? 0.0 : cpool[(ref & REF_MASK) * CW];
         return S[(size_t)(ref & REF_MASK) * TILE + s];
     };
 
     char* const base = reinterpret_cast<char*>(S);
-    const char* const cz = reinterpret_cast<const char*>(cpool - 1);    // constant operands: (index + 1) * 8
+    const char* const cz = reinterpret_cast<const char*>(cpool - CPRE * CW);    // constant operands: (index + CPRE) * 8 * CW
 
     const double h = 1.0 / (double)img.nfe;
     const int p_dim = img.p_dim, d_dim = img.d_dim;
@@ -491,6 +502,93 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
         STVP(w0.y, 0, xo[0]); STVP(w0.y, 1, xo[1]); STVP(w0.y, 2, xo[2]);                                       \
     }                                                                                                           \
     break;
+// INIT: initial states (seeded at collocation point 2), quadratures
+#define X_INIT_BODY                                                                                             \
+    {                                                                                                           \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) {                                                       \
+            double x0v[MAX_STATES];                                                                             \
+            for (int n = 0; n < img.ns; ++n) x0v[n] = ref_ld(tab_x0[n], s);                                     \
+            for (int n = 0; n < img.ns; ++n) slot(img.x_slot + 3 * n + 2, s) = x0v[n];                          \
+            for (int q = 0; q < img.nq; ++q) slot(img.qe_slot + q, s) = ref_ld(tab_q0[q], s);                   \
+            if (img.zero_slot) slot(img.zero_slot, s) = 0.0;                                                    \
+            if constexpr (TRAJ) {                                                                               \
+                if (valid[s]) {                                                                                 \
+                    double* o = la.g_out + (id_of(s) * la.n_t + jj_[s]) * traj_rows * traj_w;                   \
+                    for (int n = 0; n < img.ns; ++n) o[n] = x0v[n];                                             \
+                    for (int qn = 0; qn < img.nq; ++qn) o[img.ns + qn] = slot(img.qe_slot + qn, s);             \
+                }                                                                                               \
+            }                                                                                                   \
+        }                                                                                                       \
+    }
+// LDCTRL: control w0.z of finite element e -> slot w0.y
+#define X_LDCTRL_BODY                                                                                           \
+    {                                                                                                           \
+        VecT zv_;                                                                                               \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s) zv_.v[s] = ctrl_ld(e, (int)w0.z, s);                    \
+        STV(w0.y, zv_);                                                                                         \
+    }
+// XEND: end-point states for the CQA tape
+#define X_XEND_BODY                                                                                             \
+    {                                                                                                           \
+        _Pragma("unroll") for (int s = 0; s < SPT; ++s)                                                         \
+            for (int n = 0; n < img.ns; ++n) slot(img.xe_slot + n, s) = slot(img.x_slot + 3 * n + 2, s);        \
+    }
+        // value of control c on finite element el for the thread's scenario s (z_mode: where the controls come from)
+        auto ctrl_ld = [&](int el, int c, int s) -> double {
+            const int zi = tab_cmap[el * img.nce + c];
+            if (la.z_mode == 0 || tab_zfix[zi]) return ref_ld(tab_z[zi], s);
+            if (la.z_mode == 1) return __ldg(la.z + zi);
+            if (la.z_mode == 2) return __ldg(la.z + id_of(s) * img.nz + zi);
+            return __ldg(la.z + (id_of(s) * la.n_t + jj_[s]) * img.nz + zi);
+        };
+        if constexpr (CHAIN > 0) {
+            // A chain program has a fixed shape: two counted loops over scalar ops around the fused element loop.  Operands
+            // of the scalar ops: a slot of this thread or an entry of the constant pool (staged SPT-wide, so both are one
+            // VecT load from a selected base); the FMA-class ops (MOV NEG ADD SUB MUL FMA FMS FNMA SQR) are ONE op, FMAG:
+            // r = fma(+-a, b, +-c) with 1.0 / -0.0 from the pool -- bit-identical to the individual ops, no dispatch.
+            auto scalar_run = [&](int pc, const int pc_end) {
+                for (; pc < pc_end; pc += 2) {
+                    const uint4 w0 = c_prog[pc], w1 = c_prog[pc + 1];
+                    const unsigned fl = w1.y;
+                    const unsigned op = w0.x;
+                    if (op == X_INIT) { X_INIT_BODY continue; }
+                    if (op == X_LDCTRL) { X_LDCTRL_BODY continue; }
+                    const VecT av = *reinterpret_cast<const VecT*>(((fl & 1u) ? cz : base) + w0.z);
+                    const VecT bv = *reinterpret_cast<const VecT*>(((fl & 2u) ? cz : base) + w0.w);
+                    VecT rv;
+                    if (op == X_FMAG) {
+                        const VecT cv = *reinterpret_cast<const VecT*>(((fl & 4u) ? cz : base) + w1.x);
+                        const int sa = (int)((fl & 8u) << 28), sc = (int)((fl & 16u) << 27);    // sign bits to flip
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) {
+                            const double a = __hiloint2double(__double2hiint(av.v[s]) ^ sa, __double2loint(av.v[s]));
+                            const double c = __hiloint2double(__double2hiint(cv.v[s]) ^ sc, __double2loint(cv.v[s]));
+                            rv.v[s] = fma(a, bv.v[s], c);
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) {
+                            const double a = av.v[s], b = bv.v[s];
+                            double r;
+                            switch (op) {
+                            case X_DIV1: r = a / b; break;
+                            case X_RCP1: r = 1.0 / a; break;
+                            case X_ABS1: r = fabs(a); break;
+                            case X_MIN1: r = fmin(a, b); break;
+                            case X_MAX1: r = fmax(a, b); break;
+                            default: r = cold_op(w1.z, a, b); break;       // X_COLD1
+                            }
+                            rv.v[s] = r;
+                        }
+                    }
+                    STV(w0.y, rv);
+                }
+            };
+            scalar_run(0, (int)c_chain.pre_end);
+            poly_chain<SPT, CHAIN, SB, SQ>(img, base, h, ctrl_ld, failed, my_acc, cnt_warp_iters);
+            { X_XEND_BODY }
+            scalar_run((int)c_chain.g_begin, (int)c_chain.g_end);
+        } else
         for (;;) {
             const uint4 w0 = c_prog[pcw];
             pcw += 2;
@@ -629,38 +727,8 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 case X_MIN1: X1_BIN(fmin(a, b))
                 case X_MAX1: X1_BIN(fmax(a, b))
                 case X_COLD1: X1_BIN(cold_op(w1.z, a, b))
-                case X_INIT:                               // initial states (seeded at collocation point 2), quadratures
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        double x0v[MAX_STATES];
-                        for (int n = 0; n < img.ns; ++n) x0v[n] = ref_ld(tab_x0[n], s);
-                        for (int n = 0; n < img.ns; ++n) slot(img.x_slot + 3 * n + 2, s) = x0v[n];
-                        for (int q = 0; q < img.nq; ++q) slot(img.qe_slot + q, s) = ref_ld(tab_q0[q], s);
-                        if (img.zero_slot) slot(img.zero_slot, s) = 0.0;
-                        if constexpr (TRAJ) {
-                            if (valid[s]) {
-                                double* o = la.g_out + (id_of(s) * la.n_t + jj_[s]) * traj_rows * traj_w;
-                                for (int n = 0; n < img.ns; ++n) o[n] = x0v[n];
-                                for (int qn = 0; qn < img.nq; ++qn) o[img.ns + qn] = slot(img.qe_slot + qn, s);
-                            }
-                        }
-                    }
-                    break;
-                case X_LDCTRL: {                           // control w0.z of finite element e -> slot w0.y
-                    const int zi = tab_cmap[e * img.nce + (int)w0.z];
-                    VecT zv_;
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        double zv1;
-                        if (la.z_mode == 0 || tab_zfix[zi]) zv1 = ref_ld(tab_z[zi], s);
-                        else if (la.z_mode == 1) zv1 = __ldg(la.z + zi);
-                        else if (la.z_mode == 2) zv1 = __ldg(la.z + id_of(s) * img.nz + zi);
-                        else zv1 = __ldg(la.z + (id_of(s) * la.n_t + jj_[s]) * img.nz + zi);
-                        zv_.v[s] = zv1;
-                    }
-                    STV(w0.y, zv_);
-                    break;
-                }
+                case X_INIT: X_INIT_BODY break;
+                case X_LDCTRL: X_LDCTRL_BODY break;
                 case X_NB2:
                     if constexpr (MAXNS >= 2) X_NB_CASE(2)
                     break;
@@ -676,17 +744,16 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? 3 : (MAXNS <= 1 ? 5 : (MAXN
                 case X_NS3:
                     if constexpr (MAXNS >= 3) X_NS_CASE(3, true)
                     break;
-                case X_XEND:                               // end-point states for the CQA tape
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s)
-                        for (int n = 0; n < img.ns; ++n) slot(img.xe_slot + n, s) = slot(img.x_slot + 3 * n + 2, s);
-                    break;
+                case X_XEND: X_XEND_BODY break;
                 default: break;
                 }
                 if (op == X_END) break;
             }
         }
 #undef X_POLY1_CASE
+#undef X_INIT_BODY
+#undef X_LDCTRL_BODY
+#undef X_XEND_BODY
 #undef X_NS_CASE
 #undef X_NSL_CASE
 #undef X_NB_CASE

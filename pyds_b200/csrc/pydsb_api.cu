@@ -16,6 +16,7 @@
 
 #include "../../include/pydsb.h"
 #include "assembler.h"
+#include "chain_shapes.h"
 #include "recourse_kernel.cuh"
 
 using namespace pydsb;
@@ -57,6 +58,11 @@ struct Program {
     void* d_consts = nullptr;
     void* d_tabs = nullptr;
     std::vector<uint32_t> xprog;        // the assembled program (program 0: whole scenario; program 1: tape segments)
+    std::vector<uint32_t> xprog_interp; // program 0 with the element loop interpreted (pydsb_state_solve), when xprog is fused
+    int chain_nb = 0;                   // blocks of the fused element loop (X_PCHAIN) in xprog; 0: none
+    ChainDesc chain{};                  // its descriptor, copied to the constant bank (c_chain) before a launch
+    unsigned long long shape_sb = 0;    // compile-time shape words of the chain (poly_chain.cuh, chain_shape_bits)
+    unsigned shape_sq = 0;
     PolyBlock poly[MAX_BLOCKS];         // program 0: blocks lowered to polynomial coefficients
     bool present = false;
 };
@@ -94,8 +100,32 @@ typedef void (*SensFn)(const ExecImage, const RecourseArgs);
 // 7 % faster once the one-state blocks run in registers (POLY1; bound by instruction issue).  Default: 2 when
 // every block is a polynomial one-state block, else 1; PYDSB_SPT=1|2 overrides (2 needs one-state blocks: the two
 // Newton systems have to fit the register file).
-FeasFn feas_for(int ns, int spt)
+struct ChainKernel {
+    unsigned long long sb;
+    unsigned sq;
+    FeasFn plain, pack;
+};
+#define PYDSB_X(SB_, SQ_, NB_) {SB_, SQ_, feas_kernel<1, 2, false, false, NB_, SB_, SQ_>, feas_kernel<1, 2, false, true, NB_, SB_, SQ_>},
+const ChainKernel g_chain_kernels[] = {PYDSB_CHAIN_SHAPES(PYDSB_X)};
+#undef PYDSB_X
+
+// instantiation with the chain's shape folded at compile time, if that shape is registered
+const ChainKernel* chain_kernel_for(const Program& p, int spt)
 {
+    if (p.chain_nb <= 0 || spt != 2 || getenv("PYDSB_GENERIC_CHAIN")) return nullptr;
+    for (const ChainKernel& k : g_chain_kernels)
+        if (k.sb == p.shape_sb && k.sq == p.shape_sq) return &k;
+    return nullptr;
+}
+
+FeasFn feas_for(int ns, int spt, const Program* p = nullptr)
+{
+    const int chain = p ? p->chain_nb : 0;
+    if (chain > 0 && ns == 1) {              // fused element loop (poly_chain.cuh): 2 or 3 blocks in registers
+        if (const ChainKernel* k = chain_kernel_for(*p, spt)) return k->plain;
+        if (spt == 2) return chain <= 2 ? feas_kernel<1, 2, false, false, 2> : feas_kernel<1, 2, false, false, 3>;
+        return chain <= 2 ? feas_kernel<1, 1, false, false, 2> : feas_kernel<1, 1, false, false, 3>;
+    }
     switch (ns * 10 + spt) {
     case 11: return feas_kernel<1, 1>;
     case 12: return feas_kernel<1, 2>;
@@ -118,8 +148,14 @@ FeasFn traj_for(int ns, int spt)
 }
 
 // small theta sets: several design points per tile
-FeasFn pack_for(int ns, int spt)
+FeasFn pack_for(int ns, int spt, const Program* p = nullptr)
 {
+    const int chain = p ? p->chain_nb : 0;
+    if (chain > 0 && ns == 1) {
+        if (const ChainKernel* k = chain_kernel_for(*p, spt)) return k->pack;
+        if (spt == 2) return chain <= 2 ? feas_kernel<1, 2, false, true, 2> : feas_kernel<1, 2, false, true, 3>;
+        return chain <= 2 ? feas_kernel<1, 1, false, true, 2> : feas_kernel<1, 1, false, true, 3>;
+    }
     switch (ns * 10 + spt) {
     case 11: return feas_kernel<1, 1, false, true>;
     case 12: return feas_kernel<1, 2, false, true>;
@@ -359,9 +395,43 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
         if ((int)find(secs, "CMAP")->count < g.nfe * g.nce) return fail(PYDSB_ERR_INVALID, "control map shorter than nfe x nce");
         in.poly = P.poly;
         in.spt = g.spt;
+        // HEAD[15] bit 0 (DaeModel(fused_chain=False)) or PYDSB_NO_CHAIN=1: keep the element loop interpreted
+        const char* no_chain = getenv("PYDSB_NO_CHAIN");
+        in.allow_chain = !(H[15] & 1u) && !(no_chain && atoi(no_chain) != 0);
         Assembler as;
         if (!as.assemble(in)) return fail(PYDSB_ERR_UNSUPPORTED, "assembler: " + as.err);
         P.xprog.swap(as.words);
+        P.chain_nb = as.chain_nb;
+        if (P.chain_nb > 0) {
+            // the descriptor words that follow the PCHAIN opcode -> the fixed constant-bank struct the kernel reads
+            const std::vector<uint32_t>& W = P.xprog;
+            size_t at = 0;
+            while (at < W.size() && W[at] != (uint32_t)X_PCHAIN) at += 8;          // scalar ops, INIT, LDCTRL: length 2
+            if (at >= W.size()) return fail(PYDSB_ERR_INVALID, "assembler: chain program without PCHAIN");
+            ChainDesc& cd = P.chain;
+            cd = ChainDesc{};
+            cd.nb = W[at + 1] & 0xFFu; cd.nq = (W[at + 1] >> 8) & 0xFFu; cd.max_it = W[at + 2];
+            cd.pre_end = (unsigned)(at / 4);
+            size_t q = at + 8;
+            for (unsigned b = 0; b < cd.nb; ++b, q += 12) {
+                ChainBlockD& bd = cd.blk[b];
+                bd.x_off = W[q]; bd.flops = W[q + 1]; bd.kind = W[q + 2]; bd.minv_off = W[q + 3];
+                for (int k = 0; k < 3; ++k) { bd.c[k].n_off = W[q + 4 + 2 * k]; bd.c[k].meta = W[q + 5 + 2 * k]; }
+            }
+            for (unsigned i = 0; i < cd.nq; ++i, q += 4) {
+                cd.quad[i].q_off = W[q]; cd.quad[i].n_off = W[q + 1]; cd.quad[i].meta = W[q + 2];
+            }
+            cd.g_begin = (unsigned)(q / 4) + 2;                                      // after XEND
+            cd.g_end = (unsigned)(W.size() / 4) - 2;                                 // before END
+            if (W[q] != (uint32_t)X_XEND || W[W.size() - 8] != (uint32_t)X_END || cd.g_begin > cd.g_end)
+                return fail(PYDSB_ERR_INVALID, "assembler: malformed chain program");
+            chain_shape_bits(cd, P.shape_sb, P.shape_sq);
+            // the trajectory variant of the kernel stores the points element by element: it runs the interpreted loop
+            in.allow_chain = false;
+            Assembler as2;
+            if (!as2.assemble(in)) return fail(PYDSB_ERR_UNSUPPORTED, "assembler: " + as2.err);
+            P.xprog_interp.swap(as2.words);
+        }
         g.n_prog = (int)(P.xprog.size() / 4);             // uint4 units
     }
     const Section* cn = find(secs, "CNST");
@@ -419,7 +489,7 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
 
     // shared-memory carve-up
     int o = 128;                                            // mbarrier + reduction scratch
-    g.off_const = o; o += (g.n_const + 1) * 8;
+    g.off_const = o; o += (g.n_const + 3) * 8 * g.spt;      // chain programs: SPT-wide entries after three specials
     g.off_tabs = o; o = align_up(o + g.n_tabs * 2, 128);
     int land = g.spt * BLOCK * g.p_dim * 8;
     if (sens) {
@@ -559,7 +629,7 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
                 return fail(PYDSB_ERR_UNSUPPORTED, "model needs more shared memory per CTA than the device offers");
             }
     }
-    FeasFn fn = feas_for(image_maxns(g), g.spt);
+    FeasFn fn = feas_for(image_maxns(g), g.spt, &m->prog[0]);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
     int bps = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, BLOCK, g.smem_bytes);
@@ -683,8 +753,9 @@ int pydsb_assemble(const void* blob, size_t nbytes, uint32_t* words, size_t cap,
     if (words)
         for (size_t i = 0; i < P.xprog.size() && i < cap; ++i) words[i] = P.xprog[i];
     const ExecImage& g = P.img;
-    const long long v[4] = {g.spt, g.n_units + (g.zero_off ? 1 : 0), g.smem_bytes, g.n_prog};
-    for (int i = 0; info && i < n_info && i < 4; ++i) info[i] = v[i];
+    const long long v[8] = {g.spt, g.n_units + (g.zero_off ? 1 : 0), g.smem_bytes, g.n_prog, P.chain_nb,
+                            (long long)P.shape_sb, (long long)P.shape_sq, chain_kernel_for(P, g.spt) ? 1 : 0};
+    for (int i = 0; info && i < n_info && i < 8; ++i) info[i] = v[i];
     return PYDSB_OK;
 }
 
@@ -763,12 +834,16 @@ int eval_impl(void* handle, const double* d, long long n_d, const double* theta,
 
     const long long max_ctas = (long long)m->num_sms * m->blocks_per_sm;
     const int grid = (int)(total < max_ctas ? total : max_ctas);
-    FeasFn fn = traj ? traj_for(image_maxns(img), img.spt) : (pack ? pack_for(image_maxns(img), img.spt) : feas_for(image_maxns(img), img.spt));
+    const int chain = m->prog[0].chain_nb;
+    FeasFn fn = traj ? traj_for(image_maxns(img), img.spt)
+                     : (pack ? pack_for(image_maxns(img), img.spt, &m->prog[0]) : feas_for(image_maxns(img), img.spt, &m->prog[0]));
+    const std::vector<uint32_t>& xp = (traj && chain > 0) ? m->prog[0].xprog_interp : m->prog[0].xprog;
     // several models may share one template instantiation: (re)assert this model's smem size and
-    // (re)load its point tape into the constant bank (stream ordered)
+    // (re)load its program into the constant bank (stream ordered)
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, m->prog[0].xprog.data(), m->prog[0].xprog.size() * sizeof(uint32_t), 0,
-                                     cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, xp.data(), xp.size() * sizeof(uint32_t), 0, cudaMemcpyHostToDevice, st));
+    if (chain > 0 && !traj)
+        CUDA_TRY(cudaMemcpyToSymbolAsync(c_chain, &m->prog[0].chain, sizeof(ChainDesc), 0, cudaMemcpyHostToDevice, st));
     fn<<<grid, BLOCK, img.smem_bytes, st>>>(img, la);
     CUDA_TRY(cudaGetLastError());
     m->launches += 1;

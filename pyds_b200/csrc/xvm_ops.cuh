@@ -22,6 +22,10 @@ enum XCode : unsigned {
     X_FMS1, X_FNMA1, X_SUB1, X_DIV1, X_SQR1, X_NEG1, X_RCP1, X_ABS1, X_MOV1, X_MIN1, X_MAX1, X_COLD1,
     // ... structure
     X_INIT, X_LDCTRL, X_NB2, X_NB3, X_NS3, X_NS2L, X_NS3L, X_XEND, X_END,
+    // ... the whole element loop of a chain of polynomial one-state blocks (poly_chain.cuh)
+    X_PCHAIN,
+    // ... chain programs only: r = fma(+-a, b, +-c), every FMA-class scalar op (flags bit 3: negate a, bit 4: negate c)
+    X_FMAG,
     X_COUNT
 };
 constexpr unsigned X_TIER1 = 4, X_TIER2 = 16;
@@ -35,6 +39,7 @@ constexpr unsigned X_TIER1 = 4, X_TIER2 = 16;
 //   LDCTRL      w0 = { op, dst, control }
 //   ELEM_END    w0 = { op, target pcw, n }        then n x { dst, o0, o1, o2 | scale, has_scale, -, - }: quadratures
 //               to advance, optionally times a narrow scale factor                                 length 1 + 2n
+//   PCHAIN      w0 = { op, nb | nq << 8, max_it }  then 3 words per block, 1 per quadrature (poly_chain.cuh)   length 2 + 3 nb + nq
 __host__ __device__ constexpr int ns_words(int nsb) { return nsb + 3 * nsb + 3 * nsb * nsb; }
 __host__ __device__ constexpr int ns_length(int nsb) { return 1 + (ns_words(nsb) + 3) / 4; }
 

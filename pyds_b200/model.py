@@ -52,7 +52,8 @@ class _Control:
 
 class DaeModel:
     def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-12, newton_max_it=25, predictor=False,
-                 quadratures="auto", block_triangular=True, polynomial_blocks=True, second_derivatives=False):
+                 quadratures="auto", block_triangular=True, polynomial_blocks=True, second_derivatives=False,
+                 fused_chain=True):
         self.graph = T.Graph()
         self.d_names = list(d_names)
         self.p_names = list(p_names)
@@ -73,6 +74,10 @@ class DaeModel:
         # does not consume them, so by default the tapes stay short): d2g_k/de_a de_b over the end values
         # e = (x(1), q(1)) after the g tape, d2f_r/dx_a dx_b in the point tape
         self.second_derivatives = bool(second_derivatives)
+        # when every block is a polynomial one-state block whose coefficients are single mass-action terms, the assembler
+        # fuses the whole finite-element loop into one instruction with the states in registers (csrc/poly_chain.cuh);
+        # False keeps the interpreted loop (POLY1 per block and element) -- both are parity-tested
+        self.fused_chain = bool(fused_chain)
         self.states: list[_State] = []
         self.controls: list[_Control] = []
         self.constraints = []          # (name, Expr (<= 0 feasible), bigM)
@@ -309,7 +314,7 @@ class DaeModel:
                 blk_fixed = fixed
             sec("HEAD", "u32", [ns, nq, ng, len(self.d_names), len(self.p_names), nz, self.nfe, self.ncp, nce,
                                 lay.n_units, lay.ctrl_slot, lay.xe_slot, lay.qe_slot, lay.x_slot, self.newton_max_it,
-                                0, lay.fq_state_dep, 1 if self.predictor else 0, len(blks)])
+                                0 if self.fused_chain else 1, lay.fq_state_dep, 1 if self.predictor else 0, len(blks)])
             sec("RPAR", "u16", lay.param_slots)
             sec("DBLS", "f64", [self.newton_rtol])
             sec("CNST", "f64", low.consts if len(low.consts) else [0.0])
