@@ -34,6 +34,9 @@ struct AsmInput {
     const PolyBlock* poly;                     // [n_blocks]
     const ExecImage* img;                      // resolved per-block offsets: blk_x_o, blk_f_o, blk_j_o, blk_jmask
     bool allow_chain = false;                  // fuse the element loop into one X_PCHAIN when the model has that shape
+    // reference tables (chain programs resolve them into the descriptor: no table walking in the kernel)
+    const uint16_t *x0_refs = nullptr, *q0_refs = nullptr, *par_refs = nullptr, *g_refs = nullptr;
+    int n_par = 0, ng = 0, xe_slot = 0;
 };
 
 class Assembler {
@@ -41,6 +44,7 @@ public:
     std::vector<uint32_t> words;               // 8 per instruction
     std::string err;
     int chain_nb = 0;                          // blocks of the fused chain (0: the element loop is interpreted)
+    ChainDesc chain{};                         // its descriptor (poly_chain.cuh): what the kernel reads from the constant bank
 
     int pc() const { return (int)(words.size() / 4); }      // uint4 index of the next instruction
 
@@ -57,9 +61,14 @@ public:
         chain_mode_ = in.allow_chain && try_chain(in, invariant, chain, nb);
         for (int i = 0; i < in.n_pro; ++i)
             if (!scalar_op(in.pro[i])) return false;
-        emit(X_INIT);
+        if (!chain_mode_) emit(X_INIT);                    // a chain reads the initial values where they are
         auto ctrl_and_elem = [&]() -> bool {
-            for (int c = 0; c < in.nce; ++c) emit(X_LDCTRL, (uint32_t)(in.ctrl_slot + c) * US * (uint32_t)in.spt, (uint32_t)c);
+            for (int c = 0; c < in.nce; ++c) {
+                const uint32_t dst = (uint32_t)(in.ctrl_slot + c) * US * (uint32_t)in.spt;
+                // chain programs: every scalar op loads its a / b operands before it looks at the opcode -- keep them valid
+                if (chain_mode_) emit(X_LDCTRL, dst, 0u, 0u, 0u, 0u, (uint32_t)c);
+                else emit(X_LDCTRL, dst, (uint32_t)c);
+            }
             for (int i = 0; i < in.n_elem; ++i)
                 if (!scalar_op(in.elem[i])) return false;
             return true;
@@ -67,11 +76,14 @@ public:
         if (chain_mode_) {
             // scalar ops | PCHAIN | XEND | scalar ops | END  (the shape feas_kernel<.., CHAIN> relies on)
             if (invariant && !ctrl_and_elem()) return false;
+            this->chain.pre_end = (unsigned)pc();
             words.insert(words.end(), chain.begin(), chain.end());
             chain_nb = nb;
             emit(X_XEND);
+            this->chain.g_begin = (unsigned)pc();
             for (int i = 0; i < in.n_g; ++i)
                 if (!scalar_op(in.g[i])) return false;
+            this->chain.g_end = (unsigned)pc();
             emit(X_END);
             if (pc() > 2 * MAX_PROG - 2) return fail("program longer than the constant-bank window");
             return true;
@@ -251,6 +263,22 @@ private:
         return -1;
     }
 
+    // where an initial value lives: the constant pool of a chain program (SPT-wide entries after the three specials
+    // 1.0, -0.0, 0.0) or a slot
+    static bool source_ref(const AsmInput& in, unsigned ref, uint32_t& off, uint32_t& is_const)
+    {
+        const uint32_t cw = 8u * (uint32_t)in.spt;
+        if (ref & REF_WIDE && !(ref & REF_CONST)) return false;
+        if (ref & REF_CONST) {
+            is_const = 1u;
+            off = (ref == REF_NONE) ? 2u * cw : ((ref & REF_MASK) + 3u) * cw;
+        } else {
+            is_const = 0u;
+            off = (ref & REF_MASK) * US * (uint32_t)in.spt;
+        }
+        return true;
+    }
+
     // narrow factor: a plain persistent slot, or (controls that differ between the elements) a control value / an
     // elem-tape value `a * control`
     static bool narrow_factor(const AsmInput& in, unsigned ref, bool invariant, const std::vector<ElemVal>& ev, Term& t)
@@ -348,6 +376,15 @@ private:
             }
         }
         std::vector<uint32_t> blkw, quadw;
+        ChainDesc& cd = chain;
+        cd = ChainDesc{};
+        if (!in.par_refs || !in.g_refs || in.n_par > 16 || in.ng > 8) return false;
+        cd.n_par = (unsigned)in.n_par; cd.ng = (unsigned)in.ng;
+        for (int i = 0; i < in.n_par; ++i) cd.par_off[i] = (uint32_t)(in.par_refs[i] & REF_MASK) * usp;
+        for (int k = 0; k < in.ng; ++k) {
+            if (in.g_refs[k] & (REF_CONST | REF_WIDE)) return false;  // a constant constraint: leave it to the generic path
+            cd.g_off[k] = (uint32_t)(in.g_refs[k] & REF_MASK) * usp;
+        }
         int pos = 0, scratch = g.x_slot;                               // units [x_slot, n_units) are dead during the loop
         for (int b = 0; b < in.n_blocks; ++b) {
             const PolyBlock& pb = in.poly[b];
@@ -375,6 +412,12 @@ private:
             const uint32_t w[12] = {g.blk_x_o[b][0][0], flops, kind, minv, t[0].n_off, t[0].meta(), t[1].n_off, t[1].meta(),
                                     t[2].n_off, t[2].meta(), 0u, 0u};
             blkw.insert(blkw.end(), w, w + 12);
+            ChainBlockD& bd = cd.blk[b];
+            bd.x_off = w[0]; bd.flops = flops; bd.kind = kind; bd.minv_off = minv;
+            for (int k = 0; k < 3; ++k) { bd.c[k].n_off = t[k].n_off; bd.c[k].meta = t[k].meta(); }
+            const int st = (int)(g.blk_x_o[b][0][0] / usp - (uint32_t)g.x_slot) / 3;      // the block's state
+            if (!in.x0_refs || st < 0 || st >= g.ns || !source_ref(in, in.x0_refs[st], bd.x0_off, bd.x0_const)) return false;
+            bd.xe_off = (uint32_t)(in.xe_slot + st) * usp;
         }
         // quadrature integrands
         {
@@ -384,7 +427,7 @@ private:
             int nq = 0;
             for (int q = 0; q < in.nq; ++q) {
                 const unsigned r = in.fq_refs[q];
-                if (r == REF_NONE) continue;
+                if (r == REF_NONE) return false;                       // a constant quadrature state: generic path
                 Term t;
                 if (r & REF_CONST) return false;
                 if (r & REF_WIDE) {
@@ -396,10 +439,14 @@ private:
                 if (++nq > CHAIN_MAXQ) return false;
                 const uint32_t w[4] = {(uint32_t)(in.qe_slot + q) * usp, t.n_off, t.meta(), 0u};
                 quadw.insert(quadw.end(), w, w + 4);
+                ChainQuadD& qd = cd.quad[nq - 1];
+                qd.q_off = w[0]; qd.n_off = t.n_off; qd.meta = t.meta();
+                if (!in.q0_refs || !source_ref(in, in.q0_refs[q], qd.q0_off, qd.q0_const)) return false;
             }
             for (int i = 0; i < n; ++i)
                 if (!used[i]) return false;
             if (g.max_it < 1 || g.max_it > 0xFFFF) return false;
+            cd.nb = (unsigned)in.n_blocks; cd.nq = (unsigned)nq; cd.max_it = (unsigned)g.max_it;
             const uint32_t head[8] = {X_PCHAIN, (uint32_t)in.n_blocks | ((uint32_t)nq << 8), (uint32_t)g.max_it, 0u, 0u, 0u, 0u, 0u};
             out.assign(head, head + 8);
         }

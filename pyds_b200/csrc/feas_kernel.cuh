@@ -246,36 +246,42 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
     const long long total = PACK ? (la.n_d + pack_k - 1) / pack_k : la.n_d * (long long)la.n_tiles;
     unsigned phase = 0;
 
-    // theta rows a tile needs in the landing buffer (PACK: the whole set, every tile)
-    auto tile_rows = [&](long long t) -> int {
+    // theta rows tile tj of a design point needs in the landing buffer (PACK: the whole set, every tile)
+    auto tile_rows = [&](int tj) -> int {
         if constexpr (PACK) return (int)la.n_t;
-        const long long j0 = (t % la.n_tiles) * (long long)TILE;
-        const long long rem = la.n_t - j0;
+        const long long rem = la.n_t - (long long)tj * TILE;
         return rem < TILE ? (int)rem : TILE;
     };
     auto tile_tma = [&](int rows) -> bool {
         return la.theta_tma_ok && ((rows * p_dim * (int)sizeof(double)) % 16 == 0);
     };
-    auto issue = [&](long long t) {
-        const int rows = tile_rows(t);
+    auto issue = [&](int tj) {
+        const int rows = tile_rows(tj);
         if (tile_tma(rows)) {
-            const long long j0 = PACK ? 0 : (t % la.n_tiles) * (long long)TILE;
+            const long long j0 = PACK ? 0 : (long long)tj * TILE;
             const unsigned bytes = (unsigned)(rows * p_dim * sizeof(double));
             mbar_expect_tx(&mbar[0], bytes);
             tma_load_1d(land, la.theta + j0 * p_dim, bytes, &mbar[0]);
         }
     };
 
+    // tile t = (design point t / n_tiles, theta tile t % n_tiles): divided once, then advanced by the grid stride
     long long t = blockIdx.x;
-    if (t < total && tid == 0) issue(t);
+    long long i_dn = PACK ? 0 : t / la.n_tiles;
+    int tjn = PACK ? 0 : (int)(t % la.n_tiles);
+    const int step_q = PACK ? 0 : (int)(gridDim.x / (unsigned)la.n_tiles), step_r = PACK ? 0 : (int)(gridDim.x % (unsigned)la.n_tiles);
+    if (t < total && tid == 0) issue(tjn);
 
     unsigned long long cnt_iters = 0, cnt_flops = 0;
     unsigned cnt_warp_iters = 0, cnt_failed = 0, cnt_done = 0;
 
     for (; t < total; t += gridDim.x) {
-        const long long i_d = PACK ? t * pack_k : t / la.n_tiles;      // PACK: the tile's first design point
-        const long long j0 = PACK ? 0 : (t % la.n_tiles) * (long long)TILE;
-        const int rows = tile_rows(t);
+        const long long i_d = PACK ? t * pack_k : i_dn;                // PACK: the tile's first design point
+        const int tj = tjn;
+        i_dn += step_q; tjn += step_r;                                 // the CTA's next tile
+        if (tjn >= la.n_tiles) { tjn -= la.n_tiles; ++i_dn; }
+        const long long j0 = PACK ? 0 : (long long)tj * TILE;
+        const int rows = tile_rows(tj);
         bool valid[SPT];
         long long jj_[SPT];
         int row[SPT];                                      // row of the landing buffer
@@ -310,36 +316,41 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
         };
 
         // ---- parameters into the register file (theta from the TMA landing buffer) ----
+        // slot of parameter c of scenario s (chain programs: from the descriptor, no table read)
+        auto par_slot = [&](int c, int s) -> double& {
+            if constexpr (CHAIN > 0) return *reinterpret_cast<double*>(reinterpret_cast<char*>(S) + c_chain.par_off[c] + s * 8);
+            else return slot(tab_par[c], s);
+        };
         if (tile_tma(rows)) {
             mbar_wait(&mbar[0], phase);
             phase ^= 1u;
 #pragma unroll
             for (int s = 0; s < SPT; ++s) {
                 const double* src = land + (size_t)row[s] * p_dim;
-                for (int c = 0; c < p_dim; ++c) slot(tab_par[d_dim + c], s) = src[c];
+                for (int c = 0; c < p_dim; ++c) par_slot(d_dim + c, s) = src[c];
             }
         } else {
 #pragma unroll
             for (int s = 0; s < SPT; ++s) {
                 const double* src = la.theta + jj_[s] * p_dim;
-                for (int c = 0; c < p_dim; ++c) slot(tab_par[d_dim + c], s) = __ldg(src + c);
+                for (int c = 0; c < p_dim; ++c) par_slot(d_dim + c, s) = __ldg(src + c);
             }
         }
         if constexpr (PACK) {
 #pragma unroll
             for (int s = 0; s < SPT; ++s)
-                for (int c = 0; c < d_dim; ++c) slot(tab_par[c], s) = __ldg(la.d + id_of(s) * d_dim + c);
+                for (int c = 0; c < d_dim; ++c) par_slot(c, s) = __ldg(la.d + id_of(s) * d_dim + c);
         } else {
             for (int c = 0; c < d_dim; ++c) {
                 const double dv = __ldg(la.d + i_d * d_dim + c);
 #pragma unroll
-                for (int s = 0; s < SPT; ++s) slot(tab_par[c], s) = dv;
+                for (int s = 0; s < SPT; ++s) par_slot(c, s) = dv;
             }
         }
         __syncthreads();                                   // landing buffer and `red` are free again
         {
             const long long nt = t + gridDim.x;            // prefetch the next tile's theta rows
-            if (nt < total && tid == 0) issue(nt);
+            if (nt < total && tid == 0) issue(tjn);
         }
 
         // ---- the scenarios' program ----
@@ -547,12 +558,15 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
             // VecT load from a selected base); the FMA-class ops (MOV NEG ADD SUB MUL FMA FMS FNMA SQR) are ONE op, FMAG:
             // r = fma(+-a, b, +-c) with 1.0 / -0.0 from the pool -- bit-identical to the individual ops, no dispatch.
             auto scalar_run = [&](int pc, const int pc_end) {
-                for (; pc < pc_end; pc += 2) {
-                    const uint4 w0 = c_prog[pc], w1 = c_prog[pc + 1];
+                if (pc >= pc_end) return;
+                uint4 w0 = c_prog[pc], w1 = c_prog[pc + 1];
+                for (;;) {
+                    pc += 2;
+                    const bool more = pc < pc_end;
+                    // the next instruction is fetched while this one executes (the last fetch re-reads a valid word)
+                    const uint4 n0 = c_prog[more ? pc : pc - 2], n1 = c_prog[more ? pc + 1 : pc - 1];
                     const unsigned fl = w1.y;
                     const unsigned op = w0.x;
-                    if (op == X_INIT) { X_INIT_BODY continue; }
-                    if (op == X_LDCTRL) { X_LDCTRL_BODY continue; }
                     const VecT av = *reinterpret_cast<const VecT*>(((fl & 1u) ? cz : base) + w0.z);
                     const VecT bv = *reinterpret_cast<const VecT*>(((fl & 2u) ? cz : base) + w0.w);
                     VecT rv;
@@ -565,6 +579,12 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
                             const double c = __hiloint2double(__double2hiint(cv.v[s]) ^ sc, __double2loint(cv.v[s]));
                             rv.v[s] = fma(a, bv.v[s], c);
                         }
+                    } else if (op == X_LDCTRL) {
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) rv.v[s] = ctrl_ld(0, (int)w1.z, s);      // element-invariant controls only
+                    } else if (op == X_COLD1 && w1.z == OP_EXP) {
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) rv.v[s] = exp(av.v[s]);
                     } else {
 #pragma unroll
                         for (int s = 0; s < SPT; ++s) {
@@ -582,11 +602,12 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
                         }
                     }
                     STV(w0.y, rv);
+                    if (!more) break;
+                    w0 = n0; w1 = n1;
                 }
             };
             scalar_run(0, (int)c_chain.pre_end);
-            poly_chain<SPT, CHAIN, SB, SQ>(img, base, h, ctrl_ld, failed, my_acc, cnt_warp_iters);
-            { X_XEND_BODY }
+            poly_chain<SPT, CHAIN, SB, SQ>(img, base, cz, h, ctrl_ld, failed, my_acc, cnt_warp_iters);
             scalar_run((int)c_chain.g_begin, (int)c_chain.g_end);
         } else
         for (;;) {
@@ -765,7 +786,9 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
             bool feasible = !failed[s];
             const long long j = jj_[s];
             for (int c = 0; c < img.ng; ++c) {
-                double gv = ref_ld(tab_g[c], s);
+                double gv;
+                if constexpr (CHAIN > 0) gv = *reinterpret_cast<const double*>(base + c_chain.g_off[c] + s * 8);
+                else gv = ref_ld(tab_g[c], s);
                 if (failed[s]) gv = __longlong_as_double(0x7ff8000000000000LL);
                 feasible = feasible && (gv <= la.gtol[c]);
                 if constexpr (!TRAJ)

@@ -30,7 +30,9 @@
 // a program counter the descriptors arrived in vector registers (LDC R, c[3][R]) and the per-element decode cost as much
 // as the Newton iterations (profiles/r02_v1_*).  A chain program has a fixed shape,
 //     scalar ops (pro tape, INIT, element-invariant control loads + elem tape) | PCHAIN | XEND | scalar ops (g tape) | END,
-// so the chain instantiation of feas_kernel runs two counted loops around poly_chain instead of a dispatch loop.
+// so the chain instantiation of feas_kernel runs two counted loops around poly_chain instead of a dispatch loop; INIT and
+// XEND are not executed either: the chain reads the initial values where they are (constant pool or parameter slot) and
+// writes the end values to the slots the g tape reads.
 #pragma once
 #include "xvm_ops.cuh"
 
@@ -51,13 +53,17 @@ __host__ __device__ constexpr unsigned chain_meta(bool has_n, bool has_ctrl, uns
 __host__ __device__ constexpr int chain_length(int nb, int nq) { return 2 + 3 * nb + nq; }
 
 struct ChainTermD { unsigned n_off, meta; };
-struct ChainBlockD { unsigned x_off, flops, kind, minv_off; ChainTermD c[3]; unsigned pad[2]; };
-struct ChainQuadD { unsigned q_off, n_off, meta, pad; };
+// x0: where the initial value comes from (byte offset; x0_const: in the constant pool, else a slot); xe_off: the slot the
+// g tape reads the end value from
+struct ChainBlockD { unsigned x_off, flops, kind, minv_off; ChainTermD c[3]; unsigned x0_off, x0_const, xe_off, pad; };
+struct ChainQuadD { unsigned q_off, n_off, meta, q0_off, q0_const, pad[3]; };
 struct ChainDesc {
     unsigned nb, nq, max_it, pre_end;          // scalar ops [0, pre_end) run before the chain ...
-    unsigned g_begin, g_end, pad0, pad1;       // ... and [g_begin, g_end) after XEND (uint4 indices into c_prog)
+    unsigned g_begin, g_end, n_par, ng;        // ... and [g_begin, g_end) after it (uint4 indices into c_prog)
     ChainBlockD blk[CHAIN_MAXB];
     ChainQuadD quad[CHAIN_MAXQ];
+    unsigned par_off[16];                      // slot of every parameter (d first, then theta)
+    unsigned g_off[8];                         // slot of every constraint value
 };
 __constant__ ChainDesc c_chain;
 
@@ -181,8 +187,9 @@ __device__ __forceinline__ void chain_term(unsigned n_off, unsigned meta, int e,
 
 // NB = blocks the instantiation holds in registers (2 or 3); SB / SQ = the chain's compile-time shape (0: decoded at run time).
 template <int SPT, int NB, unsigned long long SB, unsigned SQ, class CtrlLd>
-__device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restrict__ base, const double h, CtrlLd ctrl_ld,
-                                           bool (&failed)[SPT], unsigned long long (&my_acc)[SPT], unsigned& cnt_warp_iters)
+__device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restrict__ base, const char* __restrict__ cz,
+                                           const double h, CtrlLd ctrl_ld, bool (&failed)[SPT],
+                                           unsigned long long (&my_acc)[SPT], unsigned& cnt_warp_iters)
 {
     typedef Vec<SPT> VecT;
     typedef ChainShape<SB, SQ> SH;
@@ -199,7 +206,7 @@ __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restric
         VecT v;
 #pragma unroll
         for (int s = 0; s < SPT; ++s) v.v[s] = 0.0;
-        if (b < nb) v = LDVP(c_chain.blk[b].x_off, 2);     // INIT seeded point 2 with x(0)
+        if (b < nb) v = *reinterpret_cast<const VecT*>((c_chain.blk[b].x0_const ? cz : base) + c_chain.blk[b].x0_off);
 #pragma unroll
         for (int s = 0; s < SPT; ++s) {
             X[b][s][0] = X[b][s][1] = X[b][s][2] = v.v[s];
@@ -211,7 +218,7 @@ __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restric
         VecT v;
 #pragma unroll
         for (int s = 0; s < SPT; ++s) v.v[s] = 0.0;
-        if (q < nq) v = LDV(c_chain.quad[q].q_off);
+        if (q < nq) v = *reinterpret_cast<const VecT*>((c_chain.quad[q].q0_const ? cz : base) + c_chain.quad[q].q0_off);
 #pragma unroll
         for (int s = 0; s < SPT; ++s) Q[q][s] = v.v[s];
     }
@@ -360,15 +367,15 @@ __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restric
         }
     }
 
-    // ---- converged end values back to the register file (XEND and the g tape read them); counters ----
+    // ---- converged end values to the slots the g tape reads; counters ----
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         if (b >= nb) continue;
         const unsigned kind = SH::kind(b);
-        VecT o[3];
+        VecT o;
 #pragma unroll
         for (int s = 0; s < SPT; ++s) {
-            o[0].v[s] = X[b][s][0]; o[1].v[s] = X[b][s][1]; o[2].v[s] = X[b][s][2];
+            o.v[s] = X[b][s][2];
             // a LINCONST block has no stop test: a non-finite value reaches the end (the recurrence is linear in x)
             failed[s] = failed[s] | !(fabs(X[b][s][2]) <= DBL_MAX);
             if (kind == CHAIN_LINCONST)
@@ -376,7 +383,7 @@ __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restric
             else
                 my_acc[s] += ((unsigned long long)nit[b][s] << 40) | (unsigned long long)(nit[b][s] * c_chain.blk[b].flops);
         }
-        STVP(c_chain.blk[b].x_off, 0, o[0]); STVP(c_chain.blk[b].x_off, 1, o[1]); STVP(c_chain.blk[b].x_off, 2, o[2]);
+        STV(c_chain.blk[b].xe_off, o);
     }
 #pragma unroll
     for (int q = 0; q < CHAIN_MAXQ; ++q) {

@@ -395,6 +395,14 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
         if ((int)find(secs, "CMAP")->count < g.nfe * g.nce) return fail(PYDSB_ERR_INVALID, "control map shorter than nfe x nce");
         in.poly = P.poly;
         in.spt = g.spt;
+        in.x0_refs = reinterpret_cast<const uint16_t*>(find(secs, "RX0_")->data);
+        in.q0_refs = reinterpret_cast<const uint16_t*>(find(secs, "RQ0_")->data);
+        in.par_refs = reinterpret_cast<const uint16_t*>(find(secs, "RPAR")->data);
+        in.g_refs = reinterpret_cast<const uint16_t*>(find(secs, "RG__")->data);
+        if ((int)find(secs, "RX0_")->count < g.ns || (int)find(secs, "RQ0_")->count < g.nq ||
+            (int)find(secs, "RPAR")->count < g.d_dim + g.p_dim || (int)find(secs, "RG__")->count < g.ng)
+            return fail(PYDSB_ERR_INVALID, "reference table shorter than its dimension");
+        in.n_par = g.d_dim + g.p_dim; in.ng = g.ng; in.xe_slot = g.xe_slot;
         // HEAD[15] bit 0 (DaeModel(fused_chain=False)) or PYDSB_NO_CHAIN=1: keep the element loop interpreted
         const char* no_chain = getenv("PYDSB_NO_CHAIN");
         in.allow_chain = !(H[15] & 1u) && !(no_chain && atoi(no_chain) != 0);
@@ -403,28 +411,8 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
         P.xprog.swap(as.words);
         P.chain_nb = as.chain_nb;
         if (P.chain_nb > 0) {
-            // the descriptor words that follow the PCHAIN opcode -> the fixed constant-bank struct the kernel reads
-            const std::vector<uint32_t>& W = P.xprog;
-            size_t at = 0;
-            while (at < W.size() && W[at] != (uint32_t)X_PCHAIN) at += 8;          // scalar ops, INIT, LDCTRL: length 2
-            if (at >= W.size()) return fail(PYDSB_ERR_INVALID, "assembler: chain program without PCHAIN");
-            ChainDesc& cd = P.chain;
-            cd = ChainDesc{};
-            cd.nb = W[at + 1] & 0xFFu; cd.nq = (W[at + 1] >> 8) & 0xFFu; cd.max_it = W[at + 2];
-            cd.pre_end = (unsigned)(at / 4);
-            size_t q = at + 8;
-            for (unsigned b = 0; b < cd.nb; ++b, q += 12) {
-                ChainBlockD& bd = cd.blk[b];
-                bd.x_off = W[q]; bd.flops = W[q + 1]; bd.kind = W[q + 2]; bd.minv_off = W[q + 3];
-                for (int k = 0; k < 3; ++k) { bd.c[k].n_off = W[q + 4 + 2 * k]; bd.c[k].meta = W[q + 5 + 2 * k]; }
-            }
-            for (unsigned i = 0; i < cd.nq; ++i, q += 4) {
-                cd.quad[i].q_off = W[q]; cd.quad[i].n_off = W[q + 1]; cd.quad[i].meta = W[q + 2];
-            }
-            cd.g_begin = (unsigned)(q / 4) + 2;                                      // after XEND
-            cd.g_end = (unsigned)(W.size() / 4) - 2;                                 // before END
-            if (W[q] != (uint32_t)X_XEND || W[W.size() - 8] != (uint32_t)X_END || cd.g_begin > cd.g_end)
-                return fail(PYDSB_ERR_INVALID, "assembler: malformed chain program");
+            P.chain = as.chain;                              // what the kernel reads from the constant bank
+            const ChainDesc& cd = P.chain;
             chain_shape_bits(cd, P.shape_sb, P.shape_sq);
             // the trajectory variant of the kernel stores the points element by element: it runs the interpreted loop
             in.allow_chain = false;
