@@ -11,10 +11,12 @@
 // through the shared-memory register file per block -- by this one instruction: the states and quadratures stay in
 // registers over all nfe elements, nothing is dispatched, and nothing but the narrow coefficients is loaded.
 //
-// Same equations, same start (x_j = x(element start)) and same stop rule as POLY1 (feas_kernel.cuh), with two
-// algebraic savings:
+// Same equations and same start (x_j = x(element start)) as POLY1 (feas_kernel.cuh); the stop rule is POLY1's with the
+// relative scale |x|^2 taken at the element start (3 x_s^2, one limit per element) instead of at every iterate.  Algebraic
+// savings:
 //   * coefficients are pre-scaled by h once per element and the x(element start) column of the differentiation matrix is
-//     folded into the constant term, so a residual is 5 FMAs per point and the Jacobian diagonal 2;
+//     folded into the constant term; the diagonal of the differentiation matrix joins the Horner form, so a residual is
+//     4 FMAs per point and the Jacobian diagonal 1 (the Newton matrix is assembled negated:  N = h J - A,  x -= N^-1 r);
 //   * a block that is LINEAR with an element- and point-invariant c1 (first-order decay, -t_f K2 cB) has the same
 //     collocation matrix  A - h c1 I  on every element: it is inverted once per scenario (9 values in register-file
 //     units that are dead during the loop) and every element costs one 3x3 matrix-vector product instead of an LU.
@@ -297,42 +299,48 @@ __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restric
             }
             const bool linear = kind == CHAIN_LINEAR;
             bool conv[SPT];
-            double s_prev[SPT];
+            double s_prev[SPT], lim[SPT], dg[SPT][3];
 #pragma unroll
             for (int s = 0; s < SPT; ++s) {
-                X[b][s][0] = X[b][s][1] = X[b][s][2];       // start: x_j = x(element start)
+                // stop test against |x(element start)|: one limit per element instead of |x|^2 of every iterate
+                const double xs = X[b][s][2];
+                lim[s] = fma(img.rtol2 * 3.0, xs * xs, img.rtol2);
+                X[b][s][0] = X[b][s][1] = xs;               // start: x_j = x(element start)
                 conv[s] = false;
                 s_prev[s] = 0.0;
+                // the diagonal of the linear part joins the Horner form:  h f(x_j) - A_jj x_j = (dg_j + hc2 x_j) x_j + h c0_j
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dg[s][j] = hc1[s][j] - CH_A(j, j);
             }
             for (int it = 0;;) {
                 bool all = true;
 #pragma unroll
                 for (int s = 0; s < SPT; ++s) {
                     nit[b][s] += conv[s] ? 0u : 1u;
-                    double M[3][3], r[3];
+                    // N = h J - A (the negated Newton matrix):  N dx = r,  x -= dx
+                    double N[3][3], r[3];
 #pragma unroll
                     for (int jj = 0; jj < 3; ++jj) {
                         const double x = X[b][s][jj];
-                        const double t = fma(hc2[s], x, hc1[s][jj]);
-                        double rr = fma(t, x, cb[s][jj]);                 // h f(x_j) - A0_j x_s
-                        rr = fma(-CH_A(jj, 0), X[b][s][0], rr);
-                        rr = fma(-CH_A(jj, 1), X[b][s][1], rr);
-                        r[jj] = fma(-CH_A(jj, 2), X[b][s][2], rr);
+                        const double t = fma(hc2[s], x, dg[s][jj]);
+                        double rr = fma(t, x, cb[s][jj]);                 // h f(x_j) - A0_j x_s - A_jj x_j
 #pragma unroll
-                        for (int kk = 0; kk < 3; ++kk) M[jj][kk] = CH_A(jj, kk);
-                        M[jj][jj] = fma(-hc2[s], x, CH_A(jj, jj) - t);   // A_jj - h (2 c2 x + c1)
+                        for (int kk = 0; kk < 3; ++kk) {
+                            if (kk != jj) rr = fma(-CH_A(jj, kk), X[b][s][kk], rr);
+                            N[jj][kk] = -CH_A(jj, kk);
+                        }
+                        r[jj] = rr;
+                        N[jj][jj] = fma(hc2[s], x, t);                   // h (2 c2 x + c1) - A_jj
                     }
-                    lu_solve_inplace<3>(M, r);
-                    double sq = 0.0, sc = 0.0;
+                    lu_solve_inplace<3>(N, r);
+                    double sq = 0.0;
 #pragma unroll
                     for (int kk = 0; kk < 3; ++kk) {
-                        X[b][s][kk] += r[kk];
+                        X[b][s][kk] -= r[kk];
                         sq = fma(r[kk], r[kk], sq);
-                        sc = fma(X[b][s][kk], X[b][s][kk], sc);
                     }
-                    const double lim = fma(img.rtol2, sc, img.rtol2);
                     const bool ok = linear ? (sq <= DBL_MAX)
-                                           : ((sq <= lim) | ((sq * sq <= lim * s_prev[s]) & (sq <= 0.01 * s_prev[s])));
+                                           : ((sq <= lim[s]) | ((sq * sq <= lim[s] * s_prev[s]) & (sq <= 0.01 * s_prev[s])));
                     s_prev[s] = sq;
                     conv[s] = conv[s] | ok;
                     all = all & conv[s];
