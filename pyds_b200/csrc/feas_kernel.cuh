@@ -327,7 +327,13 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
 #pragma unroll
             for (int s = 0; s < SPT; ++s) {
                 const double* src = land + (size_t)row[s] * p_dim;
-                for (int c = 0; c < p_dim; ++c) par_slot(d_dim + c, s) = src[c];
+                int c0 = 0;
+                for (; c0 + 4 <= p_dim; c0 += 4) {         // four at a time: the loads issue back to back
+                    const double v0 = src[c0], v1 = src[c0 + 1], v2 = src[c0 + 2], v3 = src[c0 + 3];
+                    par_slot(d_dim + c0, s) = v0; par_slot(d_dim + c0 + 1, s) = v1;
+                    par_slot(d_dim + c0 + 2, s) = v2; par_slot(d_dim + c0 + 3, s) = v3;
+                }
+                for (int c = c0; c < p_dim; ++c) par_slot(d_dim + c, s) = src[c];
             }
         } else {
 #pragma unroll
@@ -341,8 +347,17 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
             for (int s = 0; s < SPT; ++s)
                 for (int c = 0; c < d_dim; ++c) par_slot(c, s) = __ldg(la.d + id_of(s) * d_dim + c);
         } else {
-            for (int c = 0; c < d_dim; ++c) {
-                const double dv = __ldg(la.d + i_d * d_dim + c);
+            const double* drow = la.d + i_d * d_dim;
+            int c0 = 0;
+            for (; c0 + 4 <= d_dim; c0 += 4) {
+                const double v0 = __ldg(drow + c0), v1 = __ldg(drow + c0 + 1), v2 = __ldg(drow + c0 + 2), v3 = __ldg(drow + c0 + 3);
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) {
+                    par_slot(c0, s) = v0; par_slot(c0 + 1, s) = v1; par_slot(c0 + 2, s) = v2; par_slot(c0 + 3, s) = v3;
+                }
+            }
+            for (int c = c0; c < d_dim; ++c) {
+                const double dv = __ldg(drow + c);
 #pragma unroll
                 for (int s = 0; s < SPT; ++s) par_slot(c, s) = dv;
             }
@@ -591,8 +606,9 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
                             const double a = av.v[s], b = bv.v[s];
                             double r;
                             switch (op) {
-                            case X_DIV1: r = a / b; break;
-                            case X_RCP1: r = 1.0 / a; break;
+                            // MUFU seed + Newton steps and one residual correction: within 1 ulp of a / b, no slow path
+                            case X_DIV1: { const double rb = fast_rcp(b), q = a * rb; r = fma(fma(-b, q, a), rb, q); break; }
+                            case X_RCP1: { const double ra = fast_rcp(a); r = fma(fma(-a, ra, 1.0), ra, ra); break; }
                             case X_ABS1: r = fabs(a); break;
                             case X_MIN1: r = fmin(a, b); break;
                             case X_MAX1: r = fmax(a, b); break;
@@ -816,15 +832,9 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
             }
             __syncthreads();                               // before the next tile's parameters overwrite the unit
         } else {
+            // one partial per warp (reduce_partials_kernel adds them in fixed order): no CTA barrier, no serial tail
             wv = warp_sum(wv);
-            if (lane == 0) red[warp] = wv;
-            __syncthreads();
-            if (tid == 0) {
-                double sum = 0.0;
-#pragma unroll
-                for (int i = 0; i < BLOCK / 32; ++i) sum += red[i];
-                la.partial[t] = sum;
-            }
+            if (lane == 0) la.partial[t * (BLOCK / 32) + warp] = wv;
         }
     }
 

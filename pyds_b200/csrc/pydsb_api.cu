@@ -806,10 +806,11 @@ int eval_impl(void* handle, const double* d, long long n_d, const double* theta,
     const bool pack = !traj && 2 * n_t <= tile;
     const long long pack_k = pack ? tile / n_t : 1;
     const long long n_tiles_ll = pack ? 1 : (n_t + tile - 1) / tile;
-    if (n_tiles_ll > 0x7fffffffLL) return fail(PYDSB_ERR_INVALID, "n_t too large");
+    if (n_tiles_ll > 0x7fffffffLL / (BLOCK / 32)) return fail(PYDSB_ERR_INVALID, "n_t too large");
     const int n_tiles = (int)n_tiles_ll;                              // partial sums per design point
     const long long total = pack ? (n_d + pack_k - 1) / pack_k : n_d * n_tiles_ll;   // tiles = CTAs' work items
-    int rc = ensure_partial(m, (size_t)(n_d * n_tiles_ll));
+    const int n_part = pack ? 1 : n_tiles * (BLOCK / 32);              // partial sums per design point: one per warp and tile
+    int rc = ensure_partial(m, (size_t)n_d * (size_t)n_part);
     if (rc) return rc;
 
     LaunchArgs la{};
@@ -837,7 +838,7 @@ int eval_impl(void* handle, const double* d, long long n_d, const double* theta,
     m->launches += 1;
     if (P_out) {
         const int tb = 128;
-        reduce_partials_kernel<<<(unsigned)((n_d + tb - 1) / tb), tb, 0, st>>>(m->d_partial, n_tiles, n_d, P_out);
+        reduce_partials_kernel<<<(unsigned)((n_d + tb - 1) / tb), tb, 0, st>>>(m->d_partial, n_part, n_d, P_out);
         CUDA_TRY(cudaGetLastError());
         m->launches += 1;
     }
