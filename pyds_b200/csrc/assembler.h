@@ -85,6 +85,8 @@ public:
                 if (!scalar_op(in.g[i])) return false;
             this->chain.g_end = (unsigned)pc();
             emit(X_END);
+            this->chain.pre_run0 = fmag_runs(0, this->chain.pre_end);
+            this->chain.g_run0 = fmag_runs(this->chain.g_begin, this->chain.g_end);
             if (pc() > 2 * MAX_PROG - 2) return fail("program longer than the constant-bank window");
             return true;
         }
@@ -238,6 +240,25 @@ public:
 private:
     const AsmInput* in_ = nullptr;
     bool chain_mode_ = false;                  // chain programs: FMAG scalar ops, SPT-wide constant pool
+
+    // Scalar section [begin, end) of a chain program (every op two uint4 long): the FMAG ops that directly follow another
+    // op are counted into that op's w1.w -- the kernel runs them in a loop without looking at opcodes.  Returns the
+    // length of the run at the head of the section.
+    unsigned fmag_runs(unsigned begin, unsigned end)
+    {
+        unsigned run0 = 0;
+        long long last = -1;                                          // uint4 index of the last non-FMAG op
+        for (unsigned p4 = begin; p4 < end; p4 += 2) {
+            if (words[(size_t)p4 * 4] == (uint32_t)X_FMAG) {
+                if (last < 0) ++run0;
+                else ++words[(size_t)(last + 1) * 4 + 3];
+            } else {
+                last = p4;
+                words[(size_t)(p4 + 1) * 4 + 3] = 0u;
+            }
+        }
+        return run0;
+    }
 
     // ---- fused polynomial chain (poly_chain.cuh) ----------------------------------------------------------------
     struct Term {

@@ -572,59 +572,68 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
             // of the scalar ops: a slot of this thread or an entry of the constant pool (staged SPT-wide, so both are one
             // VecT load from a selected base); the FMA-class ops (MOV NEG ADD SUB MUL FMA FMS FNMA SQR) are ONE op, FMAG:
             // r = fma(+-a, b, +-c) with 1.0 / -0.0 from the pool -- bit-identical to the individual ops, no dispatch.
-            auto scalar_run = [&](int pc, const int pc_end) {
-                if (pc >= pc_end) return;
-                uint4 w0 = c_prog[pc], w1 = c_prog[pc + 1];
-                for (;;) {
-                    pc += 2;
-                    const bool more = pc < pc_end;
-                    // the next instruction is fetched while this one executes (the last fetch re-reads a valid word)
-                    const uint4 n0 = c_prog[more ? pc : pc - 2], n1 = c_prog[more ? pc + 1 : pc - 1];
+            // a run of n FMAG ops: nothing but fetch, three operand loads, two sign flips, the FMA and the store
+            auto fmag_run = [&](int pc, const int n) -> int {
+                for (int i = 0; i < n; ++i, pc += 2) {
+                    const uint4 w0 = c_prog[pc], w1 = c_prog[pc + 1];
                     const unsigned fl = w1.y;
-                    const unsigned op = w0.x;
                     const VecT av = *reinterpret_cast<const VecT*>(((fl & 1u) ? cz : base) + w0.z);
                     const VecT bv = *reinterpret_cast<const VecT*>(((fl & 2u) ? cz : base) + w0.w);
+                    const VecT cv = *reinterpret_cast<const VecT*>(((fl & 4u) ? cz : base) + w1.x);
+                    const int sa = (int)((fl & 8u) << 28), sc = (int)((fl & 16u) << 27);        // sign bits to flip
                     VecT rv;
-                    if (op == X_FMAG) {
-                        const VecT cv = *reinterpret_cast<const VecT*>(((fl & 4u) ? cz : base) + w1.x);
-                        const int sa = (int)((fl & 8u) << 28), sc = (int)((fl & 16u) << 27);    // sign bits to flip
 #pragma unroll
-                        for (int s = 0; s < SPT; ++s) {
-                            const double a = __hiloint2double(__double2hiint(av.v[s]) ^ sa, __double2loint(av.v[s]));
-                            const double c = __hiloint2double(__double2hiint(cv.v[s]) ^ sc, __double2loint(cv.v[s]));
-                            rv.v[s] = fma(a, bv.v[s], c);
-                        }
-                    } else if (op == X_LDCTRL) {
+                    for (int s = 0; s < SPT; ++s) {
+                        const double a = __hiloint2double(__double2hiint(av.v[s]) ^ sa, __double2loint(av.v[s]));
+                        const double c = __hiloint2double(__double2hiint(cv.v[s]) ^ sc, __double2loint(cv.v[s]));
+                        rv.v[s] = fma(a, bv.v[s], c);
+                    }
+                    STV(w0.y, rv);
+                }
+                return pc;
+            };
+            // [pc, pc_end): run0 FMAG ops, then { one other op, the FMAG run that follows it (length in its w1.w) } ...
+            auto scalar_run = [&](int pc, const int pc_end, const int run0) {
+                pc = fmag_run(pc, run0);
+                while (pc < pc_end) {
+                    const uint4 w0 = c_prog[pc], w1 = c_prog[pc + 1];
+                    const unsigned fl = w1.y;
+                    const unsigned op = w0.x;
+                    VecT rv;
+                    if (op == X_LDCTRL) {
 #pragma unroll
                         for (int s = 0; s < SPT; ++s) rv.v[s] = ctrl_ld(0, (int)w1.z, s);      // element-invariant controls only
-                    } else if (op == X_COLD1 && w1.z == OP_EXP) {
-#pragma unroll
-                        for (int s = 0; s < SPT; ++s) rv.v[s] = exp(av.v[s]);
                     } else {
+                        const VecT av = *reinterpret_cast<const VecT*>(((fl & 1u) ? cz : base) + w0.z);
+                        const VecT bv = *reinterpret_cast<const VecT*>(((fl & 2u) ? cz : base) + w0.w);
+                        if (op == X_COLD1 && w1.z == OP_EXP) {
 #pragma unroll
-                        for (int s = 0; s < SPT; ++s) {
-                            const double a = av.v[s], b = bv.v[s];
-                            double r;
-                            switch (op) {
-                            // MUFU seed + Newton steps and one residual correction: within 1 ulp of a / b, no slow path
-                            case X_DIV1: { const double rb = fast_rcp(b), q = a * rb; r = fma(fma(-b, q, a), rb, q); break; }
-                            case X_RCP1: { const double ra = fast_rcp(a); r = fma(fma(-a, ra, 1.0), ra, ra); break; }
-                            case X_ABS1: r = fabs(a); break;
-                            case X_MIN1: r = fmin(a, b); break;
-                            case X_MAX1: r = fmax(a, b); break;
-                            default: r = cold_op(w1.z, a, b); break;       // X_COLD1
+                            for (int s = 0; s < SPT; ++s) rv.v[s] = exp(av.v[s]);
+                        } else {
+#pragma unroll
+                            for (int s = 0; s < SPT; ++s) {
+                                const double a = av.v[s], b = bv.v[s];
+                                double r;
+                                switch (op) {
+                                // MUFU seed + Newton steps and one residual correction: within 1 ulp of a / b, no slow path
+                                case X_DIV1: { const double rb = fast_rcp(b), q = a * rb; r = fma(fma(-b, q, a), rb, q); break; }
+                                case X_RCP1: { const double ra = fast_rcp(a); r = fma(fma(-a, ra, 1.0), ra, ra); break; }
+                                case X_ABS1: r = fabs(a); break;
+                                case X_MIN1: r = fmin(a, b); break;
+                                case X_MAX1: r = fmax(a, b); break;
+                                default: r = cold_op(w1.z, a, b); break;       // X_COLD1
+                                }
+                                rv.v[s] = r;
                             }
-                            rv.v[s] = r;
                         }
                     }
                     STV(w0.y, rv);
-                    if (!more) break;
-                    w0 = n0; w1 = n1;
+                    pc = fmag_run(pc + 2, (int)w1.w);
                 }
             };
-            scalar_run(0, (int)c_chain.pre_end);
+            scalar_run(0, (int)c_chain.pre_end, (int)c_chain.pre_run0);
             poly_chain<SPT, CHAIN, SB, SQ>(img, base, cz, h, ctrl_ld, failed, my_acc, cnt_warp_iters);
-            scalar_run((int)c_chain.g_begin, (int)c_chain.g_end);
+            scalar_run((int)c_chain.g_begin, (int)c_chain.g_end, (int)c_chain.g_run0);
         } else
         for (;;) {
             const uint4 w0 = c_prog[pcw];

@@ -64,6 +64,7 @@ struct ChainDesc {
     unsigned g_begin, g_end, n_par, ng;        // ... and [g_begin, g_end) after it (uint4 indices into c_prog)
     ChainBlockD blk[CHAIN_MAXB];
     ChainQuadD quad[CHAIN_MAXQ];
+    unsigned pre_run0, g_run0, pad2, pad3;     // FMAG ops at the head of either scalar section (later runs: w1.w of the op before)
     unsigned par_off[16];                      // slot of every parameter (d first, then theta)
     unsigned g_off[8];                         // slot of every constraint value
 };
@@ -237,19 +238,27 @@ __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restric
 #pragma unroll
         for (int s = 0; s < SPT; ++s) {
             const double lam = h * c1.v[s];
-            double M[3][3], inv[3];
+            double M[3][3];
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj)
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk) M[jj][kk] = (jj == kk) ? CH_A(jj, kk) - lam : CH_A(jj, kk);
-            lu_factor<3>(M, inv);
+            // adjugate / determinant: no dependent chain of pivots (the matrix is the well-conditioned collocation matrix
+            // shifted by a decay rate)
+            double C[3][3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                double r[3] = {c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? 1.0 : 0.0};
-                lu_apply<3>(M, inv, r);
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) mi[3 * j + c].v[s] = r[j];
-            }
+                for (int j = 0; j < 3; ++j) {
+                    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                    C[i][j] = fma(M[i1][j1], M[i2][j2], -(M[i1][j2] * M[i2][j1]));      // cofactor (cyclic form: sign included)
+                }
+            const double det = fma(M[0][0], C[0][0], fma(M[0][1], C[0][1], M[0][2] * C[0][2]));
+            const double rd = fast_rcp(det);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) mi[3 * i + j].v[s] = C[j][i] * rd;                // inverse = adjugate^T / det
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) STV(c_chain.blk[b].minv_off + i * USP, mi[i]);
