@@ -262,9 +262,9 @@ private:
 
     // ---- fused polynomial chain (poly_chain.cuh) ----------------------------------------------------------------
     struct Term {
-        bool present = false, has_n = false, has_ctrl = false;
+        bool present = false, has_n = false, has_ctrl = false, neg = false;
         uint32_t n_off = 0, ctrl = 0, p = 0, src = 0;
-        uint32_t meta() const { return present ? chain_meta(has_n, has_ctrl, ctrl, p, src) : 0u; }
+        uint32_t meta() const { return present ? (chain_meta(has_n, has_ctrl, ctrl, p, src) | (neg ? CT_NEG : 0u)) : 0u; }
     };
     struct ElemVal {                           // value of the elem tape:  (narrow slot a, or 1) * control c
         unsigned dst;
@@ -324,42 +324,55 @@ private:
         return true;
     }
 
-    // A wide value of the tape `code[0..n)` as ONE term  narrow * (earlier state)^p: the state itself (p = 1), its SQR
-    // (p = 2), MUL narrow x state (p = 1) or MUL narrow x SQR(state) (p = 2).  Marks the tape ops it stands for.
+    // A wide value of the tape `code[0..n)`, as it stands before instruction `before`, as ONE term
+    //     +-narrow * (state of an earlier block)^p:
+    // the state itself (p = 1), SQR of it (p = 2), MUL narrow x such a value, NEG of such a value.  Slots are reused inside
+    // a tape, so the producer of a reference is the LAST write before its reader.  Marks the tape ops the term stands for.
+    static bool wide_value(const AsmInput& in, const uint64_t* code, int before, unsigned ref, bool invariant,
+                           const std::vector<ElemVal>& ev, std::vector<char>& used, Term& t)
+    {
+        int at = -1;
+        for (int i = before - 1; i >= 0 && at < 0; --i) {
+            unsigned op, refs[4];
+            split(code[i], op, refs);
+            if (refs[0] == ref) at = i;
+        }
+        if (at < 0) {                                                  // not computed here: a state's collocation points
+            const int b = state_block(in, ref);
+            if (b < 0) return false;
+            t.p = 1; t.src = (uint32_t)b;
+            return true;
+        }
+        unsigned op, refs[4];
+        split(code[at], op, refs);
+        used[at] = 1;
+        if (op == OP_NEG) {
+            if (!wide_value(in, code, at, refs[1], invariant, ev, used, t)) return false;
+            t.neg = !t.neg;
+            return true;
+        }
+        if (op == OP_SQR) {
+            if (!wide_value(in, code, at, refs[1], invariant, ev, used, t)) return false;
+            if (t.p != 1 || t.has_n || t.has_ctrl || t.neg) return false;             // only the square of a bare state
+            t.p = 2;
+            return true;
+        }
+        if (op == OP_MUL) {
+            unsigned na = refs[1], wb = refs[2];
+            if ((na & REF_WIDE) && !(wb & REF_WIDE)) { const unsigned s = na; na = wb; wb = s; }
+            if ((na & (REF_WIDE | REF_CONST)) || !(wb & REF_WIDE) || (wb & REF_CONST)) return false;
+            if (!wide_value(in, code, at, wb, invariant, ev, used, t)) return false;
+            if (t.has_n || t.has_ctrl) return false;                   // one narrow factor per term
+            return narrow_factor(in, na, invariant, ev, t);
+        }
+        return false;
+    }
     static bool wide_term(const AsmInput& in, const uint64_t* code, int n, unsigned ref, int own_block, bool invariant,
                           const std::vector<ElemVal>& ev, std::vector<char>& used, Term& t)
     {
-        auto src_of = [&](unsigned r, unsigned& p) -> int {            // state, or SQR of a state computed by this tape
-            int b = state_block(in, r);
-            if (b >= 0) { p = 1; return b; }
-            for (int i = 0; i < n; ++i) {
-                unsigned op, refs[4];
-                split(code[i], op, refs);
-                if (op == OP_SQR && refs[0] == r) {
-                    b = state_block(in, refs[1]);
-                    if (b >= 0) { p = 2; used[i] = 1; return b; }
-                }
-            }
-            return -1;
-        };
-        unsigned p = 0;
-        int b = src_of(ref, p);
-        if (b < 0) {
-            for (int i = 0; i < n && b < 0; ++i) {
-                unsigned op, refs[4];
-                split(code[i], op, refs);
-                if (op != OP_MUL || refs[0] != ref) continue;
-                unsigned na = refs[1], wb = refs[2];
-                if ((na & REF_WIDE) && !(wb & REF_WIDE)) { const unsigned s = na; na = wb; wb = s; }
-                if ((na & (REF_WIDE | REF_CONST)) || !(wb & REF_WIDE)) return false;
-                if (!narrow_factor(in, na, invariant, ev, t)) return false;
-                b = src_of(wb, p);
-                if (b < 0) return false;
-                used[i] = 1;
-            }
-        }
-        if (b < 0 || b >= own_block) return false;                     // only states of earlier blocks
-        t.present = true; t.p = p; t.src = (uint32_t)b;
+        if (!wide_value(in, code, n, ref, invariant, ev, used, t)) return false;
+        if ((int)t.src >= own_block) return false;                     // only states of earlier blocks
+        t.present = true;
         return true;
     }
 

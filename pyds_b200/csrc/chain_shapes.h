@@ -6,8 +6,8 @@
 #pragma once
 
 // the two shape words of the A -> B -> C kinetics chain (tests/test_assembler_cpu.py pins them on the shipped models)
-#define PYDSB_SHAPE_ABC_SB 0x32EC00C02ull
-#define PYDSB_SHAPE_ABC_SQ 0x5C32u
+#define PYDSB_SHAPE_ABC_SB 0x18B980062ull
+#define PYDSB_SHAPE_ABC_SQ 0x5C1Au
 
 #define PYDSB_CHAIN_SHAPES(X)                                                                                           \
     /* A -> B -> C semi-batch kinetics, fixed feed (models.kinetics("design4" / "design6"); BASELINE configs C3, C5): */ \

@@ -26,7 +26,7 @@
 //   per block b (3 words):  { x_off, flops per iteration, kind, minv_off }
 //                           { c0.n_off, c0.meta, c1.n_off, c1.meta }      { c2.n_off, c2.meta, 0, 0 }
 //   per quadrature (1):     { q_off, n_off, meta, 0 }
-//   meta = present | has_n << 1 | has_ctrl << 2 | ctrl << 4 | p << 8 | source block << 12
+//   meta = present | has_n << 1 | has_ctrl << 2 | negated << 3 | ctrl << 4 | p << 8 | source block << 12
 // The kernel does not decode this from the instruction stream: the host copies it into the fixed constant-bank struct
 // c_chain (ChainDesc), so every field is a direct constant operand and every branch on it a uniform one -- read through
 // a program counter the descriptors arrived in vector registers (LDC R, c[3][R]) and the per-element decode cost as much
@@ -42,7 +42,7 @@ namespace pydsb {
 
 constexpr int CHAIN_MAXB = 3;              // blocks in one chain
 constexpr int CHAIN_MAXQ = 4;              // quadratures advanced by the chain
-constexpr unsigned CT_PRESENT = 1u, CT_HAS_N = 2u, CT_HAS_CTRL = 4u;
+constexpr unsigned CT_PRESENT = 1u, CT_HAS_N = 2u, CT_HAS_CTRL = 4u, CT_NEG = 8u;
 constexpr unsigned CHAIN_NEWTON = 0, CHAIN_LINEAR = 1, CHAIN_LINCONST = 2;
 // algorithmic flops (SURVEY 8d convention): one-off inverse = LU (2/3 n^3) + three solves (2 n^2 each);
 // one element of a LINCONST block = right-hand side (2 n) + matrix-vector product (2 n^2)
@@ -75,11 +75,11 @@ __constant__ ChainDesc c_chain;
 // run time (the generic instantiation, SB = 0) that is ~330 instructions per element of selects and uniform branches around
 // ~80 of arithmetic.  A shape registered in chain_shapes.h gets an instantiation in which all of it is folded at compile
 // time; offsets, iteration cap and the control indices stay in the descriptor.  Bit layout (host: chain_shape_bits):
-//   SB  [0:1] nb   [2] some term depends on a control   block b at 8 + 16 b: kind(2) c0(6) c1(6) c2(2)
-//   SQ  [0:2] nq   quadrature q at 4 + 6 q: term(6)          term = present | has_n << 1 | p << 2 | source block << 4
+//   SB  [0:1] nb   [2] some term depends on a control   block b at 3 + 19 b: kind(2) c0(7) c1(7) c2(3)
+//   SQ  [0:2] nq   quadrature q at 3 + 7 q: term(7)     term = present | has_n << 1 | p << 2 | source block << 4 | negated << 6
 inline unsigned chain_term_bits(unsigned meta)
 {
-    return (meta & 3u) | (((meta >> 8) & 3u) << 2) | (((meta >> 12) & 3u) << 4);
+    return (meta & 3u) | (((meta >> 8) & 3u) << 2) | (((meta >> 12) & 3u) << 4) | ((meta & CT_NEG) ? 64u : 0u);
 }
 inline void chain_shape_bits(const ChainDesc& cd, unsigned long long& sb, unsigned& sq)
 {
@@ -89,13 +89,15 @@ inline void chain_shape_bits(const ChainDesc& cd, unsigned long long& sb, unsign
     for (unsigned b = 0; b < cd.nb; ++b) {
         unsigned long long v = cd.blk[b].kind & 3u;
         for (int k = 0; k < 3; ++k) {
-            v |= (unsigned long long)(chain_term_bits(cd.blk[b].c[k].meta) & (k == 2 ? 3u : 63u)) << (2 + 6 * k);
+            const unsigned t = chain_term_bits(cd.blk[b].c[k].meta);
+            // c2 is narrow: present, has_n, negated
+            v |= (unsigned long long)(k == 2 ? ((t & 3u) | ((t >> 6) << 2)) : t) << (2 + 7 * k);
             ctrl = ctrl || (cd.blk[b].c[k].meta & CT_HAS_CTRL);
         }
-        sb |= v << (8 + 16 * b);
+        sb |= v << (3 + 19 * b);
     }
     for (unsigned q = 0; q < cd.nq; ++q) {
-        sq |= chain_term_bits(cd.quad[q].meta) << (4 + 6 * q);
+        sq |= chain_term_bits(cd.quad[q].meta) << (3 + 7 * q);
         ctrl = ctrl || (cd.quad[q].meta & CT_HAS_CTRL);
     }
     if (ctrl) sb |= 4ull;
@@ -107,25 +109,27 @@ struct ChainShape {
     static constexpr bool ctrl = generic || ((SB >> 2) & 1ull);
     static __device__ __forceinline__ unsigned unpack(unsigned t)
     {
-        return (t & 3u) | (((t >> 2) & 3u) << 8) | (((t >> 4) & 3u) << 12);
+        return (t & 3u) | (((t >> 2) & 3u) << 8) | (((t >> 4) & 3u) << 12) | ((t & 64u) ? CT_NEG : 0u);
     }
     static __device__ __forceinline__ int nb() { return generic ? (int)c_chain.nb : (int)(SB & 3ull); }
     static __device__ __forceinline__ int nq() { return generic ? (int)c_chain.nq : (int)(SQ & 7u); }
     static __device__ __forceinline__ unsigned kind(int b)
     {
-        return generic ? c_chain.blk[b].kind : (unsigned)((SB >> (8 + 16 * b)) & 3ull);
+        return generic ? c_chain.blk[b].kind : (unsigned)((SB >> (3 + 19 * b)) & 3ull);
     }
     // meta word of coefficient k of block b: structural bits from the shape, control bits from the descriptor
     static __device__ __forceinline__ unsigned meta(int b, int k)
     {
         if (generic) return c_chain.blk[b].c[k].meta;
-        const unsigned st = unpack((unsigned)((SB >> (8 + 16 * b + 2 + 6 * k)) & (k == 2 ? 3ull : 63ull)));
+        unsigned t = (unsigned)((SB >> (3 + 19 * b + 2 + 7 * k)) & (k == 2 ? 7ull : 127ull));
+        if (k == 2) t = (t & 3u) | ((t >> 2) << 6);
+        const unsigned st = unpack(t);
         return ctrl ? (st | (c_chain.blk[b].c[k].meta & (CT_HAS_CTRL | 0xF0u))) : st;
     }
     static __device__ __forceinline__ unsigned qmeta(int q)
     {
         if (generic) return c_chain.quad[q].meta;
-        const unsigned st = unpack((SQ >> (4 + 6 * q)) & 63u);
+        const unsigned st = unpack((SQ >> (3 + 7 * q)) & 127u);
         return ctrl ? (st | (c_chain.quad[q].meta & (CT_HAS_CTRL | 0xF0u))) : st;
     }
 };
@@ -139,6 +143,7 @@ __device__ __forceinline__ void chain_narrow(unsigned n_off, unsigned meta, int 
                                              CtrlLd& ctrl_ld, double scale, double (&nv)[SPT])
 {
     typedef Vec<SPT> VecT;
+    if (meta & CT_NEG) scale = -scale;
     if (meta & CT_HAS_N) {
         const VecT v = LDV(n_off);
 #pragma unroll
@@ -237,7 +242,7 @@ __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restric
         VecT mi[9];
 #pragma unroll
         for (int s = 0; s < SPT; ++s) {
-            const double lam = h * c1.v[s];
+            const double lam = (SH::meta(b, 1) & CT_NEG) ? -h * c1.v[s] : h * c1.v[s];
             double M[3][3];
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj)

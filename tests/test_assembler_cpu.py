@@ -21,13 +21,14 @@ def _elem_loop(ops):
 
 
 def test_polynomial_blocks_program_c3():
-    lm = models.kinetics("design4").lower()
+    """The interpreted element loop (fused_chain=False): POLY1 per block and element."""
+    lm = models.kinetics("design4", fused_chain=False).lower()
     ops, info = capi.assemble(lm.blob)
     names = _names(ops)
     assert names[-1] == "END" and names.count("INIT") == 1 and names.count("XEND") == 1
     # both one-state blocks run as in-register polynomial solves: no NB / NS, two scenarios per thread
     assert names.count("POLY1") == 2 and not any(n.startswith(("NB", "NS")) for n in names)
-    assert info["scenarios_per_thread"] == 2
+    assert info["scenarios_per_thread"] == 2 and info["chain_blocks"] == 0
     a, b = _elem_loop(ops)
     # Fbar is one control entry for every element: its load and the elem tape are hoisted out of the loop
     assert "LDCTRL" in names[:a] and "LDCTRL" not in names[a:b]
@@ -48,10 +49,87 @@ def test_polynomial_blocks_program_c3():
 
 
 def test_per_element_controls_stay_inside_the_loop():
-    ops, _ = capi.assemble(models.kinetics("twostage").lower().blob)
+    ops, _ = capi.assemble(models.kinetics("twostage", fused_chain=False).lower().blob)
     names = _names(ops)
     a, b = _elem_loop(ops)
     assert names[a] == "LDCTRL" and "LDCTRL" not in names[:a]      # F_in has one entry per finite element
+
+
+def _chain_fields(pc):
+    """Decode a PCHAIN instruction (csrc/poly_chain.cuh): blocks [(x_off, flops, kind, minv, [(n_off, meta)] * 3)], quadratures."""
+    w = [int(x) for x in pc]
+    nb, nq = w[1] & 0xFF, (w[1] >> 8) & 0xFF
+    blocks = [(w[8 + 12 * b], w[9 + 12 * b], w[10 + 12 * b], w[11 + 12 * b],
+               [(w[12 + 12 * b + 2 * k], w[13 + 12 * b + 2 * k]) for k in range(3)]) for b in range(nb)]
+    q0 = 8 + 12 * nb
+    quads = [(w[q0 + 4 * q], w[q0 + 4 * q + 1], w[q0 + 4 * q + 2]) for q in range(nq)]
+    return nb, nq, w[2], blocks, quads
+
+
+def _meta(m):
+    return dict(present=m & 1, has_n=(m >> 1) & 1, has_ctrl=(m >> 2) & 1, ctrl=(m >> 4) & 15, p=(m >> 8) & 3, src=(m >> 12) & 3)
+
+
+def test_fused_chain_program_c3():
+    """design4 (config C3): the whole element loop is one PCHAIN between two sections of scalar ops; no INIT, no POLY1."""
+    lm = models.kinetics("design4").lower()
+    ops, info = capi.assemble(lm.blob)
+    names = _names(ops)
+    assert names.count("PCHAIN") == 1 and names[-1] == "END" and "INIT" not in names and "POLY1" not in names
+    assert set(names) <= {"FMAG", "DIV1", "RCP1", "COLD1", "LDCTRL", "PCHAIN", "XEND", "END"}
+    k = names.index("PCHAIN")
+    assert names[k + 1] == "XEND" and "LDCTRL" in names[:k]                    # Fbar: element invariant, loaded before the chain
+    assert info["chain_blocks"] == 2 and info["chain_shape_registered"] == 1
+    assert (info["chain_shape_sb"], info["chain_shape_sq"]) == (0x18B980062, 0x5C1A)        # csrc/chain_shapes.h
+    nb, nq, max_it, blocks, quads = _chain_fields(ops[k][2])
+    assert (nb, nq, max_it) == (2, 2, lm.newton_max_it)
+    (xa, fa, ka, _, ca), (xb, fb, kb, minv, cb) = blocks
+    assert ka == 0 and fa == lm.block_flops[0]                                 # cA: Newton
+    assert [_meta(m)["present"] for _, m in ca] == [1, 0, 1] and all(_meta(m)["p"] == 0 for _, m in ca)
+    assert kb == 2 and fb == 24                                                # cB: linear, constant decay -> one inverse
+    m0 = _meta(cb[0][1])
+    assert (m0["present"], m0["has_n"], m0["p"], m0["src"]) == (1, 1, 2, 0)    # c0 = narrow * cA^2
+    assert _meta(cb[1][1])["p"] == 0 and _meta(cb[2][1])["present"] == 0
+    unit = 2 * 1024 * 8 // 8                                                   # bytes per unit, two scenarios per thread
+    assert minv // unit >= lm.tapes.layout.x_slot and minv // unit + 9 <= info["units"]     # scratch: dead wide units
+    assert [(_meta(m)["p"], _meta(m)["src"]) for _, _, m in quads] == [(0, 0), (1, 1)]      # u: element constant; cC: k * cB
+    # every non-FMAG scalar op carries the length of the FMAG run that follows it
+    for sec in (range(0, k), range(k + 2, len(ops) - 1)):
+        run = 0
+        for i in reversed(list(sec)):
+            if names[i] == "FMAG":
+                run += 1
+            else:
+                assert int(ops[i][2][7]) == run
+                run = 0
+
+
+def test_fused_chain_per_element_controls():
+    """twostage: F_in differs between the elements, so no LDCTRL / elem ops remain -- the chain multiplies the narrow
+    factor by the element's control itself (c0 of cA = t_f * F_in, u integrand = F_in / t_f)."""
+    ops, info = capi.assemble(models.kinetics("twostage").lower().blob)
+    names = _names(ops)
+    assert "LDCTRL" not in names and names.count("PCHAIN") == 1
+    assert info["chain_shape_registered"] == 1 and info["chain_shape_sb"] == 0x18B980062 | 4
+    _, _, _, blocks, quads = _chain_fields(ops[names.index("PCHAIN")][2])
+    m = _meta(blocks[0][4][0][1])
+    assert (m["has_n"], m["has_ctrl"], m["ctrl"], m["p"]) == (1, 1, 0, 0)
+    mq = _meta(quads[0][2])
+    assert (mq["has_ctrl"], mq["ctrl"], mq["p"]) == (1, 0, 0)
+    assert all(_meta(mm)["has_ctrl"] == 0 for _, mm in blocks[1][4]) and _meta(quads[1][2])["has_ctrl"] == 0
+
+
+def test_models_outside_the_chain_shape_keep_the_interpreted_loop():
+    # a right-hand side with two mass-action terms in c0 (k3 cD + k1 cA^2) is not a single term
+    m = DaeModel(["a"], ["k"], nfe=4)
+    xa, xd, xb = m.state("xa", 1.0), m.state("xd", 0.5), m.state("xb", 0.0)
+    k = m.p["k"]
+    m.ode(xa, -k * xa * xa)
+    m.ode(xd, -0.3 * xd)
+    m.ode(xb, k * xa * xa + 0.3 * xd - m.d["a"] * xb)
+    m.constraint("c", m.end(xb) - 0.4, 1.0)
+    ops, info = capi.assemble(m.lower().blob)
+    assert info["chain_blocks"] == 0 and _names(ops).count("POLY1") == 3 and "INIT" in _names(ops)
 
 
 def test_generic_paths_and_kernel_instantiations():
