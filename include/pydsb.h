@@ -16,6 +16,8 @@
  *   - one handle per (process, device); a handle is not thread-safe.  The handles of one process share the
  *     program window in constant memory (every evaluation call re-uploads its model's program, stream ordered):
  *     calls on DIFFERENT handles of the same device must be issued on the same stream or be synchronised.
+ *     On ONE handle the *_host entry points (which work on a private stream) are ordered after every earlier
+ *     asynchronous call of that handle by an event; asynchronous calls on different streams are the caller's to order.
  */
 #ifndef PYDSB_H
 #define PYDSB_H
@@ -176,6 +178,16 @@ int pydsb_recourse_solve_global_dist(void* handle, const double* d, long long n_
 
 /* Counters since the last reset (device-side totals; synchronises the handle's work). */
 int pydsb_get_counters(void* handle, unsigned long long* out, int n, int reset);
+
+/* Per-kernel device time (CUDA events on the call's stream around every launch of the three compute kernels) since the
+ * last reset -- what bench.py's roofline figures divide by.  Off by default (two event records per launch).
+ * pydsb_get_profile synchronises the device; out[i] per the enum below (ms / launch counts). */
+enum {
+    PYDSB_PROF_FEAS_MS = 0, PYDSB_PROF_FEAS_LAUNCHES, PYDSB_PROF_SENS_MS, PYDSB_PROF_SENS_LAUNCHES, PYDSB_PROF_LM_MS,
+    PYDSB_PROF_LM_LAUNCHES, PYDSB_PROF_COUNT
+};
+int pydsb_set_profiling(void* handle, int on);
+int pydsb_get_profile(void* handle, double* out, int n, int reset);
 
 /* Measured FP64 FMA throughput of the device (dependent-chain-free DFMA microkernel, CUDA-event
  * timed): the roofline denominator for this path.  Returns TFLOP/s in *tflops (2 flop per FMA). */

@@ -38,15 +38,26 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     """``defines``/``out``: development variants (tools/build_variant.py), loaded through PYDSB_LIB."""
     if not force and not is_stale() and out == LIB:
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
-          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
-    env = dict(os.environ)
-    # the image exports CC/CXX pointing at a gcc without its spec files; let nvcc pick the system one
-    env.pop("CC", None)
-    env.pop("CXX", None)
-    res = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    # several processes may get here at once (torchrun ranks after a fresh checkout): one builds, under a file lock, into
+    # a temporary file that is renamed over the target -- nobody can dlopen a half-written library
+    import fcntl
+    with open(out + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and out == LIB and not is_stale():
+            return LIB                                   # another process built it while this one waited
+        tmp = f"{out}.tmp.{os.getpid()}"
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+              ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+        env = dict(os.environ)
+        # the image exports CC/CXX pointing at a gcc without its spec files; let nvcc pick the system one
+        env.pop("CC", None)
+        env.pop("CXX", None)
+        res = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
+        if res.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        os.replace(tmp, out)
     if verbose:
         print(res.stdout + res.stderr)
     return out

@@ -23,7 +23,8 @@ COUNTER_NAMES = ["scenarios", "newton_iters", "newton_warp_iters", "failed", "la
 EXPORTS = ["pydsb_last_error", "pydsb_version", "pydsb_model_create", "pydsb_model_destroy", "pydsb_model_info",
            "pydsb_eval", "pydsb_eval_tol", "pydsb_eval_g", "pydsb_efp", "pydsb_eval_host", "pydsb_state_solve", "pydsb_recourse_solve",
            "pydsb_recourse_solve_global_dist", "pydsb_get_counters", "pydsb_dfma_peak", "pydsb_assemble",
-           "pydsb_ns_replace_worst", "pydsb_ns_ellipsoid"]
+           "pydsb_ns_replace_worst", "pydsb_ns_ellipsoid", "pydsb_set_profiling", "pydsb_get_profile"]
+PROFILE_NAMES = ["feas_ms", "feas_launches", "sens_ms", "sens_launches", "lm_ms", "lm_launches"]
 # int (*pydsb_allreduce_fn)(double* device_buf, int n, void* user)
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
 
@@ -82,6 +83,10 @@ def load():
     L.pydsb_recourse_solve_global_dist.argtypes = [vp, dp, ll, ll, dp, dp, ll, dp, dp, dp, dp, vp, vp, dp, ALLREDUCE_FN, vp, vp]
     L.pydsb_get_counters.restype = ci
     L.pydsb_get_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong), ci, ci]
+    L.pydsb_set_profiling.restype = ci
+    L.pydsb_set_profiling.argtypes = [vp, ci]
+    L.pydsb_get_profile.restype = ci
+    L.pydsb_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ci, ci]
     L.pydsb_dfma_peak.restype = ci
     L.pydsb_dfma_peak.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _LIB = L
@@ -312,6 +317,15 @@ class Engine:
             for k in ("phi", "status", "iters"):
                 out[k] = out[k].reshape(n_d, n_t)
         return out
+
+    def set_profiling(self, on=True):
+        """Per-kernel device time (CUDA events around every launch); read with :meth:`profile`."""
+        _check(self._lib.pydsb_set_profiling(self._h, 1 if on else 0))
+
+    def profile(self, reset=False):
+        buf = (ctypes.c_double * len(PROFILE_NAMES))()
+        _check(self._lib.pydsb_get_profile(self._h, buf, len(PROFILE_NAMES), 1 if reset else 0))
+        return {k: float(v) for k, v in zip(PROFILE_NAMES, buf)}
 
     def counters(self, reset=False):
         buf = (ctypes.c_ulonglong * len(COUNTER_NAMES))()

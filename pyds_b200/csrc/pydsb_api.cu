@@ -88,7 +88,48 @@ struct Model {
     // groups, thousands of times): cudaMalloc/cudaFree cost more than the kernels there
     void* rws[3] = {nullptr, nullptr, nullptr};
     size_t rws_cap[3] = {0, 0, 0};
+    // eval_host works on own_stream while the device entry points work on the caller's stream, and both use the model's
+    // partial-sum buffer and the program window in constant memory: own_stream waits for the last asynchronous launch
+    cudaEvent_t ev_async = nullptr;
+    bool async_pending = false;
+    // per-kernel device time (pydsb_set_profiling): event pairs around launches, folded into ms[] by prof_collect
+    bool prof_on = false;
+    struct ProfRec { int kind; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    double prof_ms[3] = {0.0, 0.0, 0.0};
+    unsigned long long prof_n[3] = {0, 0, 0};
 };
+
+// RAII: events around one launch of kernel class `kind` (0 feas, 1 sens, 2 lm_update) when profiling is on
+struct ProfScope {
+    Model* m; cudaStream_t st; int kind; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(Model* m_, int kind_, cudaStream_t st_) : m(m_), st(st_), kind(kind_)
+    {
+        if (!m->prof_on) return;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+        cudaEventRecord(e0, st);
+    }
+    ~ProfScope()
+    {
+        if (!e0 || !e1) return;
+        cudaEventRecord(e1, st);
+        m->prof_recs.push_back(Model::ProfRec{kind, e0, e1});
+    }
+};
+
+void prof_collect(Model* m)
+{
+    for (const Model::ProfRec& r : m->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            m->prof_ms[r.kind] += ms;
+            m->prof_n[r.kind] += 1;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    m->prof_recs.clear();
+}
 
 typedef void (*FeasFn)(const ExecImage, const LaunchArgs);
 typedef void (*SensFn)(const ExecImage, const RecourseArgs);
@@ -624,6 +665,7 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
     cudaFuncAttributes fa{};
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fn);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_async, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         std::string msg = std::string("model upload: ") + cudaGetErrorString(e);
         pydsb_model_destroy(m);
@@ -762,6 +804,8 @@ int pydsb_model_destroy(void* handle)
     if (m->d_stage) cudaFree(m->d_stage);
     for (void* p : m->rws) if (p) cudaFree(p);
     if (m->h_pin) cudaFreeHost(m->h_pin);
+    prof_collect(m);
+    if (m->ev_async) cudaEventDestroy(m->ev_async);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     delete m;
     return PYDSB_OK;
@@ -801,6 +845,11 @@ int eval_impl(void* handle, const double* d, long long n_d, const double* theta,
         if (P_out) CUDA_TRY(cudaMemsetAsync(P_out, 0, (size_t)n_d * sizeof(double), st));
         return PYDSB_OK;
     }
+    if (st == m->own_stream && m->async_pending) {
+        // an asynchronous call on the caller's stream may still be using the partial sums and the program window
+        CUDA_TRY(cudaStreamWaitEvent(st, m->ev_async, 0));
+        m->async_pending = false;
+    }
     const long long tile = (long long)img.spt * BLOCK;               // theta rows per tile
     // a theta set of at most half a tile (the shipped scripts use 50 samples): tile / n_t design points share a tile
     const bool pack = !traj && 2 * n_t <= tile;
@@ -833,7 +882,10 @@ int eval_impl(void* handle, const double* d, long long n_d, const double* theta,
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, xp.data(), xp.size() * sizeof(uint32_t), 0, cudaMemcpyHostToDevice, st));
     if (chain > 0 && !traj)
         CUDA_TRY(cudaMemcpyToSymbolAsync(c_chain, &m->prog[0].chain, sizeof(ChainDesc), 0, cudaMemcpyHostToDevice, st));
-    fn<<<grid, BLOCK, img.smem_bytes, st>>>(img, la);
+    {
+        ProfScope ps(m, 0, st);
+        fn<<<grid, BLOCK, img.smem_bytes, st>>>(img, la);
+    }
     CUDA_TRY(cudaGetLastError());
     m->launches += 1;
     if (P_out) {
@@ -841,6 +893,10 @@ int eval_impl(void* handle, const double* d, long long n_d, const double* theta,
         reduce_partials_kernel<<<(unsigned)((n_d + tb - 1) / tb), tb, 0, st>>>(m->d_partial, n_part, n_d, P_out);
         CUDA_TRY(cudaGetLastError());
         m->launches += 1;
+    }
+    if (st != m->own_stream) {
+        CUDA_TRY(cudaEventRecord(m->ev_async, st));
+        m->async_pending = true;
     }
     return PYDSB_OK;
 }
@@ -1067,7 +1123,10 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
         ra.active = act_in; ra.n_active = n_in;
         const unsigned sens_grid = compact ? (unsigned)((upper + BLOCK - 1) / BLOCK) : (unsigned)total_tiles;
         if (sens_grid > 0) {
-            fn<<<sens_grid, BLOCK, img.smem_bytes, st>>>(img, ra);
+            {
+                ProfScope ps(m, 1, st);
+                fn<<<sens_grid, BLOCK, img.smem_bytes, st>>>(img, ra);
+            }
             CUDA_TRY_WS(cudaGetLastError());
         }
         if (per_scenario == 2) {
@@ -1085,8 +1144,11 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
         }
         la.active_in = act_in; la.n_active_in = n_in; la.n_running = n_out;
         la.active_out = compact ? act + (size_t)(it & 1) * G : nullptr;
-        if (nz <= 8) lm_update_kernel<8><<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
-        else lm_update_kernel<0><<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
+        {
+            ProfScope ps(m, 2, st);
+            if (nz <= 8) lm_update_kernel<8><<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
+            else lm_update_kernel<0><<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
+        }
         CUDA_TRY_WS(cudaGetLastError());
         m->launches += 2;
         if (compact) { act_in = la.active_out; n_in = n_out; }
@@ -1144,6 +1206,29 @@ int pydsb_get_counters(void* handle, unsigned long long* out, int n, int reset)
         CUDA_TRY(cudaMemset(m->d_counters, 0, sizeof(v)));
         m->launches = 0;
     }
+    return PYDSB_OK;
+}
+
+int pydsb_set_profiling(void* handle, int on)
+{
+    Model* m = static_cast<Model*>(handle);
+    if (!m) return fail(PYDSB_ERR_INVALID, "null handle");
+    m->prof_on = on != 0;
+    return PYDSB_OK;
+}
+
+int pydsb_get_profile(void* handle, double* out, int n, int reset)
+{
+    Model* m = static_cast<Model*>(handle);
+    if (!m || !out) return fail(PYDSB_ERR_INVALID, "null handle/out");
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    prof_collect(m);
+    const double v[PYDSB_PROF_COUNT] = {m->prof_ms[0], (double)m->prof_n[0], m->prof_ms[1], (double)m->prof_n[1],
+                                        m->prof_ms[2], (double)m->prof_n[2]};
+    for (int i = 0; i < n && i < PYDSB_PROF_COUNT; ++i) out[i] = v[i];
+    if (reset)
+        for (int k = 0; k < 3; ++k) { m->prof_ms[k] = 0.0; m->prof_n[k] = 0; }
     return PYDSB_OK;
 }
 

@@ -65,7 +65,9 @@ class ShardedEfp:
         import torch
         import torch.distributed as dist
         backend = dist.get_backend(self.group)
-        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        # the gather runs on the engine's device (a manager may have been given an explicit one)
+        dev = torch.device("cuda", getattr(self.engine, "device", torch.cuda.current_device())) if backend == "nccl" \
+            else torch.device("cpu")
         t = torch.from_numpy(np.ascontiguousarray(P_local, dtype=np.float64)).to(dev)
         if sizes is None:
             sizes = [None] * self.world

@@ -211,6 +211,22 @@ def lower_stage_model(model, input_map, f_profile_suffix=None, **model_kw):
     return dm
 
 
+def _default_device() -> int:
+    """The GPU of this process: under torchrun every rank owns one device (LOCAL_RANK, or the device the caller made
+    current), so that N managers do not all land on GPU 0; a single process uses device 0."""
+    import os
+    try:
+        import torch
+        if torch.cuda.is_available():
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                if "LOCAL_RANK" in os.environ:
+                    return int(os.environ["LOCAL_RANK"]) % max(torch.cuda.device_count(), 1)
+                return int(torch.cuda.current_device())
+    except Exception:
+        pass
+    return 0
+
+
 class Simulator:
     def __init__(self, parent, config):
         self.parent = parent
@@ -228,7 +244,7 @@ class Simulator:
         self.user_time = None
         self.output = []
         self._traj = None
-        self.device = int(config.get("device", 0))
+        self.device = int(config["device"]) if "device" in config else _default_device()
         self._build_model()
         self.input_names = []
         for stage, names in self.parent.input_map.items():
