@@ -9,11 +9,19 @@ scaling, theta replicated) and the step ends with the all-gather of the per-poin
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n-d ND] [--n-theta NT]
 
-Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU restatement of the reference
-path (the reference itself -- Pyomo + GAMS/CONOPT + DEUS -- cannot be installed here, see
-DESIGN.md) on the host cores, on a bounded sample of the same workload.
+Prints ONE JSON line (rank 0).  Besides the contract keys it carries
+  configs[]    the other BASELINE.json configs measured in the same run: C4 (1e3 x 1e4, 8 recourse controls per scenario:
+               sens_kernel + lm_update_kernel with their own roofline), C1 (run_twostage.py's g(150 x 50) through the
+               manager), C3 at FIXED total work (strong scaling) and the C5 nested-sampling iteration (6 design variables,
+               1e5 live points x 1e5 theta sharded over the ranks);
+  ns_iteration seconds per nested-sampling iteration at config C5 (BASELINE.json's second metric).
+``--impl reference`` times the CPU restatement of the reference path (the reference itself -- Pyomo + GAMS/CONOPT +
+DEUS -- cannot be installed here) on the host cores, on a bounded sample of the same workload, in the
+formulation ``--ref-formulation`` names (blocktri: the equations as the GPU solves them; dense9: the 9-unknown Newton
+system SURVEY.md A.5 counts).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -46,6 +54,12 @@ def emit(line):
     os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def workload(n_d, n_t):
+    """The workload string of BOTH arms (the driver compares them)."""
+    return (f"C3 synthetic kinetics (A->B->C semi-batch, Radau 8x3), 4 design vars, {n_d} design points per GPU x "
+            f"{n_t} theta, no recourse; P(feasible) per point")
+
+
 def make_inputs(n_d, n_t, rank=0, rows=None):
     """Config C3 inputs (SURVEY.md 8d): d = (t_f, T, cA0, Fbar) uniform in the box, seed 1989 (+rank);
     theta as run_twostage.py:113-116 with size n_t, seed 12341234; w = 1/n_t.  ``rows`` keeps only the
@@ -60,6 +74,53 @@ def make_inputs(n_d, n_t, rank=0, rows=None):
                       ran.normal(9.938e3, 9.938e1, n_t)], axis=1)
     w = np.full(n_t, 1.0 / n_t)
     return d, theta, w
+
+
+def source_hash():
+    """sha256 over the kernel sources: the committed ncu figures (profiles/traffic_feas_kernel.json) are only quoted
+    while the kernels they were captured from are the ones that run."""
+    h = hashlib.sha256()
+    src = os.path.join(ROOT, "pyds_b200", "csrc")
+    for name in sorted(os.listdir(src)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(src, name), "rb").read())
+    return h.hexdigest()
+
+
+def committed_ncu(kernel_name, n_d, n_t, path=None, current_hash=None):
+    """(traffic bytes per launch, pipe figures, note) from the committed ncu capture, or (None, None, why) when it was
+    taken from other kernel sources or another shape."""
+    path = path or os.path.join(ROOT, "profiles", "traffic_feas_kernel.json")
+    try:
+        tj = json.load(open(path))
+    except (OSError, ValueError):
+        return None, None, "no committed capture"
+    if tj.get("kernel") != kernel_name or tj.get("n_d") != n_d or tj.get("n_theta") != n_t:
+        return None, None, "committed capture is of another kernel / shape"
+    if tj.get("source_sha256") != (current_hash or source_hash()):
+        return None, None, "kernel sources changed since the committed capture (stale: not quoted)"
+    pipes = {k: tj[k] for k in ("fp64_pipe_active_pct", "issue_active_pct", "shared_wavefronts_pct") if k in tj}
+    return tj["dram_bytes_read"] + tj["dram_bytes_write"], pipes, tj.get("source")
+
+
+def sens_flops_per_solve(lm, newton_iters_per_solve):
+    """Algorithmic flops of ONE state + control-sensitivity solve of sens_kernel (SURVEY.md 8d convention applied to the
+    algorithm that runs: FMA = 2, a division 1).  Per Newton iteration of an element: the point tape at the three
+    points, the linear collocation residual 2 n (ncp + 1), the factorisation and one solve; once more per element at the
+    converged point (the factors the sensitivities reuse); per element and control that has acted so far: a
+    right-hand side (2 n) and a solve, plus the quadrature sensitivities.  The Newton system of the kinetics is block
+    lower triangular (ns systems of 3 unknowns with the coupling substituted)."""
+    fl = lm.tapes_sens.stats["flops"]
+    ns, ncp, nfe = lm.ns, lm.ncp, lm.nfe
+    n = ns * ncp
+    factor = ns * (2 * 27) // 3
+    solve = ns * 2 * 9 + ns * (ns - 1) // 2 * 2 * ncp
+    per_iter = ncp * fl["pt0"] + 2 * n * (ncp + 1) + factor + solve
+    per_elem = ncp * fl["pt0"] + 2 * n * (ncp + 1) + factor
+    live = sum(len(set(int(z) for z in lm.cmap[:e + 1].reshape(-1))) for e in range(nfe))     # controls acted so far
+    per_sens = 2 * n + solve + 2 * ncp * (lm.nq + 1)
+    return fl["pro"] + fl["g"] + nfe * (fl["elem"] + per_elem) + newton_iters_per_solve * per_iter + live * per_sens
 
 
 class ClockSampler:
@@ -113,15 +174,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(n_rows, n_t, threads, tol=1e-10, n_d=10000):
-    """Time the C restatement (oracle, kind 'port') on `threads` host threads over n_rows x n_t."""
+def cpu_baseline(n_rows, n_t, threads, tol=1e-10, n_d=10000, formulation="blocktri"):
+    """Time the C restatement (oracle, kind 'port') on `threads` host threads over n_rows x n_t.
+    Returns (evals/s, seconds, P, Newton iterations per evaluation)."""
     from oracle import cbind
     d, theta, w = make_inputs(n_d, n_t, rows=n_rows)
-    cbind.kinetics_grid(d[:8], theta[:64], w[:64], tol=tol, want_g=False, threads=threads)      # warm
+    cbind.kinetics_grid(d[:8], theta[:64], w[:64], tol=tol, want_g=False, threads=threads, formulation=formulation)      # warm
     t0 = time.perf_counter()
-    _, P, it = cbind.kinetics_grid(d, theta, w, tol=tol, want_g=False, threads=threads)
+    _, P, it = cbind.kinetics_grid(d, theta, w, tol=tol, want_g=False, threads=threads, formulation=formulation)
     dt = time.perf_counter() - t0
-    return n_rows * n_t / dt, dt, P, it
+    return n_rows * n_t / dt, dt, P, abs(it) / float(n_rows * n_t)
 
 
 class _EfpOwner:
@@ -138,28 +200,55 @@ class _EfpOwner:
         raise NotImplementedError("the bench uses the fused efp path")
 
 
-def ns_iteration_seconds(sharded, n_live, theta, w, iterations):
-    """Seconds per nested-sampling iteration (BASELINE.json's second metric) of pyds_b200.ns at the bench
-    configuration: n_live live points, n_live/10 proposals per iteration drawn from the enlarged bounding
-    ellipsoid of the live set (host, numpy), their P(feasible) over all theta through the host-buffer path
-    (H2D, kernels, D2H, all-gather), live-set update."""
+C5_BOX = [{"t_f": [250.0, 350.0]}, {"T": [250.0, 300.0]}, {"cA0": [1500.0, 2500.0]}, {"Fbar": [0.0, 2.5]},
+          {"pB": [90.0, 110.0]}, {"pA": [15.0, 25.0]}]
+
+
+def ns_iteration_seconds(sharded, design_box, n_live, theta, w, iterations):
+    """Seconds per nested-sampling iteration (BASELINE.json's second metric) of pyds_b200.ns: n_live live points,
+    n_live/10 proposals per iteration from the enlarged bounding ellipsoid of the live set, their P(feasible) over all
+    theta sharded over the ranks, live-set update.  Returns (s per iteration, iterations, proposals, s of the initial
+    live-set evaluation)."""
     from pyds_b200 import ns
     owner = _EfpOwner(sharded)
+    n_rep = max(n_live // 10, 1)
     form = {
         "activity_type": "ds",
-        "problem": {"design_variables": [{"t_f": [250.0, 350.0]}, {"T": [250.0, 300.0]}, {"cA0": [1500.0, 2500.0]},
-                                         {"Fbar": [0.0, 2.5]}],
+        "problem": {"design_variables": design_box,
                     "parameters_best_estimate": [2.5e3, 5e3, 6.409e-2, 9.938e3],
                     "parameters_samples": [{"c": row, "w": float(wi)} for row, wi in zip(theta, w)],
                     "target_reliability": 0.65},
         "solver": {"name": "ds-ns",
                    "settings": {"efp_evaluation": {"constraints_func_ptr": owner.g},
-                                "points_schedule": [(0.0, n_live, max(n_live // 10, 1))],
+                                "points_schedule": [(0.0, n_live, n_rep)],
                                 "stop_criteria": [{"inside_fraction": 1.0}]},
                    "algorithms": {"sampling": {"settings": {"prng_seed": 1989, "stop_criteria": [{"max_iterations": iterations}]}}}},
     }
+    t0 = time.time()
     res = ns.DEUS(form).solve()
-    return res["seconds_per_iteration"], res["iterations"], max(n_live // 10, 1)
+    wall = time.time() - t0
+    return res["seconds_per_iteration"], res["iterations"], n_rep, wall - res["seconds_per_iteration"] * res["iterations"]
+
+
+def reference_line(args, value, ms, threads, iters_per_eval):
+    from oracle import cbind
+    rows, n_t = args.ref_rows, args.n_theta
+    sample = f"{rows} of the {args.n_d} design points x all {n_t} theta per step (same seeds as the GPU arm)"
+    return {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload(args.n_d, n_t), "n_d_per_gpu": args.n_d, "n_theta": n_t,
+                   "sample_per_step": sample,
+                   "reference_impl": "CPU restatement in C + OpenMP (oracle/kinetics_c.c); the Pyomo+GAMS/CONOPT+DEUS "
+                                     "reference is not installable in this image",
+                   "formulation": args.ref_formulation,
+                   "newton_iters_per_eval": iters_per_eval,
+                   "flops_per_eval": cbind.flops_per_eval(args.ref_formulation, iters_per_eval)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
 
 
 def run_reference(args):
@@ -171,27 +260,135 @@ def run_reference(args):
     rows = args.ref_rows
     from oracle import cbind  # noqa: F401  (builds the C oracle if needed)
     for _ in range(args.warmup):
-        cpu_baseline(max(rows // 8, 1), n_t, threads, n_d=args.n_d)
-    times = []
+        cpu_baseline(max(rows // 8, 1), n_t, threads, n_d=args.n_d, formulation=args.ref_formulation)
+    times, its = [], []
     for _ in range(args.steps):
-        v, dt, _, _ = cpu_baseline(rows, n_t, threads, n_d=args.n_d)
-        times.append(dt)
+        v, dt, _, it = cpu_baseline(rows, n_t, threads, n_d=args.n_d, formulation=args.ref_formulation)
+        times.append(dt); its.append(it)
     ms = 1e3 * float(np.mean(times))
-    value = rows * n_t / (ms * 1e-3)
-    sample = f"{rows} of the {args.n_d} design points x all {n_t} theta per step (same seeds as the GPU arm)"
+    emit(reference_line(args, rows * n_t / (ms * 1e-3), ms, threads, float(np.mean(its))))
+
+
+def build_line(m):
+    """The JSON line of the B200 arm from the measurements in ``m`` (a pure function: tests/test_bench_contract_cpu.py
+    runs it on stub numbers)."""
+    n_d, n_t, world = m["n_d"], m["n_t"], m["world"]
+    evals_per_step = world * n_d * n_t
+    value = evals_per_step / (m["ms_per_step"] * 1e-3)
+    achieved = n_d * n_t * m["f_alg"] / (m["kernel_ms"] * 1e-3) / 1e12
+    pipe = (m.get("ncu_pipes") or {}).get("fp64_pipe_active_pct")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3 synthetic kinetics, 4 design vars, {args.n_d} x {n_t} (d,theta), no recourse; "
-                               f"bounded sample of {rows} design points per step",
-                   "reference_impl": "CPU restatement in C + OpenMP (oracle/kinetics_c.c); the Pyomo+GAMS/CONOPT+DEUS "
-                                     "reference is not installable in this image"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": m["steps"], "warmup": m["warmup"],
+        "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload(n_d, n_t),
+                   "n_d_per_gpu": n_d, "n_theta": n_t, "sharding": f"design points over {world} GPU(s), theta replicated",
+                   "l2": "256 MiB buffer written between timed steps (flush); inputs are < 1 MB, the path is fp64-pipe bound",
+                   "newton_iters_per_element": m["newton_iters_per_element"], "flops_per_eval": m["f_alg"],
+                   "formulation": m["formulation"], "state_blocks": m["state_blocks"]},
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": m["peak_tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / m["peak_tflops"], "frac_fp64_pipe_ncu": None if pipe is None else pipe / 100.0,
+                     "traffic": m.get("traffic"), "kernel": m["kernel_name"], "ncu": m.get("ncu_pipes"),
+                     "ncu_note": m.get("ncu_note"), "kernel_ms": m["kernel_ms"],
+                     "algorithmic_bytes": 8 * (n_d * m["d_dim"] + n_t * (m["p_dim"] + 1) + n_d),
+                     "peak_source": "measured in this run: pydsb_dfma_peak (independent-chain DFMA microkernel, best of 5); "
+                                    "MEASURED_PEAKS.json carries no fp64 figure"},
+        "cpu_baseline": m.get("cpu"),
+        "e2e": {"value": evals_per_step / m["e2e_s"], "unit": UNIT,
+                "h2d_bytes_per_step": 8 * (n_d * m["d_dim"] + n_t * m["p_dim"] + n_t) * world,
+                "d2h_bytes_per_step": 8 * n_d * world, "matches_device_path": m["e2e_matches"]},
+        "configs": m.get("configs", []),
+        "ns_iteration": m.get("ns_iteration"),
+        "gpu_launches": m["counters"]["launches"],
+        "clocks": m["clocks"],
+        "counters": m["counters"],
     }
-    emit(line)
+    return line
+
+
+def c4_section(torch, capi, models, dev, peak_tflops, n_d=1000, n_t=10000):
+    """Config C4: synthetic two-stage model, 8 recourse controls re-optimised PER SCENARIO, 1e3 design points x 1e4 theta
+    (batched Levenberg-Marquardt on the smoothed hinge: sens_kernel + lm_update_kernel), then the shared-control
+    (reference-shaped) solve of the same grid."""
+    lm = models.kinetics("twostage").lower()
+    eng = capi.Engine(lm.blob, dev.index)
+    rng = np.random.default_rng(1989)
+    d = np.stack([rng.uniform(250, 350, n_d), rng.uniform(250, 300, n_d)], axis=1)
+    _, p, w = make_inputs(10, n_t)
+    td, tp, tw = (torch.from_numpy(a).to(dev) for a in (d, p, w))
+    eng.recourse_solve_device(td[:4].contiguous(), tp[:256].contiguous(), per_scenario=True)             # warm-up
+    torch.cuda.synchronize()
+    eng.set_profiling(True)
+    eng.counters(reset=True); eng.profile(reset=True)
+    t0 = time.perf_counter()
+    r = eng.recourse_solve_device(td, tp, per_scenario=True, max_iter=50)
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    c, pr = eng.counters(), eng.profile()
+    solves = c["scenarios"]
+    iters = c["newton_iters"] / max(solves, 1)
+    f_alg = sens_flops_per_solve(lm, iters)
+    achieved = solves * f_alg / (pr["sens_ms"] * 1e-3) / 1e12
+    # classification at the optimised controls, and how many scenarios sit inside the relaxed big-M tolerance band
+    g = torch.empty((n_d, n_t, lm.ng), dtype=torch.float64, device=dev)
+    eng.eval_device(td, tp, None, z=r["z"].view(n_d, n_t, lm.nz).contiguous(), z_mode=capi.Z_PER_SCENARIO, g_out=g)
+    cmax = (g / torch.tensor(lm.big_m, device=dev)).amax(dim=-1)
+    band = int(((cmax > 0) & (cmax <= 1e-7)).sum().item())
+    feas0 = int((cmax <= 0).sum().item())
+    out = {"name": "C4", "workload": f"synthetic two-stage kinetics, 8 recourse controls per scenario, {n_d} x {n_t} (d,theta), "
+                                     "batched Levenberg-Marquardt on the smoothed hinge, iteration cap 50",
+           "value": n_d * n_t / secs, "unit": "scenario optimisations/s", "seconds": secs,
+           "state_sensitivity_solves": solves, "solves_per_scenario": solves / (n_d * n_t),
+           "solves_per_s": solves / secs, "newton_iters_per_solve": iters,
+           "kernels": {"sens_kernel_ms": pr["sens_ms"], "sens_launches": int(pr["sens_launches"]),
+                       "lm_update_kernel_ms": pr["lm_ms"], "lm_launches": int(pr["lm_launches"]),
+                       "lm_share_of_kernel_time": pr["lm_ms"] / max(pr["sens_ms"] + pr["lm_ms"], 1e-12),
+                       "kernel_time_share_of_wall": (pr["sens_ms"] + pr["lm_ms"]) * 1e-3 / secs},
+           "roofline": {"bound": "fp64", "kernel": f"sens_kernel<{lm.ns},tri>", "kernel_ms": pr["sens_ms"],
+                        "flops_per_solve": f_alg, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                        "frac": achieved / peak_tflops},
+           "classification": {"feasible_at_optimum": feas0, "inside_1e-7_band": band, "scenarios": n_d * n_t,
+                              "status_counts": {int(k): int(v) for k, v in zip(*np.unique(r["status"].cpu().numpy(), return_counts=True))}}}
+    del g, r
+    # the reference's own formulation: ONE control vector per design point, shared by every theta
+    eng.counters(reset=True); eng.profile(reset=True)
+    z0 = torch.zeros((1, lm.nz), dtype=torch.float64, device=dev)
+    t0 = time.perf_counter()
+    rs = eng.recourse_solve_device(td, tp, tw, z0)
+    torch.cuda.synchronize()
+    secs_s = time.perf_counter() - t0
+    cs, ps = eng.counters(), eng.profile()
+    out["shared_control"] = {"what": "one control vector per design point (reference pyds/run.py:55-67), same grid",
+                             "seconds": secs_s, "design_points_per_s": n_d / secs_s, "evaluations_per_design_point": float(rs["iters"].double().mean().item()),
+                             "state_sensitivity_solves": cs["scenarios"], "sens_kernel_ms": ps["sens_ms"], "lm_update_kernel_ms": ps["lm_ms"]}
+    eng.set_profiling(False)
+    return out
+
+
+def c1_section(np_, tempfile_mod):
+    """Config C1: the shipped two-stage script's call shape -- g(150 design points x 50 theta) through TwoStageManager,
+    control optimisation included (what DEUS calls once per nested-sampling iteration)."""
+    from examples import twostage_reactor as ex2
+    from examples.reactor_model import theta_samples
+    from pyds_b200.run import TwoStageManager
+    m = TwoStageManager(ex2.build_config(tempfile_mod.mkdtemp()))
+    _, p_samples = theta_samples()
+    rng = np_.random.default_rng(1989)
+    d150 = np_.stack([rng.uniform(250, 350, 150), rng.uniform(250, 300, 150)], axis=1)
+    p50 = np_.array([s["c"] for s in p_samples])
+    m.g(d150[:10], p50)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter(); m.g(d150, p50); ts.append(time.perf_counter() - t0)
+    te = []
+    for _ in range(5):
+        t0 = time.perf_counter(); P = m.efp(d150, p50, np_.full(50, 0.02)); te.append(time.perf_counter() - t0)
+    res = getattr(m.solver, "result", {}) or {}
+    return {"name": "C1", "workload": "run_twostage.py as shipped: TwoStageManager.g(150 design points x 50 theta), one control "
+                                      "vector optimised per design point",
+            "g_call_ms": 1e3 * float(np_.median(ts)), "efp_call_ms": 1e3 * float(np_.median(te)),
+            "evals_per_call": 7500, "P_mean": float(np_.mean(P)),
+            "inside_band": res.get("inside_band"), "lm_evaluations_mean": float(np_.mean(res["iters"])) if "iters" in res else None}
 
 
 def main():
@@ -202,13 +399,19 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-d", type=int, default=10000, help="design points per GPU")
     ap.add_argument("--n-theta", type=int, default=10000)
-    ap.add_argument("--ref-rows", type=int, default=200, help="design points per step of the CPU reference arm")
+    ap.add_argument("--ref-rows", type=int, default=1000, help="design points per step of the CPU reference arm")
+    ap.add_argument("--ref-formulation", default="blocktri", choices=["blocktri", "dense9"],
+                    help="CPU arm: the equations as the GPU solves them (block triangular) or the dense 9-unknown Newton system")
     ap.add_argument("--cpu-rows", type=int, default=1000, help="design points of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ns-iterations", type=int, default=5, help="nested-sampling iterations timed for the secondary metric")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C4 / strong-scaling / C5 sections")
+    ap.add_argument("--ns-iterations", type=int, default=3, help="nested-sampling iterations timed (config C5)")
+    ap.add_argument("--ns-live", type=int, default=100000, help="live points of the C5 nested-sampling section")
+    ap.add_argument("--ns-theta", type=int, default=100000)
     ap.add_argument("--dense9", action="store_true", help="keep cC in the Newton system (9 unknowns, SURVEY A.5 flop count)")
     ap.add_argument("--coupled", action="store_true", help="one coupled 6-unknown Newton system instead of the block-triangular solve")
     ap.add_argument("--generic-blocks", action="store_true", help="block-triangular solve through the generic point-op / NS path (no POLY1)")
+    ap.add_argument("--interpreted-loop", action="store_true", help="POLY1 per block and element instead of the fused chain")
     args = ap.parse_args()
     claim_stdout()
     if args.warmup < 3 and args.impl == "b200":
@@ -218,10 +421,12 @@ def main():
         run_reference(args)
         return
 
+    import tempfile
+
     import torch
     import torch.distributed as dist
     from pyds_b200 import capi, models
-    from pyds_b200.parallel import ShardedEfp
+    from pyds_b200.parallel import ShardedEfp, shard_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -239,6 +444,8 @@ def main():
         kw["block_triangular"] = False
     if args.generic_blocks:
         kw["polynomial_blocks"] = False
+    if args.interpreted_loop:
+        kw["fused_chain"] = False
     lm = models.kinetics("design4", dense9=args.dense9, **kw).lower()
     eng = capi.Engine(lm.blob, local_rank)
     sharded = ShardedEfp(eng, world, rank)
@@ -258,6 +465,12 @@ def main():
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     peak_tflops, _ = capi.dfma_peak(local_rank, 5)
     for _ in range(args.warmup):
@@ -285,29 +498,17 @@ def main():
     clocks = sampler.stop(t0, t1)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     kern_ms = [a.elapsed_time(b) for a, b in kev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
+    ms_per_step = max_over_ranks(sum(step_ms)) / args.steps
     cnt = eng.counters()
-    evals_per_step = world * n_d * n_t
-    value = evals_per_step / (ms_per_step * 1e-3)
 
     # roofline of the dominant kernel (feas_kernel): algorithmic flops per launch / its event time
     I = cnt["newton_iters"] / max(cnt["scenarios"], 1) / lm.nfe
     f_alg = lm.flops_per_evaluation(I, newton_flops_per_eval=cnt["newton_flops"] / max(cnt["scenarios"], 1))
     k_ms = float(np.mean(kern_ms))
-    achieved = n_d * n_t * f_alg / (k_ms * 1e-3) / 1e12
-    alg_bytes = 8 * (n_d * lm.d_dim + n_t * (lm.p_dim + 1) + n_d)
-    kernel_name = f"feas_kernel<{max(len(s) for s in lm.blocks)},{eng.info['scenarios_per_thread']}>"
-    traffic, ncu_pipes = None, None     # per launch, from the committed ncu --set full capture of this config
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_feas_kernel.json")))
-        if tj["kernel"] == kernel_name and tj["n_d"] == n_d and tj["n_theta"] == n_t:
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-            ncu_pipes = {k: tj[k] for k in ("fp64_pipe_active_pct", "issue_active_pct", "shared_wavefronts_pct") if k in tj}
-    except (OSError, KeyError, ValueError):
-        pass
+    info = capi.assemble(lm.blob)[1]
+    kernel_name = f"feas_kernel<{max(len(s) for s in lm.blocks)},{eng.info['scenarios_per_thread']}>" + \
+                  (f" fused chain, shape {'registered' if info['chain_shape_registered'] else 'generic'}" if info["chain_blocks"] else "")
+    traffic, ncu_pipes, ncu_note = committed_ncu(kernel_name, n_d, n_t)
 
     # end to end through the host-buffer C-ABI call (pinned staging, H2D, kernels, D2H inside the timed region)
     P_host = None
@@ -318,51 +519,72 @@ def main():
     for _ in range(args.steps):
         P_host = sharded.efp_host(d_np, th_np, w_np, equal_shards=True)
     barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - te0) / args.steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = evals_per_step / float(e2e_s.item())
-    h2d = 8 * (n_d * lm.d_dim + n_t * lm.p_dim + n_t)
-    d2h = 8 * n_d
+    e2e_s = max_over_ranks((time.perf_counter() - te0) / args.steps)
     same = bool(np.allclose(P_host[rank * n_d:(rank + 1) * n_d], P_all[rank * n_d:(rank + 1) * n_d].cpu().numpy(), atol=1e-12))
 
-    ns_s, ns_it, ns_rep = ns_iteration_seconds(sharded, world * n_d, th_np, w_np, args.ns_iterations)
+    configs = []
+    ns_entry = None
+    if not args.no_configs:
+        # ---- C3 at FIXED total work: the same n_d x n_t batch with its rows sharded over the ranks (strong scaling) ----
+        a, b = shard_rows(n_d, world, rank)
+        d0 = torch.from_numpy(make_inputs(n_d, n_t, 0)[0][a:b].copy()).to(dev)
+        Pl = torch.empty(max(b - a, 1), dtype=torch.float64, device=dev)
+        for _ in range(3):
+            eng.eval_device(d0, th, w, P_out=Pl)
+        barrier()
+        fe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for k in range(args.steps):
+            flush.fill_(float(k))
+            fe[k][0].record(); eng.eval_device(d0, th, w, P_out=Pl); fe[k][1].record()
+        barrier()
+        fixed_ms = max_over_ranks(sum(x.elapsed_time(y) for x, y in fe)) / args.steps
+        configs.append({"name": "C3-fixed", "workload": f"C3 with FIXED total work: {n_d} x {n_t} (d,theta) in all, rows sharded over "
+                                                       f"{world} GPU(s) (kernel + partial reduction, max over ranks)",
+                        "ms_per_step": fixed_ms, "value": n_d * n_t / (fixed_ms * 1e-3), "unit": UNIT, "scaling": "strong",
+                        "strong_efficiency": k_ms / (world * fixed_ms) if world > 1 else 1.0,
+                        "strong_efficiency_note": "single-GPU kernel time of the same batch (this run, rank-local) / (N x sharded time)"})
+        if world == 1:
+            configs.append(c4_section(torch, capi, models, dev, peak_tflops))
+            try:
+                configs.append(c1_section(np, tempfile))
+            except Exception as e:                     # the manager path must not take the headline down with it
+                configs.append({"name": "C1", "error": repr(e)})
+        # ---- C5: nested sampling, 6 design variables, n_live x n_theta sharded over the ranks ----
+        eng6 = capi.Engine(models.kinetics("design6").lower().blob, local_rank)
+        sh6 = ShardedEfp(eng6, world, rank)
+        _, th5, w5 = make_inputs(10, args.ns_theta)
+        ns_s, ns_it, ns_rep, ns_init = ns_iteration_seconds(sh6, C5_BOX, args.ns_live, th5, w5, args.ns_iterations)
+        ns_s, ns_init = max_over_ranks(ns_s), max_over_ranks(ns_init)
+        ns_entry = {"seconds": ns_s, "iterations_timed": ns_it, "n_live": args.ns_live, "n_theta": args.ns_theta,
+                    "proposals_per_iteration": ns_rep, "evals_per_iteration": ns_rep * args.ns_theta,
+                    "evals_per_s": ns_rep * args.ns_theta / max(ns_s, 1e-12), "initial_live_set_seconds": ns_init,
+                    "what": "config C5 (6 design vars): pyds_b200.ns iteration = ellipsoid proposals + P(feasible) of the "
+                            "proposals over all theta sharded over the ranks + live-set update; FIXED total work (strong scaling)"}
+        configs.append(dict(ns_entry, name="C5-ns"))
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, dt, P_cpu, _ = cpu_baseline(min(args.cpu_rows, n_d), n_t, threads, n_d=n_d)
+            from oracle import cbind
+            rows = min(args.cpu_rows, n_d)
+            v, dt, P_cpu, it_cpu = cpu_baseline(rows, n_t, threads, n_d=n_d, formulation="blocktri")
+            v9, dt9, _, it9 = cpu_baseline(max(rows // 5, 1), n_t, threads, n_d=n_d, formulation="dense9")
             agree = bool(np.allclose(P_cpu, P_all[:len(P_cpu)].cpu().numpy(), atol=1e-12))
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"first {args.cpu_rows} of the {n_d} design points x all {n_t} theta ({dt:.1f} s); "
-                             f"P(feasible) equal to the GPU result on the sample: {agree}"}
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"C3 synthetic kinetics (A->B->C semi-batch, Radau 8x3), 4 design vars, "
-                                   f"{n_d} design points per GPU x {n_t} theta, no recourse; P(feasible) per point",
-                       "n_d_per_gpu": n_d, "n_theta": n_t, "sharding": f"design points over {world} GPU(s), theta replicated",
-                       "l2": "256 MiB buffer written between timed steps (flush); inputs are < 1 MB, the path is fp64-pipe bound",
-                       "newton_iters_per_element": I, "flops_per_eval": f_alg,
-                       "state_blocks": [{"states": s, "unknowns": len(s) * lm.ncp, "linear": bool(l)} for s, l in zip(lm.blocks, lm.block_linear)]},
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": traffic, "kernel": kernel_name, "ncu": ncu_pipes,
-                         "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
-                         "peak_source": "measured in this run: pydsb_dfma_peak (independent-chain DFMA microkernel, best of 5); "
-                                        "MEASURED_PEAKS.json carries no fp64 figure"},
-            "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "matches_device_path": same},
-            "ns_iteration": {"seconds": ns_s, "iterations_timed": ns_it, "n_live": world * n_d, "proposals_per_iteration": ns_rep,
-                             "what": "pyds_b200.ns: ellipsoid proposals (host) + P(feasible) of the proposals over all theta "
-                                     "through the host-buffer path + live-set update"},
-            "gpu_launches": cnt["launches"],
-            "clocks": clocks,
-            "counters": cnt,
-        }
-        emit(line)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "formulation": "blocktri",
+                   "flops_per_eval": cbind.flops_per_eval("blocktri", it_cpu),
+                   "sample": f"first {rows} of the {n_d} design points x all {n_t} theta ({dt:.1f} s); "
+                             f"P(feasible) equal to the GPU result on the sample: {agree}",
+                   "dense9": {"value": v9, "flops_per_eval": cbind.flops_per_eval("dense9", it9),
+                              "sample": f"first {max(rows // 5, 1)} design points ({dt9:.1f} s), the 9-unknown Newton system of SURVEY A.5"}}
+        m = {"n_d": n_d, "n_t": n_t, "world": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+             "kernel_ms": k_ms, "f_alg": f_alg, "newton_iters_per_element": I, "peak_tflops": peak_tflops,
+             "kernel_name": kernel_name, "traffic": traffic, "ncu_pipes": ncu_pipes, "ncu_note": ncu_note,
+             "d_dim": lm.d_dim, "p_dim": lm.p_dim, "cpu": cpu, "e2e_s": e2e_s, "e2e_matches": same, "configs": configs,
+             "ns_iteration": ns_entry, "counters": cnt, "clocks": clocks,
+             "formulation": "dense9" if args.dense9 else ("coupled" if args.coupled else "blocktri"),
+             "state_blocks": [{"states": s, "unknowns": len(s) * lm.ncp, "linear": bool(l)} for s, l in zip(lm.blocks, lm.block_linear)]}
+        emit(build_line(m))
     if world > 1:
         dist.destroy_process_group()
 

@@ -32,6 +32,8 @@ def lib():
                                            ctypes.c_longlong, ctypes.c_double, ctypes.c_int, dp, dp]
         L.oracle_set_threads.restype = ctypes.c_int
         L.oracle_set_threads.argtypes = [ctypes.c_int]
+        L.oracle_set_formulation.restype = ctypes.c_int
+        L.oracle_set_formulation.argtypes = [ctypes.c_int]
         L.oracle_set_tables.restype = None
         L.oracle_set_tables.argtypes = [dp, dp]
         a = np.ascontiguousarray(np.asarray(ADOT, dtype=np.float64).reshape(-1))
@@ -45,9 +47,23 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
 
-def kinetics_grid(d, p, w=None, F=None, tol=1e-13, max_it=60, want_g=True, want_P=True, threads=None):
-    """Returns (g (n_d,n_p,2) or None, P (n_d,) or None, newton_iterations)."""
+FORMULATIONS = {"dense9": 0, "blocktri": 1}
+# algorithmic flops of one evaluation (SURVEY.md 8d convention, FMA = 2, per Newton iteration and element):
+#   dense9:   3 points x (f, J) ~ 45, residual 2 n (ncp + 1) = 72, LU 2/3 n^3 = 486, solves 2 n^2 = 162   (n = 9)
+#   blocktri: cA iteration 18 + 24 + 18 + 18 = 78; per element cB solve 78 and the quadratures ~ 20
+FLOPS_PER_ITERATION = {"dense9": 45 + 72 + 486 + 162, "blocktri": 78}
+FLOPS_PER_ELEMENT = {"dense9": 6, "blocktri": 78 + 20}
+
+
+def flops_per_eval(formulation, iters_per_eval, nfe=8):
+    return FLOPS_PER_ITERATION[formulation] * iters_per_eval + nfe * FLOPS_PER_ELEMENT[formulation] + 40
+
+
+def kinetics_grid(d, p, w=None, F=None, tol=1e-13, max_it=60, want_g=True, want_P=True, threads=None, formulation="dense9"):
+    """Returns (g (n_d,n_p,2) or None, P (n_d,) or None, newton_iterations).  ``formulation``: "dense9" (one 9-unknown
+    Newton system per element) or "blocktri" (cA Newton, cB linear, cC quadrature -- what the GPU kernels solve)."""
     L = lib()
+    L.oracle_set_formulation(FORMULATIONS[formulation])
     d = np.ascontiguousarray(np.atleast_2d(d), dtype=np.float64)
     p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
     n_d, d_dim = d.shape

@@ -12,6 +12,14 @@
  * d columns: (t_f, T[, cA0[, Fbar[, pB, pA]]]); p columns: (E1, E2, k1, k2).
  * Each (d,theta) pair: 8 finite elements, full Newton on the 9x9 collocation system,
  * dense LU with partial pivoting.  OpenMP over design points.
+ *
+ * Two formulations of the SAME collocation equations (oracle_set_formulation):
+ *   0 "dense9"   the 9 unknowns of an element (cA, cB, cC at three points) in one pivoted Newton system -- what
+ *                SURVEY.md A.3 / A.5 count (about 22 kflop per evaluation);
+ *   1 "blocktri" what the GPU kernels solve: the system is block lower triangular (A -> B -> C), so cA is a 3-unknown
+ *                Newton solve, cB one linear 3x3 solve given cA, cC a quadrature (about 3 kflop per evaluation).
+ *                Same Newton iterates for cA, hence the same solution; lets bench.py separate what the hardware
+ *                buys from what the restructuring buys.
  */
 #include <math.h>
 #include <stddef.h>
@@ -160,6 +168,98 @@ static int eval_one(double tf, double T, double cA0, const double* F, double pB,
     return total;
 }
 
+static int lu_solve3(double M[3][3], double r[3])
+{
+    for (int k = 0; k < 3; ++k) {
+        int piv = k; double best = fabs(M[k][k]);
+        for (int i = k + 1; i < 3; ++i) if (fabs(M[i][k]) > best) { best = fabs(M[i][k]); piv = i; }
+        if (best == 0.0) return -1;
+        if (piv != k) {
+            for (int c = 0; c < 3; ++c) { double t = M[k][c]; M[k][c] = M[piv][c]; M[piv][c] = t; }
+            double t = r[k]; r[k] = r[piv]; r[piv] = t;
+        }
+        const double inv = 1.0 / M[k][k];
+        for (int i = k + 1; i < 3; ++i) {
+            const double l = M[i][k] * inv;
+            for (int c = k + 1; c < 3; ++c) M[i][c] -= l * M[k][c];
+            r[i] -= l * r[k];
+        }
+    }
+    for (int k = 2; k >= 0; --k) {
+        double s = r[k];
+        for (int c = k + 1; c < 3; ++c) s -= M[k][c] * r[c];
+        r[k] = s / M[k][k];
+    }
+    return 0;
+}
+
+/* The block-triangular formulation of the same equations: cA by Newton (3 unknowns), cB by one linear solve,
+ * cC by its quadrature  cC(end) = cC(start) + h sum_j bw_j t_f K2 cB_j  (Radau IIA weights: exact for the collocation
+ * polynomial).  Returns the Newton iterations of the cA blocks, or -1. */
+static int eval_one_blocktri(double tf, double T, double cA0, const double* F, double pB, double pA,
+                             double E1, double E2, double k1, double k2, double tol, int max_it,
+                             double* g1, double* g2)
+{
+    const double K1 = k1 * exp(-E1 / T), K2 = k2 * exp(-E2 / T);
+    const double h = 1.0 / NFE;
+    double cA = cA0, cB = 0.0, cC = 0.0, u = 0.0;
+    int total = 0;
+    for (int e = 0; e < NFE; ++e) {
+        double XA[NCP] = {cA, cA, cA};
+        int it = 0, conv = 0;
+        while (it < max_it && !conv) {
+            double M[3][3], r[3];
+            for (int j = 0; j < NCP; ++j) {
+                double lin = A[0][j + 1] * cA;
+                for (int k = 0; k < NCP; ++k) { lin += A[k + 1][j + 1] * XA[k]; M[j][k] = A[k + 1][j + 1]; }
+                const double f = tf * (-2.0 * K1 * XA[j] * XA[j] + F[e]);
+                r[j] = -(lin - h * f);
+                M[j][j] -= h * (-4.0 * tf * K1 * XA[j]);
+            }
+            if (lu_solve3(M, r) != 0) return -1;
+            double dmax = 0.0, xmax = 1.0;
+            for (int j = 0; j < NCP; ++j) {
+                XA[j] += r[j];
+                if (fabs(r[j]) > dmax) dmax = fabs(r[j]);
+                if (fabs(XA[j]) > xmax) xmax = fabs(XA[j]);
+            }
+            ++it;
+            if (!(dmax == dmax)) return -1;
+            conv = dmax <= tol * xmax;
+        }
+        if (!conv) return -1;
+        total += it;
+        {
+            double M[3][3], r[3];
+            for (int j = 0; j < NCP; ++j) {
+                for (int k = 0; k < NCP; ++k) M[j][k] = A[k + 1][j + 1];
+                M[j][j] += h * tf * K2;
+                r[j] = h * tf * K1 * XA[j] * XA[j] - A[0][j + 1] * cB;
+            }
+            if (lu_solve3(M, r) != 0) return -1;
+            double q = 0.0;
+            for (int j = 0; j < NCP; ++j) q += BW[j] * r[j];
+            cC += h * tf * K2 * q;
+            cB = r[NCP - 1];
+            if (!(cB == cB)) return -1;
+        }
+        u += h * F[e] * (BW[0] + BW[1] + BW[2]) / tf;
+        cA = XA[NCP - 1];
+    }
+    *g1 = 0.8 - (cB + 1e-2) / (cA + cB + cC + 1e-2);
+    *g2 = -(pB * cB - pA * (cA0 + u * tf) - 128.0 * (tf + 30.0));
+    return total;
+}
+
+static int formulation = 0;
+/* 0: dense 9x9 Newton per element (default), 1: block-triangular 3 + 3.  Returns the previous value. */
+int oracle_set_formulation(int f)
+{
+    const int old = formulation;
+    if (f == 0 || f == 1) formulation = f;
+    return old;
+}
+
 /* Full grid.  F: NULL (zeros), or (f_rows, 8) with f_rows in {1, n_d}; ignored when d_dim >= 4.
  * g_out: NULL or (n_d, n_p, 2).  P_out: NULL or (n_d).  Returns total Newton iterations
  * (negative count of failed scenarios if any failed; failed scenarios count as infeasible). */
@@ -182,7 +282,8 @@ long long oracle_kinetics_grid(long long n_d, int d_dim, const double* d, long l
         for (long long j = 0; j < n_p; ++j) {
             const double* pj = p + j * 4;
             double g1, g2;
-            int it = eval_one(tf, T, cA0, Fl, pB, pA, pj[0], pj[1], pj[2], pj[3], tol, max_it, &g1, &g2);
+            int it = formulation ? eval_one_blocktri(tf, T, cA0, Fl, pB, pA, pj[0], pj[1], pj[2], pj[3], tol, max_it, &g1, &g2)
+                                 : eval_one(tf, T, cA0, Fl, pB, pA, pj[0], pj[1], pj[2], pj[3], tol, max_it, &g1, &g2);
             if (it < 0) { ++fails; g1 = g2 = NAN; } else iters += it;
             if (g_out) { g_out[(i * n_p + j) * 2] = g1; g_out[(i * n_p + j) * 2 + 1] = g2; }
             if (it >= 0 && g1 <= 0.0 && g2 <= 0.0) acc += w ? w[j] : 1.0;

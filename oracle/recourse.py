@@ -242,3 +242,57 @@ def slsqp_shared(vm, d_row, p, w, z0, maxiter=300):
     z = res.x[:nz]
     c, _ = ev(z.copy())
     return dict(z=z, phi_raw=float(w @ np.maximum(0.0, c.max(axis=1))), success=res.success, nit=res.nit)
+
+
+def slsqp_group(vm, d_rows, p, w, z0, maxiter=300):
+    """``slsqp_shared`` for a group of scenarios spread over SEVERAL design points that share one control vector (the
+    three-stage formulation, reference pyds/run.py:76-91; with one row it is the two-stage problem, with one row and one
+    theta the per-scenario problem).  ``w``: weights of the theta samples; the objective averages over the rows."""
+    from scipy.optimize import minimize
+    d_rows, p = np.atleast_2d(d_rows), np.atleast_2d(p)
+    n_d, n_p, nz, ng = len(d_rows), len(p), vm.nz, vm.ng
+    S = n_d * n_p
+    lo, hi = vm.sec["ZLOW"][:nz], vm.sec["ZHIG"][:nz]
+    bigm = vm.big_m
+    ws = np.tile(np.asarray(w, float), n_d) / n_d
+    cache = {}
+
+    def ev(z):
+        key = z.tobytes()
+        if key not in cache:
+            cache.clear()
+            r = vm.evaluate(d_rows, p, z=z, tol=1e-13, want_sens=True)
+            cache[key] = ((r["g"] / bigm).reshape(S, ng), (r["dg"] / bigm[:, None]).reshape(S, ng, nz))
+        return cache[key]
+
+    z0 = np.asarray(z0, float)
+    y0 = np.maximum(0.0, ev(z0)[0].max(axis=1)) + 1e-6
+    x0 = np.concatenate([z0, y0])
+    fun = lambda x: float(ws @ x[nz:])
+    jac = lambda x: np.concatenate([np.zeros(nz), ws])
+
+    def con(x):
+        return (x[nz:, None] - ev(x[:nz].copy())[0]).reshape(-1)
+
+    def con_jac(x):
+        dc = ev(x[:nz].copy())[1]
+        Jm = np.zeros((S * ng, nz + S))
+        Jm[:, :nz] = -dc.reshape(S * ng, nz)
+        for s in range(S):
+            Jm[s * ng:(s + 1) * ng, nz + s] = 1.0
+        return Jm
+
+    bounds = [(lo[i], hi[i]) for i in range(nz)] + [(0.0, None)] * S
+    res = minimize(fun, x0, jac=jac, bounds=bounds, constraints=[{"type": "ineq", "fun": con, "jac": con_jac}],
+                   method="SLSQP", options={"maxiter": maxiter, "ftol": 1e-14})
+    z = np.clip(res.x[:nz], lo, hi)
+    c = ev(z.copy())[0]
+    return dict(z=z, phi_raw=float(ws @ np.maximum(0.0, c.max(axis=1))), success=res.success, nit=res.nit)
+
+
+def hinge_value(vm, d_rows, p, w, z):
+    """The reduced objective  (1/n_d) sum_i sum_s w_s max(0, max_k g_k / M_k)  at the controls ``z`` (independent of any
+    optimiser: one state solve per scenario with the tape interpreter)."""
+    d_rows, p = np.atleast_2d(d_rows), np.atleast_2d(p)
+    c = vm.evaluate(d_rows, p, z=np.asarray(z, float), tol=1e-13)["g"] / vm.big_m
+    return float((np.maximum(0.0, c.max(axis=-1)) * np.asarray(w, float)[None, :]).sum() / len(d_rows))

@@ -37,6 +37,8 @@ class _State:
     name: str
     x0: object
     rhs: object = None
+    lo: float = -np.inf            # variable bounds of the user's model (reference run_twostage.py:44: 0 <= c <= 1e8);
+    hi: float = np.inf             # not enforced by the state solve -- violations are detected (Solver, 'check state bounds')
 
 
 @dataclass
@@ -94,9 +96,11 @@ class DaeModel:
     def param(self, name):
         return self.d[name] if name in self.d else self.p[name]
 
-    def state(self, name, x0=0.0):
+    def state(self, name, x0=0.0, bounds=None):
         i = len(self.states)
-        self.states.append(_State(name, x0))
+        lo, hi = (-np.inf, np.inf) if bounds is None else (-np.inf if bounds[0] is None else float(bounds[0]),
+                                                           np.inf if bounds[1] is None else float(bounds[1]))
+        self.states.append(_State(name, x0, lo=lo, hi=hi))
         return self.graph._mk("x", (), i)            # provisional index = declaration order
 
     def control(self, name, lo, hi, init=0.0, per_element=True):
@@ -184,8 +188,24 @@ class DaeModel:
         memo = {}
         rb = lambda e: self._rebuild(g.wrap(e), leaf_map, memo)
 
+        def ctrl_linear(e):
+            """An element-level value that is LINEAR in one control, ``alpha(parameters) * z``, rewritten to exactly that
+            product: however the user's equations spell it (``F_in[t] / t_f == dudt[t]`` reaches here as
+            ``-((z * (1 / t_f)) / -1)``), the elem tape then holds one multiplication and the fused element loop
+            (csrc/poly_chain.cuh) can take the control straight from z.  Anything else is returned unchanged."""
+            if e is None or e.level != T.LEVEL_CTRL:
+                return e
+            leaves = {n.value: n for n in T.topo_order([e]) if n.op == "ctrl"}
+            if len(leaves) != 1:
+                return e
+            z = next(iter(leaves.values()))
+            pc = g.poly_coeffs(e, z, 1)
+            if pc is None or len(pc) != 2 or not pc[0].is_const(0.0) or pc[1].level > T.LEVEL_PARAM:
+                return e
+            return g.mul(pc[1], z)
+
         f = [rb(self.states[i].rhs) for i in dyn]
-        fq = [rb(self.states[i].rhs) for i in quad]
+        fq = [ctrl_linear(rb(self.states[i].rhs)) for i in quad]
         x0 = [rb(self.states[i].x0) for i in dyn]
         q0 = [rb(self.states[i].x0) for i in quad]
         for e in x0 + q0:
@@ -239,7 +259,7 @@ class DaeModel:
             if self.polynomial_blocks and len(blk) == 1:
                 co = g.poly_coeffs(f[blk[0]], g.x(blk[0]), 2)
             if co is not None:
-                co = [None if c.is_const(0.0) else c for c in co] + [None] * (3 - len(co))
+                co = [None if c.is_const(0.0) else ctrl_linear(c) for c in co] + [None] * (3 - len(co))
                 roots[f"c{b}"] = co
                 groups.append((f"pt{b}", [f"c{b}"]))       # the coefficients that depend on earlier blocks' states
                 blk_poly.append(f"c{b}")
@@ -367,7 +387,8 @@ class DaeModel:
             block_flops=blk_flops, block_fixed_flops=blk_fixed, block_poly=[bool(x) for x in blk_poly],
             z_fixed=np.asarray(z_fixed, dtype=bool), big_m=np.asarray([m for _, _, m in self.constraints]),
             constraint_names=[n for n, _, _ in self.constraints], cmap=cmap, newton_rtol=self.newton_rtol,
-            newton_max_it=self.newton_max_it)
+            newton_max_it=self.newton_max_it,
+            state_lo=np.asarray([self.states[i].lo for i in dyn + quad]), state_hi=np.asarray([self.states[i].hi for i in dyn + quad]))
         return info
 
 
@@ -401,6 +422,8 @@ class LoweredModel:
     cmap: np.ndarray
     newton_rtol: float
     newton_max_it: int
+    state_lo: np.ndarray = None        # bounds of the states in trajectory column order (dynamic, then quadrature)
+    state_hi: np.ndarray = None
 
     def flops_per_newton_iteration(self, block=0):
         """Algorithmic flops of one Newton iteration of one block on one finite element:

@@ -151,7 +151,7 @@ def lower_stage_model(model, input_map, f_profile_suffix=None, **model_kw):
         x0 = fx
         if hasattr(fx, "_as_expr") or isinstance(fx, T.Expr):
             x0 = translate(g_src.wrap(fx), {})
-        state_handle[(vid, key)] = dm.state(f"{sv.name}{list(key) if key else ''}", x0)
+        state_handle[(vid, key)] = dm.state(f"{sv.name}{list(key) if key else ''}", x0, bounds=sv.bounds)
         dm.state_keys[f"{sv.name}{list(key) if key else ''}"] = (sv.name, key, sv.contset.bounds)
 
     # --- equations -------------------------------------------------------------------------------------

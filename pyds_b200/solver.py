@@ -11,7 +11,21 @@ Classification rule (reference pyds/solver.py:71-80): the relaxed indicator is s
 big-M rows to its feasibility tolerance; the equivalent here is ``max_k g_k/M_k <= feasibility
 tolerance`` at the optimised controls (default 1e-7 in big-M-scaled units; 0 when the controls are
 not optimised).  A scenario whose state solve fails is reported infeasible (indicator 1), as the
-reference does for an infeasible NLP (pyds/solver.py:39-44, 63-69).
+reference does for an infeasible NLP (pyds/solver.py:39-44, 63-69).  That tolerance is a guess at the solver's
+behaviour (parity with CONOPT is unpinned), so every call reports how much rests on it: ``result['inside_band']`` counts
+the scenarios with ``0 < max_k g_k/M_k <= tolerance`` (``efp``: ``result['band_weight']``, the theta weight per design
+point that the tolerance turns feasible).
+
+``io options`` beyond the reference's:
+  'optimise controls' (True), 'feasibility tolerance' (1e-7), the optimiser's 'mu0' 'mu_min' 'lam0' 'step_tol' 'max_iter',
+  'warm start carry-over' (False): the reference's sequencing -- Pyomo keeps the variable values between solves
+      (``warmstart=True``, pyds/solver.py:17) and the warm-start simulator rewrites the states only (pyds/simulator.py:70-94),
+      so the control profile of design point i starts from the optimum of design point i-1 (pyds/run.py:55-67), across calls
+      too.  Serial by nature: one optimiser run per design point; a mode, not the default.
+  'check state bounds' (None = whenever 'save output' computes the profiles anyway; True: always, one extra state solve
+      per call): count the scenarios whose solved profiles leave the variable bounds of the user's model (``c`` in
+      [0, 1e8], reference run_twostage.py:44), which the state solve does not enforce; ``result['bound_violations']``
+      (None when not checked).
 """
 from __future__ import annotations
 
@@ -36,6 +50,9 @@ class Solver:
         self.optimise_controls = bool(opt.get("optimise controls", True))
         self.feas_tol = float(opt.get("feasibility tolerance", 1e-7))
         self.lm_options = {k: opt[k] for k in ("mu0", "mu_min", "lam0", "step_tol", "max_iter", "check_every") if k in opt}
+        self.carry_over = bool(opt.get("warm start carry-over", False))
+        self.check_bounds = opt.get("check state bounds", None)
+        self._z_carry = None                             # the last optimised control profile (carry-over mode)
         self.result = None
         self.output = {"relaxation": None, "trajectories": None}
         self._indicator = None
@@ -68,6 +85,8 @@ class Solver:
             z0 = sim.default_controls()[None, :]
             if n_d_total is not None:
                 res = self._solve_global_sharded(eng, d, int(n_d_total), p, w, z0, group)
+            elif self.carry_over and mode == "shared" and len(d):
+                res = self._solve_carry_over(eng, d, p, w, z0)
             else:
                 res = eng.recourse_solve(d, p, w, z0=z0, per_scenario=(mode == "per_scenario"),
                                          global_group=(mode == "global"), **self.lm_options)
@@ -88,6 +107,9 @@ class Solver:
             indicator = np.where(y <= tol, 0.0, 1.0)
         failed = ~np.isfinite(c).all(axis=-1)
         indicator[failed] = 1.0
+        with np.errstate(invalid="ignore"):
+            self.result["inside_band"] = int(((y > 0.0) & (y <= tol) & ~failed).sum())
+        self.result["band"] = tol
         if failed.any():
             self.no_infeasible += int(failed.sum())
             if self.warn_infeasible:
@@ -95,10 +117,14 @@ class Solver:
         self._indicator = indicator
         self._g = g
         self._traj = None
-        if self.save_output:
+        check = self.save_output if self.check_bounds is None else bool(self.check_bounds)
+        traj_failed = None
+        if self.save_output or check:
             # the solved state profiles the reference reads back with utils.parse_value (pyds/solver.py:100-117)
-            self._traj = eng.state_solve(d, p, z=z)[0]
+            self._traj, traj_failed = eng.state_solve(d, p, z=z)
             self._time = eng.time_grid()
+        self.result["bound_violations"] = self._count_bound_violations(self._traj, traj_failed) if check else None
+        if self.save_output:
             self.output["relaxation"] = self._collect_output()
             if self.solve_trajectories:
                 # reference pyds/solver.py:46-48,57-61: a second NLP solve with the snapped indicators fixed -- its
@@ -150,15 +176,49 @@ class Solver:
         if n_d == 0:
             return np.empty(0)
         P = torch.empty(n_d, dtype=torch.float64, device=dev)
-        before = eng.counters()["failed"]
+        eng.counters(reset=True)
         eng.eval_device(td, tp, tw, z=tz, z_mode=z_mode, P_out=P, feas_tol=tol)
         out = P.cpu().numpy()
-        failed = eng.counters()["failed"] - before
+        failed = eng.counters()["failed"]                # one synchronising read (the call above is the only work since the reset)
+        if tol > 0.0:
+            # how much of the answer rests on the tolerance: the same pass with the exact rule g <= 0
+            P0 = torch.empty(n_d, dtype=torch.float64, device=dev)
+            eng.eval_device(td, tp, tw, z=tz, z_mode=z_mode, P_out=P0, feas_tol=0.0)
+            self.result["band_weight"] = (P - P0).cpu().numpy()
+            self.result["band"] = tol
         if failed:
             self.no_infeasible += int(failed)
             if self.warn_infeasible:
                 print("Warning: Infeasible relaxation. Total number of infeasible solves: {}".format(self.no_infeasible))
         return out
+
+    def _solve_carry_over(self, eng, d, p, w, z0):
+        """The reference's sequencing (pyds/run.py:55-67 with ``warmstart=True``): design point i starts its control
+        optimisation from the optimum of design point i-1; the first point of the first call from the warm-start profile."""
+        z_prev = self._z_carry if self._z_carry is not None else np.asarray(z0, dtype=np.float64).reshape(-1)
+        out = {"z": [], "phi": [], "status": [], "iters": []}
+        for i in range(d.shape[0]):
+            r = eng.recourse_solve(d[i:i + 1], p, w, z0=z_prev[None, :], **self.lm_options)
+            z_prev = r["z"][0].copy()
+            for k in out:
+                out[k].append(r[k][0])
+        self._z_carry = z_prev
+        return {k: np.asarray(v) for k, v in out.items()}
+
+    def _count_bound_violations(self, x, failed):
+        """Scenarios whose solved state profiles ``x`` (pydsb_state_solve) leave the bounds the user's model declares (not
+        enforced by the state solve; the reference hands them to the NLP solver)."""
+        lm = self.parent.simulator.lowered
+        lo, hi = lm.state_lo, lm.state_hi
+        if lo is None or not (np.isfinite(lo).any() or np.isfinite(hi).any()):
+            return 0
+        with np.errstate(invalid="ignore"):
+            bad = ((x < lo[None, None, None, :] - 1e-9 * np.maximum(1.0, np.abs(lo))) |
+                   (x > hi[None, None, None, :] + 1e-9 * np.maximum(1.0, np.abs(hi)))).any(axis=(2, 3)) & ~failed
+        n = int(bad.sum())
+        if n and self.warn_infeasible:
+            print(f"Warning: {n} scenario(s) leave the variable bounds of the model (not enforced by the state solve)")
+        return n
 
     def _solve_global_sharded(self, eng, d_local, n_d_total, p, w, z0, group):
         import torch

@@ -51,6 +51,60 @@ def test_shared_control_vs_slsqp_optimum(setup):
         assert out["phi"][i] <= s["phi_raw"] + 1e-6 * max(s["phi_raw"], 1e-6)
 
 
+def _two_sided(vm, eng_phi, eng_z, d_rows, p, w, rng, n_random=2):
+    """Independent check of an optimum the GPU reports, from both sides (BASELINE.json: optima within 1e-6):
+    (i) the objective at the reported controls, re-evaluated by the tape interpreter, IS the reported value;
+    (ii) SLSQP on the epigraph NLP started AT the reported controls finds nothing lower (local optimality);
+    (iii) SLSQP from the warm start and from random starts finds nothing lower either (no better optimum within reach of
+    an independent solver), and its own optimum from the warm start is not better by more than the tolerance."""
+    tol = 1e-6 * max(eng_phi, 1e-3)
+    lo, hi = vm.sec["ZLOW"][:vm.nz], vm.sec["ZHIG"][:vm.nz]
+    assert abs(RC.hinge_value(vm, d_rows, p, w, eng_z) - eng_phi) <= 1e-9 + 1e-9 * eng_phi
+    polish = RC.slsqp_group(vm, d_rows, p, w, eng_z)
+    assert polish["phi_raw"] >= eng_phi - tol, (polish["phi_raw"], eng_phi)
+    starts = [np.zeros(vm.nz)] + [rng.uniform(lo, hi) for _ in range(n_random)]
+    best = min(RC.slsqp_group(vm, d_rows, p, w, z0)["phi_raw"] for z0 in starts)
+    assert eng_phi <= best + tol, (eng_phi, best)
+    return best
+
+
+def test_two_sided_independent_optimum_check_two_stage(setup):
+    """Every design point of D6, shared control across the 50 shipped theta samples."""
+    lm, eng, vm = setup
+    p = K.theta_samples(50)
+    w = np.full(50, 1 / 50)
+    out = eng.recourse_solve(D6, p, w, z0=np.zeros((1, 8)))
+    rng = np.random.default_rng(41)
+    for i in range(len(D6)):
+        _two_sided(vm, float(out["phi"][i]), out["z"][i], D6[i:i + 1], p, w, rng)
+
+
+def test_two_sided_independent_optimum_check_three_stage(setup):
+    """One control vector for the whole (d, theta) tree (reference pyds/run.py:76-91)."""
+    lm, eng, vm = setup
+    p = K.theta_samples(20)
+    w = np.full(20, 1 / 20)
+    d = D6[[0, 2, 4]]
+    out = eng.recourse_solve(d, p, w, z0=np.array([[2.5, 0, 0, 0, 0, 0, 0, 0.0]]), global_group=True)
+    _two_sided(vm, float(out["phi"][0]), out["z"], d, p, w, np.random.default_rng(43), n_random=1)
+
+
+def test_two_sided_independent_optimum_check_per_scenario_c4_shape(setup):
+    """Config C4's shape on a sample: 24 (d, theta) scenarios, 8 recourse controls each."""
+    lm, eng, vm = setup
+    rng = np.random.default_rng(47)
+    d = np.stack([rng.uniform(250, 350, 6), rng.uniform(250, 300, 6)], axis=1)
+    p = K.theta_samples(4)
+    out = eng.recourse_solve(d, p, per_scenario=True, max_iter=50)
+    n_infeasible = 0
+    for i in range(6):
+        for j in range(4):
+            phi = float(out["phi"][i, j])
+            n_infeasible += phi > 0
+            _two_sided(vm, phi, out["z"][i, j], d[i:i + 1], p[j:j + 1], np.ones(1), rng, n_random=1)
+    assert 0 < n_infeasible < 24                                   # the sample exercises both outcomes
+
+
 def test_per_scenario_recourse(setup):
     lm, eng, vm = setup
     p = K.theta_samples(7)
