@@ -33,8 +33,8 @@ def parse_blob(blob: bytes):
         nbytes = cnt * np.dtype(_DT[dt]).itemsize
         arr = np.frombuffer(blob, dtype=_DT[dt], count=cnt, offset=off).copy()
         off += nbytes + ((-nbytes) % 8)
-        if tag == b"PSEP":
-            cur = out.setdefault("sens", {})
+        if tag == b"PSEP":                               # payload: the program's number (1 sensitivities, 2 chain + dg)
+            cur = out.setdefault("sens" if int(arr[0]) == 1 else "chain", {})
             continue
         cur[tag.decode()] = arr
     return out

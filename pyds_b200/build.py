@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpyds_b200.so")
 SOURCES = ["pydsb_api.cu"]
-HEADERS = ["feas_kernel.cuh", "poly_chain.cuh", "chain_shapes.h", "recourse_kernel.cuh", "tape_vm.cuh", "common.cuh", "xvm_ops.cuh", "assembler.h", os.path.join("..", "..", "include", "pydsb.h")]
+HEADERS = ["feas_kernel.cuh", "poly_chain.cuh", "chain_shapes.h", "recourse_chain.cuh", "recourse_kernel.cuh", "tape_vm.cuh", "common.cuh", "xvm_ops.cuh", "assembler.h", os.path.join("..", "..", "include", "pydsb.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]

@@ -18,6 +18,7 @@
 #include "assembler.h"
 #include "chain_shapes.h"
 #include "recourse_kernel.cuh"
+#include "recourse_chain.cuh"
 
 using namespace pydsb;
 
@@ -63,13 +64,14 @@ struct Program {
     ChainDesc chain{};                  // its descriptor, copied to the constant bank (c_chain) before a launch
     unsigned long long shape_sb = 0;    // compile-time shape words of the chain (poly_chain.cuh, chain_shape_bits)
     unsigned shape_sq = 0;
+    RChainDesc rchain{};                // program 2: the chain with control sensitivities (recourse_chain.cuh)
     PolyBlock poly[MAX_BLOCKS];         // program 0: blocks lowered to polynomial coefficients
     bool present = false;
 };
 
 struct Model {
     int device = 0;
-    Program prog[2];
+    Program prog[3];                    // 0 feasibility, 1 coupled-block sensitivities, 2 chain + dg (sensitivities in registers)
     std::vector<double> z_lo, z_hi;
     std::vector<unsigned char> z_fix;
     double* d_zlo = nullptr;
@@ -236,6 +238,19 @@ SensFn sens_for(int ns, bool tri)
     }
 }
 
+// the chain evaluator of the control optimisation: the instantiation with the chain's shape folded at compile time when
+// that shape is registered (chain_shapes.h), else the generic one
+#define PYDSB_X(SB_, SQ_, NB_) {SB_, SQ_, rsens_kernel<NB_, SB_, SQ_>},
+const struct { unsigned long long sb; unsigned sq; SensFn fn; } g_rsens_kernels[] = {PYDSB_CHAIN_SHAPES(PYDSB_X)};
+#undef PYDSB_X
+SensFn rsens_for(const Program& p)
+{
+    if (!getenv("PYDSB_GENERIC_CHAIN"))
+        for (const auto& k : g_rsens_kernels)
+            if (k.sb == p.shape_sb && k.sq == p.shape_sq) return k.fn;
+    return p.chain_nb <= 2 ? rsens_kernel<2> : rsens_kernel<3>;
+}
+
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 void free_program(Program& p)
@@ -263,8 +278,10 @@ bool resolve_table(const Sections& secs, const char* tag, int n, int cap, unsign
 }
 
 // Parse one program's sections into an ExecImage + device buffers.
-int build_program(const Sections& secs, bool sens, Program& P, bool upload = true)
+// mode: 0 feasibility program, 1 coupled-block sensitivity program, 2 chain program with dg/dxe, dg/dqe (rsens_kernel)
+int build_program(const Sections& secs, int mode, Program& P, bool upload = true)
 {
+    const bool sens = mode == 1, rchain = mode == 2;
     static const char* need[] = {"HEAD", "DBLS", "CNST", "ADOT", "BWTS", "BIGM", "ZFIX", "TPRO", "TELM", "TPNT", "TGEE",
                                  "RPAR", "RX0_", "RQ0_", "RZ__", "RF__", "RJ__", "RFQ_", "RG__", "CMAP"};
     for (const char* t : need)
@@ -291,7 +308,7 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
                 if (B0[5 * b] > maxns) maxns = B0[5 * b];
                 all_poly = all_poly && (B0[5 * b + 1] & 2u);
             }
-        g.spt = sens ? 1 : choose_spt(maxns, all_poly);
+        g.spt = (sens || rchain) ? 1 : choose_spt(maxns, all_poly);
     }
     const unsigned US = (unsigned)g.spt * BLOCK * 8u;      // bytes between consecutive slots
     {
@@ -446,12 +463,69 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
         in.n_par = g.d_dim + g.p_dim; in.ng = g.ng; in.xe_slot = g.xe_slot;
         // HEAD[15] bit 0 (DaeModel(fused_chain=False)) or PYDSB_NO_CHAIN=1: keep the element loop interpreted
         const char* no_chain = getenv("PYDSB_NO_CHAIN");
-        in.allow_chain = !(H[15] & 1u) && !(no_chain && atoi(no_chain) != 0);
+        in.allow_chain = rchain || (!(H[15] & 1u) && !(no_chain && atoi(no_chain) != 0));
         Assembler as;
         if (!as.assemble(in)) return fail(PYDSB_ERR_UNSUPPORTED, "assembler: " + as.err);
         P.xprog.swap(as.words);
         P.chain_nb = as.chain_nb;
-        if (P.chain_nb > 0) {
+        if (rchain && P.xprog.size() / 4 > 2 * (size_t)MAX_PROG_R) { P.present = false; P.chain_nb = 0; return PYDSB_OK; }
+        if (rchain) {
+            // the sensitivity chain needs the fused shape (and what recourse_chain.cuh supports of it): otherwise this
+            // program is simply absent and sens_kernel (program 1) evaluates
+            bool ok = as.chain_nb > 0 && g.nz >= 1 && g.nz <= RC_NZ && g.nq <= RC_NQ && g.nfe <= RC_MAXFE && g.nce <= 4 && g.ng <= 8;
+            const ChainDesc& cdx = as.chain;
+            for (unsigned b = 0; ok && b < cdx.nb; ++b) {
+                const unsigned m2 = cdx.blk[b].c[2].meta;
+                ok = ok && !(m2 & CT_HAS_CTRL);
+                for (int k = 0; k < 2; ++k) {
+                    const unsigned mk = cdx.blk[b].c[k].meta;
+                    ok = ok && !((mk & CT_HAS_CTRL) && ((mk >> 8) & 3u) != 0u);      // a control enters as narrow x control
+                }
+            }
+            for (unsigned q = 0; ok && q < cdx.nq; ++q) {
+                const unsigned mq = cdx.quad[q].meta;
+                ok = ok && !((mq & CT_HAS_CTRL) && ((mq >> 8) & 3u) != 0u);
+            }
+            const Section *rgx = find(secs, "RGX_"), *rgq = find(secs, "RGQ_"), *rz = find(secs, "RZ__"), *zf = find(secs, "ZFIX");
+            ok = ok && rgx && rgq && (int)rgx->count >= g.ng * g.ns && (int)rgq->count >= (g.nq ? g.ng * g.nq : 0) &&
+                 rz && zf && (int)rz->count >= g.nz && (int)zf->count >= g.nz;
+            if (!ok) { P.present = false; P.chain_nb = 0; return PYDSB_OK; }
+            RChainDesc& rd = P.rchain;
+            rd = RChainDesc{};
+            rd.ch = as.chain;
+            chain_shape_bits(rd.ch, P.shape_sb, P.shape_sq);
+            auto enc = [&](unsigned ref) -> unsigned {       // narrow reference -> slot offset / constant-pool offset / none
+                if (ref == REF_NONE) return RC_REF_NONE;
+                if (ref & REF_CONST) return RC_REF_CONST | (((ref & REF_MASK) + 3u) * 8u);
+                return (ref & REF_MASK) * US;
+            };
+            const uint16_t* GX = reinterpret_cast<const uint16_t*>(rgx->data);
+            const uint16_t* GQ = reinterpret_cast<const uint16_t*>(rgq->data);
+            for (int k = 0; k < 8; ++k) {
+                for (int b = 0; b < CHAIN_MAXB; ++b) rd.gx_off[k][b] = RC_REF_NONE;
+                for (int q = 0; q < RC_NQ; ++q) rd.gq_off[k][q] = RC_REF_NONE;
+            }
+            for (int k = 0; k < g.ng; ++k) {
+                for (unsigned b = 0; b < rd.ch.nb; ++b) {
+                    const int st = (int)(rd.ch.blk[b].x_off / US) - g.x_slot;          // the block's state: x_slot + 3 st
+                    rd.gx_off[k][b] = enc(GX[k * g.ns + st / 3]);
+                }
+                for (int q = 0; q < g.nq; ++q) rd.gq_off[k][q] = enc(GQ[k * g.nq + q]);
+            }
+            const uint16_t* cm = reinterpret_cast<const uint16_t*>(find(secs, "CMAP")->data);
+            unsigned live = 0;
+            for (int e = 0; e < g.nfe; ++e) {
+                for (int k = 0; k < g.nce; ++k) { rd.cmap[e][k] = (unsigned char)cm[e * g.nce + k]; live |= 1u << cm[e * g.nce + k]; }
+                rd.live[e] = live;
+            }
+            rd.nce = (unsigned)g.nce;
+            const uint16_t* RZ = reinterpret_cast<const uint16_t*>(rz->data);
+            const uint16_t* ZF = reinterpret_cast<const uint16_t*>(zf->data);
+            for (int c = 0; c < g.nz; ++c) {
+                rd.zfix_ref[c] = RC_REF_NONE;
+                if (ZF[c]) { rd.zfix_mask |= 1u << c; rd.zfix_ref[c] = enc(RZ[c]); }
+            }
+        } else if (P.chain_nb > 0) {
             P.chain = as.chain;                              // what the kernel reads from the constant bank
             const ChainDesc& cd = P.chain;
             chain_shape_bits(cd, P.shape_sb, P.shape_sq);
@@ -521,6 +595,11 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
     g.off_const = o; o += (g.n_const + 3) * 8 * g.spt;      // chain programs: SPT-wide entries after three specials
     g.off_tabs = o; o = align_up(o + g.n_tabs * 2, 128);
     int land = g.spt * BLOCK * g.p_dim * 8;
+    if (rchain) {
+        land = 0;
+        if ((BLOCK / 32) * RECOURSE_STAGES * recourse_nv(g.nz) > g.n_units * BLOCK)
+            return fail(PYDSB_ERR_UNSUPPORTED, "chain program too small for the reduction scratch");
+    }
     if (sens) {
         land = 0;                                           // sens_kernel loads theta directly
         // the cross-warp scratch of the shared modes overlays the program's slots
@@ -531,6 +610,7 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
     g.off_slots = o;
     int units = g.n_units + (g.zero_off ? 1 : 0);
     if (sens) units += recourse_sens_rows(g.ns, g.nq, g.ng) * g.nz;     // Sx, Sq (later Dc + one row) of sens_kernel
+    if (rchain) units += (g.ng + 1) * g.nz;                             // Dc + one row (the sensitivities live in registers)
     o += units * g.spt * BLOCK * 8;
     g.smem_bytes = o;
 
@@ -547,7 +627,7 @@ int build_program(const Sections& secs, bool sens, Program& P, bool upload = tru
 }
 
 // Split a blob into the section lists of its (one or two) programs.
-int split_blob(const void* blob, size_t nbytes, Sections (&progs)[2], int& n_progs)
+int split_blob(const void* blob, size_t nbytes, Sections (&progs)[3], int& n_progs)
 {
     if (!blob || nbytes < 16) return fail(PYDSB_ERR_INVALID, "null or truncated blob");
     const unsigned char* p = static_cast<const unsigned char*>(blob);
@@ -570,13 +650,17 @@ int split_blob(const void* blob, size_t nbytes, Sections (&progs)[2], int& n_pro
         if (off + nb > nbytes) return fail(PYDSB_ERR_INVALID, "truncated section payload");
         s.data = p + off;
         off += nb;
-        if (strncmp(s.tag, "PSEP", 4) == 0) {
-            if (++cur > 1) return fail(PYDSB_ERR_INVALID, "more than two programs in blob");
+        if (strncmp(s.tag, "PSEP", 4) == 0) {             // payload: the number of the program that follows
+            uint32_t idx = 0;
+            if (s.count >= 1) memcpy(&idx, s.data, 4);
+            if (idx < 1 || idx > 2) return fail(PYDSB_ERR_INVALID, "bad program separator in blob");
+            cur = (int)idx;
+            if (cur + 1 > n_progs) n_progs = cur + 1;
             continue;
         }
         progs[cur].push_back(s);
     }
-    n_progs = cur + 1;
+    if (n_progs < 1) n_progs = 1;
     return PYDSB_OK;
 }
 
@@ -601,13 +685,12 @@ int pydsb_version(void) { return 1; }
 int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handle)
 {
     if (!blob || !handle || nbytes < 16) return fail(PYDSB_ERR_INVALID, "null or truncated blob");
-    Sections progs[2];
+    Sections progs[3];
     int n_progs = 0;
     {
         const int prc = split_blob(blob, nbytes, progs, n_progs);
         if (prc != PYDSB_OK) return prc;
     }
-    const int cur = n_progs - 1;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -617,8 +700,9 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
     CUDA_TRY(cudaSetDevice(device));
     Model* m = new Model();
     m->device = device;
-    int rc = build_program(progs[0], false, m->prog[0]);
-    if (rc == PYDSB_OK && cur == 1) rc = build_program(progs[1], true, m->prog[1]);
+    int rc = build_program(progs[0], 0, m->prog[0]);
+    if (rc == PYDSB_OK && !progs[1].empty()) rc = build_program(progs[1], 1, m->prog[1]);
+    if (rc == PYDSB_OK && !progs[2].empty()) rc = build_program(progs[2], 2, m->prog[2]);
     if (rc != PYDSB_OK) {
         std::string msg = g_err;
         pydsb_model_destroy(m);
@@ -652,7 +736,7 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
     if (e == cudaSuccess) e = cudaMalloc(&m->d_counters, PYDSB_CNT_COUNT * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(m->d_counters, 0, PYDSB_CNT_COUNT * sizeof(unsigned long long));
     if (e == cudaSuccess) {
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < 3; ++q)
             if (m->prog[q].present && (size_t)m->prog[q].img.smem_bytes > prop.sharedMemPerBlockOptin) {
                 pydsb_model_destroy(m);
                 return fail(PYDSB_ERR_UNSUPPORTED, "model needs more shared memory per CTA than the device offers");
@@ -772,12 +856,12 @@ int pydsb_ns_replace_worst(double* live_p, long long n_live, const double* cand_
 
 int pydsb_assemble(const void* blob, size_t nbytes, uint32_t* words, size_t cap, size_t* n_words, long long* info, int n_info)
 {
-    Sections progs[2];
+    Sections progs[3];
     int n_progs = 0;
     int rc = split_blob(blob, nbytes, progs, n_progs);
     if (rc != PYDSB_OK) return rc;
     Program P;
-    rc = build_program(progs[0], false, P, /*upload=*/false);
+    rc = build_program(progs[0], 0, P, /*upload=*/false);
     if (rc != PYDSB_OK) return rc;
     if (n_words) *n_words = P.xprog.size();
     if (words)
@@ -796,6 +880,7 @@ int pydsb_model_destroy(void* handle)
     cudaSetDevice(m->device);
     free_program(m->prog[0]);
     free_program(m->prog[1]);
+    free_program(m->prog[2]);
     if (m->d_zlo) cudaFree(m->d_zlo);
     if (m->d_zhi) cudaFree(m->d_zhi);
     if (m->d_zfix) cudaFree(m->d_zfix);
@@ -1001,7 +1086,11 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
     Model* m = static_cast<Model*>(handle);
     if (!m) return fail(PYDSB_ERR_INVALID, "null handle");
     if (!m->prog[1].present) return fail(PYDSB_ERR_UNSUPPORTED, "blob carries no sensitivity program");
-    const ExecImage& img = m->prog[1].img;
+    // evaluator: the chain with its sensitivities in registers (program 2, rsens_kernel) when the model has that shape,
+    // else the coupled-block interpreter (program 1, sens_kernel); PYDSB_NO_RCHAIN=1 forces the latter
+    const char* no_rc = getenv("PYDSB_NO_RCHAIN");
+    const bool use_rc = m->prog[2].present && m->prog[2].chain_nb > 0 && !(no_rc && atoi(no_rc) != 0);
+    const ExecImage& img = use_rc ? m->prog[2].img : m->prog[1].img;
     const int nz = img.nz;
     if (nz < 1) return fail(PYDSB_ERR_INVALID, "model has no control to optimise");
     if (n_d < 0 || n_t < 1) return fail(PYDSB_ERR_INVALID, "bad sizes");
@@ -1092,10 +1181,16 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
     lm_init_kernel<<<gb, tb, 0, st>>>(G, nz, z0, (int)(z0 ? z0_rows : 0), z_cur, z_try, F_cur, raw_cur, lam, mu, status,
                                       first, iters, o[2], o[0]);
     CUDA_TRY_WS(cudaGetLastError());
-    SensFn fn = sens_for(img.ns, img.tri != 0);
+    SensFn fn = use_rc ? rsens_for(m->prog[2]) : sens_for(img.ns, img.tri != 0);
     CUDA_TRY_WS(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
-    CUDA_TRY_WS(cudaMemcpyToSymbolAsync(c_prog_s, m->prog[1].xprog.data(), m->prog[1].xprog.size() * sizeof(uint32_t), 0,
-                                        cudaMemcpyHostToDevice, st));
+    if (use_rc) {
+        CUDA_TRY_WS(cudaMemcpyToSymbolAsync(c_prog_r, m->prog[2].xprog.data(), m->prog[2].xprog.size() * sizeof(uint32_t), 0,
+                                            cudaMemcpyHostToDevice, st));
+        CUDA_TRY_WS(cudaMemcpyToSymbolAsync(c_rchain, &m->prog[2].rchain, sizeof(RChainDesc), 0, cudaMemcpyHostToDevice, st));
+    } else {
+        CUDA_TRY_WS(cudaMemcpyToSymbolAsync(c_prog_s, m->prog[1].xprog.data(), m->prog[1].xprog.size() * sizeof(uint32_t), 0,
+                                            cudaMemcpyHostToDevice, st));
+    }
     RecourseArgs ra{};
     ra.d = d; ra.theta = theta; ra.w = w; ra.n_d = n_d; ra.n_d_total = n_d_total; ra.n_t = n_t; ra.n_tiles = n_tiles;
     ra.per_scenario = per_scenario;

@@ -107,6 +107,88 @@ __device__ __forceinline__ void hinge_point(int ng, const double* ck, double cma
 // integrated, then Dc (ng) + one spare row
 __host__ __device__ inline int recourse_sens_rows(int ns, int nq, int ng) { return ns + nq > ng + 1 ? ns + nq : ng + 1; }
 
+// What one evaluation hands to the optimiser, shared by both evaluators (sens_kernel here, rsens_kernel in
+// recourse_chain.cuh): per-scenario mode the scenario's own {failed, c_k, grad c_k}; shared modes the reduced statistics
+// {Phi_mu, Phi, grad, Gauss-Newton H} of RECOURSE_STAGES smoothing stages, summed over the tile in a fixed order.
+// Dc[(k * nz + c) * BLOCK] = d c_k / d z_c of this thread's scenario (shared memory, one spare row of nz after the ng
+// rows); wsum: [BLOCK / 32][n_stages][NV] cross-warp scratch that may overlay the program's slots.
+__device__ __forceinline__ void recourse_emit(const RecourseArgs& ra, const int nz, const int ng, const int NV, const bool active,
+                                              const bool failed, const double (&ck)[8], const double cmax, double* const Dc,
+                                              double* const wsum, const long long grp, const long long j, const long long t,
+                                              const unsigned my_iters)
+{
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool per_scen = ra.per_scenario == 1;
+    if (per_scen) {
+        // the scenario's own c_k and grad c_k: lm_update_kernel evaluates the smoothed hinge for any mu
+        if (active) {
+            double* out = ra.acc + grp * recourse_nvp(ng, nz);
+            out[0] = failed ? 1.0 : 0.0;
+            for (int k = 0; k < ng; ++k) out[1 + k] = ck[k];
+            for (int k = 0; k < ng; ++k)
+                for (int c = 0; c < nz; ++c) out[1 + ng + k * nz + c] = Dc[(size_t)(k * nz + c) * BLOCK];
+        }
+    } else {
+        double wv = 0.0;
+        if (active) {
+            wv = ra.w ? __ldg(ra.w + j) : 1.0 / (double)ra.n_t;
+            if (ra.per_scenario == 2) wv /= (double)ra.n_d_total;   // the whole grid is one sample average
+        }
+        // v_c = sum_k p_k dc_kc kept in the spare row after Dc
+        double* const Vv = Dc + (size_t)ng * nz * BLOCK;
+        double mu = ra.mu[grp];
+        const int SNV = ra.n_stages * NV;
+        __syncthreads();                                         // every thread is done with the program's slots
+        for (int st = 0; st < ra.n_stages; ++st) {
+            double pk[8];
+            double phi, raw;
+            hinge_point(ng, ck, cmax, failed, mu, pk, phi, raw);
+            for (int c = 0; c < nz; ++c) {
+                double v = 0.0;
+                for (int k = 0; k < ng; ++k) v = fma(pk[k], Dc[(size_t)(k * nz + c) * BLOCK], v);
+                Vv[(size_t)c * BLOCK] = v;
+            }
+            const double wmu = wv / mu;
+            double* const ws = wsum + warp * SNV + st * NV;
+            auto emit = [&](int idx, double val) {
+                const double sm = warp_sum(val);
+                if (lane == 0) ws[idx] = sm;
+            };
+            emit(0, wv * phi);
+            emit(1, wv * raw);
+            for (int c = 0; c < nz; ++c) emit(2 + c, wv * Vv[(size_t)c * BLOCK]);
+            int idx = 2 + nz;
+            for (int a = 0; a < nz; ++a)
+                for (int b = a; b < nz; ++b, ++idx) {
+                    double hv = 0.0;
+                    for (int k = 0; k < ng; ++k)
+                        hv = fma(pk[k] * Dc[(size_t)(k * nz + a) * BLOCK], Dc[(size_t)(k * nz + b) * BLOCK], hv);
+                    hv = fma(-Vv[(size_t)a * BLOCK], Vv[(size_t)b * BLOCK], hv);
+                    emit(idx, wmu * hv);
+                }
+            mu = fmax(mu / 10.0, ra.mu_min);
+        }
+        __syncthreads();
+        for (int v = tid; v < SNV; v += BLOCK) {
+            double sm = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < BLOCK / 32; ++wq) sm += wsum[wq * SNV + v];    // fixed order: deterministic
+            ra.acc[t * SNV + v] = sm;                                // (i_d, tile) == blockIdx.x in the shared modes
+        }
+    }
+    if (ra.counters) {
+        const unsigned it_sum = warp_sum_u32(active ? my_iters : 0u);
+        const unsigned dn = warp_sum_u32(active ? 1u : 0u);
+        const unsigned fl = warp_sum_u32((active && failed) ? 1u : 0u);
+        if (lane == 0) {
+            atomicAdd(&ra.counters[0], (unsigned long long)dn);
+            atomicAdd(&ra.counters[1], (unsigned long long)it_sum);
+            atomicAdd(&ra.counters[3], (unsigned long long)fl);
+        }
+    }
+}
+
 // TRI: the Jacobian df/dx is lower triangular in the state order (every state depends on itself and on earlier
 // states only -- A -> B -> C kinetics): the 3*NS Newton system is solved by forward substitution over NS 3x3 systems
 // (the same Newton step as the dense LU, a third of the flops for NS = 2) and so are the sensitivity systems.
@@ -392,73 +474,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
         }
         for (int k = 0; k < ng; ++k) Dc[(size_t)(k * nz + c) * BLOCK] = dcv[k];
     }
-    if (per_scen) {
-        // the scenario's own c_k and grad c_k: lm_update_kernel evaluates the smoothed hinge for any mu
-        if (active) {
-            double* out = ra.acc + grp * recourse_nvp(ng, nz);
-            out[0] = failed ? 1.0 : 0.0;
-            for (int k = 0; k < ng; ++k) out[1 + k] = ck[k];
-            for (int k = 0; k < ng; ++k)
-                for (int c = 0; c < nz; ++c) out[1 + ng + k * nz + c] = Dc[(size_t)(k * nz + c) * BLOCK];
-        }
-    } else {
-        double wv = 0.0;
-        if (active) {
-            wv = ra.w ? __ldg(ra.w + j) : 1.0 / (double)ra.n_t;
-            if (ra.per_scenario == 2) wv /= (double)ra.n_d_total;   // the whole grid is one sample average
-        }
-        // v_c = sum_k p_k dc_kc kept in the spare row after Dc
-        double* const Vv = Dc + (size_t)ng * nz * BLOCK;
-        double mu = ra.mu[grp];
-        const int SNV = ra.n_stages * NV;
-        __syncthreads();                                         // every thread is done with the program's slots
-        for (int st = 0; st < ra.n_stages; ++st) {
-            double pk[8];
-            double phi, raw;
-            hinge_point(ng, ck, cmax, failed, mu, pk, phi, raw);
-            for (int c = 0; c < nz; ++c) {
-                double v = 0.0;
-                for (int k = 0; k < ng; ++k) v = fma(pk[k], Dc[(size_t)(k * nz + c) * BLOCK], v);
-                Vv[(size_t)c * BLOCK] = v;
-            }
-            const double wmu = wv / mu;
-            double* const ws = wsum + warp * SNV + st * NV;
-            auto emit = [&](int idx, double val) {
-                const double sm = warp_sum(val);
-                if (lane == 0) ws[idx] = sm;
-            };
-            emit(0, wv * phi);
-            emit(1, wv * raw);
-            for (int c = 0; c < nz; ++c) emit(2 + c, wv * Vv[(size_t)c * BLOCK]);
-            int idx = 2 + nz;
-            for (int a = 0; a < nz; ++a)
-                for (int b = a; b < nz; ++b, ++idx) {
-                    double hv = 0.0;
-                    for (int k = 0; k < ng; ++k)
-                        hv = fma(pk[k] * Dc[(size_t)(k * nz + a) * BLOCK], Dc[(size_t)(k * nz + b) * BLOCK], hv);
-                    hv = fma(-Vv[(size_t)a * BLOCK], Vv[(size_t)b * BLOCK], hv);
-                    emit(idx, wmu * hv);
-                }
-            mu = fmax(mu / 10.0, ra.mu_min);
-        }
-        __syncthreads();
-        for (int v = tid; v < SNV; v += BLOCK) {
-            double sm = 0.0;
-#pragma unroll
-            for (int wq = 0; wq < BLOCK / 32; ++wq) sm += wsum[wq * SNV + v];    // fixed order: deterministic
-            ra.acc[t * SNV + v] = sm;                                // (i_d, tile) == blockIdx.x in the shared modes
-        }
-    }
-    if (ra.counters) {
-        const unsigned it_sum = warp_sum_u32(active ? my_iters : 0u);
-        const unsigned dn = warp_sum_u32(active ? 1u : 0u);
-        const unsigned fl = warp_sum_u32((active && failed) ? 1u : 0u);
-        if (lane == 0) {
-            atomicAdd(&ra.counters[0], (unsigned long long)dn);
-            atomicAdd(&ra.counters[1], (unsigned long long)it_sum);
-            atomicAdd(&ra.counters[3], (unsigned long long)fl);
-        }
-    }
+    recourse_emit(ra, nz, ng, NV, active, failed, ck, cmax, Dc, wsum, grp, j, t, my_iters);
 }
 
 struct LmArgs {

@@ -304,6 +304,14 @@ class DaeModel:
         programs = [(roots, groups, blocks, blk_linear, blk_poly)]
         if ns <= 3:          # the sensitivity program is one coupled block: only for <= 3 dynamic states
             programs.append((roots_s, groups_s, [all_blk], [0], [None]))
+            if all(blk_poly) and self.fused_chain and any(not c.fixed for c in self.controls):
+                # program 2: the feasibility program again, its g tape extended by dg/dxe and dg/dqe -- when it assembles
+                # to a fused chain, the control sensitivities are propagated through the chain in registers
+                # (csrc/recourse_chain.cuh) instead of through the coupled-block interpreter of program 1
+                roots_c = dict(roots)
+                roots_c["gx"] = roots_s["gx"]
+                roots_c["gq"] = roots_s["gq"]
+                programs.append((roots_c, groups, blocks, blk_linear, blk_poly))
         blk_fixed = []
         for prog, (rts, grp, blks, lin, pol) in enumerate(programs):
             low = T.lower(g, n_param=self.n_param, n_ctrl_elem=nce, ns=ns, nq=nq, roots=rts, pt_groups=grp, ncp=self.ncp)
@@ -360,13 +368,16 @@ class DaeModel:
             sec("RFQ_", "u16", tab(low, "fq", nq))
             sec("RG__", "u16", low.refs["g"])
             sec("CMAP", "u16", cmap)
-            if prog:
+            if prog == 2:
+                sec("RGX_", "u16", tab(low, "gx", ng * ns))
+                sec("RGQ_", "u16", tab(low, "gq", ng * nq))
+            if prog == 1:
                 sec("RFQX", "u16", tab(low, "fqx", nq * ns))
                 sec("RFZ_", "u16", tab(low, "fz", ns * nce))
                 sec("RFQZ", "u16", tab(low, "fqz", nq * nce))
                 sec("RGX_", "u16", tab(low, "gx", ng * ns))
                 sec("RGQ_", "u16", tab(low, "gq", ng * nq))
-                if self.second_derivatives:
+                if self.second_derivatives and prog == 1:
                     sec("RGEE", "u16", low.refs["gee"])          # (ng, ns+nq, ns+nq)
                     sec("RFXX", "u16", low.refs["fxx"])          # (ns, ns, ns), wide references
         low = lows[0]
@@ -489,8 +500,8 @@ def parse_blob(blob: bytes):
         nbytes = cnt * np.dtype(dtype).itemsize
         arr = np.frombuffer(blob, dtype=dtype, count=cnt, offset=off).copy()
         off += nbytes + ((-nbytes) % 8)
-        if tag == b"PSEP":
-            cur = out.setdefault("sens", {})
+        if tag == b"PSEP":                               # payload: the program's number (1 sensitivities, 2 chain + dg)
+            cur = out.setdefault("sens" if int(arr[0]) == 1 else "chain", {})
             continue
         cur[tag.decode()] = arr
     return out
