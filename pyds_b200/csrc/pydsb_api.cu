@@ -251,6 +251,19 @@ SensFn rsens_for(const Program& p)
     return p.chain_nb <= 2 ? rsens_kernel<2> : rsens_kernel<3>;
 }
 
+// the whole shared-control optimisation of a group in one launch (theta set within one tile)
+typedef void (*RFusedFn)(const ExecImage, const RecourseArgs, const LmArgs);
+#define PYDSB_X(SB_, SQ_, NB_) {SB_, SQ_, rfused_kernel<NB_, SB_, SQ_>},
+const struct { unsigned long long sb; unsigned sq; RFusedFn fn; } g_rfused_kernels[] = {PYDSB_CHAIN_SHAPES(PYDSB_X)};
+#undef PYDSB_X
+RFusedFn rfused_for(const Program& p)
+{
+    if (!getenv("PYDSB_GENERIC_CHAIN"))
+        for (const auto& k : g_rfused_kernels)
+            if (k.sb == p.shape_sb && k.sq == p.shape_sq) return k.fn;
+    return p.chain_nb <= 2 ? rfused_kernel<2> : rfused_kernel<3>;
+}
+
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 void free_program(Program& p)
@@ -1208,6 +1221,21 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
     if (!(opts && opts[5] > 0) && total_tiles <= 4096) check_every = 1;
     if (reduce) check_every = 1;                 // every process must take the same decisions at the same iterations
     if (total_tiles > 0x7fffffffLL || G > 0x7fffffffLL) { cleanup(); return fail(PYDSB_ERR_INVALID, "grid too large"); }
+    const char* no_fused = getenv("PYDSB_NO_FUSED_LM");
+    if (use_rc && per_scenario == 0 && n_tiles == 1 && nz <= RC_NZ && !reduce && !(no_fused && atoi(no_fused) != 0)) {
+        // a shared-control group whose theta set fits one tile (the shipped scripts: 50 samples): the whole optimisation of
+        // the group runs inside ONE launch, a CTA per group (rfused_kernel) -- no launch pair, no count read-back per iteration
+        RFusedFn ff = rfused_for(m->prog[2]);
+        CUDA_TRY_WS(cudaFuncSetAttribute(ff, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
+        ra.active = nullptr; ra.n_active = nullptr;
+        la.active_in = nullptr; la.n_active_in = nullptr; la.active_out = nullptr; la.n_running = counts;
+        {
+            ProfScope ps(m, 1, st);
+            ff<<<(unsigned)G, BLOCK, img.smem_bytes, st>>>(img, ra, la);
+        }
+        CUDA_TRY_WS(cudaGetLastError());
+        m->launches += 1;
+    } else {
     // every group stops after max_iter evaluations (status 3) at the latest
     const long long* act_in = nullptr;           // null: every group (first iteration; always in the shared modes)
     const int* n_in = nullptr;
@@ -1254,6 +1282,7 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
             if (running == 0) break;
             if (compact) upper = running;
         }
+    }
     }
     CUDA_TRY_WS(cudaMemcpyAsync(z_out, z_cur, (size_t)G * nz * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (phi_out) CUDA_TRY_WS(cudaMemcpyAsync(phi_out, raw_cur, (size_t)G * sizeof(double), cudaMemcpyDeviceToDevice, st));

@@ -136,7 +136,7 @@ __device__ __forceinline__ RcTerm rc_term(const char* __restrict__ base, const c
     if (meta & CT_HAS_CTRL) {
         t.zi = (int)c_rchain.cmap[e][(meta >> 4) & 0xFu];
         t.nvn = nv;
-        t.nvz = nv * (((c_rchain.zfix_mask >> t.zi) & 1u) ? rc_ref(base, cz, c_rchain.zfix_ref[t.zi]) : __ldg(zg + t.zi));
+        t.nvz = nv * (((c_rchain.zfix_mask >> t.zi) & 1u) ? rc_ref(base, cz, c_rchain.zfix_ref[t.zi]) : __ldcg(zg + t.zi));
     }
     return t;
 }
@@ -160,8 +160,12 @@ __device__ __forceinline__ double rc_dpow(const double (&X)[NB][3], const double
     return p == 1u ? dv : 2.0 * xv * dv;
 }
 
-template <int NB, unsigned long long SB = 0ull, unsigned SQ = 0u>
-__global__ void __launch_bounds__(BLOCK, SB ? 3 : 2) rsens_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ RecourseArgs ra)
+// la == nullptr: one evaluation (the host loop of pydsb_recourse_solve launches lm_update_kernel next).
+// la != nullptr (rfused_kernel): the WHOLE optimisation of a shared-control group whose theta set fits one tile -- evaluate,
+// reduce the statistics over the CTA, thread 0 takes the Levenberg-Marquardt decision (lm_update_group_regs, the same
+// code the separate kernel runs), repeat until the group stops: no launch, no host round trip per iteration.
+template <int NB, unsigned long long SB, unsigned SQ>
+__device__ __forceinline__ void rsens_body(const ExecImage& img, const RecourseArgs& ra, const LmArgs* la)
 {
     typedef RChainShape<SB, SQ> SH;
     constexpr int NQ = SH::NQC;
@@ -183,6 +187,7 @@ __global__ void __launch_bounds__(BLOCK, SB ? 3 : 2) rsens_kernel(const __grid_c
     const double h = 1.0 / (double)img.nfe;
     const int NV = recourse_nv(nz);
 
+  for (int fused_it = 0;; ++fused_it) {
     // ---- which scenario (as sens_kernel) ----
     const long long t = blockIdx.x;
     const bool per_scen = ra.per_scenario == 1;
@@ -215,9 +220,9 @@ __global__ void __launch_bounds__(BLOCK, SB ? 3 : 2) rsens_kernel(const __grid_c
         valid = tid < rows;
         j = j0 + (valid ? tid : rows - 1);
         grp = i_d;
-        if (ra.status[grp] != 0) return;
+        if (__ldcg(ra.status + grp) != 0) return;
     }
-    const bool active = valid && ra.status[grp] == 0;
+    const bool active = valid && __ldcg(ra.status + grp) == 0;
     if (!__syncthreads_or(active)) return;
 
     for (int c = 0; c < img.p_dim; ++c) RC_LD_W(base, cd.par_off[img.d_dim + c]) = __ldg(ra.theta + j * img.p_dim + c);
@@ -460,6 +465,28 @@ __global__ void __launch_bounds__(BLOCK, SB ? 3 : 2) rsens_kernel(const __grid_c
         }
     }
     recourse_emit(ra, nz, ng, NV, active, failed, ck, cmax, Dc, wsum, grp, j, t, my_iters);
+    if (la == nullptr) return;
+    // ---- fused: the group's update by one thread, then the next evaluation (or the end) ----
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0) lm_update_group_regs<RC_NZ>(*la, grp);
+    __threadfence_block();
+    __syncthreads();
+    if (fused_it > la->max_iter) return;                     // (the update stops the group at its iteration cap)
+  }
+}
+
+template <int NB, unsigned long long SB = 0ull, unsigned SQ = 0u>
+__global__ void __launch_bounds__(BLOCK, SB ? 3 : 2) rsens_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ RecourseArgs ra)
+{
+    rsens_body<NB, SB, SQ>(img, ra, nullptr);
+}
+
+template <int NB, unsigned long long SB = 0ull, unsigned SQ = 0u>
+__global__ void __launch_bounds__(BLOCK, 2) rfused_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ RecourseArgs ra,
+                                                         const __grid_constant__ LmArgs la)
+{
+    rsens_body<NB, SB, SQ>(img, ra, &la);
 }
 
 #undef RC_A

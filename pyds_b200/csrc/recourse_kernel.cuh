@@ -137,7 +137,7 @@ __device__ __forceinline__ void recourse_emit(const RecourseArgs& ra, const int 
         }
         // v_c = sum_k p_k dc_kc kept in the spare row after Dc
         double* const Vv = Dc + (size_t)ng * nz * BLOCK;
-        double mu = ra.mu[grp];
+        double mu = __ldcg(ra.mu + grp);                         // (rfused_kernel: updated by the group's thread 0 in between)
         const int SNV = ra.n_stages * NV;
         __syncthreads();                                         // every thread is done with the program's slots
         for (int st = 0; st < ra.n_stages; ++st) {

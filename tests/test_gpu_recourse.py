@@ -281,3 +281,50 @@ def test_threestage_manager_on_two_gpus():
                         "127.0.0.1", "--master-port", "29733", os.path.join(root, "tools", "run_threestage_dist.py"),
                         "--n-d", "21", "--n-p", "20"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_evaluators_and_fused_loop_agree(setup, monkeypatch):
+    """Three ways through the same optimisation of a shared-control group with 50 theta samples: the chain evaluator
+    inside the single-launch loop (rfused_kernel), the chain evaluator under the host loop (rsens_kernel +
+    lm_update_kernel), the coupled-block interpreter under the host loop (sens_kernel).  The first two run the same
+    code in a different harness: identical bits.  The third is another evaluation of the same derivatives."""
+    lm, eng, vm = setup
+    p = K.theta_samples(50)
+    w = np.full(50, 1 / 50)
+    rng = np.random.default_rng(53)
+    d = np.stack([rng.uniform(250, 350, 40), rng.uniform(250, 300, 40)], axis=1)
+    fused = eng.recourse_solve(d, p, w, z0=np.zeros((1, 8)))
+    monkeypatch.setenv("PYDSB_NO_FUSED_LM", "1")
+    host = eng.recourse_solve(d, p, w, z0=np.zeros((1, 8)))
+    for k in ("z", "phi", "status", "iters"):
+        np.testing.assert_array_equal(fused[k], host[k])
+    monkeypatch.setenv("PYDSB_NO_RCHAIN", "1")
+    interp = eng.recourse_solve(d, p, w, z0=np.zeros((1, 8)))
+    np.testing.assert_allclose(interp["phi"], fused["phi"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_array_equal(interp["status"], fused["status"])
+    # per-scenario mode: chain evaluator against the interpreter
+    monkeypatch.delenv("PYDSB_NO_RCHAIN")
+    a = eng.recourse_solve(d[:5], p[:9], per_scenario=True)
+    monkeypatch.setenv("PYDSB_NO_RCHAIN", "1")
+    b = eng.recourse_solve(d[:5], p[:9], per_scenario=True)
+    np.testing.assert_allclose(a["phi"], b["phi"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_array_equal(a["status"], b["status"])
+
+
+def test_chain_sensitivities_against_the_tape_interpreter(setup):
+    """The derivatives themselves: one LM iteration from a generic interior point moves along -H^-1 grad; comparing the
+    objective decrease is indirect, so take the gradient of the smoothed objective by central differences of the GPU's own
+    objective values (per-scenario mode, mu large enough to be smooth) against the interpreter's analytic dg."""
+    lm, eng, vm = setup
+    p = K.theta_samples(3)
+    d = D6[:2]
+    z = np.random.default_rng(59).uniform(0.3, 2.2, 8)
+    r = vm.evaluate(d, p, z=z, tol=1e-13, want_sens=True)            # dg (n_d, n_p, ng, nz) by the numpy interpreter
+    eps = 1e-5
+    g0 = eng.eval_host(d, p, None, z=z, want_g=True)[0]
+    np.testing.assert_allclose(g0, r["g"], rtol=1e-10, atol=1e-8)
+    for c in range(8):
+        zp, zm = z.copy(), z.copy()
+        zp[c] += eps; zm[c] -= eps
+        fd = (eng.eval_host(d, p, None, z=zp, want_g=True)[0] - eng.eval_host(d, p, None, z=zm, want_g=True)[0]) / (2 * eps)
+        np.testing.assert_allclose(fd, r["dg"][..., c], rtol=2e-5, atol=1e-6 * np.abs(r["dg"]).max())

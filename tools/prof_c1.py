@@ -25,3 +25,12 @@ r = eng.recourse_solve(d, p, w, z0=z0)
 print("iters", r["iters"].mean(), r["iters"].max())
 print("eval_host g ms", T(lambda: eng.eval_host(d, p, None, z=r["z"], want_g=True, want_P=False)))
 print("h2d 4 tensors ms", T(lambda: [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (d, p, w, z0)]))
+eng.set_profiling(True); eng.profile(reset=True)
+for _ in range(10): eng.recourse_solve_device(td, tp, tw, tz)
+pr = eng.profile(); print("per call: evaluator kernel ms", pr["sens_ms"] / 10, "launches", pr["sens_launches"] / 10, "lm ms", pr["lm_ms"] / 10)
+eng.set_profiling(False)
+print("g total ms", T(lambda: m.g(d, p), 10))
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for _ in range(10): m.g(d, p)
+pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
