@@ -123,6 +123,25 @@ def sens_flops_per_solve(lm, newton_iters_per_solve):
     return fl["pro"] + fl["g"] + nfe * (fl["elem"] + per_elem) + newton_iters_per_solve * per_iter + live * per_sens
 
 
+def rsens_flops_per_solve(lm, newton_iters_per_solve):
+    """The same count for the chain evaluator (rsens_kernel, csrc/recourse_chain.cuh): the state solve of the fused chain
+    (Newton iterations of the nonlinear blocks x their algorithmic flops, one inverse per scenario and a matrix-vector
+    product per element for a constant-decay block), the LU factors at the converged points (2/3 n^3 + the diagonal, once
+    per element and Newton block), and per element and control that has acted so far, per block: the derivative of the
+    right-hand side (4 flops per point), the right-hand side (2 n) and a solve (2 n^2); the quadrature sensitivities
+    (2 ncp + 2 each); the gradient assembly 2 ng nz (nb + nq)."""
+    fl = (lm.tapes_chain or lm.tapes).stats["flops"]
+    ncp, nfe, nb, nq, n = lm.ncp, lm.nfe, len(lm.blocks), lm.nq, lm.ncp
+    newton_blocks = [b for b in range(nb) if not lm.block_linear[b]]
+    const_blocks = nb - len(newton_blocks)
+    state = newton_iters_per_solve * lm.block_flops[newton_blocks[0]] if newton_blocks else 0.0
+    state += len(newton_blocks) * nfe * ((2 * n ** 3) // 3 + 2 * n) + const_blocks * (72 + nfe * (2 * n + 2 * n * n))
+    state += nfe * (fl["elem"] + sum(lm.block_fixed_flops) + ncp * fl.get("ptq", 0))
+    live = sum(len(set(int(z) for z in lm.cmap[:e + 1].reshape(-1))) for e in range(nfe))
+    per_pair = nb * (4 * ncp + 2 * n + 2 * n * n) + nq * (2 * ncp + 2)
+    return fl["pro"] + fl["g"] + state + live * per_pair + 2 * lm.ng * lm.nz * (nb + nq)
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -327,7 +346,9 @@ def c4_section(torch, capi, models, dev, peak_tflops, n_d=1000, n_t=10000):
     c, pr = eng.counters(), eng.profile()
     solves = c["scenarios"]
     iters = c["newton_iters"] / max(solves, 1)
-    f_alg = sens_flops_per_solve(lm, iters)
+    chain = eng.info.get("recourse_chain_blocks", 0) > 0
+    f_alg = rsens_flops_per_solve(lm, iters) if chain else sens_flops_per_solve(lm, iters)
+    kernel = f"rsens_kernel<{eng.info['recourse_chain_blocks']}> (chain, sensitivities in registers)" if chain else f"sens_kernel<{lm.ns},tri>"
     achieved = solves * f_alg / (pr["sens_ms"] * 1e-3) / 1e12
     # classification at the optimised controls, and how many scenarios sit inside the relaxed big-M tolerance band
     g = torch.empty((n_d, n_t, lm.ng), dtype=torch.float64, device=dev)
@@ -340,11 +361,11 @@ def c4_section(torch, capi, models, dev, peak_tflops, n_d=1000, n_t=10000):
            "value": n_d * n_t / secs, "unit": "scenario optimisations/s", "seconds": secs,
            "state_sensitivity_solves": solves, "solves_per_scenario": solves / (n_d * n_t),
            "solves_per_s": solves / secs, "newton_iters_per_solve": iters,
-           "kernels": {"sens_kernel_ms": pr["sens_ms"], "sens_launches": int(pr["sens_launches"]),
+           "kernels": {"evaluator": kernel, "sens_kernel_ms": pr["sens_ms"], "sens_launches": int(pr["sens_launches"]),
                        "lm_update_kernel_ms": pr["lm_ms"], "lm_launches": int(pr["lm_launches"]),
                        "lm_share_of_kernel_time": pr["lm_ms"] / max(pr["sens_ms"] + pr["lm_ms"], 1e-12),
                        "kernel_time_share_of_wall": (pr["sens_ms"] + pr["lm_ms"]) * 1e-3 / secs},
-           "roofline": {"bound": "fp64", "kernel": f"sens_kernel<{lm.ns},tri>", "kernel_ms": pr["sens_ms"],
+           "roofline": {"bound": "fp64", "kernel": kernel, "kernel_ms": pr["sens_ms"],
                         "flops_per_solve": f_alg, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                         "frac": achieved / peak_tflops},
            "classification": {"feasible_at_optimum": feas0, "inside_1e-7_band": band, "scenarios": n_d * n_t,

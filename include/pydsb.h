@@ -52,6 +52,8 @@ enum {
     PYDSB_INFO_NS = 0, PYDSB_INFO_NQ, PYDSB_INFO_NG, PYDSB_INFO_D_DIM, PYDSB_INFO_P_DIM, PYDSB_INFO_NZ,
     PYDSB_INFO_NFE, PYDSB_INFO_NCP, PYDSB_INFO_N_UNITS, PYDSB_INFO_SMEM_BYTES, PYDSB_INFO_BLOCKS_PER_SM,
     PYDSB_INFO_NUM_SMS, PYDSB_INFO_REGS_PER_THREAD, PYDSB_INFO_SCENARIOS_PER_THREAD, PYDSB_INFO_PROGRAM_LENGTH,
+    PYDSB_INFO_CHAIN_BLOCKS,          /* blocks of the fused element loop of the feasibility program (0: interpreted)   */
+    PYDSB_INFO_RECOURSE_CHAIN_BLOCKS, /* blocks of the chain evaluator of the control optimisation (0: sens_kernel)     */
     PYDSB_INFO_COUNT
 };
 

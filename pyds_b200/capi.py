@@ -17,7 +17,7 @@ _LIB = None
 
 Z_MODEL, Z_SHARED, Z_PER_DESIGN, Z_PER_SCENARIO = 0, 1, 2, 3
 INFO_NAMES = ["ns", "nq", "ng", "d_dim", "p_dim", "nz", "nfe", "ncp", "n_units", "smem_bytes", "blocks_per_sm",
-              "num_sms", "regs_per_thread", "scenarios_per_thread", "program_length"]
+              "num_sms", "regs_per_thread", "scenarios_per_thread", "program_length", "chain_blocks", "recourse_chain_blocks"]
 COUNTER_NAMES = ["scenarios", "newton_iters", "newton_warp_iters", "failed", "launches", "newton_flops"]
 
 EXPORTS = ["pydsb_last_error", "pydsb_version", "pydsb_model_create", "pydsb_model_destroy", "pydsb_model_info",

@@ -915,7 +915,8 @@ int pydsb_model_info(void* handle, long long* out, int n)
     if (!m || !out) return fail(PYDSB_ERR_INVALID, "null handle/out");
     const ExecImage& g = m->prog[0].img;
     long long v[PYDSB_INFO_COUNT] = {g.ns, g.nq, g.ng, g.d_dim, g.p_dim, g.nz, g.nfe, 3, g.n_units, g.smem_bytes,
-                                     m->blocks_per_sm, m->num_sms, m->regs, g.spt, g.n_prog};
+                                     m->blocks_per_sm, m->num_sms, m->regs, g.spt, g.n_prog, m->prog[0].chain_nb,
+                                     m->prog[2].present ? m->prog[2].chain_nb : 0};
     for (int i = 0; i < n && i < PYDSB_INFO_COUNT; ++i) out[i] = v[i];
     return PYDSB_OK;
 }

@@ -394,7 +394,7 @@ class DaeModel:
             blob=bytes(blob), ns=ns, nq=nq, ng=ng, nz=nz, d_dim=len(self.d_names), p_dim=len(self.p_names),
             nfe=self.nfe, ncp=self.ncp, n_units=lay.n_units, tapes=low, dyn_states=[self.states[i].name for i in dyn],
             quad_states=[self.states[i].name for i in quad], z_lo=np.asarray(z_lo), z_hi=np.asarray(z_hi),
-            tapes_sens=lows[1] if len(lows) > 1 else None, z_init=z_exprs, blocks=[[dyn_names[i] for i in blk] for blk in blocks], block_linear=blk_linear,
+            tapes_sens=lows[1] if len(lows) > 1 else None, tapes_chain=lows[2] if len(lows) > 2 else None, z_init=z_exprs, blocks=[[dyn_names[i] for i in blk] for blk in blocks], block_linear=blk_linear,
             block_flops=blk_flops, block_fixed_flops=blk_fixed, block_poly=[bool(x) for x in blk_poly],
             z_fixed=np.asarray(z_fixed, dtype=bool), big_m=np.asarray([m for _, _, m in self.constraints]),
             constraint_names=[n for n, _, _ in self.constraints], cmap=cmap, newton_rtol=self.newton_rtol,
@@ -433,6 +433,7 @@ class LoweredModel:
     cmap: np.ndarray
     newton_rtol: float
     newton_max_it: int
+    tapes_chain: T.LoweredTapes = None   # program 2: the feasibility tapes with dg/dxe, dg/dqe (chain evaluator)
     state_lo: np.ndarray = None        # bounds of the states in trajectory column order (dynamic, then quadrature)
     state_hi: np.ndarray = None
 
