@@ -58,6 +58,9 @@ class DEUS:
         for c in alg.get("stop_criteria", []):
             self.max_iterations = int(c.get("max_iterations", self.max_iterations))
         self.use_fast_path = bool(st["efp_evaluation"].get("use_fused_efp", True))
+        # device-resident sampling (settings 'device': a torch device): live set, proposals and probabilities stay on
+        # the GPU; needs an owner with ``efp_device(d, p, w) -> tensor`` (solve_device below)
+        self.device = alg.get("device", None)
         self.native_update = True                 # live-set update in libpyds_b200 (False: the Python loop)
         self.result = None
 
@@ -167,12 +170,15 @@ class DEUS:
         return live, live_p, heap
 
     def solve(self):
+        if self.device is not None:
+            return self.solve_device()
         rng = np.random.default_rng(self.seed)
         dim = len(self.lo)
         level, n_live, n_rep = self.schedule[0]
         live = self.lo + rng.uniform(size=(n_live, dim)) * (self.hi - self.lo)
         t_start = time.time()
         live_p = self.efp(live)
+        t_initial = time.time() - t_start
         n_evals = len(live)
         history, iter_times = [(live.copy(), live_p.copy())], []
         heap = None
@@ -211,6 +217,108 @@ class DEUS:
             "live_points": live, "live_efp": live_p, "iterations": it, "evaluations": n_evals,
             "inside_fraction": float(np.mean(live_p >= self.target)), "seconds": time.time() - t_start,
             "seconds_per_iteration": float(np.mean(iter_times)) if iter_times else 0.0,
+            "initial_live_set_seconds": t_initial,
             "samples": np.vstack([h[0] for h in history]), "samples_efp": np.concatenate([h[1] for h in history]),
+        }
+        return self.result
+
+    # ---- device-resident variant ---------------------------------------------------------------------
+    def solve_device(self):
+        """The same loop with the live set, the proposals and their probabilities resident on ``self.device`` (torch
+        tensors): per iteration nothing crosses the host boundary but a handful of scalars.
+
+        * bounding ellipsoid: mean / covariance / largest Mahalanobis radius by reductions on the device (the 6 x 6
+          Cholesky factor goes through the host: 36 doubles);
+        * proposals: rejection sampling from the tighter of (ellipsoid, its bounding box clipped to the design box) with
+          the device's counter-based generator -- every rank seeds it alike and therefore draws the SAME global proposal
+          set without any exchange, then evaluates only its own row block (``owner.efp_device``);
+        * live-set update: the sequential replace-the-worst pass leaves the ``n_live`` best of (live, accepted
+          candidates); here that set is selected in one stable descending sort of the concatenated probabilities
+          (ties: live points before candidates, candidates in proposal order).  Same set as the sequential rule whenever
+          no candidate ties with the final worst live value below the target; DEUS's own tie handling is unpinned.
+
+        Parity with DEUS is unpinned like ``solve``; the host variant stays the default."""
+        import torch
+        dev = torch.device(self.device)
+        owner = getattr(self.g_func, "__self__", None)
+        if owner is None or not hasattr(owner, "efp_device"):
+            raise ValueError("device-resident sampling needs a constraint-function owner with efp_device(d, p, w)")
+        f64 = dict(dtype=torch.float64, device=dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(self.seed)
+        lo, hi = torch.tensor(self.lo, **f64), torch.tensor(self.hi, **f64)
+        span = hi - lo
+        p_t, w_t = torch.tensor(self.p, **f64), torch.tensor(self.w, **f64)
+        dim = len(self.lo)
+        level, n_live, n_rep = self.schedule[0]
+        sync = (lambda: torch.cuda.synchronize(dev)) if dev.type == "cuda" else (lambda: None)
+        live = lo + torch.rand((n_live, dim), generator=gen, **f64) * span
+        sync(); t_start = time.time()
+        live_p = owner.efp_device(live, p_t, w_t)
+        sync(); t_initial = time.time() - t_start
+        n_evals = n_live
+        iter_times, it = [], 0
+        vol_ball = math.pi ** (dim / 2.0) / math.gamma(dim / 2.0 + 1.0)
+        while it < self.max_iterations:
+            inside = float((live_p >= self.target).double().mean())
+            if inside >= self.inside_fraction:
+                break
+            sync(); t0 = time.time()
+            worst = float(live_p.min())
+            for lv, nl, nr in self.schedule:
+                if worst >= lv:
+                    level, n_live, n_rep = lv, nl, nr
+            enlarge = self.f0 * max(1.0 - inside, 0.05) ** self.alpha
+            # ---- bounding ellipsoid in box-scaled coordinates ----
+            u = (live - lo) / span
+            mu = u.mean(dim=0)
+            xc = u - mu
+            n_pts = u.shape[0]
+            cov = (xc.T @ xc) / (n_pts - 1) + 1e-12 * torch.eye(dim, **f64) if n_pts > dim else 0.25 * torch.eye(dim, **f64)
+            L = torch.linalg.cholesky(cov)
+            y = torch.linalg.solve_triangular(L, xc.T, upper=False)
+            r = float((y * y).sum(dim=0).max().sqrt()) * (1.0 + enlarge)
+            ext = r * (L * L).sum(dim=1).sqrt()
+            blo, bhi = torch.clamp(mu - ext, min=0.0), torch.clamp(mu + ext, max=1.0)
+            vol_box = float(torch.clamp(bhi - blo, min=0.0).prod())
+            vol_ell = vol_ball * r ** dim * float(torch.diagonal(L).prod())
+            # ---- proposals ----
+            m = max(int(4 * n_rep) + 64, 4096)
+            from_box, chunks, have, first = False, [], 0, True
+            while have < n_rep:
+                if from_box:
+                    cand = blo + (bhi - blo) * torch.rand((m, dim), generator=gen, **f64)
+                    yy = torch.linalg.solve_triangular(L, (cand - mu).T, upper=False)
+                    ok = (yy * yy).sum(dim=0) <= r * r
+                else:
+                    z = torch.randn((m, dim), generator=gen, **f64)
+                    rad = torch.rand(m, generator=gen, **f64) ** (1.0 / dim) * r
+                    z = z * (rad / z.norm(dim=1))[:, None]
+                    cand = mu + z @ L.T
+                    ok = (cand.min(dim=1).values >= 0.0) & (cand.max(dim=1).values <= 1.0)
+                sel = cand[ok]
+                chunks.append(sel)
+                have += sel.shape[0]
+                if first and have < n_rep and vol_box > 0.0:
+                    a_ell = max(sel.shape[0] / m, 1.0 / m)
+                    from_box = vol_ell > vol_box              # same test as the host sampler: the tighter region wins
+                    m = min(max(int(1.5 * (n_rep - have) / max(a_ell if not from_box else a_ell * vol_ell / vol_box, 1e-3)), 4096), 1 << 20)
+                first = False
+            cand = lo + torch.cat(chunks)[:n_rep] * span
+            cand_p = owner.efp_device(cand, p_t, w_t)
+            n_evals += n_rep
+            # ---- live-set update: the n_live best of (live, candidates that beat the worst) ----
+            allp = torch.cat([live_p, cand_p])
+            allx = torch.cat([live, cand])
+            keep = torch.sort(allp, descending=True, stable=True).indices[:n_live]
+            keep = torch.sort(keep).values                    # keep the surviving live points in their slots' order
+            live, live_p = allx[keep], allp[keep]
+            sync(); iter_times.append(time.time() - t0)
+            it += 1
+        self.result = {
+            "live_points": live.cpu().numpy(), "live_efp": live_p.cpu().numpy(), "iterations": it, "evaluations": n_evals,
+            "inside_fraction": float((live_p >= self.target).double().mean()), "seconds": time.time() - t_start,
+            "seconds_per_iteration": float(np.mean(iter_times)) if iter_times else 0.0,
+            "initial_live_set_seconds": t_initial,
         }
         return self.result

@@ -100,3 +100,27 @@ class ShardedEfp:
         if self.world == 1:
             return P
         return self.all_gather_host(P, shard_sizes(len(d_global), self.world))
+
+    def efp_global_device(self, d_global, theta, w=None):
+        """``efp_global`` with everything resident: ``d_global`` (n, d_dim), ``theta``, ``w`` are fp64 tensors on the
+        engine's device and identical on every rank (the nested-sampling driver draws the proposals from a generator every
+        rank seeds alike); this rank evaluates its row block, one ``all_gather_into_tensor`` returns the probabilities of
+        all rows as a device tensor.  No host round trip: the only transfers are the gather over NVLink.  Works with CPU
+        tensors / gloo when the engine does (tests use a stand-in engine)."""
+        import torch
+        n = d_global.shape[0]
+        a, b = shard_rows(n, self.world, self.rank)
+        m = max(shard_sizes(n, self.world)) if self.world > 1 else n
+        P_pad = torch.zeros(m, dtype=torch.float64, device=d_global.device)
+        if b > a:
+            self.engine.eval_device(d_global[a:b].contiguous(), theta, w=w, P_out=P_pad[:b - a])
+        if self.world == 1:
+            return P_pad
+        import torch.distributed as dist
+        out = torch.empty(self.world * m, dtype=torch.float64, device=d_global.device)
+        dist.all_gather_into_tensor(out, P_pad, group=self.group)
+        sizes = shard_sizes(n, self.world)
+        if len(set(sizes)) == 1:
+            return out
+        out = out.view(self.world, m)
+        return torch.cat([out[r, :sizes[r]] for r in range(self.world)])

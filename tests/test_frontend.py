@@ -300,3 +300,51 @@ def test_output_record_value_dicts_have_the_reference_shape():
     assert v["c"][("A", round(0.155051 / 8, 6))] == s._traj[1, 2, 1, 0]
     assert v["c"][("C", 2.0)] == s._traj[1, 2, 24, 3]                # a state on a [0, 2] time set keeps its own bounds
     assert v["u"][0.125] == s._traj[1, 2, 3, 2]                      # scalar-indexed Var: keyed by t alone
+
+
+def test_device_resident_sampler_matches_the_host_sampler_statistically():
+    """ns.DEUS with settings 'device' (torch tensors; the CPU here): same loop, live set / proposals / probabilities resident.
+    Both variants must converge to the same region: live set inside the target, similar centre and spread."""
+    import torch
+
+    class Owner:
+        def g(self, d, p):
+            raise NotImplementedError
+
+        def efp(self, d, p, w):
+            d = np.asarray(d)
+            return np.clip(1.2 - ((d - 0.6) ** 2).sum(1) * 4.0, 0.0, 1.0)
+
+        def efp_device(self, d, p, w):
+            return torch.clamp(1.2 - ((d - 0.6) ** 2).sum(dim=1) * 4.0, 0.0, 1.0)
+
+    o = Owner()
+
+    def form(device):
+        alg = {"prng_seed": 11, "stop_criteria": [{"max_iterations": 200}]}
+        if device:
+            alg["device"] = device
+        return {"activity_type": "ds",
+                "problem": {"design_variables": [{"a": [0, 1]}, {"b": [0, 1]}, {"c": [0, 1]}], "parameters_best_estimate": [1.0],
+                            "parameters_samples": [{"c": [1.0], "w": 1.0}], "target_reliability": 0.9},
+                "solver": {"name": "ds-ns", "settings": {"efp_evaluation": {"constraints_func_ptr": o.g},
+                                                         "points_schedule": [(0.0, 300, 30), (0.5, 400, 40)],
+                                                         "stop_criteria": [{"inside_fraction": 1.0}]},
+                           "algorithms": {"sampling": {"settings": alg}}}}
+
+    host, dev = ns.DEUS(form(None)).solve(), ns.DEUS(form("cpu")).solve()
+    for r in (host, dev):
+        assert r["inside_fraction"] == 1.0 and r["live_efp"].min() >= 0.9 and len(r["live_points"]) == 400
+        assert r["initial_live_set_seconds"] >= 0.0
+    # the feasible region is the ball |d - 0.6|^2 <= 0.075: both live sets fill it
+    np.testing.assert_allclose(host["live_points"].mean(0), dev["live_points"].mean(0), atol=0.03)
+    np.testing.assert_allclose(host["live_points"].std(0), dev["live_points"].std(0), rtol=0.25)
+    assert abs(host["iterations"] - dev["iterations"]) <= 0.5 * host["iterations"]
+    # an owner without efp_device is refused, not silently run on the host
+    class HostOnly:
+        def g(self, d, p):
+            raise NotImplementedError
+    f = form("cpu")
+    f["solver"]["settings"]["efp_evaluation"]["constraints_func_ptr"] = HostOnly().g
+    with pytest.raises(ValueError):
+        ns.DEUS(f).solve()

@@ -149,3 +149,66 @@ def test_manager_efp_coupled_design_points_gloo_world2(n_d):
     for r in range(2):
         np.testing.assert_allclose(res[r][0], P_ref, atol=1e-15)
     assert sorted(res[r][1][0] for r in range(2)) == ([(5, 11), (6, 11)] if n_d == 11 else [(0, 1), (1, 1)])
+
+
+class _TorchEngine:
+    """Stand-in with the Engine.eval_device signature on CPU tensors: P = smooth function of the design point."""
+
+    def eval_device(self, d, theta, w=None, z=None, z_mode=0, g_out=None, ind_out=None, P_out=None, stream=None, feas_tol=0.0):
+        import torch
+        P_out.copy_(torch.clamp(1.2 - ((d - 0.6) ** 2).sum(dim=1) * 4.0, 0.0, 1.0))
+
+
+def _device_ns_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from pyds_b200 import ns
+    from pyds_b200.parallel import ShardedEfp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = ShardedEfp(_TorchEngine(), world, rank)
+    # the resident gather itself, ragged (7 rows over 2 ranks)
+    d = torch.linspace(0.0, 1.0, 21, dtype=torch.float64).reshape(7, 3)
+    P = sh.efp_global_device(d, None, None)
+    ref = torch.clamp(1.2 - ((d - 0.6) ** 2).sum(dim=1) * 4.0, 0.0, 1.0)
+    assert P.shape == (7,) and torch.equal(P, ref)
+
+    class Owner:
+        def g(self, d, p):
+            raise NotImplementedError
+
+        def efp_device(self, d, p, w):
+            return sh.efp_global_device(d, p, w)
+
+    o = Owner()
+    form = {"activity_type": "ds",
+            "problem": {"design_variables": [{"a": [0, 1]}, {"b": [0, 1]}, {"c": [0, 1]}], "parameters_best_estimate": [1.0],
+                        "parameters_samples": [{"c": [1.0], "w": 1.0}], "target_reliability": 0.9},
+            "solver": {"name": "ds-ns", "settings": {"efp_evaluation": {"constraints_func_ptr": o.g}, "points_schedule": [(0.0, 301, 31)],
+                                                     "stop_criteria": [{"inside_fraction": 1.0}]},
+                       "algorithms": {"sampling": {"settings": {"prng_seed": 7, "device": "cpu", "stop_criteria": [{"max_iterations": 80}]}}}}}
+    res = ns.DEUS(form).solve()
+    q.put((rank, res["iterations"], res["inside_fraction"], res["live_points"], res["live_efp"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_device_resident_nested_sampling_gloo_world2():
+    """Every rank seeds the generator alike, draws the same proposals without any exchange, evaluates its own rows, and
+    all-gathers the probabilities: both ranks must follow the identical trajectory and reach the target."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_device_ns_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = {r: rest for r, *rest in (q.get(timeout=240) for _ in range(2))}
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    assert res[0][0] == res[1][0] and 0 < res[0][0] < 80 and res[0][1] == 1.0
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    np.testing.assert_array_equal(res[0][3], res[1][3])
+    assert res[0][3].min() >= 0.9 and res[0][2].shape == (301, 3)
