@@ -274,9 +274,11 @@ class DEUS:
             mu = u.mean(dim=0)
             xc = u - mu
             n_pts = u.shape[0]
-            cov = (xc.T @ xc) / (n_pts - 1) + 1e-12 * torch.eye(dim, **f64) if n_pts > dim else 0.25 * torch.eye(dim, **f64)
-            L = torch.linalg.cholesky(cov)
-            y = torch.linalg.solve_triangular(L, xc.T, upper=False)
+            # the dim x dim factor goes through the host (a few dozen doubles): no dense-solver library on the device path
+            cov_h = ((xc.T @ xc) / (n_pts - 1)).cpu().numpy() + 1e-12 * np.eye(dim) if n_pts > dim else 0.25 * np.eye(dim)
+            L_h = np.linalg.cholesky(cov_h)
+            L, Linv = torch.tensor(L_h, **f64), torch.tensor(np.linalg.inv(L_h), **f64)
+            y = Linv @ xc.T
             r = float((y * y).sum(dim=0).max().sqrt()) * (1.0 + enlarge)
             ext = r * (L * L).sum(dim=1).sqrt()
             blo, bhi = torch.clamp(mu - ext, min=0.0), torch.clamp(mu + ext, max=1.0)
@@ -288,7 +290,7 @@ class DEUS:
             while have < n_rep:
                 if from_box:
                     cand = blo + (bhi - blo) * torch.rand((m, dim), generator=gen, **f64)
-                    yy = torch.linalg.solve_triangular(L, (cand - mu).T, upper=False)
+                    yy = Linv @ (cand - mu).T
                     ok = (yy * yy).sum(dim=0) <= r * r
                 else:
                     z = torch.randn((m, dim), generator=gen, **f64)
