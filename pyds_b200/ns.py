@@ -257,7 +257,7 @@ class DEUS:
         live_p = owner.efp_device(live, p_t, w_t)
         sync(); t_initial = time.time() - t_start
         n_evals = n_live
-        iter_times, it = [], 0
+        iter_times, eval_times, it = [], [], 0
         vol_ball = math.pi ** (dim / 2.0) / math.gamma(dim / 2.0 + 1.0)
         while it < self.max_iterations:
             inside = float((live_p >= self.target).double().mean())
@@ -307,7 +307,9 @@ class DEUS:
                     m = min(max(int(1.5 * (n_rep - have) / max(a_ell if not from_box else a_ell * vol_ell / vol_box, 1e-3)), 4096), 1 << 20)
                 first = False
             cand = lo + torch.cat(chunks)[:n_rep] * span
+            sync(); t_e = time.time()
             cand_p = owner.efp_device(cand, p_t, w_t)
+            sync(); eval_times.append(time.time() - t_e)
             n_evals += n_rep
             # ---- live-set update: the n_live best of (live, candidates that beat the worst) ----
             allp = torch.cat([live_p, cand_p])
@@ -321,6 +323,8 @@ class DEUS:
             "live_points": live.cpu().numpy(), "live_efp": live_p.cpu().numpy(), "iterations": it, "evaluations": n_evals,
             "inside_fraction": float((live_p >= self.target).double().mean()), "seconds": time.time() - t_start,
             "seconds_per_iteration": float(np.mean(iter_times)) if iter_times else 0.0,
+            # of which the evaluation of the proposals (kernel + gather); the rest is the sampler itself
+            "seconds_per_iteration_evaluation": float(np.mean(eval_times)) if eval_times else 0.0,
             "initial_live_set_seconds": t_initial,
         }
         return self.result
