@@ -2,8 +2,12 @@
 usage: ncu_traffic.py rep kernel_name n_d n_theta "source note" """
 import csv
 import json
+import os
 import subprocess
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import source_hash  # noqa: E402
 
 rep, kernel, n_d, n_t, note = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -23,6 +27,8 @@ out = {"source": note, "kernel": kernel, "n_d": n_d, "n_theta": n_t,
        "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
        "shared_wavefronts_pct": val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
        "registers_per_thread": int(val("launch__registers_per_thread")),
-       "warp_instructions": int(val("smsp__inst_executed.sum"))}
+       "warp_instructions": int(val("smsp__inst_executed.sum")),
+       # bench.py quotes these figures only while the kernel sources hash to this value
+       "source_sha256": source_hash()}
 json.dump(out, open("profiles/traffic_feas_kernel.json", "w"), indent=1)
 print(out)
