@@ -1144,7 +1144,11 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
     int* wsi = nullptr;
     long long* act = nullptr;                    // two active lists (per-scenario mode)
     const size_t want[3] = {nd_dbl * sizeof(double), nd_int * sizeof(int), compact ? 2 * (size_t)G * sizeof(long long) : 0};
-    constexpr size_t KEEP = 64u << 20;           // cache workspaces up to 64 MiB each in the model
+    // Workspaces are kept in the model between calls (the nested-sampling loop calls with a few hundred groups thousands
+    // of times; a per-scenario batch of 1e7 groups needs 9 GB, and allocating / releasing that much per call costs
+    // hundreds of milliseconds on a busy allocator -- 0.05 s of kernels measured at 0.49 s).  Up to 16 GiB each; released
+    // by pydsb_model_destroy.
+    constexpr size_t KEEP = (size_t)16 << 30;
     void* got[3] = {nullptr, nullptr, nullptr};
     bool owned[3] = {false, false, false};       // allocated for this call only
     for (int i = 0; i < 3; ++i) {

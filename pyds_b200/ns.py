@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import heapq
 import math
+import os
 import time
 
 import numpy as np
@@ -217,6 +218,7 @@ class DEUS:
             "live_points": live, "live_efp": live_p, "iterations": it, "evaluations": n_evals,
             "inside_fraction": float(np.mean(live_p >= self.target)), "seconds": time.time() - t_start,
             "seconds_per_iteration": float(np.mean(iter_times)) if iter_times else 0.0,
+            "iteration_seconds": list(iter_times),
             "initial_live_set_seconds": t_initial,
             "samples": np.vstack([h[0] for h in history]), "samples_efp": np.concatenate([h[1] for h in history]),
         }
@@ -264,6 +266,10 @@ class DEUS:
             if inside >= self.inside_fraction:
                 break
             sync(); t0 = time.time()
+            trace = [] if os.environ.get("PYDSB_NS_TRACE") else None
+            def mark(name):
+                if trace is not None:
+                    sync(); trace.append((name, time.time()))
             worst = float(live_p.min())
             for lv, nl, nr in self.schedule:
                 if worst >= lv:
@@ -280,6 +286,7 @@ class DEUS:
             L, Linv = torch.tensor(L_h, **f64), torch.tensor(np.linalg.inv(L_h), **f64)
             y = Linv @ xc.T
             r = float((y * y).sum(dim=0).max().sqrt()) * (1.0 + enlarge)
+            mark("ellipsoid")
             ext = r * (L * L).sum(dim=1).sqrt()
             blo, bhi = torch.clamp(mu - ext, min=0.0), torch.clamp(mu + ext, max=1.0)
             vol_box = float(torch.clamp(bhi - blo, min=0.0).prod())
@@ -307,6 +314,7 @@ class DEUS:
                     m = min(max(int(1.5 * (n_rep - have) / max(a_ell if not from_box else a_ell * vol_ell / vol_box, 1e-3)), 4096), 1 << 20)
                 first = False
             cand = lo + torch.cat(chunks)[:n_rep] * span
+            mark("proposals")
             sync(); t_e = time.time()
             cand_p = owner.efp_device(cand, p_t, w_t)
             sync(); eval_times.append(time.time() - t_e)
@@ -317,12 +325,16 @@ class DEUS:
             keep = torch.sort(allp, descending=True, stable=True).indices[:n_live]
             keep = torch.sort(keep).values                    # keep the surviving live points in their slots' order
             live, live_p = allx[keep], allp[keep]
+            mark("update")
+            if trace:
+                print("ns trace:", [(n, round(1e3 * (t - (trace[i - 1][1] if i else t0)), 2)) for i, (n, t) in enumerate(trace)], flush=True)
             sync(); iter_times.append(time.time() - t0)
             it += 1
         self.result = {
             "live_points": live.cpu().numpy(), "live_efp": live_p.cpu().numpy(), "iterations": it, "evaluations": n_evals,
             "inside_fraction": float((live_p >= self.target).double().mean()), "seconds": time.time() - t_start,
             "seconds_per_iteration": float(np.mean(iter_times)) if iter_times else 0.0,
+            "iteration_seconds": list(iter_times),
             # of which the evaluation of the proposals (kernel + gather); the rest is the sampler itself
             "seconds_per_iteration_evaluation": float(np.mean(eval_times)) if eval_times else 0.0,
             "initial_live_set_seconds": t_initial,

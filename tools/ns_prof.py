@@ -1,4 +1,4 @@
-"""Where a device-resident nested-sampling iteration of config C5 spends its time (development tool)."""
+"""Where a device-resident nested-sampling iteration of config C5 spends its time (development tool; PYDSB_NS_TRACE=1)."""
 import sys, time, os
 sys.path.insert(0, '.')
 import numpy as np, torch
@@ -17,9 +17,5 @@ def form(n_live, th, w, its, dev):
                        "algorithms": {"sampling": {"settings": {"prng_seed": 1989, "device": dev, "stop_criteria": [{"max_iterations": its}]}}}}}
 ns.DEUS(form(2000, th5[:2000], np.full(2000, 1 / 2000), 2, "cuda:0")).solve()
 for n_theta in (100000, 1000):
-    r = ns.DEUS(form(100000, th5[:n_theta], np.full(n_theta, 1 / n_theta), 5, "cuda:0")).solve()
+    r = ns.DEUS(form(100000, th5[:n_theta], np.full(n_theta, 1 / n_theta), 4, "cuda:0")).solve()
     print(n_theta, {k: r[k] for k in ("seconds_per_iteration", "seconds_per_iteration_evaluation", "initial_live_set_seconds")}, flush=True)
-import cProfile, pstats
-d = ns.DEUS(form(100000, th5[:1000], np.full(1000, 1e-3), 5, "cuda:0"))
-pr = cProfile.Profile(); pr.enable(); d.solve(); pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(12)
