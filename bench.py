@@ -76,15 +76,17 @@ def make_inputs(n_d, n_t, rank=0, rows=None):
     return d, theta, w
 
 
+FEAS_KERNEL_SOURCES = ["chain_shapes.h", "common.cuh", "feas_kernel.cuh", "poly_chain.cuh", "tape_vm.cuh", "xvm_ops.cuh"]
+
+
 def source_hash():
     """sha256 over the kernel sources: the committed ncu figures (profiles/traffic_feas_kernel.json) are only quoted
     while the kernels they were captured from are the ones that run."""
     h = hashlib.sha256()
     src = os.path.join(ROOT, "pyds_b200", "csrc")
-    for name in sorted(os.listdir(src)):
-        if name.endswith((".cu", ".cuh", ".h")):
-            h.update(name.encode())
-            h.update(open(os.path.join(src, name), "rb").read())
+    for name in FEAS_KERNEL_SOURCES:                   # device code of feas_kernel (the host side may change freely)
+        h.update(name.encode())
+        h.update(open(os.path.join(src, name), "rb").read())
     return h.hexdigest()
 
 
