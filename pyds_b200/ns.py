@@ -11,6 +11,11 @@ restated from memory; what is exact is the contract: the constraint function is 
 ``g(d, p) -> list of (n_p, n_g)`` and the probability of feasibility is
 ``sum_j w_j 1[all_k g_jk >= 0]``.  If the function's owner offers ``efp(d, p, w)`` (pyds_b200's
 managers do), that fused GPU path is used instead and g is never materialised.
+
+``parameters_best_estimate`` (reference run_twostage.py:145-150) is read and kept as ``p_best`` but NOT used: DEUS
+starts with a deterministic phase that scores points by the worst constraint value at the nominal parameters before it
+switches to the probabilistic phase; this driver samples the probabilistic phase from the first iteration (the
+feasibility probability over the whole theta set is cheap here), so the nominal point never enters.
 """
 from __future__ import annotations
 
