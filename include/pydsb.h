@@ -81,7 +81,9 @@ int pydsb_model_destroy(void* handle);
 /* Host-only half of pydsb_model_create (needs no CUDA device): assembles the blob's tapes into the
  * pre-decoded per-scenario program feas_kernel interprets (csrc/assembler.h, csrc/feas_kernel.cuh) and copies up
  * to `cap` 32-bit words of it into `words`; *n_words = the full length.  info = { scenarios per thread,
- * register-file units, shared-memory bytes per CTA, program length in 16-byte words }.  What it replaces in
+ * register-file units, shared-memory bytes per CTA, program length in 16-byte words, blocks of the fused chain (0: the
+ * element loop is interpreted), the two shape words of the chain, 1 when that shape has a compiled instantiation };
+ * info[8 ...] (optional, n_info > 8): the chain descriptor word by word (csrc/poly_chain.cuh).  What it replaces in
  * the reference: the GAMS model file Pyomo writes for every solve (reference pyds/solver.py:50-55). */
 int pydsb_assemble(const void* blob, size_t nbytes, uint32_t* words, size_t cap, size_t* n_words, long long* info,
                    int n_info);

@@ -394,6 +394,36 @@ def assemble(blob: bytes):
                           "chain_shape_sq", "chain_shape_registered"), (int(v) for v in info)))
 
 
+def chain_descriptor(blob: bytes):
+    """Host-only: the descriptor of the fused chain of ``blob``'s feasibility program (csrc/poly_chain.cuh, ChainDesc) as
+    a dict of byte offsets into a thread's register file, or None when the element loop is interpreted."""
+    L = load()
+    n = ctypes.c_size_t()
+    N = 8 + 130
+    info = (ctypes.c_longlong * N)()
+    _check(L.pydsb_assemble(blob, len(blob), None, 0, ctypes.byref(n), info, N))
+    if int(info[4]) == 0:
+        return None
+    w = [int(v) for v in info[8:]]
+    head = dict(zip(("nb", "nq", "max_it", "pre_end", "g_begin", "g_end", "n_par", "ng"), w[:8]))
+    blocks = []
+    for b in range(3):
+        o = 8 + 14 * b
+        blocks.append(dict(x_off=w[o], flops=w[o + 1], kind=w[o + 2], minv_off=w[o + 3],
+                           terms=[(w[o + 4 + 2 * k], w[o + 5 + 2 * k]) for k in range(3)],      # (n_off, meta)
+                           x0_off=w[o + 10], x0_const=w[o + 11], xe_off=w[o + 12]))
+    quads = []
+    for q in range(4):
+        o = 8 + 42 + 8 * q
+        quads.append(dict(q_off=w[o], n_off=w[o + 1], meta=w[o + 2], q0_off=w[o + 3], q0_const=w[o + 4]))
+    o = 8 + 42 + 32
+    head.update(blocks=blocks[:head["nb"]], quads=quads[:head["nq"]], pre_run0=w[o], g_run0=w[o + 1],
+                par_off=w[o + 4:o + 4 + head["n_par"]], g_off=w[o + 20:o + 20 + head["ng"]])
+    nz = w[o + 45]
+    head.update(z_off=w[o + 28:o + 28 + nz], z_const=[(w[o + 44] >> i) & 1 for i in range(nz)])
+    return head
+
+
 def dfma_peak(device: int = 0, repeats: int = 5):
     """Measured FP64 FMA throughput (TFLOP/s, best of ``repeats``) and the kernel time in ms."""
     t, ms = ctypes.c_double(), ctypes.c_double()

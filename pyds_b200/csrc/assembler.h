@@ -6,6 +6,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -35,8 +36,8 @@ struct AsmInput {
     const ExecImage* img;                      // resolved per-block offsets: blk_x_o, blk_f_o, blk_j_o, blk_jmask
     bool allow_chain = false;                  // fuse the element loop into one X_PCHAIN when the model has that shape
     // reference tables (chain programs resolve them into the descriptor: no table walking in the kernel)
-    const uint16_t *x0_refs = nullptr, *q0_refs = nullptr, *par_refs = nullptr, *g_refs = nullptr;
-    int n_par = 0, ng = 0, xe_slot = 0;
+    const uint16_t *x0_refs = nullptr, *q0_refs = nullptr, *par_refs = nullptr, *g_refs = nullptr, *z_refs = nullptr;
+    int n_par = 0, ng = 0, xe_slot = 0, nz = 0;
 };
 
 class Assembler {
@@ -45,6 +46,8 @@ public:
     std::string err;
     int chain_nb = 0;                          // blocks of the fused chain (0: the element loop is interpreted)
     ChainDesc chain{};                         // its descriptor (poly_chain.cuh): what the kernel reads from the constant bank
+    int chain_units = 0;                       // register-file units a chain program touches after compaction (0: not compacted)
+    bool compact = true;                       // renumber the units of a chain program by liveness (compact_units)
 
     int pc() const { return (int)(words.size() / 4); }      // uint4 index of the next instruction
 
@@ -66,7 +69,7 @@ public:
             for (int c = 0; c < in.nce; ++c) {
                 const uint32_t dst = (uint32_t)(in.ctrl_slot + c) * US * (uint32_t)in.spt;
                 // chain programs: every scalar op loads its a / b operands before it looks at the opcode -- keep them valid
-                if (chain_mode_) emit(X_LDCTRL, dst, 0u, 0u, 0u, 0u, (uint32_t)c);
+                if (chain_mode_) { emit(X_LDCTRL, dst, 0u, 0u, 0u, 0u, (uint32_t)c); nread_.push_back(0); }
                 else emit(X_LDCTRL, dst, (uint32_t)c);
             }
             for (int i = 0; i < in.n_elem; ++i)
@@ -76,13 +79,20 @@ public:
         if (chain_mode_) {
             // scalar ops | PCHAIN | XEND | scalar ops | END  (the shape feas_kernel<.., CHAIN> relies on)
             if (invariant && !ctrl_and_elem()) return false;
+            std::vector<uint32_t> pre, post;
+            pre.swap(words);
+            for (int i = 0; i < in.n_g; ++i)
+                if (!scalar_op(in.g[i])) return false;
+            post.swap(words);
+            if (compact && !compact_units(in, pre, post)) return false;
+            words.swap(pre);
             this->chain.pre_end = (unsigned)pc();
+            chain_words(chain);
             words.insert(words.end(), chain.begin(), chain.end());
             chain_nb = nb;
             emit(X_XEND);
             this->chain.g_begin = (unsigned)pc();
-            for (int i = 0; i < in.n_g; ++i)
-                if (!scalar_op(in.g[i])) return false;
+            words.insert(words.end(), post.begin(), post.end());
             this->chain.g_end = (unsigned)pc();
             emit(X_END);
             this->chain.pre_run0 = fmag_runs(0, this->chain.pre_end);
@@ -240,6 +250,7 @@ public:
 private:
     const AsmInput* in_ = nullptr;
     bool chain_mode_ = false;                  // chain programs: FMAG scalar ops, SPT-wide constant pool
+    std::vector<unsigned char> nread_;         // chain programs: operand fields (a, b, c) every scalar op really reads
 
     // Scalar section [begin, end) of a chain program (every op two uint4 long): the FMAG ops that directly follow another
     // op are counted into that op's w1.w -- the kernel runs them in a loop without looking at opcodes.  Returns the
@@ -409,7 +420,6 @@ private:
                 ev.push_back(v);
             }
         }
-        std::vector<uint32_t> blkw, quadw;
         ChainDesc& cd = chain;
         cd = ChainDesc{};
         if (!in.par_refs || !in.g_refs || in.n_par > 16 || in.ng > 8) return false;
@@ -418,6 +428,13 @@ private:
         for (int k = 0; k < in.ng; ++k) {
             if (in.g_refs[k] & (REF_CONST | REF_WIDE)) return false;  // a constant constraint: leave it to the generic path
             cd.g_off[k] = (uint32_t)(in.g_refs[k] & REF_MASK) * usp;
+        }
+        if (in.nz > 16 || (in.nz > 0 && !in.z_refs)) return false;
+        cd.nz = (unsigned)in.nz;
+        for (int zi = 0; zi < in.nz; ++zi) {
+            uint32_t is_const = 0;
+            if (!source_ref(in, in.z_refs[zi], cd.z_off[zi], is_const)) return false;
+            cd.z_const |= is_const << zi;
         }
         int pos = 0, scratch = g.x_slot;                               // units [x_slot, n_units) are dead during the loop
         for (int b = 0; b < in.n_blocks; ++b) {
@@ -445,7 +462,6 @@ private:
             }
             const uint32_t w[12] = {g.blk_x_o[b][0][0], flops, kind, minv, t[0].n_off, t[0].meta(), t[1].n_off, t[1].meta(),
                                     t[2].n_off, t[2].meta(), 0u, 0u};
-            blkw.insert(blkw.end(), w, w + 12);
             ChainBlockD& bd = cd.blk[b];
             bd.x_off = w[0]; bd.flops = flops; bd.kind = kind; bd.minv_off = minv;
             for (int k = 0; k < 3; ++k) { bd.c[k].n_off = t[k].n_off; bd.c[k].meta = t[k].meta(); }
@@ -472,7 +488,6 @@ private:
                 }
                 if (++nq > CHAIN_MAXQ) return false;
                 const uint32_t w[4] = {(uint32_t)(in.qe_slot + q) * usp, t.n_off, t.meta(), 0u};
-                quadw.insert(quadw.end(), w, w + 4);
                 ChainQuadD& qd = cd.quad[nq - 1];
                 qd.q_off = w[0]; qd.n_off = t.n_off; qd.meta = t.meta();
                 if (!in.q0_refs || !source_ref(in, in.q0_refs[q], qd.q0_off, qd.q0_const)) return false;
@@ -481,12 +496,160 @@ private:
                 if (!used[i]) return false;
             if (g.max_it < 1 || g.max_it > 0xFFFF) return false;
             cd.nb = (unsigned)in.n_blocks; cd.nq = (unsigned)nq; cd.max_it = (unsigned)g.max_it;
-            const uint32_t head[8] = {X_PCHAIN, (uint32_t)in.n_blocks | ((uint32_t)nq << 8), (uint32_t)g.max_it, 0u, 0u, 0u, 0u, 0u};
-            out.assign(head, head + 8);
         }
-        out.insert(out.end(), blkw.begin(), blkw.end());
-        out.insert(out.end(), quadw.begin(), quadw.end());
         nb_out = in.n_blocks;
+        return true;
+    }
+
+    // The PCHAIN instruction (head, 12 words per block, 4 per quadrature) as the descriptor stands
+    void chain_words(std::vector<uint32_t>& out) const
+    {
+        const ChainDesc& cd = chain;
+        const uint32_t head[8] = {X_PCHAIN, cd.nb | (cd.nq << 8), cd.max_it, 0u, 0u, 0u, 0u, 0u};
+        out.assign(head, head + 8);
+        for (unsigned b = 0; b < cd.nb; ++b) {
+            const ChainBlockD& bd = cd.blk[b];
+            const uint32_t w[12] = {bd.x_off, bd.flops, bd.kind, bd.minv_off, bd.c[0].n_off, bd.c[0].meta, bd.c[1].n_off, bd.c[1].meta,
+                                    bd.c[2].n_off, bd.c[2].meta, 0u, 0u};
+            out.insert(out.end(), w, w + 12);
+        }
+        for (unsigned q = 0; q < cd.nq; ++q) {
+            const uint32_t w[4] = {cd.quad[q].q_off, cd.quad[q].n_off, cd.quad[q].meta, 0u};
+            out.insert(out.end(), w, w + 4);
+        }
+    }
+
+    // Liveness-based renumbering of the register-file units of a chain program.  The layout the lowering chose
+    // (pyds_b200/tape.py) serves the interpreted element loop: a persistent narrow region plus three units per wide value.
+    // A chain program is straight-line code around ONE instruction that keeps the states in registers, so a unit is live
+    // from the op that writes a value to the last op that reads it and interval colouring is exact: parameters (written at
+    // the tile start), prologue temporaries, coefficients, the scratch of a constant-decay block (9 consecutive units, live
+    // inside PCHAIN only), end values and g temporaries share units.  Times: op i reads at 2i and writes at 2i + 1, so an
+    // op may overwrite an operand it reads last.  PCHAIN stores its end values after the element loop: they may take the
+    // units of the scratch (last read in the loop), not those of its inputs.
+    bool compact_units(const AsmInput& in, std::vector<uint32_t>& pre, std::vector<uint32_t>& post)
+    {
+        const uint32_t usp = US * (uint32_t)in.spt;
+        const int n_pre = (int)(pre.size() / 8), n_post = (int)(post.size() / 8);
+        if ((int)nread_.size() != n_pre + n_post) return fail("internal: operand counts of the scalar ops");
+        const int t_chain = n_pre, t_end = n_pre + 1 + n_post;         // op indices of PCHAIN and END (parameters: op -1)
+        struct Val { int start, end, unit; };
+        std::vector<Val> vals;
+        std::vector<int> cur((size_t)in.n_units + 16, -1);             // value that currently sits in an (old) unit
+        struct Patch { uint32_t* where; int val; };
+        std::vector<Patch> patches;
+        auto old_unit = [&](uint32_t off) -> int { return (int)(off / usp); };
+        auto def = [&](uint32_t* where, int t) {
+            const int u = old_unit(*where);
+            if (u < 0 || u >= (int)cur.size()) return false;
+            vals.push_back(Val{2 * t + 1, 2 * t + 1, -1});
+            cur[(size_t)u] = (int)vals.size() - 1;
+            patches.push_back(Patch{where, cur[(size_t)u]});
+            return true;
+        };
+        auto use = [&](uint32_t* where, int t, int late) {
+            const int u = old_unit(*where);
+            if (u < 0 || u >= (int)cur.size()) return false;
+            if (cur[(size_t)u] < 0) {                                  // read before any write: lives from the tile start
+                vals.push_back(Val{-1, -1, -1});
+                cur[(size_t)u] = (int)vals.size() - 1;
+            }
+            Val& v = vals[(size_t)cur[(size_t)u]];
+            v.end = std::max(v.end, 2 * t + late);
+            patches.push_back(Patch{where, cur[(size_t)u]});
+            return true;
+        };
+        ChainDesc& cd = chain;
+        bool ok = true;
+        for (unsigned i = 0; i < cd.n_par; ++i) ok = ok && def(&cd.par_off[i], -1);
+        // control values read through the descriptor (initial / fixed values): by LDCTRL before the chain when every
+        // element sees the same entry, else by the chain itself (any entry, any element)
+        auto z_use = [&](unsigned zi, int t, int late) {
+            if (zi < cd.nz && !((cd.z_const >> zi) & 1u)) ok = ok && use(&cd.z_off[zi], t, late);
+        };
+        auto scalar_section = [&](std::vector<uint32_t>& w, int n, int t0, int op0) {
+            for (int i = 0; i < n && ok; ++i) {
+                uint32_t* o = &w[(size_t)i * 8];
+                if (o[0] == (uint32_t)X_LDCTRL) z_use(in.cmap[o[6]], t0 + i, 0);
+                const unsigned fl = o[5];
+                const int nr = nread_[(size_t)(op0 + i)];
+                for (int k = 0; k < 3; ++k) {
+                    uint32_t* f = &o[2 + k];
+                    if (k < nr) { if (!((fl >> k) & 1u)) ok = ok && use(f, t0 + i, 0); }
+                    else if (!((fl >> k) & 1u)) *f = 0u;               // never read for its value: any valid address
+                }
+                ok = ok && def(&o[1], t0 + i);
+            }
+        };
+        scalar_section(pre, n_pre, 0, 0);
+        bool chain_reads_ctrl = false;
+        for (unsigned b = 0; b < cd.nb; ++b)
+            for (int k = 0; k < 3; ++k) chain_reads_ctrl = chain_reads_ctrl || (cd.blk[b].c[k].meta & CT_HAS_CTRL);
+        for (unsigned q = 0; q < cd.nq; ++q) chain_reads_ctrl = chain_reads_ctrl || (cd.quad[q].meta & CT_HAS_CTRL);
+        for (int e = 0; chain_reads_ctrl && e < in.nfe; ++e)
+            for (int c = 0; c < in.nce; ++c) z_use(in.cmap[e * in.nce + c], t_chain, 1);
+        // PCHAIN: inputs (late = 1: still held while the outputs are written), outputs; the scratch further down
+        for (unsigned b = 0; b < cd.nb && ok; ++b) {
+            ChainBlockD& bd = cd.blk[b];
+            for (int k = 0; k < 3; ++k)
+                if ((bd.c[k].meta & CT_PRESENT) && (bd.c[k].meta & CT_HAS_N)) ok = ok && use(&bd.c[k].n_off, t_chain, 1);
+            if (!bd.x0_const) ok = ok && use(&bd.x0_off, t_chain, 1);
+        }
+        for (unsigned q = 0; q < cd.nq && ok; ++q) {
+            ChainQuadD& qd = cd.quad[q];
+            if ((qd.meta & CT_PRESENT) && (qd.meta & CT_HAS_N)) ok = ok && use(&qd.n_off, t_chain, 1);
+            if (!qd.q0_const) ok = ok && use(&qd.q0_off, t_chain, 1);
+        }
+        for (unsigned b = 0; b < cd.nb && ok; ++b) ok = ok && def(&cd.blk[b].xe_off, t_chain);
+        for (unsigned q = 0; q < cd.nq && ok; ++q) ok = ok && def(&cd.quad[q].q_off, t_chain);
+        scalar_section(post, n_post, t_chain + 1, n_pre);
+        for (unsigned k = 0; k < cd.ng && ok; ++k) ok = ok && use(&cd.g_off[k], t_end, 0);
+        if (!ok) return fail("internal: unit out of range while compacting");
+
+        // interval colouring: values that are live when PCHAIN starts first (they all overlap there), then the scratch blocks
+        // right above them, then everything else in order of its start -- lowest unit whose intervals do not overlap
+        std::vector<std::vector<std::pair<int, int>>> busy;
+        auto fits = [&](int u, int s, int e) {
+            if (u >= (int)busy.size()) return true;
+            for (const auto& iv : busy[(size_t)u])
+                if (s <= iv.second && iv.first <= e) return false;
+            return true;
+        };
+        auto take = [&](int u, int s, int e) {
+            if (u >= (int)busy.size()) busy.resize((size_t)u + 1);
+            busy[(size_t)u].push_back(std::make_pair(s, e));
+        };
+        auto place = [&](Val& v) {
+            int u = 0;
+            while (!fits(u, v.start, v.end)) ++u;
+            take(u, v.start, v.end);
+            v.unit = u;
+        };
+        const int tc0 = 2 * t_chain, tc1 = 2 * t_chain + 1;
+        std::vector<int> order;
+        for (size_t i = 0; i < vals.size(); ++i)
+            if (vals[i].start <= tc0 && vals[i].end >= tc0) order.push_back((int)i);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return vals[(size_t)a].start < vals[(size_t)b].start; });
+        for (int i : order) place(vals[(size_t)i]);
+        for (unsigned b = 0; b < cd.nb; ++b) {
+            if (cd.blk[b].kind != CHAIN_LINCONST) continue;
+            int u = 0;
+            for (;; ++u) {
+                bool free9 = true;
+                for (int k = 0; k < 9 && free9; ++k) free9 = fits(u + k, tc0, tc0);
+                if (free9) break;
+            }
+            for (int k = 0; k < 9; ++k) take(u + k, tc0, tc0);
+            cd.blk[b].minv_off = (uint32_t)u * usp;
+        }
+        order.clear();
+        for (size_t i = 0; i < vals.size(); ++i)
+            if (vals[i].unit < 0) order.push_back((int)i);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return vals[(size_t)a].start < vals[(size_t)b].start; });
+        for (int i : order) place(vals[(size_t)i]);
+        for (const Patch& p : patches) *p.where = (uint32_t)vals[(size_t)p.val].unit * usp;
+        chain_units = (int)busy.size();
+        if (chain_units > in.n_units) return fail("internal: compaction grew the register file");
         return true;
     }
 
@@ -614,6 +777,7 @@ private:
             if (fmag) {
                 const uint32_t f = (a.cst ? 1u : 0u) | (b.cst ? 2u : 0u) | (c.cst ? 4u : 0u) | (neg_a ? 8u : 0u) | (neg_c ? 16u : 0u);
                 emit(X_FMAG, slot_off(refs[0]), a.off, b.off, c.off, f, 0u);
+                nread_.push_back(3);
                 return true;
             }
         }
@@ -622,6 +786,7 @@ private:
             if (flags & 1u) flags |= 2u;
         }
         emit((uint32_t)map[op], slot_off(refs[0]), off[0], off[1], off[2], flags, is_cold(op) ? op : 0u);
+        if (chain_mode_) nread_.push_back((unsigned char)(n == 1 ? 2 : n));
         return true;
     }
 

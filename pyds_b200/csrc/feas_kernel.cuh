@@ -172,7 +172,7 @@ template <int MAXNS, int SPT, bool TRAJ = false, bool PACK = false, int CHAIN = 
 #ifndef PYDSB_CHAIN_CTAS
 #define PYDSB_CHAIN_CTAS 3
 #endif
-__global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CTAS : 3) : (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))))
+__global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 && SB != 0ull ? PYDSB_CHAIN_CTAS : 3) : (MAXNS <= 1 ? 5 : (MAXNS == 2 ? 4 : 2))))
     feas_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ LaunchArgs la)
 {
     typedef Vec<SPT> VecT;
@@ -562,7 +562,12 @@ __global__ void __launch_bounds__(BLOCK, (SPT == 2 ? (CHAIN > 0 ? PYDSB_CHAIN_CT
         // value of control c on finite element el for the thread's scenario s (z_mode: where the controls come from)
         auto ctrl_ld = [&](int el, int c, int s) -> double {
             const int zi = tab_cmap[el * img.nce + c];
-            if (la.z_mode == 0 || tab_zfix[zi]) return ref_ld(tab_z[zi], s);
+            if (la.z_mode == 0 || tab_zfix[zi]) {
+                // chain programs: the assembler renumbers the units, the reference table of the lowering does not apply
+                if constexpr (CHAIN > 0)
+                    return *reinterpret_cast<const double*>((((c_chain.z_const >> zi) & 1u) ? cz : base) + c_chain.z_off[zi] + s * 8);
+                else return ref_ld(tab_z[zi], s);
+            }
             if (la.z_mode == 1) return __ldg(la.z + zi);
             if (la.z_mode == 2) return __ldg(la.z + id_of(s) * img.nz + zi);
             return __ldg(la.z + (id_of(s) * la.n_t + jj_[s]) * img.nz + zi);

@@ -67,6 +67,8 @@ struct ChainDesc {
     unsigned pre_run0, g_run0, pad2, pad3;     // FMAG ops at the head of either scalar section (later runs: w1.w of the op before)
     unsigned par_off[16];                      // slot of every parameter (d first, then theta)
     unsigned g_off[8];                         // slot of every constraint value
+    unsigned z_off[16];                        // where the initial / fixed value of control value zi lives ...
+    unsigned z_const, nz, pad4, pad5;          // ... bit zi of z_const: in the constant pool, else a slot
 };
 __constant__ ChainDesc c_chain;
 

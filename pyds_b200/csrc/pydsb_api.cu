@@ -61,6 +61,8 @@ struct Program {
     std::vector<uint32_t> xprog;        // the assembled program (program 0: whole scenario; program 1: tape segments)
     std::vector<uint32_t> xprog_interp; // program 0 with the element loop interpreted (pydsb_state_solve), when xprog is fused
     int chain_nb = 0;                   // blocks of the fused element loop (X_PCHAIN) in xprog; 0: none
+    int chain_units = 0;                // register-file units xprog touches after the assembler's compaction (0: img.n_units)
+    int chain_smem_bytes = 0;           // shared memory per CTA of the fused program (xprog_interp needs img.smem_bytes)
     ChainDesc chain{};                  // its descriptor, copied to the constant bank (c_chain) before a launch
     unsigned long long shape_sb = 0;    // compile-time shape words of the chain (poly_chain.cuh, chain_shape_bits)
     unsigned shape_sq = 0;
@@ -474,13 +476,24 @@ int build_program(const Sections& secs, int mode, Program& P, bool upload = true
             (int)find(secs, "RPAR")->count < g.d_dim + g.p_dim || (int)find(secs, "RG__")->count < g.ng)
             return fail(PYDSB_ERR_INVALID, "reference table shorter than its dimension");
         in.n_par = g.d_dim + g.p_dim; in.ng = g.ng; in.xe_slot = g.xe_slot;
+        in.nz = g.nz;
+        if (g.nz > 0) {
+            const Section* rzs = find(secs, "RZ__");
+            if (!rzs || (int)rzs->count < g.nz) return fail(PYDSB_ERR_INVALID, "reference table shorter than its dimension");
+            in.z_refs = reinterpret_cast<const uint16_t*>(rzs->data);
+        }
         // HEAD[15] bit 0 (DaeModel(fused_chain=False)) or PYDSB_NO_CHAIN=1: keep the element loop interpreted
         const char* no_chain = getenv("PYDSB_NO_CHAIN");
         in.allow_chain = rchain || (!(H[15] & 1u) && !(no_chain && atoi(no_chain) != 0));
         Assembler as;
+        // PYDSB_NO_COMPACT=1: keep the lowering's unit numbers (A/B switch); the sensitivity chain addresses its extra rows
+        // behind n_units and keeps them too
+        const char* no_compact = getenv("PYDSB_NO_COMPACT");
+        as.compact = !rchain && !(no_compact && atoi(no_compact) != 0);
         if (!as.assemble(in)) return fail(PYDSB_ERR_UNSUPPORTED, "assembler: " + as.err);
         P.xprog.swap(as.words);
         P.chain_nb = as.chain_nb;
+        P.chain_units = as.chain_nb > 0 ? as.chain_units : 0;
         if (rchain && P.xprog.size() / 4 > 2 * (size_t)MAX_PROG_R) { P.present = false; P.chain_nb = 0; return PYDSB_OK; }
         if (rchain) {
             // the sensitivity chain needs the fused shape (and what recourse_chain.cuh supports of it): otherwise this
@@ -624,6 +637,7 @@ int build_program(const Sections& secs, int mode, Program& P, bool upload = true
     int units = g.n_units + (g.zero_off ? 1 : 0);
     if (sens) units += recourse_sens_rows(g.ns, g.nq, g.ng) * g.nz;     // Sx, Sq (later Dc + one row) of sens_kernel
     if (rchain) units += (g.ng + 1) * g.nz;                             // Dc + one row (the sensitivities live in registers)
+    P.chain_smem_bytes = (P.chain_nb > 0 && P.chain_units > 0) ? o + P.chain_units * g.spt * BLOCK * 8 : 0;
     o += units * g.spt * BLOCK * 8;
     g.smem_bytes = o;
 
@@ -756,9 +770,10 @@ int pydsb_model_create(const void* blob, size_t nbytes, int device, void** handl
             }
     }
     FeasFn fn = feas_for(image_maxns(g), g.spt, &m->prog[0]);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
+    const int feas_smem = m->prog[0].chain_smem_bytes ? m->prog[0].chain_smem_bytes : g.smem_bytes;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, feas_smem);
     int bps = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, BLOCK, g.smem_bytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, BLOCK, feas_smem);
     cudaFuncAttributes fa{};
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fn);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
@@ -880,9 +895,13 @@ int pydsb_assemble(const void* blob, size_t nbytes, uint32_t* words, size_t cap,
     if (words)
         for (size_t i = 0; i < P.xprog.size() && i < cap; ++i) words[i] = P.xprog[i];
     const ExecImage& g = P.img;
-    const long long v[8] = {g.spt, g.n_units + (g.zero_off ? 1 : 0), g.smem_bytes, g.n_prog, P.chain_nb,
+    const long long v[8] = {g.spt, P.chain_units ? P.chain_units : g.n_units + (g.zero_off ? 1 : 0),
+                            P.chain_smem_bytes ? P.chain_smem_bytes : g.smem_bytes, g.n_prog, P.chain_nb,
                             (long long)P.shape_sb, (long long)P.shape_sq, chain_kernel_for(P, g.spt) ? 1 : 0};
     for (int i = 0; info && i < n_info && i < 8; ++i) info[i] = v[i];
+    // info[8 ...]: the chain descriptor, word by word (ChainDesc, poly_chain.cuh) -- inspection and the CPU tests
+    const uint32_t* cdw = reinterpret_cast<const uint32_t*>(&P.chain);
+    for (int i = 8; info && i < n_info && i < 8 + (int)(sizeof(ChainDesc) / 4); ++i) info[i] = P.chain_nb > 0 ? cdw[i - 8] : 0;
     return PYDSB_OK;
 }
 
@@ -977,13 +996,14 @@ int eval_impl(void* handle, const double* d, long long n_d, const double* theta,
     const std::vector<uint32_t>& xp = (traj && chain > 0) ? m->prog[0].xprog_interp : m->prog[0].xprog;
     // several models may share one template instantiation: (re)assert this model's smem size and
     // (re)load its program into the constant bank (stream ordered)
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
+    const int smem = (!traj && chain > 0 && m->prog[0].chain_smem_bytes) ? m->prog[0].chain_smem_bytes : img.smem_bytes;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, xp.data(), xp.size() * sizeof(uint32_t), 0, cudaMemcpyHostToDevice, st));
     if (chain > 0 && !traj)
         CUDA_TRY(cudaMemcpyToSymbolAsync(c_chain, &m->prog[0].chain, sizeof(ChainDesc), 0, cudaMemcpyHostToDevice, st));
     {
         ProfScope ps(m, 0, st);
-        fn<<<grid, BLOCK, img.smem_bytes, st>>>(img, la);
+        fn<<<grid, BLOCK, smem, st>>>(img, la);
     }
     CUDA_TRY(cudaGetLastError());
     m->launches += 1;

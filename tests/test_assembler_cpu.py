@@ -91,7 +91,8 @@ def test_fused_chain_program_c3():
     assert (m0["present"], m0["has_n"], m0["p"], m0["src"]) == (1, 1, 2, 0)    # c0 = narrow * cA^2
     assert _meta(cb[1][1])["p"] == 0 and _meta(cb[2][1])["present"] == 0
     unit = 2 * 1024 * 8 // 8                                                   # bytes per unit, two scenarios per thread
-    assert minv // unit >= lm.tapes.layout.x_slot and minv // unit + 9 <= info["units"]     # scratch: dead wide units
+    assert minv % unit == 0 and minv // unit + 9 <= info["units"]              # scratch: nine consecutive units
+    assert info["units"] < lm.tapes.layout.n_units                             # renumbered by liveness (compact_units)
     assert [(_meta(m)["p"], _meta(m)["src"]) for _, _, m in quads] == [(0, 0), (1, 1)]      # u: element constant; cC: k * cB
     # every non-FMAG scalar op carries the length of the FMAG run that follows it
     for sec in (range(0, k), range(k + 2, len(ops) - 1)):
@@ -102,6 +103,91 @@ def test_fused_chain_program_c3():
             else:
                 assert int(ops[i][2][7]) == run
                 run = 0
+
+
+def _run_chain_program(lm, par, monkeypatch, compact):
+    """Execute the scalar dataflow of an assembled chain program in Python (one scenario): the two scalar sections as
+    the kernel runs them, PCHAIN as a black box that reads its inputs, poisons its scratch and then writes values that
+    depend on every input.  Returns the constraint values and the number of units."""
+    import math
+    from pyds_b200.tape import OPS
+    if compact: monkeypatch.delenv("PYDSB_NO_COMPACT", raising=False)
+    else: monkeypatch.setenv("PYDSB_NO_COMPACT", "1")
+    blob, consts = lm.blob, lm.tapes.consts
+    ops, info = capi.assemble(blob)
+    cd = capi.chain_descriptor(blob)
+    spt = info["scenarios_per_thread"]
+    unit, cw = spt * 1024, 8 * spt
+    S = [float("nan")] * info["units"]
+
+    def cst(off):
+        i = off // cw
+        return (1.0, -0.0, 0.0)[i] if i < 3 else float(consts[i - 3])
+
+    def ld(off, is_c):
+        if is_c: return cst(off)
+        assert off % unit == 0 and off // unit < info["units"]
+        return S[off // unit]
+
+    assert len(cd["par_off"]) == len(par) and len(set(cd["par_off"])) == len(par)      # all written at the tile start
+    for o, v in zip(cd["par_off"], par): S[o // unit] = v
+    names = [n for _, n, _ in ops]
+    k = names.index("PCHAIN")
+    assert ops[k][0] == cd["pre_end"] and ops[k + 2][0] == cd["g_begin"] if k + 2 < len(ops) - 1 else True
+
+    def scalar(sec):
+        for _, name, w in sec:
+            w = [int(x) for x in w]
+            fl = w[5]
+            if name == "LDCTRL":                                       # z_mode 0: the control's initial / fixed value
+                zi = int(lm.cmap[0, w[6]])
+                r = ld(cd["z_off"][zi], cd["z_const"][zi])
+            else:
+                a, b = ld(w[2], fl & 1), ld(w[3], fl & 2)              # the kernel loads a and b of every op
+                if name == "FMAG":
+                    c = ld(w[4], fl & 4)
+                    r = (-a if fl & 8 else a) * b + (-c if fl & 16 else c)
+                elif name == "DIV1": r = a / b
+                elif name == "RCP1": r = 1.0 / a
+                elif name == "COLD1": r = {"EXP": math.exp, "LOG": math.log, "SQRT": math.sqrt}[OPS[w[6]]](a)
+                else: raise AssertionError(name)
+            S[w[1] // unit] = r
+
+    scalar(ops[:k])
+    ins = []
+    for b in cd["blocks"]:
+        ins += [ld(o, False) for o, m in b["terms"] if (m & 1) and (m & 2)]
+        ins.append(ld(b["x0_off"], b["x0_const"]))
+    for q in cd["quads"]:
+        if (q["meta"] & 1) and (q["meta"] & 2): ins.append(ld(q["n_off"], False))
+        ins.append(ld(q["q0_off"], q["q0_const"]))
+    if any(m & 4 for b in cd["blocks"] for _, m in b["terms"]) or any(q["meta"] & 4 for q in cd["quads"]):
+        ins += [ld(cd["z_off"][int(zi)], cd["z_const"][int(zi)]) for zi in lm.cmap.ravel()]    # per-element controls
+    assert all(v == v for v in ins)                                    # no input was overwritten before the chain
+    for b in cd["blocks"]:
+        if b["kind"] == 2:
+            for i in range(9): S[b["minv_off"] // unit + i] = float("nan")
+    mix = sum((i + 1) * math.atan(v) for i, v in enumerate(ins))
+    outs = [b["xe_off"] for b in cd["blocks"]] + [q["q_off"] for q in cd["quads"]]
+    assert len(set(outs)) == len(outs)
+    for i, o in enumerate(outs): S[o // unit] = mix + i
+    scalar(ops[k + 2:-1])
+    return [ld(o, False) for o in cd["g_off"]], info["units"]
+
+
+@pytest.mark.parametrize("variant", ["design4", "design6", "twostage"])
+def test_unit_compaction_preserves_the_dataflow(variant, monkeypatch):
+    """The liveness-based renumbering of a chain program's units (assembler.h, compact_units) must not change what the
+    program computes: same g from the renumbered and the original program, fewer units, nothing read after its unit was
+    given to another value (such a read would see the other value or the poison the scratch is filled with)."""
+    lm = models.kinetics(variant).lower()
+    rng = np.random.default_rng(7)
+    n_par = len(lm.tapes.layout.param_slots)
+    par = list(rng.uniform(0.5, 2.0, n_par))
+    g1, u1 = _run_chain_program(lm, par, monkeypatch, compact=True)
+    g0, u0 = _run_chain_program(lm, par, monkeypatch, compact=False)
+    assert all(v == v for v in g0) and g1 == g0
+    assert u1 < u0 and u1 <= 20                      # 4 CTAs of 128 threads x 2 scenarios per SM need <= 25 units
 
 
 def test_fused_chain_per_element_controls():
