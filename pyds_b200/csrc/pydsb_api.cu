@@ -623,14 +623,12 @@ int build_program(const Sections& secs, int mode, Program& P, bool upload = true
     int land = g.spt * BLOCK * g.p_dim * 8;
     if (rchain) {
         land = 0;
-        if ((BLOCK / 32) * RECOURSE_STAGES * recourse_nv(g.nz) > g.n_units * BLOCK)
-            return fail(PYDSB_ERR_UNSUPPORTED, "chain program too small for the reduction scratch");
+        if (g.n_units < 1) return fail(PYDSB_ERR_UNSUPPORTED, "chain program too small for the reduction scratch");
     }
     if (sens) {
         land = 0;                                           // sens_kernel loads theta directly
-        // the cross-warp scratch of the shared modes overlays the program's slots
-        if ((BLOCK / 32) * RECOURSE_STAGES * recourse_nv(g.nz) > g.n_units * BLOCK)
-            return fail(PYDSB_ERR_UNSUPPORTED, "sensitivity program too small for the reduction scratch");
+        // the reduction scratch of the shared modes (rows of BLOCK doubles) overlays the program's slots
+        if (g.n_units < 1) return fail(PYDSB_ERR_UNSUPPORTED, "sensitivity program too small for the reduction scratch");
     }
     g.off_land = o; o = align_up(o + land, 128);
     g.off_slots = o;

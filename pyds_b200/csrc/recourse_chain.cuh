@@ -464,7 +464,7 @@ __device__ __forceinline__ void rsens_body(const ExecImage& img, const RecourseA
             Dc[(size_t)(k * nz + c) * BLOCK] = ((c_rchain.zfix_mask >> c) & 1u) ? 0.0 : v * img.bigm_inv[k];
         }
     }
-    recourse_emit(ra, nz, ng, NV, active, failed, ck, cmax, Dc, wsum, grp, j, t, my_iters);
+    recourse_emit(ra, nz, ng, NV, active, failed, ck, cmax, Dc, wsum, img.n_units < 32 ? img.n_units : 32, grp, j, t, my_iters);
     if (la == nullptr) return;
     // ---- fused: the group's update by one thread, then the next evaluation (or the end) ----
     __threadfence_block();

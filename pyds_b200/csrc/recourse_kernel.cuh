@@ -111,11 +111,11 @@ __host__ __device__ inline int recourse_sens_rows(int ns, int nq, int ng) { retu
 // recourse_chain.cuh): per-scenario mode the scenario's own {failed, c_k, grad c_k}; shared modes the reduced statistics
 // {Phi_mu, Phi, grad, Gauss-Newton H} of RECOURSE_STAGES smoothing stages, summed over the tile in a fixed order.
 // Dc[(k * nz + c) * BLOCK] = d c_k / d z_c of this thread's scenario (shared memory, one spare row of nz after the ng
-// rows); wsum: [BLOCK / 32][n_stages][NV] cross-warp scratch that may overlay the program's slots.
+// rows); wsum: scratch_rows (<= 32) rows of BLOCK doubles for the sums over the tile, may overlay the program's slots.
 __device__ __forceinline__ void recourse_emit(const RecourseArgs& ra, const int nz, const int ng, const int NV, const bool active,
                                               const bool failed, const double (&ck)[8], const double cmax, double* const Dc,
-                                              double* const wsum, const long long grp, const long long j, const long long t,
-                                              const unsigned my_iters)
+                                              double* const wsum, const int scratch_rows, const long long grp, const long long j,
+                                              const long long t, const unsigned my_iters)
 {
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -139,7 +139,41 @@ __device__ __forceinline__ void recourse_emit(const RecourseArgs& ra, const int 
         double* const Vv = Dc + (size_t)ng * nz * BLOCK;
         double mu = __ldcg(ra.mu + grp);                         // (rfused_kernel: updated by the group's thread 0 in between)
         const int SNV = ra.n_stages * NV;
-        __syncthreads();                                         // every thread is done with the program's slots
+        // Sum of every value over the tile's scenarios: the threads write their values side by side into rows of the
+        // scratch (row v = value v of all threads, skewed by 4 v columns so that both the writes and the reads below are
+        // conflict-free); every `scratch_rows` values the rows are summed -- four threads per row, each a quarter of the
+        // columns in a fixed order, combined by two shuffles -- and stored.  (A warp_sum per value costs five dependent
+        // shuffle + add rounds for each of the stages * NV values: that was most of the time of one evaluation.)
+        const int cnt = __syncthreads_count(active);             // (also: every thread is done with the program's slots)
+        // shared modes: the scenarios of a tile sit in the threads [0, cnt); anything else sums all columns
+        const int n_cols = __syncthreads_and(active == (tid < cnt)) ? cnt : BLOCK;
+        double* const buf = wsum;
+        int row = 0, out0 = 0;
+        auto flush = [&]() {
+            __syncthreads();
+            const int r = warp * 8 + (lane >> 2), part = lane & 3;
+            double s0 = 0.0, s1 = 0.0;
+            if (r < row) {
+                const double* const rowp = buf + (size_t)r * BLOCK;
+                int c = part;
+                for (; c + 4 < n_cols; c += 8) {
+                    s0 += rowp[(c + 4 * r) & (BLOCK - 1)];
+                    s1 += rowp[(c + 4 + 4 * r) & (BLOCK - 1)];
+                }
+                if (c < n_cols) s0 += rowp[(c + 4 * r) & (BLOCK - 1)];
+            }
+            double sm = s0 + s1;
+            sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+            sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+            if (r < row && part == 0) ra.acc[t * SNV + out0 + r] = sm;   // (i_d, tile) == blockIdx.x in the shared modes
+            out0 += row;
+            row = 0;
+            __syncthreads();
+        };
+        auto emit = [&](double val) {                            // values in the order [stage][Phi_mu, Phi, grad, H packed]
+            buf[(size_t)row * BLOCK + ((tid + 4 * row) & (BLOCK - 1))] = val;
+            if (++row == scratch_rows) flush();
+        };
         for (int st = 0; st < ra.n_stages; ++st) {
             double pk[8];
             double phi, raw;
@@ -150,32 +184,20 @@ __device__ __forceinline__ void recourse_emit(const RecourseArgs& ra, const int 
                 Vv[(size_t)c * BLOCK] = v;
             }
             const double wmu = wv / mu;
-            double* const ws = wsum + warp * SNV + st * NV;
-            auto emit = [&](int idx, double val) {
-                const double sm = warp_sum(val);
-                if (lane == 0) ws[idx] = sm;
-            };
-            emit(0, wv * phi);
-            emit(1, wv * raw);
-            for (int c = 0; c < nz; ++c) emit(2 + c, wv * Vv[(size_t)c * BLOCK]);
-            int idx = 2 + nz;
+            emit(wv * phi);
+            emit(wv * raw);
+            for (int c = 0; c < nz; ++c) emit(wv * Vv[(size_t)c * BLOCK]);
             for (int a = 0; a < nz; ++a)
-                for (int b = a; b < nz; ++b, ++idx) {
+                for (int b = a; b < nz; ++b) {
                     double hv = 0.0;
                     for (int k = 0; k < ng; ++k)
                         hv = fma(pk[k] * Dc[(size_t)(k * nz + a) * BLOCK], Dc[(size_t)(k * nz + b) * BLOCK], hv);
                     hv = fma(-Vv[(size_t)a * BLOCK], Vv[(size_t)b * BLOCK], hv);
-                    emit(idx, wmu * hv);
+                    emit(wmu * hv);
                 }
             mu = fmax(mu / 10.0, ra.mu_min);
         }
-        __syncthreads();
-        for (int v = tid; v < SNV; v += BLOCK) {
-            double sm = 0.0;
-#pragma unroll
-            for (int wq = 0; wq < BLOCK / 32; ++wq) sm += wsum[wq * SNV + v];    // fixed order: deterministic
-            ra.acc[t * SNV + v] = sm;                                // (i_d, tile) == blockIdx.x in the shared modes
-        }
+        if (row) flush();
     }
     if (ra.counters) {
         const unsigned it_sum = warp_sum_u32(active ? my_iters : 0u);
@@ -474,7 +496,7 @@ __global__ void __launch_bounds__(BLOCK, (NS <= 2 ? 3 : 1))
         }
         for (int k = 0; k < ng; ++k) Dc[(size_t)(k * nz + c) * BLOCK] = dcv[k];
     }
-    recourse_emit(ra, nz, ng, NV, active, failed, ck, cmax, Dc, wsum, grp, j, t, my_iters);
+    recourse_emit(ra, nz, ng, NV, active, failed, ck, cmax, Dc, wsum, img.n_units < 32 ? img.n_units : 32, grp, j, t, my_iters);
 }
 
 struct LmArgs {

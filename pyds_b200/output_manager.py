@@ -2,6 +2,8 @@
 ``pyds/output_manager.py`` (unchanged by the north star): the previous ``pyds_output.pkl`` is removed
 at construction, a buffer ``{input, solver, simulator}`` is filled per inner iteration and appended."""
 import pickle
+
+import numpy as np
 from os import remove
 from os.path import exists, join
 
@@ -36,3 +38,35 @@ class OutputManager:
         with open(self.output_path_fnx, "ab+") as f:
             for rec in records:
                 pickle.dump(rec, f)
+
+    def write_input_records(self, key_d, key_p, d, p, solver_output):
+        """One record per row of ``d`` whose only varying part is that row: ``{input: {key_d: d[i:i+1], key_p: p}, solver:
+        solver_output, simulator: None}`` -- what the two-stage manager logs when no output is saved (reference
+        run.py:55-67 with ``save output`` off).  The byte stream is the one ``pickle.dump`` per record produces: the first
+        record is pickled, the others are that byte string with the row's 8-byte values replaced, which is checked against
+        a real pickle of the last record; anything unexpected (the row's bytes occurring twice, a different length) falls
+        back to pickling every record."""
+        n = len(d)
+        if n == 0:
+            return
+
+        def rec(i):
+            return {"input": {key_d: d[i:i + 1], key_p: p}, "solver": dict(solver_output), "simulator": None}
+
+        first = pickle.dumps(rec(0))
+        blob = None
+        if n >= 3 and d.dtype == np.float64 and d.ndim == 2 and d.flags.c_contiguous:
+            row = d[0:1].tobytes()
+            off = first.find(row)
+            if off >= 0 and first.find(row, off + 1) < 0:
+                last = bytearray(first)
+                last[off:off + len(row)] = d[n - 1:n].tobytes()
+                if bytes(last) == pickle.dumps(rec(n - 1)):
+                    arr = np.tile(np.frombuffer(first, dtype=np.uint8), (n, 1))
+                    arr[:, off:off + len(row)] = d.view(np.uint8).reshape(n, len(row))
+                    blob = arr.tobytes()
+        if blob is None:
+            blob = b"".join(pickle.dumps(rec(i)) for i in range(n))
+        with open(self.output_path_fnx, "ab+") as f:
+            f.write(blob)
+

@@ -139,6 +139,11 @@ class TwoStageManager(Manager):
         if self.simulator.save_output and len(d):            # warm-start simulation records (reference run.py:61-62)
             self.simulator.simulate_all_scenarios(self.model, {self._stages[0]: d, self._stages[1]: p})
         indicator = self.solver.solve(d, p, w, mode="shared") if len(d) else np.zeros((0, n_p))
+        if not self.simulator.save_output and not self.solver.save_output:
+            # nothing but the inputs to log: the same records (one per design point, reference run.py:67), written at once;
+            # DEUS uses g >= 0 as "feasible" -- the (n_p, 1) matrices are views of one negated array
+            self.output_manager.write_input_records(self._stages[0], self._stages[1], d, p, self.solver.output)
+            return list((-indicator)[:, :, None])
         g_list, records = [], []
         for i in range(d.shape[0]):
             g_mat = np.empty((n_p, 1))
