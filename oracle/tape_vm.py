@@ -48,7 +48,7 @@ class TapeVM:
         self.sec = s
         (self.ns, self.nq, self.ng, self.d_dim, self.p_dim, self.nz, self.nfe, self.ncp, self.nce, self.n_units,
          self.ctrl_slot, self.xe_slot, self.qe_slot, self.x_slot, self.max_it,
-         _, self.fq_state_dep, self.predictor, self.n_blocks) = [int(v) for v in s["HEAD"]]
+         _, self.fq_state_dep, _, self.n_blocks) = [int(v) for v in s["HEAD"]]
         # blocks of the block-triangular state solve: (states, linear flag, tape) + the quadrature tape
         B, Tn = s["BLKS"], s["BLKT"]
         self.blocks, pc, fpos, jpos = [], 0, 0, 0

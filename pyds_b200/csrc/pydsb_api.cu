@@ -1252,6 +1252,7 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
         CUDA_TRY_WS(cudaFuncSetAttribute(ff, cudaFuncAttributeMaxDynamicSharedMemorySize, img.smem_bytes));
         ra.active = nullptr; ra.n_active = nullptr;
         la.active_in = nullptr; la.n_active_in = nullptr; la.active_out = nullptr; la.n_running = counts;
+        ra.n_stages = 1; la.n_stages = 1;            // one smoothing stage per emission, the next one on request
         {
             ProfScope ps(m, 1, st);
             ff<<<(unsigned)G, BLOCK, img.smem_bytes, st>>>(img, ra, la);

@@ -464,14 +464,25 @@ __device__ __forceinline__ void rsens_body(const ExecImage& img, const RecourseA
             Dc[(size_t)(k * nz + c) * BLOCK] = ((c_rchain.zfix_mask >> c) & 1u) ? 0.0 : v * img.bigm_inv[k];
         }
     }
-    recourse_emit(ra, nz, ng, NV, active, failed, ck, cmax, Dc, wsum, img.n_units < 32 ? img.n_units : 32, grp, j, t, my_iters);
+    const int scratch_rows = img.n_units < 32 ? img.n_units : 32;
+    recourse_emit(ra, nz, ng, NV, active, failed, ck, cmax, Dc, wsum, scratch_rows, grp, j, t, my_iters);
     if (la == nullptr) return;
-    // ---- fused: the group's update by one thread, then the next evaluation (or the end) ----
-    __threadfence_block();
-    __syncthreads();
-    if (tid == 0) lm_update_group_regs<RC_NZ>(*la, grp);
-    __threadfence_block();
-    __syncthreads();
+    // ---- fused: the group's update by one thread, then the next evaluation (or the end).  One smoothing stage is emitted
+    // per call (ra.n_stages = 1); when the update moves on to the next stage at the same controls it asks for that stage's
+    // statistics (want_stage): c_k and their gradients are still in place, only the smoothing changes ----
+    int* const want_stage = reinterpret_cast<int*>(smem + 64);
+    for (bool resumed = false;; resumed = true) {
+        __threadfence_block();
+        __syncthreads();
+        if (tid == 0) {
+            *want_stage = 0;
+            lm_update_group_regs<RC_NZ>(*la, grp, ra.n_stages == 1 ? want_stage : nullptr, resumed);
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (!*want_stage) break;
+        recourse_emit(ra, nz, ng, NV, active, failed, ck, cmax, Dc, wsum, scratch_rows, grp, j, t, my_iters, false);
+    }
     if (fused_it > la->max_iter) return;                     // (the update stops the group at its iteration cap)
   }
 }

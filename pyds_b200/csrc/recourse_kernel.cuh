@@ -115,7 +115,7 @@ __host__ __device__ inline int recourse_sens_rows(int ns, int nq, int ng) { retu
 __device__ __forceinline__ void recourse_emit(const RecourseArgs& ra, const int nz, const int ng, const int NV, const bool active,
                                               const bool failed, const double (&ck)[8], const double cmax, double* const Dc,
                                               double* const wsum, const int scratch_rows, const long long grp, const long long j,
-                                              const long long t, const unsigned my_iters)
+                                              const long long t, const unsigned my_iters, const bool count = true)
 {
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -174,10 +174,60 @@ __device__ __forceinline__ void recourse_emit(const RecourseArgs& ra, const int 
             buf[(size_t)row * BLOCK + ((tid + 4 * row) & (BLOCK - 1))] = val;
             if (++row == scratch_rows) flush();
         };
+        constexpr int NZS = 8, NVS = 2 + NZS + NZS * (NZS + 1) / 2, HALF = NVS / 2;   // the static path: nz = 8, 46 values
+        const bool static_path = nz == NZS && scratch_rows >= HALF;
         for (int st = 0; st < ra.n_stages; ++st) {
             double pk[8];
             double phi, raw;
             hinge_point(ng, ck, cmax, failed, mu, pk, phi, raw);
+            if (static_path) {
+                // nz = 8 (the shipped problems): everything of a stage in registers with static indices -- the gradient
+                // rows are read once per constraint instead of once per Hessian entry -- and two flushes of 23 rows
+                double V[NZS], Hh[NZS * (NZS + 1) / 2];
+#pragma unroll
+                for (int c = 0; c < NZS; ++c) V[c] = 0.0;
+#pragma unroll
+                for (int i = 0; i < NZS * (NZS + 1) / 2; ++i) Hh[i] = 0.0;
+#pragma unroll 1
+                for (int k = 0; k < ng; ++k) {
+                    const double* const Dk = Dc + (size_t)k * NZS * BLOCK;
+                    double D[NZS];
+#pragma unroll
+                    for (int c = 0; c < NZS; ++c) D[c] = Dk[(size_t)c * BLOCK];
+                    const double pkk = pk[k];
+                    int idx = 0;
+#pragma unroll
+                    for (int a = 0; a < NZS; ++a) {
+                        V[a] = fma(pkk, D[a], V[a]);
+                        const double pa = pkk * D[a];
+#pragma unroll
+                        for (int b = a; b < NZS; ++b, ++idx) Hh[idx] = fma(pa, D[b], Hh[idx]);
+                    }
+                }
+                const double wmu = wv / mu;
+                {
+                    int idx = 0;
+#pragma unroll
+                    for (int a = 0; a < NZS; ++a)
+#pragma unroll
+                        for (int b = a; b < NZS; ++b, ++idx) Hh[idx] = wmu * fma(-V[a], V[b], Hh[idx]);
+                }
+                if (row) flush();
+                // value v of the stage: Phi_mu, Phi, grad (8), H packed (36); rows [0, HALF) of the scratch, twice
+                auto value = [&](int v) -> double {                 // (v is a compile-time constant after unrolling)
+                    return v == 0 ? wv * phi : (v == 1 ? wv * raw : (v < 2 + NZS ? wv * V[v - 2 < NZS ? (v >= 2 ? v - 2 : 0) : 0]
+                                                                                 : Hh[v - 2 - NZS >= 0 ? v - 2 - NZS : 0]));
+                };
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int i = 0; i < HALF; ++i) buf[(size_t)i * BLOCK + ((tid + 4 * i) & (BLOCK - 1))] = value(half * HALF + i);
+                    row = HALF;
+                    flush();
+                }
+                mu = fmax(mu / 10.0, ra.mu_min);
+                continue;
+            }
             for (int c = 0; c < nz; ++c) {
                 double v = 0.0;
                 for (int k = 0; k < ng; ++k) v = fma(pk[k], Dc[(size_t)(k * nz + c) * BLOCK], v);
@@ -199,7 +249,7 @@ __device__ __forceinline__ void recourse_emit(const RecourseArgs& ra, const int 
         }
         if (row) flush();
     }
-    if (ra.counters) {
+    if (ra.counters && count) {
         const unsigned it_sum = warp_sum_u32(active ? my_iters : 0u);
         const unsigned dn = warp_sum_u32(active ? 1u : 0u);
         const unsigned fl = warp_sum_u32((active && failed) ? 1u : 0u);
@@ -531,7 +581,7 @@ struct LmArgs {
 
 __device__ bool lm_update_group(const LmArgs& a, long long g);
 template <int NZC>
-__device__ bool lm_update_group_regs(const LmArgs& a, long long g);
+__device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_stage = nullptr, bool resumed = false);
 
 // One thread per (running) group.  NZC > 0: the register-resident update for nz <= NZC controls (lm_update_group_regs);
 // NZC = 0: the generic one (local-memory arrays, any nz <= MAX_NZ).
@@ -793,8 +843,12 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
 // all arrays are statically indexed (the free set is a bit mask, the damped system is the full nz x nz matrix with
 // identity rows for the controls that are not free -- the same factors and the same step as the compacted system),
 // and the state is written back once at the end.  Same decisions and, up to FMA contraction, the same numbers.
+// want_stage (rfused_kernel): the caller emits ONE stage per call; when the group converges at the evaluated point and the
+// continuation goes on, *want_stage is set instead of reading the next stage -- the caller emits the statistics for the new
+// mu at the same point (nothing but the smoothing changes) and calls again with resumed = true, which is the `continue` of
+// the stage loop below: the same numbers, the same decisions, no iteration counted in between.
 template <int NZC>
-__device__ bool lm_update_group_regs(const LmArgs& a, long long g)
+__device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_stage, bool resumed)
 {
     const int nz = a.nz, ng = a.ng;
     const double* __restrict__ acc = a.acc;
@@ -811,8 +865,9 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
         gr[c] = in ? a.gr[g * nz + c] : 0.0;
         fixd[c] = in ? a.zfix[c] != 0 : true;
     }
-    const int iters = a.iters[g] + 1;
+    const int iters = a.iters[g] + (resumed ? 0 : 1);
     int first = a.first[g], status = 0;
+    bool lazy = false;
     double F_cur = a.F_cur[g], raw_cur = a.raw_cur[g], lam = a.lam[g], mu = a.mu[g];
     double* const H = a.H + g * nz * nz;
     // per-scenario mode: the scenario's own record
@@ -1051,9 +1106,10 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g)
 #pragma unroll
                     for (int c = 0; c < NZC; ++c) zt[c] = zc[c];
                     if (at_eval_point && stage + 1 < stages_in_hand) continue;
+                    if (at_eval_point && want_stage) { *want_stage = 1; lazy = true; }
                 }
             }
-            if (!done && iters >= a.max_iter) {
+            if (!done && !lazy && iters >= a.max_iter) {
                 status = 3;
                 done = true;
             }

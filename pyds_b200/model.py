@@ -53,7 +53,7 @@ class _Control:
 
 
 class DaeModel:
-    def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-12, newton_max_it=25, predictor=False,
+    def __init__(self, d_names, p_names, nfe=8, ncp=3, newton_rtol=1e-12, newton_max_it=25,
                  quadratures="auto", block_triangular=True, polynomial_blocks=True, second_derivatives=False,
                  fused_chain=True):
         self.graph = T.Graph()
@@ -62,7 +62,6 @@ class DaeModel:
         self.nfe, self.ncp = int(nfe), int(ncp)
         self.newton_rtol = float(newton_rtol)
         self.newton_max_it = int(newton_max_it)
-        self.predictor = bool(predictor)        # start Newton from the extrapolated previous element
         # "auto": every state that appears in no right-hand side becomes a quadrature (exact); or an explicit
         # list of state names, e.g. ["u"] keeps cC in the Newton system (the 9-unknown form of SURVEY.md A.3)
         self.quadratures = quadratures
@@ -342,7 +341,7 @@ class DaeModel:
                 blk_fixed = fixed
             sec("HEAD", "u32", [ns, nq, ng, len(self.d_names), len(self.p_names), nz, self.nfe, self.ncp, nce,
                                 lay.n_units, lay.ctrl_slot, lay.xe_slot, lay.qe_slot, lay.x_slot, self.newton_max_it,
-                                0 if self.fused_chain else 1, lay.fq_state_dep, 1 if self.predictor else 0, len(blks)])
+                                0 if self.fused_chain else 1, lay.fq_state_dep, 0, len(blks)])      # HEAD[17]: reserved
             sec("RPAR", "u16", lay.param_slots)
             sec("DBLS", "f64", [self.newton_rtol])
             sec("CNST", "f64", low.consts if len(low.consts) else [0.0])
