@@ -1293,7 +1293,8 @@ int recourse_solve_impl(void* handle, int per_scenario, const double* d, long lo
         la.active_out = compact ? act + (size_t)(it & 1) * G : nullptr;
         {
             ProfScope ps(m, 2, st);
-            if (nz <= 8) lm_update_kernel<8><<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
+            if (nz <= 8 && la.per_scenario && img.ng <= 2) lm_update_kernel<8, 2><<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
+            else if (nz <= 8) lm_update_kernel<8><<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
             else lm_update_kernel<0><<<(unsigned)((upper + tb - 1) / tb), tb, 0, st>>>(la);
         }
         CUDA_TRY_WS(cudaGetLastError());

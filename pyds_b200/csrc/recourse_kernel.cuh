@@ -580,13 +580,17 @@ struct LmArgs {
 };
 
 __device__ bool lm_update_group(const LmArgs& a, long long g);
-template <int NZC>
+template <int NZC, int NGC = 8>
 __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_stage = nullptr, bool resumed = false);
 
 // One thread per (running) group.  NZC > 0: the register-resident update for nz <= NZC controls (lm_update_group_regs);
 // NZC = 0: the generic one (local-memory arrays, any nz <= MAX_NZ).
-template <int NZC>
-__global__ void __launch_bounds__(128, NZC > 0 ? 3 : 1) lm_update_kernel(const LmArgs a)
+// NGC: compile-time bound on the constraints per scenario (per-scenario mode keeps c_k and their gradients in registers).
+template <int NZC, int NGC = 8>
+#ifndef PYDSB_LM_CTAS
+#define PYDSB_LM_CTAS 2
+#endif
+__global__ void __launch_bounds__(128, NZC > 0 ? PYDSB_LM_CTAS : 1) lm_update_kernel(const LmArgs a)
 {
     const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long n_in = a.n_active_in ? (long long)*a.n_active_in : a.n_groups;
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(128, NZC > 0 ? 3 : 1) lm_update_kernel(const L
     if (k < n_in) {
         g = a.active_in ? a.active_in[k] : k;
         if (a.status[g] == 0) {
-            if constexpr (NZC > 0) done = lm_update_group_regs<NZC>(a, g);
+            if constexpr (NZC > 0) done = lm_update_group_regs<NZC, NGC>(a, g);
             else done = lm_update_group(a, g);
         }
     }
@@ -847,7 +851,7 @@ __device__ bool lm_update_group(const LmArgs& a, long long g)
 // continuation goes on, *want_stage is set instead of reading the next stage -- the caller emits the statistics for the new
 // mu at the same point (nothing but the smoothing changes) and calls again with resumed = true, which is the `continue` of
 // the stage loop below: the same numbers, the same decisions, no iteration counted in between.
-template <int NZC>
+template <int NZC, int NGC>
 __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_stage, bool resumed)
 {
     const int nz = a.nz, ng = a.ng;
@@ -873,23 +877,34 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_sta
     // per-scenario mode: the scenario's own record
     const double* const rec = acc + g * recourse_nvp(ng, nz);
     bool rec_failed = false;
-    double ck[8], cmax = 0.0;
+    double ck[NGC], cmax = 0.0;
+    // per-scenario mode: the scenario's gradients d c_k / d z_c -- loaded once when they fit the registers (few constraints)
+    constexpr bool PRE = NGC <= 2;
+    double Dr[PRE ? NGC : 1][PRE ? NZC : 1];
+    const double* const Dc = rec + 1 + ng;
     if (a.per_scenario) {
         rec_failed = rec[0] != 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < NGC; ++k) {
             ck[k] = k < ng ? rec[1 + k] : 0.0;
             if (k < ng) cmax = fmax(cmax, ck[k]);
+            if constexpr (PRE) {
+#pragma unroll
+                for (int c = 0; c < NZC; ++c) Dr[k][c] = (k < ng && c < nz) ? Dc[k * nz + c] : 0.0;
+            }
         }
     }
-    const double* const Dc = rec + 1 + ng;
+    auto dval = [&](int k, int c) -> double {
+        if constexpr (PRE) return Dr[k][c];
+        else return Dc[k * nz + c];
+    };
     const int NV = recourse_nv(nz);
 
     bool done = false;
     const int stages_in_hand = a.per_scenario ? (1 << 30) : a.n_stages;
     for (int stage = 0;; ++stage) {
         // ---- statistics of this stage: {Phi_mu, Phi, grad} ----
-        double F_t = 0.0, raw_t = 0.0, g_t[NZC], pk[8];
+        double F_t = 0.0, raw_t = 0.0, g_t[NZC], pk[NGC];
 #pragma unroll
         for (int c = 0; c < NZC; ++c) g_t[c] = 0.0;
         const double mu_stage = mu;
@@ -897,17 +912,17 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_sta
             if (rec_failed) {
                 F_t = raw_t = 1.0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) pk[k] = 0.0;
+                for (int k = 0; k < NGC; ++k) pk[k] = 0.0;
             } else {
                 double Z = exp(-cmax / mu_stage);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < NGC; ++k) {
                     pk[k] = k < ng ? exp((ck[k] - cmax) / mu_stage) : 0.0;
                     if (k < ng) Z += pk[k];
                 }
                 const double zi = 1.0 / Z;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) pk[k] *= zi;
+                for (int k = 0; k < NGC; ++k) pk[k] *= zi;
                 F_t = cmax + mu_stage * log(Z);
                 raw_t = cmax;
             }
@@ -915,8 +930,8 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_sta
             for (int c = 0; c < NZC; ++c)
                 if (c < nz) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (k < ng) g_t[c] = fma(pk[k], Dc[k * nz + c], g_t[c]);
+                    for (int k = 0; k < NGC; ++k)
+                        if (k < ng) g_t[c] = fma(pk[k], dval(k, c), g_t[c]);
                 }
         } else {
             for (int t = 0; t < a.n_tiles; ++t) {
@@ -981,8 +996,8 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_sta
                                     if (((fm >> r) & (fm >> c)) & 1u) {    // only free x free entries are ever read,
                                         double hv = 0.0;                   // and only from the lower triangle
 #pragma unroll
-                                        for (int k = 0; k < 8; ++k)
-                                            if (k < ng) hv = fma(pk[k] * Dc[k * nz + r], Dc[k * nz + c], hv);
+                                        for (int k = 0; k < NGC; ++k)
+                                            if (k < ng) hv = fma(pk[k] * dval(k, r), dval(k, c), hv);
                                         H[c * nz + r] = fma(-g_t[r], g_t[c], hv) * inv_mu;
                                     }
                         } else {
@@ -1082,12 +1097,12 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_sta
                     int kmax = -1;
                     double cm = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
+                    for (int k = 0; k < NGC; ++k)
                         if (k < ng && ck[k] > cm) { cm = ck[k]; kmax = k; }
                     if (kmax >= 0) {
                         double rest = exp(-cm / mu);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
+                        for (int k = 0; k < NGC; ++k)
                             if (k < ng && k != kmax) rest += exp((ck[k] - cm) / mu);
                         saturated = rest < 1e-30;
                     }

@@ -27,6 +27,12 @@ torch.cuda.synchronize()
 t0 = time.time(); rd = eng.recourse_solve_device(td, tp, per_scenario=True, max_iter=50); t_dev = time.time() - t0
 c = eng.counters()
 del rd
+if os.environ.get("PYDSB_C4_PROFILE"):               # CUDA events around every kernel of a second, warm solve
+    eng.set_profiling(True); eng.profile(reset=True)
+    t0 = time.time(); rd = eng.recourse_solve_device(td, tp, per_scenario=True, max_iter=50); t_w = time.time() - t0
+    print({"warm_seconds": t_w, **eng.profile()}, flush=True)
+    eng.set_profiling(False)
+    del rd
 t0 = time.time(); r = eng.recourse_solve(d, p, per_scenario=True, max_iter=50); t = time.time() - t0
 print({"seconds_device_resident": t_dev, "seconds": t, "scenarios": n_d * n_t, "state_solves": c["scenarios"], "launches": c["launches"],
        "feasible_frac": float((r["phi"] == 0).mean()), "iters_mean": float(r["iters"].mean()), "iters_max": int(r["iters"].max()),
