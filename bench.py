@@ -420,6 +420,33 @@ def c1_section(np_, tempfile_mod):
             "inside_band": res.get("inside_band"), "lm_evaluations_mean": float(np_.mean(res["iters"])) if "iters" in res else None}
 
 
+def c2_section(np_, tempfile_mod):
+    """Config C2: run_threestage.py's call shape -- ThreeStageManager.g(100 design points x 50 theta), ONE control vector for
+    the whole tree optimised over all 5 000 scenarios (reference pyds/run.py:76-98) -- and the same at 2 000 design points."""
+    from examples import threestage_reactor as ex3
+    from examples.reactor_model import theta_samples
+    from pyds_b200.run import ThreeStageManager
+    m = ThreeStageManager(ex3.build_config(tempfile_mod.mkdtemp()))
+    _, p_samples = theta_samples()
+    p50 = np_.array([s["c"] for s in p_samples])
+    rng = np_.random.default_rng(1989)
+    out = {"name": "C2", "workload": "run_threestage.py as repaired in examples/threestage_reactor.py: ThreeStageManager.g(n_d design points "
+                                     "x 50 theta), one control vector for the whole tree (global group)"}
+    for n_d in (100, 2000):
+        d = np_.stack([rng.uniform(250, 350, n_d), rng.uniform(250, 300, n_d)], axis=1)
+        m.g(d[:8], p50)
+        tg, te = [], []
+        for _ in range(3):
+            t0 = time.perf_counter(); m.g(d, p50); tg.append(time.perf_counter() - t0)
+        for _ in range(3):
+            t0 = time.perf_counter(); P = m.efp(d, p50, np_.full(50, 0.02)); te.append(time.perf_counter() - t0)
+        res = getattr(m.solver, "result", {}) or {}
+        out[f"n_d_{n_d}"] = {"g_call_ms": 1e3 * float(np_.median(tg)), "efp_call_ms": 1e3 * float(np_.median(te)),
+                             "scenarios": n_d * 50, "P_mean": float(np_.mean(P)),
+                             "lm_evaluations": int(np_.max(res["iters"])) if "iters" in res else None}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -433,7 +460,7 @@ def main():
                     help="CPU arm: the equations as the GPU solves them (block triangular) or the dense 9-unknown Newton system")
     ap.add_argument("--cpu-rows", type=int, default=1000, help="design points of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C4 / strong-scaling / C5 sections")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C2 / C4 / strong-scaling / C5 sections")
     ap.add_argument("--ns-iterations", type=int, default=5, help="nested-sampling iterations timed (config C5; the median is reported)")
     ap.add_argument("--ns-live", type=int, default=100000, help="live points of the C5 nested-sampling section")
     ap.add_argument("--ns-theta", type=int, default=100000)
@@ -579,6 +606,10 @@ def main():
                 configs.append(c1_section(np, tempfile))
             except Exception as e:                     # the manager path must not take the headline down with it
                 configs.append({"name": "C1", "error": repr(e)})
+            try:
+                configs.append(c2_section(np, tempfile))
+            except Exception as e:
+                configs.append({"name": "C2", "error": repr(e)})
         # ---- C5: nested sampling, 6 design variables, n_live x n_theta sharded over the ranks ----
         eng6 = capi.Engine(models.kinetics("design6").lower().blob, local_rank)
         sh6 = ShardedEfp(eng6, world, rank)
