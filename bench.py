@@ -394,6 +394,36 @@ def c4_section(torch, capi, models, dev, peak_tflops, n_d=1000, n_t=10000):
     return out
 
 
+def c4_sharded_section(torch, capi, models, dev, world, rank, barrier, max_over_ranks, n_d=1000, n_t=10000):
+    """Config C4 with its design points sharded over the ranks (every (d,theta) problem is independent: no exchange), FIXED
+    total work: max-over-ranks wall time of the sharded solve against this rank's own solve of the whole grid."""
+    lm = models.kinetics("twostage").lower()
+    eng = capi.Engine(lm.blob, dev.index)
+    rng = np.random.default_rng(1989)
+    d = np.stack([rng.uniform(250, 350, n_d), rng.uniform(250, 300, n_d)], axis=1)
+    _, p, _ = make_inputs(10, n_t)
+    a, b = shard_rows(n_d, world, rank)
+    td, tp = torch.from_numpy(d).to(dev), torch.from_numpy(p).to(dev)
+    tds = td[a:b].contiguous()
+    eng.recourse_solve_device(td, tp, per_scenario=True, max_iter=2)      # warm-up + the workspace of the full batch
+    torch.cuda.synchronize()
+
+    def timed(rows):
+        barrier()
+        t0 = time.perf_counter()
+        eng.recourse_solve_device(rows, tp, per_scenario=True, max_iter=50)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    full = min(timed(td) for _ in range(2))
+    part = max_over_ranks(min(timed(tds) for _ in range(2)))
+    full = max_over_ranks(full)
+    return {"name": "C4-fixed", "workload": f"C4 with FIXED total work: {n_d} x {n_t} per-scenario 8-control problems in all, design "
+                                            f"points sharded over {world} GPU(s), no exchange (wall time, max over ranks)",
+            "seconds": part, "value": n_d * n_t / part, "unit": "scenario optimisations/s", "scaling": "strong",
+            "single_gpu_seconds": full, "strong_efficiency": full / (world * part)}
+
+
 def c1_section(np_, tempfile_mod):
     """Config C1: the shipped two-stage script's call shape -- g(150 design points x 50 theta) through TwoStageManager,
     control optimisation included (what DEUS calls once per nested-sampling iteration)."""
@@ -600,6 +630,35 @@ def main():
                         "ms_per_step": fixed_ms, "value": n_d * n_t / (fixed_ms * 1e-3), "unit": UNIT, "scaling": "strong",
                         "strong_efficiency": k_ms / (world * fixed_ms) if world > 1 else 1.0,
                         "strong_efficiency_note": "single-GPU kernel time of the same batch (this run, rank-local) / (N x sharded time)"})
+        # ---- C3 with the DEUS-shaped return materialised on the device: g (n_d, n_t, n_g) and -indicator (n_d, n_t) ----
+        if world == 1:
+            try:
+                g_buf = torch.empty((n_d, n_t, lm.ng), dtype=torch.float64, device=dev)
+                i_buf = torch.empty((n_d, n_t), dtype=torch.float64, device=dev)
+                eng.eval_device(d, th, w, P_out=P_all[:n_d], g_out=g_buf, ind_out=i_buf)
+                torch.cuda.synchronize()
+                ge = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+                for k in range(args.steps):
+                    flush.fill_(float(k))
+                    ge[k][0].record(); eng.eval_device(d, th, w, P_out=P_all[:n_d], g_out=g_buf, ind_out=i_buf); ge[k][1].record()
+                torch.cuda.synchronize()
+                g_ms = sum(x.elapsed_time(y) for x, y in ge) / args.steps
+                wbytes = g_buf.numel() * 8 + i_buf.numel() * 8
+                configs.append({"name": "C3-g", "workload": "C3 with g and -indicator of every (d,theta) written to device memory "
+                                                            "(what the list-of-arrays contract of DEUS needs before any copy)",
+                                "ms_per_step": g_ms, "value": n_d * n_t / (g_ms * 1e-3), "unit": UNIT,
+                                "bytes_written_per_step": wbytes, "extra_ms_over_P_only": g_ms - k_ms,
+                                "write_GBps": wbytes / (g_ms * 1e-3) / 1e9,
+                                "note": "the stores run under the FP64 work (a few percent of the HBM write bandwidth): the kernel "
+                                        "stays FP64 bound; what the DEUS contract costs is the copy of these bytes to the host"})
+                del g_buf, i_buf
+            except Exception as e:
+                configs.append({"name": "C3-g", "error": repr(e)})
+        if world > 1:
+            try:
+                configs.append(c4_sharded_section(torch, capi, models, dev, world, rank, barrier, max_over_ranks))
+            except Exception as e:
+                configs.append({"name": "C4-fixed", "error": repr(e)})
         if world == 1:
             configs.append(c4_section(torch, capi, models, dev, peak_tflops))
             try:

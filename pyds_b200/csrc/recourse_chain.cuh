@@ -125,7 +125,7 @@ struct RcTerm {
     unsigned p, src;
 };
 __device__ __forceinline__ RcTerm rc_term(const char* __restrict__ base, const char* __restrict__ cz, unsigned n_off, unsigned meta,
-                                          int e, const double* __restrict__ zg, double scale)
+                                          int e, const double* __restrict__ zs, double scale)
 {
     RcTerm t;
     t.nvz = t.nvn = 0.0; t.zi = -1; t.p = (meta >> 8) & 3u; t.src = (meta >> 12) & 3u;
@@ -136,7 +136,7 @@ __device__ __forceinline__ RcTerm rc_term(const char* __restrict__ base, const c
     if (meta & CT_HAS_CTRL) {
         t.zi = (int)c_rchain.cmap[e][(meta >> 4) & 0xFu];
         t.nvn = nv;
-        t.nvz = nv * (((c_rchain.zfix_mask >> t.zi) & 1u) ? rc_ref(base, cz, c_rchain.zfix_ref[t.zi]) : __ldcg(zg + t.zi));
+        t.nvz = nv * (((c_rchain.zfix_mask >> t.zi) & 1u) ? rc_ref(base, cz, c_rchain.zfix_ref[t.zi]) : zs[(size_t)t.zi * BLOCK]);
     }
     return t;
 }
@@ -227,7 +227,19 @@ __device__ __forceinline__ void rsens_body(const ExecImage& img, const RecourseA
 
     for (int c = 0; c < img.p_dim; ++c) RC_LD_W(base, cd.par_off[img.d_dim + c]) = __ldg(ra.theta + j * img.p_dim + c);
     for (int c = 0; c < img.d_dim; ++c) RC_LD_W(base, cd.par_off[c]) = __ldg(ra.d + i_d * img.d_dim + c);
-    const double* const zg = ra.z_try + grp * nz;
+    // the group's control values, staged once per evaluation in this thread's column of the (still unused) Dc rows: one
+    // round of L2 loads in flight together instead of an L2 latency per term and element (z_try is rewritten between the
+    // evaluations of the fused loop by another thread: read past L1)
+    double* const zs = Dc;
+    {
+        const double* const zg = ra.z_try + grp * nz;
+        double zv[RC_NZ];
+#pragma unroll
+        for (int c = 0; c < RC_NZ; ++c) zv[c] = c < nz ? __ldcg(zg + c) : 0.0;
+#pragma unroll
+        for (int c = 0; c < RC_NZ; ++c)
+            if (c < nz) zs[(size_t)c * BLOCK] = zv[c];
+    }
 
     rc_scalar_run(base, cz, 0, (int)cd.pre_end);
 
@@ -285,9 +297,9 @@ __device__ __forceinline__ void rsens_body(const ExecImage& img, const RecourseA
             if (b >= nb) continue;
             const ChainBlockD& bd = cd.blk[b];
             const unsigned kind = SH::kind(b);
-            t0[b] = rc_term(base, cz, bd.c[0].n_off, SH::meta(b, 0), e, zg, h);
-            t1[b] = rc_term(base, cz, bd.c[1].n_off, SH::meta(b, 1), e, zg, h);
-            const RcTerm t2 = rc_term(base, cz, bd.c[2].n_off, SH::meta(b, 2), e, zg, h);     // narrow, control free (assembler)
+            t0[b] = rc_term(base, cz, bd.c[0].n_off, SH::meta(b, 0), e, zs, h);
+            t1[b] = rc_term(base, cz, bd.c[1].n_off, SH::meta(b, 1), e, zs, h);
+            const RcTerm t2 = rc_term(base, cz, bd.c[2].n_off, SH::meta(b, 2), e, zs, h);     // narrow, control free (assembler)
             const double hc2 = t2.nvz;
             const double xs = X[b][2];
             double cb[3], dg[3];
@@ -355,7 +367,7 @@ __device__ __forceinline__ void rsens_body(const ExecImage& img, const RecourseA
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             if (q >= nq) continue;
-            tq[q] = rc_term(base, cz, cd.quad[q].n_off, SH::qmeta(q), e, zg, h);
+            tq[q] = rc_term(base, cz, cd.quad[q].n_off, SH::qmeta(q), e, zs, h);
             double acc = img.bw[0] * rc_pow<NB>(X, tq[q].p, tq[q].src, 0);
             acc = fma(img.bw[1], rc_pow<NB>(X, tq[q].p, tq[q].src, 1), acc);
             acc = fma(img.bw[2], rc_pow<NB>(X, tq[q].p, tq[q].src, 2), acc);

@@ -187,12 +187,8 @@ class ThreeStageManager(Manager):
         if self.simulator.save_output and n_d:               # reference run.py:89-90
             self.simulator.simulate_all_scenarios(self.model, {self._stages[0]: d, self._stages[1]: p})
         indicator = self.solver.solve(d, p, w, mode="global") if n_d else np.zeros((0, n_p))
-        flat = indicator.reshape(-1)
-        g_list = []
-        for i in range(n_d):
-            g_mat = np.empty((n_p, 1))
-            g_mat[:, 0] = -flat[n_p * i:n_p * (i + 1)]
-            g_list.append(g_mat)
+        # DEUS uses g >= 0 as "feasible": one (n_p, 1) matrix per design point (reference run.py:92-96), views of one array
+        g_list = list((-indicator.reshape(n_d, n_p))[:, :, None])
         self.output_manager.clear_buffer()
         self.output_manager.add_input({self._stages[0]: d, self._stages[1]: p})
         self.output_manager.add_solver_solution(self.solver.output)
