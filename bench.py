@@ -397,6 +397,7 @@ def c4_section(torch, capi, models, dev, peak_tflops, n_d=1000, n_t=10000):
 def c4_sharded_section(torch, capi, models, dev, world, rank, barrier, max_over_ranks, n_d=1000, n_t=10000):
     """Config C4 with its design points sharded over the ranks (every (d,theta) problem is independent: no exchange), FIXED
     total work: max-over-ranks wall time of the sharded solve against this rank's own solve of the whole grid."""
+    from pyds_b200.parallel import shard_rows
     lm = models.kinetics("twostage").lower()
     eng = capi.Engine(lm.blob, dev.index)
     rng = np.random.default_rng(1989)
