@@ -9,7 +9,8 @@ rep = sys.argv[1]
 W = float(sys.argv[2]) if len(sys.argv) > 2 else 1.5625e6
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-h = rows[1]; data = rows[2:]
+hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)      # (a kernel-name line comes first)
+h = rows[hi]; data = [r for r in rows[hi + 1:] if len(r) == len(h)]
 ia = h.index("Instructions Executed"); isrc = h.index("Source"); iss = h.index("Warp Stall Sampling (All Samples)")
 reasons = [(i, c[6:]) for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
 tots = sum(int(r[iss]) for r in data)
