@@ -281,6 +281,19 @@ class Engine:
                 err.append(e)
                 return 1
 
+        # every rank must enter the loop with the same problem, or the all-reduce inside it never completes: agree on the
+        # sizes first, so that an inconsistent call fails on ALL ranks here instead of hanging some of them
+        local_ok = int(d_local.dim() == 2 and d_local.shape[1] == self.info["d_dim"] and theta.dim() == 2 and
+                       theta.shape[1] == self.info["p_dim"] and (w is None or w.numel() == n_t) and nz > 0)
+        on = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        mine = torch.tensor([float(n_d_total), float(n_t), float(nz), float(local_ok)], dtype=torch.float64, device=on)
+        lo_, hi_, tot = mine.clone(), mine.clone(), torch.tensor([float(n_d)], dtype=torch.float64, device=on)
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(tot, group=group)
+        if not torch.equal(lo_, hi_) or lo_[3].item() != 1.0 or int(tot.item()) != int(n_d_total):
+            raise ValueError(f"inconsistent distributed solve: (n_d_total, n_t, nz, ok) ranges {lo_.tolist()} .. {hi_.tolist()}, "
+                             f"rows of all ranks {int(tot.item())}")
         cb = ALLREDUCE_FN(reduce)
         torch.cuda.synchronize(self.device)
         rc = self._lib.pydsb_recourse_solve_global_dist(self._h, ptr(d_local), n_d, int(n_d_total), ptr(theta), ptr(w), n_t,
