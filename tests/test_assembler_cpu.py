@@ -175,12 +175,30 @@ def _run_chain_program(lm, par, monkeypatch, compact):
     return [ld(o, False) for o in cd["g_off"]], info["units"]
 
 
-@pytest.mark.parametrize("variant", ["design4", "design6", "twostage"])
+def _three_block_chain():
+    """An unregistered chain: three blocks, a bimolecular term, a quadrature without narrow factor, a control-only one,
+    per-element controls with initial values (tests/test_gpu_chain.py runs the same model on the GPU)."""
+    m = DaeModel(["a"], ["k1", "k2"], nfe=6)
+    a, k1, k2 = m.d["a"], m.p["k1"], m.p["k2"]
+    cA, cB, cC = m.state("cA", 1.0 + a), m.state("cB", 0.1), m.state("cC", 0.0)
+    q1, q2 = m.state("q1", 0.0), m.state("q2", 0.5)
+    F = m.control("F", 0.0, 1.0, init=[0.1, 0.3, 0.0, 0.2, 0.5, 0.4])
+    m.ode(cA, F - k1 * cA ** 2)
+    m.ode(cB, k1 * cA ** 2 - k2 * cA * cB)
+    m.ode(cC, 0.7 * cB - (0.2 + a) * cC)
+    m.ode(q1, cC * cC)
+    m.ode(q2, F)
+    m.constraint("c1", m.end(cC) - 0.4, 10.0)
+    m.constraint("c2", m.end(q1) + m.end(q2) - m.end(cB) - 0.55, 10.0)
+    return m
+
+
+@pytest.mark.parametrize("variant", ["design4", "design6", "twostage", "three-block"])
 def test_unit_compaction_preserves_the_dataflow(variant, monkeypatch):
     """The liveness-based renumbering of a chain program's units (assembler.h, compact_units) must not change what the
     program computes: same g from the renumbered and the original program, fewer units, nothing read after its unit was
     given to another value (such a read would see the other value or the poison the scratch is filled with)."""
-    lm = models.kinetics(variant).lower()
+    lm = (_three_block_chain() if variant == "three-block" else models.kinetics(variant)).lower()
     rng = np.random.default_rng(7)
     n_par = len(lm.tapes.layout.param_slots)
     par = list(rng.uniform(0.5, 2.0, n_par))
