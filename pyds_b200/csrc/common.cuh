@@ -136,12 +136,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 // has the fixed, well-conditioned collocation part on every diagonal block; a vanishing pivot
 // produces inf/nan which the caller reports as a failed scenario.
 // ---------------------------------------------------------------------------------------------
-template <int N>
+// STEP: the factors serve ONE Newton step (inexact Newton: the residual is exact, so the fixed point and the stop test do
+// not change) -- the pivot reciprocals then carry one correction of the 20-bit seed (relative error 2^-40) instead of two.
+template <int N, bool STEP = false>
 __device__ __forceinline__ void lu_factor(double (&M)[N][N], double (&inv)[N])
 {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        inv[k] = fast_rcp(M[k][k]);
+        inv[k] = STEP ? step_rcp(M[k][k]) : fast_rcp(M[k][k]);
 #pragma unroll
         for (int i = k + 1; i < N; ++i) {
             const double l = M[i][k] * inv[k];
@@ -168,11 +170,11 @@ __device__ __forceinline__ void lu_apply(const double (&M)[N][N], const double (
     }
 }
 
-template <int N>
+template <int N, bool STEP = false>
 __device__ __forceinline__ void lu_solve_inplace(double (&M)[N][N], double (&r)[N])
 {
     double inv[N];
-    lu_factor<N>(M, inv);
+    lu_factor<N, STEP>(M, inv);
     lu_apply<N>(M, inv, r);
 }
 

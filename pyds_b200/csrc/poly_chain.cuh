@@ -328,6 +328,9 @@ __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restric
 #pragma unroll
                 for (int j = 0; j < 3; ++j) dg[s][j] = hc1[s][j] - CH_A(j, j);
             }
+            double lim_step[SPT];                                     // |dx|^2 below which 2^-16 |dx| is inside the tolerance
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) lim_step[s] = PYDSB_STEP_RCP == 2 ? lim[s] * 0x1p32 : DBL_MAX;
             for (int it = 0;;) {
                 bool all = true;
 #pragma unroll
@@ -348,15 +351,21 @@ __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restric
                         r[jj] = rr;
                         N[jj][jj] = fma(hc2[s], x, t);                   // h (2 c2 x + c1) - A_jj
                     }
-                    lu_solve_inplace<3>(N, r);
+                    // a Newton step may be inexact (pivot reciprocals: the bare 20-bit seed -- three dependent FMAs less per
+                    // pivot in the one serial chain of the iteration); a linear block is solved by this one step: exact pivots
+                    if (linear) lu_solve_inplace<3, false>(N, r);
+                    else lu_solve_inplace<3, true>(N, r);
                     double sq = 0.0;
 #pragma unroll
                     for (int kk = 0; kk < 3; ++kk) {
                         X[b][s][kk] -= r[kk];
                         sq = fma(r[kk], r[kk], sq);
                     }
+                    // stop: the step is below the tolerance, or the NEXT one will be -- by the quadratic prediction
+                    // |dx|^2 / |dx_prev| and by what the inexact pivots leave behind, 2^-16 |dx| (seed error x conditioning)
                     const bool ok = linear ? (sq <= DBL_MAX)
-                                           : ((sq <= lim[s]) | ((sq * sq <= lim[s] * s_prev[s]) & (sq <= 0.01 * s_prev[s])));
+                                           : ((sq <= lim[s]) | ((sq * sq <= lim[s] * s_prev[s]) & (sq <= 0.01 * s_prev[s]) &
+                                                                (sq <= lim_step[s])));
                     s_prev[s] = sq;
                     conv[s] = conv[s] | ok;
                     all = all & conv[s];

@@ -321,6 +321,7 @@ __device__ __forceinline__ void rsens_body(const ExecImage& img, const RecourseA
             }
             const bool linear = kind == CHAIN_LINEAR;
             const double lim = fma(img.rtol2 * 3.0, xs * xs, img.rtol2);
+            const double lim_step = PYDSB_STEP_RCP == 2 ? lim * 0x1p32 : DBL_MAX;
             X[b][0] = X[b][1] = xs;
             bool conv = !active;
             double s_prev = 0.0;
@@ -339,13 +340,15 @@ __device__ __forceinline__ void rsens_body(const ExecImage& img, const RecourseA
                     r[jj] = rr;
                     N[jj][jj] = fma(hc2, x, tt);
                 }
-                lu_solve_inplace<3>(N, r);
+                // inexact Newton step / exact single step of a linear block, and the stop test, as in poly_chain.cuh
+                if (linear) lu_solve_inplace<3, false>(N, r);
+                else lu_solve_inplace<3, true>(N, r);
                 double sq = 0.0;
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk) { X[b][kk] -= r[kk]; sq = fma(r[kk], r[kk], sq); }
                 if (!conv) ++my_iters;
                 const bool bad = !(sq <= DBL_MAX);
-                const bool ok = linear ? true : ((sq <= lim) | ((sq * sq <= lim * s_prev) & (sq <= 0.01 * s_prev)));
+                const bool ok = linear ? true : ((sq <= lim) | ((sq * sq <= lim * s_prev) & (sq <= 0.01 * s_prev) & (sq <= lim_step)));
                 s_prev = sq;
                 if (bad && active) failed = true;
                 conv = conv | ok | bad;

@@ -71,4 +71,25 @@ __device__ __forceinline__ double fast_rcp(double x)
     return fma(y, e2, y);
 }
 
+// Pivot reciprocal of a Newton STEP (lu_factor<N, true>): the bare MUFU seed, relative error 2^-20.  The residual of the
+// step is exact, so the fixed point does not move; the step is off by ~2^-20 x conditioning of itself, which the caller's
+// stop test accounts for (poly_chain.cuh).  PYDSB_STEP_RCP = 1: seed + one correction (2^-40), 0: fast_rcp (A/B builds).
+#ifndef PYDSB_STEP_RCP
+#define PYDSB_STEP_RCP 2
+#endif
+__device__ __forceinline__ double step_rcp(double x)
+{
+#if PYDSB_STEP_RCP == 0
+    return fast_rcp(x);
+#else
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if PYDSB_STEP_RCP == 1
+    return fma(y, fma(-x, y, 1.0), y);
+#else
+    return y;
+#endif
+#endif
+}
+
 }  // namespace pydsb
