@@ -215,8 +215,10 @@ __device__ __forceinline__ void recourse_emit(const RecourseArgs& ra, const int 
                 if (row) flush();
                 // value v of the stage: Phi_mu, Phi, grad (8), H packed (36); rows [0, HALF) of the scratch, twice
                 auto value = [&](int v) -> double {                 // (v is a compile-time constant after unrolling)
-                    return v == 0 ? wv * phi : (v == 1 ? wv * raw : (v < 2 + NZS ? wv * V[v - 2 < NZS ? (v >= 2 ? v - 2 : 0) : 0]
-                                                                                 : Hh[v - 2 - NZS >= 0 ? v - 2 - NZS : 0]));
+                    if (v == 0) return wv * phi;
+                    if (v == 1) return wv * raw;
+                    if (v < 2 + NZS) return wv * V[v - 2];
+                    return Hh[v - 2 - NZS];
                 };
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
