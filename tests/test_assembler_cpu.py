@@ -208,6 +208,22 @@ def test_unit_compaction_preserves_the_dataflow(variant, monkeypatch):
     assert u1 < u0 and u1 <= 20                      # 4 CTAs of 128 threads x 2 scenarios per SM need <= 25 units
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_unit_compaction_on_random_chains(seed, monkeypatch):
+    """The same check over randomly drawn chain-shaped models (tests/random_chains.py): every combination of term kinds,
+    free and fixed controls, 1-3 blocks, 0-2 quadratures."""
+    from random_chains import random_chain_model
+    m, nb = random_chain_model(seed)
+    lm = m.lower()
+    if capi.assemble(lm.blob)[1]["chain_blocks"] == 0:
+        pytest.skip("not chain shaped (more than one term in a coefficient)")
+    rng = np.random.default_rng(seed)
+    par = list(rng.uniform(0.5, 2.0, len(lm.tapes.layout.param_slots)))
+    g1, u1 = _run_chain_program(lm, par, monkeypatch, compact=True)
+    g0, u0 = _run_chain_program(lm, par, monkeypatch, compact=False)
+    assert all(v == v for v in g0) and g1 == g0 and u1 <= u0
+
+
 def test_fused_chain_per_element_controls():
     """twostage: F_in differs between the elements, so no LDCTRL / elem ops remain -- the chain multiplies the narrow
     factor by the element's control itself (c0 of cA = t_f * F_in, u integrand = F_in / t_f)."""

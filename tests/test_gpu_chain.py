@@ -117,6 +117,32 @@ def test_unregistered_three_block_chain_against_the_tape_interpreter():
     assert np.all(np.abs(g - g0) <= 1e-12 * np.maximum(np.abs(g0), 1.0))
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_chains_against_the_tape_interpreter(seed):
+    """Randomly drawn chain-shaped models (tests/random_chains.py: every combination of term kinds, free and fixed
+    controls, 1-3 blocks, 0-2 quadratures; generic instantiation, renumbered units, inexact Newton steps) against the numpy
+    interpreter of the same blob, and against the interpreted element loop."""
+    from random_chains import random_chain_model, random_inputs
+    m, nb = random_chain_model(seed)
+    lm = m.lower()
+    info = capi.assemble(lm.blob)[1]
+    eng = capi.Engine(lm.blob, 0)
+    vm = tape_vm.TapeVM(lm.blob)
+    d, p = random_inputs(seed, 9, 301)                   # ragged against the 256-row tile
+    rng = np.random.default_rng(seed)
+    zs = [None] + ([rng.uniform(0, 1, (9, lm.nz))] if lm.nz and not all(lm.z_fixed) else [])
+    for z in zs:
+        g, ind, P = eng.eval_host(d, p, None, z=z, want_g=True, want_ind=True)
+        r = vm.evaluate(d, p, z=z, tol=1e-13)
+        assert np.all(np.abs(g - r["g"]) <= 1e-10 * np.maximum(np.abs(r["g"]), 1.0))
+        near = np.any(np.abs(r["g"]) < 1e-8, axis=-1)
+        assert np.all(((ind == 0.0) == r["feasible"]) | near)
+    assert eng.counters()["failed"] == 0
+    if info["chain_blocks"]:
+        g0 = capi.Engine(random_chain_model(seed, fused_chain=False)[0].lower().blob, 0).eval_host(d, p, None, z=z, want_g=True)[0]
+        assert np.all(np.abs(g - g0) <= 1e-11 * np.maximum(np.abs(g0), 1.0))
+
+
 def test_registered_shape_instantiation_equals_the_generic_one(monkeypatch):
     rng = np.random.default_rng(113)
     d, p = _d4(rng, 11), K.theta_samples(520)
