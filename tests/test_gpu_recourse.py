@@ -328,3 +328,28 @@ def test_chain_sensitivities_against_the_tape_interpreter(setup):
         zp[c] += eps; zm[c] -= eps
         fd = (eng.eval_host(d, p, None, z=zp, want_g=True)[0] - eng.eval_host(d, p, None, z=zm, want_g=True)[0]) / (2 * eps)
         np.testing.assert_allclose(fd, r["dg"][..., c], rtol=2e-5, atol=1e-6 * np.abs(r["dg"]).max())
+
+
+@pytest.mark.parametrize("seed", [0, 1, 4, 6, 7, 9, 11, 13, 14, 15, 16, 22, 24, 26, 35, 37])      # the draws with a free control
+def test_random_chain_models_optimise_like_the_oracle(seed):
+    """Randomly drawn chain-shaped models with a free piecewise-constant control (tests/random_chains.py): the chain
+    evaluator with sensitivities in registers (rsens_kernel, generic instantiation) and the fused single-launch loop against
+    the numpy restatement of the optimiser, shared controls and per-scenario controls."""
+    from random_chains import random_chain_model, random_inputs
+    m, nb = random_chain_model(seed)
+    lm = m.lower()
+    if all(lm.z_fixed):
+        pytest.skip("the drawn control is fixed: nothing to optimise")
+    eng = capi.Engine(lm.blob, 0)
+    vm = tape_vm.TapeVM(lm.blob, program=1)
+    d, p = random_inputs(seed, 4, 24)
+    w = np.full(len(p), 1.0 / len(p))
+    ref = RC.shared_control_problem(vm, d, p, w)
+    out = eng.recourse_solve(d, p, w)
+    np.testing.assert_allclose(out["phi"], ref["phi_raw"], rtol=1e-6, atol=1e-9)
+    ref_ps = RC.per_scenario_problem(vm, d[:2], p[:6])
+    out_ps = eng.recourse_solve(d[:2], p[:6], per_scenario=True)
+    np.testing.assert_allclose(out_ps["phi"], ref_ps["phi_raw"], rtol=1e-6, atol=1e-9)
+    # the evaluator in use is the chain one whenever the model has that shape
+    assert eng.info["recourse_chain_blocks"] in (0, nb)
+
