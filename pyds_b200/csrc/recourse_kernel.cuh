@@ -907,6 +907,7 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_sta
     for (int stage = 0;; ++stage) {
         // ---- statistics of this stage: {Phi_mu, Phi, grad} ----
         double F_t = 0.0, raw_t = 0.0, g_t[NZC], pk[NGC];
+        double e0 = 0.0, ek[PRE ? NGC : 1];         // the unnormalised softmax terms of this stage (saturation test below)
 #pragma unroll
         for (int c = 0; c < NZC; ++c) g_t[c] = 0.0;
         const double mu_stage = mu;
@@ -916,11 +917,14 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_sta
 #pragma unroll
                 for (int k = 0; k < NGC; ++k) pk[k] = 0.0;
             } else {
-                double Z = exp(-cmax / mu_stage);
+                e0 = exp(-cmax / mu_stage);
+                double Z = e0;
 #pragma unroll
                 for (int k = 0; k < NGC; ++k) {
-                    pk[k] = k < ng ? exp((ck[k] - cmax) / mu_stage) : 0.0;
+                    // (the largest c_k, when positive, is cmax itself: exp(0) needs no call)
+                    pk[k] = k < ng ? (ck[k] == cmax ? 1.0 : exp((ck[k] - cmax) / mu_stage)) : 0.0;
                     if (k < ng) Z += pk[k];
+                    if constexpr (PRE) ek[k] = pk[k];
                 }
                 const double zi = 1.0 / Z;
 #pragma unroll
@@ -1102,10 +1106,14 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_sta
                     for (int k = 0; k < NGC; ++k)
                         if (k < ng && ck[k] > cm) { cm = ck[k]; kmax = k; }
                     if (kmax >= 0) {
-                        double rest = exp(-cm / mu);
+                        // cm = cmax and mu = this stage's: the terms are the ones the statistics were formed from
+                        double rest = PRE ? e0 : exp(-cm / mu);
 #pragma unroll
                         for (int k = 0; k < NGC; ++k)
-                            if (k < ng && k != kmax) rest += exp((ck[k] - cm) / mu);
+                            if (k < ng && k != kmax) {
+                                if constexpr (PRE) rest += ek[k];
+                                else rest += exp((ck[k] - cm) / mu);
+                            }
                         saturated = rest < 1e-30;
                     }
                 }
