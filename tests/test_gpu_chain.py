@@ -168,3 +168,29 @@ def test_chain_reports_failed_newton_solves():
     assert res[True][2] == res[False][2] > 0
     np.testing.assert_array_equal(res[True][0], res[False][0])
     np.testing.assert_array_equal(res[True][1], res[False][1])
+
+
+def test_handles_of_different_models_alternate():
+    """All handles of a process share the kernels' constant-bank windows (program, chain descriptor): every launch
+    re-loads its own model's program, stream ordered.  Two models -- a registered chain and a generic three-block one --
+    evaluated alternately (feasibility, optimiser, trajectories) must each give what they give alone."""
+    rng = np.random.default_rng(131)
+    d4, p4 = _d4(rng, 5), K.theta_samples(300)
+    d3 = rng.uniform(0.0, 1.0, (5, 1))
+    p3 = np.stack([rng.uniform(0.5, 3.0, 300), rng.uniform(0.2, 2.0, 300)], axis=1)
+    ea = capi.Engine(models.kinetics("design4").lower().blob, 0)
+    eb = capi.Engine(_three_block_model().lower().blob, 0)
+    ec = capi.Engine(models.kinetics("twostage").lower().blob, 0)
+    d2 = np.stack([rng.uniform(250, 350, 4), rng.uniform(250, 300, 4)], axis=1)
+    ga = ea.eval_host(d4, p4, None, want_g=True)[0]
+    gb = eb.eval_host(d3, p3, None, want_g=True)[0]
+    rc = ec.recourse_solve(d2, p4[:50], np.full(50, 0.02))
+    xa = ea.state_solve(d4[:2], p4[:40])[0]
+    for _ in range(3):
+        gb2 = eb.eval_host(d3, p3, None, want_g=True)[0]
+        rc2 = ec.recourse_solve(d2, p4[:50], np.full(50, 0.02))
+        ga2 = ea.eval_host(d4, p4, None, want_g=True)[0]
+        xa2 = ea.state_solve(d4[:2], p4[:40])[0]
+        assert np.array_equal(ga, ga2) and np.array_equal(gb, gb2) and np.array_equal(xa, xa2)
+        assert np.array_equal(rc["z"], rc2["z"]) and np.array_equal(rc["phi"], rc2["phi"])
+
