@@ -503,7 +503,10 @@ __device__ __forceinline__ void rsens_body(const ExecImage& img, const RecourseA
 }
 
 template <int NB, unsigned long long SB = 0ull, unsigned SQ = 0u>
-__global__ void __launch_bounds__(BLOCK, SB ? 3 : 2) rsens_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ RecourseArgs ra)
+#ifndef PYDSB_RSENS_CTAS
+#define PYDSB_RSENS_CTAS 3
+#endif
+__global__ void __launch_bounds__(BLOCK, SB ? PYDSB_RSENS_CTAS : 2) rsens_kernel(const __grid_constant__ ExecImage img, const __grid_constant__ RecourseArgs ra)
 {
     rsens_body<NB, SB, SQ>(img, ra, nullptr);
 }
