@@ -32,6 +32,29 @@ from __future__ import annotations
 import numpy as np
 
 
+class _LazyResult(dict):
+    """``Solver.result`` with entries that are computed when they are first read."""
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        self.lazy = {}
+
+    def __missing__(self, key):
+        if key in self.lazy:
+            self[key] = self.lazy.pop(key)()
+            return self[key]
+        raise KeyError(key)
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self.lazy
+
+
 class Solver:
     def __init__(self, parent, config):
         self.parent = parent
@@ -187,10 +210,15 @@ class Solver:
         out = P.cpu().numpy()
         failed = eng.counters()["failed"]                # one synchronising read (the call above is the only work since the reset)
         if tol > 0.0:
-            # how much of the answer rests on the tolerance: the same pass with the exact rule g <= 0
-            P0 = torch.empty(n_d, dtype=torch.float64, device=dev)
-            eng.eval_device(td, tp, tw, z=tz, z_mode=z_mode, P_out=P0, feas_tol=0.0)
-            self.result["band_weight"] = (P - P0).cpu().numpy()
+            # how much of the answer rests on the tolerance: the same pass with the exact rule g <= 0.  It costs a second
+            # evaluation of the grid, so it runs when the figure is first read (the inputs stay on the device until the
+            # next call replaces ``result``)
+            def band_weight():
+                P0 = torch.empty(n_d, dtype=torch.float64, device=dev)
+                eng.eval_device(td, tp, tw, z=tz, z_mode=z_mode, P_out=P0, feas_tol=0.0)
+                return (P - P0).cpu().numpy()
+            self.result = _LazyResult(self.result)
+            self.result.lazy["band_weight"] = band_weight
             self.result["band"] = tol
         if failed:
             self.no_infeasible += int(failed)

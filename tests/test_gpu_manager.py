@@ -56,6 +56,11 @@ def test_twostage_manager_g_contract_and_classification(tmp_path):
     # DEUS's reduction on the returned list equals the fused fast path
     P_from_g = ns.efp_from_g(g_list, w)
     np.testing.assert_allclose(m.efp(d, p, w), P_from_g, atol=1e-15)
+    # ... and says how much of each probability rests on the tolerance of the relaxed big-M rule (computed when read): the
+    # theta weight of the scenarios with 0 < max_k g_k / M_k <= tol, i.e. the count solve() reported, in units of 1 / n_p
+    bw = m.solver.result["band_weight"]
+    assert "band_weight" in m.solver.result and bw.shape == (12,) and np.all(bw >= 0.0) and np.all(bw <= P_from_g + 1e-15)
+    assert abs(bw.sum() / w[0] - band_ref) <= near.sum() + 1e-9
     # optimising the controls never lowers the probability of feasibility relative to the warm start
     g0 = m.simulator.simulate_all_scenarios(m.model, {0: d, 1: p})
     P0 = ((g0 <= 0).all(-1) * w).sum(1)
