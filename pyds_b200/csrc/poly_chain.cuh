@@ -196,6 +196,13 @@ __device__ __forceinline__ void chain_term(unsigned n_off, unsigned meta, int e,
 }
 
 // NB = blocks the instantiation holds in registers (2 or 3); SB / SQ = the chain's compile-time shape (0: decoded at run time).
+// Copies of the Newton iteration per loop trip: with two, the loop-carried iterates need no register moves at the back
+// edge (measured on C3: 1 -> 16.60 ms, 2 -> 16.26, 3 -> 16.28, 4 -> 16.36).
+#ifndef PYDSB_NEWTON_UNROLL
+#define PYDSB_NEWTON_UNROLL 2
+#endif
+constexpr int NEWTON_UNROLL = PYDSB_NEWTON_UNROLL;
+
 template <int SPT, int NB, unsigned long long SB, unsigned SQ, class CtrlLd>
 __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restrict__ base, const char* __restrict__ cz,
                                            const double h, CtrlLd ctrl_ld, bool (&failed)[SPT],
@@ -331,6 +338,7 @@ __device__ __forceinline__ void poly_chain(const ExecImage& img, char* __restric
             double lim_step[SPT];                                     // |dx|^2 below which 2^-16 |dx| is inside the tolerance
 #pragma unroll
             for (int s = 0; s < SPT; ++s) lim_step[s] = PYDSB_STEP_RCP == 2 ? lim[s] * 0x1p32 : DBL_MAX;
+#pragma unroll NEWTON_UNROLL
             for (int it = 0;;) {
                 bool all = true;
 #pragma unroll

@@ -325,6 +325,7 @@ __device__ __forceinline__ void rsens_body(const ExecImage& img, const RecourseA
             X[b][0] = X[b][1] = xs;
             bool conv = !active;
             double s_prev = 0.0;
+#pragma unroll NEWTON_UNROLL
             for (int it = 0;;) {
                 double N[3][3], r[3];
 #pragma unroll
