@@ -1033,6 +1033,7 @@ __device__ bool lm_update_group_regs(const LmArgs& a, long long g, int* want_sta
                     }
                     const double floor_ = 1e-8 * dmax + 1e-300;
                     double l = lam;
+#pragma unroll 1                                             /* (the retries are rare: one copy of the factorisation) */
                     for (int attempt = 0; attempt < 12; ++attempt) {
                         double A[NZC][NZC];                // lower triangle used
 #pragma unroll
