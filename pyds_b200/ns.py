@@ -267,7 +267,8 @@ class DEUS:
         iter_times, eval_times, it = [], [], 0
         vol_ball = math.pi ** (dim / 2.0) / math.gamma(dim / 2.0 + 1.0)
         while it < self.max_iterations:
-            inside = float((live_p >= self.target).double().mean())
+            # (scalars the host needs leave the device in as few transfers as possible: each one is a synchronisation)
+            inside, worst = torch.stack([(live_p >= self.target).double().mean(), live_p.min()]).tolist()
             if inside >= self.inside_fraction:
                 break
             sync(); t0 = time.time()
@@ -275,7 +276,6 @@ class DEUS:
             def mark(name):
                 if trace is not None:
                     sync(); trace.append((name, time.time()))
-            worst = float(live_p.min())
             for lv, nl, nr in self.schedule:
                 if worst >= lv:
                     level, n_live, n_rep = lv, nl, nr
@@ -285,17 +285,22 @@ class DEUS:
             mu = u.mean(dim=0)
             xc = u - mu
             n_pts = u.shape[0]
-            # the dim x dim factor goes through the host (a few dozen doubles): no dense-solver library on the device path
-            cov_h = ((xc.T @ xc) / (n_pts - 1)).cpu().numpy() + 1e-12 * np.eye(dim) if n_pts > dim else 0.25 * np.eye(dim)
+            # the dim x dim factor goes through the host (a few dozen doubles, with the mean in the same transfer): no
+            # dense-solver library on the device path
+            mc = torch.cat([mu, ((xc.T @ xc) / max(n_pts - 1, 1)).reshape(-1)]).cpu().numpy()
+            mu_h = mc[:dim]
+            cov_h = mc[dim:].reshape(dim, dim) + 1e-12 * np.eye(dim) if n_pts > dim else 0.25 * np.eye(dim)
             L_h = np.linalg.cholesky(cov_h)
             L, Linv = torch.tensor(L_h, **f64), torch.tensor(np.linalg.inv(L_h), **f64)
             y = Linv @ xc.T
             r = float((y * y).sum(dim=0).max().sqrt()) * (1.0 + enlarge)
             mark("ellipsoid")
-            ext = r * (L * L).sum(dim=1).sqrt()
-            blo, bhi = torch.clamp(mu - ext, min=0.0), torch.clamp(mu + ext, max=1.0)
-            vol_box = float(torch.clamp(bhi - blo, min=0.0).prod())
-            vol_ell = vol_ball * r ** dim * float(torch.diagonal(L).prod())
+            # bounding box of the ellipsoid and the two volumes: on the host, from the factor that is there already
+            ext_h = r * np.sqrt((L_h * L_h).sum(axis=1))
+            blo_h, bhi_h = np.maximum(mu_h - ext_h, 0.0), np.minimum(mu_h + ext_h, 1.0)
+            blo, bhi = torch.tensor(blo_h, **f64), torch.tensor(bhi_h, **f64)
+            vol_box = float(np.prod(np.maximum(bhi_h - blo_h, 0.0)))
+            vol_ell = vol_ball * r ** dim * float(np.prod(np.diagonal(L_h)))
             # ---- proposals ----
             m = max(int(4 * n_rep) + 64, 4096)
             from_box, chunks, have, first = False, [], 0, True
